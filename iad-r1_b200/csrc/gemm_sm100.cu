@@ -1,0 +1,555 @@
+// The tcgen05 GEMM family for sm_100a:  C[z] (+)= alpha * A[z] * B[z]^T  with bf16 operands, fp32 TMEM accumulators.
+//
+// One persistent, warp-specialised kernel covers every dense matmul on the SC-GRPO hot path
+// (K1 patch-embed, K4/K12 QKV + proj, K7/K14 MLP, K8 merger, K15 lm_head, K17 their dgrad/wgrad,
+// K19 the decode "skinny" products via operand swap) and the batched QK^T / PV products of attention:
+//   warp 0   : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
+//   warp 1   : MMA issuer     (one elected lane issues tcgen05.mma, UMMA 128 x block_n x 16, commit -> mbarrier)
+//   warp 2   : TMEM allocator (512 columns = two accumulator stages so tile i+1's MMAs overlap tile i's epilogue)
+//   warps 4-7: epilogue       (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
+// Both operands may be K-major (reduction dim contiguous: activations x[M,K], torch Linear weights W[N,K]) or
+// MN-major (free dim contiguous: W[N,K] read as B^T for dgrad, dY / X read transposed for wgrad, V for P*V), which
+// is what lets forward, dgrad and wgrad all run from the same row-major buffers without a transpose pass.
+//
+// The reference reaches these products through cuBLAS via torch (`model(**inputs).logits`,
+// ref: train/stage_rl/trainer/sc_grpo_trainer.py:505); there is no reference native code to follow.
+#include "gemm_sm100.cuh"
+#include "ptx.cuh"
+#include "runtime.h"
+
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <cstring>
+#include <cstdio>
+
+namespace iadr1 {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;
+static constexpr int kThreads = 256;
+static constexpr int kMaxStages = 12;
+static constexpr int kAccStride = 256;  // TMEM columns per accumulator stage
+
+struct TileInfo {
+  int z, m0, n0, n_blk, kb_begin, kb_end;
+  bool skip;
+};
+
+__device__ __forceinline__ TileInfo decode_tile(const GemmArgs& g, int t, int tiles_m, int tiles_n) {
+  TileInfo ti;
+  const int mn = tiles_m * tiles_n;
+  const int per_z = mn * g.split_k;
+  ti.z = t / per_z;
+  int r = t - ti.z * per_z;
+  const int split = r / mn;
+  r -= split * mn;
+  ti.n_blk = r / tiles_m;
+  const int m_blk = r - ti.n_blk * tiles_m;
+  ti.m0 = m_blk * BM;
+  ti.n0 = ti.n_blk * g.block_n;
+  int k_lo = 0, k_hi = g.K;
+  if (g.kmode == 1) {
+    k_hi = min(g.K, max(0, ti.m0 + BM + g.causal_off));
+  } else if (g.kmode == 2) {
+    k_lo = min(g.K, max(0, ti.m0 - g.causal_off));
+  }
+  const int kb_lo = k_lo / BK;
+  const int kb_hi = (k_hi + BK - 1) / BK;
+  const int nkb = max(0, kb_hi - kb_lo);
+  const int per = (nkb + g.split_k - 1) / g.split_k;
+  ti.kb_begin = kb_lo + split * per;
+  ti.kb_end = min(kb_lo + nkb, ti.kb_begin + per);
+  if (ti.kb_end < ti.kb_begin) ti.kb_end = ti.kb_begin;
+  ti.skip = g.skip_mode && (ti.n0 > ti.m0 + BM - 1 + g.causal_off);
+  return ti;
+}
+
+template <int W>
+__device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const TileInfo& ti, const uint32_t (&v)[W], int m,
+                                               int nb, bool have_acc, bool vec_ok, float& run_max, float& run_sum,
+                                               float& tgt, bool& tgt_found, int label, float row_lse,
+                                               float row_g) {
+  float acc[W];
+#pragma unroll
+  for (int j = 0; j < W; ++j) acc[j] = have_acc ? g.alpha * __uint_as_float(v[j]) : 0.f;
+  const int nvalid = min(W, g.N - nb);
+  if (nvalid <= 0 || m >= g.M) return;
+
+  if (g.epi == EPI_LSE) {
+    float cmax = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < W; ++j)
+      if (j < nvalid) cmax = fmaxf(cmax, acc[j]);
+    const float nmax = fmaxf(run_max, cmax);
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < W; ++j)
+      if (j < nvalid) s += __expf(acc[j] - nmax);
+    run_sum = run_sum * __expf(run_max - nmax) + s;
+    run_max = nmax;
+    if (label >= nb && label < nb + nvalid) {
+#pragma unroll
+      for (int j = 0; j < W; ++j)
+        if (nb + j == label) tgt = acc[j];
+      tgt_found = true;
+    }
+    return;
+  }
+  if (g.epi == EPI_DLOGITS) {
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      const float p = __expf(acc[j] - row_lse);
+      acc[j] = (p - ((nb + j) == label ? 1.f : 0.f)) * row_g;
+    }
+  }
+
+  const long long zoff = (long long)(ti.z % g.batch_lo) * g.c_bs_lo + (long long)(ti.z / g.batch_lo) * g.c_bs_hi;
+  if (g.bias != nullptr) {
+    if (g.bias_per_m) {
+      const float b = __bfloat162float(g.bias[m]);
+#pragma unroll
+      for (int j = 0; j < W; ++j) acc[j] += b;
+    } else {
+#pragma unroll
+      for (int j = 0; j < W; ++j)
+        if (j < nvalid) acc[j] += __bfloat162float(g.bias[nb + j]);
+    }
+  }
+  if (g.trans_c) {
+    // C^T[n][m]: lanes of a warp hold consecutive m, so each j is one coalesced row segment.
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      if (j < nvalid) {
+        const long long idx = zoff + (long long)(nb + j) * g.ldc + m;
+        float x = acc[j];
+        if (g.residual) x += __bfloat162float(g.residual[idx]);
+        if (g.atomic) {
+          atomicAdd(reinterpret_cast<float*>(g.C) + idx, x);
+        } else if (g.c_f32) {
+          float* p = reinterpret_cast<float*>(g.C) + idx;
+          *p = g.accumulate ? (*p + x) : x;
+        } else {
+          reinterpret_cast<__nv_bfloat16*>(g.C)[idx] = __float2bfloat16(x);
+        }
+      }
+    }
+    return;
+  }
+  const long long idx0 = zoff + (long long)m * g.ldc + nb;
+  if (g.residual) {
+    if (vec_ok && nvalid == W) {
+      const uint4* rp = reinterpret_cast<const uint4*>(g.residual + idx0);
+#pragma unroll
+      for (int q = 0; q < W / 8; ++q) {
+        const uint4 r = rp[q];
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __bfloat1622float2(h[e]);
+          acc[q * 8 + 2 * e] += f.x;
+          acc[q * 8 + 2 * e + 1] += f.y;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < W; ++j)
+        if (j < nvalid) acc[j] += __bfloat162float(g.residual[idx0 + j]);
+    }
+  }
+  if (g.atomic) {
+    float* p = reinterpret_cast<float*>(g.C) + idx0;
+#pragma unroll
+    for (int j = 0; j < W; ++j)
+      if (j < nvalid) atomicAdd(p + j, acc[j]);
+  } else if (g.c_f32) {
+    float* p = reinterpret_cast<float*>(g.C) + idx0;
+    if (vec_ok && nvalid == W) {
+      float4* p4 = reinterpret_cast<float4*>(p);
+#pragma unroll
+      for (int q = 0; q < W / 4; ++q) {
+        float4 o = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+        if (g.accumulate) {
+          const float4 c = p4[q];
+          o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
+        }
+        p4[q] = o;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < W; ++j)
+        if (j < nvalid) p[j] = g.accumulate ? (p[j] + acc[j]) : acc[j];
+    }
+  } else {
+    __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(g.C) + idx0;
+    if (vec_ok && nvalid == W) {
+      uint4* p4 = reinterpret_cast<uint4*>(p);
+#pragma unroll
+      for (int q = 0; q < W / 8; ++q) {
+        uint4 o;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(acc[q * 8 + 2 * e], acc[q * 8 + 2 * e + 1]);
+        p4[q] = o;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < W; ++j)
+        if (j < nvalid) p[j] = __float2bfloat16(acc[j]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const GemmArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int a_bytes = BM * BK * 2;                 // 16 KiB
+  const int b_bytes = g.block_n * BK * 2;          // block_n * 128 B
+  const int stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)g.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tfull_bar = empty_bar + kMaxStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int tiles_m = (g.M + BM - 1) / BM;
+  const int tiles_n = (g.N + g.block_n - 1) / g.block_n;
+  const int total_tiles = tiles_m * tiles_n * g.split_k * g.batch;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < g.stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t tx_bytes = a_bytes + b_bytes;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const TileInfo ti = decode_tile(g, t, tiles_m, tiles_n);
+        if (ti.skip) continue;
+        const int zlo = ti.z % g.batch_lo, zhi = ti.z / g.batch_lo;
+        const int zlo_b = zlo / g.b_lo_div;
+        for (int kb = ti.kb_begin; kb < ti.kb_end; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + (size_t)s * stage_bytes;
+          uint8_t* sb = sa + a_bytes;
+          mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+          if (!g.a_mn) {
+            tma_load_4d(sa, &tmA, &full_bar[s], kb * BK, ti.m0, zlo, zhi);
+          } else {
+            tma_load_4d(sa, &tmA, &full_bar[s], ti.m0, kb * BK, zlo, zhi);
+            tma_load_4d(sa + 8192, &tmA, &full_bar[s], ti.m0 + 64, kb * BK, zlo, zhi);
+          }
+          if (!g.b_mn) {
+            tma_load_4d(sb, &tmB, &full_bar[s], kb * BK, ti.n0, zlo_b, zhi);
+          } else {
+            for (int j = 0; j < g.block_n / 64; ++j)
+              tma_load_4d(sb + j * 8192, &tmB, &full_bar[s], ti.n0 + 64 * j, kb * BK, zlo_b, zhi);
+          }
+          if (++s == g.stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(BM, g.block_n, g.a_mn, g.b_mn);
+      // K-major SW128: 8-row groups 1024 B apart (SBO), LBO unused. MN-major SW128: 64-wide MN chunks 8192 B apart
+      // (LBO = BK rows * 128 B), 8-row K groups 1024 B apart (SBO).
+      const uint32_t a_lbo = g.a_mn ? 8192u : 16u, b_lbo = g.b_mn ? 8192u : 16u;
+      const uint32_t a_kstep = g.a_mn ? (2048u >> 4) : (32u >> 4);
+      const uint32_t b_kstep = g.b_mn ? (2048u >> 4) : (32u >> 4);
+      int s = 0;
+      uint32_t ph = 0;
+      int as = 0;
+      uint32_t aph = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const TileInfo ti = decode_tile(g, t, tiles_m, tiles_n);
+        if (ti.skip) continue;
+        mbar_wait(&tempty_bar[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * kAccStride;
+        for (int kb = ti.kb_begin; kb < ti.kb_end; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t sb = sa + a_bytes;
+          const uint64_t adesc = make_smem_desc_sw128(sa, a_lbo, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(sb, b_lbo, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            umma_bf16(d_tmem, adesc + (uint64_t)(k * a_kstep), bdesc + (uint64_t)(k * b_kstep), idesc,
+                      (kb > ti.kb_begin || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+          if (++s == g.stages) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&tfull_bar[as]);
+        if (++as == 2) { as = 0; aph ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;
+    const bool vec_ok = ((g.ldc & 7) == 0) && ((g.c_bs_lo & 7) == 0) && ((g.c_bs_hi & 7) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) &&
+                        (g.residual == nullptr || (reinterpret_cast<uintptr_t>(g.residual) & 15) == 0);
+    int as = 0;
+    uint32_t aph = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const TileInfo ti = decode_tile(g, t, tiles_m, tiles_n);
+      if (ti.skip) continue;
+      const bool have_acc = ti.kb_end > ti.kb_begin;
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+      const int m = ti.m0 + q * 32 + lane;
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * kAccStride;
+      float run_max = -INFINITY, run_sum = 0.f, tgt = 0.f, row_lse = 0.f, row_g = 0.f;
+      bool tgt_found = false;
+      int label = -1;
+      if (g.epi != EPI_STORE && m < g.M) {
+        label = g.labels[m];
+        if (g.epi == EPI_DLOGITS) {
+          row_lse = g.lse[m];
+          row_g = g.gscale[m];
+        }
+      }
+      int c0 = 0;
+      for (; c0 + 32 <= g.block_n; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + c0, v);
+        tmem_ld_wait();
+        epilogue_chunk<32>(g, ti, v, m, ti.n0 + c0, have_acc, vec_ok, run_max, run_sum, tgt, tgt_found, label,
+                           row_lse, row_g);
+      }
+      if (c0 < g.block_n) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(taddr + c0, v);
+        tmem_ld_wait();
+        epilogue_chunk<16>(g, ti, v, m, ti.n0 + c0, have_acc, vec_ok, run_max, run_sum, tgt, tgt_found, label,
+                           row_lse, row_g);
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[as]);
+      if (g.epi == EPI_LSE && m < g.M) {
+        g.part_max[(long long)m * tiles_n + ti.n_blk] = run_max;
+        g.part_sum[(long long)m * tiles_n + ti.n_blk] = run_sum;
+        if (tgt_found) g.tgt_logit[m] = tgt;
+      }
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side: tensor-map cache + launch heuristics
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  long long d0, d1, d2, d3, s1, s2, s3;
+  int b0, b1;
+  bool operator<(const MapKey& o) const {
+    return std::tie(ptr, d0, d1, d2, d3, s1, s2, s3, b0, b1) <
+           std::tie(o.ptr, o.d0, o.d1, o.d2, o.d3, o.s1, o.s2, o.s3, o.b0, o.b1);
+  }
+};
+
+static int make_map(CUtensorMap* out, const void* ptr, long long d0, long long d1, long long d2, long long d3,
+                    long long s1, long long s2, long long s3, int b0, int b1) {
+  static std::map<MapKey, CUtensorMap> cache;
+  static std::mutex mu;
+  MapKey key{ptr, d0, d1, d2, d3, s1, s2, s3, b0, b1};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return 0;
+    }
+  }
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error("cuTensorMapEncodeTiled entry point not found (no CUDA driver?)");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return set_error("gemm operand not 16-byte aligned");
+  if (((s1 * 2) & 15) || ((s2 * 2) & 15) || ((s3 * 2) & 15))
+    return set_error("gemm operand strides must be multiples of 8 elements (ld=%lld bs_lo=%lld bs_hi=%lld)", s1, s2,
+                     s3);
+  cuuint64_t dims[4] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2, (cuuint64_t)d3};
+  cuuint64_t strides[3] = {(cuuint64_t)s1 * 2, (cuuint64_t)s2 * 2, (cuuint64_t)s3 * 2};
+  cuuint32_t box[4] = {(cuuint32_t)b0, (cuuint32_t)b1, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error("cuTensorMapEncodeTiled failed (%d) dims=%lld,%lld,%lld,%lld strides=%lld,%lld,%lld box=%d,%d",
+                     (int)r, d0, d1, d2, d3, s1, s2, s3, b0, b1);
+  std::lock_guard<std::mutex> lk(mu);
+  if (cache.size() > 8192) cache.clear();
+  cache[key] = *out;
+  return 0;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+static int pick_block_n(int N, int b_mn) {
+  if (b_mn) {
+    // MN-major B is staged in 64-column swizzle atoms.
+    if (N <= 64) return 64;
+    if (N <= 128) return 128;
+    if (N <= 192) return 192;
+    return 256;
+  }
+  if (N <= 256) return (N + 15) / 16 * 16;
+  // fewest tiles first, then least padding
+  int best = 256, best_tiles = (N + 255) / 256;
+  for (int bn = 240; bn >= 128; bn -= 16) {
+    int tiles = (N + bn - 1) / bn;
+    if (tiles == best_tiles) best = bn;
+  }
+  return best;
+}
+
+int pick_block_n_public(int N, int b_mn) { return pick_block_n(N, b_mn); }
+
+int launch_gemm(const iadr1_gemm_t& d, cudaStream_t stream) {
+  if (d.M <= 0 || d.N <= 0 || d.batch <= 0) return 0;
+  if (d.K <= 0) return set_error("gemm: K must be positive");
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.M = d.M; g.N = d.N; g.K = d.K;
+  g.batch = d.batch;
+  g.batch_lo = d.batch_lo > 0 ? d.batch_lo : d.batch;
+  g.b_lo_div = d.b_lo_div > 0 ? d.b_lo_div : 1;
+  g.a_mn = d.a_mn; g.b_mn = d.b_mn;
+  g.kmode = d.kmode; g.skip_mode = d.skip_mode; g.causal_off = d.causal_off;
+  g.split_k = d.split_k > 0 ? d.split_k : 1;
+  g.epi = d.epi;
+  g.c_f32 = d.c_f32; g.trans_c = d.trans_c; g.accumulate = d.accumulate; g.atomic = d.atomic;
+  g.bias_per_m = d.bias_per_m;
+  g.alpha = d.alpha;
+  g.C = d.C; g.ldc = d.ldc; g.c_bs_lo = d.c_bs_lo; g.c_bs_hi = d.c_bs_hi;
+  g.bias = reinterpret_cast<const __nv_bfloat16*>(d.bias);
+  g.residual = reinterpret_cast<const __nv_bfloat16*>(d.residual);
+  g.labels = d.labels; g.part_max = d.part_max; g.part_sum = d.part_sum; g.tgt_logit = d.tgt_logit;
+  g.lse = d.lse; g.gscale = d.gscale;
+  if (g.split_k > 1 && !(g.atomic && g.c_f32)) return set_error("gemm: split_k > 1 needs atomic f32 output");
+  if (g.atomic && !g.c_f32) return set_error("gemm: atomic output must be f32");
+  if (g.batch % g.batch_lo) return set_error("gemm: batch must be a multiple of batch_lo");
+  g.block_n = d.block_n > 0 ? d.block_n : pick_block_n(d.N, d.b_mn);
+  if (g.block_n % 16 || g.block_n > 256 || g.block_n < 16) return set_error("gemm: bad block_n %d", g.block_n);
+  if (g.b_mn && (g.block_n % 64)) return set_error("gemm: MN-major B needs block_n %% 64 == 0");
+  if (g.epi == EPI_LSE && d.lse_tiles_n != (d.N + g.block_n - 1) / g.block_n)
+    return set_error("gemm: lse partial buffer sized for %d tiles, kernel uses %d", d.lse_tiles_n,
+                     (d.N + g.block_n - 1) / g.block_n);
+
+  const int a_bytes = BM * BK * 2;
+  const int b_bytes = g.block_n * BK * 2;
+  const int stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023);
+  const int smem_budget = 227 * 1024 - 1024 - 512;
+  int stages = smem_budget / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (d.stages > 0 && d.stages < stages) stages = d.stages;
+  if (stages < 2) return set_error("gemm: not enough shared memory for 2 stages");
+  g.stages = stages;
+  const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + 512;
+
+  const int nb_hi = g.batch / g.batch_lo;
+  const int nb_lo_b = (g.batch_lo + g.b_lo_div - 1) / g.b_lo_div;
+  CUtensorMap tmA, tmB;
+  int rc;
+  // dims: {contiguous, rows, batch_lo, batch_hi}
+  if (!g.a_mn)
+    rc = make_map(&tmA, d.A, d.K, d.M, g.batch_lo, nb_hi, d.lda, d.a_bs_lo ? d.a_bs_lo : d.lda,
+                  d.a_bs_hi ? d.a_bs_hi : d.lda, BK, BM);
+  else
+    rc = make_map(&tmA, d.A, d.M, d.K, g.batch_lo, nb_hi, d.lda, d.a_bs_lo ? d.a_bs_lo : d.lda,
+                  d.a_bs_hi ? d.a_bs_hi : d.lda, 64, BK);
+  if (rc) return rc;
+  if (!g.b_mn)
+    rc = make_map(&tmB, d.B, d.K, d.N, nb_lo_b, nb_hi, d.ldb, d.b_bs_lo ? d.b_bs_lo : d.ldb,
+                  d.b_bs_hi ? d.b_bs_hi : d.ldb, BK, g.block_n);
+  else
+    rc = make_map(&tmB, d.B, d.N, d.K, nb_lo_b, nb_hi, d.ldb, d.b_bs_lo ? d.b_bs_lo : d.ldb,
+                  d.b_bs_hi ? d.b_bs_hi : d.ldb, 64, BK);
+  if (rc) return rc;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         227 * 1024);
+    if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(gemm smem): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int tiles_m = (g.M + BM - 1) / BM;
+  const int tiles_n = (g.N + g.block_n - 1) / g.block_n;
+  const long long total = (long long)tiles_m * tiles_n * g.split_k * g.batch;
+  int grid = (int)(total < (long long)num_sms() ? total : num_sms());
+  if (d.max_ctas > 0 && grid > d.max_ctas) grid = d.max_ctas;
+  gemm_bf16_tcgen05_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, g);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("gemm launch failed: %s", cudaGetErrorString(e));
+  count_launch();
+  return 0;
+}
+
+}  // namespace iadr1

@@ -1,0 +1,43 @@
+// Argument block of the one tcgen05 GEMM kernel family (see gemm_sm100.cu).
+#pragma once
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace iadr1 {
+
+enum GemmEpilogue : int {
+  EPI_STORE = 0,     // C = alpha * acc (+ bias) (+ residual), bf16 or f32, optional f32 accumulate / atomic / transposed
+  EPI_LSE = 1,       // per-row partial (max, sum exp) over this tile's columns + target-logit pick  (fused lm_head)
+  EPI_DLOGITS = 2,   // C = (exp(alpha*acc - lse[m]) - [n == label[m]]) * gscale[m]  as bf16         (lm_head bwd)
+};
+
+struct GemmArgs {
+  int M, N, K;
+  int batch;      // number of independent problems; z -> (z % batch_lo, z / batch_lo)
+  int batch_lo;
+  int b_lo_div;   // B's lo batch coordinate is (z % batch_lo) / b_lo_div (grouped-query sharing)
+  int block_n;    // multiple of 16, <= 256
+  int stages;
+  int a_mn, b_mn; // operand majorness: 0 = K-major (reduction dim contiguous), 1 = MN-major
+  int kmode;      // 0 full K; 1: k < m0 + 128 + causal_off (rows attend to keys <= row + off); 2: k >= m0 - causal_off
+  int skip_mode;  // 1: skip output tiles with n0 > m0 + 127 + causal_off (fully masked)
+  int causal_off;
+  int split_k;    // >= 1; > 1 requires atomic f32 output
+  int epi;
+  int c_f32, trans_c, accumulate, atomic;
+  int bias_per_m;
+  float alpha;
+  void* C;
+  long long ldc, c_bs_lo, c_bs_hi;
+  const __nv_bfloat16* bias;
+  const __nv_bfloat16* residual;  // same indexing as C
+  // EPI_LSE / EPI_DLOGITS
+  const int* labels;     // [M]
+  float* part_max;       // [M, tiles_n]
+  float* part_sum;       // [M, tiles_n]
+  float* tgt_logit;      // [M]
+  const float* lse;      // [M]
+  const float* gscale;   // [M]
+};
+
+}  // namespace iadr1
