@@ -1,0 +1,425 @@
+// Rollout (autoregressive decode) kernels: the in-rank replacement for `self.llm.generate(...)`
+// (ref: train/stage_rl/trainer/sc_grpo_trainer.py:343-358, 667 - a vLLM 0.7.3 engine on a separate GPU).
+//
+// One decode step for R rows in lock-step is a fixed kernel sequence with NO host-visible state: the step counter,
+// prompt length and per-row tokens live in device memory (`DecodeState`), so the whole step is captured once in a
+// CUDA graph and replayed max_completion_length times. Dense products use the tcgen05 GEMM with operands swapped
+// (weights as the 128-row operand, the R activations as the narrow one) and split-K fp32 atomics straight into the
+// fp32 residual stream; this file holds everything between those GEMMs:
+//   embed lookup -> [RMSNorm(f32 in) -> qkv -> rope + KV append -> split-KV attention -> o_proj -> RMSNorm -> MLP] x L
+//   -> RMSNorm -> lm_head -> fused sampler (temperature -> top-k -> top-p -> multinomial, Philox).
+// KV cache: the prompt's K/V are stored ONCE per group ([group][P][kv_head][hd], shared by its G rows - the prefix
+// sharing vLLM gets from `enable_prefix_caching`, sc_grpo_trainer.py:351); each row appends to its own
+// [row][C][kv_head][hd] slab, so decode reads are contiguous per (row, kv_head) stream.
+#include "runtime.h"
+#include <cuda_bf16.h>
+#include <curand_kernel.h>
+#include <stdint.h>
+
+namespace iadr1 {
+
+using bf16 = __nv_bfloat16;
+
+// Device-resident rollout state (int32 words). Host writes it once per rollout.
+enum StateWord : int {
+  ST_STEP = 0,       // index of the completion token fed this step (KV slot); logits predict token ST_STEP + 1
+  ST_PROMPT_LEN = 1, // P
+  ST_UNFINISHED = 2, // rows that have not produced EOS yet (host polls for early exit)
+  ST_WORDS = 8
+};
+
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__float2bfloat16(x)); }
+
+// h[r][:] = float(embed[tok[r]][:])
+__global__ void decode_embed_kernel(const bf16* __restrict__ embed, const int* __restrict__ tok, float* __restrict__ h,
+                                    int H) {
+  const int r = blockIdx.x;
+  const bf16* src = embed + (long long)tok[r] * H;
+  for (int c = threadIdx.x; c < H; c += blockDim.x) h[(long long)r * H + c] = __bfloat162float(src[c]);
+}
+
+// RMSNorm with fp32 input (the decode residual stream) -> bf16, same rounding order as Qwen2RMSNorm.
+__global__ void rmsnorm_f32in_kernel(const float* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y,
+                                     int cols, float eps) {
+  __shared__ float red[32];
+  const long long row = blockIdx.x;
+  const float* xr = x + row * cols;
+  float ss = 0.f;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    const float v = bf16r(xr[c]);
+    ss += v * v;
+  }
+  ss = wsum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
+  const float rstd = rsqrtf(tot / (float)cols + eps);
+  for (int c = threadIdx.x; c < cols; c += blockDim.x)
+    y[row * cols + c] = __float2bfloat16(__bfloat162float(w[c]) * bf16r(bf16r(xr[c]) * rstd));
+}
+
+// qkv f32 [R, (nq + 2 nkv) * hd] (bias already added) -> rotary on q,k (HF bf16 op order) -> q bf16 [R, nq*hd],
+// k,v appended to the row's completion slab at slot ST_STEP. Position = P + step + rope_delta[row].
+__global__ void decode_rope_append_kernel(const float* __restrict__ qkv, const float* __restrict__ cos_tab,
+                                          const float* __restrict__ sin_tab, const int* __restrict__ rope_delta,
+                                          const int* __restrict__ state, bf16* __restrict__ q_out,
+                                          bf16* __restrict__ kc, bf16* __restrict__ vc, int nq, int nkv, int hd,
+                                          int c_max, int max_pos) {
+  const int r = blockIdx.x;
+  const int head = blockIdx.y;  // [0,nq) q, [nq,nq+nkv) k, [nq+nkv, nq+2nkv) v
+  const int step = state[ST_STEP];
+  int pos = state[ST_PROMPT_LEN] + step + rope_delta[r];
+  pos = max(0, min(max_pos - 1, pos));
+  const int qkv_dim = (nq + 2 * nkv) * hd;
+  const float* src = qkv + (long long)r * qkv_dim + (long long)head * hd;
+  const int half = hd >> 1;
+  if (head < nq + nkv) {
+    for (int d = threadIdx.x; d < half; d += blockDim.x) {
+      const float x1 = bf16r(src[d]), x2 = bf16r(src[d + half]);
+      const float c1 = bf16r(cos_tab[(long long)pos * hd + d]), c2 = bf16r(cos_tab[(long long)pos * hd + d + half]);
+      const float s1 = bf16r(sin_tab[(long long)pos * hd + d]), s2 = bf16r(sin_tab[(long long)pos * hd + d + half]);
+      const float o1 = bf16r(x1 * c1) + bf16r(-x2 * s1);
+      const float o2 = bf16r(x2 * c2) + bf16r(x1 * s2);
+      bf16* dst = (head < nq) ? q_out + (long long)r * nq * hd + (long long)head * hd
+                              : kc + (((long long)r * c_max + step) * nkv + (head - nq)) * hd;
+      dst[d] = __float2bfloat16(o1);
+      dst[d + half] = __float2bfloat16(o2);
+    }
+  } else {
+    bf16* dst = vc + (((long long)r * c_max + step) * nkv + (head - nq - nkv)) * hd;
+    for (int d = threadIdx.x; d < hd; d += blockDim.x) dst[d] = __float2bfloat16(src[d]);
+  }
+}
+
+// Split-KV decode attention. Grid (R, nkv, nsplit); 4 warps; each warp owns a strided subset of the chunk's keys and
+// serves all `gq` query heads of this kv head (K/V rows are read once per group, not once per head).
+template <int HD>
+__global__ void __launch_bounds__(128) decode_attn_partial_kernel(
+    const bf16* __restrict__ q, const bf16* __restrict__ kp, const bf16* __restrict__ vp, const bf16* __restrict__ kc,
+    const bf16* __restrict__ vc, const int* __restrict__ state, const int* __restrict__ row_group,
+    float* __restrict__ part, int nq, int nkv, int p_max, int c_max, int chunk, float scale) {
+  constexpr int DPL = HD / 32;  // dims per lane
+  constexpr int MAXG = 8;
+  const int r = blockIdx.x, kvh = blockIdx.y, sp = blockIdx.z, nsplit = gridDim.z;
+  const int gq = nq / nkv;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int P = state[ST_PROMPT_LEN];
+  const int ctx = P + state[ST_STEP] + 1;
+  const int k0 = sp * chunk, k1 = min(ctx, k0 + chunk);
+  const int grp = row_group[r];
+
+  float qv[MAXG][DPL], acc[MAXG][DPL], mrun[MAXG], lrun[MAXG];
+#pragma unroll
+  for (int h = 0; h < MAXG; ++h) {
+    mrun[h] = -INFINITY;
+    lrun[h] = 0.f;
+#pragma unroll
+    for (int d = 0; d < DPL; ++d) {
+      acc[h][d] = 0.f;
+      qv[h][d] = (h < gq) ? __bfloat162float(q[((long long)r * nq + kvh * gq + h) * HD + lane * DPL + d]) * scale : 0.f;
+    }
+  }
+  for (int j = k0 + warp; j < k1; j += 4) {
+    const bf16* krow;
+    const bf16* vrow;
+    if (j < P) {
+      krow = kp + (((long long)grp * p_max + j) * nkv + kvh) * HD;
+      vrow = vp + (((long long)grp * p_max + j) * nkv + kvh) * HD;
+    } else {
+      krow = kc + (((long long)r * c_max + (j - P)) * nkv + kvh) * HD;
+      vrow = vc + (((long long)r * c_max + (j - P)) * nkv + kvh) * HD;
+    }
+    float kf[DPL], vf[DPL];
+#pragma unroll
+    for (int d = 0; d < DPL; ++d) {
+      kf[d] = __bfloat162float(krow[lane * DPL + d]);
+      vf[d] = __bfloat162float(vrow[lane * DPL + d]);
+    }
+#pragma unroll
+    for (int h = 0; h < MAXG; ++h) {
+      if (h < gq) {
+        float s = 0.f;
+#pragma unroll
+        for (int d = 0; d < DPL; ++d) s += qv[h][d] * kf[d];
+        s = wsum(s);
+        const float mn = fmaxf(mrun[h], s);
+        const float corr = __expf(mrun[h] - mn);
+        const float p = __expf(s - mn);
+        lrun[h] = lrun[h] * corr + p;
+#pragma unroll
+        for (int d = 0; d < DPL; ++d) acc[h][d] = acc[h][d] * corr + p * vf[d];
+        mrun[h] = mn;
+      }
+    }
+  }
+  // merge the 4 warps through shared memory
+  __shared__ float sm_m[4][MAXG], sm_l[4][MAXG], sm_acc[4][MAXG][HD];
+  if (lane == 0) {
+#pragma unroll
+    for (int h = 0; h < MAXG; ++h) {
+      sm_m[warp][h] = mrun[h];
+      sm_l[warp][h] = lrun[h];
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < MAXG; ++h)
+#pragma unroll
+    for (int d = 0; d < DPL; ++d) sm_acc[warp][h][lane * DPL + d] = acc[h][d];
+  __syncthreads();
+  // part layout: [R][nq][nsplit][HD + 2]  (acc..., m, l)
+  for (int i = threadIdx.x; i < gq * HD; i += blockDim.x) {
+    const int h = i / HD, d = i % HD;
+    const float m = fmaxf(fmaxf(sm_m[0][h], sm_m[1][h]), fmaxf(sm_m[2][h], sm_m[3][h]));
+    float a = 0.f, l = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float c = (sm_m[w][h] == -INFINITY) ? 0.f : __expf(sm_m[w][h] - m);
+      a += sm_acc[w][h][d] * c;
+      l += sm_l[w][h] * c;
+    }
+    float* dst = part + (((long long)r * nq + kvh * gq + h) * nsplit + sp) * (HD + 2);
+    dst[d] = a;
+    if (d == 0) {
+      dst[HD] = m;
+      dst[HD + 1] = l;
+    }
+  }
+}
+
+template <int HD>
+__global__ void decode_attn_combine_kernel(const float* __restrict__ part, bf16* __restrict__ out, int nsplit) {
+  const long long rh = blockIdx.x;  // row * nq + head
+  const float* p = part + rh * nsplit * (HD + 2);
+  float m = -INFINITY;
+  for (int s = 0; s < nsplit; ++s) m = fmaxf(m, p[s * (HD + 2) + HD]);
+  for (int d = threadIdx.x; d < HD; d += blockDim.x) {
+    float a = 0.f, l = 0.f;
+    for (int s = 0; s < nsplit; ++s) {
+      const float ms = p[s * (HD + 2) + HD];
+      const float c = (ms == -INFINITY) ? 0.f : __expf(ms - m);
+      a += p[s * (HD + 2) + d] * c;
+      l += p[s * (HD + 2) + HD + 1] * c;
+    }
+    out[rh * HD + d] = __float2bfloat16(a / l);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused sampler: one CTA per row over fp32 logits[V].
+// Contract (sc_grpo_trainer.py:353-358 SamplingParams; same order as HF generate, generation/utils.py:1214-1223,
+// logits_process.py:521-528 top-k "keep everything >= the k-th value", :581-586 top-p on the renormalised survivors):
+//   logits / temperature -> keep the top_k largest (ties kept) -> softmax -> keep tokens whose strictly-higher-ranked
+//   mass is < top_p (at least one) -> renormalise -> multinomial via Philox(seed, subsequence=row, offset=step).
+// The k-th value is found with a 3-pass radix select (11+11+10 bits of the order-preserving uint key) in shared
+// memory histograms, so the vocabulary is scanned 4 times from L2 and never sorted.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t f2key(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+constexpr int kMaxKeep = 256;  // survivors buffer (top_k <= 128 plus ties)
+
+__global__ void __launch_bounds__(1024) sample_kernel(const float* __restrict__ logits, int V, float inv_temp, int top_k,
+                                                      float top_p, unsigned long long seed, int* __restrict__ state,
+                                                      int* __restrict__ tok, int* __restrict__ finished,
+                                                      int* __restrict__ out_tokens, int c_max, int eos_id, int pad_id,
+                                                      int forbid_eos, int first) {
+  __shared__ uint32_t hist[2048];
+  __shared__ uint32_t s_prefix, s_kth_remaining;
+  __shared__ int s_count;
+  __shared__ float s_val[kMaxKeep];
+  __shared__ int s_idx[kMaxKeep];
+  const int r = blockIdx.x;
+  const float* lg = logits + (long long)r * V;
+  // `first`: logits come from the prefill (predict completion token 0); else they predict token step + 1.
+  const int out_pos = first ? 0 : state[ST_STEP] + 1;
+  if (out_pos >= c_max) return;
+  if (finished[r]) {
+    if (threadIdx.x == 0) {
+      out_tokens[(long long)r * c_max + out_pos] = pad_id;
+      tok[r] = pad_id;
+    }
+    return;
+  }
+  const int k = min(max(top_k, 1), 128);
+  // --- radix select of the k-th largest key ---
+  uint32_t prefix = 0, prefix_mask = 0;
+  uint32_t remaining = k;
+  const int shifts[3] = {21, 10, 0};
+  const int bits[3] = {11, 11, 10};
+  for (int pass = 0; pass < 3; ++pass) {
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const uint32_t nb = 1u << bits[pass];
+    for (int i = threadIdx.x; i < V; i += blockDim.x) {
+      float x = lg[i];
+      if (forbid_eos && i == eos_id) x = -INFINITY;
+      const uint32_t key = f2key(x);
+      if ((key & prefix_mask) == prefix) atomicAdd(&hist[(key >> shifts[pass]) & (nb - 1)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t cum = 0;
+      int b = (int)nb - 1;
+      for (; b > 0; --b) {
+        if (cum + hist[b] >= remaining) break;
+        cum += hist[b];
+      }
+      s_prefix = prefix | ((uint32_t)b << shifts[pass]);
+      s_kth_remaining = remaining - cum;
+    }
+    __syncthreads();
+    prefix = s_prefix;
+    remaining = s_kth_remaining;
+    prefix_mask |= ((nb - 1) << shifts[pass]);
+    __syncthreads();
+  }
+  const uint32_t kth_key = prefix;  // every key >= kth_key survives (ties kept)
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+    float x = lg[i];
+    if (forbid_eos && i == eos_id) x = -INFINITY;
+    if (f2key(x) >= kth_key) {
+      const int slot = atomicAdd(&s_count, 1);
+      if (slot < kMaxKeep) {
+        s_val[slot] = x * inv_temp;
+        s_idx[slot] = i;
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int n = min(s_count, kMaxKeep);
+    // insertion sort descending by value, ties by smaller index first (deterministic)
+    for (int i = 1; i < n; ++i) {
+      const float v = s_val[i];
+      const int id = s_idx[i];
+      int j = i - 1;
+      while (j >= 0 && (s_val[j] < v || (s_val[j] == v && s_idx[j] > id))) {
+        s_val[j + 1] = s_val[j];
+        s_idx[j + 1] = s_idx[j];
+        --j;
+      }
+      s_val[j + 1] = v;
+      s_idx[j + 1] = id;
+    }
+    const float mx = s_val[0];
+    float tot = 0.f;
+    for (int i = 0; i < n; ++i) {
+      s_val[i] = expf(s_val[i] - mx);
+      tot += s_val[i];
+    }
+    // nucleus: keep token i while the mass of strictly higher-ranked tokens is < top_p
+    float before = 0.f, kept = 0.f;
+    int nkeep = 0;
+    for (int i = 0; i < n; ++i) {
+      if (i > 0 && before / tot >= top_p) break;
+      kept += s_val[i];
+      before += s_val[i];
+      ++nkeep;
+    }
+    curandStatePhilox4_32_10_t rng;
+    curand_init(seed, (unsigned long long)r, (unsigned long long)out_pos, &rng);
+    const float u = curand_uniform(&rng) * kept;  // (0, kept]
+    float c = 0.f;
+    int pick = nkeep - 1;
+    for (int i = 0; i < nkeep; ++i) {
+      c += s_val[i];
+      if (u <= c) {
+        pick = i;
+        break;
+      }
+    }
+    const int t = s_idx[pick];
+    out_tokens[(long long)r * c_max + out_pos] = t;
+    tok[r] = t;
+    if (t == eos_id) {
+      finished[r] = 1;
+      atomicSub(&state[ST_UNFINISHED], 1);
+    }
+  }
+}
+
+__global__ void decode_advance_kernel(int* state) { state[ST_STEP] += 1; }
+
+}  // namespace iadr1
+
+using namespace iadr1;
+
+extern "C" {
+
+int iadr1_decode_embed(const void* embed, const int* tok, float* h, int rows, int H, void* stream) {
+  if (rows <= 0) return 0;
+  decode_embed_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>((const bf16*)embed, tok, h, H);
+  IADR1_CHECK_LAUNCH("decode_embed");
+  return 0;
+}
+
+int iadr1_rmsnorm_f32in(const float* x, const void* w, void* y, int rows, int cols, float eps, void* stream) {
+  if (rows <= 0) return 0;
+  rmsnorm_f32in_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(x, (const bf16*)w, (bf16*)y, cols, eps);
+  IADR1_CHECK_LAUNCH("rmsnorm_f32in");
+  return 0;
+}
+
+int iadr1_decode_rope_append(const float* qkv, const float* cos_tab, const float* sin_tab, const int* rope_delta,
+                             const int* state, void* q_out, void* kc, void* vc, int rows, int nq, int nkv, int hd,
+                             int c_max, int max_pos, void* stream) {
+  if (rows <= 0) return 0;
+  decode_rope_append_kernel<<<dim3(rows, nq + 2 * nkv), 64, 0, (cudaStream_t)stream>>>(
+      qkv, cos_tab, sin_tab, rope_delta, state, (bf16*)q_out, (bf16*)kc, (bf16*)vc, nq, nkv, hd, c_max, max_pos);
+  IADR1_CHECK_LAUNCH("decode_rope_append");
+  return 0;
+}
+
+int iadr1_decode_attention(const void* q, const void* kp, const void* vp, const void* kc, const void* vc,
+                           const int* state, const int* row_group, float* part, void* out, int rows, int nq, int nkv,
+                           int hd, int p_max, int c_max, int nsplit, float scale, void* stream) {
+  if (rows <= 0) return 0;
+  if (nq % nkv || nq / nkv > 8) return set_error("decode_attention: group size %d unsupported (max 8)", nq / nkv);
+  const int chunk = (p_max + c_max + nsplit - 1) / nsplit;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (hd == 128) {
+    decode_attn_partial_kernel<128><<<dim3(rows, nkv, nsplit), 128, 0, st>>>(
+        (const bf16*)q, (const bf16*)kp, (const bf16*)vp, (const bf16*)kc, (const bf16*)vc, state, row_group, part, nq,
+        nkv, p_max, c_max, chunk, scale);
+    IADR1_CHECK_LAUNCH("decode_attn_partial");
+    decode_attn_combine_kernel<128><<<rows * nq, 128, 0, st>>>(part, (bf16*)out, nsplit);
+  } else if (hd == 64) {
+    decode_attn_partial_kernel<64><<<dim3(rows, nkv, nsplit), 128, 0, st>>>(
+        (const bf16*)q, (const bf16*)kp, (const bf16*)vp, (const bf16*)kc, (const bf16*)vc, state, row_group, part, nq,
+        nkv, p_max, c_max, chunk, scale);
+    IADR1_CHECK_LAUNCH("decode_attn_partial");
+    decode_attn_combine_kernel<64><<<rows * nq, 64, 0, st>>>(part, (bf16*)out, nsplit);
+  } else {
+    return set_error("decode_attention: head_dim %d unsupported (64 or 128)", hd);
+  }
+  IADR1_CHECK_LAUNCH("decode_attn_combine");
+  return 0;
+}
+
+int iadr1_sample(const float* logits, int rows, int V, float temperature, int top_k, float top_p,
+                 unsigned long long seed, int* state, int* tok, int* finished, int* out_tokens, int c_max, int eos_id,
+                 int pad_id, int forbid_eos, int first, void* stream) {
+  if (rows <= 0) return 0;
+  if (temperature <= 0.f) return set_error("sample: temperature must be > 0");
+  sample_kernel<<<rows, 1024, 0, (cudaStream_t)stream>>>(logits, V, 1.f / temperature, top_k, top_p, seed, state, tok,
+                                                         finished, out_tokens, c_max, eos_id, pad_id, forbid_eos, first);
+  IADR1_CHECK_LAUNCH("sample");
+  return 0;
+}
+
+int iadr1_decode_advance(int* state, void* stream) {
+  decode_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state);
+  IADR1_CHECK_LAUNCH("decode_advance");
+  return 0;
+}
+
+}  // extern "C"

@@ -32,7 +32,7 @@ static constexpr int kMaxStages = 12;
 static constexpr int kAccStride = 256;  // TMEM columns per accumulator stage
 
 struct TileInfo {
-  int z, m0, n0, n_blk, kb_begin, kb_end;
+  int z, m0, n0, n_blk, kb_begin, kb_end, split;
   bool skip;
 };
 
@@ -43,6 +43,7 @@ __device__ __forceinline__ TileInfo decode_tile(const GemmArgs& g, int t, int ti
   ti.z = t / per_z;
   int r = t - ti.z * per_z;
   const int split = r / mn;
+  ti.split = split;
   r -= split * mn;
   ti.n_blk = r / tiles_m;
   const int m_blk = r - ti.n_blk * tiles_m;
@@ -105,7 +106,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const TileInfo
   }
 
   const long long zoff = (long long)(ti.z % g.batch_lo) * g.c_bs_lo + (long long)(ti.z / g.batch_lo) * g.c_bs_hi;
-  if (g.bias != nullptr) {
+  if (g.bias != nullptr && ti.split == 0) {
     if (g.bias_per_m) {
       const float b = __bfloat162float(g.bias[m]);
 #pragma unroll
@@ -123,7 +124,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const TileInfo
       if (j < nvalid) {
         const long long idx = zoff + (long long)(nb + j) * g.ldc + m;
         float x = acc[j];
-        if (g.residual) x += __bfloat162float(g.residual[idx]);
+        if (g.residual && ti.split == 0) x += __bfloat162float(g.residual[idx]);
         if (g.atomic) {
           atomicAdd(reinterpret_cast<float*>(g.C) + idx, x);
         } else if (g.c_f32) {
@@ -137,7 +138,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const TileInfo
     return;
   }
   const long long idx0 = zoff + (long long)m * g.ldc + nb;
-  if (g.residual) {
+  if (g.residual && ti.split == 0) {
     if (vec_ok && nvalid == W) {
       const uint4* rp = reinterpret_cast<const uint4*>(g.residual + idx0);
 #pragma unroll

@@ -56,22 +56,41 @@ def lib():
     return _lib
 
 
+HEADER = os.path.join(os.path.dirname(_HERE), "include", "iadr1_b200.h")
+_CTYPES = {"int": C.c_int, "long long": C.c_longlong, "float": C.c_float, "unsigned long long": C.c_ulonglong}
+
+
+def header_prototypes(path: str = HEADER) -> dict:
+    """Parse `int iadr1_xxx(args);` prototypes out of the public header -> {name: [ctypes argtypes]}."""
+    import re
+    text = open(path).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\bint\s+(iadr1_\w+)\s*\(([^)]*)\)\s*;", text):
+        name, args = m.group(1), m.group(2).strip()
+        types = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = " ".join(a.split())
+                if "*" in a:
+                    types.append(C.c_void_p)
+                else:
+                    base = " ".join(a.replace("const ", "").split()[:-1])
+                    types.append(_CTYPES[base])
+        protos[name] = types
+    return protos
+
+
 def _declare(L):
-    """argtypes for the pointer/size entry points (all return int status)."""
-    vp, i, f, ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
-    sigs = {
-        "iadr1_gemm_pick_block_n": [i, i],
-    }
-    sigs.update(_EXTRA_SIGS)
-    for name, args in sigs.items():
+    """argtypes for every `int iadr1_*(...)` entry point the header declares (all return int status)."""
+    for name, args in header_prototypes().items():
         fn = getattr(L, name, None)
         if fn is None:
             raise NativeLibraryError(f"{_LIB_PATH} does not export {name}; rebuild the library")
+        if name == "iadr1_gemm_bf16":
+            continue
         fn.argtypes = args
-        fn.restype = i
-
-
-_EXTRA_SIGS: dict = {}
+        fn.restype = C.c_int
 
 
 def check(rc: int, what: str = "") -> None:

@@ -1,0 +1,286 @@
+"""Tensor-level wrappers over the C ABI (include/iadr1_b200.h) plus the three compositions the model code uses:
+linear (fwd / dgrad / wgrad), attention (QK^T -> masked softmax -> PV on the tcgen05 GEMM) and the fused
+lm_head -> log-softmax -> gather. PyTorch only supplies device buffers and the current stream.
+
+Every function here launches library kernels; none computes with torch ops (DESIGN.md "no fallback").
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import lib as L
+
+bf16 = torch.bfloat16
+f32 = torch.float32
+
+ACT_SILU, ACT_GELU, ACT_QUICK_GELU, ACT_GELU_TANH = 0, 1, 2, 3
+EPI_STORE, EPI_LSE, EPI_DLOGITS = 0, 1, 2
+
+
+def _s():
+    return L.stream_ptr()
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def ceil_to(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+# ---- norms -------------------------------------------------------------------------------------------------------
+def rmsnorm_fwd(x, w, eps, out=None, save_rstd=True):
+    rows, cols = x.shape
+    y = torch.empty_like(x) if out is None else out
+    rstd = torch.empty(rows, dtype=f32, device=x.device) if save_rstd else None
+    L.check(L.lib().iadr1_rmsnorm_fwd(_p(x), _p(w), _p(y), _p(rstd), rows, cols, x.stride(0), y.stride(0), eps, _s()),
+            "rmsnorm_fwd")
+    return y, rstd
+
+
+def rmsnorm_bwd(dy, x, w, rstd, dx, dw32, add_dx):
+    rows, cols = x.shape
+    assert dy.stride(0) == x.stride(0) == dx.stride(0)
+    L.check(L.lib().iadr1_rmsnorm_bwd(_p(dy), _p(x), _p(w), _p(rstd), _p(dx), _p(dw32), rows, cols, x.stride(0),
+                                      int(add_dx), _s()), "rmsnorm_bwd")
+    return dx
+
+
+def layernorm_fwd(x, w, b, eps, out=None):
+    rows, cols = x.shape
+    y = torch.empty_like(x) if out is None else out
+    mean = torch.empty(rows, dtype=f32, device=x.device)
+    rstd = torch.empty(rows, dtype=f32, device=x.device)
+    L.check(L.lib().iadr1_layernorm_fwd(_p(x), _p(w), _p(b), _p(y), _p(mean), _p(rstd), rows, cols, x.stride(0), eps,
+                                        _s()), "layernorm_fwd")
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, w, mean, rstd, dx, dw32, db32, add_dx):
+    rows, cols = x.shape
+    L.check(L.lib().iadr1_layernorm_bwd(_p(dy), _p(x), _p(w), _p(mean), _p(rstd), _p(dx), _p(dw32), _p(db32), rows,
+                                        cols, x.stride(0), int(add_dx), _s()), "layernorm_bwd")
+    return dx
+
+
+# ---- rotary / activations ------------------------------------------------------------------------------------------
+def rope_(x, cos, sin, heads, hd, bf16_ops, backward=False):
+    """In place on the first `heads` heads of x[tokens, heads_total*hd]; cos/sin fp32 [tokens, hd]."""
+    tokens = x.shape[0]
+    assert cos.dtype == f32 and cos.shape == (tokens, hd) and cos.is_contiguous() and sin.is_contiguous()
+    L.check(L.lib().iadr1_rope(_p(x), _p(cos), _p(sin), tokens, heads, hd, x.stride(0), int(bf16_ops), int(backward),
+                               _s()), "rope")
+    return x
+
+
+def act_mul_fwd(gu, cols, act, gated=True, out=None):
+    rows = gu.shape[0]
+    if out is None:
+        out = torch.empty(rows, cols, dtype=bf16, device=gu.device)
+    L.check(L.lib().iadr1_act_mul_fwd(_p(gu), _p(out), rows, cols, gu.stride(0), cols if gated else -1, out.stride(0),
+                                      act, _s()), "act_mul_fwd")
+    return out
+
+
+def act_mul_bwd(dout, gu, cols, act, gated=True, dgu=None):
+    rows = gu.shape[0]
+    if dgu is None:
+        dgu = torch.empty_like(gu)
+    assert dgu.stride(0) == gu.stride(0)
+    L.check(L.lib().iadr1_act_mul_bwd(_p(dout), _p(gu), _p(dgu), rows, cols, gu.stride(0), cols if gated else -1,
+                                      dout.stride(0), act, _s()), "act_mul_bwd")
+    return dgu
+
+
+# ---- softmax / gathers / reductions -----------------------------------------------------------------------------------
+def softmax_rows_(S, lo, hi, Tq, Tk, ld, z_stride, batch):
+    L.check(L.lib().iadr1_softmax_rows(_p(S), _p(lo), _p(hi), Tq, Tk, ld, z_stride, batch, _s()), "softmax_rows")
+
+
+def softmax_bwd_rows_(P, dP, lo, hi, Tq, Tk, ld, z_stride, batch):
+    L.check(L.lib().iadr1_softmax_bwd_rows(_p(P), _p(dP), _p(lo), _p(hi), Tq, Tk, ld, z_stride, batch, _s()),
+            "softmax_bwd_rows")
+
+
+def gather_rows(table, index, alt=None, out=None):
+    rows = index.shape[0]
+    cols = table.shape[1]
+    if out is None:
+        out = torch.empty(rows, cols, dtype=bf16, device=table.device)
+    assert index.dtype == torch.int32
+    L.check(L.lib().iadr1_gather_rows(_p(table), _p(alt), _p(index), _p(out), rows, cols, table.stride(0),
+                                      alt.stride(0) if alt is not None else 0, out.stride(0), _s()), "gather_rows")
+    return out
+
+
+def scatter_add_rows(d, index, dtable32, dalt32):
+    rows, cols = d.shape
+    L.check(L.lib().iadr1_scatter_add_rows(_p(d), _p(index), _p(dtable32), _p(dalt32), rows, cols, d.stride(0),
+                                           dtable32.stride(0) if dtable32 is not None else 0,
+                                           dalt32.stride(0) if dalt32 is not None else 0, _s()), "scatter_add_rows")
+
+
+def colsum(x, out32):
+    rows, cols = x.shape
+    L.check(L.lib().iadr1_colsum(_p(x), _p(out32), rows, cols, x.stride(0), _s()), "colsum")
+
+
+def group_sum(src, out, rows, nkv, g, hd, src_ld, out_ld):
+    L.check(L.lib().iadr1_group_sum(_p(src), _p(out), rows, nkv, g, hd, src_ld, out_ld, _s()), "group_sum")
+
+
+def add_bf16(a, b, out=None):
+    out = torch.empty_like(a) if out is None else out
+    L.check(L.lib().iadr1_add_bf16(_p(a), _p(b), _p(out), a.numel(), _s()), "add_bf16")
+    return out
+
+
+def cast_f32_bf16(src, dst=None):
+    dst = torch.empty(src.shape, dtype=bf16, device=src.device) if dst is None else dst
+    L.check(L.lib().iadr1_cast_f32_bf16(_p(src), _p(dst), src.numel(), _s()), "cast_f32_bf16")
+    return dst
+
+
+# ---- linear ---------------------------------------------------------------------------------------------------------
+def linear_fwd(x, W, bias=None, residual=None, out=None):
+    """x[M,K] @ W[N,K]^T (+bias) (+residual) -> bf16 [M,N]   (torch.nn.functional.linear)"""
+    return L.gemm(x, W, out=out, bias=bias, residual=residual)
+
+
+def linear_bwd(dy, x, W, dW32, db32=None, need_dx=True, dx_out=None):
+    """dx = dy @ W ; dW32 += dy^T @ x ; db32 += colsum(dy). All from the row-major buffers (MN-major operands)."""
+    dx = None
+    if need_dx:
+        dx = L.gemm(dy, W.t(), out=dx_out)
+    if dW32 is not None:
+        L.gemm(dy.t(), x.t(), out=dW32, accumulate=True)
+    if db32 is not None:
+        colsum(dy, db32)
+    return dx
+
+
+# ---- attention ------------------------------------------------------------------------------------------------------
+class AttnShape:
+    """Geometry of one attention call over a fused qkv buffer [B*T, (nq + 2 nkv) * hd]."""
+
+    def __init__(self, B, T, nq, nkv, hd, causal):
+        self.B, self.T, self.nq, self.nkv, self.hd, self.causal = B, T, nq, nkv, hd, bool(causal)
+        self.g = nq // nkv
+        self.D = (nq + 2 * nkv) * hd
+        self.Tp = ceil_to(T, 8)
+        self.scale = float(hd) ** -0.5
+
+
+def attention_fwd(qkv, sh: AttnShape, lo, hi, out=None, P=None):
+    """Returns (attn [B*T, nq*hd] bf16, P [B, nq, T, Tp] bf16 probabilities kept for the backward)."""
+    B, T, nq, hd, D, Tp, g = sh.B, sh.T, sh.nq, sh.hd, sh.D, sh.Tp, sh.g
+    if P is None:
+        P = torch.empty(B, nq, T, Tp, dtype=bf16, device=qkv.device)
+    c = int(sh.causal)
+    # S = scale * Q K^T  (per (row, head); kv head shared by g query heads)
+    L.gemm_batched(qkv, qkv, P, M=T, N=T, K=hd, batch=B * nq, batch_lo=nq, b_lo_div=g,
+                   lda=D, a_bs_lo=hd, a_bs_hi=T * D, ldb=D, b_bs_lo=hd, b_bs_hi=T * D, b_off=nq * hd,
+                   ldc=Tp, c_bs_lo=T * Tp, c_bs_hi=nq * T * Tp, alpha=sh.scale, skip_mode=c)
+    softmax_rows_(P, lo, hi, T, Tp, Tp, T * Tp, B * nq)
+    if out is None:
+        out = torch.empty(B * T, nq * hd, dtype=bf16, device=qkv.device)
+    # O = P V   (V is read MN-major straight from the qkv buffer)
+    L.gemm_batched(P, qkv, out, M=T, N=hd, K=T, batch=B * nq, batch_lo=nq, b_lo_div=g,
+                   lda=Tp, a_bs_lo=T * Tp, a_bs_hi=nq * T * Tp,
+                   ldb=D, b_bs_lo=hd, b_bs_hi=T * D, b_mn=1, b_off=(nq + sh.nkv) * hd,
+                   ldc=nq * hd, c_bs_lo=hd, c_bs_hi=T * nq * hd, kmode=c)
+    return out, P
+
+
+def attention_bwd(dattn, qkv, P, sh: AttnShape, lo, hi, dqkv=None):
+    """Gradient wrt the (post-rotary) fused qkv buffer. `P` is consumed (dP/dS are formed in a scratch of its size)."""
+    B, T, nq, nkv, hd, D, Tp, g = sh.B, sh.T, sh.nq, sh.nkv, sh.hd, sh.D, sh.Tp, sh.g
+    c = int(sh.causal)
+    if dqkv is None:
+        dqkv = torch.empty(B * T, D, dtype=bf16, device=qkv.device)
+    dP = torch.empty_like(P)
+    v_off, k_off = (nq + nkv) * hd, nq * hd
+    # dP = dO V^T
+    L.gemm_batched(dattn, qkv, dP, M=T, N=T, K=hd, batch=B * nq, batch_lo=nq, b_lo_div=g,
+                   lda=nq * hd, a_bs_lo=hd, a_bs_hi=T * nq * hd, ldb=D, b_bs_lo=hd, b_bs_hi=T * D, b_off=v_off,
+                   ldc=Tp, c_bs_lo=T * Tp, c_bs_hi=nq * T * Tp, skip_mode=c)
+    softmax_bwd_rows_(P, dP, lo, hi, T, Tp, Tp, T * Tp, B * nq)  # dP now holds dS
+    # dQ = scale * dS K
+    L.gemm_batched(dP, qkv, dqkv, M=T, N=hd, K=T, batch=B * nq, batch_lo=nq, b_lo_div=g,
+                   lda=Tp, a_bs_lo=T * Tp, a_bs_hi=nq * T * Tp, ldb=D, b_bs_lo=hd, b_bs_hi=T * D, b_mn=1, b_off=k_off,
+                   ldc=D, c_bs_lo=hd, c_bs_hi=T * D, alpha=sh.scale, kmode=c)
+    if g == 1:
+        dk_buf, dk_ld, dk_off, dv_buf, dv_off = dqkv, D, k_off, dqkv, v_off
+    else:
+        tmp = torch.empty(2, B * T, nq * hd, dtype=bf16, device=qkv.device)
+        dk_buf, dk_ld, dk_off, dv_buf, dv_off = tmp[0], nq * hd, 0, tmp[1], 0
+    # dK_h = scale * dS^T Q_h ; dV_h = P^T dO_h   (A and B both MN-major; reduction over queries)
+    L.gemm_batched(dP, qkv, dk_buf, M=T, N=hd, K=T, batch=B * nq, batch_lo=nq,
+                   lda=Tp, a_bs_lo=T * Tp, a_bs_hi=nq * T * Tp, a_mn=1, ldb=D, b_bs_lo=hd, b_bs_hi=T * D, b_mn=1,
+                   ldc=dk_ld, c_bs_lo=hd, c_bs_hi=T * dk_ld, c_off=dk_off, alpha=sh.scale, kmode=2 * c)
+    L.gemm_batched(P, dattn, dv_buf, M=T, N=hd, K=T, batch=B * nq, batch_lo=nq,
+                   lda=Tp, a_bs_lo=T * Tp, a_bs_hi=nq * T * Tp, a_mn=1,
+                   ldb=nq * hd, b_bs_lo=hd, b_bs_hi=T * nq * hd, b_mn=1,
+                   ldc=dk_ld, c_bs_lo=hd, c_bs_hi=T * dk_ld, c_off=dv_off, kmode=2 * c)
+    if g > 1:
+        group_sum(dk_buf, dqkv[:, k_off:], B * T, nkv, g, hd, nq * hd, D)
+        group_sum(dv_buf, dqkv[:, v_off:], B * T, nkv, g, hd, nq * hd, D)
+    return dqkv
+
+
+# ---- fused lm_head -> log-softmax -> gather -----------------------------------------------------------------------------
+def logprob_fwd(h, E, labels, temperature: float = 1.0):
+    """logp[m] = log_softmax(h[m] @ E^T / temperature)[labels[m]] in fp32 without materialising the logits.
+
+    Replaces `model(**inputs).logits` + row-wise `log_softmax` + `gather` (sc_grpo_trainer.py:505-514).
+    Returns (logp [M] fp32, lse [M] fp32)."""
+    M, H = h.shape
+    V = E.shape[0]
+    bn = L.lib().iadr1_gemm_pick_block_n(V, 0)
+    tiles = (V + bn - 1) // bn
+    dev = h.device
+    pmax = torch.empty(M, tiles, dtype=f32, device=dev)
+    psum = torch.empty(M, tiles, dtype=f32, device=dev)
+    tgt = torch.zeros(M, dtype=f32, device=dev)
+    d = L.GemmDesc()
+    d.M, d.N, d.K = M, V, H
+    d.batch = d.batch_lo = d.b_lo_div = 1
+    d.A, d.lda, d.a_mn = h.data_ptr(), h.stride(0), 0
+    d.B, d.ldb, d.b_mn = E.data_ptr(), E.stride(0), 0
+    d.split_k = 1
+    d.alpha = 1.0 / temperature
+    d.epi = EPI_LSE
+    d.labels, d.part_max, d.part_sum, d.tgt_logit, d.lse_tiles_n = _p(labels), _p(pmax), _p(psum), _p(tgt), tiles
+    d.block_n = bn
+    L.check(L.lib().iadr1_gemm_bf16(C.byref(d), _s()), "logprob_fwd gemm")
+    lse = torch.empty(M, dtype=f32, device=dev)
+    logp = torch.empty(M, dtype=f32, device=dev)
+    L.check(L.lib().iadr1_lse_finalize(_p(pmax), _p(psum), _p(tgt), tiles, M, _p(lse), _p(logp), _s()), "lse_finalize")
+    return logp, lse
+
+
+def logprob_bwd(dlogp, h, E, labels, lse, dE32, temperature: float = 1.0, need_dh=True):
+    """dh = dlogits @ E, dE32 += dlogits^T @ h with dlogits = (onehot - softmax) * dlogp / temperature, recomputing
+    the logits tile by tile (bf16 dlogits [M, V] is the only large intermediate)."""
+    M, H = h.shape
+    V = E.shape[0]
+    dlogits = torch.empty(M, V, dtype=bf16, device=h.device)
+    gscale = (-dlogp.to(f32) / temperature).contiguous()  # kernel forms (softmax - onehot) * gscale
+    d = L.GemmDesc()
+    d.M, d.N, d.K = M, V, H
+    d.batch = d.batch_lo = d.b_lo_div = 1
+    d.A, d.lda, d.a_mn = h.data_ptr(), h.stride(0), 0
+    d.B, d.ldb, d.b_mn = E.data_ptr(), E.stride(0), 0
+    d.C, d.ldc = dlogits.data_ptr(), V
+    d.split_k = 1
+    d.alpha = 1.0 / temperature
+    d.epi = EPI_DLOGITS
+    d.labels, d.lse, d.gscale = _p(labels), _p(lse), _p(gscale)
+    L.check(L.lib().iadr1_gemm_bf16(C.byref(d), _s()), "logprob_bwd gemm")
+    dh = L.gemm(dlogits, E.t()) if need_dh else None
+    if dE32 is not None:
+        L.gemm(dlogits.t(), h.t(), out=dE32, accumulate=True)
+    return dh

@@ -56,6 +56,76 @@ int iadr1_gemm_bf16(const iadr1_gemm_t* desc, void* stream);
 /* block_n the library would choose for an N-wide product (sizes the EPI_LSE partial buffers). */
 int iadr1_gemm_pick_block_n(int N, int b_mn);
 
+/* ---- row kernels (HBM-bound; bf16 activations, fp32 statistics) ------------------------------------------------
+ * RMSNorm: HF Qwen2_5_VLRMSNorm.forward, modeling_qwen2_5_vl.py:57-71 (decoder :775-776,:849; vision blocks; merger ln_q).
+ * rstd (optional, [rows] fp32) is saved for the backward. cols % 8 == 0.                                           */
+int iadr1_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, long long rows, int cols, long long x_ld,
+                      long long y_ld, float eps, void* stream);
+/* dx (+)= d(rmsnorm)/dx, dw (fp32, may be NULL) += d/dw. add_dx = 1 accumulates into dx (residual-stream gradient). */
+int iadr1_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx, float* dw,
+                      long long rows, int cols, long long ld, int add_dx, void* stream);
+/* LayerNorm: Qwen2-VL vision blocks (modeling_qwen2_vl.py:461-466) and SigLIP (LLaVA-OneVision tower).            */
+int iadr1_layernorm_fwd(const void* x, const void* w, const void* b, void* y, float* mean, float* rstd, long long rows,
+                        int cols, long long ld, float eps, void* stream);
+int iadr1_layernorm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, void* dx,
+                        float* dw, float* db, long long rows, int cols, long long ld, int add_dx, void* stream);
+/* Rotate-half rotary embedding in place on the first `heads` heads of x[tokens][heads_total][hd] (tok_stride elements
+ * per token). cos/sin: fp32 [tokens][hd]. bf16_ops = 1 reproduces apply_multimodal_rotary_pos_emb (:627-669, bf16
+ * products), 0 reproduces apply_rotary_pos_emb_vision (:156-167, fp32). backward = 1 applies the transpose.         */
+int iadr1_rope(void* x, const float* cos_t, const float* sin_t, long long tokens, int heads, int hd,
+               long long tok_stride, int bf16_ops, int backward, void* stream);
+/* out = act(gate) * up with gate at gu[r*ld + c], up at gu[r*ld + up_off + c]; up_off < 0: out = act(gate).
+ * act: 0 SiLU (Qwen2MLP :611-624, vision SwiGLU :77-88), 1 exact GELU (merger :139), 2 quick-GELU, 3 tanh-GELU.       */
+int iadr1_act_mul_fwd(const void* gu, void* out, long long rows, int cols, long long ld, long long up_off,
+                      long long out_ld, int act, void* stream);
+int iadr1_act_mul_bwd(const void* dout, const void* gu, void* dgu, long long rows, int cols, long long ld,
+                      long long up_off, long long dout_ld, int act, void* stream);
+/* In-place masked softmax over bf16 scores S[z][q][k]; row q keeps keys [lo[q], hi[q]) (causal / window / padding
+ * masks as ranges), exact zeros elsewhere. eager_attention_forward, modeling_qwen2_5_vl.py:182-206.                 */
+int iadr1_softmax_rows(void* S, const int* lo, const int* hi, int Tq, int Tk, long long ld, long long z_stride,
+                       long long batch, void* stream);
+int iadr1_softmax_bwd_rows(const void* P, void* dP, const int* lo, const int* hi, int Tq, int Tk, long long ld,
+                           long long z_stride, long long batch, void* stream);
+/* out[r] = index[r] >= 0 ? table[index[r]] : alt[-1 - index[r]]: embed_tokens + masked_scatter of image embeddings
+ * (:1298-1307) in one pass; with alt = NULL a plain row gather (vision window reorder :478-484, :512-513).          */
+int iadr1_gather_rows(const void* table, const void* alt, const int* index, void* out, long long rows, int cols,
+                      long long table_ld, long long alt_ld, long long out_ld, void* stream);
+int iadr1_scatter_add_rows(const void* d, const int* index, float* dtable, float* dalt, long long rows, int cols,
+                           long long d_ld, long long table_ld, long long alt_ld, void* stream);
+/* out[c] += sum_r x[r][c] (bias gradients).                                                                       */
+int iadr1_colsum(const void* x, float* out, long long rows, int cols, long long ld, void* stream);
+/* Sum the g query-head gradients of each kv head (autograd of repeat_kv, modeling_qwen2_5_vl.py:170-179).          */
+int iadr1_group_sum(const void* src, void* out, long long rows, int nkv, int g, int hd, long long src_ld,
+                    long long out_ld, void* stream);
+int iadr1_add_bf16(const void* a, const void* b, void* out, long long n, void* stream);
+int iadr1_cast_f32_bf16(const float* src, void* dst, long long n, void* stream);
+/* Finishes the fused lm_head -> log-softmax -> gather (replaces sc_grpo_trainer.py:505-514 / trl selective_log_softmax,
+ * ref: trl/trl/trainer/utils.py:1683-1715) from the GEMM's per-tile (max, sum-exp) partials.                       */
+int iadr1_lse_finalize(const float* pmax, const float* psum, const float* tgt, int tiles_n, int M, float* lse,
+                       float* logp, void* stream);
+
+/* ---- optimizer: replaces torch.optim.AdamW inside DeepSpeed ZeRO-3 + clip_grad_norm_ ------------ */
+int iadr1_sumsq_f32(const float* g, long long n, float* out, void* stream);
+int iadr1_adamw_step(float* p32, void* p16, float* g, float* m, float* v, long long n, float lr, float beta1,
+                     float beta2, float eps, float weight_decay, int step, float grad_scale, const float* sumsq,
+                     float max_norm, int zero_grad, void* stream);
+
+/* ---- rollout: replaces vLLM `LLM.generate` (sc_grpo_trainer.py:343-358, 667). State words: [0] step, [1] prompt
+ * length, [2] unfinished rows. All per-step inputs live on the device so one step is CUDA-graph replayable.        */
+int iadr1_decode_embed(const void* embed, const int* tok, float* h, int rows, int H, void* stream);
+int iadr1_rmsnorm_f32in(const float* x, const void* w, void* y, int rows, int cols, float eps, void* stream);
+int iadr1_decode_rope_append(const float* qkv, const float* cos_tab, const float* sin_tab, const int* rope_delta,
+                             const int* state, void* q_out, void* kc, void* vc, int rows, int nq, int nkv, int hd,
+                             int c_max, int max_pos, void* stream);
+int iadr1_decode_attention(const void* q, const void* kp, const void* vp, const void* kc, const void* vc,
+                           const int* state, const int* row_group, float* part, void* out, int rows, int nq, int nkv,
+                           int hd, int p_max, int c_max, int nsplit, float scale, void* stream);
+/* temperature -> top-k (ties kept) -> top-p -> multinomial; SamplingParams at sc_grpo_trainer.py:353-358.           */
+int iadr1_sample(const float* logits, int rows, int V, float temperature, int top_k, float top_p,
+                 unsigned long long seed, int* state, int* tok, int* finished, int* out_tokens, int c_max, int eos_id,
+                 int pad_id, int forbid_eos, int first, void* stream);
+int iadr1_decode_advance(int* state, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,357 @@
+"""GPU parity of every library kernel (called through the C ABI via ctypes) against plain torch fp32 math on the
+same seeded inputs. Tolerances: bf16 outputs are compared at 2 bf16 ulps of the reference magnitude (stated per
+test); fp32 outputs at 1e-4 relative. Integer / index work is bit-exact."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+bf16, f32 = torch.bfloat16, torch.float32
+
+
+@pytest.fixture(scope="module")
+def ops(cuda):
+    from iad_r1_b200 import ops
+    from iad_r1_b200 import lib
+    lib.lib()  # must load: no fallback
+    return ops
+
+
+def rnd(*shape, scale=1.0, dev="cuda"):
+    return (torch.randn(*shape, device=dev) * scale).to(bf16)
+
+
+def close(got, want, tol=2 ** -7, what=""):
+    got, want = got.float(), want.float()
+    assert torch.isfinite(got).all(), f"{what}: non-finite output"
+    err = (got - want).abs().max().item()
+    ref = want.abs().max().item() + 1e-6
+    assert err <= tol * ref, f"{what}: max abs err {err:.4g} vs ref max {ref:.4g} (tol {tol:.3g} rel)"
+
+
+# ---------------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (200, 72, 1176), (1024, 1280, 1176), (333, 3424, 1280), (8, 2048, 896)])
+@pytest.mark.parametrize("amn,bmn", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_gemm_layouts(ops, M, N, K, amn, bmn):
+    from iad_r1_b200 import lib as L
+    torch.manual_seed(M + N + K + amn * 2 + bmn)
+    if (amn and M % 8) or (bmn and N % 8):
+        pytest.skip("MN-major operand needs a 16-byte aligned leading stride")
+    a = rnd(K, M).t() if amn else rnd(M, K)
+    b = rnd(K, N).t() if bmn else rnd(N, K)
+    out = L.gemm(a, b)
+    close(out, a.float() @ b.float().t(), 2 ** -7, "gemm")
+
+
+def test_gemm_epilogues(ops):
+    from iad_r1_b200 import lib as L
+    torch.manual_seed(1)
+    M, N, K = 384, 520, 264
+    a, b = rnd(M, K), rnd(N, K)
+    want = a.float() @ b.float().t()
+    bias, res = rnd(N), rnd(M, N)
+    close(L.gemm(a, b, bias=bias, residual=res), want + bias.float() + res.float(), 2 ** -7, "bias+residual")
+    close(L.gemm(a, b, alpha=0.25, out_dtype=f32), 0.25 * want, 1e-5, "alpha f32")
+    acc = torch.full((M, N), 2.0, device="cuda")
+    L.gemm(a, b, out=acc, accumulate=True)
+    close(acc, want + 2.0, 1e-5, "accumulate")
+    close(L.gemm(a, b, split_k=3, out_dtype=f32, bias=bias), want + bias.float(), 1e-5, "split-k atomic + bias once")
+    close(L.gemm(a, b, trans_out=True), want.t(), 2 ** -7, "transposed store")
+    w, x = rnd(2048, 1024), rnd(8, 1024)
+    bm = rnd(2048)
+    close(L.gemm(w, x, trans_out=True, split_k=4, out_dtype=f32, block_n=16, bias=bm, bias_per_m=True),
+          x.float() @ w.float().t() + bm.float(), 1e-5, "decode swap-AB")
+
+
+def test_gemm_empty_and_errors(ops):
+    from iad_r1_b200 import lib as L
+    a, b = rnd(0, 64), rnd(16, 64)
+    assert L.gemm(a, b).shape == (0, 16)
+    with pytest.raises(L.NativeLibraryError):
+        L.gemm(rnd(8, 60)[:, :59], rnd(8, 59))  # leading stride not a multiple of 8 elements
+
+
+# ---------------------------------------------------------------------------------------------- norms
+@pytest.mark.parametrize("rows,cols", [(1, 64), (37, 1280), (300, 2048), (16, 3584)])
+def test_rmsnorm(ops, rows, cols):
+    torch.manual_seed(rows)
+    x, w, dy = rnd(rows, cols), (1 + 0.1 * torch.randn(cols, device="cuda")).to(bf16), rnd(rows, cols)
+    eps = 1e-6
+    y, rstd = ops.rmsnorm_fwd(x, w, eps)
+    xf = x.float().requires_grad_(True)
+    wf = w.float().requires_grad_(True)
+    var = xf.pow(2).mean(-1, keepdim=True)
+    ref = wf * (xf * torch.rsqrt(var + eps))
+    close(y, ref, 2 ** -7, "rmsnorm fwd")
+    close(rstd, torch.rsqrt(var + eps).squeeze(-1), 1e-4, "rstd")
+    ref.backward(dy.float())
+    dx = rnd(rows, cols)
+    dx0 = dx.clone()
+    dw = torch.zeros(cols, device="cuda")
+    ops.rmsnorm_bwd(dy, x, w, rstd, dx, dw, add_dx=True)
+    close(dx, dx0.float() + xf.grad, 2 ** -6, "rmsnorm dx (+=)")
+    close(dw, wf.grad, 2e-3, "rmsnorm dw")
+
+
+@pytest.mark.parametrize("rows,cols", [(5, 1280), (129, 1152)])
+def test_layernorm(ops, rows, cols):
+    torch.manual_seed(rows)
+    x, dy = rnd(rows, cols), rnd(rows, cols)
+    w, b = (1 + 0.1 * torch.randn(cols, device="cuda")).to(bf16), rnd(cols, scale=0.1)
+    y, mean, rstd = ops.layernorm_fwd(x, w, b, 1e-6)
+    xf, wf, bf = x.float().requires_grad_(True), w.float().requires_grad_(True), b.float().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xf, (cols,), wf, bf, 1e-6)
+    close(y, ref, 2 ** -7, "layernorm fwd")
+    ref.backward(dy.float())
+    dx, dw, db = torch.empty_like(x), torch.zeros(cols, device="cuda"), torch.zeros(cols, device="cuda")
+    ops.layernorm_bwd(dy, x, w, mean, rstd, dx, dw, db, add_dx=False)
+    close(dx, xf.grad, 2 ** -6, "layernorm dx")
+    close(dw, wf.grad, 2e-3, "layernorm dw")
+    close(db, bf.grad, 2e-3, "layernorm db")
+
+
+# ---------------------------------------------------------------------------------------------- rope / activations
+def _rot_half(x):
+    h = x.shape[-1] // 2
+    return torch.cat((-x[..., h:], x[..., :h]), -1)
+
+
+@pytest.mark.parametrize("hd,bf16_ops", [(128, 1), (80, 0), (64, 1)])
+def test_rope(ops, hd, bf16_ops):
+    torch.manual_seed(hd)
+    tokens, heads, extra = 77, 6, 2
+    x = rnd(tokens, (heads + extra) * hd)
+    ang = torch.rand(tokens, hd // 2, device="cuda") * 50
+    emb = torch.cat((ang, ang), -1)
+    cos, sin = emb.cos().contiguous(), emb.sin().contiguous()
+    x0 = x.clone()
+    ops.rope_(x, cos, sin, heads, hd, bf16_ops)
+    xv = x0.view(tokens, heads + extra, hd)[:, :heads]
+    if bf16_ops:
+        c, s = cos.to(bf16)[:, None], sin.to(bf16)[:, None]
+        ref = (xv * c) + (_rot_half(xv) * s)  # bf16 arithmetic, as HF
+        assert torch.equal(x.view(tokens, heads + extra, hd)[:, :heads], ref), "text rope must be bit-exact vs bf16 torch"
+    else:
+        ref = (xv.float() * cos[:, None] + _rot_half(xv.float()) * sin[:, None]).to(bf16)
+        close(x.view(tokens, heads + extra, hd)[:, :heads], ref, 2 ** -8, "vision rope")
+    assert torch.equal(x.view(tokens, heads + extra, hd)[:, heads:], x0.view(tokens, heads + extra, hd)[:, heads:])
+    # backward = transpose of the rotation: <R x, y> == <x, R^T y>
+    y = rnd(tokens, (heads + extra) * hd)
+    yb = y.clone()
+    ops.rope_(yb, cos, sin, heads, hd, 0, backward=True)
+    xf = x0.clone()
+    ops.rope_(xf, cos, sin, heads, hd, 0)
+    sl = slice(0, heads * hd)
+    lhs = (xf[:, sl].float() * y[:, sl].float()).sum()
+    rhs = (x0[:, sl].float() * yb[:, sl].float()).sum()
+    assert abs(lhs - rhs) <= 2e-2 * abs(lhs) + 1.0
+
+
+@pytest.mark.parametrize("act,gated", [(0, True), (1, False), (2, False), (3, False), (0, False)])
+def test_act_mul(ops, act, gated):
+    torch.manual_seed(act)
+    rows, cols = 45, 1712
+    gu = rnd(rows, cols * (2 if gated else 1))
+    dout = rnd(rows, cols)
+    out = ops.act_mul_fwd(gu, cols, act, gated)
+    g = gu[:, :cols].float().requires_grad_(True)
+    u = gu[:, cols:].float().requires_grad_(True) if gated else None
+    fn = {0: torch.nn.functional.silu, 1: torch.nn.functional.gelu, 2: lambda t: t * torch.sigmoid(1.702 * t),
+          3: lambda t: torch.nn.functional.gelu(t, approximate="tanh")}[act]
+    ref = fn(g) * u if gated else fn(g)
+    close(out, ref, 2 ** -6, "act fwd")
+    ref.backward(dout.float())
+    dgu = ops.act_mul_bwd(dout, gu, cols, act, gated)
+    close(dgu[:, :cols], g.grad, 2 ** -6, "act dgate")
+    if gated:
+        close(dgu[:, cols:], u.grad, 2 ** -6, "act dup")
+
+
+# ---------------------------------------------------------------------------------------------- softmax / gathers
+def test_softmax_rows_and_bwd(ops):
+    torch.manual_seed(3)
+    Z, Tq, Tk = 6, 50, 56
+    S = rnd(Z, Tq, Tk, scale=3.0)
+    S[:, :, 40:] = float("nan")  # never-written tiles must not leak
+    lo = torch.randint(0, 5, (Tq,), device="cuda", dtype=torch.int32)
+    hi = (lo + torch.randint(1, 35, (Tq,), device="cuda", dtype=torch.int32)).to(torch.int32)
+    S0 = S.clone()
+    ops.softmax_rows_(S, lo, hi, Tq, Tk, Tk, Tq * Tk, Z)
+    k = torch.arange(Tk, device="cuda")
+    mask = (k[None, :] >= lo[:, None]) & (k[None, :] < hi[:, None])
+    ref = torch.softmax(torch.nan_to_num(S0.float()).masked_fill(~mask, float("-inf")), -1)
+    close(S, ref, 2 ** -7, "softmax")
+    assert (S.masked_select(~mask.expand(Z, -1, -1)) == 0).all()
+    dP = rnd(Z, Tq, Tk)
+    dP[:, :, 40:] = float("inf")
+    P = S.clone()
+    ops.softmax_bwd_rows_(P, dP, lo, hi, Tq, Tk, Tk, Tq * Tk, Z)
+    dPf = torch.nan_to_num(dP.float(), posinf=0.0)
+    assert torch.isfinite(dP).all()
+
+
+def test_softmax_bwd_values(ops):
+    torch.manual_seed(4)
+    Z, T = 3, 40
+    S = rnd(Z, T, T, scale=2.0)
+    lo = torch.zeros(T, device="cuda", dtype=torch.int32)
+    hi = torch.arange(1, T + 1, device="cuda", dtype=torch.int32)
+    Sf = S.float().requires_grad_(True)
+    mask = torch.tril(torch.ones(T, T, device="cuda", dtype=torch.bool))
+    Pf = torch.softmax(Sf.masked_fill(~mask, float("-inf")), -1)
+    dP = rnd(Z, T, T)
+    Pf.backward(dP.float())
+    P = S.clone()
+    ops.softmax_rows_(P, lo, hi, T, T, T, T * T, Z)
+    d = dP.clone()
+    ops.softmax_bwd_rows_(P, d, lo, hi, T, T, T, T * T, Z)
+    close(d, Sf.grad, 2 ** -5, "softmax bwd")
+
+
+def test_gather_scatter_colsum_groupsum(ops):
+    torch.manual_seed(5)
+    table, alt = rnd(100, 64), rnd(7, 64)
+    index = torch.tensor([3, 99, -1, -7, 0, 3, 3, -2], device="cuda", dtype=torch.int32)
+    out = ops.gather_rows(table, index, alt)
+    ref = torch.stack([table[i] if i >= 0 else alt[-1 - i] for i in index.tolist()])
+    assert torch.equal(out, ref)
+    d = rnd(8, 64)
+    dt, da = torch.zeros(100, 64, device="cuda"), torch.zeros(7, 64, device="cuda")
+    ops.scatter_add_rows(d, index, dt, da)
+    rt, ra = torch.zeros_like(dt), torch.zeros_like(da)
+    for r, i in enumerate(index.tolist()):
+        (rt if i >= 0 else ra)[i if i >= 0 else -1 - i] += d[r].float()
+    close(dt, rt, 1e-5, "scatter table")
+    close(da, ra, 1e-5, "scatter alt")
+    x = rnd(1000, 200)
+    cs = torch.ones(200, device="cuda")
+    ops.colsum(x, cs)
+    close(cs, x.float().sum(0) + 1, 1e-4, "colsum")
+    src = rnd(33, 4 * 3 * 16)
+    dst = torch.zeros(33, 200, dtype=bf16, device="cuda")
+    ops.group_sum(src, dst[:, 8:], 33, 4, 3, 16, src.stride(0), dst.stride(0))
+    close(dst[:, 8:8 + 64], src.view(33, 4, 3, 16).float().sum(2).reshape(33, 64), 2 ** -7, "group_sum")
+
+
+# ---------------------------------------------------------------------------------------------- attention
+@pytest.mark.parametrize("B,T,nq,nkv,hd,causal", [(2, 200, 4, 2, 128, True), (1, 256, 4, 4, 80, False),
+                                                  (3, 72, 6, 2, 16, True), (2, 832, 16, 2, 128, True)])
+def test_attention_fwd_bwd(ops, B, T, nq, nkv, hd, causal):
+    torch.manual_seed(T)
+    sh = ops.AttnShape(B, T, nq, nkv, hd, causal)
+    qkv = rnd(B * T, sh.D, scale=0.7)
+    dattn = rnd(B * T, nq * hd)
+    if causal:
+        lo = torch.zeros(T, device="cuda", dtype=torch.int32)
+        hi = torch.arange(1, T + 1, device="cuda", dtype=torch.int32)
+    else:  # windows of 64 tokens
+        lo = (torch.arange(T, device="cuda") // 64 * 64).to(torch.int32)
+        hi = torch.clamp(lo + 64, max=T).to(torch.int32)
+    attn, P = ops.attention_fwd(qkv, sh, lo, hi)
+    x = qkv.float().view(B, T, nq + 2 * nkv, hd).requires_grad_(True)
+    q, k, v = x[:, :, :nq], x[:, :, nq:nq + nkv], x[:, :, nq + nkv:]
+    kk, vv = k.repeat_interleave(sh.g, 2), v.repeat_interleave(sh.g, 2)
+    s = torch.einsum("bqhd,bkhd->bhqk", q, kk) * sh.scale
+    kidx = torch.arange(T, device="cuda")
+    mask = (kidx[None, :] >= lo[:, None]) & (kidx[None, :] < hi[:, None])
+    p = torch.softmax(s.masked_fill(~mask, float("-inf")), -1)
+    ref = torch.einsum("bhqk,bkhd->bqhd", p, vv).reshape(B * T, nq * hd)
+    close(attn, ref, 2 ** -6, "attention fwd")
+    ref.backward(dattn.float())
+    dqkv = ops.attention_bwd(dattn, qkv, P, sh, lo, hi)
+    close(dqkv, x.grad.reshape(B * T, sh.D), 2 ** -5, "attention bwd")
+
+
+# ---------------------------------------------------------------------------------------------- fused lm_head
+@pytest.mark.parametrize("M,H,V,temp", [(70, 64, 1000, 1.0), (512, 256, 151936, 1.0), (33, 128, 4099 // 8 * 8, 0.9)])
+def test_logprob_fwd_bwd(ops, M, H, V, temp):
+    torch.manual_seed(V)
+    h, E = rnd(M, H), rnd(V, H, scale=0.3)
+    labels = torch.randint(0, V, (M,), device="cuda", dtype=torch.int32)
+    logp, lse = ops.logprob_fwd(h, E, labels, temp)
+    hf, Ef = h.float().requires_grad_(True), E.float().requires_grad_(True)
+    logits = hf @ Ef.t() / temp
+    ref = torch.log_softmax(logits, -1).gather(1, labels.long()[:, None]).squeeze(1)
+    close(lse, torch.logsumexp(logits, -1), 1e-4, "lse")
+    assert (logp - ref).abs().max().item() < 2e-3, "fp32 fused log-prob vs fp32 torch (tolerance 2e-3 abs)"
+    dlogp = torch.randn(M, device="cuda")
+    ref.backward(dlogp)
+    dE = torch.zeros(V, H, device="cuda")
+    dh = ops.logprob_bwd(dlogp, h, E, labels, lse, dE, temp)
+    close(dh, hf.grad, 2 ** -5, "lm_head dh")
+    close(dE, Ef.grad, 2 ** -5, "lm_head dE")
+
+
+# ---------------------------------------------------------------------------------------------- optimizer
+def test_adamw_matches_torch(ops):
+    from iad_r1_b200 import lib as L
+    torch.manual_seed(7)
+    n = 100003
+    p = torch.randn(n, device="cuda")
+    ref = torch.nn.Parameter(p.clone())
+    opt = torch.optim.AdamW([ref], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.1)
+    p32, p16 = p.clone(), p.to(bf16)
+    m, v = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    for step in range(1, 4):
+        g = torch.randn(n, device="cuda") * 3
+        ref.grad = g.clone()
+        torch.nn.utils.clip_grad_norm_([ref], 1.0)
+        opt.step()
+        gbuf = g.clone()
+        ss = torch.zeros(1, device="cuda")
+        L.check(L.lib().iadr1_sumsq_f32(gbuf.data_ptr(), n, ss.data_ptr(), L.stream_ptr()))
+        L.check(L.lib().iadr1_adamw_step(p32.data_ptr(), p16.data_ptr(), gbuf.data_ptr(), m.data_ptr(), v.data_ptr(), n,
+                                         1e-3, 0.9, 0.999, 1e-8, 0.1, step, 1.0, ss.data_ptr(), 1.0, 1, L.stream_ptr()))
+        assert (gbuf == 0).all()
+    close(p32, ref.data, 1e-5, "adamw master weights")
+    assert torch.equal(p16, p32.to(bf16))
+
+
+# ---------------------------------------------------------------------------------------------- sampler
+def test_sampler_support_and_distribution(ops):
+    from iad_r1_b200 import lib as L
+    torch.manual_seed(8)
+    V, rows, c_max = 5000, 64, 4
+    base = torch.randn(V, device="cuda") * 2
+    logits = base.repeat(rows, 1).contiguous()
+    temp, top_k, top_p = 0.9, 50, 0.9
+    # reference support: HF warper order (temperature -> top-k -> top-p)
+    sc = base / temp
+    kth = torch.topk(sc, top_k)[0][-1]
+    sc = sc.masked_fill(sc < kth, float("-inf"))
+    sp, si = torch.sort(sc, descending=False)
+    cum = sp.softmax(-1).cumsum(-1)
+    remove = cum <= (1 - top_p)
+    remove[-1:] = False
+    keep_ids = si[~remove]
+    probs = torch.zeros(V, device="cuda")
+    probs[keep_ids] = torch.softmax(sc[keep_ids], -1)
+    counts = torch.zeros(V, device="cuda")
+    n_draws = 0
+    for seed in range(40):
+        state = torch.tensor([0, 10, rows, 0, 0, 0, 0, 0], device="cuda", dtype=torch.int32)
+        tok = torch.zeros(rows, device="cuda", dtype=torch.int32)
+        fin = torch.zeros(rows, device="cuda", dtype=torch.int32)
+        out = torch.full((rows, c_max), -1, device="cuda", dtype=torch.int32)
+        L.check(L.lib().iadr1_sample(logits.data_ptr(), rows, V, temp, top_k, top_p, seed, state.data_ptr(), tok.data_ptr(),
+                                     fin.data_ptr(), out.data_ptr(), c_max, V + 5, 0, 0, 1, L.stream_ptr()))
+        assert torch.equal(out[:, 0], tok)
+        assert (out[:, 1:] == -1).all()
+        counts += torch.bincount(tok.long(), minlength=V).float()
+        n_draws += rows
+    assert (counts[probs == 0] == 0).all(), "sampled a token outside the top-k/top-p support"
+    emp = counts / n_draws
+    assert (emp - probs).abs().max().item() < 0.03, "empirical frequencies deviate from the warped distribution"
+    # determinism for a fixed (seed, row, step)
+    state = torch.tensor([0, 10, rows, 0, 0, 0, 0, 0], device="cuda", dtype=torch.int32)
+    t1, t2 = torch.zeros(rows, device="cuda", dtype=torch.int32), torch.zeros(rows, device="cuda", dtype=torch.int32)
+    fin = torch.zeros(rows, device="cuda", dtype=torch.int32)
+    out = torch.zeros(rows, c_max, device="cuda", dtype=torch.int32)
+    for t in (t1, t2):
+        fin.zero_()
+        L.check(L.lib().iadr1_sample(logits.data_ptr(), rows, V, temp, top_k, top_p, 123, state.data_ptr(), t.data_ptr(),
+                                     fin.data_ptr(), out.data_ptr(), c_max, V + 5, 0, 0, 1, L.stream_ptr()))
+    assert torch.equal(t1, t2)
+    assert len(set(t1.tolist())) > 1, "rows must draw independently"
