@@ -1,0 +1,172 @@
+"""Model geometry for the VLM families the reference trains. Parsed from an HF `config.json`
+dict (both the transformers 4.51 flat schema the reference pins and the 5.x nested schema), never hard-coded."""
+from __future__ import annotations
+
+from dataclasses import dataclass, field, asdict
+
+
+@dataclass
+class TextConfig:
+    vocab_size: int
+    hidden_size: int
+    intermediate_size: int
+    num_layers: int
+    num_heads: int
+    num_kv_heads: int
+    head_dim: int
+    rms_norm_eps: float = 1e-6
+    rope_theta: float = 1e6
+    mrope_section: tuple = (16, 24, 24)   # () -> plain 1-D rotary (Qwen2 under LLaVA-OneVision)
+    tie_word_embeddings: bool = True
+
+    @property
+    def qkv_dim(self) -> int:
+        return (self.num_heads + 2 * self.num_kv_heads) * self.head_dim
+
+
+@dataclass
+class VisionConfig:
+    kind: str                 # "qwen2_5_vl" (RMSNorm, SwiGLU+bias, windowed attention) | "qwen2_vl" (LayerNorm, quick-GELU MLP)
+    depth: int
+    hidden_size: int
+    num_heads: int
+    intermediate_size: int
+    out_hidden_size: int
+    patch_size: int = 14
+    spatial_merge_size: int = 2
+    temporal_patch_size: int = 2
+    in_channels: int = 3
+    window_size: int = 112
+    fullatt_block_indexes: tuple = (7, 15, 23, 31)
+
+    @property
+    def head_dim(self) -> int:
+        return self.hidden_size // self.num_heads
+
+    @property
+    def patch_dim(self) -> int:
+        return self.in_channels * self.temporal_patch_size * self.patch_size * self.patch_size
+
+    @property
+    def intermediate_padded(self) -> int:
+        """MLP width rounded up to 8 elements so every row / half-row starts 16-byte aligned (3420 -> 3424)."""
+        return (self.intermediate_size + 7) // 8 * 8
+
+
+@dataclass
+class VLMConfig:
+    family: str               # "qwen2_5_vl" | "qwen2_vl"
+    text: TextConfig
+    vision: VisionConfig
+    image_token_id: int = 151655
+    video_token_id: int = 151656
+    vision_start_token_id: int = 151652
+    vision_end_token_id: int = 151653
+    eos_token_id: int = 151645
+    pad_token_id: int = 151643
+    extra: dict = field(default_factory=dict)
+
+    def to_dict(self):
+        return asdict(self)
+
+    # ------------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def from_hf_dict(d: dict) -> "VLMConfig":
+        mt = d.get("model_type", "")
+        if mt not in ("qwen2_5_vl", "qwen2_vl"):
+            raise ValueError(f"unsupported model_type {mt!r} (supported: qwen2_5_vl, qwen2_vl)")
+        t = d.get("text_config") or d
+        rope = t.get("rope_parameters") or t.get("rope_scaling") or d.get("rope_scaling") or {}
+        theta = rope.get("rope_theta", t.get("rope_theta", d.get("rope_theta", 1e6)))
+        nh = t["num_attention_heads"]
+        text = TextConfig(
+            vocab_size=t["vocab_size"], hidden_size=t["hidden_size"], intermediate_size=t["intermediate_size"],
+            num_layers=t["num_hidden_layers"], num_heads=nh, num_kv_heads=t.get("num_key_value_heads", nh),
+            head_dim=t.get("head_dim") or t["hidden_size"] // nh, rms_norm_eps=t.get("rms_norm_eps", 1e-6),
+            rope_theta=float(theta), mrope_section=tuple(rope.get("mrope_section", (16, 24, 24))),
+            tie_word_embeddings=bool(d.get("tie_word_embeddings", t.get("tie_word_embeddings", False))))
+        v = d["vision_config"]
+        if mt == "qwen2_5_vl":
+            vision = VisionConfig(
+                kind="qwen2_5_vl", depth=v["depth"], hidden_size=v["hidden_size"], num_heads=v["num_heads"],
+                intermediate_size=v["intermediate_size"], out_hidden_size=v.get("out_hidden_size", text.hidden_size),
+                patch_size=v.get("patch_size", 14), spatial_merge_size=v.get("spatial_merge_size", 2),
+                temporal_patch_size=v.get("temporal_patch_size", 2), in_channels=v.get("in_channels", v.get("in_chans", 3)),
+                window_size=v.get("window_size", 112), fullatt_block_indexes=tuple(v.get("fullatt_block_indexes", (7, 15, 23, 31))))
+        else:
+            e = v["embed_dim"]
+            vision = VisionConfig(
+                kind="qwen2_vl", depth=v["depth"], hidden_size=e, num_heads=v["num_heads"],
+                intermediate_size=int(e * v.get("mlp_ratio", 4)), out_hidden_size=v.get("hidden_size", text.hidden_size),
+                patch_size=v.get("patch_size", 14), spatial_merge_size=v.get("spatial_merge_size", 2),
+                temporal_patch_size=v.get("temporal_patch_size", 2), in_channels=v.get("in_channels", v.get("in_chans", 3)),
+                window_size=0, fullatt_block_indexes=())
+        return VLMConfig(family=mt, text=text, vision=vision,
+                         image_token_id=d.get("image_token_id", 151655), video_token_id=d.get("video_token_id", 151656),
+                         vision_start_token_id=d.get("vision_start_token_id", 151652),
+                         vision_end_token_id=d.get("vision_end_token_id", 151653),
+                         eos_token_id=d.get("eos_token_id", 151645) if not isinstance(d.get("eos_token_id"), list) else d["eos_token_id"][0],
+                         pad_token_id=d.get("pad_token_id") or 151643)
+
+    def to_hf_dict(self) -> dict:
+        """config.json in the 4.51-era flat schema the reference's `from_pretrained` expects."""
+        t, v = self.text, self.vision
+        d = {
+            "model_type": self.family,
+            "architectures": ["Qwen2_5_VLForConditionalGeneration" if self.family == "qwen2_5_vl" else "Qwen2VLForConditionalGeneration"],
+            "vocab_size": t.vocab_size, "hidden_size": t.hidden_size, "intermediate_size": t.intermediate_size,
+            "num_hidden_layers": t.num_layers, "num_attention_heads": t.num_heads, "num_key_value_heads": t.num_kv_heads,
+            "rms_norm_eps": t.rms_norm_eps, "rope_theta": t.rope_theta,
+            "rope_scaling": {"type": "mrope", "mrope_section": list(t.mrope_section)},
+            "tie_word_embeddings": t.tie_word_embeddings, "hidden_act": "silu", "torch_dtype": "bfloat16",
+            "image_token_id": self.image_token_id, "video_token_id": self.video_token_id,
+            "vision_start_token_id": self.vision_start_token_id, "vision_end_token_id": self.vision_end_token_id,
+            "eos_token_id": self.eos_token_id, "pad_token_id": self.pad_token_id, "max_position_embeddings": 128000,
+        }
+        if self.family == "qwen2_5_vl":
+            d["vision_config"] = {
+                "model_type": "qwen2_5_vl", "depth": v.depth, "hidden_size": v.hidden_size, "num_heads": v.num_heads,
+                "intermediate_size": v.intermediate_size, "out_hidden_size": v.out_hidden_size, "patch_size": v.patch_size,
+                "spatial_merge_size": v.spatial_merge_size, "temporal_patch_size": v.temporal_patch_size,
+                "in_chans": v.in_channels, "window_size": v.window_size, "fullatt_block_indexes": list(v.fullatt_block_indexes),
+                "hidden_act": "silu", "tokens_per_second": 2}
+        else:
+            d["vision_config"] = {
+                "model_type": "qwen2_vl", "depth": v.depth, "embed_dim": v.hidden_size, "num_heads": v.num_heads,
+                "mlp_ratio": v.intermediate_size // v.hidden_size, "hidden_size": v.out_hidden_size,
+                "patch_size": v.patch_size, "spatial_merge_size": v.spatial_merge_size,
+                "temporal_patch_size": v.temporal_patch_size, "in_chans": v.in_channels, "hidden_act": "quick_gelu"}
+        return d
+
+
+# ---- the public checkpoints' geometry (used for synthetic random-init benchmarks) ---------------
+def _qwen25_vision(out_hidden):
+    return VisionConfig(kind="qwen2_5_vl", depth=32, hidden_size=1280, num_heads=16, intermediate_size=3420,
+                        out_hidden_size=out_hidden)
+
+
+PRESETS = {
+    "qwen2.5-vl-3b": lambda: VLMConfig("qwen2_5_vl", TextConfig(151936, 2048, 11008, 36, 16, 2, 128, tie_word_embeddings=True),
+                                       _qwen25_vision(2048)),
+    "qwen2.5-vl-7b": lambda: VLMConfig("qwen2_5_vl", TextConfig(152064, 3584, 18944, 28, 28, 4, 128, tie_word_embeddings=False),
+                                       _qwen25_vision(3584)),
+    "qwen2-vl-2b": lambda: VLMConfig("qwen2_vl", TextConfig(151936, 1536, 8960, 28, 12, 2, 128, tie_word_embeddings=True),
+                                     VisionConfig(kind="qwen2_vl", depth=32, hidden_size=1280, num_heads=16,
+                                                  intermediate_size=5120, out_hidden_size=1536, window_size=0,
+                                                  fullatt_block_indexes=())),
+}
+
+
+def tiny_config(family: str = "qwen2_5_vl") -> VLMConfig:
+    """A few-hundred-k-parameter twin with every structural feature of the real model (GQA, M-RoPE sections, windowed +
+    full vision blocks, ragged MLP width, tied head) - the parity-test geometry (tests/golden)."""
+    text = TextConfig(vocab_size=1024, hidden_size=128, intermediate_size=256, num_layers=2, num_heads=4, num_kv_heads=2,
+                      head_dim=32, mrope_section=(4, 6, 6), tie_word_embeddings=True)
+    if family == "qwen2_5_vl":
+        vis = VisionConfig(kind="qwen2_5_vl", depth=2, hidden_size=64, num_heads=4, intermediate_size=108,
+                           out_hidden_size=128, window_size=56, fullatt_block_indexes=(1,))
+    else:
+        vis = VisionConfig(kind="qwen2_vl", depth=2, hidden_size=64, num_heads=4, intermediate_size=256,
+                           out_hidden_size=128, window_size=0, fullatt_block_indexes=())
+    return VLMConfig(family, text, vis, image_token_id=1001, video_token_id=1002, vision_start_token_id=1003,
+                     vision_end_token_id=1004, eos_token_id=1005, pad_token_id=1006)

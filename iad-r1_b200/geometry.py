@@ -1,0 +1,186 @@
+"""Host-side integer bookkeeping of the VLM forward: M-RoPE position ids, rotary tables, the vision tower's window
+permutation / attention segments / 2-D rotary positions, and the image-token -> image-row index map.
+
+All of this is tiny, data-independent (a function of token ids and `image_grid_thw` only) and runs once per batch;
+results are cached per grid. Semantics follow transformers 4.51.3, the version the reference pins
+(ref: requirements.txt:205), re-stated from the HF sources cited per function.
+"""
+from __future__ import annotations
+
+import functools
+
+import numpy as np
+import torch
+
+from .config import TextConfig, VisionConfig, VLMConfig
+
+
+# ---- M-RoPE position ids (Qwen2_5_VLForConditionalGeneration.get_rope_index, 4.51.3 semantics) ------------------------
+def mrope_position_ids(input_ids: np.ndarray, grid_thw: list, cfg: VLMConfig, attention_mask: np.ndarray | None = None):
+    """input_ids [B, T] int -> (position_ids [3, B, T] int64, rope_deltas [B] int64).
+
+    Text runs count up on all three axes; a still image occupying t*(h/m)*(w/m) tokens from base b gets
+    (b, b + row, b + col); text resumes at max + 1. Masked (pad) positions get 1 (4.51.3 filler, masked anyway).
+    """
+    B, T = input_ids.shape
+    m = cfg.vision.spatial_merge_size
+    pos = np.ones((3, B, T), dtype=np.int64)
+    deltas = np.zeros((B,), dtype=np.int64)
+    img_cursor = 0
+    for b in range(B):
+        keep = np.ones(T, dtype=bool) if attention_mask is None else attention_mask[b].astype(bool)
+        ids = input_ids[b][keep]
+        out = np.zeros((3, len(ids)), dtype=np.int64)
+        i, nxt = 0, 0
+        while i < len(ids):
+            if ids[i] == cfg.image_token_id:
+                t, h, w = grid_thw[img_cursor]
+                img_cursor += 1
+                gh, gw = h // m, w // m
+                n = t * gh * gw
+                if i + n > len(ids) or not (ids[i:i + n] == cfg.image_token_id).all():
+                    raise ValueError("image token span does not match image_grid_thw (prompt truncated into an image?)")
+                tt = np.repeat(np.arange(t), gh * gw) * 0  # still images: temporal index 0 for every token
+                hh = np.tile(np.repeat(np.arange(gh), gw), t)
+                ww = np.tile(np.tile(np.arange(gw), gh), t)
+                out[0, i:i + n] = nxt + tt
+                out[1, i:i + n] = nxt + hh
+                out[2, i:i + n] = nxt + ww
+                nxt = nxt + max(gh, gw, 1 if t > 0 else 0)
+                i += n
+            else:
+                out[:, i] = nxt
+                nxt += 1
+                i += 1
+        pos[:, b, keep] = out
+        deltas[b] = (out.max() + 1 - T) if len(ids) else 0
+    return pos, deltas
+
+
+def text_rope_tables(position_ids: torch.Tensor, t: TextConfig, device):
+    """cos/sin fp32 [B*T, hd] for the decoder. Qwen2_5_VLRotaryEmbedding.forward (modeling_qwen2_5_vl.py:595-608) +
+    the section select of apply_multimodal_rotary_pos_emb (:659-665): band i of the duplicated `mrope_section` list
+    takes its angle from axis i % 3."""
+    pos = position_ids.to(device=device, dtype=torch.float32)  # [3, B, T]
+    hd = t.head_dim
+    inv_freq = 1.0 / (t.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.int64, device=device).float() / hd))
+    freqs = pos[..., None] * inv_freq  # [3, B, T, hd/2]
+    if t.mrope_section:
+        sel = torch.cat([torch.full((s,), i % 3, dtype=torch.long, device=device)
+                         for i, s in enumerate(t.mrope_section)])  # [hd/2] axis per frequency band
+        f = torch.gather(freqs.permute(1, 2, 3, 0), 3, sel.view(1, 1, -1, 1).expand(freqs.shape[1], freqs.shape[2], -1, 1))
+        f = f.squeeze(-1)  # [B, T, hd/2]
+    else:
+        f = freqs[0]
+    emb = torch.cat((f, f), dim=-1).reshape(-1, hd)
+    return emb.cos().contiguous(), emb.sin().contiguous()
+
+
+def decode_rope_table(t: TextConfig, max_pos: int, device):
+    """[max_pos, hd] fp32 tables for the rollout (generated tokens have equal positions on the three axes)."""
+    hd = t.head_dim
+    inv_freq = 1.0 / (t.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.int64, device=device).float() / hd))
+    f = torch.arange(max_pos, device=device, dtype=torch.float32)[:, None] * inv_freq
+    emb = torch.cat((f, f), dim=-1)
+    return emb.cos().contiguous(), emb.sin().contiguous()
+
+
+# ---- vision tower geometry -------------------------------------------------------------------------------------------------
+class VisionGeometry:
+    """Everything the vision tower derives from `image_grid_thw` (Qwen2_5_VisionTransformerPretrainedModel.forward,
+    modeling_qwen2_5_vl.py:455-518; rot_pos_emb :382-409; get_window_index :411-453)."""
+
+    def __init__(self, v: VisionConfig, grid_thw: list, device):
+        m = v.spatial_merge_size
+        unit = m * m
+        self.n_patches = int(sum(t * h * w for t, h, w in grid_thw))
+        self.n_tokens = self.n_patches // unit
+        # 2-D rotary position of each patch, in merge-block-major patch order
+        pos = []
+        for t, h, w in grid_thw:
+            hp = np.arange(h)[:, None].repeat(w, 1).reshape(h // m, m, w // m, m).transpose(0, 2, 1, 3).reshape(-1)
+            wp = np.arange(w)[None, :].repeat(h, 0).reshape(h // m, m, w // m, m).transpose(0, 2, 1, 3).reshape(-1)
+            pos.append(np.tile(np.stack([hp, wp], -1), (t, 1)))
+        pos = np.concatenate(pos, 0)  # [Np, 2]
+        hd = v.head_dim
+        dim = hd // 2
+        inv_freq = 1.0 / (10000.0 ** (np.arange(0, dim, 2, dtype=np.float32) / dim))
+        fr = np.concatenate([pos[:, 0:1] * inv_freq[None], pos[:, 1:2] * inv_freq[None]], -1).astype(np.float32)  # [Np, hd/2]
+        # full-attention segments: one per (image, frame)
+        seg = []
+        for t, h, w in grid_thw:
+            seg += [h * w] * t
+        cu_full = np.concatenate([[0], np.cumsum(seg)]).astype(np.int64)
+        if v.kind == "qwen2_5_vl" and v.window_size > 0:
+            win = v.window_size // m // v.patch_size
+            index, cu_win, base = [], [0], 0
+            for t, h, w in grid_thw:
+                gh, gw = h // m, w // m
+                idx = np.arange(t * gh * gw).reshape(t, gh, gw)
+                ph, pw = win - gh % win, win - gw % win
+                nh, nw = (gh + ph) // win, (gw + pw) // win
+                padded = np.full((t, gh + ph, gw + pw), -100, dtype=np.int64)
+                padded[:, :gh, :gw] = idx
+                padded = padded.reshape(t, nh, win, nw, win).transpose(0, 1, 3, 2, 4).reshape(t, nh * nw, win, win)
+                lens = (padded != -100).sum((2, 3)).reshape(-1)
+                flat = padded.reshape(-1)
+                index.append(flat[flat != -100] + base)
+                cu_win += (np.cumsum(lens) * unit + cu_win[-1]).tolist()
+                base += t * gh * gw
+            window_index = np.concatenate(index)
+            cu_win = np.array(sorted(set(cu_win)), dtype=np.int64)  # unique_consecutive on a non-decreasing list
+            # reorder rotary angles the same way as the hidden states (units of `unit` patches)
+            fr = fr.reshape(self.n_tokens, unit, -1)[window_index].reshape(self.n_patches, -1)
+        else:
+            window_index = None
+            cu_win = cu_full
+        emb = np.concatenate([fr, fr], -1)
+        self.cos = torch.from_numpy(np.cos(emb)).to(device).contiguous()
+        self.sin = torch.from_numpy(np.sin(emb)).to(device).contiguous()
+
+        def ranges(cu):
+            lo = np.zeros(self.n_patches, dtype=np.int32)
+            hi = np.zeros(self.n_patches, dtype=np.int32)
+            for a, b in zip(cu[:-1], cu[1:]):
+                lo[a:b], hi[a:b] = a, b
+            return torch.from_numpy(lo).to(device), torch.from_numpy(hi).to(device)
+
+        self.full_lo, self.full_hi = ranges(cu_full)
+        self.win_lo, self.win_hi = ranges(cu_win)
+        if window_index is not None:
+            self.window_index = torch.from_numpy(window_index.astype(np.int32)).to(device)
+            self.reverse_index = torch.from_numpy(np.argsort(window_index).astype(np.int32)).to(device)
+        else:
+            self.window_index = self.reverse_index = None
+
+
+_GEOM_CACHE: dict = {}
+
+
+def vision_geometry(v: VisionConfig, grid_thw, device) -> VisionGeometry:
+    key = (v.kind, v.window_size, v.spatial_merge_size, v.patch_size, v.head_dim, tuple(map(tuple, grid_thw)), str(device))
+    g = _GEOM_CACHE.get(key)
+    if g is None:
+        if len(_GEOM_CACHE) > 64:
+            _GEOM_CACHE.clear()
+        g = _GEOM_CACHE[key] = VisionGeometry(v, [tuple(int(x) for x in r) for r in grid_thw], device)
+    return g
+
+
+def embed_source_index(input_ids: np.ndarray, image_token_id: int, rows_share_images: bool, n_image_tokens: int):
+    """[B*T] int32: token id for text, -1 - (image embedding row) for image placeholders (`masked_scatter`,
+    modeling_qwen2_5_vl.py:1298-1307). With `rows_share_images` every row consumes the same image rows from 0 (the G
+    completions of one prompt: the reference tiles pixel_values G times, sc_grpo_trainer.py:624-628, we don't)."""
+    B, T = input_ids.shape
+    out = input_ids.astype(np.int64).copy()
+    cursor = 0
+    for b in range(B):
+        is_img = input_ids[b] == image_token_id
+        n = int(is_img.sum())
+        if rows_share_images:
+            cursor = 0
+        if cursor + n > n_image_tokens:
+            raise ValueError(f"image features and image tokens do not match: tokens {cursor + n}, features {n_image_tokens}")
+        out[b, is_img] = -1 - (cursor + np.arange(n))
+        cursor += n
+    return out.reshape(-1).astype(np.int32)

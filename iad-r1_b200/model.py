@@ -1,0 +1,273 @@
+"""The VLM forward / backward, written as explicit kernel sequences over the C ABI (ops.py) - no torch.nn modules,
+no autograd graph, no recompute: every activation the backward needs is kept in HBM (180 GB makes
+`--gradient_checkpointing` unnecessary; DESIGN.md "HBM layout").
+
+This is the B200-native stand-in for `model(**inputs).logits` and autograd's backward over it
+(ref: train/stage_rl/trainer/sc_grpo_trainer.py:505; HF modeling_qwen2_5_vl.py:455-518 vision tower, :778-827 decoder
+layer, :1270-1345 model forward). What it computes per call is the per-token log-prob of given labels (the only thing
+`_get_per_token_logps` keeps, sc_grpo_trainer.py:505-514), never the [B, T, V] logits.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+from .config import VLMConfig
+from .geometry import VisionGeometry, embed_source_index, mrope_position_ids, text_rope_tables, vision_geometry
+from .params import ParamStore
+
+bf16, f32 = torch.bfloat16, torch.float32
+
+
+class VisionCtx:
+    pass
+
+
+class DecoderCtx:
+    pass
+
+
+class VLM:
+    """One set of weights (policy or frozen reference) + the kernel schedules that run over them."""
+
+    def __init__(self, cfg: VLMConfig, params: ParamStore):
+        self.cfg = cfg
+        self.params = params
+        self.p = params.p
+        self.device = params.device
+        self._zero_row = torch.zeros(1, max(cfg.text.hidden_size, cfg.vision.hidden_size), dtype=bf16, device=self.device)
+        self._causal_cache = {}
+
+    @property
+    def g(self):
+        return self.params.g
+
+    def _causal_ranges(self, T):
+        r = self._causal_cache.get(T)
+        if r is None:
+            lo = torch.zeros(T, dtype=torch.int32, device=self.device)
+            hi = torch.arange(1, T + 1, dtype=torch.int32, device=self.device)
+            r = self._causal_cache[T] = (lo, hi)
+        return r
+
+    # =============================================================================================================
+    # vision tower
+    # =============================================================================================================
+    def vision_forward(self, pixel_values: torch.Tensor, grid_thw, save: bool = True):
+        """pixel_values [Np, C*tp*ps*ps] (any float dtype) -> image embeddings [Np/merge^2, H_text] bf16."""
+        v, p = self.cfg.vision, self.p
+        geo = vision_geometry(v, grid_thw, self.device)
+        E, nh, hd, Ip = v.hidden_size, v.num_heads, v.head_dim, v.intermediate_padded
+        unit = v.spatial_merge_size ** 2
+        Np = geo.n_patches
+        if pixel_values.shape[0] != Np:
+            raise ValueError(f"pixel_values has {pixel_values.shape[0]} patches, image_grid_thw implies {Np}")
+        px = pixel_values.to(device=self.device, dtype=bf16).contiguous()
+        x = ops.linear_fwd(px, p["visual.patch_embed.weight"])
+        if geo.window_index is not None:
+            x = ops.gather_rows(x.view(Np // unit, unit * E), geo.window_index).view(Np, E)
+        sh = ops.AttnShape(1, Np, nh, nh, hd, causal=False)
+        ctx = VisionCtx()
+        ctx.geo, ctx.px, ctx.blocks, ctx.sh = geo, px, [], sh
+        q25 = v.kind == "qwen2_5_vl"
+        for i in range(v.depth):
+            b = f"visual.blocks.{i}."
+            full = (not q25) or (i in v.fullatt_block_indexes)
+            lo, hi = (geo.full_lo, geo.full_hi) if full else (geo.win_lo, geo.win_hi)
+            if q25:
+                xn, st1 = ops.rmsnorm_fwd(x, p[b + "norm1.weight"], 1e-6)
+            else:
+                xn, m1, r1 = ops.layernorm_fwd(x, p[b + "norm1.weight"], p[b + "norm1.bias"], 1e-6)
+                st1 = (m1, r1)
+            qkv = ops.linear_fwd(xn, p[b + "qkv.weight"], bias=p[b + "qkv.bias"])
+            ops.rope_(qkv, geo.cos, geo.sin, 2 * nh, hd, bf16_ops=0)
+            attn, P = ops.attention_fwd(qkv, sh, lo, hi)
+            x_mid = ops.linear_fwd(attn, p[b + "proj.weight"], bias=p[b + "proj.bias"], residual=x)
+            if q25:
+                xn2, st2 = ops.rmsnorm_fwd(x_mid, p[b + "norm2.weight"], 1e-6)
+                gu = ops.linear_fwd(xn2, p[b + "gate_up.weight"], bias=p[b + "gate_up.bias"])
+                act = ops.act_mul_fwd(gu, Ip, ops.ACT_SILU, gated=True)
+                x_out = ops.linear_fwd(act, p[b + "down.weight"], bias=p[b + "down.bias"], residual=x_mid)
+            else:
+                xn2, m2, r2 = ops.layernorm_fwd(x_mid, p[b + "norm2.weight"], p[b + "norm2.bias"], 1e-6)
+                st2 = (m2, r2)
+                gu = ops.linear_fwd(xn2, p[b + "fc1.weight"], bias=p[b + "fc1.bias"])
+                act = ops.act_mul_fwd(gu, Ip, ops.ACT_QUICK_GELU, gated=False)
+                x_out = ops.linear_fwd(act, p[b + "fc2.weight"], bias=p[b + "fc2.bias"], residual=x_mid)
+            if save:
+                ctx.blocks.append((x, st1, xn, qkv, P, attn, x_mid, st2, xn2, gu, act, lo, hi))
+            x = x_out
+        if q25:
+            xq, stq = ops.rmsnorm_fwd(x, p["visual.merger.ln_q.weight"], 1e-6)
+        else:
+            xq, mq, rq = ops.layernorm_fwd(x, p["visual.merger.ln_q.weight"], p["visual.merger.ln_q.bias"], 1e-6)
+            stq = (mq, rq)
+        xm = xq.view(Np // unit, unit * E)
+        m1 = ops.linear_fwd(xm, p["visual.merger.fc1.weight"], bias=p["visual.merger.fc1.bias"])
+        a1 = ops.act_mul_fwd(m1, unit * E, ops.ACT_GELU, gated=False)
+        out = ops.linear_fwd(a1, p["visual.merger.fc2.weight"], bias=p["visual.merger.fc2.bias"])
+        if geo.reverse_index is not None:
+            out = ops.gather_rows(out, geo.reverse_index)
+        if save:
+            ctx.x_last, ctx.stq, ctx.xq, ctx.m1, ctx.a1 = x, stq, xq, m1, a1
+        return out, (ctx if save else None)
+
+    def vision_backward(self, d_out: torch.Tensor, ctx: VisionCtx):
+        """Accumulates vision-tower gradients into the fp32 grad buffer given d(image embeddings) bf16."""
+        v, p, g, geo = self.cfg.vision, self.p, self.g, ctx.geo
+        E, nh, hd, Ip = v.hidden_size, v.num_heads, v.head_dim, v.intermediate_padded
+        unit = v.spatial_merge_size ** 2
+        Np = geo.n_patches
+        q25 = v.kind == "qwen2_5_vl"
+        if geo.window_index is not None:
+            d_out = ops.gather_rows(d_out, geo.window_index)  # inverse of the final un-permute
+        da1 = ops.linear_bwd(d_out, ctx.a1, p["visual.merger.fc2.weight"], g["visual.merger.fc2.weight"],
+                             g["visual.merger.fc2.bias"])
+        dm1 = ops.act_mul_bwd(da1, ctx.m1, unit * E, ops.ACT_GELU, gated=False)
+        dxm = ops.linear_bwd(dm1, ctx.xq.view(Np // unit, unit * E), p["visual.merger.fc1.weight"],
+                             g["visual.merger.fc1.weight"], g["visual.merger.fc1.bias"])
+        dx = torch.empty(Np, E, dtype=bf16, device=self.device)
+        if q25:
+            ops.rmsnorm_bwd(dxm.view(Np, E), ctx.x_last, p["visual.merger.ln_q.weight"], ctx.stq, dx,
+                            g["visual.merger.ln_q.weight"], add_dx=False)
+        else:
+            ops.layernorm_bwd(dxm.view(Np, E), ctx.x_last, p["visual.merger.ln_q.weight"], ctx.stq[0], ctx.stq[1], dx,
+                              g["visual.merger.ln_q.weight"], g["visual.merger.ln_q.bias"], add_dx=False)
+        for i in reversed(range(v.depth)):
+            b = f"visual.blocks.{i}."
+            x, st1, xn, qkv, P, attn, x_mid, st2, xn2, gu, act, lo, hi = ctx.blocks[i]
+            if q25:
+                dact = ops.linear_bwd(dx, act, p[b + "down.weight"], g[b + "down.weight"], g[b + "down.bias"])
+                dgu = ops.act_mul_bwd(dact, gu, Ip, ops.ACT_SILU, gated=True, dgu=gu)
+                dxn2 = ops.linear_bwd(dgu, xn2, p[b + "gate_up.weight"], g[b + "gate_up.weight"], g[b + "gate_up.bias"])
+                ops.rmsnorm_bwd(dxn2, x_mid, p[b + "norm2.weight"], st2, dx, g[b + "norm2.weight"], add_dx=True)
+            else:
+                dact = ops.linear_bwd(dx, act, p[b + "fc2.weight"], g[b + "fc2.weight"], g[b + "fc2.bias"])
+                dgu = ops.act_mul_bwd(dact, gu, Ip, ops.ACT_QUICK_GELU, gated=False, dgu=gu)
+                dxn2 = ops.linear_bwd(dgu, xn2, p[b + "fc1.weight"], g[b + "fc1.weight"], g[b + "fc1.bias"])
+                ops.layernorm_bwd(dxn2, x_mid, p[b + "norm2.weight"], st2[0], st2[1], dx, g[b + "norm2.weight"],
+                                  g[b + "norm2.bias"], add_dx=True)
+            dattn = ops.linear_bwd(dx, attn, p[b + "proj.weight"], g[b + "proj.weight"], g[b + "proj.bias"])
+            dqkv = ops.attention_bwd(dattn, qkv, P, ctx.sh, lo, hi)
+            ops.rope_(dqkv, geo.cos, geo.sin, 2 * nh, hd, bf16_ops=0, backward=True)
+            dxn = ops.linear_bwd(dqkv, xn, p[b + "qkv.weight"], g[b + "qkv.weight"], g[b + "qkv.bias"])
+            if q25:
+                ops.rmsnorm_bwd(dxn, x, p[b + "norm1.weight"], st1, dx, g[b + "norm1.weight"], add_dx=True)
+            else:
+                ops.layernorm_bwd(dxn, x, p[b + "norm1.weight"], st1[0], st1[1], dx, g[b + "norm1.weight"],
+                                  g[b + "norm1.bias"], add_dx=True)
+            ctx.blocks[i] = None
+        if geo.reverse_index is not None:
+            dx = ops.gather_rows(dx.view(Np // unit, unit * E), geo.reverse_index).view(Np, E)
+        ops.linear_bwd(dx, ctx.px, p["visual.patch_embed.weight"], g["visual.patch_embed.weight"], need_dx=False)
+
+    # =============================================================================================================
+    # decoder
+    # =============================================================================================================
+    def decoder_forward(self, src_index: torch.Tensor, image_embeds, B: int, T: int, cos, sin, save: bool = True,
+                        kv_sink=None):
+        """src_index [B*T] int32 (token id, or -1-row into image_embeds) -> last hidden states [B*T, H] (pre final norm).
+        kv_sink(layer, qkv) is called with each layer's post-rotary fused qkv buffer (rollout prefill fills its cache)."""
+        t, p = self.cfg.text, self.p
+        H, I, nq, nkv, hd = t.hidden_size, t.intermediate_size, t.num_heads, t.num_kv_heads, t.head_dim
+        h = ops.gather_rows(p["embed_tokens.weight"], src_index, alt=image_embeds)
+        sh = ops.AttnShape(B, T, nq, nkv, hd, causal=True)
+        lo, hi = self._causal_ranges(T)
+        ctx = DecoderCtx()
+        ctx.layers, ctx.sh, ctx.cos, ctx.sin, ctx.src_index = [], sh, cos, sin, src_index
+        for i in range(t.num_layers):
+            b = f"layers.{i}."
+            xn, r1 = ops.rmsnorm_fwd(h, p[b + "ln1.weight"], t.rms_norm_eps, save_rstd=save)
+            qkv = ops.linear_fwd(xn, p[b + "qkv.weight"], bias=p[b + "qkv.bias"])
+            ops.rope_(qkv, cos, sin, nq + nkv, hd, bf16_ops=1)
+            if kv_sink is not None:
+                kv_sink(i, qkv)
+            attn, P = ops.attention_fwd(qkv, sh, lo, hi)
+            h_mid = ops.linear_fwd(attn, p[b + "o.weight"], residual=h)
+            xn2, r2 = ops.rmsnorm_fwd(h_mid, p[b + "ln2.weight"], t.rms_norm_eps, save_rstd=save)
+            gu = ops.linear_fwd(xn2, p[b + "gate_up.weight"])
+            act = ops.act_mul_fwd(gu, I, ops.ACT_SILU, gated=True)
+            h_out = ops.linear_fwd(act, p[b + "down.weight"], residual=h_mid)
+            if save:
+                ctx.layers.append((h, r1, xn, qkv, P, attn, h_mid, r2, xn2, gu, act))
+            h = h_out
+        return h, (ctx if save else None)
+
+    def decoder_backward(self, dh: torch.Tensor, ctx: DecoderCtx, n_image_rows: int):
+        """dh [B*T, H] bf16 (consumed in place). Returns d(image embeddings) fp32 [n_image_rows, H] or None."""
+        t, p, g = self.cfg.text, self.p, self.g
+        I, nq, nkv, hd = t.intermediate_size, t.num_heads, t.num_kv_heads, t.head_dim
+        lo, hi = self._causal_ranges(ctx.sh.T)
+        for i in reversed(range(t.num_layers)):
+            b = f"layers.{i}."
+            h, r1, xn, qkv, P, attn, h_mid, r2, xn2, gu, act = ctx.layers[i]
+            dact = ops.linear_bwd(dh, act, p[b + "down.weight"], g[b + "down.weight"])
+            dgu = ops.act_mul_bwd(dact, gu, I, ops.ACT_SILU, gated=True, dgu=gu)
+            dxn2 = ops.linear_bwd(dgu, xn2, p[b + "gate_up.weight"], g[b + "gate_up.weight"])
+            ops.rmsnorm_bwd(dxn2, h_mid, p[b + "ln2.weight"], r2, dh, g[b + "ln2.weight"], add_dx=True)
+            dattn = ops.linear_bwd(dh, attn, p[b + "o.weight"], g[b + "o.weight"])
+            dqkv = ops.attention_bwd(dattn, qkv, P, ctx.sh, lo, hi)
+            ops.rope_(dqkv, ctx.cos, ctx.sin, nq + nkv, hd, bf16_ops=0, backward=True)
+            dxn = ops.linear_bwd(dqkv, xn, p[b + "qkv.weight"], g[b + "qkv.weight"], g[b + "qkv.bias"])
+            ops.rmsnorm_bwd(dxn, h, p[b + "ln1.weight"], r1, dh, g[b + "ln1.weight"], add_dx=True)
+            ctx.layers[i] = None  # free this layer's activations as the sweep passes
+        dimg = None
+        if n_image_rows > 0:
+            dimg = torch.zeros(n_image_rows, t.hidden_size, dtype=f32, device=self.device)
+        ops.scatter_add_rows(dh, ctx.src_index, g["embed_tokens.weight"], dimg)
+        return dimg
+
+    # =============================================================================================================
+    # per-token log-probs (the whole `_get_per_token_logps`, sc_grpo_trainer.py:502-514)
+    # =============================================================================================================
+    def prepare_batch(self, input_ids, pixel_values, grid_thw, position_ids=None, attention_mask=None):
+        """Host-side prep shared by every forward: M-RoPE positions (4.51.3 semantics), rotary tables, embed index."""
+        ids_np = input_ids.detach().cpu().numpy() if torch.is_tensor(input_ids) else np.asarray(input_ids)
+        B, T = ids_np.shape
+        grid = [tuple(int(x) for x in r) for r in (grid_thw.tolist() if torch.is_tensor(grid_thw) else grid_thw)] \
+            if grid_thw is not None else []
+        unit = self.cfg.vision.spatial_merge_size ** 2
+        n_img_tokens = sum(t * h * w for t, h, w in grid) // unit
+        per_row = int((ids_np[0] == self.cfg.image_token_id).sum()) if B else 0
+        share = B > 1 and per_row == n_img_tokens
+        if position_ids is None:
+            am = attention_mask.detach().cpu().numpy() if torch.is_tensor(attention_mask) else attention_mask
+            g_rows = grid * B if share else grid
+            position_ids, _ = mrope_position_ids(ids_np, g_rows, self.cfg, am)
+            position_ids = torch.from_numpy(position_ids)
+        cos, sin = text_rope_tables(position_ids, self.cfg.text, self.device)
+        src = torch.from_numpy(embed_source_index(ids_np, self.cfg.image_token_id, share, n_img_tokens)).to(self.device)
+        return dict(B=B, T=T, grid=grid, cos=cos, sin=sin, src_index=src, n_img_tokens=n_img_tokens,
+                    pixel_values=pixel_values)
+
+    def logprobs_forward(self, batch: dict, sel_index: torch.Tensor, labels: torch.Tensor, temperature: float = 1.0,
+                         save: bool = True):
+        """log p(labels[j] | prefix) at hidden-state rows sel_index[j] (flattened b*T + t). Returns (logp fp32, ctx)."""
+        img, vctx = (None, None)
+        if batch["n_img_tokens"] > 0:
+            img, vctx = self.vision_forward(batch["pixel_values"], batch["grid"], save=save)
+        h, dctx = self.decoder_forward(batch["src_index"], img, batch["B"], batch["T"], batch["cos"], batch["sin"], save=save)
+        hsel = ops.gather_rows(h, sel_index)
+        hn, rf = ops.rmsnorm_fwd(hsel, self.p["norm.weight"], self.cfg.text.rms_norm_eps, save_rstd=save)
+        logp, lse = ops.logprob_fwd(hn, self.params.lm_head, labels, temperature)
+        ctx = None
+        if save:
+            ctx = dict(vctx=vctx, dctx=dctx, hsel=hsel, hn=hn, rf=rf, lse=lse, labels=labels, sel_index=sel_index,
+                       temperature=temperature, N=batch["B"] * batch["T"], n_img=batch["n_img_tokens"])
+        return logp, ctx
+
+    def logprobs_backward(self, dlogp: torch.Tensor, ctx: dict):
+        """Back-propagates d(loss)/d(logp) [M] through lm_head, decoder and vision tower into the fp32 grad buffer."""
+        t = self.cfg.text
+        dhn = ops.logprob_bwd(dlogp, ctx["hn"], self.params.lm_head, ctx["labels"], ctx["lse"], self.params.lm_head_grad,
+                              ctx["temperature"])
+        dhsel = torch.empty_like(dhn)
+        ops.rmsnorm_bwd(dhn, ctx["hsel"], self.p["norm.weight"], ctx["rf"], dhsel, self.g["norm.weight"], add_dx=False)
+        N = ctx["N"]
+        inv = torch.full((N,), -1, dtype=torch.int32, device=self.device)
+        inv[ctx["sel_index"].long()] = torch.arange(dhsel.shape[0], dtype=torch.int32, device=self.device)
+        dh = ops.gather_rows(dhsel, inv, alt=self._zero_row[:, :t.hidden_size])
+        dimg32 = self.decoder_backward(dh, ctx["dctx"], ctx["n_img"])
+        if dimg32 is not None and ctx["vctx"] is not None:
+            self.vision_backward(ops.cast_f32_bf16(dimg32), ctx["vctx"])

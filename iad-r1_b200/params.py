@@ -1,0 +1,248 @@
+"""Flat parameter storage for the VLM: ONE bf16 buffer holds every weight (16-byte aligned sub-tensors, fused
+q|k|v and gate|up matrices), with matching flat fp32 buffers for gradients, master weights and Adam moments.
+
+Why flat: the gradient all-reduce (the only NCCL call), the global-norm reduction and the fused AdamW
+(csrc/optimizer.cu) each run over one contiguous range instead of ~800 tensors; 180 GB of HBM3e holds policy +
+reference + fp32 master/moments/gradients of the 3B and 7B models without sharding (DESIGN.md "HBM layout").
+
+Names follow the HF checkpoints (`model.language_model.layers.N.self_attn.q_proj.weight` ...), which are exposed
+as *views* of the fused tensors by `hf_named_tensors`, so `from_pretrained`-style directories round-trip.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+
+import torch
+
+from .config import VLMConfig
+
+
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+class ParamStore:
+    def __init__(self, cfg: VLMConfig, device, with_grads: bool = False, with_optimizer: bool = False):
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.shapes: "OrderedDict[str, tuple]" = OrderedDict()
+        self.decay: dict = {}
+        self._declare()
+        # decayed (matrices) first, then non-decayed (norms, biases): two contiguous AdamW ranges.
+        order = [n for n in self.shapes if self.decay[n]] + [n for n in self.shapes if not self.decay[n]]
+        self.offsets = {}
+        off = 0
+        for n in order:
+            self.offsets[n] = off
+            numel = 1
+            for s in self.shapes[n]:
+                numel *= s
+            off += _pad8(numel)
+            if self.decay[n]:
+                self.n_decay = off
+        self.numel = off
+        self.flat = torch.zeros(self.numel, dtype=torch.bfloat16, device=self.device)
+        self.p = self._views(self.flat)
+        self.grad_flat = self.master = self.exp_avg = self.exp_avg_sq = None
+        self.g = None
+        if with_grads:
+            self.grad_flat = torch.zeros(self.numel, dtype=torch.float32, device=self.device)
+            self.g = self._views(self.grad_flat)
+        if with_optimizer:
+            self.master = torch.zeros(self.numel, dtype=torch.float32, device=self.device)
+            self.exp_avg = torch.zeros(self.numel, dtype=torch.float32, device=self.device)
+            self.exp_avg_sq = torch.zeros(self.numel, dtype=torch.float32, device=self.device)
+
+    # ---------------------------------------------------------------------------------------------------------------
+    def _add(self, name, shape, decay):
+        self.shapes[name] = tuple(shape)
+        self.decay[name] = decay
+
+    def _declare(self):
+        t, v = self.cfg.text, self.cfg.vision
+        E, Ip = v.hidden_size, v.intermediate_padded
+        self._add("visual.patch_embed.weight", (E, v.patch_dim), True)
+        for i in range(v.depth):
+            b = f"visual.blocks.{i}."
+            self._add(b + "qkv.weight", (3 * E, E), True)
+            self._add(b + "qkv.bias", (3 * E,), False)
+            self._add(b + "proj.weight", (E, E), True)
+            self._add(b + "proj.bias", (E,), False)
+            self._add(b + "norm1.weight", (E,), False)
+            self._add(b + "norm2.weight", (E,), False)
+            if v.kind == "qwen2_5_vl":
+                self._add(b + "gate_up.weight", (2 * Ip, E), True)
+                self._add(b + "gate_up.bias", (2 * Ip,), False)
+                self._add(b + "down.weight", (E, Ip), True)
+                self._add(b + "down.bias", (E,), False)
+            else:
+                self._add(b + "norm1.bias", (E,), False)
+                self._add(b + "norm2.bias", (E,), False)
+                self._add(b + "fc1.weight", (Ip, E), True)
+                self._add(b + "fc1.bias", (Ip,), False)
+                self._add(b + "fc2.weight", (E, Ip), True)
+                self._add(b + "fc2.bias", (E,), False)
+        m = v.spatial_merge_size ** 2 * E
+        self._add("visual.merger.ln_q.weight", (E,), False)
+        if v.kind == "qwen2_vl":
+            self._add("visual.merger.ln_q.bias", (E,), False)
+        self._add("visual.merger.fc1.weight", (m, m), True)
+        self._add("visual.merger.fc1.bias", (m,), False)
+        self._add("visual.merger.fc2.weight", (v.out_hidden_size, m), True)
+        self._add("visual.merger.fc2.bias", (v.out_hidden_size,), False)
+        self._add("embed_tokens.weight", (t.vocab_size, t.hidden_size), True)
+        for i in range(t.num_layers):
+            b = f"layers.{i}."
+            self._add(b + "qkv.weight", (t.qkv_dim, t.hidden_size), True)
+            self._add(b + "qkv.bias", (t.qkv_dim,), False)
+            self._add(b + "o.weight", (t.hidden_size, t.num_heads * t.head_dim), True)
+            self._add(b + "gate_up.weight", (2 * t.intermediate_size, t.hidden_size), True)
+            self._add(b + "down.weight", (t.hidden_size, t.intermediate_size), True)
+            self._add(b + "ln1.weight", (t.hidden_size,), False)
+            self._add(b + "ln2.weight", (t.hidden_size,), False)
+        self._add("norm.weight", (t.hidden_size,), False)
+        if not t.tie_word_embeddings:
+            self._add("lm_head.weight", (t.vocab_size, t.hidden_size), True)
+
+    def _views(self, flat):
+        out = {}
+        for n, shape in self.shapes.items():
+            numel = 1
+            for s in shape:
+                numel *= s
+            out[n] = flat[self.offsets[n]: self.offsets[n] + numel].view(shape)
+        return out
+
+    @property
+    def lm_head(self):
+        return self.p["embed_tokens.weight"] if self.cfg.text.tie_word_embeddings else self.p["lm_head.weight"]
+
+    @property
+    def lm_head_grad(self):
+        return self.g["embed_tokens.weight"] if self.cfg.text.tie_word_embeddings else self.g["lm_head.weight"]
+
+    # ---------------------------------------------------------------------------------------------------------------
+    def hf_named_tensors(self, which: str = "p"):
+        """Yield (HF checkpoint name, view) pairs: fused tensors are split back into q/k/v, gate/up; MLP padding dropped.
+        Names use the 4.51-era layout (`visual.*`, `model.*`, `lm_head.weight`)."""
+        src = {"p": self.p, "g": self.g}[which]
+        t, v = self.cfg.text, self.cfg.vision
+        E, I, Ip = v.hidden_size, v.intermediate_size, v.intermediate_padded
+        yield "visual.patch_embed.proj.weight", src["visual.patch_embed.weight"]
+        for i in range(v.depth):
+            b, hb = f"visual.blocks.{i}.", f"visual.blocks.{i}."
+            yield hb + "attn.qkv.weight", src[b + "qkv.weight"]
+            yield hb + "attn.qkv.bias", src[b + "qkv.bias"]
+            yield hb + "attn.proj.weight", src[b + "proj.weight"]
+            yield hb + "attn.proj.bias", src[b + "proj.bias"]
+            yield hb + "norm1.weight", src[b + "norm1.weight"]
+            yield hb + "norm2.weight", src[b + "norm2.weight"]
+            if v.kind == "qwen2_5_vl":
+                yield hb + "mlp.gate_proj.weight", src[b + "gate_up.weight"][:I]
+                yield hb + "mlp.up_proj.weight", src[b + "gate_up.weight"][Ip:Ip + I]
+                yield hb + "mlp.gate_proj.bias", src[b + "gate_up.bias"][:I]
+                yield hb + "mlp.up_proj.bias", src[b + "gate_up.bias"][Ip:Ip + I]
+                yield hb + "mlp.down_proj.weight", src[b + "down.weight"][:, :I]
+                yield hb + "mlp.down_proj.bias", src[b + "down.bias"]
+            else:
+                yield hb + "norm1.bias", src[b + "norm1.bias"]
+                yield hb + "norm2.bias", src[b + "norm2.bias"]
+                yield hb + "mlp.fc1.weight", src[b + "fc1.weight"][:I]
+                yield hb + "mlp.fc1.bias", src[b + "fc1.bias"][:I]
+                yield hb + "mlp.fc2.weight", src[b + "fc2.weight"][:, :I]
+                yield hb + "mlp.fc2.bias", src[b + "fc2.bias"]
+        yield "visual.merger.ln_q.weight", src["visual.merger.ln_q.weight"]
+        if v.kind == "qwen2_vl":
+            yield "visual.merger.ln_q.bias", src["visual.merger.ln_q.bias"]
+        yield "visual.merger.mlp.0.weight", src["visual.merger.fc1.weight"]
+        yield "visual.merger.mlp.0.bias", src["visual.merger.fc1.bias"]
+        yield "visual.merger.mlp.2.weight", src["visual.merger.fc2.weight"]
+        yield "visual.merger.mlp.2.bias", src["visual.merger.fc2.bias"]
+        yield "model.embed_tokens.weight", src["embed_tokens.weight"]
+        nq, nkv, hd = t.num_heads * t.head_dim, t.num_kv_heads * t.head_dim, t.head_dim
+        Ti = t.intermediate_size
+        for i in range(t.num_layers):
+            b, hb = f"layers.{i}.", f"model.layers.{i}."
+            w, bi = src[b + "qkv.weight"], src[b + "qkv.bias"]
+            yield hb + "self_attn.q_proj.weight", w[:nq]
+            yield hb + "self_attn.k_proj.weight", w[nq:nq + nkv]
+            yield hb + "self_attn.v_proj.weight", w[nq + nkv:]
+            yield hb + "self_attn.q_proj.bias", bi[:nq]
+            yield hb + "self_attn.k_proj.bias", bi[nq:nq + nkv]
+            yield hb + "self_attn.v_proj.bias", bi[nq + nkv:]
+            yield hb + "self_attn.o_proj.weight", src[b + "o.weight"]
+            yield hb + "mlp.gate_proj.weight", src[b + "gate_up.weight"][:Ti]
+            yield hb + "mlp.up_proj.weight", src[b + "gate_up.weight"][Ti:]
+            yield hb + "mlp.down_proj.weight", src[b + "down.weight"]
+            yield hb + "input_layernorm.weight", src[b + "ln1.weight"]
+            yield hb + "post_attention_layernorm.weight", src[b + "ln2.weight"]
+        yield "model.norm.weight", src["norm.weight"]
+        if not t.tie_word_embeddings:
+            yield "lm_head.weight", src["lm_head.weight"]
+
+    @staticmethod
+    def canonical_name(name: str) -> str:
+        """Map transformers-5.x key names (`model.visual.*`, `model.language_model.*`) onto the 4.51 layout."""
+        if name.startswith("model.visual."):
+            return name[len("model."):]
+        if name.startswith("model.language_model."):
+            return "model." + name[len("model.language_model."):]
+        return name
+
+    def load_hf_state_dict(self, sd: dict, strict: bool = True):
+        """Copy an HF state dict (either key layout, any float dtype, any device) into the flat bf16 buffer."""
+        sd = {self.canonical_name(k): v for k, v in sd.items()}
+        missing = []
+        with torch.no_grad():
+            for name, view in self.hf_named_tensors("p"):
+                if name not in sd:
+                    if name == "lm_head.weight" or not strict:
+                        continue
+                    missing.append(name)
+                    continue
+                src = sd[name]
+                if name == "visual.patch_embed.proj.weight":
+                    src = src.reshape(src.shape[0], -1)
+                if tuple(src.shape) != tuple(view.shape):
+                    raise ValueError(f"{name}: checkpoint shape {tuple(src.shape)} != model shape {tuple(view.shape)}")
+                view.copy_(src.to(device=self.device, dtype=torch.bfloat16))
+        if missing:
+            raise KeyError(f"checkpoint is missing {len(missing)} tensors, e.g. {missing[:4]}")
+        self.sync_master()
+
+    def hf_state_dict(self) -> dict:
+        sd = {}
+        for name, view in self.hf_named_tensors("p"):
+            tns = view.detach().clone().contiguous()
+            if name == "visual.patch_embed.proj.weight":
+                v = self.cfg.vision
+                tns = tns.view(v.hidden_size, v.in_channels, v.temporal_patch_size, v.patch_size, v.patch_size)
+            sd[name] = tns
+        return sd
+
+    def init_random(self, seed: int = 0, std: float = 0.02):
+        """HF `_init_weights` convention: N(0, std) matrices/embeddings, unit norms, zero biases."""
+        gen = torch.Generator(device=self.device).manual_seed(seed)
+        with torch.no_grad():
+            self.flat.zero_()
+            for name, view in self.hf_named_tensors("p"):
+                if name.endswith("bias"):
+                    continue
+                if "norm" in name or "ln_q" in name:
+                    view.fill_(1.0)
+                else:
+                    view.copy_(torch.empty(view.shape, dtype=torch.float32, device=self.device)
+                               .normal_(0.0, std, generator=gen).to(torch.bfloat16))
+        self.sync_master()
+
+    def sync_master(self):
+        if self.master is not None:
+            self.master.copy_(self.flat.float())
+
+    def copy_from(self, other: "ParamStore"):
+        self.flat.copy_(other.flat)
+        self.sync_master()
+
+    def zero_grad(self):
+        if self.grad_flat is not None:
+            self.grad_flat.zero_()

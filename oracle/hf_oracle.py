@@ -1,0 +1,87 @@
+"""ORACLE (test infrastructure, never on the product path): the HF Transformers implementation the reference executes
+for `model(**inputs).logits` (ref: train/stage_rl/trainer/sc_grpo_trainer.py:117-137 `from_pretrained`, :505 forward),
+built from an explicit config with seeded random weights and run on CPU.
+
+The model arithmetic is NOT in /root/reference: it lives in the third-party dependency `transformers==4.51.3`
+(ref: requirements.txt:205), absent from the repo; this container has transformers 5.5.0, whose Qwen2-VL / Qwen2.5-VL
+modules compute the same function given explicit `position_ids` (SURVEY.md §8c lists the version-skew traps; we
+always pass 4.51.3-semantics position ids). Parity status: the reference's own tests hold no golden vectors for this
+path ("parity unpinned") - the pins are (a) this HF implementation run here, frozen into
+tests/golden/*.pt by oracle/make_golden.py, and (b) the KATs of the vendored TRL helpers (oracle/grpo_ref.py).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module.
+"""
+from __future__ import annotations
+
+import torch
+
+
+def hf_config(cfg, attn_implementation="eager"):
+    """iad_r1_b200.config.VLMConfig -> transformers config object (5.x nested schema)."""
+    t, v = cfg.text, cfg.vision
+    text = dict(vocab_size=t.vocab_size, hidden_size=t.hidden_size, intermediate_size=t.intermediate_size,
+                num_hidden_layers=t.num_layers, num_attention_heads=t.num_heads, num_key_value_heads=t.num_kv_heads,
+                max_position_embeddings=32768, rms_norm_eps=t.rms_norm_eps, tie_word_embeddings=t.tie_word_embeddings,
+                rope_parameters=dict(rope_type="default", rope_theta=t.rope_theta, mrope_section=list(t.mrope_section)))
+    common = dict(image_token_id=cfg.image_token_id, video_token_id=cfg.video_token_id,
+                  vision_start_token_id=cfg.vision_start_token_id, vision_end_token_id=cfg.vision_end_token_id,
+                  tie_word_embeddings=t.tie_word_embeddings)
+    if cfg.family == "qwen2_5_vl":
+        from transformers import Qwen2_5_VLConfig
+        vis = dict(depth=v.depth, hidden_size=v.hidden_size, intermediate_size=v.intermediate_size, num_heads=v.num_heads,
+                   out_hidden_size=v.out_hidden_size, patch_size=v.patch_size, spatial_merge_size=v.spatial_merge_size,
+                   temporal_patch_size=v.temporal_patch_size, window_size=v.window_size,
+                   fullatt_block_indexes=list(v.fullatt_block_indexes), in_channels=v.in_channels)
+        c = Qwen2_5_VLConfig(text_config=text, vision_config=vis, **common)
+    else:
+        from transformers import Qwen2VLConfig
+        vis = dict(depth=v.depth, embed_dim=v.hidden_size, hidden_size=v.out_hidden_size, num_heads=v.num_heads,
+                   mlp_ratio=v.intermediate_size // v.hidden_size, patch_size=v.patch_size,
+                   spatial_merge_size=v.spatial_merge_size, temporal_patch_size=v.temporal_patch_size,
+                   in_channels=v.in_channels)
+        c = Qwen2VLConfig(text_config=text, vision_config=vis, **common)
+    c._attn_implementation = attn_implementation
+    return c
+
+
+def build_hf_model(cfg, seed=0, dtype=torch.float32, attn_implementation="eager"):
+    """Random-init HF model (initializer_range 0.02, HF `_init_weights`), weights rounded to bf16 values so that the
+    fp32 oracle and the bf16 product path hold bit-identical parameters."""
+    if cfg.family == "qwen2_5_vl":
+        from transformers import Qwen2_5_VLForConditionalGeneration as Cls
+    else:
+        from transformers import Qwen2VLForConditionalGeneration as Cls
+    torch.manual_seed(seed)
+    m = Cls(hf_config(cfg, attn_implementation))
+    with torch.no_grad():
+        gen = torch.Generator().manual_seed(seed + 1)
+        for n, p in m.named_parameters():
+            if n.endswith("bias"):
+                p.copy_(torch.randn(p.shape, generator=gen) * 0.02)       # non-zero biases exercise the bias paths
+            elif p.dim() == 1:
+                p.copy_(1.0 + 0.1 * torch.randn(p.shape, generator=gen))  # norm gains away from 1
+            p.copy_(p.to(torch.bfloat16).to(p.dtype))
+    return m.to(dtype).eval()
+
+
+def hf_logits(model, input_ids, pixel_values, grid_thw, position_ids, attention_mask=None):
+    """`model(**inputs).logits` with explicit 4.51.3-semantics position ids."""
+    kw = dict(input_ids=input_ids, position_ids=position_ids, use_cache=False)
+    if attention_mask is not None:
+        kw["attention_mask"] = attention_mask
+    if pixel_values is not None:
+        kw["pixel_values"] = pixel_values.to(next(model.parameters()).dtype)
+        kw["image_grid_thw"] = grid_thw
+    return model(**kw).logits
+
+
+def per_token_logps(logits, input_ids):
+    """Restates `_get_per_token_logps` (sc_grpo_trainer.py:505-514): drop the last logit, row-wise log_softmax + gather,
+    in the dtype of `logits` (the reference runs it in bf16; call with fp32 logits for the tight oracle)."""
+    logits = logits[:, :-1, :]
+    ids = input_ids[:, 1:]
+    out = []
+    for lr, ir in zip(logits, ids):
+        lp = lr.log_softmax(dim=-1)
+        out.append(torch.gather(lp, 1, ir.unsqueeze(1)).squeeze(1))
+    return torch.stack(out)
