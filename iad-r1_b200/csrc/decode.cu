@@ -23,7 +23,7 @@ using bf16 = __nv_bfloat16;
 // Device-resident rollout state (int32 words). Host writes it once per rollout.
 enum StateWord : int {
   ST_STEP = 0,       // index of the completion token fed this step (KV slot); logits predict token ST_STEP + 1
-  ST_PROMPT_LEN = 1, // P
+  ST_RESERVED = 1,
   ST_UNFINISHED = 2, // rows that have not produced EOS yet (host polls for early exit)
   ST_WORDS = 8
 };
@@ -65,16 +65,17 @@ __global__ void rmsnorm_f32in_kernel(const float* __restrict__ x, const bf16* __
 }
 
 // qkv f32 [R, (nq + 2 nkv) * hd] (bias already added) -> rotary on q,k (HF bf16 op order) -> q bf16 [R, nq*hd],
-// k,v appended to the row's completion slab at slot ST_STEP. Position = P + step + rope_delta[row].
+// k,v appended to the row's completion slab at slot ST_STEP. Position = P[row] + step + rope_delta[row].
 __global__ void decode_rope_append_kernel(const float* __restrict__ qkv, const float* __restrict__ cos_tab,
                                           const float* __restrict__ sin_tab, const int* __restrict__ rope_delta,
-                                          const int* __restrict__ state, bf16* __restrict__ q_out,
+                                          const int* __restrict__ row_plen, const int* __restrict__ state,
+                                          bf16* __restrict__ q_out,
                                           bf16* __restrict__ kc, bf16* __restrict__ vc, int nq, int nkv, int hd,
                                           int c_max, int max_pos) {
   const int r = blockIdx.x;
   const int head = blockIdx.y;  // [0,nq) q, [nq,nq+nkv) k, [nq+nkv, nq+2nkv) v
   const int step = state[ST_STEP];
-  int pos = state[ST_PROMPT_LEN] + step + rope_delta[r];
+  int pos = row_plen[r] + step + rope_delta[r];
   pos = max(0, min(max_pos - 1, pos));
   const int qkv_dim = (nq + 2 * nkv) * hd;
   const float* src = qkv + (long long)r * qkv_dim + (long long)head * hd;
@@ -103,13 +104,13 @@ template <int HD>
 __global__ void __launch_bounds__(128) decode_attn_partial_kernel(
     const bf16* __restrict__ q, const bf16* __restrict__ kp, const bf16* __restrict__ vp, const bf16* __restrict__ kc,
     const bf16* __restrict__ vc, const int* __restrict__ state, const int* __restrict__ row_group,
-    float* __restrict__ part, int nq, int nkv, int p_max, int c_max, int chunk, float scale) {
+    const int* __restrict__ row_plen, float* __restrict__ part, int nq, int nkv, int p_max, int c_max, int chunk, float scale) {
   constexpr int DPL = HD / 32;  // dims per lane
   constexpr int MAXG = 8;
   const int r = blockIdx.x, kvh = blockIdx.y, sp = blockIdx.z, nsplit = gridDim.z;
   const int gq = nq / nkv;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int P = state[ST_PROMPT_LEN];
+  const int P = row_plen[r];
   const int ctx = P + state[ST_STEP] + 1;
   const int k0 = sp * chunk, k1 = min(ctx, k0 + chunk);
   const int grp = row_group[r];
@@ -370,17 +371,17 @@ int iadr1_rmsnorm_f32in(const float* x, const void* w, void* y, int rows, int co
 }
 
 int iadr1_decode_rope_append(const float* qkv, const float* cos_tab, const float* sin_tab, const int* rope_delta,
-                             const int* state, void* q_out, void* kc, void* vc, int rows, int nq, int nkv, int hd,
+                             const int* row_plen, const int* state, void* q_out, void* kc, void* vc, int rows, int nq, int nkv, int hd,
                              int c_max, int max_pos, void* stream) {
   if (rows <= 0) return 0;
   decode_rope_append_kernel<<<dim3(rows, nq + 2 * nkv), 64, 0, (cudaStream_t)stream>>>(
-      qkv, cos_tab, sin_tab, rope_delta, state, (bf16*)q_out, (bf16*)kc, (bf16*)vc, nq, nkv, hd, c_max, max_pos);
+      qkv, cos_tab, sin_tab, rope_delta, row_plen, state, (bf16*)q_out, (bf16*)kc, (bf16*)vc, nq, nkv, hd, c_max, max_pos);
   IADR1_CHECK_LAUNCH("decode_rope_append");
   return 0;
 }
 
 int iadr1_decode_attention(const void* q, const void* kp, const void* vp, const void* kc, const void* vc,
-                           const int* state, const int* row_group, float* part, void* out, int rows, int nq, int nkv,
+                           const int* state, const int* row_group, const int* row_plen, float* part, void* out, int rows, int nq, int nkv,
                            int hd, int p_max, int c_max, int nsplit, float scale, void* stream) {
   if (rows <= 0) return 0;
   if (nq % nkv || nq / nkv > 8) return set_error("decode_attention: group size %d unsupported (max 8)", nq / nkv);
@@ -388,13 +389,13 @@ int iadr1_decode_attention(const void* q, const void* kp, const void* vp, const 
   cudaStream_t st = (cudaStream_t)stream;
   if (hd == 128) {
     decode_attn_partial_kernel<128><<<dim3(rows, nkv, nsplit), 128, 0, st>>>(
-        (const bf16*)q, (const bf16*)kp, (const bf16*)vp, (const bf16*)kc, (const bf16*)vc, state, row_group, part, nq,
+        (const bf16*)q, (const bf16*)kp, (const bf16*)vp, (const bf16*)kc, (const bf16*)vc, state, row_group, row_plen, part, nq,
         nkv, p_max, c_max, chunk, scale);
     IADR1_CHECK_LAUNCH("decode_attn_partial");
     decode_attn_combine_kernel<128><<<rows * nq, 128, 0, st>>>(part, (bf16*)out, nsplit);
   } else if (hd == 64) {
     decode_attn_partial_kernel<64><<<dim3(rows, nkv, nsplit), 128, 0, st>>>(
-        (const bf16*)q, (const bf16*)kp, (const bf16*)vp, (const bf16*)kc, (const bf16*)vc, state, row_group, part, nq,
+        (const bf16*)q, (const bf16*)kp, (const bf16*)vp, (const bf16*)kc, (const bf16*)vc, state, row_group, row_plen, part, nq,
         nkv, p_max, c_max, chunk, scale);
     IADR1_CHECK_LAUNCH("decode_attn_partial");
     decode_attn_combine_kernel<64><<<rows * nq, 64, 0, st>>>(part, (bf16*)out, nsplit);

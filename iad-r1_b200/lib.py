@@ -129,7 +129,7 @@ def _mat(t: torch.Tensor, what: str):
 
 def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None, *, bias=None, residual=None,
          alpha: float = 1.0, accumulate: bool = False, out_dtype=torch.bfloat16, split_k: int = 1,
-         trans_out: bool = False, bias_per_m: bool = False, block_n: int = 0, stages: int = 0,
+         atomic: bool | None = None, trans_out: bool = False, bias_per_m: bool = False, block_n: int = 0, stages: int = 0,
          max_ctas: int = 0) -> torch.Tensor:
     """out[M,N] (+)= alpha * a[M,K] @ b[N,K]^T (+ bias) (+ residual).
 
@@ -151,11 +151,14 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None, *, b
     d.B, d.ldb, d.b_mn = _mat(b, "b")
     if out.stride(1) != 1:
         raise ValueError("out must be row-major")
+    if tuple(out.shape) != ((N, M) if trans_out else (M, N)):
+        raise ValueError(f"out has shape {tuple(out.shape)}, expected {(N, M) if trans_out else (M, N)}")
     d.C, d.ldc = out.data_ptr(), out.stride(0)
     d.c_f32 = 1 if out.dtype == torch.float32 else 0
     d.trans_c = int(trans_out)
-    d.accumulate = int(accumulate and split_k == 1)
-    d.atomic = int(split_k > 1)
+    atomic = (split_k > 1) if atomic is None else atomic
+    d.accumulate = int(accumulate and not atomic)
+    d.atomic = int(atomic)
     d.split_k = split_k
     d.alpha = alpha
     d.bias, d.bias_per_m = _ptr(bias), int(bias_per_m)

@@ -1,0 +1,206 @@
+"""In-rank rollout engine: prefill once per prompt, fork the KV prefix G ways, decode all rows of all in-flight groups
+in lock-step through one CUDA-graph-captured step.
+
+Replaces the reference's dedicated-GPU vLLM engine and its per-step weight copy
+(ref: train/stage_rl/trainer/sc_grpo_trainer.py:314-358 engine, :569-579 `_move_model_to_vllm`, :643-677 generate):
+  * weights are read IN PLACE from the live training buffer - no policy->engine sync (SURVEY.md K20 eliminated);
+  * the prompt (ViT + prefill) runs once per group and its K/V are shared by the G rows (what vLLM's
+    `enable_prefix_caching=True`, :351, achieves by hashing);
+  * several groups decode together so each weight byte streamed from HBM serves G x n_groups rows;
+  * sampler contract = SamplingParams(temperature, top_p=0.9, top_k=50, max_tokens=C), :353-358.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import lib as L
+from . import ops
+from .geometry import decode_rope_table
+
+bf16, f32, i32 = torch.bfloat16, torch.float32, torch.int32
+NUM_SMS = 148
+
+
+def _split_for(m_feat: int, k: int) -> int:
+    tiles = (m_feat + 127) // 128
+    nkb = (k + 63) // 64
+    return max(1, min(nkb, NUM_SMS // max(tiles, 1)))
+
+
+class RolloutEngine:
+    def __init__(self, vlm, max_groups: int, num_generations: int, p_max: int, c_max: int, temperature: float = 0.9,
+                 top_k: int = 50, top_p: float = 0.9, forbid_eos: bool = False, use_cuda_graph: bool = True):
+        if top_k is None or top_k <= 0 or top_k > 128:
+            raise ValueError("rollout sampler supports 1 <= top_k <= 128 (reference uses top_k=50)")
+        self.vlm, self.cfg = vlm, vlm.cfg
+        t = self.cfg.text
+        self.G, self.n_groups = num_generations, max_groups
+        self.R = R = max_groups * num_generations
+        if R > 256:
+            raise ValueError("at most 256 rows decode together (one UMMA N tile)")
+        self.p_max, self.c_max = p_max, c_max
+        self.temperature, self.top_k, self.top_p, self.forbid_eos = temperature, top_k, top_p, forbid_eos
+        self.use_graph = use_cuda_graph
+        dev = vlm.device
+        Lyr, nkv, hd, H, I, V = t.num_layers, t.num_kv_heads, t.head_dim, t.hidden_size, t.intermediate_size, t.vocab_size
+        self.kp = torch.zeros(Lyr, max_groups, p_max, nkv, hd, dtype=bf16, device=dev)
+        self.vp = torch.zeros_like(self.kp)
+        self.kc = torch.zeros(Lyr, R, c_max, nkv, hd, dtype=bf16, device=dev)
+        self.vc = torch.zeros_like(self.kc)
+        self.state = torch.zeros(8, dtype=i32, device=dev)
+        self.tok = torch.zeros(R, dtype=i32, device=dev)
+        self.finished = torch.zeros(R, dtype=i32, device=dev)
+        self.out_tokens = torch.zeros(R, c_max, dtype=i32, device=dev)
+        self.rope_delta = torch.zeros(R, dtype=i32, device=dev)
+        self.row_plen = torch.zeros(R, dtype=i32, device=dev)
+        self.row_group = (torch.arange(R, device=dev) // num_generations).to(i32)
+        self.h = torch.zeros(R, H, dtype=f32, device=dev)
+        self.xn = torch.zeros(R, H, dtype=bf16, device=dev)
+        self.qkv = torch.zeros(R, t.qkv_dim, dtype=f32, device=dev)
+        self.q = torch.zeros(R, t.num_heads * hd, dtype=bf16, device=dev)
+        self.attn = torch.zeros(R, t.num_heads * hd, dtype=bf16, device=dev)
+        self.nsplit = max(1, min(32, (p_max + c_max + 63) // 64))
+        self.part = torch.zeros(R, t.num_heads, self.nsplit, hd + 2, dtype=f32, device=dev)
+        self.gu = torch.zeros(R, 2 * I, dtype=bf16, device=dev)
+        self.act = torch.zeros(R, I, dtype=bf16, device=dev)
+        self.logits = torch.zeros(R, V, dtype=f32, device=dev)
+        self.max_pos = p_max + c_max + 8
+        self.cos_tab, self.sin_tab = decode_rope_table(t, self.max_pos, dev)
+        self.block_n = max(16, ops.ceil_to(R, 16))
+        self._graph = None
+        self._seed = 0
+
+    # ---------------------------------------------------------------------------------------------------------------
+    def _skinny(self, W, x, out, split_k=1, atomic=False, bias=None):
+        """out[R, F] (+)= x[R, K] @ W[F, K]^T with W as the 128-row MMA operand (swap-AB), transposed store."""
+        L.gemm(W, x, out=out, trans_out=True, split_k=split_k, atomic=atomic or split_k > 1, bias=bias, bias_per_m=True,
+               block_n=self.block_n)
+
+    def _head_and_sample(self, first: int):
+        t, p, lib = self.cfg.text, self.vlm.p, L.lib()
+        s = L.stream_ptr()
+        L.check(lib.iadr1_rmsnorm_f32in(self.h.data_ptr(), p["norm.weight"].data_ptr(), self.xn.data_ptr(), self.R,
+                                        t.hidden_size, t.rms_norm_eps, s), "rmsnorm_f32in")
+        self._skinny(self.vlm.params.lm_head, self.xn, self.logits)
+        L.check(lib.iadr1_sample(self.logits.data_ptr(), self.R, t.vocab_size, self.temperature, self.top_k, self.top_p,
+                                 self._seed, self.state.data_ptr(), self.tok.data_ptr(), self.finished.data_ptr(),
+                                 self.out_tokens.data_ptr(), self.c_max, self.cfg.eos_token_id, self.cfg.pad_token_id,
+                                 int(self.forbid_eos), first, s), "sample")
+
+    def _decode_step(self):
+        t, p, lib = self.cfg.text, self.vlm.p, L.lib()
+        R, H, I, nq, nkv, hd = self.R, t.hidden_size, t.intermediate_size, t.num_heads, t.num_kv_heads, t.head_dim
+        s = L.stream_ptr()
+        L.check(lib.iadr1_decode_embed(p["embed_tokens.weight"].data_ptr(), self.tok.data_ptr(), self.h.data_ptr(), R, H, s),
+                "decode_embed")
+        sk_qkv, sk_o, sk_d = _split_for(t.qkv_dim, H), _split_for(H, nq * hd), _split_for(H, I)
+        for i in range(t.num_layers):
+            b = f"layers.{i}."
+            L.check(lib.iadr1_rmsnorm_f32in(self.h.data_ptr(), p[b + "ln1.weight"].data_ptr(), self.xn.data_ptr(), R, H,
+                                            t.rms_norm_eps, s), "rmsnorm_f32in")
+            self.qkv.zero_()
+            self._skinny(p[b + "qkv.weight"], self.xn, self.qkv, split_k=sk_qkv, atomic=True, bias=p[b + "qkv.bias"])
+            L.check(lib.iadr1_decode_rope_append(self.qkv.data_ptr(), self.cos_tab.data_ptr(), self.sin_tab.data_ptr(),
+                                                 self.rope_delta.data_ptr(), self.row_plen.data_ptr(), self.state.data_ptr(),
+                                                 self.q.data_ptr(), self.kc[i].data_ptr(), self.vc[i].data_ptr(), R, nq, nkv,
+                                                 hd, self.c_max, self.max_pos, s), "decode_rope_append")
+            L.check(lib.iadr1_decode_attention(self.q.data_ptr(), self.kp[i].data_ptr(), self.vp[i].data_ptr(),
+                                               self.kc[i].data_ptr(), self.vc[i].data_ptr(), self.state.data_ptr(),
+                                               self.row_group.data_ptr(), self.row_plen.data_ptr(), self.part.data_ptr(),
+                                               self.attn.data_ptr(), R, nq, nkv, hd, self.p_max, self.c_max, self.nsplit,
+                                               float(hd) ** -0.5, s), "decode_attention")
+            self._skinny(p[b + "o.weight"], self.attn, self.h, split_k=sk_o, atomic=True)        # h += attn @ Wo^T
+            L.check(lib.iadr1_rmsnorm_f32in(self.h.data_ptr(), p[b + "ln2.weight"].data_ptr(), self.xn.data_ptr(), R, H,
+                                            t.rms_norm_eps, s), "rmsnorm_f32in")
+            self._skinny(p[b + "gate_up.weight"], self.xn, self.gu)
+            ops.act_mul_fwd(self.gu, I, ops.ACT_SILU, gated=True, out=self.act)
+            self._skinny(p[b + "down.weight"], self.act, self.h, split_k=sk_d, atomic=True)      # h += mlp
+        self._head_and_sample(first=0)
+        L.check(lib.iadr1_decode_advance(self.state.data_ptr(), s), "decode_advance")
+
+    # ---------------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def generate(self, prompts: list, seed: int = 0, max_new_tokens: int | None = None, sync_every: int = 32):
+        """prompts: list (<= max_groups) of dicts {input_ids [P] (list/array), pixel_values, grid_thw}.
+        Returns (completion_ids int32 [n_groups_used * G, C] on device, stats dict)."""
+        n = len(prompts)
+        if n == 0 or n > self.n_groups:
+            raise ValueError(f"need 1..{self.n_groups} prompts, got {n}")
+        C = self.c_max if max_new_tokens is None else min(max_new_tokens, self.c_max)
+        t, vlm, G = self.cfg.text, self.vlm, self.G
+        self._seed = int(seed)
+        self.state.zero_()
+        self.finished.zero_()
+        self.out_tokens.fill_(self.cfg.pad_token_id)
+        plen = np.zeros(self.R, dtype=np.int32)
+        delta = np.zeros(self.R, dtype=np.int32)
+        # ---- prefill: one sequence per group through the training forward kernels; K/V land in the shared prefix cache
+        for gi, pr in enumerate(prompts):
+            ids = np.asarray(pr["input_ids"], dtype=np.int64).reshape(1, -1)
+            P = ids.shape[1]
+            if P > self.p_max:
+                raise ValueError(f"prompt of {P} tokens exceeds p_max={self.p_max}")
+            batch = vlm.prepare_batch(ids, pr.get("pixel_values"), pr.get("grid_thw"))
+            img = None
+            if batch["n_img_tokens"] > 0:
+                img, _ = vlm.vision_forward(batch["pixel_values"], batch["grid"], save=False)
+            nq, nkv, hd = t.num_heads, t.num_kv_heads, t.head_dim
+
+            def sink(layer, qkv, gi=gi, P=P):
+                kv = qkv.view(P, nq + 2 * nkv, hd)
+                self.kp[layer, gi, :P].copy_(kv[:, nq:nq + nkv])
+                self.vp[layer, gi, :P].copy_(kv[:, nq + nkv:])
+
+            h, _ = vlm.decoder_forward(batch["src_index"], img, 1, P, batch["cos"], batch["sin"], save=False, kv_sink=sink)
+            self.h[gi * G:(gi + 1) * G].copy_(h[P - 1].float()[None, :].expand(G, -1))
+            plen[gi * G:(gi + 1) * G] = P
+            # rope delta (max position + 1 - P): generated token k sits at position P + k + delta on all three axes
+            from .geometry import mrope_position_ids
+            _, d = mrope_position_ids(ids, batch["grid"], self.cfg)
+            delta[gi * G:(gi + 1) * G] = int(d[0])
+        for gi in range(n, self.n_groups):  # unused groups: mark rows finished so they only emit pad
+            self.finished[gi * G:(gi + 1) * G] = 1
+            plen[gi * G:(gi + 1) * G] = 1
+        self.row_plen.copy_(torch.from_numpy(plen))
+        self.rope_delta.copy_(torch.from_numpy(delta))
+        self.state[2] = n * G
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        self._head_and_sample(first=1)
+        # ---- decode: C - 1 replays of the captured step
+        if self.use_graph and self._graph is None:
+            self._capture()
+        steps_done = 0
+        for sidx in range(C - 1):
+            if self._graph is not None:
+                self._graph.replay()
+            else:
+                self._decode_step()
+            steps_done += 1
+            if not self.forbid_eos and sync_every and (sidx + 1) % sync_every == 0:
+                if int(self.state[2].item()) <= 0:
+                    break
+        ev1.record()
+        torch.cuda.synchronize()
+        out = self.out_tokens[: n * G, :C].clone()
+        ms = ev0.elapsed_time(ev1)
+        return out, dict(decode_ms=ms, steps=steps_done + 1, rows=n * G)
+
+    def _capture(self):
+        """Warm up once on a side stream (also sets kernel attributes / fills the tensor-map cache), then capture.
+        The captured step is position-independent: step / tokens / lengths are read from device memory."""
+        snap = (self.state.clone(), self.tok.clone(), self.finished.clone(), self.out_tokens.clone(), self.h.clone())
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self._decode_step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.state.copy_(snap[0]); self.tok.copy_(snap[1]); self.finished.copy_(snap[2])
+        self.out_tokens.copy_(snap[3]); self.h.copy_(snap[4])
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._decode_step()
+        # the capture pass did not execute; state is as restored above
+        self._graph = g
