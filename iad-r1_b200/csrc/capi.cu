@@ -27,4 +27,13 @@ int iadr1_gemm_bf16(const iadr1_gemm_t* d, void* stream) {
   return iadr1::launch_gemm(*d, static_cast<cudaStream_t>(stream));
 }
 int iadr1_gemm_pick_block_n(int N, int b_mn) { return iadr1::pick_block_n_public(N, b_mn); }
+int iadr1_gemm_profile_enable(int on) {
+  iadr1::gemm_profile_enable(on);
+  return 0;
+}
+int iadr1_gemm_profile_collect(double* total_ms, double* total_flops, double* max_launch_ms, long long* launches) {
+  const long long n = iadr1::gemm_profile_collect(total_ms, total_flops, max_launch_ms);
+  if (launches) *launches = n;
+  return 0;
+}
 }

@@ -18,6 +18,7 @@
 #include "runtime.h"
 
 #include <map>
+#include <vector>
 #include <mutex>
 #include <tuple>
 #include <cstring>
@@ -470,6 +471,63 @@ static int pick_block_n(int N, int b_mn) {
   return best;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Optional per-launch timing (bench.py's live roofline): CUDA events around every GEMM launch that is not being
+// captured into a graph, plus the algorithmic FLOPs of the launch. Off by default.
+// ------------------------------------------------------------------------------------------------
+struct GemmProf {
+  bool enabled = false;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  std::vector<double> flops;
+  std::mutex mu;
+};
+static GemmProf g_prof;
+
+static bool prof_begin(cudaStream_t stream, cudaEvent_t* e0, cudaEvent_t* e1) {
+  if (!g_prof.enabled) return false;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return false;
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  if (g_prof.used + 2 > g_prof.pool.size()) {
+    const size_t old = g_prof.pool.size();
+    g_prof.pool.resize(old + 4096);
+    for (size_t i = old; i < g_prof.pool.size(); ++i) cudaEventCreate(&g_prof.pool[i]);
+  }
+  *e0 = g_prof.pool[g_prof.used++];
+  *e1 = g_prof.pool[g_prof.used++];
+  cudaEventRecord(*e0, stream);
+  return true;
+}
+
+void gemm_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  g_prof.enabled = on != 0;
+  g_prof.used = 0;
+  g_prof.flops.clear();
+}
+
+// Caller must have synchronised the device. Returns the number of timed launches.
+long long gemm_profile_collect(double* total_ms, double* total_flops, double* max_launch_ms) {
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  double ms = 0, fl = 0, mx = 0;
+  const size_t n = g_prof.used / 2;
+  for (size_t i = 0; i < n; ++i) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, g_prof.pool[2 * i], g_prof.pool[2 * i + 1]) == cudaSuccess) {
+      ms += t;
+      if (t > mx) mx = t;
+      fl += g_prof.flops[i];
+    }
+  }
+  if (total_ms) *total_ms = ms;
+  if (total_flops) *total_flops = fl;
+  if (max_launch_ms) *max_launch_ms = mx;
+  g_prof.used = 0;
+  g_prof.flops.clear();
+  return (long long)n;
+}
+
 int pick_block_n_public(int N, int b_mn) { return pick_block_n(N, b_mn); }
 
 int launch_gemm(const iadr1_gemm_t& d, cudaStream_t stream) {
@@ -546,7 +604,17 @@ int launch_gemm(const iadr1_gemm_t& d, cudaStream_t stream) {
   const long long total = (long long)tiles_m * tiles_n * g.split_k * g.batch;
   int grid = (int)(total < (long long)num_sms() ? total : num_sms());
   if (d.max_ctas > 0 && grid > d.max_ctas) grid = d.max_ctas;
+  cudaEvent_t pe0, pe1;
+  const bool timed = prof_begin(stream, &pe0, &pe1);
   gemm_bf16_tcgen05_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, g);
+  if (timed) {
+    cudaEventRecord(pe1, stream);
+    // algorithmic FLOPs: causal products count only the unmasked half
+    double fl = 2.0 * (double)g.M * (double)g.N * (double)g.K * (double)g.batch;
+    if (g.kmode != 0 || g.skip_mode != 0) fl *= 0.5;
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    g_prof.flops.push_back(fl);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("gemm launch failed: %s", cudaGetErrorString(e));
   count_launch();

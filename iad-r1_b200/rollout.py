@@ -70,6 +70,8 @@ class RolloutEngine:
         self.block_n = max(16, ops.ceil_to(R, 16))
         self._graph = None
         self._seed = 0
+        self.replays = 0            # graph replays so far (bench.py counts kernels = replays * kernels_per_step)
+        self.kernels_per_step = 0
 
     # ---------------------------------------------------------------------------------------------------------------
     def _skinny(self, W, x, out, split_k=1, atomic=False, bias=None):
@@ -121,7 +123,8 @@ class RolloutEngine:
 
     # ---------------------------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def generate(self, prompts: list, seed: int = 0, max_new_tokens: int | None = None, sync_every: int = 32):
+    def generate(self, prompts: list, seed: int = 0, max_new_tokens: int | None = None, sync_every: int = 32,
+                 logits_hook=None):
         """prompts: list (<= max_groups) of dicts {input_ids [P] (list/array), pixel_values, grid_thw}.
         Returns (completion_ids int32 [n_groups_used * G, C] on device, stats dict)."""
         n = len(prompts)
@@ -168,15 +171,21 @@ class RolloutEngine:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         self._head_and_sample(first=1)
+        if logits_hook is not None:
+            logits_hook(0, self.logits)
         # ---- decode: C - 1 replays of the captured step
-        if self.use_graph and self._graph is None:
+        use_graph = self.use_graph and logits_hook is None
+        if use_graph and self._graph is None:
             self._capture()
         steps_done = 0
         for sidx in range(C - 1):
-            if self._graph is not None:
+            if use_graph:
                 self._graph.replay()
+                self.replays += 1
             else:
                 self._decode_step()
+                if logits_hook is not None:
+                    logits_hook(sidx + 1, self.logits)
             steps_done += 1
             if not self.forbid_eos and sync_every and (sidx + 1) % sync_every == 0:
                 if int(self.state[2].item()) <= 0:
@@ -193,8 +202,10 @@ class RolloutEngine:
         snap = (self.state.clone(), self.tok.clone(), self.finished.clone(), self.out_tokens.clone(), self.h.clone())
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
+        n0 = L.launch_count()
         with torch.cuda.stream(side):
             self._decode_step()
+        self.kernels_per_step = L.launch_count() - n0
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.state.copy_(snap[0]); self.tok.copy_(snap[1]); self.finished.copy_(snap[2])

@@ -1,0 +1,453 @@
+"""`SCGRPOTrainer`: the reference's trainer surface (constructor signature, `.train()`, `.save_model()`, `.log()`,
+`.state`, `._metrics`, reward-callback convention) over the B200-native hot path.
+
+Mirrors ref: train/stage_rl/trainer/sc_grpo_trainer.py:72-373 (ctor), :586-819 (`compute_loss`), :821-827 (`log`) and
+the parts of `transformers.Trainer.training_step` / DeepSpeed it relied on (backward, 1/GA loss scaling because
+`model_accepts_loss_kwargs=False` :292-295, clip at `max_grad_norm`, AdamW, linear LR decay, seed-42 shuffling sharded
+per rank). What changed underneath: rollout = in-rank RolloutEngine instead of a vLLM GPU (K19, K20, C3),
+log-probs = fused kernels instead of HF modules + [G,T,V] logits (K1-K15), backward = hand-written kernels (K17),
+optimizer = fused flat AdamW (K18), ZeRO-3 traffic = ONE gradient all-reduce per optimizer step (C1 -> C2).
+The group-relative advantage, KL and loss stay in Python (grpo_loss.py).
+"""
+from __future__ import annotations
+
+import json
+import math
+import os
+import time
+import warnings
+from collections import defaultdict
+from typing import Any, Callable, Optional, Union
+
+import numpy as np
+import torch
+
+from . import grpo_loss
+from . import lib as L
+from .checkpoint import load_pretrained, save_pretrained
+from .config import VLMConfig
+from .grpo_config import GRPOConfig
+from .model import VLM
+from .params import ParamStore
+from .rollout import RolloutEngine
+
+RewardFunc = Union[str, Callable[[list, list], list]]
+
+
+class TrainerState:
+    def __init__(self):
+        self.global_step = 0
+        self.epoch = 0.0
+        self.max_steps = 0
+        self.log_history: list = []
+        self.num_input_tokens_seen = 0
+
+
+def is_conversational(example: dict) -> bool:
+    """ref: trl/trl/data_utils.py:30-68."""
+    for key in ("prompt", "chosen", "rejected", "completion", "messages"):
+        v = example.get(key)
+        if isinstance(v, list) and v and isinstance(v[0], dict) and "role" in v[0] and "content" in v[0]:
+            return True
+    return False
+
+
+def maybe_apply_chat_template(example: dict, processing_class) -> dict:
+    """Prompt-only branch of ref: trl/trl/data_utils.py:71-200."""
+    if is_conversational(example):
+        return {"prompt": processing_class.apply_chat_template(example["prompt"], tokenize=False, add_generation_prompt=True)}
+    return {"prompt": example["prompt"]}
+
+
+class _LogProbFn(torch.autograd.Function):
+    """Bridges torch autograd (the Python loss) and the CUDA forward/backward: `loss.backward()` in unchanged Python
+    drives model.logprobs_backward."""
+
+    @staticmethod
+    def forward(ctx, anchor, vlm, batch, rows, labels, temperature):
+        logp, saved = vlm.logprobs_forward(batch, rows, labels, temperature, save=True)
+        ctx.vlm, ctx.saved = vlm, saved
+        return logp
+
+    @staticmethod
+    def backward(ctx, dlogp):
+        ctx.vlm.logprobs_backward(dlogp.contiguous(), ctx.saved)
+        ctx.saved = None
+        return None, None, None, None, None, None
+
+
+class SCGRPOTrainer:
+    def __init__(self, model, reward_funcs, args: GRPOConfig = None, train_dataset=None, eval_dataset=None,
+                 processing_class=None, reward_processing_classes=None, callbacks=None, optimizers=(None, None),
+                 peft_config=None, max_pixels: Optional[int] = 12845056, min_pixels: Optional[int] = 3136,
+                 attn_implementation: str = "flash_attention_2", use_vllm_for_gen: bool = True):
+        if args is None:
+            name = model if isinstance(model, str) else getattr(model, "family", "model")
+            args = GRPOConfig(f"{str(name).split('/')[-1]}-GRPO")
+        if peft_config is not None:
+            raise NotImplementedError("peft_config: LoRA is outside the B200 hot path (SURVEY.md §8f)")
+        if optimizers != (None, None):
+            raise ValueError("custom optimizers are not supported: the fused flat AdamW is part of the hot path")
+        self.args = args
+        self.state = TrainerState()
+        self._metrics = defaultdict(list)
+        self._setup_distributed()
+        torch.manual_seed(args.seed)
+        np.random.seed(args.seed)
+
+        # ---- model / reference ----------------------------------------------------------------------------------------
+        if isinstance(model, str):
+            self.model_id = model
+            mid = model.lower()
+            families = ("qwen2-vl", "qwen2_vl", "qwen2vl", "qwen2.5-vl", "qwen2.5_vl", "qwen2.5vl")
+            if not any(k in mid for k in families):
+                # the reference raises ValueError for unknown families (sc_grpo_trainer.py:141-144); LLaVA families: §8f
+                raise ValueError(f"Unsupported model: {model} (B200 path supports Qwen2-VL / Qwen2.5-VL)")
+            self.cfg, self.params = load_pretrained(model, self.device)
+        elif isinstance(model, VLMConfig):
+            self.model_id = model.family
+            self.cfg = model
+            self.params = ParamStore(model, self.device, with_grads=True, with_optimizer=True)
+            self.params.init_random(seed=args.seed)
+        elif isinstance(model, ParamStore):
+            self.model_id, self.cfg, self.params = model.cfg.family, model.cfg, model
+        else:
+            raise ValueError("model must be a checkpoint path, a VLMConfig (random init) or a ParamStore")
+        if self.params.grad_flat is None or self.params.master is None:
+            raise ValueError("the policy ParamStore needs with_grads=True, with_optimizer=True")
+        self.model = VLM(self.cfg, self.params)
+        self.beta = args.beta
+        # Q11: the reference always builds a frozen copy of the initial policy (sc_grpo_trainer.py:152-182). With
+        # beta == 0 its only use (beta * KL) vanishes, so it is skipped and `kl` is logged as 0.
+        if self.beta != 0.0:
+            ref_store = ParamStore(self.cfg, self.device)
+            ref_store.copy_from(self.params)
+            self.ref_model = VLM(self.cfg, ref_store)
+        else:
+            self.ref_model = None
+
+        # ---- processor ----------------------------------------------------------------------------------------------------
+        if processing_class is None:
+            if not isinstance(model, str):
+                raise ValueError("processing_class is required when the model is not a checkpoint path")
+            from transformers import AutoProcessor
+            processing_class = AutoProcessor.from_pretrained(model)
+            tok = getattr(processing_class, "tokenizer", processing_class)
+            processing_class.pad_token_id = tok.pad_token_id
+            processing_class.eos_token_id = tok.eos_token_id
+            if hasattr(processing_class, "image_processor"):
+                processing_class.image_processor.max_pixels = max_pixels
+                processing_class.image_processor.min_pixels = min_pixels
+        self.processing_class = processing_class
+
+        # ---- rewards ------------------------------------------------------------------------------------------------------
+        if not isinstance(reward_funcs, list):
+            reward_funcs = [reward_funcs]
+        for rf in reward_funcs:
+            if not callable(rf):
+                raise NotImplementedError("reward *models* (str / PreTrainedModel) are not supported; pass callables "
+                                          "(sc_grpo_trainer.py:232-236 branch, SURVEY.md §8f item 4)")
+        self.reward_funcs = reward_funcs
+        self.reward_processing_classes = reward_processing_classes or [None] * len(reward_funcs)
+
+        self.max_prompt_length = args.max_prompt_length
+        self.max_completion_length = args.max_completion_length
+        self.num_generations = args.num_generations
+        self.use_vllm = use_vllm_for_gen  # kept for surface compatibility; generation always runs in-rank
+        self.train_dataset, self.eval_dataset = train_dataset, eval_dataset
+        self.callbacks = callbacks or []
+        self._engine: Optional[RolloutEngine] = None
+        self._rollout_cache: dict = {}
+        self._sumsq = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._opt_step = 0
+        self.phase_ms = defaultdict(float)
+        self._timers = []
+        self.total_rollout_tokens = 0
+        for flag, val in (("deepspeed", args.deepspeed), ("gradient_checkpointing", args.gradient_checkpointing)):
+            if val and self.is_main:
+                print(f"[iadr1-b200] note: --{flag} is accepted for script compatibility and ignored "
+                      f"(plain data parallel, all activations resident in HBM)")
+
+    # ---------------------------------------------------------------------------------------------------------------
+    def _setup_distributed(self):
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.is_main = self.rank == 0
+        if not torch.cuda.is_available():
+            raise L.NativeLibraryError("SCGRPOTrainer needs a CUDA device: the hot path has no CPU fallback")
+        torch.cuda.set_device(local)
+        self.device = torch.device("cuda", local)
+        if self.world > 1 and not torch.distributed.is_initialized():
+            import datetime
+            torch.distributed.init_process_group("nccl", timeout=datetime.timedelta(seconds=self.args.ddp_timeout),
+                                                 device_id=self.device)
+        L.lib()
+
+    def _phase(self, name):
+        trainer = self
+
+        class _T:
+            def __enter__(self_inner):
+                self_inner.e0 = torch.cuda.Event(enable_timing=True)
+                self_inner.e1 = torch.cuda.Event(enable_timing=True)
+                self_inner.e0.record()
+
+            def __exit__(self_inner, *a):
+                self_inner.e1.record()
+                trainer._timers.append((name, self_inner.e0, self_inner.e1))
+
+        return _T()
+
+    def flush_timers(self):
+        torch.cuda.synchronize()
+        for name, e0, e1 in self._timers:
+            self.phase_ms[name] += e0.elapsed_time(e1)
+        self._timers = []
+
+    # ---------------------------------------------------------------------------------------------------------------
+    # prompt encoding + rollout
+    # ---------------------------------------------------------------------------------------------------------------
+    def _encode_prompt(self, example: dict) -> dict:
+        from PIL import Image
+        text = maybe_apply_chat_template(example, self.processing_class)["prompt"]
+        images = []
+        img = example.get("image")
+        if img is not None:
+            for im in (img if isinstance(img, list) else [img]):
+                images.append(Image.open(im) if isinstance(im, str) else im)
+        enc = self.processing_class(text=[text], images=images if images else None, return_tensors="pt", padding=True,
+                                    padding_side="left", add_special_tokens=False)
+        ids = enc["input_ids"][0]
+        if "attention_mask" in enc:
+            ids = ids[enc["attention_mask"][0].bool()]
+        if self.max_prompt_length is not None:
+            ids = ids[-self.max_prompt_length:]  # Q14: ids only; cutting into image tokens raises downstream
+        pv = enc.get("pixel_values")
+        if pv is not None and not pv.is_cuda:
+            pv = pv.pin_memory().to(self.device, non_blocking=True)   # pinned staging -> async H2D
+        return dict(input_ids=ids.numpy().astype(np.int64), pixel_values=pv,
+                    grid_thw=enc["image_grid_thw"].tolist() if "image_grid_thw" in enc else None, text=text)
+
+    def _engine_for(self, n_groups: int, p_len: int) -> RolloutEngine:
+        e = self._engine
+        p_need = (p_len + 63) // 64 * 64
+        if e is None or e.n_groups < n_groups or e.p_max < p_need:
+            a = self.args
+            self._engine = e = RolloutEngine(self.model, n_groups, self.num_generations, max(p_need, e.p_max if e else 0),
+                                             self.max_completion_length, temperature=a.temperature, top_k=a.rollout_top_k,
+                                             top_p=a.rollout_top_p, forbid_eos=a.rollout_forbid_eos)
+        return e
+
+    def _rollout(self, encoded: list) -> list:
+        """Sample G completions for each encoded prompt in ONE decode batch. Returns a list of [G, C] int32 tensors."""
+        eng = self._engine_for(len(encoded), max(len(e["input_ids"]) for e in encoded))
+        seed = self.args.rollout_seed if self.args.rollout_seed is not None else self.args.seed
+        seed = (seed * 1000003 + self.state.global_step * 8191 + self.rank * 131 + self._rollout_calls) & 0x7FFFFFFF
+        self._rollout_calls += 1
+        with self._phase("rollout"):
+            out, stats = eng.generate(encoded, seed=seed)
+        G = self.num_generations
+        self.total_rollout_tokens += out.numel()
+        return [out[i * G:(i + 1) * G] for i in range(len(encoded))]
+
+    _rollout_calls = 0
+
+    def prepare_window(self, examples: list):
+        """Batched-rollout mode: roll out every group of the coming accumulation window together (the weights they are
+        sampled from are the weights at the start of the optimizer step, as in the reference: Q12)."""
+        enc = [self._encode_prompt(ex) for ex in examples]
+        comps = self._rollout(enc)
+        for ex, e, c in zip(examples, enc, comps):
+            self._rollout_cache[id(ex)] = (e, c)
+
+    # ---------------------------------------------------------------------------------------------------------------
+    # the hot path: one micro-step (ref: sc_grpo_trainer.py:586-819)
+    # ---------------------------------------------------------------------------------------------------------------
+    def compute_loss(self, model=None, inputs=None, return_outputs=False, num_items_in_batch=None):
+        if return_outputs:
+            raise ValueError("The GRPOTrainer does not support returning outputs")
+        losses = []
+        for example in inputs:
+            losses.append(self._group_loss(example))
+        return torch.stack(losses).mean()
+
+    def _group_loss(self, example: dict) -> torch.Tensor:
+        G, dev, a = self.num_generations, self.device, self.args
+        cached = self._rollout_cache.pop(id(example), None)
+        if cached is None:
+            enc = self._encode_prompt(example)
+            completion_ids = self._rollout([enc])[0]
+        else:
+            enc, completion_ids = cached
+        prompt_ids = enc["input_ids"]
+        P, C = len(prompt_ids), completion_ids.shape[1]
+        T = P + C
+        comp_long = completion_ids.long()
+        mask = grpo_loss.completion_mask(comp_long, self.processing_class.eos_token_id)          # :722-726
+        ids = torch.cat([torch.from_numpy(prompt_ids).to(dev)[None, :].expand(G, -1), comp_long], 1)  # :681-683
+        batch = self.model.prepare_batch(ids, enc["pixel_values"], enc["grid_thw"])
+        rows = (torch.arange(G, device=dev)[:, None] * T + (P - 1) + torch.arange(C, device=dev)[None, :]).reshape(-1).to(torch.int32)
+        labels = completion_ids.reshape(-1).to(torch.int32).contiguous()
+        temp = a.temperature if a.loss_mode == "clip" else 1.0   # Q1: SC mode does not temperature-scale the logits
+        anchor = torch.zeros((), device=dev, requires_grad=True)
+        with self._phase("policy_fwd"):
+            logps = _LogProbFn.apply(anchor, self.model, batch, rows, labels, temp).view(G, C)      # :733-735
+        if self.ref_model is not None:
+            with torch.no_grad(), self._phase("ref_fwd"):
+                ref_logps, _ = self.ref_model.logprobs_forward(batch, rows, labels, temp, save=False)  # :737-743
+                ref_logps = ref_logps.view(G, C)
+        else:
+            ref_logps = None
+
+        # ---- rewards on decoded text (CPU Python callbacks, verbatim convention :749-781) ----
+        with self._phase("rewards"):
+            texts = self.processing_class.batch_decode(completion_ids.cpu(), skip_special_tokens=True)
+            conv = is_conversational(example)
+            completions = [[{"role": "assistant", "content": c}] for c in texts] if conv else texts
+            prompts = [example["prompt"] for _ in range(G)]
+            rewards_per_func = torch.zeros(G, len(self.reward_funcs), device=dev)
+            reward_kwargs = {k: [example[k]] * G for k in example.keys() if k not in ("prompt", "completion")}
+            for i, rf in enumerate(self.reward_funcs):
+                out = rf(prompts=prompts, completions=completions, current_step=self.state.global_step, **reward_kwargs)
+                rewards_per_func[:, i] = torch.tensor(out, dtype=torch.float32, device=dev)
+        rw = torch.tensor(a.reward_weights, device=dev) if (a.reward_weights and a.loss_mode == "clip") else None
+        adv, rewards, std = grpo_loss.group_advantages(rewards_per_func, G, a.scale_rewards or a.loss_mode == "sc", rw)  # :784-793
+        if a.loss_mode == "sc":
+            loss, mean_kl = grpo_loss.sc_grpo_loss(logps, ref_logps, adv, mask, self.beta)       # :796-798
+        else:
+            loss, mean_kl = grpo_loss.clip_grpo_loss(logps, None, ref_logps, adv, mask, self.beta, a.epsilon,
+                                                     a.epsilon_high if a.epsilon_high is not None else a.epsilon,
+                                                     a.loss_type, self.max_completion_length)
+        # ---- metrics (:801-817); kept as device scalars, reduced across ranks at log time ----
+        m = self._metrics
+        m["completion_length"].append(mask.sum(1).float().mean().detach())
+        for i, rf in enumerate(self.reward_funcs):
+            m[f"rewards/{rf.__name__}"].append(rewards_per_func[:, i].mean().detach())
+        m["reward"].append(rewards.mean().detach())
+        m["reward_std"].append(std.mean().detach())
+        m["kl"].append(mean_kl.detach())
+        return loss
+
+    # ---------------------------------------------------------------------------------------------------------------
+    # optimizer step (backward already accumulated fp32 grads)
+    # ---------------------------------------------------------------------------------------------------------------
+    def _lr_at(self, step: int) -> float:
+        a, total = self.args, max(1, self.state.max_steps)
+        warm = a.warmup_steps if a.warmup_steps > 0 else int(math.ceil(total * a.warmup_ratio))
+        if step < warm:
+            return a.learning_rate * step / max(1, warm)
+        prog = (step - warm) / max(1, total - warm)
+        if a.lr_scheduler_type == "linear":
+            return a.learning_rate * max(0.0, 1.0 - prog)
+        if a.lr_scheduler_type == "cosine":
+            return a.learning_rate * max(0.0, 0.5 * (1.0 + math.cos(math.pi * min(1.0, prog))))
+        if a.lr_scheduler_type in ("constant", "constant_with_warmup"):
+            return a.learning_rate
+        raise ValueError(f"unsupported lr_scheduler_type {a.lr_scheduler_type}")
+
+    def optimizer_step(self):
+        ps, a, lib = self.params, self.args, L.lib()
+        s = L.stream_ptr()
+        with self._phase("allreduce"):
+            if self.world > 1:
+                # the ONLY data-path collective: sum of the flat fp32 gradient over NVLink
+                torch.distributed.all_reduce(ps.grad_flat)
+        with self._phase("optimizer"):
+            scale = 1.0 / self.world
+            self._sumsq.zero_()
+            L.check(lib.iadr1_sumsq_f32(ps.grad_flat.data_ptr(), ps.numel, self._sumsq.data_ptr(), s), "sumsq")
+            self._opt_step += 1
+            lr = self._lr_at(self.state.global_step)
+            self._last_lr = lr
+            for lo, hi, wd in ((0, ps.n_decay, a.weight_decay), (ps.n_decay, ps.numel, 0.0)):
+                if hi <= lo:
+                    continue
+                L.check(lib.iadr1_adamw_step(ps.master[lo:].data_ptr(), ps.flat[lo:].data_ptr(), ps.grad_flat[lo:].data_ptr(),
+                                             ps.exp_avg[lo:].data_ptr(), ps.exp_avg_sq[lo:].data_ptr(), hi - lo, lr,
+                                             a.adam_beta1, a.adam_beta2, a.adam_epsilon, wd, self._opt_step, scale,
+                                             self._sumsq.data_ptr(), a.max_grad_norm if a.max_grad_norm else 0.0, 1, s),
+                        "adamw_step")
+            self._grad_norm_dev = self._sumsq.sqrt() * scale
+        self.state.global_step += 1
+
+    def training_step(self, inputs: list) -> torch.Tensor:
+        loss = self.compute_loss(self.model, inputs)
+        with self._phase("backward"):
+            (loss / self.args.gradient_accumulation_steps).backward()
+        return loss.detach()
+
+    # ---------------------------------------------------------------------------------------------------------------
+    def _epoch_order(self, epoch: int):
+        n = len(self.train_dataset)
+        if self.args.shuffle_dataset:
+            g = torch.Generator().manual_seed((self.args.data_seed if self.args.data_seed is not None else self.args.seed) + epoch)
+            order = torch.randperm(n, generator=g).tolist()
+        else:
+            order = list(range(n))
+        return order[self.rank::self.world] if self.world > 1 else order
+
+    def train(self, resume_from_checkpoint=None):
+        a = self.args
+        bs, GA = a.per_device_train_batch_size, a.gradient_accumulation_steps
+        per_rank = len(self.train_dataset) // self.world
+        steps_per_epoch = max(1, per_rank // (bs * GA))
+        self.state.max_steps = a.max_steps if a.max_steps > 0 else int(math.ceil(a.num_train_epochs * steps_per_epoch))
+        t_start = time.time()
+        epoch = 0
+        tr_loss = []
+        while self.state.global_step < self.state.max_steps:
+            order = self._epoch_order(epoch)
+            micro = [order[i:i + bs] for i in range(0, len(order) - bs + 1, bs)]
+            for w in range(0, len(micro) - GA + 1, GA):
+                window = [[self.train_dataset[j] for j in mb] for mb in micro[w:w + GA]]
+                if a.batched_rollout:
+                    self.prepare_window([ex for mb in window for ex in mb])
+                for mb in window:
+                    tr_loss.append(self.training_step(mb))
+                self.optimizer_step()
+                self.state.epoch = epoch + (w + GA) / max(1, len(micro))
+                if a.logging_steps and self.state.global_step % max(1, int(a.logging_steps)) == 0:
+                    loss_val = torch.stack(tr_loss).mean().item()
+                    tr_loss = []
+                    self.log({"loss": loss_val, "grad_norm": float(self._grad_norm_dev.item()),
+                              "learning_rate": self._last_lr, "epoch": round(self.state.epoch, 4)})
+                if a.save_strategy == "steps" and a.save_steps and self.state.global_step % max(1, int(a.save_steps)) == 0:
+                    self.save_model(os.path.join(a.output_dir, f"checkpoint-{self.state.global_step}"))
+                if self.state.global_step >= self.state.max_steps:
+                    break
+            epoch += 1
+        self.flush_timers()
+        runtime = time.time() - t_start
+        self.state.log_history.append({"train_runtime": runtime, "step": self.state.global_step})
+        return {"global_step": self.state.global_step, "train_runtime": runtime}
+
+    def log(self, logs: dict, start_time: Optional[float] = None) -> None:
+        """Average the per-micro-step metrics (and across ranks, as `gather_for_metrics(...).mean()` did), :821-827."""
+        keys = sorted(self._metrics.keys())
+        if keys:
+            vec = torch.stack([torch.stack([torch.as_tensor(v, device=self.device, dtype=torch.float32) for v in self._metrics[k]]).mean()
+                               for k in keys])
+            if self.world > 1:
+                torch.distributed.all_reduce(vec)
+                vec /= self.world
+            metrics = dict(zip(keys, vec.tolist()))
+        else:
+            metrics = {}
+        logs = {**logs, **metrics, "step": self.state.global_step}
+        self._metrics.clear()
+        self.state.log_history.append(logs)
+        if self.is_main:
+            print(json.dumps({k: (round(v, 6) if isinstance(v, float) else v) for k, v in logs.items()}), flush=True)
+
+    def save_model(self, output_dir: Optional[str] = None, _internal_call: bool = False):
+        output_dir = output_dir or self.args.output_dir
+        if self.is_main:
+            save_pretrained(self.params, output_dir)
+            if hasattr(self.processing_class, "save_pretrained"):
+                self.processing_class.save_pretrained(output_dir)
+        if self.world > 1:
+            torch.distributed.barrier()
+
+    def push_to_hub(self, **kwargs):
+        warnings.warn("push_to_hub: no network access from the training box; skipped")

@@ -55,6 +55,10 @@ typedef struct iadr1_gemm_t {
 int iadr1_gemm_bf16(const iadr1_gemm_t* desc, void* stream);
 /* block_n the library would choose for an N-wide product (sizes the EPI_LSE partial buffers). */
 int iadr1_gemm_pick_block_n(int N, int b_mn);
+/* Live roofline support: time every (non-graph-captured) GEMM launch with CUDA events on its own stream and count its
+ * algorithmic FLOPs. Collect after a device synchronise.                                                            */
+int iadr1_gemm_profile_enable(int on);
+int iadr1_gemm_profile_collect(double* total_ms, double* total_flops, double* max_launch_ms, long long* launches);
 
 /* ---- row kernels (HBM-bound; bf16 activations, fp32 statistics) ------------------------------------------------
  * RMSNorm: HF Qwen2_5_VLRMSNorm.forward, modeling_qwen2_5_vl.py:57-71 (decoder :775-776,:849; vision blocks; merger ln_q).
