@@ -387,21 +387,19 @@ int iadr1_decode_attention(const void* q, const void* kp, const void* vp, const 
   if (nq % nkv || nq / nkv > 8) return set_error("decode_attention: group size %d unsupported (max 8)", nq / nkv);
   const int chunk = (p_max + c_max + nsplit - 1) / nsplit;
   cudaStream_t st = (cudaStream_t)stream;
-  if (hd == 128) {
-    decode_attn_partial_kernel<128><<<dim3(rows, nkv, nsplit), 128, 0, st>>>(
-        (const bf16*)q, (const bf16*)kp, (const bf16*)vp, (const bf16*)kc, (const bf16*)vc, state, row_group, row_plen, part, nq,
-        nkv, p_max, c_max, chunk, scale);
-    IADR1_CHECK_LAUNCH("decode_attn_partial");
-    decode_attn_combine_kernel<128><<<rows * nq, 128, 0, st>>>(part, (bf16*)out, nsplit);
-  } else if (hd == 64) {
-    decode_attn_partial_kernel<64><<<dim3(rows, nkv, nsplit), 128, 0, st>>>(
-        (const bf16*)q, (const bf16*)kp, (const bf16*)vp, (const bf16*)kc, (const bf16*)vc, state, row_group, row_plen, part, nq,
-        nkv, p_max, c_max, chunk, scale);
-    IADR1_CHECK_LAUNCH("decode_attn_partial");
-    decode_attn_combine_kernel<64><<<rows * nq, 64, 0, st>>>(part, (bf16*)out, nsplit);
-  } else {
-    return set_error("decode_attention: head_dim %d unsupported (64 or 128)", hd);
-  }
+#define IADR1_DECODE_ATTN(HD)                                                                                        \
+  do {                                                                                                               \
+    decode_attn_partial_kernel<HD><<<dim3(rows, nkv, nsplit), 128, 0, st>>>(                                         \
+        (const bf16*)q, (const bf16*)kp, (const bf16*)vp, (const bf16*)kc, (const bf16*)vc, state, row_group, row_plen, \
+        part, nq, nkv, p_max, c_max, chunk, scale);                                                                  \
+    IADR1_CHECK_LAUNCH("decode_attn_partial");                                                                       \
+    decode_attn_combine_kernel<HD><<<rows * nq, HD < 64 ? 32 : 64, 0, st>>>(part, (bf16*)out, nsplit);               \
+  } while (0)
+  if (hd == 128) IADR1_DECODE_ATTN(128);
+  else if (hd == 64) IADR1_DECODE_ATTN(64);
+  else if (hd == 32) IADR1_DECODE_ATTN(32);
+  else return set_error("decode_attention: head_dim %d unsupported (32, 64 or 128)", hd);
+#undef IADR1_DECODE_ATTN
   IADR1_CHECK_LAUNCH("decode_attn_combine");
   return 0;
 }
