@@ -35,6 +35,23 @@ __device__ __forceinline__ float wsum(float v) {
 }
 __device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__float2bfloat16(x)); }
 
+// N consecutive bf16 (N = 1, 2 or 4) -> fp32 with one load
+template <int N>
+__device__ __forceinline__ void load_bf16_vec(const bf16* p, float (&out)[N]) {
+  if constexpr (N == 4) {
+    const uint2 v = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.y));
+    out[0] = a.x; out[1] = a.y; out[2] = b.x; out[3] = b.y;
+  } else if constexpr (N == 2) {
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+    out[0] = a.x; out[1] = a.y;
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) out[i] = __bfloat162float(p[i]);
+  }
+}
+
 // h[r][:] = float(embed[tok[r]][:])
 __global__ void decode_embed_kernel(const bf16* __restrict__ embed, const int* __restrict__ tok, float* __restrict__ h,
                                     int H) {
@@ -45,22 +62,40 @@ __global__ void decode_embed_kernel(const bf16* __restrict__ embed, const int* _
 
 // RMSNorm with fp32 input (the decode residual stream) -> bf16, same rounding order as Qwen2RMSNorm.
 __global__ void rmsnorm_f32in_kernel(const float* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y,
-                                     int cols, float eps) {
+                                     int cols, float eps, float* __restrict__ zero_buf, int zero_per_row) {
   __shared__ float red[32];
   const long long row = blockIdx.x;
   const float* xr = x + row * cols;
+  constexpr int MAXE = 16;  // 256 threads x 16 = 4096 columns held in registers
+  float xv[MAXE], wv[MAXE];
   float ss = 0.f;
-  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+#pragma unroll
+  for (int i = 0; i < MAXE; ++i) {
+    const int c = threadIdx.x + i * blockDim.x;
+    if (c < cols) {
+      xv[i] = bf16r(xr[c]);
+      wv[i] = __bfloat162float(w[c]);   // issued together with x: the weight's DRAM miss overlaps the reduction
+      ss += xv[i] * xv[i];
+    }
+  }
+  for (int c = threadIdx.x + MAXE * blockDim.x; c < cols; c += blockDim.x) {
     const float v = bf16r(xr[c]);
     ss += v * v;
   }
+  // clear this row's slice of the next split-K GEMM's fp32 accumulation target (saves a memset node per layer)
+  for (int c = threadIdx.x; c < zero_per_row; c += blockDim.x) zero_buf[row * zero_per_row + c] = 0.f;
   ss = wsum(ss);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
   __syncthreads();
   float tot = 0.f;
   for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
   const float rstd = rsqrtf(tot / (float)cols + eps);
-  for (int c = threadIdx.x; c < cols; c += blockDim.x)
+#pragma unroll
+  for (int i = 0; i < MAXE; ++i) {
+    const int c = threadIdx.x + i * blockDim.x;
+    if (c < cols) y[row * cols + c] = __float2bfloat16(wv[i] * bf16r(xv[i] * rstd));
+  }
+  for (int c = threadIdx.x + MAXE * blockDim.x; c < cols; c += blockDim.x)
     y[row * cols + c] = __float2bfloat16(__bfloat162float(w[c]) * bf16r(bf16r(xr[c]) * rstd));
 }
 
@@ -193,6 +228,174 @@ __global__ void __launch_bounds__(128) decode_attn_partial_kernel(
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Fused decode attention: rotary on q/k (HF bf16 op order) + KV append + split-KV attention + combine in ONE launch.
+// Grid (R, nkv, nsplit). Every CTA rotates its kv head's `gq` query heads straight from the fp32 qkv row; the CTA whose
+// key chunk contains the new position also rotates k, appends k/v to the row's slab and uses them from registers.
+// Partials go to `part`; the last CTA of each (row, kv head) to finish (atomic ticket) merges them and writes bf16 out.
+// ------------------------------------------------------------------------------------------------
+template <int HD>
+__global__ void __launch_bounds__(128) decode_attn_fused_kernel(
+    const float* __restrict__ qkv, const float* __restrict__ cos_tab, const float* __restrict__ sin_tab,
+    const int* __restrict__ rope_delta, const bf16* __restrict__ kp, const bf16* __restrict__ vp, bf16* __restrict__ kc,
+    bf16* __restrict__ vc, const int* __restrict__ state, const int* __restrict__ row_group,
+    const int* __restrict__ row_plen, float* __restrict__ part, int* __restrict__ tickets, bf16* __restrict__ out, int nq,
+    int nkv, int p_max, int c_max, int chunk, int max_pos, float scale) {
+  constexpr int DPL = HD / 32;
+  constexpr int MAXG = 8;
+  constexpr int HALF = HD / 2;
+  const int r = blockIdx.x, kvh = blockIdx.y, sp = blockIdx.z, nsplit = gridDim.z;
+  const int gq = nq / nkv;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int P = row_plen[r];
+  const int step = state[ST_STEP];
+  const int ctx = P + step + 1;
+  const int k0 = sp * chunk, k1 = min(ctx, k0 + chunk);
+  const int grp = row_group[r];
+  const int qkv_dim = (nq + 2 * nkv) * HD;
+  const float* xrow = qkv + (long long)r * qkv_dim;
+  int pos = P + step + rope_delta[r];
+  pos = max(0, min(max_pos - 1, pos));
+  const float* cs = cos_tab + (long long)pos * HD;
+  const float* sn = sin_tab + (long long)pos * HD;
+
+  // rotate-half with bf16 rounding of every product (apply_multimodal_rotary_pos_emb)
+  auto rot = [&](const float* x, int d) -> float {
+    const float xd = bf16r(x[d]);
+    const float xp = bf16r(x[d < HALF ? d + HALF : d - HALF]);
+    const float a = bf16r(xd * bf16r(cs[d]));
+    const float b = bf16r((d < HALF ? -xp : xp) * bf16r(sn[d]));
+    return bf16r(a + b);
+  };
+
+  float qv[MAXG][DPL], acc[MAXG][DPL], mrun[MAXG], lrun[MAXG];
+#pragma unroll
+  for (int h = 0; h < MAXG; ++h) {
+    mrun[h] = -INFINITY;
+    lrun[h] = 0.f;
+#pragma unroll
+    for (int d = 0; d < DPL; ++d) {
+      acc[h][d] = 0.f;
+      qv[h][d] = (h < gq) ? rot(xrow + (long long)(kvh * gq + h) * HD, lane * DPL + d) * scale : 0.f;
+    }
+  }
+  const float* knew = xrow + (long long)(nq + kvh) * HD;
+  const float* vnew = xrow + (long long)(nq + nkv + kvh) * HD;
+  // Keys are walked UNR at a time: all K/V rows of a batch are requested before any is consumed, so the global-load
+  // latency is paid once per batch instead of once per key.
+  constexpr int UNR = 4;
+  for (int jb = k0 + warp; jb < k1; jb += 4 * UNR) {
+    float kf[UNR][DPL], vf[UNR][DPL];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int j = jb + 4 * u;
+      if (j < k1 && j != ctx - 1) {
+        const bf16* krow;
+        const bf16* vrow;
+        if (j < P) {
+          krow = kp + (((long long)grp * p_max + j) * nkv + kvh) * HD;
+          vrow = vp + (((long long)grp * p_max + j) * nkv + kvh) * HD;
+        } else {
+          krow = kc + (((long long)r * c_max + (j - P)) * nkv + kvh) * HD;
+          vrow = vc + (((long long)r * c_max + (j - P)) * nkv + kvh) * HD;
+        }
+        load_bf16_vec<DPL>(krow + lane * DPL, kf[u]);
+        load_bf16_vec<DPL>(vrow + lane * DPL, vf[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int j = jb + 4 * u;
+      if (j >= k1) break;
+      if (j == ctx - 1) {
+        // the token being decoded: rotate k, append k/v to the slab, use them from registers
+        bf16* kdst = kc + (((long long)r * c_max + step) * nkv + kvh) * HD;
+        bf16* vdst = vc + (((long long)r * c_max + step) * nkv + kvh) * HD;
+#pragma unroll
+        for (int d = 0; d < DPL; ++d) {
+          kf[u][d] = rot(knew, lane * DPL + d);
+          vf[u][d] = bf16r(vnew[lane * DPL + d]);
+          kdst[lane * DPL + d] = __float2bfloat16(kf[u][d]);
+          vdst[lane * DPL + d] = __float2bfloat16(vf[u][d]);
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < MAXG; ++h) {
+        if (h < gq) {
+          float sc = 0.f;
+#pragma unroll
+          for (int d = 0; d < DPL; ++d) sc += qv[h][d] * kf[u][d];
+          sc = wsum(sc);
+          const float mn = fmaxf(mrun[h], sc);
+          const float corr = __expf(mrun[h] - mn);
+          const float pr = __expf(sc - mn);
+          lrun[h] = lrun[h] * corr + pr;
+#pragma unroll
+          for (int d = 0; d < DPL; ++d) acc[h][d] = acc[h][d] * corr + pr * vf[u][d];
+          mrun[h] = mn;
+        }
+      }
+    }
+  }
+  __shared__ float sm_m[4][MAXG], sm_l[4][MAXG], sm_acc[4][MAXG][HD];
+  __shared__ int s_last;
+  if (lane == 0) {
+#pragma unroll
+    for (int h = 0; h < MAXG; ++h) {
+      sm_m[warp][h] = mrun[h];
+      sm_l[warp][h] = lrun[h];
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < MAXG; ++h)
+#pragma unroll
+    for (int d = 0; d < DPL; ++d) sm_acc[warp][h][lane * DPL + d] = acc[h][d];
+  __syncthreads();
+  for (int i = threadIdx.x; i < gq * HD; i += blockDim.x) {
+    const int h = i / HD, d = i % HD;
+    const float m = fmaxf(fmaxf(sm_m[0][h], sm_m[1][h]), fmaxf(sm_m[2][h], sm_m[3][h]));
+    float a = 0.f, l = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float c = (sm_m[w][h] == -INFINITY) ? 0.f : __expf(sm_m[w][h] - m);
+      a += sm_acc[w][h][d] * c;
+      l += sm_l[w][h] * c;
+    }
+    float* dst = part + (((long long)r * nq + kvh * gq + h) * nsplit + sp) * (HD + 2);
+    dst[d] = a;
+    if (d == 0) {
+      dst[HD] = m;
+      dst[HD + 1] = l;
+    }
+  }
+  // ---- last CTA of this (row, kv head) merges the splits ----
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int t = atomicAdd(&tickets[r * nkv + kvh], 1);
+    s_last = (t == nsplit - 1);
+    if (s_last) tickets[r * nkv + kvh] = 0;  // re-arm for the next layer / step
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int i = threadIdx.x; i < gq * HD; i += blockDim.x) {
+    const int h = i / HD, d = i % HD;
+    const float* p = part + ((long long)r * nq + kvh * gq + h) * nsplit * (HD + 2);
+    float m = -INFINITY;
+    for (int s2 = 0; s2 < nsplit; ++s2) m = fmaxf(m, __ldcg(p + s2 * (HD + 2) + HD));
+    float a = 0.f, l = 0.f;
+    for (int s2 = 0; s2 < nsplit; ++s2) {
+      const float ms = __ldcg(p + s2 * (HD + 2) + HD);
+      const float c = (ms == -INFINITY) ? 0.f : __expf(ms - m);
+      a += __ldcg(p + s2 * (HD + 2) + d) * c;
+      l += __ldcg(p + s2 * (HD + 2) + HD + 1) * c;
+    }
+    out[((long long)r * nq + kvh * gq + h) * HD + d] = __float2bfloat16(a / l);
+  }
+}
+
 template <int HD>
 __global__ void decode_attn_combine_kernel(const float* __restrict__ part, bf16* __restrict__ out, int nsplit) {
   const long long rh = blockIdx.x;  // row * nq + head
@@ -226,6 +429,13 @@ __device__ __forceinline__ uint32_t f2key(float f) {
 }
 constexpr int kMaxKeep = 256;  // survivors buffer (top_k <= 128 plus ties)
 
+__device__ __forceinline__ void hist_add_aggregated(uint32_t* hist, uint32_t bin) {
+  // lanes of the warp that hit the same bin elect one leader: logits cluster in a few exponent bins, and un-aggregated
+  // shared-memory atomics on one address serialise the whole CTA.
+  const unsigned peers = __match_any_sync(__activemask(), bin);
+  if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&hist[bin], (uint32_t)__popc(peers));
+}
+
 __global__ void __launch_bounds__(1024) sample_kernel(const float* __restrict__ logits, int V, float inv_temp, int top_k,
                                                       float top_p, unsigned long long seed, int* __restrict__ state,
                                                       int* __restrict__ tok, int* __restrict__ finished,
@@ -234,8 +444,8 @@ __global__ void __launch_bounds__(1024) sample_kernel(const float* __restrict__ 
   __shared__ uint32_t hist[2048];
   __shared__ uint32_t s_prefix, s_kth_remaining;
   __shared__ int s_count;
-  __shared__ float s_val[kMaxKeep];
-  __shared__ int s_idx[kMaxKeep];
+  __shared__ float s_val[kMaxKeep], s_sorted[kMaxKeep];
+  __shared__ int s_idx[kMaxKeep], s_sidx[kMaxKeep];
   const int r = blockIdx.x;
   const float* lg = logits + (long long)r * V;
   // `first`: logits come from the prefill (predict completion token 0); else they predict token step + 1.
@@ -249,7 +459,7 @@ __global__ void __launch_bounds__(1024) sample_kernel(const float* __restrict__ 
     return;
   }
   const int k = min(max(top_k, 1), 128);
-  // --- radix select of the k-th largest key ---
+  // --- radix select of the k-th largest key (11 + 11 + 10 bits) ---
   uint32_t prefix = 0, prefix_mask = 0;
   uint32_t remaining = k;
   const int shifts[3] = {21, 10, 0};
@@ -262,18 +472,40 @@ __global__ void __launch_bounds__(1024) sample_kernel(const float* __restrict__ 
       float x = lg[i];
       if (forbid_eos && i == eos_id) x = -INFINITY;
       const uint32_t key = f2key(x);
-      if ((key & prefix_mask) == prefix) atomicAdd(&hist[(key >> shifts[pass]) & (nb - 1)], 1u);
+      if ((key & prefix_mask) == prefix) hist_add_aggregated(hist, (key >> shifts[pass]) & (nb - 1));
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
+      // warp 0 walks the histogram from the top, 32 bins at a time (suffix sums by shuffle)
       uint32_t cum = 0;
-      int b = (int)nb - 1;
-      for (; b > 0; --b) {
-        if (cum + hist[b] >= remaining) break;
-        cum += hist[b];
+      int found = -1;
+      uint32_t rem_after = 0;
+      for (int base = (int)nb - 32; base >= 0 && found < 0; base -= 32) {
+        const int b = base + (31 - (int)threadIdx.x);  // lane 0 holds the highest bin of this block
+        const uint32_t c = hist[b];
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+          if ((int)threadIdx.x >= o) incl += v;
+        }
+        const bool hit = (cum + incl >= remaining);
+        const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+        if (ballot) {
+          const int ln = __ffs(ballot) - 1;
+          found = base + (31 - ln);
+          const uint32_t incl_ln = __shfl_sync(0xffffffffu, incl, ln);
+          const uint32_t c_ln = __shfl_sync(0xffffffffu, c, ln);
+          rem_after = remaining - (cum + incl_ln - c_ln);
+        } else {
+          cum += __shfl_sync(0xffffffffu, incl, 31);
+        }
       }
-      s_prefix = prefix | ((uint32_t)b << shifts[pass]);
-      s_kth_remaining = remaining - cum;
+      if (found < 0) { found = 0; rem_after = 1; }
+      if (threadIdx.x == 0) {
+        s_prefix = prefix | ((uint32_t)found << shifts[pass]);
+        s_kth_remaining = rem_after;
+      }
     }
     __syncthreads();
     prefix = s_prefix;
@@ -296,34 +528,34 @@ __global__ void __launch_bounds__(1024) sample_kernel(const float* __restrict__ 
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    const int n = min(s_count, kMaxKeep);
-    // insertion sort descending by value, ties by smaller index first (deterministic)
-    for (int i = 1; i < n; ++i) {
-      const float v = s_val[i];
-      const int id = s_idx[i];
-      int j = i - 1;
-      while (j >= 0 && (s_val[j] < v || (s_val[j] == v && s_idx[j] > id))) {
-        s_val[j + 1] = s_val[j];
-        s_idx[j + 1] = s_idx[j];
-        --j;
-      }
-      s_val[j + 1] = v;
-      s_idx[j + 1] = id;
+  const int n = min(s_count, kMaxKeep);
+  // parallel rank sort: descending by value, ties by smaller token id (deterministic)
+  if ((int)threadIdx.x < n) {
+    const float v = s_val[threadIdx.x];
+    const int id = s_idx[threadIdx.x];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+      const float vj = s_val[j];
+      rank += (vj > v) || (vj == v && s_idx[j] < id);
     }
-    const float mx = s_val[0];
+    s_sorted[rank] = v;
+    s_sidx[rank] = id;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float mx = s_sorted[0];
     float tot = 0.f;
     for (int i = 0; i < n; ++i) {
-      s_val[i] = expf(s_val[i] - mx);
-      tot += s_val[i];
+      s_sorted[i] = expf(s_sorted[i] - mx);
+      tot += s_sorted[i];
     }
     // nucleus: keep token i while the mass of strictly higher-ranked tokens is < top_p
     float before = 0.f, kept = 0.f;
     int nkeep = 0;
     for (int i = 0; i < n; ++i) {
       if (i > 0 && before / tot >= top_p) break;
-      kept += s_val[i];
-      before += s_val[i];
+      kept += s_sorted[i];
+      before += s_sorted[i];
       ++nkeep;
     }
     curandStatePhilox4_32_10_t rng;
@@ -332,13 +564,13 @@ __global__ void __launch_bounds__(1024) sample_kernel(const float* __restrict__ 
     float c = 0.f;
     int pick = nkeep - 1;
     for (int i = 0; i < nkeep; ++i) {
-      c += s_val[i];
+      c += s_sorted[i];
       if (u <= c) {
         pick = i;
         break;
       }
     }
-    const int t = s_idx[pick];
+    const int t = s_sidx[pick];
     out_tokens[(long long)r * c_max + out_pos] = t;
     tok[r] = t;
     if (t == eos_id) {
@@ -363,9 +595,11 @@ int iadr1_decode_embed(const void* embed, const int* tok, float* h, int rows, in
   return 0;
 }
 
-int iadr1_rmsnorm_f32in(const float* x, const void* w, void* y, int rows, int cols, float eps, void* stream) {
+int iadr1_rmsnorm_f32in(const float* x, const void* w, void* y, int rows, int cols, float eps, float* zero_buf,
+                        int zero_per_row, void* stream) {
   if (rows <= 0) return 0;
-  rmsnorm_f32in_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(x, (const bf16*)w, (bf16*)y, cols, eps);
+  rmsnorm_f32in_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(x, (const bf16*)w, (bf16*)y, cols, eps, zero_buf,
+                                                               zero_buf ? zero_per_row : 0);
   IADR1_CHECK_LAUNCH("rmsnorm_f32in");
   return 0;
 }
@@ -404,7 +638,30 @@ int iadr1_decode_attention(const void* q, const void* kp, const void* vp, const 
   return 0;
 }
 
-int iadr1_sample(const float* logits, int rows, int V, float temperature, int top_k, float top_p,
+int iadr1_decode_attention_fused(const float* qkv, const float* cos_tab, const float* sin_tab, const int* rope_delta,
+                                 const void* kp, const void* vp, void* kc, void* vc, const int* state,
+                                 const int* row_group, const int* row_plen, float* part, int* tickets, void* out, int rows,
+                                 int nq, int nkv, int hd, int p_max, int c_max, int nsplit, int max_pos, float scale,
+                                 void* stream) {
+  if (rows <= 0) return 0;
+  if (nq % nkv || nq / nkv > 8) return set_error("decode_attention_fused: group size %d unsupported (max 8)", nq / nkv);
+  const int chunk = (p_max + c_max + nsplit - 1) / nsplit;
+  cudaStream_t st = (cudaStream_t)stream;
+#define IADR1_DECODE_FUSED(HD)                                                                                       \
+  decode_attn_fused_kernel<HD><<<dim3(rows, nkv, nsplit), 128, 0, st>>>(                                             \
+      qkv, cos_tab, sin_tab, rope_delta, (const bf16*)kp, (const bf16*)vp, (bf16*)kc, (bf16*)vc, state, row_group,   \
+      row_plen, part, tickets, (bf16*)out, nq, nkv, p_max, c_max, chunk, max_pos, scale)
+  if (hd == 128) IADR1_DECODE_FUSED(128);
+  else if (hd == 64) IADR1_DECODE_FUSED(64);
+  else if (hd == 32) IADR1_DECODE_FUSED(32);
+  else return set_error("decode_attention_fused: head_dim %d unsupported (32, 64 or 128)", hd);
+#undef IADR1_DECODE_FUSED
+  IADR1_CHECK_LAUNCH("decode_attention_fused");
+  return 0;
+}
+
+int iadr1_sample(
+const float* logits, int rows, int V, float temperature, int top_k, float top_p,
                  unsigned long long seed, int* state, int* tok, int* finished, int* out_tokens, int c_max, int eos_id,
                  int pad_id, int forbid_eos, int first, void* stream) {
   if (rows <= 0) return 0;

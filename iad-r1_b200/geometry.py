@@ -16,11 +16,14 @@ from .config import TextConfig, VisionConfig, VLMConfig
 
 
 # ---- M-RoPE position ids (Qwen2_5_VLForConditionalGeneration.get_rope_index, 4.51.3 semantics) ------------------------
-def mrope_position_ids(input_ids: np.ndarray, grid_thw: list, cfg: VLMConfig, attention_mask: np.ndarray | None = None):
+def mrope_position_ids(input_ids: np.ndarray, grid_thw: list, cfg: VLMConfig, attention_mask: np.ndarray | None = None,
+                       prompt_len: int | None = None):
     """input_ids [B, T] int -> (position_ids [3, B, T] int64, rope_deltas [B] int64).
 
     Text runs count up on all three axes; a still image occupying t*(h/m)*(w/m) tokens from base b gets
     (b, b + row, b + col); text resumes at max + 1. Masked (pad) positions get 1 (4.51.3 filler, masked anyway).
+    `prompt_len`: image placeholders are only recognised in the first `prompt_len` columns - a SAMPLED completion token
+    that happens to equal `image_token_id` is plain text (HF would raise on the feature/token count mismatch).
     """
     B, T = input_ids.shape
     m = cfg.vision.spatial_merge_size
@@ -30,10 +33,11 @@ def mrope_position_ids(input_ids: np.ndarray, grid_thw: list, cfg: VLMConfig, at
     for b in range(B):
         keep = np.ones(T, dtype=bool) if attention_mask is None else attention_mask[b].astype(bool)
         ids = input_ids[b][keep]
+        in_prompt = (np.arange(T) < (T if prompt_len is None else prompt_len))[keep]
         out = np.zeros((3, len(ids)), dtype=np.int64)
         i, nxt = 0, 0
         while i < len(ids):
-            if ids[i] == cfg.image_token_id:
+            if ids[i] == cfg.image_token_id and in_prompt[i]:
                 t, h, w = grid_thw[img_cursor]
                 img_cursor += 1
                 gh, gw = h // m, w // m
@@ -167,7 +171,8 @@ def vision_geometry(v: VisionConfig, grid_thw, device) -> VisionGeometry:
     return g
 
 
-def embed_source_index(input_ids: np.ndarray, image_token_id: int, rows_share_images: bool, n_image_tokens: int):
+def embed_source_index(input_ids: np.ndarray, image_token_id: int, rows_share_images: bool, n_image_tokens: int,
+                       prompt_len: int | None = None):
     """[B*T] int32: token id for text, -1 - (image embedding row) for image placeholders (`masked_scatter`,
     modeling_qwen2_5_vl.py:1298-1307). With `rows_share_images` every row consumes the same image rows from 0 (the G
     completions of one prompt: the reference tiles pixel_values G times, sc_grpo_trainer.py:624-628, we don't)."""
@@ -176,6 +181,8 @@ def embed_source_index(input_ids: np.ndarray, image_token_id: int, rows_share_im
     cursor = 0
     for b in range(B):
         is_img = input_ids[b] == image_token_id
+        if prompt_len is not None:
+            is_img &= np.arange(T) < prompt_len
         n = int(is_img.sum())
         if rows_share_images:
             cursor = 0

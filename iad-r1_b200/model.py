@@ -221,7 +221,7 @@ class VLM:
     # =============================================================================================================
     # per-token log-probs (the whole `_get_per_token_logps`, sc_grpo_trainer.py:502-514)
     # =============================================================================================================
-    def prepare_batch(self, input_ids, pixel_values, grid_thw, position_ids=None, attention_mask=None):
+    def prepare_batch(self, input_ids, pixel_values, grid_thw, position_ids=None, attention_mask=None, prompt_len=None):
         """Host-side prep shared by every forward: M-RoPE positions (4.51.3 semantics), rotary tables, embed index."""
         ids_np = input_ids.detach().cpu().numpy() if torch.is_tensor(input_ids) else np.asarray(input_ids)
         B, T = ids_np.shape
@@ -229,15 +229,16 @@ class VLM:
             if grid_thw is not None else []
         unit = self.cfg.vision.spatial_merge_size ** 2
         n_img_tokens = sum(t * h * w for t, h, w in grid) // unit
-        per_row = int((ids_np[0] == self.cfg.image_token_id).sum()) if B else 0
+        pl = T if prompt_len is None else prompt_len
+        per_row = int((ids_np[0, :pl] == self.cfg.image_token_id).sum()) if B else 0
         share = B > 1 and per_row == n_img_tokens
         if position_ids is None:
             am = attention_mask.detach().cpu().numpy() if torch.is_tensor(attention_mask) else attention_mask
             g_rows = grid * B if share else grid
-            position_ids, _ = mrope_position_ids(ids_np, g_rows, self.cfg, am)
+            position_ids, _ = mrope_position_ids(ids_np, g_rows, self.cfg, am, prompt_len)
             position_ids = torch.from_numpy(position_ids)
         cos, sin = text_rope_tables(position_ids, self.cfg.text, self.device)
-        src = torch.from_numpy(embed_source_index(ids_np, self.cfg.image_token_id, share, n_img_tokens)).to(self.device)
+        src = torch.from_numpy(embed_source_index(ids_np, self.cfg.image_token_id, share, n_img_tokens, prompt_len)).to(self.device)
         return dict(B=B, T=T, grid=grid, cos=cos, sin=sin, src_index=src, n_img_tokens=n_img_tokens,
                     pixel_values=pixel_values)
 

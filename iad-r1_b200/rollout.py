@@ -62,6 +62,7 @@ class RolloutEngine:
         self.attn = torch.zeros(R, t.num_heads * hd, dtype=bf16, device=dev)
         self.nsplit = max(1, min(32, (p_max + c_max + 63) // 64))
         self.part = torch.zeros(R, t.num_heads, self.nsplit, hd + 2, dtype=f32, device=dev)
+        self.tickets = torch.zeros(R * nkv, dtype=i32, device=dev)
         self.gu = torch.zeros(R, 2 * I, dtype=bf16, device=dev)
         self.act = torch.zeros(R, I, dtype=bf16, device=dev)
         self.logits = torch.zeros(R, V, dtype=f32, device=dev)
@@ -83,7 +84,7 @@ class RolloutEngine:
         t, p, lib = self.cfg.text, self.vlm.p, L.lib()
         s = L.stream_ptr()
         L.check(lib.iadr1_rmsnorm_f32in(self.h.data_ptr(), p["norm.weight"].data_ptr(), self.xn.data_ptr(), self.R,
-                                        t.hidden_size, t.rms_norm_eps, s), "rmsnorm_f32in")
+                                        t.hidden_size, t.rms_norm_eps, None, 0, s), "rmsnorm_f32in")
         self._skinny(self.vlm.params.lm_head, self.xn, self.logits)
         L.check(lib.iadr1_sample(self.logits.data_ptr(), self.R, t.vocab_size, self.temperature, self.top_k, self.top_p,
                                  self._seed, self.state.data_ptr(), self.tok.data_ptr(), self.finished.data_ptr(),
@@ -99,22 +100,19 @@ class RolloutEngine:
         sk_qkv, sk_o, sk_d = _split_for(t.qkv_dim, H), _split_for(H, nq * hd), _split_for(H, I)
         for i in range(t.num_layers):
             b = f"layers.{i}."
+            # RMSNorm also clears the fp32 qkv accumulator the split-K GEMM adds into
             L.check(lib.iadr1_rmsnorm_f32in(self.h.data_ptr(), p[b + "ln1.weight"].data_ptr(), self.xn.data_ptr(), R, H,
-                                            t.rms_norm_eps, s), "rmsnorm_f32in")
-            self.qkv.zero_()
+                                            t.rms_norm_eps, self.qkv.data_ptr(), t.qkv_dim, s), "rmsnorm_f32in")
             self._skinny(p[b + "qkv.weight"], self.xn, self.qkv, split_k=sk_qkv, atomic=True, bias=p[b + "qkv.bias"])
-            L.check(lib.iadr1_decode_rope_append(self.qkv.data_ptr(), self.cos_tab.data_ptr(), self.sin_tab.data_ptr(),
-                                                 self.rope_delta.data_ptr(), self.row_plen.data_ptr(), self.state.data_ptr(),
-                                                 self.q.data_ptr(), self.kc[i].data_ptr(), self.vc[i].data_ptr(), R, nq, nkv,
-                                                 hd, self.c_max, self.max_pos, s), "decode_rope_append")
-            L.check(lib.iadr1_decode_attention(self.q.data_ptr(), self.kp[i].data_ptr(), self.vp[i].data_ptr(),
-                                               self.kc[i].data_ptr(), self.vc[i].data_ptr(), self.state.data_ptr(),
-                                               self.row_group.data_ptr(), self.row_plen.data_ptr(), self.part.data_ptr(),
-                                               self.attn.data_ptr(), R, nq, nkv, hd, self.p_max, self.c_max, self.nsplit,
-                                               float(hd) ** -0.5, s), "decode_attention")
+            L.check(lib.iadr1_decode_attention_fused(
+                self.qkv.data_ptr(), self.cos_tab.data_ptr(), self.sin_tab.data_ptr(), self.rope_delta.data_ptr(),
+                self.kp[i].data_ptr(), self.vp[i].data_ptr(), self.kc[i].data_ptr(), self.vc[i].data_ptr(),
+                self.state.data_ptr(), self.row_group.data_ptr(), self.row_plen.data_ptr(), self.part.data_ptr(),
+                self.tickets.data_ptr(), self.attn.data_ptr(), R, nq, nkv, hd, self.p_max, self.c_max, self.nsplit,
+                self.max_pos, float(hd) ** -0.5, s), "decode_attention_fused")
             self._skinny(p[b + "o.weight"], self.attn, self.h, split_k=sk_o, atomic=True)        # h += attn @ Wo^T
             L.check(lib.iadr1_rmsnorm_f32in(self.h.data_ptr(), p[b + "ln2.weight"].data_ptr(), self.xn.data_ptr(), R, H,
-                                            t.rms_norm_eps, s), "rmsnorm_f32in")
+                                            t.rms_norm_eps, None, 0, s), "rmsnorm_f32in")
             self._skinny(p[b + "gate_up.weight"], self.xn, self.gu)
             ops.act_mul_fwd(self.gu, I, ops.ACT_SILU, gated=True, out=self.act)
             self._skinny(p[b + "down.weight"], self.act, self.h, split_k=sk_d, atomic=True)      # h += mlp

@@ -117,13 +117,21 @@ int iadr1_adamw_step(float* p32, void* p16, float* g, float* m, float* v, long l
 /* ---- rollout: replaces vLLM `LLM.generate` (sc_grpo_trainer.py:343-358, 667). State words: [0] step,
  * [2] unfinished rows; per-row prompt lengths in row_plen. All per-step inputs live on the device so one step is CUDA-graph replayable.        */
 int iadr1_decode_embed(const void* embed, const int* tok, float* h, int rows, int H, void* stream);
-int iadr1_rmsnorm_f32in(const float* x, const void* w, void* y, int rows, int cols, float eps, void* stream);
+/* zero_buf (optional): rows x zero_per_row fp32 cleared in the same launch (the next split-K GEMM's target).        */
+int iadr1_rmsnorm_f32in(const float* x, const void* w, void* y, int rows, int cols, float eps, float* zero_buf,
+                        int zero_per_row, void* stream);
 int iadr1_decode_rope_append(const float* qkv, const float* cos_tab, const float* sin_tab, const int* rope_delta,
                              const int* row_plen, const int* state, void* q_out, void* kc, void* vc, int rows, int nq, int nkv, int hd,
                              int c_max, int max_pos, void* stream);
 int iadr1_decode_attention(const void* q, const void* kp, const void* vp, const void* kc, const void* vc,
                            const int* state, const int* row_group, const int* row_plen, float* part, void* out, int rows, int nq, int nkv,
                            int hd, int p_max, int c_max, int nsplit, float scale, void* stream);
+/* One launch: rotary on q/k + KV append + split-KV attention over (shared prompt prefix, row slab) + split merge.   */
+int iadr1_decode_attention_fused(const float* qkv, const float* cos_tab, const float* sin_tab, const int* rope_delta,
+                                 const void* kp, const void* vp, void* kc, void* vc, const int* state,
+                                 const int* row_group, const int* row_plen, float* part, int* tickets, void* out, int rows,
+                                 int nq, int nkv, int hd, int p_max, int c_max, int nsplit, int max_pos, float scale,
+                                 void* stream);
 /* temperature -> top-k (ties kept) -> top-p -> multinomial; SamplingParams at sc_grpo_trainer.py:353-358.           */
 int iadr1_sample(const float* logits, int rows, int V, float temperature, int top_k, float top_p,
                  unsigned long long seed, int* state, int* tok, int* finished, int* out_tokens, int c_max, int eos_id,

@@ -40,7 +40,7 @@ def test_decode_matches_training_forward(cuda):
         P = len(enc["input_ids"])
         comp = out[gi * G:(gi + 1) * G]
         ids = torch.cat([torch.from_numpy(enc["input_ids"]).to(cuda)[None].expand(G, -1), comp.long()], 1)
-        batch = tr.model.prepare_batch(ids, enc["pixel_values"], enc["grid_thw"])
+        batch = tr.model.prepare_batch(ids, enc["pixel_values"], enc["grid_thw"], prompt_len=P)
         T = P + C
         rows = (torch.arange(G, device=cuda)[:, None] * T + (P - 1) + torch.arange(C, device=cuda)[None]).reshape(-1).to(torch.int32)
         logp, _ = tr.model.logprobs_forward(batch, rows, comp.reshape(-1).to(torch.int32).contiguous(), save=False)
