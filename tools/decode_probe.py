@@ -1,0 +1,79 @@
+"""Times the rollout decode step and each of its kernels in isolation (CUDA events, warm, 3B widths, few layers).
+Usage (GPU box): python tools/decode_probe.py [groups] [layers]"""
+import os, sys, copy
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from iad_r1_b200 import lib as L, ops
+from iad_r1_b200.config import PRESETS
+from iad_r1_b200.params import ParamStore
+from iad_r1_b200.model import VLM
+from iad_r1_b200.rollout import RolloutEngine, _split_for
+from iad_r1_b200.synthetic import SyntheticProcessor, synthetic_dataset
+
+groups = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+layers = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+dev = torch.device("cuda:0")
+cfg = PRESETS["qwen2.5-vl-3b"]()
+cfg.text.num_layers = layers
+cfg.vision.depth = 2
+cfg.vision.fullatt_block_indexes = (1,)
+ps = ParamStore(cfg, dev)
+ps.init_random(0)
+vlm = VLM(cfg, ps)
+proc = SyntheticProcessor(cfg, max_pixels=480000)
+G, C = 8, 512
+encs = []
+for ex in synthetic_dataset(groups, 448):
+    e = proc(text=[proc.apply_chat_template(ex["prompt"])], images=ex["image"])
+    encs.append(dict(input_ids=e["input_ids"][0].numpy(), pixel_values=e["pixel_values"].to(dev), grid_thw=e["image_grid_thw"].tolist()))
+
+
+def timeit(fn, n=50, warm=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n * 1000  # us
+
+
+for graph in (False, True):
+    eng = RolloutEngine(vlm, groups, G, 320, C, forbid_eos=True, use_cuda_graph=graph)
+    out, st = eng.generate(encs, seed=1, max_new_tokens=64)
+    out, st = eng.generate(encs, seed=2, max_new_tokens=64)
+    print(f"R={eng.R} layers={layers} graph={graph}: {st['decode_ms'] / st['steps'] * 1000:.1f} us per decode step "
+          f"({st['decode_ms'] / st['steps'] * 1000 / layers:.1f} us per layer incl. head)", flush=True)
+
+t, p, lib, s = cfg.text, vlm.p, L.lib(), L.stream_ptr()
+R, H, I, nq, nkv, hd = eng.R, t.hidden_size, t.intermediate_size, t.num_heads, t.num_kv_heads, t.head_dim
+eng.state[0] = 300  # mid-rollout context
+b = "layers.0."
+sk_qkv, sk_o, sk_d = _split_for(t.qkv_dim, H), _split_for(H, nq * hd), _split_for(H, I)
+items = {
+    "decode_embed": lambda: lib.iadr1_decode_embed(p["embed_tokens.weight"].data_ptr(), eng.tok.data_ptr(), eng.h.data_ptr(), R, H, s),
+    "rmsnorm_f32in(+zero)": lambda: lib.iadr1_rmsnorm_f32in(eng.h.data_ptr(), p[b + "ln1.weight"].data_ptr(), eng.xn.data_ptr(), R, H, 1e-6, eng.qkv.data_ptr(), t.qkv_dim, s),
+    f"gemm qkv split{sk_qkv}": lambda: eng._skinny(p[b + "qkv.weight"], eng.xn, eng.qkv, split_k=sk_qkv, atomic=True, bias=p[b + "qkv.bias"]),
+    "gemm qkv split1": lambda: eng._skinny(p[b + "qkv.weight"], eng.xn, eng.qkv, split_k=1, atomic=True, bias=p[b + "qkv.bias"]),
+    "attn_fused": lambda: lib.iadr1_decode_attention_fused(
+        eng.qkv.data_ptr(), eng.cos_tab.data_ptr(), eng.sin_tab.data_ptr(), eng.rope_delta.data_ptr(), eng.kp[0].data_ptr(),
+        eng.vp[0].data_ptr(), eng.kc[0].data_ptr(), eng.vc[0].data_ptr(), eng.state.data_ptr(), eng.row_group.data_ptr(),
+        eng.row_plen.data_ptr(), eng.part.data_ptr(), eng.tickets.data_ptr(), eng.attn.data_ptr(), R, nq, nkv, hd, eng.p_max,
+        eng.c_max, eng.nsplit, eng.max_pos, hd ** -0.5, s),
+    f"gemm o split{sk_o}": lambda: eng._skinny(p[b + "o.weight"], eng.attn, eng.h, split_k=sk_o, atomic=True),
+    "gemm gate_up": lambda: eng._skinny(p[b + "gate_up.weight"], eng.xn, eng.gu),
+    "act_mul": lambda: ops.act_mul_fwd(eng.gu, I, ops.ACT_SILU, gated=True, out=eng.act),
+    f"gemm down split{sk_d}": lambda: eng._skinny(p[b + "down.weight"], eng.act, eng.h, split_k=sk_d, atomic=True),
+    "gemm lm_head": lambda: eng._skinny(vlm.params.lm_head, eng.xn, eng.logits),
+    "sample": lambda: lib.iadr1_sample(eng.logits.data_ptr(), R, t.vocab_size, 0.9, 50, 0.9, 1, eng.state.data_ptr(), eng.tok.data_ptr(),
+                                       eng.finished.data_ptr(), eng.out_tokens.data_ptr(), eng.c_max, cfg.eos_token_id, cfg.pad_token_id, 1, 0, s),
+}
+eng.finished.zero_()
+tot = 0
+for name, fn in items.items():
+    us = timeit(fn)
+    print(f"{us:9.2f} us  {name}", flush=True)
+print("note: isolated back-to-back launches of ONE kernel (weights of that layer stay L2-resident for the small ones)")
