@@ -52,6 +52,31 @@ __device__ __forceinline__ void load_bf16_vec(const bf16* p, float (&out)[N]) {
   }
 }
 
+// N consecutive bf16 kept as raw bits until needed (keeps many cache rows in flight with few registers)
+template <int N> struct RawVec;
+template <> struct RawVec<4> {
+  uint2 v;
+  __device__ __forceinline__ void load(const bf16* p) { v = *reinterpret_cast<const uint2*>(p); }
+  __device__ __forceinline__ void unpack(float (&o)[4]) const {
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.y));
+    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+  }
+};
+template <> struct RawVec<2> {
+  uint32_t v;
+  __device__ __forceinline__ void load(const bf16* p) { v = *reinterpret_cast<const uint32_t*>(p); }
+  __device__ __forceinline__ void unpack(float (&o)[2]) const {
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v));
+    o[0] = a.x; o[1] = a.y;
+  }
+};
+template <> struct RawVec<1> {
+  bf16 v;
+  __device__ __forceinline__ void load(const bf16* p) { v = *p; }
+  __device__ __forceinline__ void unpack(float (&o)[1]) const { o[0] = __bfloat162float(v); }
+};
+
 // h[r][:] = float(embed[tok[r]][:])
 __global__ void decode_embed_kernel(const bf16* __restrict__ embed, const int* __restrict__ tok, float* __restrict__ h,
                                     int H) {
@@ -282,11 +307,12 @@ __global__ void __launch_bounds__(128) decode_attn_fused_kernel(
   }
   const float* knew = xrow + (long long)(nq + kvh) * HD;
   const float* vnew = xrow + (long long)(nq + nkv + kvh) * HD;
-  // Keys are walked UNR at a time: all K/V rows of a batch are requested before any is consumed, so the global-load
-  // latency is paid once per batch instead of once per key.
-  constexpr int UNR = 4;
+  // Keys are walked UNR at a time: every K/V row of a batch is requested (raw 8/4/2-byte loads) before any is
+  // consumed, so the HBM latency of the cache read is paid once per batch, not once per key. With the default
+  // chunk of 32 keys per CTA a warp owns 8 keys = exactly one batch.
+  constexpr int UNR = 8;
   for (int jb = k0 + warp; jb < k1; jb += 4 * UNR) {
-    float kf[UNR][DPL], vf[UNR][DPL];
+    RawVec<DPL> kraw[UNR], vraw[UNR];
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
       const int j = jb + 4 * u;
@@ -300,39 +326,43 @@ __global__ void __launch_bounds__(128) decode_attn_fused_kernel(
           krow = kc + (((long long)r * c_max + (j - P)) * nkv + kvh) * HD;
           vrow = vc + (((long long)r * c_max + (j - P)) * nkv + kvh) * HD;
         }
-        load_bf16_vec<DPL>(krow + lane * DPL, kf[u]);
-        load_bf16_vec<DPL>(vrow + lane * DPL, vf[u]);
+        kraw[u].load(krow + lane * DPL);
+        vraw[u].load(vrow + lane * DPL);
       }
     }
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
       const int j = jb + 4 * u;
       if (j >= k1) break;
+      float kf[DPL], vf[DPL];
       if (j == ctx - 1) {
         // the token being decoded: rotate k, append k/v to the slab, use them from registers
         bf16* kdst = kc + (((long long)r * c_max + step) * nkv + kvh) * HD;
         bf16* vdst = vc + (((long long)r * c_max + step) * nkv + kvh) * HD;
 #pragma unroll
         for (int d = 0; d < DPL; ++d) {
-          kf[u][d] = rot(knew, lane * DPL + d);
-          vf[u][d] = bf16r(vnew[lane * DPL + d]);
-          kdst[lane * DPL + d] = __float2bfloat16(kf[u][d]);
-          vdst[lane * DPL + d] = __float2bfloat16(vf[u][d]);
+          kf[d] = rot(knew, lane * DPL + d);
+          vf[d] = bf16r(vnew[lane * DPL + d]);
+          kdst[lane * DPL + d] = __float2bfloat16(kf[d]);
+          vdst[lane * DPL + d] = __float2bfloat16(vf[d]);
         }
+      } else {
+        kraw[u].unpack(kf);
+        vraw[u].unpack(vf);
       }
 #pragma unroll
       for (int h = 0; h < MAXG; ++h) {
         if (h < gq) {
           float sc = 0.f;
 #pragma unroll
-          for (int d = 0; d < DPL; ++d) sc += qv[h][d] * kf[u][d];
+          for (int d = 0; d < DPL; ++d) sc += qv[h][d] * kf[d];
           sc = wsum(sc);
           const float mn = fmaxf(mrun[h], sc);
           const float corr = __expf(mrun[h] - mn);
           const float pr = __expf(sc - mn);
           lrun[h] = lrun[h] * corr + pr;
 #pragma unroll
-          for (int d = 0; d < DPL; ++d) acc[h][d] = acc[h][d] * corr + pr * vf[u][d];
+          for (int d = 0; d < DPL; ++d) acc[h][d] = acc[h][d] * corr + pr * vf[d];
           mrun[h] = mn;
         }
       }
@@ -380,19 +410,34 @@ __global__ void __launch_bounds__(128) decode_attn_fused_kernel(
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  // per (head, split) rescale factors exp(m_s - m) and the normaliser 1/l, computed once into shared memory;
+  // the value loads below are then independent of each other (MAXS-way unrolled), not a serial L2 round-trip chain.
+  constexpr int MAXS = 32;
+  __shared__ float s_c[MAXG][MAXS];
+  __shared__ float s_invl[MAXG];
+  if (warp < 4) {
+    for (int h = warp; h < gq; h += 4) {
+      const float* p = part + ((long long)r * nq + kvh * gq + h) * nsplit * (HD + 2);
+      const float ms = (lane < nsplit) ? __ldcg(p + lane * (HD + 2) + HD) : -INFINITY;
+      const float ls = (lane < nsplit) ? __ldcg(p + lane * (HD + 2) + HD + 1) : 0.f;
+      float m = ms;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      const float c = (ms == -INFINITY) ? 0.f : __expf(ms - m);
+      s_c[h][lane] = c;
+      const float l = wsum(ls * c);
+      if (lane == 0) s_invl[h] = 1.f / l;
+    }
+  }
+  __syncthreads();
   for (int i = threadIdx.x; i < gq * HD; i += blockDim.x) {
     const int h = i / HD, d = i % HD;
-    const float* p = part + ((long long)r * nq + kvh * gq + h) * nsplit * (HD + 2);
-    float m = -INFINITY;
-    for (int s2 = 0; s2 < nsplit; ++s2) m = fmaxf(m, __ldcg(p + s2 * (HD + 2) + HD));
-    float a = 0.f, l = 0.f;
-    for (int s2 = 0; s2 < nsplit; ++s2) {
-      const float ms = __ldcg(p + s2 * (HD + 2) + HD);
-      const float c = (ms == -INFINITY) ? 0.f : __expf(ms - m);
-      a += __ldcg(p + s2 * (HD + 2) + d) * c;
-      l += __ldcg(p + s2 * (HD + 2) + HD + 1) * c;
-    }
-    out[((long long)r * nq + kvh * gq + h) * HD + d] = __float2bfloat16(a / l);
+    const float* p = part + ((long long)r * nq + kvh * gq + h) * nsplit * (HD + 2) + d;
+    float a = 0.f;
+#pragma unroll
+    for (int s2 = 0; s2 < MAXS; ++s2)
+      if (s2 < nsplit) a += __ldcg(p + s2 * (HD + 2)) * s_c[h][s2];
+    out[((long long)r * nq + kvh * gq + h) * HD + d] = __float2bfloat16(a * s_invl[h]);
   }
 }
 
@@ -468,11 +513,38 @@ __global__ void __launch_bounds__(1024) sample_kernel(const float* __restrict__ 
     for (int i = threadIdx.x; i < 2048; i += blockDim.x) hist[i] = 0;
     __syncthreads();
     const uint32_t nb = 1u << bits[pass];
-    for (int i = threadIdx.x; i < V; i += blockDim.x) {
-      float x = lg[i];
-      if (forbid_eos && i == eos_id) x = -INFINITY;
-      const uint32_t key = f2key(x);
-      if ((key & prefix_mask) == prefix) hist_add_aggregated(hist, (key >> shifts[pass]) & (nb - 1));
+    {
+      // float4 loads, 4 in flight per thread: the scan is L2-latency-bound, not bandwidth-bound
+      const int V4 = ((reinterpret_cast<uintptr_t>(lg) & 15) == 0) ? (V >> 2) : 0;
+      const float4* lg4 = reinterpret_cast<const float4*>(lg);
+      for (int i0 = threadIdx.x; i0 < V4; i0 += 4 * blockDim.x) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * blockDim.x;
+          if (i < V4) v[u] = __ldcg(lg4 + i);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * blockDim.x;
+          if (i < V4) {
+            const float xs[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float x = xs[e];
+              if (forbid_eos && (4 * i + e) == eos_id) x = -INFINITY;
+              const uint32_t key = f2key(x);
+              if ((key & prefix_mask) == prefix) hist_add_aggregated(hist, (key >> shifts[pass]) & (nb - 1));
+            }
+          }
+        }
+      }
+      for (int i = 4 * V4 + threadIdx.x; i < V; i += blockDim.x) {
+        float x = lg[i];
+        if (forbid_eos && i == eos_id) x = -INFINITY;
+        const uint32_t key = f2key(x);
+        if ((key & prefix_mask) == prefix) hist_add_aggregated(hist, (key >> shifts[pass]) & (nb - 1));
+      }
     }
     __syncthreads();
     if (threadIdx.x < 32) {
@@ -516,16 +588,38 @@ __global__ void __launch_bounds__(1024) sample_kernel(const float* __restrict__ 
   const uint32_t kth_key = prefix;  // every key >= kth_key survives (ties kept)
   if (threadIdx.x == 0) s_count = 0;
   __syncthreads();
-  for (int i = threadIdx.x; i < V; i += blockDim.x) {
-    float x = lg[i];
-    if (forbid_eos && i == eos_id) x = -INFINITY;
-    if (f2key(x) >= kth_key) {
-      const int slot = atomicAdd(&s_count, 1);
-      if (slot < kMaxKeep) {
-        s_val[slot] = x * inv_temp;
-        s_idx[slot] = i;
+  {
+    const int V4 = ((reinterpret_cast<uintptr_t>(lg) & 15) == 0) ? (V >> 2) : 0;
+    const float4* lg4 = reinterpret_cast<const float4*>(lg);
+    auto consider = [&](float x, int i) {
+      if (forbid_eos && i == eos_id) x = -INFINITY;
+      if (f2key(x) >= kth_key) {
+        const int slot = atomicAdd(&s_count, 1);
+        if (slot < kMaxKeep) {
+          s_val[slot] = x * inv_temp;
+          s_idx[slot] = i;
+        }
+      }
+    };
+    for (int i0 = threadIdx.x; i0 < V4; i0 += 4 * blockDim.x) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * blockDim.x;
+        if (i < V4) v[u] = __ldcg(lg4 + i);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * blockDim.x;
+        if (i < V4) {
+          consider(v[u].x, 4 * i);
+          consider(v[u].y, 4 * i + 1);
+          consider(v[u].z, 4 * i + 2);
+          consider(v[u].w, 4 * i + 3);
+        }
       }
     }
+    for (int i = 4 * V4 + threadIdx.x; i < V; i += blockDim.x) consider(lg[i], i);
   }
   __syncthreads();
   const int n = min(s_count, kMaxKeep);
@@ -645,6 +739,7 @@ int iadr1_decode_attention_fused(const float* qkv, const float* cos_tab, const f
                                  void* stream) {
   if (rows <= 0) return 0;
   if (nq % nkv || nq / nkv > 8) return set_error("decode_attention_fused: group size %d unsupported (max 8)", nq / nkv);
+  if (nsplit < 1 || nsplit > 32) return set_error("decode_attention_fused: nsplit %d out of range (1..32)", nsplit);
   const int chunk = (p_max + c_max + nsplit - 1) / nsplit;
   cudaStream_t st = (cudaStream_t)stream;
 #define IADR1_DECODE_FUSED(HD)                                                                                       \
