@@ -294,6 +294,14 @@ __global__ void __launch_bounds__(128) decode_attn_fused_kernel(
     return bf16r(a + b);
   };
 
+  // rotated, pre-scaled queries of this kv head's group: computed ONCE per CTA (threads split the gq x HD elements),
+  // staged in shared memory, then every warp picks up its lane's dims.
+  __shared__ float sm_q[MAXG][HD];
+  for (int i = threadIdx.x; i < gq * HD; i += blockDim.x) {
+    const int h = i / HD, d = i % HD;
+    sm_q[h][d] = rot(xrow + (long long)(kvh * gq + h) * HD, d) * scale;
+  }
+  __syncthreads();
   float qv[MAXG][DPL], acc[MAXG][DPL], mrun[MAXG], lrun[MAXG];
 #pragma unroll
   for (int h = 0; h < MAXG; ++h) {
@@ -302,7 +310,7 @@ __global__ void __launch_bounds__(128) decode_attn_fused_kernel(
 #pragma unroll
     for (int d = 0; d < DPL; ++d) {
       acc[h][d] = 0.f;
-      qv[h][d] = (h < gq) ? rot(xrow + (long long)(kvh * gq + h) * HD, lane * DPL + d) * scale : 0.f;
+      qv[h][d] = (h < gq) ? sm_q[h][lane * DPL + d] : 0.f;
     }
   }
   const float* knew = xrow + (long long)(nq + kvh) * HD;
@@ -400,16 +408,20 @@ __global__ void __launch_bounds__(128) decode_attn_fused_kernel(
     }
   }
   // ---- last CTA of this (row, kv head) merges the splits ----
-  __threadfence();
+  // bar.sync orders the CTA's partial writes before thread 0's (cumulative) gpu-scope fence + ticket; one fence per CTA,
+  // not one per thread.
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence();
     const int t = atomicAdd(&tickets[r * nkv + kvh], 1);
     s_last = (t == nsplit - 1);
-    if (s_last) tickets[r * nkv + kvh] = 0;  // re-arm for the next layer / step
+    if (s_last) {
+      tickets[r * nkv + kvh] = 0;  // re-arm for the next layer / step
+      __threadfence();
+    }
   }
   __syncthreads();
   if (!s_last) return;
-  __threadfence();
   // per (head, split) rescale factors exp(m_s - m) and the normaliser 1/l, computed once into shared memory;
   // the value loads below are then independent of each other (MAXS-way unrolled), not a serial L2 round-trip chain.
   constexpr int MAXS = 32;

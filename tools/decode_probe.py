@@ -28,17 +28,24 @@ for ex in synthetic_dataset(groups, 448):
     encs.append(dict(input_ids=e["input_ids"][0].numpy(), pixel_values=e["pixel_values"].to(dev), grid_thw=e["image_grid_thw"].tolist()))
 
 
-def timeit(fn, n=50, warm=5):
-    for _ in range(warm):
+def timeit(fn, n=20, reps=10):
+    """GPU-side time per launch: n launches captured in a CUDA graph (no Python / launch overhead), replayed reps times."""
+    for _ in range(3):
         fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(n):
+            fn()
+    g.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(n):
-        fn()
+    for _ in range(reps):
+        g.replay()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / n * 1000  # us
+    return e0.elapsed_time(e1) / (n * reps) * 1000  # us
 
 
 for graph in (False, True):
@@ -58,6 +65,7 @@ items = {
     "rmsnorm_f32in(+zero)": lambda: lib.iadr1_rmsnorm_f32in(eng.h.data_ptr(), p[b + "ln1.weight"].data_ptr(), eng.xn.data_ptr(), R, H, 1e-6, eng.qkv.data_ptr(), t.qkv_dim, s),
     f"gemm qkv split{sk_qkv}": lambda: eng._skinny(p[b + "qkv.weight"], eng.xn, eng.qkv, split_k=sk_qkv, atomic=True, bias=p[b + "qkv.bias"]),
     "gemm qkv split1": lambda: eng._skinny(p[b + "qkv.weight"], eng.xn, eng.qkv, split_k=1, atomic=True, bias=p[b + "qkv.bias"]),
+    "gemm qkv split7 stages4": lambda: L.gemm(p[b + "qkv.weight"], eng.xn, out=eng.qkv, trans_out=True, split_k=sk_qkv, atomic=True, bias=p[b + "qkv.bias"], bias_per_m=True, block_n=eng.block_n, stages=4),
     "attn_fused": lambda: lib.iadr1_decode_attention_fused(
         eng.qkv.data_ptr(), eng.cos_tab.data_ptr(), eng.sin_tab.data_ptr(), eng.rope_delta.data_ptr(), eng.kp[0].data_ptr(),
         eng.vp[0].data_ptr(), eng.kc[0].data_ptr(), eng.vc[0].data_ptr(), eng.state.data_ptr(), eng.row_group.data_ptr(),
@@ -65,6 +73,7 @@ items = {
         eng.c_max, eng.nsplit, eng.max_pos, hd ** -0.5, s),
     f"gemm o split{sk_o}": lambda: eng._skinny(p[b + "o.weight"], eng.attn, eng.h, split_k=sk_o, atomic=True),
     "gemm gate_up": lambda: eng._skinny(p[b + "gate_up.weight"], eng.xn, eng.gu),
+    "gemm gate_up 86ctas": lambda: L.gemm(p[b + "gate_up.weight"], eng.xn, out=eng.gu, trans_out=True, block_n=eng.block_n, max_ctas=86),
     "act_mul": lambda: ops.act_mul_fwd(eng.gu, I, ops.ACT_SILU, gated=True, out=eng.act),
     f"gemm down split{sk_d}": lambda: eng._skinny(p[b + "down.weight"], eng.act, eng.h, split_k=sk_d, atomic=True),
     "gemm lm_head": lambda: eng._skinny(vlm.params.lm_head, eng.xn, eng.logits),
@@ -76,4 +85,4 @@ tot = 0
 for name, fn in items.items():
     us = timeit(fn)
     print(f"{us:9.2f} us  {name}", flush=True)
-print("note: isolated back-to-back launches of ONE kernel (weights of that layer stay L2-resident for the small ones)")
+print("note: back-to-back launches of ONE kernel inside a CUDA graph (that layer's weights stay L2-resident for the small ones)")
