@@ -295,35 +295,39 @@ __global__ void __launch_bounds__(128) decode_attn_fused_kernel(
   };
 
   // rotated, pre-scaled queries of this kv head's group: computed ONCE per CTA (threads split the gq x HD elements),
-  // staged in shared memory, then every warp picks up its lane's dims.
+  // staged in shared memory.
   __shared__ float sm_q[MAXG][HD];
   for (int i = threadIdx.x; i < gq * HD; i += blockDim.x) {
     const int h = i / HD, d = i % HD;
     sm_q[h][d] = rot(xrow + (long long)(kvh * gq + h) * HD, d) * scale;
   }
   __syncthreads();
-  float qv[MAXG][DPL], acc[MAXG][DPL], mrun[MAXG], lrun[MAXG];
+  // Work split: warp w owns HPW = ceil(gq / 4) query heads and walks ALL keys of the chunk for them (the 4 warps
+  // re-read the same K/V rows through L1). Few live registers per thread -> many resident CTAs to hide the chain of
+  // dependent memory round trips; no cross-warp merge is needed because heads are disjoint.
+  constexpr int HPW = 2;  // MAXG / 4
+  const int hpw = (gq + 3) >> 2;
+  const int h0 = warp * hpw;
+  float qv[HPW][DPL], acc[HPW][DPL], mrun[HPW], lrun[HPW];
 #pragma unroll
-  for (int h = 0; h < MAXG; ++h) {
-    mrun[h] = -INFINITY;
-    lrun[h] = 0.f;
+  for (int hh = 0; hh < HPW; ++hh) {
+    mrun[hh] = -INFINITY;
+    lrun[hh] = 0.f;
+    const bool on = hh < hpw && h0 + hh < gq;
 #pragma unroll
     for (int d = 0; d < DPL; ++d) {
-      acc[h][d] = 0.f;
-      qv[h][d] = (h < gq) ? sm_q[h][lane * DPL + d] : 0.f;
+      acc[hh][d] = 0.f;
+      qv[hh][d] = on ? sm_q[h0 + hh][lane * DPL + d] : 0.f;
     }
   }
   const float* knew = xrow + (long long)(nq + kvh) * HD;
   const float* vnew = xrow + (long long)(nq + nkv + kvh) * HD;
-  // Keys are walked UNR at a time: every K/V row of a batch is requested (raw 8/4/2-byte loads) before any is
-  // consumed, so the HBM latency of the cache read is paid once per batch, not once per key. With the default
-  // chunk of 32 keys per CTA a warp owns 8 keys = exactly one batch.
-  constexpr int UNR = 8;
-  for (int jb = k0 + warp; jb < k1; jb += 4 * UNR) {
+  constexpr int UNR = 8;  // K/V rows requested before any is consumed
+  for (int jb = k0; jb < k1; jb += UNR) {
     RawVec<DPL> kraw[UNR], vraw[UNR];
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
-      const int j = jb + 4 * u;
+      const int j = jb + u;
       if (j < k1 && j != ctx - 1) {
         const bf16* krow;
         const bf16* vrow;
@@ -340,71 +344,57 @@ __global__ void __launch_bounds__(128) decode_attn_fused_kernel(
     }
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
-      const int j = jb + 4 * u;
+      const int j = jb + u;
       if (j >= k1) break;
       float kf[DPL], vf[DPL];
       if (j == ctx - 1) {
-        // the token being decoded: rotate k, append k/v to the slab, use them from registers
-        bf16* kdst = kc + (((long long)r * c_max + step) * nkv + kvh) * HD;
-        bf16* vdst = vc + (((long long)r * c_max + step) * nkv + kvh) * HD;
+        // the token being decoded: rotate k and use k/v from registers; warp 0 also appends them to the row's slab
 #pragma unroll
         for (int d = 0; d < DPL; ++d) {
           kf[d] = rot(knew, lane * DPL + d);
           vf[d] = bf16r(vnew[lane * DPL + d]);
-          kdst[lane * DPL + d] = __float2bfloat16(kf[d]);
-          vdst[lane * DPL + d] = __float2bfloat16(vf[d]);
+        }
+        if (warp == 0) {
+          bf16* kdst = kc + (((long long)r * c_max + step) * nkv + kvh) * HD;
+          bf16* vdst = vc + (((long long)r * c_max + step) * nkv + kvh) * HD;
+#pragma unroll
+          for (int d = 0; d < DPL; ++d) {
+            kdst[lane * DPL + d] = __float2bfloat16(kf[d]);
+            vdst[lane * DPL + d] = __float2bfloat16(vf[d]);
+          }
         }
       } else {
         kraw[u].unpack(kf);
         vraw[u].unpack(vf);
       }
 #pragma unroll
-      for (int h = 0; h < MAXG; ++h) {
-        if (h < gq) {
-          float sc = 0.f;
+      for (int hh = 0; hh < HPW; ++hh) {
+        float sc = 0.f;
 #pragma unroll
-          for (int d = 0; d < DPL; ++d) sc += qv[h][d] * kf[d];
-          sc = wsum(sc);
-          const float mn = fmaxf(mrun[h], sc);
-          const float corr = __expf(mrun[h] - mn);
-          const float pr = __expf(sc - mn);
-          lrun[h] = lrun[h] * corr + pr;
+        for (int d = 0; d < DPL; ++d) sc += qv[hh][d] * kf[d];
+        sc = wsum(sc);
+        const float mn = fmaxf(mrun[hh], sc);
+        const float corr = __expf(mrun[hh] - mn);
+        const float pr = __expf(sc - mn);
+        lrun[hh] = lrun[hh] * corr + pr;
 #pragma unroll
-          for (int d = 0; d < DPL; ++d) acc[h][d] = acc[h][d] * corr + pr * vf[d];
-          mrun[h] = mn;
-        }
+        for (int d = 0; d < DPL; ++d) acc[hh][d] = acc[hh][d] * corr + pr * vf[d];
+        mrun[hh] = mn;
       }
     }
   }
-  __shared__ float sm_m[4][MAXG], sm_l[4][MAXG], sm_acc[4][MAXG][HD];
+  // each warp writes the partials of its own heads: part[r][head][split][HD + 2]
   __shared__ int s_last;
-  if (lane == 0) {
 #pragma unroll
-    for (int h = 0; h < MAXG; ++h) {
-      sm_m[warp][h] = mrun[h];
-      sm_l[warp][h] = lrun[h];
-    }
-  }
+  for (int hh = 0; hh < HPW; ++hh) {
+    if (hh < hpw && h0 + hh < gq) {
+      float* dst = part + (((long long)r * nq + kvh * gq + h0 + hh) * nsplit + sp) * (HD + 2);
 #pragma unroll
-  for (int h = 0; h < MAXG; ++h)
-#pragma unroll
-    for (int d = 0; d < DPL; ++d) sm_acc[warp][h][lane * DPL + d] = acc[h][d];
-  __syncthreads();
-  for (int i = threadIdx.x; i < gq * HD; i += blockDim.x) {
-    const int h = i / HD, d = i % HD;
-    const float m = fmaxf(fmaxf(sm_m[0][h], sm_m[1][h]), fmaxf(sm_m[2][h], sm_m[3][h]));
-    float a = 0.f, l = 0.f;
-#pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      const float c = (sm_m[w][h] == -INFINITY) ? 0.f : __expf(sm_m[w][h] - m);
-      a += sm_acc[w][h][d] * c;
-      l += sm_l[w][h] * c;
-    }
-    float* dst = part + (((long long)r * nq + kvh * gq + h) * nsplit + sp) * (HD + 2);
-    dst[d] = a;
-    if (d == 0) {
-      dst[HD] = m;
-      dst[HD + 1] = l;
+      for (int d = 0; d < DPL; ++d) dst[lane * DPL + d] = acc[hh][d];
+      if (lane == 0) {
+        dst[HD] = mrun[hh];
+        dst[HD + 1] = lrun[hh];
+      }
     }
   }
   // ---- last CTA of this (row, kv head) merges the splits ----

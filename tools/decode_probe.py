@@ -55,14 +55,22 @@ for graph in (False, True):
     print(f"R={eng.R} layers={layers} graph={graph}: {st['decode_ms'] / st['steps'] * 1000:.1f} us per decode step "
           f"({st['decode_ms'] / st['steps'] * 1000 / layers:.1f} us per layer incl. head)", flush=True)
 
-t, p, lib, s = cfg.text, vlm.p, L.lib(), L.stream_ptr()
+t, p, lib = cfg.text, vlm.p, L.lib()
+
+
+class _S:
+    def __index__(self):
+        return L.stream_ptr()
+
+
+s = None
 R, H, I, nq, nkv, hd = eng.R, t.hidden_size, t.intermediate_size, t.num_heads, t.num_kv_heads, t.head_dim
 eng.state[0] = 300  # mid-rollout context
 b = "layers.0."
 sk_qkv, sk_o, sk_d = _split_for(t.qkv_dim, H), _split_for(H, nq * hd), _split_for(H, I)
 items = {
-    "decode_embed": lambda: lib.iadr1_decode_embed(p["embed_tokens.weight"].data_ptr(), eng.tok.data_ptr(), eng.h.data_ptr(), R, H, s),
-    "rmsnorm_f32in(+zero)": lambda: lib.iadr1_rmsnorm_f32in(eng.h.data_ptr(), p[b + "ln1.weight"].data_ptr(), eng.xn.data_ptr(), R, H, 1e-6, eng.qkv.data_ptr(), t.qkv_dim, s),
+    "decode_embed": lambda: lib.iadr1_decode_embed(p["embed_tokens.weight"].data_ptr(), eng.tok.data_ptr(), eng.h.data_ptr(), R, H, L.stream_ptr()),
+    "rmsnorm_f32in(+zero)": lambda: lib.iadr1_rmsnorm_f32in(eng.h.data_ptr(), p[b + "ln1.weight"].data_ptr(), eng.xn.data_ptr(), R, H, 1e-6, eng.qkv.data_ptr(), t.qkv_dim, L.stream_ptr()),
     f"gemm qkv split{sk_qkv}": lambda: eng._skinny(p[b + "qkv.weight"], eng.xn, eng.qkv, split_k=sk_qkv, atomic=True, bias=p[b + "qkv.bias"]),
     "gemm qkv split1": lambda: eng._skinny(p[b + "qkv.weight"], eng.xn, eng.qkv, split_k=1, atomic=True, bias=p[b + "qkv.bias"]),
     "gemm qkv split7 stages4": lambda: L.gemm(p[b + "qkv.weight"], eng.xn, out=eng.qkv, trans_out=True, split_k=sk_qkv, atomic=True, bias=p[b + "qkv.bias"], bias_per_m=True, block_n=eng.block_n, stages=4),
@@ -70,7 +78,7 @@ items = {
         eng.qkv.data_ptr(), eng.cos_tab.data_ptr(), eng.sin_tab.data_ptr(), eng.rope_delta.data_ptr(), eng.kp[0].data_ptr(),
         eng.vp[0].data_ptr(), eng.kc[0].data_ptr(), eng.vc[0].data_ptr(), eng.state.data_ptr(), eng.row_group.data_ptr(),
         eng.row_plen.data_ptr(), eng.part.data_ptr(), eng.tickets.data_ptr(), eng.attn.data_ptr(), R, nq, nkv, hd, eng.p_max,
-        eng.c_max, eng.nsplit, eng.max_pos, hd ** -0.5, s),
+        eng.c_max, eng.nsplit, eng.max_pos, hd ** -0.5, L.stream_ptr()),
     f"gemm o split{sk_o}": lambda: eng._skinny(p[b + "o.weight"], eng.attn, eng.h, split_k=sk_o, atomic=True),
     "gemm gate_up": lambda: eng._skinny(p[b + "gate_up.weight"], eng.xn, eng.gu),
     "gemm gate_up 86ctas": lambda: L.gemm(p[b + "gate_up.weight"], eng.xn, out=eng.gu, trans_out=True, block_n=eng.block_n, max_ctas=86),
@@ -78,10 +86,19 @@ items = {
     f"gemm down split{sk_d}": lambda: eng._skinny(p[b + "down.weight"], eng.act, eng.h, split_k=sk_d, atomic=True),
     "gemm lm_head": lambda: eng._skinny(vlm.params.lm_head, eng.xn, eng.logits),
     "sample": lambda: lib.iadr1_sample(eng.logits.data_ptr(), R, t.vocab_size, 0.9, 50, 0.9, 1, eng.state.data_ptr(), eng.tok.data_ptr(),
-                                       eng.finished.data_ptr(), eng.out_tokens.data_ptr(), eng.c_max, cfg.eos_token_id, cfg.pad_token_id, 1, 0, s),
+                                       eng.finished.data_ptr(), eng.out_tokens.data_ptr(), eng.c_max, cfg.eos_token_id, cfg.pad_token_id, 1, 0, L.stream_ptr()),
 }
 eng.finished.zero_()
 tot = 0
+only = sys.argv[3] if len(sys.argv) > 3 else None
+if only:
+    for name, fn in items.items():
+        if only in name:
+            for _ in range(8):
+                fn()
+            torch.cuda.synchronize()
+            print('ran', name)
+    sys.exit(0)
 for name, fn in items.items():
     us = timeit(fn)
     print(f"{us:9.2f} us  {name}", flush=True)
