@@ -15,6 +15,7 @@
 #include <cuda_bf16.h>
 #include <curand_kernel.h>
 #include <stdint.h>
+#include <cstdlib>
 
 namespace iadr1 {
 
@@ -50,6 +51,14 @@ __device__ __forceinline__ void load_bf16_vec(const bf16* p, float (&out)[N]) {
 #pragma unroll
     for (int i = 0; i < N; ++i) out[i] = __bfloat162float(p[i]);
   }
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
 // N consecutive bf16 kept as raw bits until needed (keeps many cache rows in flight with few registers)
@@ -266,7 +275,7 @@ __global__ void __launch_bounds__(128) decode_attn_fused_kernel(
     const int* __restrict__ rope_delta, const bf16* __restrict__ kp, const bf16* __restrict__ vp, bf16* __restrict__ kc,
     bf16* __restrict__ vc, const int* __restrict__ state, const int* __restrict__ row_group,
     const int* __restrict__ row_plen, float* __restrict__ part, int* __restrict__ tickets, bf16* __restrict__ out, int nq,
-    int nkv, int p_max, int c_max, int chunk, int max_pos, float scale) {
+    int nkv, int p_max, int c_max, int chunk, int max_pos, float scale, int dbg) {
   constexpr int DPL = HD / 32;
   constexpr int MAXG = 8;
   constexpr int HALF = HD / 2;
@@ -299,7 +308,7 @@ __global__ void __launch_bounds__(128) decode_attn_fused_kernel(
   __shared__ float sm_q[MAXG][HD];
   for (int i = threadIdx.x; i < gq * HD; i += blockDim.x) {
     const int h = i / HD, d = i % HD;
-    sm_q[h][d] = rot(xrow + (long long)(kvh * gq + h) * HD, d) * scale;
+    sm_q[h][d] = (dbg & 1) ? 0.f : rot(xrow + (long long)(kvh * gq + h) * HD, d) * scale;
   }
   __syncthreads();
   // Work split: warp w owns HPW = ceil(gq / 4) query heads and walks ALL keys of the chunk for them (the 4 warps
@@ -322,64 +331,71 @@ __global__ void __launch_bounds__(128) decode_attn_fused_kernel(
   }
   const float* knew = xrow + (long long)(nq + kvh) * HD;
   const float* vnew = xrow + (long long)(nq + nkv + kvh) * HD;
-  constexpr int UNR = 8;  // K/V rows requested before any is consumed
-  for (int jb = k0; jb < k1; jb += UNR) {
-    RawVec<DPL> kraw[UNR], vraw[UNR];
+  // The chunk's K/V rows are staged in shared memory with ONE round of cp.async (16 B per request, every thread
+  // issuing all of its requests before anyone waits), so the cache read costs one memory latency per CTA instead of one
+  // per batch of keys. The token being decoded is not in the cache yet: warp 0 rotates it, appends it to the row's
+  // slab and drops it into the staging buffer.
+  extern __shared__ __align__(16) uint8_t sm_kv_raw[];
+  bf16* sK = reinterpret_cast<bf16*>(sm_kv_raw);
+  bf16* sV = sK + (size_t)chunk * HD;
+  const int nkeys = max(0, k1 - k0);
+  if (!(dbg & 2)) {
+    constexpr int PPR = HD / 8;  // 16-byte pieces per row
+    for (int q = threadIdx.x; q < nkeys * PPR; q += blockDim.x) {
+      const int jj = q / PPR, piece = q % PPR;
+      const int j = k0 + jj;
+      if (j == ctx - 1) continue;
+      const bf16* krow;
+      const bf16* vrow;
+      if (j < P) {
+        krow = kp + (((long long)grp * p_max + j) * nkv + kvh) * HD;
+        vrow = vp + (((long long)grp * p_max + j) * nkv + kvh) * HD;
+      } else {
+        krow = kc + (((long long)r * c_max + (j - P)) * nkv + kvh) * HD;
+        vrow = vc + (((long long)r * c_max + (j - P)) * nkv + kvh) * HD;
+      }
+      cp_async16(sK + (size_t)jj * HD + piece * 8, krow + piece * 8);
+      cp_async16(sV + (size_t)jj * HD + piece * 8, vrow + piece * 8);
+    }
+    if (ctx - 1 >= k0 && ctx - 1 < k1 && warp == 0) {
+      const int jj = ctx - 1 - k0;
+      bf16* kdst = kc + (((long long)r * c_max + step) * nkv + kvh) * HD;
+      bf16* vdst = vc + (((long long)r * c_max + step) * nkv + kvh) * HD;
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const int j = jb + u;
-      if (j < k1 && j != ctx - 1) {
-        const bf16* krow;
-        const bf16* vrow;
-        if (j < P) {
-          krow = kp + (((long long)grp * p_max + j) * nkv + kvh) * HD;
-          vrow = vp + (((long long)grp * p_max + j) * nkv + kvh) * HD;
-        } else {
-          krow = kc + (((long long)r * c_max + (j - P)) * nkv + kvh) * HD;
-          vrow = vc + (((long long)r * c_max + (j - P)) * nkv + kvh) * HD;
-        }
-        kraw[u].load(krow + lane * DPL);
-        vraw[u].load(vrow + lane * DPL);
+      for (int d = 0; d < DPL; ++d) {
+        const bf16 kb = __float2bfloat16(rot(knew, lane * DPL + d));
+        const bf16 vb = __float2bfloat16(vnew[lane * DPL + d]);
+        sK[(size_t)jj * HD + lane * DPL + d] = kb;
+        sV[(size_t)jj * HD + lane * DPL + d] = vb;
+        kdst[lane * DPL + d] = kb;
+        vdst[lane * DPL + d] = vb;
       }
     }
+    cp_async_wait_all();
+    __syncthreads();
+    constexpr int UNR = 4;
+    for (int jb = 0; jb < nkeys; jb += UNR) {
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const int j = jb + u;
-      if (j >= k1) break;
-      float kf[DPL], vf[DPL];
-      if (j == ctx - 1) {
-        // the token being decoded: rotate k and use k/v from registers; warp 0 also appends them to the row's slab
+      for (int u = 0; u < UNR; ++u) {
+        const int jj = jb + u;
+        if (jj >= nkeys) break;
+        float kf[DPL], vf[DPL];
+        load_bf16_vec<DPL>(sK + (size_t)jj * HD + lane * DPL, kf);
+        load_bf16_vec<DPL>(sV + (size_t)jj * HD + lane * DPL, vf);
 #pragma unroll
-        for (int d = 0; d < DPL; ++d) {
-          kf[d] = rot(knew, lane * DPL + d);
-          vf[d] = bf16r(vnew[lane * DPL + d]);
+        for (int hh = 0; hh < HPW; ++hh) {
+          float sc = 0.f;
+#pragma unroll
+          for (int d = 0; d < DPL; ++d) sc += qv[hh][d] * kf[d];
+          sc = wsum(sc);
+          const float mn = fmaxf(mrun[hh], sc);
+          const float corr = __expf(mrun[hh] - mn);
+          const float pr = __expf(sc - mn);
+          lrun[hh] = lrun[hh] * corr + pr;
+#pragma unroll
+          for (int d = 0; d < DPL; ++d) acc[hh][d] = acc[hh][d] * corr + pr * vf[d];
+          mrun[hh] = mn;
         }
-        if (warp == 0) {
-          bf16* kdst = kc + (((long long)r * c_max + step) * nkv + kvh) * HD;
-          bf16* vdst = vc + (((long long)r * c_max + step) * nkv + kvh) * HD;
-#pragma unroll
-          for (int d = 0; d < DPL; ++d) {
-            kdst[lane * DPL + d] = __float2bfloat16(kf[d]);
-            vdst[lane * DPL + d] = __float2bfloat16(vf[d]);
-          }
-        }
-      } else {
-        kraw[u].unpack(kf);
-        vraw[u].unpack(vf);
-      }
-#pragma unroll
-      for (int hh = 0; hh < HPW; ++hh) {
-        float sc = 0.f;
-#pragma unroll
-        for (int d = 0; d < DPL; ++d) sc += qv[hh][d] * kf[d];
-        sc = wsum(sc);
-        const float mn = fmaxf(mrun[hh], sc);
-        const float corr = __expf(mrun[hh] - mn);
-        const float pr = __expf(sc - mn);
-        lrun[hh] = lrun[hh] * corr + pr;
-#pragma unroll
-        for (int d = 0; d < DPL; ++d) acc[hh][d] = acc[hh][d] * corr + pr * vf[d];
-        mrun[hh] = mn;
       }
     }
   }
@@ -397,49 +413,63 @@ __global__ void __launch_bounds__(128) decode_attn_fused_kernel(
       }
     }
   }
+  if (dbg & 4) return;
   // ---- last CTA of this (row, kv head) merges the splits ----
-  // bar.sync orders the CTA's partial writes before thread 0's (cumulative) gpu-scope fence + ticket; one fence per CTA,
-  // not one per thread.
+  // bar.sync orders the CTA's partial writes before thread 0's (cumulative) gpu-scope fence + ticket; one fence per CTA.
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
     const int t = atomicAdd(&tickets[r * nkv + kvh], 1);
     s_last = (t == nsplit - 1);
     if (s_last) {
       tickets[r * nkv + kvh] = 0;  // re-arm for the next layer / step
-      __threadfence();
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
     }
   }
   __syncthreads();
   if (!s_last) return;
-  // per (head, split) rescale factors exp(m_s - m) and the normaliser 1/l, computed once into shared memory;
-  // the value loads below are then independent of each other (MAXS-way unrolled), not a serial L2 round-trip chain.
+  // per (head, split) rescale factors exp(m_s - m) and the normaliser 1/l, computed once into shared memory
   constexpr int MAXS = 32;
   __shared__ float s_c[MAXG][MAXS];
   __shared__ float s_invl[MAXG];
-  if (warp < 4) {
-    for (int h = warp; h < gq; h += 4) {
-      const float* p = part + ((long long)r * nq + kvh * gq + h) * nsplit * (HD + 2);
-      const float ms = (lane < nsplit) ? __ldcg(p + lane * (HD + 2) + HD) : -INFINITY;
-      const float ls = (lane < nsplit) ? __ldcg(p + lane * (HD + 2) + HD + 1) : 0.f;
-      float m = ms;
+  for (int h = warp; h < gq; h += 4) {
+    const float* p = part + ((long long)r * nq + kvh * gq + h) * nsplit * (HD + 2);
+    const float ms = (lane < nsplit) ? __ldcg(p + lane * (HD + 2) + HD) : -INFINITY;
+    const float ls = (lane < nsplit) ? __ldcg(p + lane * (HD + 2) + HD + 1) : 0.f;
+    float m = ms;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-      const float c = (ms == -INFINITY) ? 0.f : __expf(ms - m);
-      s_c[h][lane] = c;
-      const float l = wsum(ls * c);
-      if (lane == 0) s_invl[h] = 1.f / l;
-    }
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    const float c = (ms == -INFINITY) ? 0.f : __expf(ms - m);
+    s_c[h][lane] = c;
+    const float l = wsum(ls * c);
+    if (lane == 0) s_invl[h] = 1.f / l;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < gq * HD; i += blockDim.x) {
-    const int h = i / HD, d = i % HD;
-    const float* p = part + ((long long)r * nq + kvh * gq + h) * nsplit * (HD + 2) + d;
-    float a = 0.f;
+  // every thread owns OUTS outputs (element o = threadIdx.x + 128 * oo); the split loop is outermost so that OUTS
+  // independent L2 loads are in flight per iteration instead of one serial chain per output.
+  constexpr int OUTS = (MAXG * HD + 127) / 128;
+  float a[OUTS];
 #pragma unroll
-    for (int s2 = 0; s2 < MAXS; ++s2)
-      if (s2 < nsplit) a += __ldcg(p + s2 * (HD + 2)) * s_c[h][s2];
-    out[((long long)r * nq + kvh * gq + h) * HD + d] = __float2bfloat16(a * s_invl[h]);
+  for (int oo = 0; oo < OUTS; ++oo) a[oo] = 0.f;
+  const float* pbase = part + ((long long)r * nq + kvh * gq) * nsplit * (HD + 2);
+#pragma unroll 2
+  for (int s2 = 0; s2 < nsplit; ++s2) {
+#pragma unroll
+    for (int oo = 0; oo < OUTS; ++oo) {
+      const int o = threadIdx.x + 128 * oo;
+      if (o < gq * HD) {
+        const int h = o / HD, d = o % HD;
+        a[oo] += __ldcg(pbase + ((long long)h * nsplit + s2) * (HD + 2) + d) * s_c[h][s2];
+      }
+    }
+  }
+#pragma unroll
+  for (int oo = 0; oo < OUTS; ++oo) {
+    const int o = threadIdx.x + 128 * oo;
+    if (o < gq * HD) {
+      const int h = o / HD, d = o % HD;
+      out[((long long)r * nq + kvh * gq + h) * HD + d] = __float2bfloat16(a[oo] * s_invl[h]);
+    }
   }
 }
 
@@ -744,10 +774,15 @@ int iadr1_decode_attention_fused(const float* qkv, const float* cos_tab, const f
   if (nsplit < 1 || nsplit > 32) return set_error("decode_attention_fused: nsplit %d out of range (1..32)", nsplit);
   const int chunk = (p_max + c_max + nsplit - 1) / nsplit;
   cudaStream_t st = (cudaStream_t)stream;
+  const size_t kv_smem = (size_t)chunk * hd * 4;
+  if (kv_smem > 160 * 1024) return set_error("decode_attention_fused: context too long for one staging buffer (chunk %d)", chunk);
+  static const int dbg = getenv("IADR1_ATTN_DEBUG") ? atoi(getenv("IADR1_ATTN_DEBUG")) : 0;  // phase-skipping, probes only
 #define IADR1_DECODE_FUSED(HD)                                                                                       \
-  decode_attn_fused_kernel<HD><<<dim3(rows, nkv, nsplit), 128, 0, st>>>(                                             \
+  if (kv_smem > 48 * 1024)                                                                                           \
+    cudaFuncSetAttribute(decode_attn_fused_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);     \
+  decode_attn_fused_kernel<HD><<<dim3(rows, nkv, nsplit), 128, kv_smem, st>>>(                                             \
       qkv, cos_tab, sin_tab, rope_delta, (const bf16*)kp, (const bf16*)vp, (bf16*)kc, (bf16*)vc, state, row_group,   \
-      row_plen, part, tickets, (bf16*)out, nq, nkv, p_max, c_max, chunk, max_pos, scale)
+      row_plen, part, tickets, (bf16*)out, nq, nkv, p_max, c_max, chunk, max_pos, scale, dbg)
   if (hd == 128) IADR1_DECODE_FUSED(128);
   else if (hd == 64) IADR1_DECODE_FUSED(64);
   else if (hd == 32) IADR1_DECODE_FUSED(32);
