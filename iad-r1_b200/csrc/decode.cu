@@ -265,9 +265,16 @@ __global__ void __launch_bounds__(128) decode_attn_partial_kernel(
 
 // ------------------------------------------------------------------------------------------------
 // Fused decode attention: rotary on q/k (HF bf16 op order) + KV append + split-KV attention + combine in ONE launch.
-// Grid (R, nkv, nsplit). Every CTA rotates its kv head's `gq` query heads straight from the fp32 qkv row; the CTA whose
-// key chunk contains the new position also rotates k, appends k/v to the row's slab and uses them from registers.
-// Partials go to `part`; the last CTA of each (row, kv head) to finish (atomic ticket) merges them and writes bf16 out.
+// Grid (R, nkv, nsplit), 4 warps. Per CTA:
+//   1. the gq rotated, pre-scaled queries of this kv head are built once into shared memory;
+//   2. the chunk's K/V rows are staged in shared memory with ONE round of cp.async (one memory latency per CTA); K is
+//      stored with its 16-byte pieces XOR-swizzled by the key index so that "one lane = one key" reads are conflict-free;
+//      the token being decoded is rotated, appended to the row's slab and dropped into the staging buffers by warp 0;
+//   3. warp w owns up to two query heads and walks the chunk in tiles of 32 keys, flash-decoding style:
+//        phase A (lane = key): full-length dot products from shared memory - no per-key shuffle reductions;
+//        one warp max / sum per TILE for the online softmax;
+//        phase B (lane = head dims): probabilities broadcast by shuffle, P.V accumulated from the V rows;
+//   4. partials go to `part`; the last CTA of each (row, kv head) to finish (atomic ticket) merges the splits.
 // ------------------------------------------------------------------------------------------------
 template <int HD>
 __global__ void __launch_bounds__(128) decode_attn_fused_kernel(
@@ -278,7 +285,10 @@ __global__ void __launch_bounds__(128) decode_attn_fused_kernel(
     int nkv, int p_max, int c_max, int chunk, int max_pos, float scale, int dbg) {
   constexpr int DPL = HD / 32;
   constexpr int MAXG = 8;
+  constexpr int HPW = 2;             // heads per warp (MAXG / 4 warps)
   constexpr int HALF = HD / 2;
+  constexpr int PPR = HD / 8;        // 16-byte pieces per K/V row
+  constexpr int SWZ = PPR >= 8 ? 7 : PPR - 1;
   const int r = blockIdx.x, kvh = blockIdx.y, sp = blockIdx.z, nsplit = gridDim.z;
   const int gq = nq / nkv;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -286,6 +296,7 @@ __global__ void __launch_bounds__(128) decode_attn_fused_kernel(
   const int step = state[ST_STEP];
   const int ctx = P + step + 1;
   const int k0 = sp * chunk, k1 = min(ctx, k0 + chunk);
+  const int nkeys = max(0, k1 - k0);
   const int grp = row_group[r];
   const int qkv_dim = (nq + 2 * nkv) * HD;
   const float* xrow = qkv + (long long)r * qkv_dim;
@@ -303,44 +314,14 @@ __global__ void __launch_bounds__(128) decode_attn_fused_kernel(
     return bf16r(a + b);
   };
 
-  // rotated, pre-scaled queries of this kv head's group: computed ONCE per CTA (threads split the gq x HD elements),
-  // staged in shared memory.
-  __shared__ float sm_q[MAXG][HD];
-  for (int i = threadIdx.x; i < gq * HD; i += blockDim.x) {
-    const int h = i / HD, d = i % HD;
-    sm_q[h][d] = (dbg & 1) ? 0.f : rot(xrow + (long long)(kvh * gq + h) * HD, d) * scale;
-  }
-  __syncthreads();
-  // Work split: warp w owns HPW = ceil(gq / 4) query heads and walks ALL keys of the chunk for them (the 4 warps
-  // re-read the same K/V rows through L1). Few live registers per thread -> many resident CTAs to hide the chain of
-  // dependent memory round trips; no cross-warp merge is needed because heads are disjoint.
-  constexpr int HPW = 2;  // MAXG / 4
-  const int hpw = (gq + 3) >> 2;
-  const int h0 = warp * hpw;
-  float qv[HPW][DPL], acc[HPW][DPL], mrun[HPW], lrun[HPW];
-#pragma unroll
-  for (int hh = 0; hh < HPW; ++hh) {
-    mrun[hh] = -INFINITY;
-    lrun[hh] = 0.f;
-    const bool on = hh < hpw && h0 + hh < gq;
-#pragma unroll
-    for (int d = 0; d < DPL; ++d) {
-      acc[hh][d] = 0.f;
-      qv[hh][d] = on ? sm_q[h0 + hh][lane * DPL + d] : 0.f;
-    }
-  }
-  const float* knew = xrow + (long long)(nq + kvh) * HD;
-  const float* vnew = xrow + (long long)(nq + nkv + kvh) * HD;
-  // The chunk's K/V rows are staged in shared memory with ONE round of cp.async (16 B per request, every thread
-  // issuing all of its requests before anyone waits), so the cache read costs one memory latency per CTA instead of one
-  // per batch of keys. The token being decoded is not in the cache yet: warp 0 rotates it, appends it to the row's
-  // slab and drops it into the staging buffer.
+  __shared__ __align__(16) float sm_q[MAXG][HD];
+  __shared__ int s_last;
   extern __shared__ __align__(16) uint8_t sm_kv_raw[];
-  bf16* sK = reinterpret_cast<bf16*>(sm_kv_raw);
-  bf16* sV = sK + (size_t)chunk * HD;
-  const int nkeys = max(0, k1 - k0);
+  bf16* sK = reinterpret_cast<bf16*>(sm_kv_raw);   // [chunk][HD], 16-byte pieces swizzled by (key & SWZ)
+  bf16* sV = sK + (size_t)chunk * HD;              // [chunk][HD], linear
+
+  // ---- 1 + 2: stage K/V (async) while the queries are rotated ----
   if (!(dbg & 2)) {
-    constexpr int PPR = HD / 8;  // 16-byte pieces per row
     for (int q = threadIdx.x; q < nkeys * PPR; q += blockDim.x) {
       const int jj = q / PPR, piece = q % PPR;
       const int j = k0 + jj;
@@ -354,59 +335,115 @@ __global__ void __launch_bounds__(128) decode_attn_fused_kernel(
         krow = kc + (((long long)r * c_max + (j - P)) * nkv + kvh) * HD;
         vrow = vc + (((long long)r * c_max + (j - P)) * nkv + kvh) * HD;
       }
-      cp_async16(sK + (size_t)jj * HD + piece * 8, krow + piece * 8);
-      cp_async16(sV + (size_t)jj * HD + piece * 8, vrow + piece * 8);
+      cp_async16(sK + (size_t)jj * HD + ((piece ^ (jj & SWZ)) << 3), krow + piece * 8);
+      cp_async16(sV + (size_t)jj * HD + (piece << 3), vrow + piece * 8);
     }
-    if (ctx - 1 >= k0 && ctx - 1 < k1 && warp == 0) {
-      const int jj = ctx - 1 - k0;
-      bf16* kdst = kc + (((long long)r * c_max + step) * nkv + kvh) * HD;
-      bf16* vdst = vc + (((long long)r * c_max + step) * nkv + kvh) * HD;
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < gq * HD; i += blockDim.x) {
+    const int h = i / HD, d = i % HD;
+    sm_q[h][d] = (dbg & 1) ? 0.f : rot(xrow + (long long)(kvh * gq + h) * HD, d) * scale;
+  }
+  if (!(dbg & 2) && ctx - 1 >= k0 && ctx - 1 < k1 && warp == 0) {
+    const int jj = ctx - 1 - k0;
+    const float* knew = xrow + (long long)(nq + kvh) * HD;
+    const float* vnew = xrow + (long long)(nq + nkv + kvh) * HD;
+    bf16* kdst = kc + (((long long)r * c_max + step) * nkv + kvh) * HD;
+    bf16* vdst = vc + (((long long)r * c_max + step) * nkv + kvh) * HD;
 #pragma unroll
-      for (int d = 0; d < DPL; ++d) {
-        const bf16 kb = __float2bfloat16(rot(knew, lane * DPL + d));
-        const bf16 vb = __float2bfloat16(vnew[lane * DPL + d]);
-        sK[(size_t)jj * HD + lane * DPL + d] = kb;
-        sV[(size_t)jj * HD + lane * DPL + d] = vb;
-        kdst[lane * DPL + d] = kb;
-        vdst[lane * DPL + d] = vb;
+    for (int e = 0; e < DPL; ++e) {
+      const int d = lane * DPL + e;
+      const bf16 kb = __float2bfloat16(rot(knew, d));
+      const bf16 vb = __float2bfloat16(vnew[d]);
+      sK[(size_t)jj * HD + ((((d >> 3) ^ (jj & SWZ)) << 3) | (d & 7))] = kb;
+      sV[(size_t)jj * HD + d] = vb;
+      kdst[d] = kb;
+      vdst[d] = vb;
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  // ---- 3: flash-decoding over tiles of 32 keys; this warp's heads are [h0, h0 + hpw) ----
+  const int hpw = (gq + 3) >> 2;
+  const int h0 = warp * hpw;
+  float acc[HPW][DPL], mrun[HPW], lrun[HPW];
+  bool on[HPW];
+#pragma unroll
+  for (int hh = 0; hh < HPW; ++hh) {
+    mrun[hh] = -INFINITY;
+    lrun[hh] = 0.f;
+    on[hh] = hh < hpw && h0 + hh < gq;
+#pragma unroll
+    for (int e = 0; e < DPL; ++e) acc[hh][e] = 0.f;
+  }
+  if (!(dbg & 2) && (on[0] || on[1])) {
+    for (int t0 = 0; t0 < nkeys; t0 += 32) {
+      const int jj = t0 + lane;
+      const bool valid = jj < nkeys;
+      // phase A: lane = key
+      float sc[HPW] = {0.f, 0.f};
+      if (valid) {
+        const uint4* krow = reinterpret_cast<const uint4*>(sK + (size_t)jj * HD);
+#pragma unroll
+        for (int pi = 0; pi < PPR; ++pi) {
+          const uint4 kv = krow[pi ^ (jj & SWZ)];
+          float kf[8];
+          const __nv_bfloat162* kh = reinterpret_cast<const __nv_bfloat162*>(&kv);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __bfloat1622float2(kh[e]);
+            kf[2 * e] = f.x;
+            kf[2 * e + 1] = f.y;
+          }
+#pragma unroll
+          for (int hh = 0; hh < HPW; ++hh) {
+            if (on[hh]) {
+              const float4 qa = *reinterpret_cast<const float4*>(&sm_q[h0 + hh][pi * 8]);
+              const float4 qb = *reinterpret_cast<const float4*>(&sm_q[h0 + hh][pi * 8 + 4]);
+              sc[hh] += qa.x * kf[0] + qa.y * kf[1] + qa.z * kf[2] + qa.w * kf[3] + qb.x * kf[4] + qb.y * kf[5] +
+                        qb.z * kf[6] + qb.w * kf[7];
+            }
+          }
+        }
       }
-    }
-    cp_async_wait_all();
-    __syncthreads();
-    constexpr int UNR = 4;
-    for (int jb = 0; jb < nkeys; jb += UNR) {
+      float pr[HPW];
 #pragma unroll
-      for (int u = 0; u < UNR; ++u) {
-        const int jj = jb + u;
-        if (jj >= nkeys) break;
-        float kf[DPL], vf[DPL];
-        load_bf16_vec<DPL>(sK + (size_t)jj * HD + lane * DPL, kf);
-        load_bf16_vec<DPL>(sV + (size_t)jj * HD + lane * DPL, vf);
+      for (int hh = 0; hh < HPW; ++hh) {
+        const float sv = valid ? sc[hh] : -INFINITY;
+        float mt = sv;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, o));
+        const float mn = fmaxf(mrun[hh], mt);
+        const float corr = (mrun[hh] == -INFINITY) ? 0.f : __expf(mrun[hh] - mn);
+        pr[hh] = valid ? __expf(sv - mn) : 0.f;
+        lrun[hh] = lrun[hh] * corr + wsum(pr[hh]);
+#pragma unroll
+        for (int e = 0; e < DPL; ++e) acc[hh][e] *= corr;
+        mrun[hh] = mn;
+      }
+      // phase B: lane = head dims; probabilities are broadcast from the lane that owns the key
+      const int nt = min(32, nkeys - t0);
+#pragma unroll 8
+      for (int k = 0; k < nt; ++k) {
+        float vf[DPL];
+        load_bf16_vec<DPL>(sV + (size_t)(t0 + k) * HD + lane * DPL, vf);
 #pragma unroll
         for (int hh = 0; hh < HPW; ++hh) {
-          float sc = 0.f;
+          const float pk = __shfl_sync(0xffffffffu, pr[hh], k);
 #pragma unroll
-          for (int d = 0; d < DPL; ++d) sc += qv[hh][d] * kf[d];
-          sc = wsum(sc);
-          const float mn = fmaxf(mrun[hh], sc);
-          const float corr = __expf(mrun[hh] - mn);
-          const float pr = __expf(sc - mn);
-          lrun[hh] = lrun[hh] * corr + pr;
-#pragma unroll
-          for (int d = 0; d < DPL; ++d) acc[hh][d] = acc[hh][d] * corr + pr * vf[d];
-          mrun[hh] = mn;
+          for (int e = 0; e < DPL; ++e) acc[hh][e] += pk * vf[e];
         }
       }
     }
   }
   // each warp writes the partials of its own heads: part[r][head][split][HD + 2]
-  __shared__ int s_last;
 #pragma unroll
   for (int hh = 0; hh < HPW; ++hh) {
-    if (hh < hpw && h0 + hh < gq) {
+    if (on[hh]) {
       float* dst = part + (((long long)r * nq + kvh * gq + h0 + hh) * nsplit + sp) * (HD + 2);
 #pragma unroll
-      for (int d = 0; d < DPL; ++d) dst[lane * DPL + d] = acc[hh][d];
+      for (int e = 0; e < DPL; ++e) dst[lane * DPL + e] = acc[hh][e];
       if (lane == 0) {
         dst[HD] = mrun[hh];
         dst[HD + 1] = lrun[hh];
@@ -414,7 +451,7 @@ __global__ void __launch_bounds__(128) decode_attn_fused_kernel(
     }
   }
   if (dbg & 4) return;
-  // ---- last CTA of this (row, kv head) merges the splits ----
+  // ---- 4: last CTA of this (row, kv head) merges the splits ----
   // bar.sync orders the CTA's partial writes before thread 0's (cumulative) gpu-scope fence + ticket; one fence per CTA.
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -778,11 +815,13 @@ int iadr1_decode_attention_fused(const float* qkv, const float* cos_tab, const f
   if (kv_smem > 160 * 1024) return set_error("decode_attention_fused: context too long for one staging buffer (chunk %d)", chunk);
   static const int dbg = getenv("IADR1_ATTN_DEBUG") ? atoi(getenv("IADR1_ATTN_DEBUG")) : 0;  // phase-skipping, probes only
 #define IADR1_DECODE_FUSED(HD)                                                                                       \
-  if (kv_smem > 48 * 1024)                                                                                           \
-    cudaFuncSetAttribute(decode_attn_fused_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);     \
-  decode_attn_fused_kernel<HD><<<dim3(rows, nkv, nsplit), 128, kv_smem, st>>>(                                             \
-      qkv, cos_tab, sin_tab, rope_delta, (const bf16*)kp, (const bf16*)vp, (bf16*)kc, (bf16*)vc, state, row_group,   \
-      row_plen, part, tickets, (bf16*)out, nq, nkv, p_max, c_max, chunk, max_pos, scale, dbg)
+  do {                                                                                                               \
+    if (kv_smem > 48 * 1024)                                                                                         \
+      cudaFuncSetAttribute(decode_attn_fused_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);   \
+    decode_attn_fused_kernel<HD><<<dim3(rows, nkv, nsplit), 128, kv_smem, st>>>(                                     \
+        qkv, cos_tab, sin_tab, rope_delta, (const bf16*)kp, (const bf16*)vp, (bf16*)kc, (bf16*)vc, state, row_group, \
+        row_plen, part, tickets, (bf16*)out, nq, nkv, p_max, c_max, chunk, max_pos, scale, dbg);                     \
+  } while (0)
   if (hd == 128) IADR1_DECODE_FUSED(128);
   else if (hd == 64) IADR1_DECODE_FUSED(64);
   else if (hd == 32) IADR1_DECODE_FUSED(32);

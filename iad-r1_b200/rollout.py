@@ -60,7 +60,7 @@ class RolloutEngine:
         self.qkv = torch.zeros(R, t.qkv_dim, dtype=f32, device=dev)
         self.q = torch.zeros(R, t.num_heads * hd, dtype=bf16, device=dev)
         self.attn = torch.zeros(R, t.num_heads * hd, dtype=bf16, device=dev)
-        self.nsplit = max(1, min(32, (p_max + c_max + 63) // 64))   # ~64 keys per CTA
+        self.nsplit = max(1, min(32, (p_max + c_max + 127) // 128))   # ~128 keys (4 tiles of 32) per CTA
         self.part = torch.zeros(R, t.num_heads, self.nsplit, hd + 2, dtype=f32, device=dev)
         self.tickets = torch.zeros(R * nkv, dtype=i32, device=dev)
         self.gu = torch.zeros(R, 2 * I, dtype=bf16, device=dev)
