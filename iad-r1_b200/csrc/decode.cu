@@ -291,7 +291,8 @@ __global__ void __launch_bounds__(128) decode_attn_fused_kernel(
   constexpr int SWZ = PPR >= 8 ? 7 : PPR - 1;
   const int r = blockIdx.x, kvh = blockIdx.y, sp = blockIdx.z, nsplit = gridDim.z;
   const int gq = nq / nkv;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform
   const int P = row_plen[r];
   const int step = state[ST_STEP];
   const int ctx = P + step + 1;
@@ -321,7 +322,7 @@ __global__ void __launch_bounds__(128) decode_attn_fused_kernel(
   bf16* sV = sK + (size_t)chunk * HD;              // [chunk][HD], linear
 
   // ---- 1 + 2: stage K/V (async) while the queries are rotated ----
-  if (!(dbg & 2)) {
+  if (!(dbg & 2) && !(dbg & 16)) {
     for (int q = threadIdx.x; q < nkeys * PPR; q += blockDim.x) {
       const int jj = q / PPR, piece = q % PPR;
       const int j = k0 + jj;
@@ -377,63 +378,66 @@ __global__ void __launch_bounds__(128) decode_attn_fused_kernel(
 #pragma unroll
     for (int e = 0; e < DPL; ++e) acc[hh][e] = 0.f;
   }
-  if (!(dbg & 2) && (on[0] || on[1])) {
-    for (int t0 = 0; t0 < nkeys; t0 += 32) {
-      const int jj = t0 + lane;
-      const bool valid = jj < nkeys;
-      // phase A: lane = key
-      float sc[HPW] = {0.f, 0.f};
-      if (valid) {
-        const uint4* krow = reinterpret_cast<const uint4*>(sK + (size_t)jj * HD);
+  // The tile loop is written branch-free (clamped indices, zero probabilities for out-of-range keys, clamped head
+  // ids for unused head slots) so that every shuffle is provably convergent - no per-shuffle WARPSYNC/BSSY pairs.
+  const int hq[HPW] = {min(h0, gq - 1), min(h0 + 1, gq - 1)};
+  const int ntiles = ((dbg & 2) || (dbg & 8)) ? 0 : (nkeys + 31) >> 5;
+  for (int ti = 0; ti < ntiles; ++ti) {
+    const int t0 = ti << 5;
+    const int jj = t0 + lane;
+    const bool valid = jj < nkeys;
+    const int jc = min(jj, nkeys - 1);
+    // phase A: lane = key
+    float sc[HPW] = {0.f, 0.f};
+    {
+      const uint4* krow = reinterpret_cast<const uint4*>(sK + (size_t)jc * HD);
 #pragma unroll
-        for (int pi = 0; pi < PPR; ++pi) {
-          const uint4 kv = krow[pi ^ (jj & SWZ)];
-          float kf[8];
-          const __nv_bfloat162* kh = reinterpret_cast<const __nv_bfloat162*>(&kv);
+      for (int pi = 0; pi < PPR; ++pi) {
+        const uint4 kv = krow[pi ^ (jc & SWZ)];
+        float kf[8];
+        const __nv_bfloat162* kh = reinterpret_cast<const __nv_bfloat162*>(&kv);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 f = __bfloat1622float2(kh[e]);
-            kf[2 * e] = f.x;
-            kf[2 * e + 1] = f.y;
-          }
-#pragma unroll
-          for (int hh = 0; hh < HPW; ++hh) {
-            if (on[hh]) {
-              const float4 qa = *reinterpret_cast<const float4*>(&sm_q[h0 + hh][pi * 8]);
-              const float4 qb = *reinterpret_cast<const float4*>(&sm_q[h0 + hh][pi * 8 + 4]);
-              sc[hh] += qa.x * kf[0] + qa.y * kf[1] + qa.z * kf[2] + qa.w * kf[3] + qb.x * kf[4] + qb.y * kf[5] +
-                        qb.z * kf[6] + qb.w * kf[7];
-            }
-          }
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __bfloat1622float2(kh[e]);
+          kf[2 * e] = f.x;
+          kf[2 * e + 1] = f.y;
         }
-      }
-      float pr[HPW];
-#pragma unroll
-      for (int hh = 0; hh < HPW; ++hh) {
-        const float sv = valid ? sc[hh] : -INFINITY;
-        float mt = sv;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, o));
-        const float mn = fmaxf(mrun[hh], mt);
-        const float corr = (mrun[hh] == -INFINITY) ? 0.f : __expf(mrun[hh] - mn);
-        pr[hh] = valid ? __expf(sv - mn) : 0.f;
-        lrun[hh] = lrun[hh] * corr + wsum(pr[hh]);
-#pragma unroll
-        for (int e = 0; e < DPL; ++e) acc[hh][e] *= corr;
-        mrun[hh] = mn;
-      }
-      // phase B: lane = head dims; probabilities are broadcast from the lane that owns the key
-      const int nt = min(32, nkeys - t0);
-#pragma unroll 8
-      for (int k = 0; k < nt; ++k) {
-        float vf[DPL];
-        load_bf16_vec<DPL>(sV + (size_t)(t0 + k) * HD + lane * DPL, vf);
 #pragma unroll
         for (int hh = 0; hh < HPW; ++hh) {
-          const float pk = __shfl_sync(0xffffffffu, pr[hh], k);
-#pragma unroll
-          for (int e = 0; e < DPL; ++e) acc[hh][e] += pk * vf[e];
+          const float4 qa = *reinterpret_cast<const float4*>(&sm_q[hq[hh]][pi * 8]);
+          const float4 qb = *reinterpret_cast<const float4*>(&sm_q[hq[hh]][pi * 8 + 4]);
+          // two independent 4-term chains per head (shorter dependency chain than one 8-term sum)
+          const float s0 = qa.x * kf[0] + qa.y * kf[1] + qa.z * kf[2] + qa.w * kf[3];
+          const float s1 = qb.x * kf[4] + qb.y * kf[5] + qb.z * kf[6] + qb.w * kf[7];
+          sc[hh] += s0 + s1;
         }
+      }
+    }
+    float pr[HPW];
+#pragma unroll
+    for (int hh = 0; hh < HPW; ++hh) {
+      const float sv = valid ? sc[hh] : -INFINITY;
+      float mt = sv;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, o));
+      const float mn = fmaxf(mrun[hh], mt);
+      const float corr = (mrun[hh] == -INFINITY) ? 0.f : __expf(mrun[hh] - mn);
+      pr[hh] = valid ? __expf(sv - mn) : 0.f;
+      lrun[hh] = lrun[hh] * corr + wsum(pr[hh]);
+#pragma unroll
+      for (int e = 0; e < DPL; ++e) acc[hh][e] *= corr;
+      mrun[hh] = mn;
+    }
+    // phase B: lane = head dims; probabilities are broadcast from the lane that owns the key (0 beyond the chunk)
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      float vf[DPL];
+      load_bf16_vec<DPL>(sV + (size_t)min(t0 + k, nkeys - 1) * HD + lane * DPL, vf);
+#pragma unroll
+      for (int hh = 0; hh < HPW; ++hh) {
+        const float pk = __shfl_sync(0xffffffffu, pr[hh], k);
+#pragma unroll
+        for (int e = 0; e < DPL; ++e) acc[hh][e] += pk * vf[e];
       }
     }
   }
