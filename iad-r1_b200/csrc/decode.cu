@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(128) decode_attn_partial_kernel(
 //   4. partials go to `part`; the last CTA of each (row, kv head) to finish (atomic ticket) merges the splits.
 // ------------------------------------------------------------------------------------------------
 template <int HD>
-__global__ void __launch_bounds__(512, 2) decode_attn_fused_kernel(
+__global__ void __launch_bounds__(128) decode_attn_fused_kernel(
     const float* __restrict__ qkv, const float* __restrict__ cos_tab, const float* __restrict__ sin_tab,
     const int* __restrict__ rope_delta, const bf16* __restrict__ kp, const bf16* __restrict__ vp, bf16* __restrict__ kc,
     bf16* __restrict__ vc, const int* __restrict__ state, const int* __restrict__ row_group,
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(512, 2) decode_attn_fused_kernel(
     int nkv, int p_max, int c_max, int chunk, int max_pos, float scale, int dbg) {
   constexpr int DPL = HD / 32;
   constexpr int MAXG = 8;
-  constexpr int NTG = 2;             // 16 warps = 8 head slots x NTG tile groups
+  constexpr int HPW = 2;             // heads per warp (MAXG / 4 warps)
   constexpr int HALF = HD / 2;
   constexpr int PPR = HD / 8;        // 16-byte pieces per K/V row
   constexpr int SWZ = PPR >= 8 ? 7 : PPR - 1;
@@ -365,91 +365,93 @@ __global__ void __launch_bounds__(512, 2) decode_attn_fused_kernel(
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
-  // ---- 3: flash-decoding over tiles of 32 keys. Warp w = (head slot w & 7, tile group w >> 3): one query head, every
-  // NTG-th tile. 16 warps per CTA keep ~4 warps per scheduler busy, which is what hides the FMA / shuffle / LDS
-  // latencies of these short dependent chains (a 4-warp CTA ran at one warp per scheduler, i.e. latency-bound).
-  const int hs = warp & 7, tg = warp >> 3;
-  const int hq = min(hs, gq - 1);   // clamped: unused head slots compute on a valid row and are discarded
-  float acc[DPL], mrun = -INFINITY, lrun = 0.f;
+  // ---- 3: flash-decoding over tiles of 32 keys; this warp's heads are [h0, h0 + hpw) ----
+  const int hpw = (gq + 3) >> 2;
+  const int h0 = warp * hpw;
+  float acc[HPW][DPL], mrun[HPW], lrun[HPW];
+  bool on[HPW];
 #pragma unroll
-  for (int e = 0; e < DPL; ++e) acc[e] = 0.f;
-  // The tile loop is branch-free (clamped indices, zero probabilities for out-of-range keys) so every shuffle is
-  // provably convergent.
+  for (int hh = 0; hh < HPW; ++hh) {
+    mrun[hh] = -INFINITY;
+    lrun[hh] = 0.f;
+    on[hh] = hh < hpw && h0 + hh < gq;
+#pragma unroll
+    for (int e = 0; e < DPL; ++e) acc[hh][e] = 0.f;
+  }
+  // The tile loop is written branch-free (clamped indices, zero probabilities for out-of-range keys, clamped head
+  // ids for unused head slots) so that every shuffle is provably convergent - no per-shuffle WARPSYNC/BSSY pairs.
+  const int hq[HPW] = {min(h0, gq - 1), min(h0 + 1, gq - 1)};
   const int ntiles = ((dbg & 2) || (dbg & 8)) ? 0 : (nkeys + 31) >> 5;
-  for (int ti = tg; ti < ntiles; ti += NTG) {
+  for (int ti = 0; ti < ntiles; ++ti) {
     const int t0 = ti << 5;
     const int jj = t0 + lane;
     const bool valid = jj < nkeys;
     const int jc = min(jj, nkeys - 1);
-    // phase A: lane = key; four independent partial sums shorten the FMA dependency chain
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    // phase A: lane = key
+    float sc[HPW] = {0.f, 0.f};
     {
       const uint4* krow = reinterpret_cast<const uint4*>(sK + (size_t)jc * HD);
 #pragma unroll
       for (int pi = 0; pi < PPR; ++pi) {
         const uint4 kv = krow[pi ^ (jc & SWZ)];
+        float kf[8];
         const __nv_bfloat162* kh = reinterpret_cast<const __nv_bfloat162*>(&kv);
-        const float2 k01 = __bfloat1622float2(kh[0]), k23 = __bfloat1622float2(kh[1]);
-        const float2 k45 = __bfloat1622float2(kh[2]), k67 = __bfloat1622float2(kh[3]);
-        const float4 qa = *reinterpret_cast<const float4*>(&sm_q[hq][pi * 8]);
-        const float4 qb = *reinterpret_cast<const float4*>(&sm_q[hq][pi * 8 + 4]);
-        s0 += qa.x * k01.x + qa.y * k01.y;
-        s1 += qa.z * k23.x + qa.w * k23.y;
-        s2 += qb.x * k45.x + qb.y * k45.y;
-        s3 += qb.z * k67.x + qb.w * k67.y;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __bfloat1622float2(kh[e]);
+          kf[2 * e] = f.x;
+          kf[2 * e + 1] = f.y;
+        }
+#pragma unroll
+        for (int hh = 0; hh < HPW; ++hh) {
+          const float4 qa = *reinterpret_cast<const float4*>(&sm_q[hq[hh]][pi * 8]);
+          const float4 qb = *reinterpret_cast<const float4*>(&sm_q[hq[hh]][pi * 8 + 4]);
+          // two independent 4-term chains per head (shorter dependency chain than one 8-term sum)
+          const float s0 = qa.x * kf[0] + qa.y * kf[1] + qa.z * kf[2] + qa.w * kf[3];
+          const float s1 = qb.x * kf[4] + qb.y * kf[5] + qb.z * kf[6] + qb.w * kf[7];
+          sc[hh] += s0 + s1;
+        }
       }
     }
-    const float sv = valid ? (s0 + s1) + (s2 + s3) : -INFINITY;
-    float mt = sv;
+    float pr[HPW];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, o));
-    const float mn = fmaxf(mrun, mt);
-    const float corr = (mrun == -INFINITY) ? 0.f : __expf(mrun - mn);
-    const float pr = valid ? __expf(sv - mn) : 0.f;
-    lrun = lrun * corr + wsum(pr);
+    for (int hh = 0; hh < HPW; ++hh) {
+      const float sv = valid ? sc[hh] : -INFINITY;
+      float mt = sv;
 #pragma unroll
-    for (int e = 0; e < DPL; ++e) acc[e] *= corr;
-    mrun = mn;
+      for (int o = 16; o > 0; o >>= 1) mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, o));
+      const float mn = fmaxf(mrun[hh], mt);
+      const float corr = (mrun[hh] == -INFINITY) ? 0.f : __expf(mrun[hh] - mn);
+      pr[hh] = valid ? __expf(sv - mn) : 0.f;
+      lrun[hh] = lrun[hh] * corr + wsum(pr[hh]);
+#pragma unroll
+      for (int e = 0; e < DPL; ++e) acc[hh][e] *= corr;
+      mrun[hh] = mn;
+    }
     // phase B: lane = head dims; probabilities are broadcast from the lane that owns the key (0 beyond the chunk)
 #pragma unroll
     for (int k = 0; k < 32; ++k) {
       float vf[DPL];
       load_bf16_vec<DPL>(sV + (size_t)min(t0 + k, nkeys - 1) * HD + lane * DPL, vf);
-      const float pk = __shfl_sync(0xffffffffu, pr, k);
 #pragma unroll
-      for (int e = 0; e < DPL; ++e) acc[e] += pk * vf[e];
+      for (int hh = 0; hh < HPW; ++hh) {
+        const float pk = __shfl_sync(0xffffffffu, pr[hh], k);
+#pragma unroll
+        for (int e = 0; e < DPL; ++e) acc[hh][e] += pk * vf[e];
+      }
     }
   }
-  // merge the NTG tile groups of each head through shared memory; head-slot warps of group 0 write the CTA partial
-  __shared__ float sm_mrg[NTG][MAXG][HD + 2];
+  // each warp writes the partials of its own heads: part[r][head][split][HD + 2]
 #pragma unroll
-  for (int e = 0; e < DPL; ++e) sm_mrg[tg][hs][lane * DPL + e] = acc[e];
-  if (lane == 0) {
-    sm_mrg[tg][hs][HD] = mrun;
-    sm_mrg[tg][hs][HD + 1] = lrun;
-  }
-  __syncthreads();
-  if (tg == 0 && hs < gq) {
-    float m = -INFINITY;
+  for (int hh = 0; hh < HPW; ++hh) {
+    if (on[hh]) {
+      float* dst = part + (((long long)r * nq + kvh * gq + h0 + hh) * nsplit + sp) * (HD + 2);
 #pragma unroll
-    for (int g2 = 0; g2 < NTG; ++g2) m = fmaxf(m, sm_mrg[g2][hs][HD]);
-    float l = 0.f, o[DPL];
-#pragma unroll
-    for (int e = 0; e < DPL; ++e) o[e] = 0.f;
-#pragma unroll
-    for (int g2 = 0; g2 < NTG; ++g2) {
-      const float mg = sm_mrg[g2][hs][HD];
-      const float c = (mg == -INFINITY) ? 0.f : __expf(mg - m);
-      l += sm_mrg[g2][hs][HD + 1] * c;
-#pragma unroll
-      for (int e = 0; e < DPL; ++e) o[e] += sm_mrg[g2][hs][lane * DPL + e] * c;
-    }
-    float* dst = part + (((long long)r * nq + kvh * gq + hs) * nsplit + sp) * (HD + 2);
-#pragma unroll
-    for (int e = 0; e < DPL; ++e) dst[lane * DPL + e] = o[e];
-    if (lane == 0) {
-      dst[HD] = m;
-      dst[HD + 1] = l;
+      for (int e = 0; e < DPL; ++e) dst[lane * DPL + e] = acc[hh][e];
+      if (lane == 0) {
+        dst[HD] = mrun[hh];
+        dst[HD + 1] = lrun[hh];
+      }
     }
   }
   if (dbg & 4) return;
@@ -471,7 +473,7 @@ __global__ void __launch_bounds__(512, 2) decode_attn_fused_kernel(
   constexpr int MAXS = 32;
   __shared__ float s_c[MAXG][MAXS];
   __shared__ float s_invl[MAXG];
-  for (int h = warp; h < gq; h += 16) {
+  for (int h = warp; h < gq; h += 4) {
     const float* p = part + ((long long)r * nq + kvh * gq + h) * nsplit * (HD + 2);
     const float ms = (lane < nsplit) ? __ldcg(p + lane * (HD + 2) + HD) : -INFINITY;
     const float ls = (lane < nsplit) ? __ldcg(p + lane * (HD + 2) + HD + 1) : 0.f;
@@ -484,18 +486,18 @@ __global__ void __launch_bounds__(512, 2) decode_attn_fused_kernel(
     if (lane == 0) s_invl[h] = 1.f / l;
   }
   __syncthreads();
-  // every thread owns OUTS outputs (element o = threadIdx.x + 512 * oo); the split loop is unrolled so several
-  // independent L2 loads are in flight per thread instead of one serial chain per output.
-  constexpr int OUTS = (MAXG * HD + 511) / 512;
+  // every thread owns OUTS outputs (element o = threadIdx.x + 128 * oo); the split loop is outermost so that OUTS
+  // independent L2 loads are in flight per iteration instead of one serial chain per output.
+  constexpr int OUTS = (MAXG * HD + 127) / 128;
   float a[OUTS];
 #pragma unroll
   for (int oo = 0; oo < OUTS; ++oo) a[oo] = 0.f;
   const float* pbase = part + ((long long)r * nq + kvh * gq) * nsplit * (HD + 2);
-#pragma unroll 8
+#pragma unroll 2
   for (int s2 = 0; s2 < nsplit; ++s2) {
 #pragma unroll
     for (int oo = 0; oo < OUTS; ++oo) {
-      const int o = threadIdx.x + 512 * oo;
+      const int o = threadIdx.x + 128 * oo;
       if (o < gq * HD) {
         const int h = o / HD, d = o % HD;
         a[oo] += __ldcg(pbase + ((long long)h * nsplit + s2) * (HD + 2) + d) * s_c[h][s2];
@@ -504,7 +506,7 @@ __global__ void __launch_bounds__(512, 2) decode_attn_fused_kernel(
   }
 #pragma unroll
   for (int oo = 0; oo < OUTS; ++oo) {
-    const int o = threadIdx.x + 512 * oo;
+    const int o = threadIdx.x + 128 * oo;
     if (o < gq * HD) {
       const int h = o / HD, d = o % HD;
       out[((long long)r * nq + kvh * gq + h) * HD + d] = __float2bfloat16(a[oo] * s_invl[h]);
@@ -820,7 +822,7 @@ int iadr1_decode_attention_fused(const float* qkv, const float* cos_tab, const f
   do {                                                                                                               \
     if (kv_smem > 48 * 1024)                                                                                         \
       cudaFuncSetAttribute(decode_attn_fused_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);   \
-    decode_attn_fused_kernel<HD><<<dim3(rows, nkv, nsplit), 512, kv_smem, st>>>(                                     \
+    decode_attn_fused_kernel<HD><<<dim3(rows, nkv, nsplit), 128, kv_smem, st>>>(                                     \
         qkv, cos_tab, sin_tab, rope_delta, (const bf16*)kp, (const bf16*)vp, (bf16*)kc, (bf16*)vc, state, row_group, \
         row_plen, part, tickets, (bf16*)out, nq, nkv, p_max, c_max, chunk, max_pos, scale, dbg);                     \
   } while (0)
