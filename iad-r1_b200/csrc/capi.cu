@@ -15,6 +15,9 @@ int set_error(const char* fmt, ...) {
   return -1;
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+static std::atomic<bool> g_pdl{false};
+bool pdl_enabled() { return g_pdl.load(std::memory_order_relaxed); }
+void pdl_set(bool on) { g_pdl.store(on); }
 }  // namespace iadr1
 
 extern "C" {
@@ -27,6 +30,10 @@ int iadr1_gemm_bf16(const iadr1_gemm_t* d, void* stream) {
   return iadr1::launch_gemm(*d, static_cast<cudaStream_t>(stream));
 }
 int iadr1_gemm_pick_block_n(int N, int b_mn) { return iadr1::pick_block_n_public(N, b_mn); }
+int iadr1_set_pdl(int on) {
+  iadr1::pdl_set(on != 0);
+  return 0;
+}
 int iadr1_gemm_profile_enable(int on) {
   iadr1::gemm_profile_enable(on);
   return 0;

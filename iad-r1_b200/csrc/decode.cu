@@ -89,6 +89,8 @@ template <> struct RawVec<1> {
 // h[r][:] = float(embed[tok[r]][:])
 __global__ void decode_embed_kernel(const bf16* __restrict__ embed, const int* __restrict__ tok, float* __restrict__ h,
                                     int H) {
+  pdl_wait();
+  if (threadIdx.x == 0) pdl_trigger();
   const int r = blockIdx.x;
   const bf16* src = embed + (long long)tok[r] * H;
   for (int c = threadIdx.x; c < H; c += blockDim.x) h[(long long)r * H + c] = __bfloat162float(src[c]);
@@ -106,9 +108,15 @@ __global__ void rmsnorm_f32in_kernel(const float* __restrict__ x, const bf16* __
 #pragma unroll
   for (int i = 0; i < MAXE; ++i) {
     const int c = threadIdx.x + i * blockDim.x;
+    if (c < cols) wv[i] = __bfloat162float(w[c]);   // static weights: requested before the PDL wait (DRAM miss hidden)
+  }
+  pdl_wait();
+  if (threadIdx.x == 0) pdl_trigger();
+#pragma unroll
+  for (int i = 0; i < MAXE; ++i) {
+    const int c = threadIdx.x + i * blockDim.x;
     if (c < cols) {
       xv[i] = bf16r(xr[c]);
-      wv[i] = __bfloat162float(w[c]);   // issued together with x: the weight's DRAM miss overlaps the reduction
       ss += xv[i] * xv[i];
     }
   }
@@ -341,6 +349,10 @@ __global__ void __launch_bounds__(128) decode_attn_fused_kernel(
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
+  // everything above reads only scalars / tables / cache rows written at least two kernels ago; the qkv row below is
+  // produced by the immediately preceding GEMM
+  pdl_wait();
+  if (threadIdx.x == 0) pdl_trigger();
   for (int i = threadIdx.x; i < gq * HD; i += blockDim.x) {
     const int h = i / HD, d = i % HD;
     sm_q[h][d] = (dbg & 1) ? 0.f : rot(xrow + (long long)(kvh * gq + h) * HD, d) * scale;
@@ -391,7 +403,7 @@ __global__ void __launch_bounds__(128) decode_attn_fused_kernel(
     float sc[HPW] = {0.f, 0.f};
     {
       const uint4* krow = reinterpret_cast<const uint4*>(sK + (size_t)jc * HD);
-#pragma unroll
+#pragma unroll 4
       for (int pi = 0; pi < PPR; ++pi) {
         const uint4 kv = krow[pi ^ (jc & SWZ)];
         float kf[8];
@@ -429,7 +441,7 @@ __global__ void __launch_bounds__(128) decode_attn_fused_kernel(
       mrun[hh] = mn;
     }
     // phase B: lane = head dims; probabilities are broadcast from the lane that owns the key (0 beyond the chunk)
-#pragma unroll
+#pragma unroll 8
     for (int k = 0; k < 32; ++k) {
       float vf[DPL];
       load_bf16_vec<DPL>(sV + (size_t)min(t0 + k, nkeys - 1) * HD + lane * DPL, vf);
@@ -547,24 +559,58 @@ __device__ __forceinline__ uint32_t f2key(float f) {
 }
 constexpr int kMaxKeep = 256;  // survivors buffer (top_k <= 128 plus ties)
 
-__device__ __forceinline__ void hist_add_aggregated(uint32_t* hist, uint32_t bin) {
-  // lanes of the warp that hit the same bin elect one leader: logits cluster in a few exponent bins, and un-aggregated
-  // shared-memory atomics on one address serialise the whole CTA.
-  const unsigned peers = __match_any_sync(__activemask(), bin);
-  if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&hist[bin], (uint32_t)__popc(peers));
+constexpr int kMaxCand = 2048;  // candidate pool for the top-k selection
+
+// Applies `f(x, index)` to every logit of the row with 16-byte loads, four requests in flight per thread (the scan is
+// L2-latency-bound, not bandwidth-bound).
+template <typename F>
+__device__ __forceinline__ void scan_row(const float* __restrict__ lg, int V, int eos_id, int forbid_eos, F f) {
+  const int V4 = ((reinterpret_cast<uintptr_t>(lg) & 15) == 0) ? (V >> 2) : 0;
+  const float4* lg4 = reinterpret_cast<const float4*>(lg);
+  for (int i0 = threadIdx.x; i0 < V4; i0 += 4 * blockDim.x) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i < V4) v[u] = __ldcg(lg4 + i);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i < V4) {
+        const float xs[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int idx = 4 * i + e;
+          f((forbid_eos && idx == eos_id) ? -INFINITY : xs[e], idx);
+        }
+      }
+    }
+  }
+  for (int i = 4 * V4 + threadIdx.x; i < V; i += blockDim.x) f((forbid_eos && i == eos_id) ? -INFINITY : lg[i], i);
 }
 
+// Top-k threshold search without sorting or histograms: (1) row max; (2) how many logits lie within delta_i of the max,
+// for 8 nested deltas, counted in registers and block-reduced; the smallest delta holding >= k (and <= kMaxCand)
+// logits defines a candidate pool; (3) the pool is gathered into shared memory and the exact k-th value is found by
+// rank counting. Pathological rows (more than kMaxCand logits inside every usable delta, e.g. constant logits) fall
+// back to a bisection on the threshold.
 __global__ void __launch_bounds__(1024) sample_kernel(const float* __restrict__ logits, int V, float inv_temp, int top_k,
                                                       float top_p, unsigned long long seed, int* __restrict__ state,
                                                       int* __restrict__ tok, int* __restrict__ finished,
                                                       int* __restrict__ out_tokens, int c_max, int eos_id, int pad_id,
                                                       int forbid_eos, int first) {
-  __shared__ uint32_t hist[2048];
-  __shared__ uint32_t s_prefix, s_kth_remaining;
-  __shared__ int s_count;
+  __shared__ float s_red[32];
+  __shared__ int s_cnt[8][32];
+  __shared__ int s_count, s_nsurv;
+  __shared__ float s_cval[kMaxCand];
+  __shared__ int s_cidx[kMaxCand];
   __shared__ float s_val[kMaxKeep], s_sorted[kMaxKeep];
   __shared__ int s_idx[kMaxKeep], s_sidx[kMaxKeep];
+  pdl_wait();
+  if (threadIdx.x == 0) pdl_trigger();
   const int r = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const float* lg = logits + (long long)r * V;
   // `first`: logits come from the prefill (predict completion token 0); else they predict token step + 1.
   const int out_pos = first ? 0 : state[ST_STEP] + 1;
@@ -577,125 +623,112 @@ __global__ void __launch_bounds__(1024) sample_kernel(const float* __restrict__ 
     return;
   }
   const int k = min(max(top_k, 1), 128);
-  // --- radix select of the k-th largest key (11 + 11 + 10 bits) ---
-  uint32_t prefix = 0, prefix_mask = 0;
-  uint32_t remaining = k;
-  const int shifts[3] = {21, 10, 0};
-  const int bits[3] = {11, 11, 10};
-  for (int pass = 0; pass < 3; ++pass) {
-    for (int i = threadIdx.x; i < 2048; i += blockDim.x) hist[i] = 0;
-    __syncthreads();
-    const uint32_t nb = 1u << bits[pass];
-    {
-      // float4 loads, 4 in flight per thread: the scan is L2-latency-bound, not bandwidth-bound
-      const int V4 = ((reinterpret_cast<uintptr_t>(lg) & 15) == 0) ? (V >> 2) : 0;
-      const float4* lg4 = reinterpret_cast<const float4*>(lg);
-      for (int i0 = threadIdx.x; i0 < V4; i0 += 4 * blockDim.x) {
-        float4 v[4];
+  // ---- (1) row max ----
+  float mx = -INFINITY;
+  scan_row(lg, V, eos_id, forbid_eos, [&](float x, int) { mx = fmaxf(mx, x); });
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = i0 + u * blockDim.x;
-          if (i < V4) v[u] = __ldcg(lg4 + i);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = i0 + u * blockDim.x;
-          if (i < V4) {
-            const float xs[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float x = xs[e];
-              if (forbid_eos && (4 * i + e) == eos_id) x = -INFINITY;
-              const uint32_t key = f2key(x);
-              if ((key & prefix_mask) == prefix) hist_add_aggregated(hist, (key >> shifts[pass]) & (nb - 1));
-            }
-          }
-        }
-      }
-      for (int i = 4 * V4 + threadIdx.x; i < V; i += blockDim.x) {
-        float x = lg[i];
-        if (forbid_eos && i == eos_id) x = -INFINITY;
-        const uint32_t key = f2key(x);
-        if ((key & prefix_mask) == prefix) hist_add_aggregated(hist, (key >> shifts[pass]) & (nb - 1));
-      }
-    }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      // warp 0 walks the histogram from the top, 32 bins at a time (suffix sums by shuffle)
-      uint32_t cum = 0;
-      int found = -1;
-      uint32_t rem_after = 0;
-      for (int base = (int)nb - 32; base >= 0 && found < 0; base -= 32) {
-        const int b = base + (31 - (int)threadIdx.x);  // lane 0 holds the highest bin of this block
-        const uint32_t c = hist[b];
-        uint32_t incl = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-          if ((int)threadIdx.x >= o) incl += v;
-        }
-        const bool hit = (cum + incl >= remaining);
-        const unsigned ballot = __ballot_sync(0xffffffffu, hit);
-        if (ballot) {
-          const int ln = __ffs(ballot) - 1;
-          found = base + (31 - ln);
-          const uint32_t incl_ln = __shfl_sync(0xffffffffu, incl, ln);
-          const uint32_t c_ln = __shfl_sync(0xffffffffu, c, ln);
-          rem_after = remaining - (cum + incl_ln - c_ln);
-        } else {
-          cum += __shfl_sync(0xffffffffu, incl, 31);
-        }
-      }
-      if (found < 0) { found = 0; rem_after = 1; }
-      if (threadIdx.x == 0) {
-        s_prefix = prefix | ((uint32_t)found << shifts[pass]);
-        s_kth_remaining = rem_after;
-      }
-    }
-    __syncthreads();
-    prefix = s_prefix;
-    remaining = s_kth_remaining;
-    prefix_mask |= ((nb - 1) << shifts[pass]);
-    __syncthreads();
-  }
-  const uint32_t kth_key = prefix;  // every key >= kth_key survives (ties kept)
-  if (threadIdx.x == 0) s_count = 0;
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) s_red[warp] = mx;
   __syncthreads();
-  {
-    const int V4 = ((reinterpret_cast<uintptr_t>(lg) & 15) == 0) ? (V >> 2) : 0;
-    const float4* lg4 = reinterpret_cast<const float4*>(lg);
-    auto consider = [&](float x, int i) {
-      if (forbid_eos && i == eos_id) x = -INFINITY;
-      if (f2key(x) >= kth_key) {
-        const int slot = atomicAdd(&s_count, 1);
-        if (slot < kMaxKeep) {
-          s_val[slot] = x * inv_temp;
-          s_idx[slot] = i;
-        }
-      }
-    };
-    for (int i0 = threadIdx.x; i0 < V4; i0 += 4 * blockDim.x) {
-      float4 v[4];
+  mx = -INFINITY;
+  for (int i = 0; i < nwarps; ++i) mx = fmaxf(mx, s_red[i]);
+  // ---- (2) nested counts; up to three rounds of widening deltas, then bisection ----
+  float thr = -INFINITY;
+  bool found = false;
+  float lo_thr = -INFINITY, hi_thr = mx;  // count(x >= lo_thr) >= k always; hi side may hold < k
+  for (int round = 0; round < 3 && !found; ++round) {
+    const float base = round == 0 ? 1.f : (round == 1 ? 16.f : 256.f);
+    const float dl[8] = {base, 2 * base, 3 * base, 4 * base, 6 * base, 8 * base, 12 * base, 16 * base};
+    int c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    scan_row(lg, V, eos_id, forbid_eos, [&](float x, int) {
+      const float d = mx - x;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u * blockDim.x;
-        if (i < V4) v[u] = __ldcg(lg4 + i);
-      }
+      for (int t = 0; t < 8; ++t) c[t] += (d <= dl[t]) ? 1 : 0;
+    });
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u * blockDim.x;
-        if (i < V4) {
-          consider(v[u].x, 4 * i);
-          consider(v[u].y, 4 * i + 1);
-          consider(v[u].z, 4 * i + 2);
-          consider(v[u].w, 4 * i + 3);
+    for (int t = 0; t < 8; ++t) {
+      int v = c[t];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) s_cnt[t][warp] = v;
+    }
+    __syncthreads();
+    int tot[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      tot[t] = 0;
+      for (int i = 0; i < nwarps; ++i) tot[t] += s_cnt[t][i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      if (!found) {
+        if (tot[t] >= k && tot[t] <= kMaxCand) {
+          thr = mx - dl[t];
+          found = true;
+        } else if (tot[t] < k) {
+          hi_thr = mx - dl[t];       // still too few: the k-th value is below this
+        } else if (tot[t] > kMaxCand) {
+          lo_thr = mx - dl[t];       // too many inside this delta: bisect between hi_thr and lo_thr
+          round = 3;
+          break;
         }
       }
     }
-    for (int i = 4 * V4 + threadIdx.x; i < V; i += blockDim.x) consider(lg[i], i);
+  }
+  if (!found) {
+    // bisection on the threshold (flat or extremely wide rows); 40 halvings reach fp32 resolution
+    if (lo_thr == -INFINITY) lo_thr = mx - 1e30f;
+    for (int it = 0; it < 40 && !found; ++it) {
+      const float mid = 0.5f * (lo_thr + hi_thr);
+      int c0 = 0;
+      scan_row(lg, V, eos_id, forbid_eos, [&](float x, int) { c0 += (x >= mid) ? 1 : 0; });
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+      if (lane == 0) s_cnt[0][warp] = c0;
+      __syncthreads();
+      int tot0 = 0;
+      for (int i = 0; i < nwarps; ++i) tot0 += s_cnt[0][i];
+      __syncthreads();
+      if (tot0 >= k && tot0 <= kMaxCand) {
+        thr = mid;
+        found = true;
+      } else if (tot0 < k) {
+        hi_thr = mid;
+      } else {
+        lo_thr = mid;
+      }
+    }
+    if (!found) thr = hi_thr;  // >kMaxCand exact ties at the k-th value: keep the first kMaxCand of them
+  }
+  // ---- (3) gather the pool, exact k-th value by rank counting (ties kept) ----
+  if (threadIdx.x == 0) { s_count = 0; s_nsurv = 0; }
+  __syncthreads();
+  scan_row(lg, V, eos_id, forbid_eos, [&](float x, int i) {
+    if (x >= thr && x > -INFINITY) {
+      const int slot = atomicAdd(&s_count, 1);
+      if (slot < kMaxCand) {
+        s_cval[slot] = x;
+        s_cidx[slot] = i;
+      }
+    }
+  });
+  __syncthreads();
+  const int nc = min(s_count, kMaxCand);
+  for (int i = threadIdx.x; i < nc; i += blockDim.x) {
+    const float v = s_cval[i];
+    int greater = 0;
+    for (int j = 0; j < nc; ++j) greater += (s_cval[j] > v) ? 1 : 0;
+    if (greater < k) {  // value >= k-th largest: survives (HF TopKLogitsWarper keeps ties)
+      const int slot = atomicAdd(&s_nsurv, 1);
+      if (slot < kMaxKeep) {
+        s_val[slot] = v * inv_temp;
+        s_idx[slot] = s_cidx[i];
+      }
+    }
   }
   __syncthreads();
-  const int n = min(s_count, kMaxKeep);
+  const int n = min(s_nsurv, kMaxKeep);
   // parallel rank sort: descending by value, ties by smaller token id (deterministic)
   if ((int)threadIdx.x < n) {
     const float v = s_val[threadIdx.x];
@@ -710,10 +743,10 @@ __global__ void __launch_bounds__(1024) sample_kernel(const float* __restrict__ 
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    const float mx = s_sorted[0];
+    const float m0 = s_sorted[0];
     float tot = 0.f;
     for (int i = 0; i < n; ++i) {
-      s_sorted[i] = expf(s_sorted[i] - mx);
+      s_sorted[i] = expf(s_sorted[i] - m0);
       tot += s_sorted[i];
     }
     // nucleus: keep token i while the mass of strictly higher-ranked tokens is < top_p
@@ -747,7 +780,11 @@ __global__ void __launch_bounds__(1024) sample_kernel(const float* __restrict__ 
   }
 }
 
-__global__ void decode_advance_kernel(int* state) { state[ST_STEP] += 1; }
+__global__ void decode_advance_kernel(int* state) {
+  pdl_wait();
+  pdl_trigger();
+  state[ST_STEP] += 1;
+}
 
 }  // namespace iadr1
 
@@ -757,7 +794,7 @@ extern "C" {
 
 int iadr1_decode_embed(const void* embed, const int* tok, float* h, int rows, int H, void* stream) {
   if (rows <= 0) return 0;
-  decode_embed_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>((const bf16*)embed, tok, h, H);
+  launch_kernel(decode_embed_kernel, dim3(rows), dim3(256), 0, (cudaStream_t)stream, (const bf16*)embed, tok, h, H);
   IADR1_CHECK_LAUNCH("decode_embed");
   return 0;
 }
@@ -765,8 +802,8 @@ int iadr1_decode_embed(const void* embed, const int* tok, float* h, int rows, in
 int iadr1_rmsnorm_f32in(const float* x, const void* w, void* y, int rows, int cols, float eps, float* zero_buf,
                         int zero_per_row, void* stream) {
   if (rows <= 0) return 0;
-  rmsnorm_f32in_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(x, (const bf16*)w, (bf16*)y, cols, eps, zero_buf,
-                                                               zero_buf ? zero_per_row : 0);
+  launch_kernel(rmsnorm_f32in_kernel, dim3(rows), dim3(256), 0, (cudaStream_t)stream, x, (const bf16*)w, (bf16*)y, cols,
+                eps, zero_buf, zero_buf ? zero_per_row : 0);
   IADR1_CHECK_LAUNCH("rmsnorm_f32in");
   return 0;
 }
@@ -822,9 +859,9 @@ int iadr1_decode_attention_fused(const float* qkv, const float* cos_tab, const f
   do {                                                                                                               \
     if (kv_smem > 48 * 1024)                                                                                         \
       cudaFuncSetAttribute(decode_attn_fused_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);   \
-    decode_attn_fused_kernel<HD><<<dim3(rows, nkv, nsplit), 128, kv_smem, st>>>(                                     \
-        qkv, cos_tab, sin_tab, rope_delta, (const bf16*)kp, (const bf16*)vp, (bf16*)kc, (bf16*)vc, state, row_group, \
-        row_plen, part, tickets, (bf16*)out, nq, nkv, p_max, c_max, chunk, max_pos, scale, dbg);                     \
+    launch_kernel(decode_attn_fused_kernel<HD>, dim3(rows, nkv, nsplit), dim3(128), kv_smem, st, qkv, cos_tab,       \
+                  sin_tab, rope_delta, (const bf16*)kp, (const bf16*)vp, (bf16*)kc, (bf16*)vc, state, row_group,     \
+                  row_plen, part, tickets, (bf16*)out, nq, nkv, p_max, c_max, chunk, max_pos, scale, dbg);           \
   } while (0)
   if (hd == 128) IADR1_DECODE_FUSED(128);
   else if (hd == 64) IADR1_DECODE_FUSED(64);
@@ -841,14 +878,14 @@ const float* logits, int rows, int V, float temperature, int top_k, float top_p,
                  int pad_id, int forbid_eos, int first, void* stream) {
   if (rows <= 0) return 0;
   if (temperature <= 0.f) return set_error("sample: temperature must be > 0");
-  sample_kernel<<<rows, 1024, 0, (cudaStream_t)stream>>>(logits, V, 1.f / temperature, top_k, top_p, seed, state, tok,
-                                                         finished, out_tokens, c_max, eos_id, pad_id, forbid_eos, first);
+  launch_kernel(sample_kernel, dim3(rows), dim3(1024), 0, (cudaStream_t)stream, logits, V, 1.f / temperature, top_k,
+                top_p, seed, state, tok, finished, out_tokens, c_max, eos_id, pad_id, forbid_eos, first);
   IADR1_CHECK_LAUNCH("sample");
   return 0;
 }
 
 int iadr1_decode_advance(int* state, void* stream) {
-  decode_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state);
+  launch_kernel(decode_advance_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, state);
   IADR1_CHECK_LAUNCH("decode_advance");
   return 0;
 }

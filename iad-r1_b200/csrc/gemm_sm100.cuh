@@ -26,6 +26,7 @@ struct GemmArgs {
   int epi;
   int c_f32, trans_c, accumulate, atomic;
   int bias_per_m;
+  int a_static;   // A does not depend on the preceding kernel (weights): its first TMA loads may precede pdl_wait()
   float alpha;
   void* C;
   long long ldc, c_bs_lo, c_bs_hi;

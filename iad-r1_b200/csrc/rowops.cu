@@ -374,6 +374,8 @@ __device__ __forceinline__ float act_grad(int act, float g) {
 // gate at gu[r*ld + c], up at gu[r*ld + up_off + c] (up_off < 0: ungated), out[r*out_ld + c]; cols % 8 == 0.
 __global__ void act_mul_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict__ out, long long rows, int cols,
                                    long long ld, long long up_off, long long out_ld, int act) {
+  pdl_wait();   // no-op unless launched with the programmatic-serialization attribute (rollout decode chain)
+  if (threadIdx.x == 0) pdl_trigger();
   const int nvec = cols >> 3;
   const long long total = rows * nvec;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -667,8 +669,8 @@ int iadr1_act_mul_fwd(const void* gu, void* out, long long rows, int cols, long 
                       long long out_ld, int act, void* stream) {
   if (rows <= 0) return 0;
   if (cols % 8 || ld % 8 || out_ld % 8 || (up_off > 0 && up_off % 8)) return set_error("act_mul_fwd: alignment");
-  act_mul_fwd_kernel<<<grid_for(rows * (cols / 8), 256, 16), 256, 0, (cudaStream_t)stream>>>(
-      (const bf16*)gu, (bf16*)out, rows, cols, ld, up_off, out_ld, act);
+  launch_kernel(act_mul_fwd_kernel, dim3(grid_for(rows * (cols / 8), 256, 16)), dim3(256), 0, (cudaStream_t)stream,
+                (const bf16*)gu, (bf16*)out, rows, cols, ld, up_off, out_ld, act);
   IADR1_CHECK_LAUNCH("act_mul_fwd");
   return 0;
 }

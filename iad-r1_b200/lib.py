@@ -35,7 +35,7 @@ class GemmDesc(C.Structure):
         ("labels", C.c_void_p), ("part_max", C.c_void_p), ("part_sum", C.c_void_p), ("tgt_logit", C.c_void_p),
         ("lse_tiles_n", C.c_int),
         ("lse", C.c_void_p), ("gscale", C.c_void_p),
-        ("block_n", C.c_int), ("stages", C.c_int), ("max_ctas", C.c_int),
+        ("block_n", C.c_int), ("stages", C.c_int), ("max_ctas", C.c_int), ("a_static", C.c_int),
     ]
 
 
@@ -163,7 +163,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None, *, b
     d.alpha = alpha
     d.bias, d.bias_per_m = _ptr(bias), int(bias_per_m)
     d.residual = _ptr(residual)
-    d.block_n, d.stages, d.max_ctas = block_n, stages, max_ctas
+    d.block_n, d.stages, d.max_ctas, d.a_static = block_n, stages, max_ctas, int(a_static)
     check(lib().iadr1_gemm_bf16(C.byref(d), stream_ptr()), "iadr1_gemm_bf16")
     return out
 

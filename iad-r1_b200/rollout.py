@@ -11,6 +11,8 @@ Replaces the reference's dedicated-GPU vLLM engine and its per-step weight copy
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -42,6 +44,7 @@ class RolloutEngine:
         self.p_max, self.c_max = p_max, c_max
         self.temperature, self.top_k, self.top_p, self.forbid_eos = temperature, top_k, top_p, forbid_eos
         self.use_graph = use_cuda_graph
+        self.use_pdl = os.environ.get("IADR1_PDL", "1") != "0"
         dev = vlm.device
         Lyr, nkv, hd, H, I, V = t.num_layers, t.num_kv_heads, t.head_dim, t.hidden_size, t.intermediate_size, t.vocab_size
         self.kp = torch.zeros(Lyr, max_groups, p_max, nkv, hd, dtype=bf16, device=dev)
@@ -78,7 +81,7 @@ class RolloutEngine:
     def _skinny(self, W, x, out, split_k=1, atomic=False, bias=None):
         """out[R, F] (+)= x[R, K] @ W[F, K]^T with W as the 128-row MMA operand (swap-AB), transposed store."""
         L.gemm(W, x, out=out, trans_out=True, split_k=split_k, atomic=atomic or split_k > 1, bias=bias, bias_per_m=True,
-               block_n=self.block_n)
+               block_n=self.block_n, a_static=True)
 
     def _head_and_sample(self, first: int):
         t, p, lib = self.cfg.text, self.vlm.p, L.lib()
@@ -92,6 +95,14 @@ class RolloutEngine:
                                  int(self.forbid_eos), first, s), "sample")
 
     def _decode_step(self):
+        lib = L.lib()
+        lib.iadr1_set_pdl(int(self.use_pdl))
+        try:
+            self._decode_step_body()
+        finally:
+            lib.iadr1_set_pdl(0)
+
+    def _decode_step_body(self):
         t, p, lib = self.cfg.text, self.vlm.p, L.lib()
         R, H, I, nq, nkv, hd = self.R, t.hidden_size, t.intermediate_size, t.num_heads, t.num_kv_heads, t.head_dim
         s = L.stream_ptr()

@@ -51,10 +51,14 @@ typedef struct iadr1_gemm_t {
   const int* labels; float* part_max; float* part_sum; float* tgt_logit; int lse_tiles_n;
   const float* lse; const float* gscale;
   int block_n, stages, max_ctas;     /* 0 = library heuristics */
+  int a_static;                      /* A (weights) is not produced by the preceding kernel: prefetchable under PDL */
 } iadr1_gemm_t;
 int iadr1_gemm_bf16(const iadr1_gemm_t* desc, void* stream);
 /* block_n the library would choose for an N-wide product (sizes the EPI_LSE partial buffers). */
 int iadr1_gemm_pick_block_n(int N, int b_mn);
+/* Programmatic dependent launch for the kernels launched while enabled (the rollout decode chain): each kernel's
+ * launch + prologue + predecessor-independent prefetch overlaps the previous kernel's tail.                          */
+int iadr1_set_pdl(int on);
 /* Live roofline support: time every (non-graph-captured) GEMM launch with CUDA events on its own stream and count its
  * algorithmic FLOPs. Collect after a device synchronise.                                                            */
 int iadr1_gemm_profile_enable(int on);
