@@ -130,7 +130,7 @@ def _mat(t: torch.Tensor, what: str):
 def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None, *, bias=None, residual=None,
          alpha: float = 1.0, accumulate: bool = False, out_dtype=torch.bfloat16, split_k: int = 1,
          atomic: bool | None = None, trans_out: bool = False, bias_per_m: bool = False, block_n: int = 0, stages: int = 0,
-         max_ctas: int = 0) -> torch.Tensor:
+         max_ctas: int = 0, a_static: bool = False) -> torch.Tensor:
     """out[M,N] (+)= alpha * a[M,K] @ b[N,K]^T (+ bias) (+ residual).
 
     ``a`` and ``b`` are 2-D bf16 *views*; either of their dims may be the contiguous one, so ``x @ W.T`` is
