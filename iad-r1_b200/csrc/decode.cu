@@ -715,15 +715,51 @@ __global__ void __launch_bounds__(1024) sample_kernel(const float* __restrict__ 
   });
   __syncthreads();
   const int nc = min(s_count, kMaxCand);
+  // Refine the threshold INSIDE the pool (shared memory only): bisection with __syncthreads_count until the pool above
+  // the threshold holds between k and 2k values, so the exact rank counting below is O((2k)^2), not O(pool^2).
+  float rlo = thr, rhi = mx;
+  {
+    const float e0 = ((int)threadIdx.x < nc) ? s_cval[threadIdx.x] : -INFINITY;
+    const float e1 = ((int)threadIdx.x + 1024 < nc) ? s_cval[threadIdx.x + 1024] : -INFINITY;
+    for (int it = 0; it < 24; ++it) {
+      const float mid = 0.5f * (rlo + rhi);
+      const int cnt = __syncthreads_count(e0 >= mid) + __syncthreads_count(e1 >= mid);
+      if (cnt >= k) {
+        rlo = mid;
+        if (cnt <= 2 * k) break;
+      } else {
+        rhi = mid;
+      }
+    }
+  }
+  // compact the refined pool (values >= rlo: between k and ~2k of them, more only under exact ties) ...
+  __shared__ int s_m;
+  __shared__ float s_pv[kMaxKeep * 2];
+  __shared__ int s_pi[kMaxKeep * 2];
+  if (threadIdx.x == 0) s_m = 0;
+  __syncthreads();
   for (int i = threadIdx.x; i < nc; i += blockDim.x) {
     const float v = s_cval[i];
+    if (v >= rlo) {
+      const int slot = atomicAdd(&s_m, 1);
+      if (slot < kMaxKeep * 2) {
+        s_pv[slot] = v;
+        s_pi[slot] = s_cidx[i];
+      }
+    }
+  }
+  __syncthreads();
+  const int m = min(s_m, kMaxKeep * 2);
+  // ... and rank-count inside it: anything greater than a pool member is itself in the pool, so ranks are global
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    const float v = s_pv[i];
     int greater = 0;
-    for (int j = 0; j < nc; ++j) greater += (s_cval[j] > v) ? 1 : 0;
+    for (int j = 0; j < m; ++j) greater += (s_pv[j] > v) ? 1 : 0;
     if (greater < k) {  // value >= k-th largest: survives (HF TopKLogitsWarper keeps ties)
       const int slot = atomicAdd(&s_nsurv, 1);
       if (slot < kMaxKeep) {
         s_val[slot] = v * inv_temp;
-        s_idx[slot] = s_cidx[i];
+        s_idx[slot] = s_pi[i];
       }
     }
   }
