@@ -427,7 +427,8 @@ __global__ void act_mul_bwd_kernel(const bf16* __restrict__ dout, const bf16* gu
 // One warp per row.
 // ------------------------------------------------------------------------------------------------
 __global__ void softmax_rows_kernel(bf16* __restrict__ S, const int* __restrict__ lo, const int* __restrict__ hi,
-                                    int Tq, int Tk, long long ld, long long z_stride, long long nrows) {
+                                    int Tq, int Tk, long long ld, long long z_stride, long long nrows, int hole_lo,
+                                    int hole_hi) {
   const int lane = threadIdx.x & 31;
   const long long gw = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   if (gw >= nrows) return;
@@ -435,23 +436,26 @@ __global__ void softmax_rows_kernel(bf16* __restrict__ S, const int* __restrict_
   const long long z = gw / Tq;
   bf16* row = S + z * z_stride + (long long)q * ld;
   const int a = max(0, lo[q]), b = min(Tk, hi[q]);
+  // keys in [hole_lo, hole_hi) are padding between two key segments (shared-prefix layout) and are always masked
   float mx = -INFINITY;
-  for (int k = a + lane; k < b; k += 32) mx = fmaxf(mx, __bfloat162float(row[k]));
+  for (int k = a + lane; k < b; k += 32)
+    if (k < hole_lo || k >= hole_hi) mx = fmaxf(mx, __bfloat162float(row[k]));
   mx = warp_max(mx);
   float sum = 0.f;
-  for (int k = a + lane; k < b; k += 32) sum += __expf(__bfloat162float(row[k]) - mx);
+  for (int k = a + lane; k < b; k += 32)
+    if (k < hole_lo || k >= hole_hi) sum += __expf(__bfloat162float(row[k]) - mx);
   sum = warp_sum(sum);
-  const float inv = (b > a) ? 1.f / sum : 0.f;
+  const float inv = (sum > 0.f) ? 1.f / sum : 0.f;
   for (int k = lane; k < Tk; k += 32) {
     float p = 0.f;
-    if (k >= a && k < b) p = __expf(__bfloat162float(row[k]) - mx) * inv;
+    if (k >= a && k < b && (k < hole_lo || k >= hole_hi)) p = __expf(__bfloat162float(row[k]) - mx) * inv;
     row[k] = __float2bfloat16(p);
   }
 }
 // dS = P * (dP - sum_k dP*P) in place on dP; exact zero outside the row's range.
 __global__ void softmax_bwd_rows_kernel(const bf16* __restrict__ P, bf16* __restrict__ dP, const int* __restrict__ lo,
                                         const int* __restrict__ hi, int Tq, int Tk, long long ld, long long z_stride,
-                                        long long nrows) {
+                                        long long nrows, int hole_lo, int hole_hi) {
   const int lane = threadIdx.x & 31;
   const long long gw = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   if (gw >= nrows) return;
@@ -461,11 +465,12 @@ __global__ void softmax_bwd_rows_kernel(const bf16* __restrict__ P, bf16* __rest
   bf16* d = dP + z * z_stride + (long long)q * ld;
   const int a = max(0, lo[q]), b = min(Tk, hi[q]);
   float dot = 0.f;
-  for (int k = a + lane; k < b; k += 32) dot += __bfloat162float(p[k]) * __bfloat162float(d[k]);
+  for (int k = a + lane; k < b; k += 32)
+    if (k < hole_lo || k >= hole_hi) dot += __bfloat162float(p[k]) * __bfloat162float(d[k]);
   dot = warp_sum(dot);
   for (int k = lane; k < Tk; k += 32) {
     float o = 0.f;
-    if (k >= a && k < b) o = __bfloat162float(p[k]) * (__bfloat162float(d[k]) - dot);
+    if (k >= a && k < b && (k < hole_lo || k >= hole_hi)) o = __bfloat162float(p[k]) * (__bfloat162float(d[k]) - dot);
     d[k] = __float2bfloat16(o);
   }
 }
@@ -529,7 +534,7 @@ __global__ void colsum_kernel(const bf16* __restrict__ x, float* __restrict__ ou
 // out[r][kvh*hd + d] = sum_{j<g} src[r][(kvh*g + j)*hd + d]: folds the per-query-head dK / dV of grouped-query
 // attention back onto the shared kv heads (autograd of repeat_kv, modeling_qwen2_5_vl.py:170-179).
 __global__ void group_sum_kernel(const bf16* __restrict__ src, bf16* __restrict__ out, long long rows, int nkv, int g,
-                                 int hd, long long src_ld, long long out_ld) {
+                                 int hd, long long src_ld, long long out_ld, int accumulate) {
   const long long total = rows * nkv * hd;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -539,7 +544,9 @@ __global__ void group_sum_kernel(const bf16* __restrict__ src, bf16* __restrict_
     const long long r = t / nkv;
     float acc = 0.f;
     for (int j = 0; j < g; ++j) acc += __bfloat162float(src[r * src_ld + (long long)(kvh * g + j) * hd + d]);
-    out[r * out_ld + (long long)kvh * hd + d] = __float2bfloat16(acc);
+    bf16* o = out + r * out_ld + (long long)kvh * hd + d;
+    if (accumulate) acc += __bfloat162float(*o);
+    *o = __float2bfloat16(acc);
   }
 }
 
@@ -686,23 +693,23 @@ int iadr1_act_mul_bwd(const void* dout, const void* gu, void* dgu, long long row
 }
 
 int iadr1_softmax_rows(void* S, const int* lo, const int* hi, int Tq, int Tk, long long ld, long long z_stride,
-                       long long batch, void* stream) {
+                       long long batch, int hole_lo, int hole_hi, void* stream) {
   const long long nrows = batch * Tq;
   if (nrows <= 0) return 0;
   const long long blocks = (nrows * 32 + 255) / 256;
   softmax_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((bf16*)S, lo, hi, Tq, Tk, ld, z_stride,
-                                                                          nrows);
+                                                                          nrows, hole_lo, hole_hi);
   IADR1_CHECK_LAUNCH("softmax_rows");
   return 0;
 }
 
 int iadr1_softmax_bwd_rows(const void* P, void* dP, const int* lo, const int* hi, int Tq, int Tk, long long ld,
-                           long long z_stride, long long batch, void* stream) {
+                           long long z_stride, long long batch, int hole_lo, int hole_hi, void* stream) {
   const long long nrows = batch * Tq;
   if (nrows <= 0) return 0;
   const long long blocks = (nrows * 32 + 255) / 256;
   softmax_bwd_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)P, (bf16*)dP, lo, hi, Tq,
-                                                                              Tk, ld, z_stride, nrows);
+                                                                              Tk, ld, z_stride, nrows, hole_lo, hole_hi);
   IADR1_CHECK_LAUNCH("softmax_bwd_rows");
   return 0;
 }
@@ -740,10 +747,10 @@ int iadr1_colsum(const void* x, float* out, long long rows, int cols, long long 
 }
 
 int iadr1_group_sum(const void* src, void* out, long long rows, int nkv, int g, int hd, long long src_ld,
-                    long long out_ld, void* stream) {
+                    long long out_ld, int accumulate, void* stream) {
   if (rows <= 0) return 0;
   group_sum_kernel<<<grid_for(rows * nkv * hd, 256, 16), 256, 0, (cudaStream_t)stream>>>((const bf16*)src, (bf16*)out,
-                                                                                        rows, nkv, g, hd, src_ld, out_ld);
+                                                                                        rows, nkv, g, hd, src_ld, out_ld, accumulate);
   IADR1_CHECK_LAUNCH("group_sum");
   return 0;
 }

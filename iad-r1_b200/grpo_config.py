@@ -106,6 +106,7 @@ class GRPOConfig:
     rollout_top_p: float = 0.9                 # SCGRPOTrainer hard-codes top_p=0.9, top_k=50 (sc_grpo_trainer.py:353-358)
     rollout_top_k: int = 50
     batched_rollout: bool = True               # roll out every group of an accumulation window in one decode batch
+    shared_prefix: bool = True                 # score a group as [prompt | G completions]: the prompt is computed once
     rollout_forbid_eos: bool = False           # benchmarking only: fixed-length completions
     rollout_seed: Optional[int] = None
 

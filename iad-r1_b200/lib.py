@@ -170,7 +170,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None, *, b
 
 def gemm_batched(a, b, out, *, M, N, K, batch, batch_lo=0, b_lo_div=1, lda, a_bs_lo=0, a_bs_hi=0, a_mn=0, ldb,
                  b_bs_lo=0, b_bs_hi=0, b_mn=0, ldc, c_bs_lo=0, c_bs_hi=0, alpha=1.0, kmode=0, skip_mode=0,
-                 causal_off=0, block_n=0, a_off=0, b_off=0, c_off=0):
+                 causal_off=0, block_n=0, a_off=0, b_off=0, c_off=0, residual=None):
     """Raw batched entry (element strides) used by the attention compositions. Offsets are in elements."""
     d = GemmDesc()
     d.M, d.N, d.K = M, N, K
@@ -184,5 +184,7 @@ def gemm_batched(a, b, out, *, M, N, K, batch, batch_lo=0, b_lo_div=1, lda, a_bs
     d.alpha = alpha
     d.kmode, d.skip_mode, d.causal_off = kmode, skip_mode, causal_off
     d.block_n = block_n
+    if residual is not None:  # bf16, indexed exactly like C (same offset / strides)
+        d.residual = residual.data_ptr() + 2 * c_off
     check(lib().iadr1_gemm_bf16(C.byref(d), stream_ptr()), "iadr1_gemm_bf16(batched)")
     return out

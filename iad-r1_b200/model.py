@@ -165,17 +165,20 @@ class VLM:
     # =============================================================================================================
     # decoder
     # =============================================================================================================
-    def decoder_forward(self, src_index: torch.Tensor, image_embeds, B: int, T: int, cos, sin, save: bool = True,
-                        kv_sink=None):
-        """src_index [B*T] int32 (token id, or -1-row into image_embeds) -> last hidden states [B*T, H] (pre final norm).
-        kv_sink(layer, qkv) is called with each layer's post-rotary fused qkv buffer (rollout prefill fills its cache)."""
+    def full_attention(self, B: int, T: int):
+        t = self.cfg.text
+        lo, hi = self._causal_ranges(T)
+        return ops.FullAttention(B, T, t.num_heads, t.num_kv_heads, t.head_dim, lo, hi, causal=True)
+
+    def decoder_forward(self, src_index: torch.Tensor, image_embeds, attn, cos, sin, save: bool = True, kv_sink=None):
+        """src_index [N] int32 (token id, or -1-row into image_embeds) -> last hidden states [N, H] (pre final norm).
+        `attn` is the attention strategy for the token layout (ops.FullAttention: B x T rows; ops.SharedPrefixAttention:
+        one prompt + G completions). kv_sink(layer, qkv) sees each layer's post-rotary fused qkv buffer (rollout prefill)."""
         t, p = self.cfg.text, self.p
         H, I, nq, nkv, hd = t.hidden_size, t.intermediate_size, t.num_heads, t.num_kv_heads, t.head_dim
         h = ops.gather_rows(p["embed_tokens.weight"], src_index, alt=image_embeds)
-        sh = ops.AttnShape(B, T, nq, nkv, hd, causal=True)
-        lo, hi = self._causal_ranges(T)
         ctx = DecoderCtx()
-        ctx.layers, ctx.sh, ctx.cos, ctx.sin, ctx.src_index = [], sh, cos, sin, src_index
+        ctx.layers, ctx.attn, ctx.cos, ctx.sin, ctx.src_index = [], attn, cos, sin, src_index
         for i in range(t.num_layers):
             b = f"layers.{i}."
             xn, r1 = ops.rmsnorm_fwd(h, p[b + "ln1.weight"], t.rms_norm_eps, save_rstd=save)
@@ -183,14 +186,14 @@ class VLM:
             ops.rope_(qkv, cos, sin, nq + nkv, hd, bf16_ops=1)
             if kv_sink is not None:
                 kv_sink(i, qkv)
-            attn, P = ops.attention_fwd(qkv, sh, lo, hi)
-            h_mid = ops.linear_fwd(attn, p[b + "o.weight"], residual=h)
+            a_out, a_saved = attn.forward(qkv)
+            h_mid = ops.linear_fwd(a_out, p[b + "o.weight"], residual=h)
             xn2, r2 = ops.rmsnorm_fwd(h_mid, p[b + "ln2.weight"], t.rms_norm_eps, save_rstd=save)
             gu = ops.linear_fwd(xn2, p[b + "gate_up.weight"])
             act = ops.act_mul_fwd(gu, I, ops.ACT_SILU, gated=True)
             h_out = ops.linear_fwd(act, p[b + "down.weight"], residual=h_mid)
             if save:
-                ctx.layers.append((h, r1, xn, qkv, P, attn, h_mid, r2, xn2, gu, act))
+                ctx.layers.append((h, r1, xn, qkv, a_saved, a_out, h_mid, r2, xn2, gu, act))
             h = h_out
         return h, (ctx if save else None)
 
@@ -198,7 +201,6 @@ class VLM:
         """dh [B*T, H] bf16 (consumed in place). Returns d(image embeddings) fp32 [n_image_rows, H] or None."""
         t, p, g = self.cfg.text, self.p, self.g
         I, nq, nkv, hd = t.intermediate_size, t.num_heads, t.num_kv_heads, t.head_dim
-        lo, hi = self._causal_ranges(ctx.sh.T)
         for i in reversed(range(t.num_layers)):
             b = f"layers.{i}."
             h, r1, xn, qkv, P, attn, h_mid, r2, xn2, gu, act = ctx.layers[i]
@@ -207,7 +209,7 @@ class VLM:
             dxn2 = ops.linear_bwd(dgu, xn2, p[b + "gate_up.weight"], g[b + "gate_up.weight"])
             ops.rmsnorm_bwd(dxn2, h_mid, p[b + "ln2.weight"], r2, dh, g[b + "ln2.weight"], add_dx=True)
             dattn = ops.linear_bwd(dh, attn, p[b + "o.weight"], g[b + "o.weight"])
-            dqkv = ops.attention_bwd(dattn, qkv, P, ctx.sh, lo, hi)
+            dqkv = ctx.attn.backward(dattn, qkv, P)
             ops.rope_(dqkv, ctx.cos, ctx.sin, nq + nkv, hd, bf16_ops=0, backward=True)
             dxn = ops.linear_bwd(dqkv, xn, p[b + "qkv.weight"], g[b + "qkv.weight"], g[b + "qkv.bias"])
             ops.rmsnorm_bwd(dxn, h, p[b + "ln1.weight"], r1, dh, g[b + "ln1.weight"], add_dx=True)
@@ -242,20 +244,50 @@ class VLM:
         return dict(B=B, T=T, grid=grid, cos=cos, sin=sin, src_index=src, n_img_tokens=n_img_tokens,
                     pixel_values=pixel_values)
 
+    def prepare_group(self, prompt_ids, completion_ids, pixel_values, grid_thw):
+        """Shared-prefix layout for ONE GRPO group: tokens [prompt (P) | completion row 0 (C) | ... | row G-1 (C)].
+        Returns the batch dict plus `sel_index` / flattened labels for the G*C completion log-probs: the logit predicting
+        completion token 0 of every row comes from the (single) last prompt position."""
+        pr = np.asarray(prompt_ids, dtype=np.int64).reshape(1, -1)
+        comp = completion_ids.detach().cpu().numpy() if torch.is_tensor(completion_ids) else np.asarray(completion_ids)
+        G, C = comp.shape
+        P = pr.shape[1]
+        grid = [tuple(int(x) for x in r) for r in (grid_thw.tolist() if torch.is_tensor(grid_thw) else grid_thw)] \
+            if grid_thw is not None else []
+        unit = self.cfg.vision.spatial_merge_size ** 2
+        n_img_tokens = sum(t * h * w for t, h, w in grid) // unit
+        pos_p, delta = mrope_position_ids(pr, grid, self.cfg)
+        nxt = int(pos_p.max()) + 1 if P else 0
+        pos_c = np.broadcast_to((nxt + np.arange(C))[None, None, :], (3, G, C)).reshape(3, 1, G * C)
+        pos = torch.from_numpy(np.concatenate([pos_p, pos_c], axis=2))
+        cos, sin = text_rope_tables(pos, self.cfg.text, self.device)
+        src_p = embed_source_index(pr, self.cfg.image_token_id, False, n_img_tokens)
+        src = torch.from_numpy(np.concatenate([src_p, comp.reshape(-1).astype(np.int32)])).to(self.device)
+        rows = np.empty((G, C), dtype=np.int32)
+        rows[:, 0] = P - 1
+        rows[:, 1:] = P + np.arange(G)[:, None] * C + np.arange(C - 1)[None, :]
+        t = self.cfg.text
+        attn = ops.SharedPrefixAttention(P, G, C, t.num_heads, t.num_kv_heads, t.head_dim, self.device)
+        return dict(shared=True, P=P, G=G, C=C, N=P + G * C, attn=attn, grid=grid, cos=cos, sin=sin, src_index=src,
+                    n_img_tokens=n_img_tokens, pixel_values=pixel_values,
+                    sel_index=torch.from_numpy(rows.reshape(-1)).to(self.device),
+                    labels=torch.from_numpy(comp.reshape(-1).astype(np.int32)).to(self.device))
+
     def logprobs_forward(self, batch: dict, sel_index: torch.Tensor, labels: torch.Tensor, temperature: float = 1.0,
                          save: bool = True):
         """log p(labels[j] | prefix) at hidden-state rows sel_index[j] (flattened b*T + t). Returns (logp fp32, ctx)."""
         img, vctx = (None, None)
         if batch["n_img_tokens"] > 0:
             img, vctx = self.vision_forward(batch["pixel_values"], batch["grid"], save=save)
-        h, dctx = self.decoder_forward(batch["src_index"], img, batch["B"], batch["T"], batch["cos"], batch["sin"], save=save)
+        attn = batch["attn"] if batch.get("shared") else self.full_attention(batch["B"], batch["T"])
+        h, dctx = self.decoder_forward(batch["src_index"], img, attn, batch["cos"], batch["sin"], save=save)
         hsel = ops.gather_rows(h, sel_index)
         hn, rf = ops.rmsnorm_fwd(hsel, self.p["norm.weight"], self.cfg.text.rms_norm_eps, save_rstd=save)
         logp, lse = ops.logprob_fwd(hn, self.params.lm_head, labels, temperature)
         ctx = None
         if save:
             ctx = dict(vctx=vctx, dctx=dctx, hsel=hsel, hn=hn, rf=rf, lse=lse, labels=labels, sel_index=sel_index,
-                       temperature=temperature, N=batch["B"] * batch["T"], n_img=batch["n_img_tokens"])
+                       temperature=temperature, N=attn.n_tokens, n_img=batch["n_img_tokens"])
         return logp, ctx
 
     def logprobs_backward(self, dlogp: torch.Tensor, ctx: dict):
@@ -265,10 +297,10 @@ class VLM:
                               ctx["temperature"])
         dhsel = torch.empty_like(dhn)
         ops.rmsnorm_bwd(dhn, ctx["hsel"], self.p["norm.weight"], ctx["rf"], dhsel, self.g["norm.weight"], add_dx=False)
-        N = ctx["N"]
-        inv = torch.full((N,), -1, dtype=torch.int32, device=self.device)
-        inv[ctx["sel_index"].long()] = torch.arange(dhsel.shape[0], dtype=torch.int32, device=self.device)
-        dh = ops.gather_rows(dhsel, inv, alt=self._zero_row[:, :t.hidden_size])
+        # scatter-ADD back to token rows (the last prompt position is selected once per row in the shared layout)
+        dh32 = torch.zeros(ctx["N"], t.hidden_size, dtype=f32, device=self.device)
+        ops.scatter_add_rows(dhsel, ctx["sel_index"], dh32, None)
+        dh = ops.cast_f32_bf16(dh32)
         dimg32 = self.decoder_backward(dh, ctx["dctx"], ctx["n_img"])
         if dimg32 is not None and ctx["vctx"] is not None:
             self.vision_backward(ops.cast_f32_bf16(dimg32), ctx["vctx"])

@@ -96,13 +96,14 @@ def act_mul_bwd(dout, gu, cols, act, gated=True, dgu=None):
 
 
 # ---- softmax / gathers / reductions -----------------------------------------------------------------------------------
-def softmax_rows_(S, lo, hi, Tq, Tk, ld, z_stride, batch):
-    L.check(L.lib().iadr1_softmax_rows(_p(S), _p(lo), _p(hi), Tq, Tk, ld, z_stride, batch, _s()), "softmax_rows")
+def softmax_rows_(S, lo, hi, Tq, Tk, ld, z_stride, batch, hole=(0, 0)):
+    L.check(L.lib().iadr1_softmax_rows(_p(S), _p(lo), _p(hi), Tq, Tk, ld, z_stride, batch, hole[0], hole[1], _s()),
+            "softmax_rows")
 
 
-def softmax_bwd_rows_(P, dP, lo, hi, Tq, Tk, ld, z_stride, batch):
-    L.check(L.lib().iadr1_softmax_bwd_rows(_p(P), _p(dP), _p(lo), _p(hi), Tq, Tk, ld, z_stride, batch, _s()),
-            "softmax_bwd_rows")
+def softmax_bwd_rows_(P, dP, lo, hi, Tq, Tk, ld, z_stride, batch, hole=(0, 0)):
+    L.check(L.lib().iadr1_softmax_bwd_rows(_p(P), _p(dP), _p(lo), _p(hi), Tq, Tk, ld, z_stride, batch, hole[0], hole[1],
+                                           _s()), "softmax_bwd_rows")
 
 
 def gather_rows(table, index, alt=None, out=None):
@@ -128,8 +129,8 @@ def colsum(x, out32):
     L.check(L.lib().iadr1_colsum(_p(x), _p(out32), rows, cols, x.stride(0), _s()), "colsum")
 
 
-def group_sum(src, out, rows, nkv, g, hd, src_ld, out_ld):
-    L.check(L.lib().iadr1_group_sum(_p(src), _p(out), rows, nkv, g, hd, src_ld, out_ld, _s()), "group_sum")
+def group_sum(src, out, rows, nkv, g, hd, src_ld, out_ld, accumulate=False):
+    L.check(L.lib().iadr1_group_sum(_p(src), _p(out), rows, nkv, g, hd, src_ld, out_ld, int(accumulate), _s()), "group_sum")
 
 
 def add_bf16(a, b, out=None):
@@ -229,6 +230,109 @@ def attention_bwd(dattn, qkv, P, sh: AttnShape, lo, hi, dqkv=None):
         group_sum(dk_buf, dqkv[:, k_off:], B * T, nkv, g, hd, nq * hd, D)
         group_sum(dv_buf, dqkv[:, v_off:], B * T, nkv, g, hd, nq * hd, D)
     return dqkv
+
+
+class FullAttention:
+    """B sequences of T tokens, causal (or ranged) attention inside each sequence."""
+
+    def __init__(self, B, T, nq, nkv, hd, lo, hi, causal=True):
+        self.sh = AttnShape(B, T, nq, nkv, hd, causal)
+        self.lo, self.hi = lo, hi
+        self.n_tokens = B * T
+
+    def forward(self, qkv):
+        return attention_fwd(qkv, self.sh, self.lo, self.hi)
+
+    def backward(self, dattn, qkv, saved):
+        return attention_bwd(dattn, qkv, saved, self.sh, self.lo, self.hi)
+
+
+class SharedPrefixAttention:
+    """One prompt of P tokens followed by G completions of C tokens, laid out [prefix | row 0 | row 1 | ...].
+
+    The G rows of a GRPO group share their prompt (ref: sc_grpo_trainer.py:624-628 repeats the prompt tensors G times and
+    runs the full [G, P + C] batch); causal attention makes the prompt's hidden states identical in every row, so they
+    are computed once: prefix tokens attend causally to the prefix, completion token c of row g attends to the whole
+    prefix plus tokens <= c of its own row. Scores live in S[nq, G*C, Pp + Cp] with the prefix keys in columns [0, P),
+    a masked alignment gap [P, Pp) and the row's own keys from column Pp. Gradients into the prefix K/V sum over rows
+    inside the GEMM reduction (the K dimension runs over all G*C queries)."""
+
+    def __init__(self, P, G, C, nq, nkv, hd, device):
+        self.P, self.G, self.C, self.nq, self.nkv, self.hd = P, G, C, nq, nkv, hd
+        self.g = nq // nkv
+        self.D = (nq + 2 * nkv) * hd
+        self.Pp, self.Cp = ceil_to(P, 8), ceil_to(C, 8)
+        self.Tk = self.Pp + self.Cp
+        self.scale = float(hd) ** -0.5
+        self.n_tokens = P + G * C
+        self.prefix = AttnShape(1, P, nq, nkv, hd, True)
+        self.p_lo = torch.zeros(P, dtype=torch.int32, device=device)
+        self.p_hi = torch.arange(1, P + 1, dtype=torch.int32, device=device)
+        self.c_lo = torch.zeros(G * C, dtype=torch.int32, device=device)
+        self.c_hi = (self.Pp + (torch.arange(G * C, device=device) % C) + 1).to(torch.int32)
+
+    def forward(self, qkv):
+        P, G, C, nq, nkv, hd, g, D, Pp, Tk = self.P, self.G, self.C, self.nq, self.nkv, self.hd, self.g, self.D, self.Pp, self.Tk
+        GC = G * C
+        attn = torch.empty(self.n_tokens, nq * hd, dtype=bf16, device=qkv.device)
+        _, Pm = attention_fwd(qkv[:P], self.prefix, self.p_lo, self.p_hi, out=attn[:P])
+        S = torch.empty(nq, GC, Tk, dtype=bf16, device=qkv.device)
+        k_off, v_off = nq * hd, (nq + nkv) * hd
+        L.gemm_batched(qkv, qkv, S, M=GC, N=P, K=hd, batch=nq, batch_lo=nq, b_lo_div=g, lda=D, a_bs_lo=hd, a_off=P * D,
+                       ldb=D, b_bs_lo=hd, b_off=k_off, ldc=Tk, c_bs_lo=GC * Tk, alpha=self.scale)
+        L.gemm_batched(qkv, qkv, S, M=C, N=C, K=hd, batch=G * nq, batch_lo=nq, b_lo_div=g, lda=D, a_bs_lo=hd,
+                       a_bs_hi=C * D, a_off=P * D, ldb=D, b_bs_lo=hd, b_bs_hi=C * D, b_off=P * D + k_off, ldc=Tk,
+                       c_bs_lo=GC * Tk, c_bs_hi=C * Tk, c_off=Pp, alpha=self.scale, skip_mode=1)
+        softmax_rows_(S, self.c_lo, self.c_hi, GC, Tk, Tk, GC * Tk, nq, hole=(P, Pp))
+        out = attn[P:]
+        L.gemm_batched(S, qkv, out, M=GC, N=hd, K=P, batch=nq, batch_lo=nq, b_lo_div=g, lda=Tk, a_bs_lo=GC * Tk,
+                       ldb=D, b_bs_lo=hd, b_mn=1, b_off=v_off, ldc=nq * hd, c_bs_lo=hd)
+        L.gemm_batched(S, qkv, out, M=C, N=hd, K=C, batch=G * nq, batch_lo=nq, b_lo_div=g, lda=Tk, a_bs_lo=GC * Tk,
+                       a_bs_hi=C * Tk, a_off=Pp, ldb=D, b_bs_lo=hd, b_bs_hi=C * D, b_mn=1, b_off=P * D + v_off,
+                       ldc=nq * hd, c_bs_lo=hd, c_bs_hi=C * nq * hd, kmode=1, residual=out)
+        return attn, (Pm, S)
+
+    def backward(self, dattn, qkv, saved):
+        P, G, C, nq, nkv, hd, g, D, Pp, Tk = self.P, self.G, self.C, self.nq, self.nkv, self.hd, self.g, self.D, self.Pp, self.Tk
+        GC, QH = G * C, nq * hd
+        Pm, S = saved
+        dev = qkv.device
+        dqkv = torch.empty(self.n_tokens, D, dtype=bf16, device=dev)
+        attention_bwd(dattn[:P], qkv[:P], Pm, self.prefix, self.p_lo, self.p_hi, dqkv=dqkv[:P])
+        k_off, v_off = nq * hd, (nq + nkv) * hd
+        dP = torch.empty_like(S)
+        # dP = dO V^T over both key segments
+        L.gemm_batched(dattn, qkv, dP, M=GC, N=P, K=hd, batch=nq, batch_lo=nq, b_lo_div=g, lda=QH, a_bs_lo=hd,
+                       a_off=P * QH, ldb=D, b_bs_lo=hd, b_off=v_off, ldc=Tk, c_bs_lo=GC * Tk)
+        L.gemm_batched(dattn, qkv, dP, M=C, N=C, K=hd, batch=G * nq, batch_lo=nq, b_lo_div=g, lda=QH, a_bs_lo=hd,
+                       a_bs_hi=C * QH, a_off=P * QH, ldb=D, b_bs_lo=hd, b_bs_hi=C * D, b_off=P * D + v_off, ldc=Tk,
+                       c_bs_lo=GC * Tk, c_bs_hi=C * Tk, c_off=Pp, skip_mode=1)
+        softmax_bwd_rows_(S, dP, self.c_lo, self.c_hi, GC, Tk, Tk, GC * Tk, nq, hole=(P, Pp))  # dP now holds dS
+        # dQ_c = scale * (dS[:, :P] K_p + dS[:, Pp:] K_g)
+        L.gemm_batched(dP, qkv, dqkv, M=GC, N=hd, K=P, batch=nq, batch_lo=nq, b_lo_div=g, lda=Tk, a_bs_lo=GC * Tk,
+                       ldb=D, b_bs_lo=hd, b_mn=1, b_off=k_off, ldc=D, c_bs_lo=hd, c_off=P * D, alpha=self.scale)
+        L.gemm_batched(dP, qkv, dqkv, M=C, N=hd, K=C, batch=G * nq, batch_lo=nq, b_lo_div=g, lda=Tk, a_bs_lo=GC * Tk,
+                       a_bs_hi=C * Tk, a_off=Pp, ldb=D, b_bs_lo=hd, b_bs_hi=C * D, b_mn=1, b_off=P * D + k_off,
+                       ldc=D, c_bs_lo=hd, c_bs_hi=C * D, c_off=P * D, alpha=self.scale, kmode=1, residual=dqkv)
+        # prefix keys / values: reduction over ALL G*C completion queries in one product per head
+        tp = torch.empty(2, P, QH, dtype=bf16, device=dev)
+        L.gemm_batched(dP, qkv, tp[0], M=P, N=hd, K=GC, batch=nq, batch_lo=nq, lda=Tk, a_bs_lo=GC * Tk, a_mn=1,
+                       ldb=D, b_bs_lo=hd, b_mn=1, b_off=P * D, ldc=QH, c_bs_lo=hd, alpha=self.scale)
+        L.gemm_batched(S, dattn, tp[1], M=P, N=hd, K=GC, batch=nq, batch_lo=nq, lda=Tk, a_bs_lo=GC * Tk, a_mn=1,
+                       ldb=QH, b_bs_lo=hd, b_mn=1, b_off=P * QH, ldc=QH, c_bs_lo=hd)
+        group_sum(tp[0], dqkv[:, k_off:], P, nkv, g, hd, QH, D, accumulate=True)
+        group_sum(tp[1], dqkv[:, v_off:], P, nkv, g, hd, QH, D, accumulate=True)
+        # each row's own keys / values
+        tc = torch.empty(2, GC, QH, dtype=bf16, device=dev)
+        L.gemm_batched(dP, qkv, tc[0], M=C, N=hd, K=C, batch=G * nq, batch_lo=nq, lda=Tk, a_bs_lo=GC * Tk,
+                       a_bs_hi=C * Tk, a_off=Pp, a_mn=1, ldb=D, b_bs_lo=hd, b_bs_hi=C * D, b_mn=1, b_off=P * D,
+                       ldc=QH, c_bs_lo=hd, c_bs_hi=C * QH, alpha=self.scale, kmode=2)
+        L.gemm_batched(S, dattn, tc[1], M=C, N=hd, K=C, batch=G * nq, batch_lo=nq, lda=Tk, a_bs_lo=GC * Tk,
+                       a_bs_hi=C * Tk, a_off=Pp, a_mn=1, ldb=QH, b_bs_lo=hd, b_bs_hi=C * QH, b_mn=1, b_off=P * QH,
+                       ldc=QH, c_bs_lo=hd, c_bs_hi=C * QH, kmode=2)
+        group_sum(tc[0], dqkv[P:, k_off:], GC, nkv, g, hd, QH, D)
+        group_sum(tc[1], dqkv[P:, v_off:], GC, nkv, g, hd, QH, D)
+        return dqkv
 
 
 # ---- fused lm_head -> log-softmax -> gather -----------------------------------------------------------------------------

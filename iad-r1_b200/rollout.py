@@ -164,7 +164,8 @@ class RolloutEngine:
                 self.kp[layer, gi, :P].copy_(kv[:, nq:nq + nkv])
                 self.vp[layer, gi, :P].copy_(kv[:, nq + nkv:])
 
-            h, _ = vlm.decoder_forward(batch["src_index"], img, 1, P, batch["cos"], batch["sin"], save=False, kv_sink=sink)
+            h, _ = vlm.decoder_forward(batch["src_index"], img, vlm.full_attention(1, P), batch["cos"], batch["sin"],
+                                       save=False, kv_sink=sink)
             self.h[gi * G:(gi + 1) * G].copy_(h[P - 1].float()[None, :].expand(G, -1))
             plen[gi * G:(gi + 1) * G] = P
             # rope delta (max position + 1 - P): generated token k sits at position P + k + delta on all three axes

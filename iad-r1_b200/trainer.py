@@ -285,10 +285,15 @@ class SCGRPOTrainer:
         T = P + C
         comp_long = completion_ids.long()
         mask = grpo_loss.completion_mask(comp_long, self.processing_class.eos_token_id)          # :722-726
-        ids = torch.cat([torch.from_numpy(prompt_ids).to(dev)[None, :].expand(G, -1), comp_long], 1)  # :681-683
-        batch = self.model.prepare_batch(ids, enc["pixel_values"], enc["grid_thw"], prompt_len=P)
-        rows = (torch.arange(G, device=dev)[:, None] * T + (P - 1) + torch.arange(C, device=dev)[None, :]).reshape(-1).to(torch.int32)
-        labels = completion_ids.reshape(-1).to(torch.int32).contiguous()
+        if a.shared_prefix:
+            # one prompt + G completions in the shared-prefix layout: the prompt's hidden states are computed once
+            batch = self.model.prepare_group(prompt_ids, completion_ids, enc["pixel_values"], enc["grid_thw"])
+            rows, labels = batch["sel_index"], batch["labels"]
+        else:
+            ids = torch.cat([torch.from_numpy(prompt_ids).to(dev)[None, :].expand(G, -1), comp_long], 1)  # :681-683
+            batch = self.model.prepare_batch(ids, enc["pixel_values"], enc["grid_thw"], prompt_len=P)
+            rows = (torch.arange(G, device=dev)[:, None] * T + (P - 1) + torch.arange(C, device=dev)[None, :]).reshape(-1).to(torch.int32)
+            labels = completion_ids.reshape(-1).to(torch.int32).contiguous()
         temp = a.temperature if a.loss_mode == "clip" else 1.0   # Q1: SC mode does not temperature-scale the logits
         anchor = torch.zeros((), device=dev, requires_grad=True)
         with self._phase("policy_fwd"):

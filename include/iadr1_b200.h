@@ -90,10 +90,11 @@ int iadr1_act_mul_bwd(const void* dout, const void* gu, void* dgu, long long row
                       long long up_off, long long dout_ld, int act, void* stream);
 /* In-place masked softmax over bf16 scores S[z][q][k]; row q keeps keys [lo[q], hi[q]) (causal / window / padding
  * masks as ranges), exact zeros elsewhere. eager_attention_forward, modeling_qwen2_5_vl.py:182-206.                 */
+/* Keys in [hole_lo, hole_hi) are always masked (padding between the shared-prefix and per-row key segments).          */
 int iadr1_softmax_rows(void* S, const int* lo, const int* hi, int Tq, int Tk, long long ld, long long z_stride,
-                       long long batch, void* stream);
+                       long long batch, int hole_lo, int hole_hi, void* stream);
 int iadr1_softmax_bwd_rows(const void* P, void* dP, const int* lo, const int* hi, int Tq, int Tk, long long ld,
-                           long long z_stride, long long batch, void* stream);
+                           long long z_stride, long long batch, int hole_lo, int hole_hi, void* stream);
 /* out[r] = index[r] >= 0 ? table[index[r]] : alt[-1 - index[r]]: embed_tokens + masked_scatter of image embeddings
  * (:1298-1307) in one pass; with alt = NULL a plain row gather (vision window reorder :478-484, :512-513).          */
 int iadr1_gather_rows(const void* table, const void* alt, const int* index, void* out, long long rows, int cols,
@@ -104,7 +105,7 @@ int iadr1_scatter_add_rows(const void* d, const int* index, float* dtable, float
 int iadr1_colsum(const void* x, float* out, long long rows, int cols, long long ld, void* stream);
 /* Sum the g query-head gradients of each kv head (autograd of repeat_kv, modeling_qwen2_5_vl.py:170-179).          */
 int iadr1_group_sum(const void* src, void* out, long long rows, int nkv, int g, int hd, long long src_ld,
-                    long long out_ld, void* stream);
+                    long long out_ld, int accumulate, void* stream);
 int iadr1_add_bf16(const void* a, const void* b, void* out, long long n, void* stream);
 int iadr1_cast_f32_bf16(const float* src, void* dst, long long n, void* stream);
 /* Finishes the fused lm_head -> log-softmax -> gather (replaces sc_grpo_trainer.py:505-514 / trl selective_log_softmax,

@@ -84,6 +84,39 @@ def test_logprobs_and_grads_match_hf(cuda, family):
     print(f"[{family}] worst gradient rel err {worst[0]:.4f} at {worst[1]} over {len(fix['grads'])} tensors")
 
 
+@pytest.mark.parametrize("family", ["qwen2_5_vl", "qwen2_vl"])
+def test_shared_prefix_layout_matches_hf(cuda, family):
+    """The production layout [prompt | G completions] (prompt computed once, ops.SharedPrefixAttention) against the same
+    HF oracle fixture, which runs the reference's full [G, P + C] batch: same log-probs, same gradients."""
+    fix = _load(family)
+    cfg, ps, vlm = _build(fix, cuda)
+    P, G, C = fix["P"], fix["G"], fix["C"]
+    batch = vlm.prepare_group(fix["input_ids"][0, :P].numpy(), fix["input_ids"][:, P:], fix["pixel_values"], [fix["grid"]])
+    assert batch["N"] == P + G * C
+    logp, ctx = vlm.logprobs_forward(batch, batch["sel_index"], batch["labels"])
+    logp = logp.view(G, C).cpu()
+    mask = fix["completion_mask"].bool()
+    err = (logp - fix["logp_fp32"]).abs()[mask].max().item()
+    ref_err = (fix["logp_bf16_ref"] - fix["logp_fp32"]).abs()[mask].max().item()
+    print(f"\n[{family}] shared-prefix logp max err vs fp32 oracle: {err:.5f} (HF bf16 err {ref_err:.5f})")
+    assert err <= max(2 * ref_err, 0.02)
+    vlm.logprobs_backward(fix["dlogp"].reshape(-1).to(cuda), ctx)
+    torch.cuda.synchronize()
+    ours = {ps.canonical_name(k): v for k, v in ps.hf_named_tensors("g")}
+    worst = (0.0, None)
+    for name, gref in fix["grads"].items():
+        name = ps.canonical_name(name)
+        if name == "lm_head.weight":
+            continue
+        g = ours[name].float().cpu().reshape(gref.shape)
+        gref = gref.float()
+        rel = ((g - gref).norm() / (gref.norm() + 1e-12)).item()
+        cosv = torch.nn.functional.cosine_similarity(g.flatten(), gref.flatten(), dim=0).item()
+        worst = max(worst, (rel, name))
+        assert rel <= 0.06 and cosv >= 0.998, f"{name}: rel err {rel:.4f}, cos {cosv:.5f}"
+    print(f"[{family}] shared-prefix worst gradient rel err {worst[0]:.4f} at {worst[1]}")
+
+
 def test_hf_state_dict_roundtrip(cuda):
     fix = _load("qwen2_5_vl")
     cfg, ps, vlm = _build(fix, cuda)
