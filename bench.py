@@ -38,7 +38,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="qwen2.5-vl-3b")
-    ap.add_argument("--ga", type=int, default=2, help="gradient_accumulation_steps (reference scripts: 2)")
+    ap.add_argument("--ga", type=int, default=8,
+                    help="gradient_accumulation_steps = groups rolled out together per rank (reference scripts use 2)")
     ap.add_argument("--completion-len", type=int, default=512)
     ap.add_argument("--image-size", type=int, default=448)
     ap.add_argument("--num-generations", type=int, default=8)
@@ -232,8 +233,9 @@ def run_ours(args):
     clk = clocks.stop()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     tms, tfl, tmax, nl = C.c_double(), C.c_double(), C.c_double(), C.c_longlong()
-    L.lib().iadr1_gemm_profile_collect.argtypes = [C.POINTER(C.c_double)] * 3 + [C.POINTER(C.c_longlong)]
-    L.check(L.lib().iadr1_gemm_profile_collect(C.byref(tms), C.byref(tfl), C.byref(tmax), C.byref(nl)))
+    L.lib().iadr1_gemm_profile_collect.argtypes = [C.POINTER(C.c_double)] * 3 + [C.POINTER(C.c_longlong), C.c_char_p]
+    shape_csv = os.environ.get("IADR1_GEMM_SHAPES_CSV", "") if rank == 0 else ""
+    L.check(L.lib().iadr1_gemm_profile_collect(C.byref(tms), C.byref(tfl), C.byref(tmax), C.byref(nl), shape_csv.encode()))
     L.check(L.lib().iadr1_gemm_profile_enable(0))
     eng = trainer._engine
     launches = L.launch_count() + (eng.replays - replay0) * eng.kernels_per_step

@@ -38,8 +38,9 @@ int iadr1_gemm_profile_enable(int on) {
   iadr1::gemm_profile_enable(on);
   return 0;
 }
-int iadr1_gemm_profile_collect(double* total_ms, double* total_flops, double* max_launch_ms, long long* launches) {
-  const long long n = iadr1::gemm_profile_collect(total_ms, total_flops, max_launch_ms);
+int iadr1_gemm_profile_collect(double* total_ms, double* total_flops, double* max_launch_ms, long long* launches,
+                               const char* csv_path) {
+  const long long n = iadr1::gemm_profile_collect(total_ms, total_flops, max_launch_ms, csv_path);
   if (launches) *launches = n;
   return 0;
 }

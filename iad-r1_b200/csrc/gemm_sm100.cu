@@ -19,6 +19,8 @@
 
 #include <map>
 #include <vector>
+#include <array>
+#include <string>
 #include <mutex>
 #include <tuple>
 #include <cstring>
@@ -508,6 +510,7 @@ struct GemmProf {
   std::vector<cudaEvent_t> pool;
   size_t used = 0;
   std::vector<double> flops;
+  std::vector<std::array<int, 8>> shapes;  // M, N, K, batch, a_mn, b_mn, epi, block_n
   std::mutex mu;
 };
 static GemmProf g_prof;
@@ -533,19 +536,37 @@ void gemm_profile_enable(int on) {
   g_prof.enabled = on != 0;
   g_prof.used = 0;
   g_prof.flops.clear();
+  g_prof.shapes.clear();
 }
 
 // Caller must have synchronised the device. Returns the number of timed launches.
-long long gemm_profile_collect(double* total_ms, double* total_flops, double* max_launch_ms) {
+long long gemm_profile_collect(double* total_ms, double* total_flops, double* max_launch_ms, const char* csv_path) {
   std::lock_guard<std::mutex> lk(g_prof.mu);
   double ms = 0, fl = 0, mx = 0;
   const size_t n = g_prof.used / 2;
+  std::map<std::array<int, 8>, std::array<double, 3>> by_shape;  // launches, ms, flops
   for (size_t i = 0; i < n; ++i) {
     float t = 0.f;
     if (cudaEventElapsedTime(&t, g_prof.pool[2 * i], g_prof.pool[2 * i + 1]) == cudaSuccess) {
       ms += t;
       if (t > mx) mx = t;
       fl += g_prof.flops[i];
+      auto& e = by_shape[g_prof.shapes[i]];
+      e[0] += 1;
+      e[1] += t;
+      e[2] += g_prof.flops[i];
+    }
+  }
+  if (csv_path && csv_path[0]) {
+    if (FILE* f = fopen(csv_path, "w")) {
+      fprintf(f, "M,N,K,batch,a_mn,b_mn,epi,block_n,launches,total_ms,avg_us,tflops\n");
+      for (auto& kv : by_shape) {
+        const auto& k = kv.first;
+        const auto& v = kv.second;
+        fprintf(f, "%d,%d,%d,%d,%d,%d,%d,%d,%.0f,%.3f,%.2f,%.1f\n", k[0], k[1], k[2], k[3], k[4], k[5], k[6], k[7], v[0], v[1],
+                v[1] / v[0] * 1e3, v[1] > 0 ? v[2] / (v[1] * 1e-3) / 1e12 : 0.0);
+      }
+      fclose(f);
     }
   }
   if (total_ms) *total_ms = ms;
@@ -553,6 +574,7 @@ long long gemm_profile_collect(double* total_ms, double* total_flops, double* ma
   if (max_launch_ms) *max_launch_ms = mx;
   g_prof.used = 0;
   g_prof.flops.clear();
+  g_prof.shapes.clear();
   return (long long)n;
 }
 
@@ -643,6 +665,7 @@ int launch_gemm(const iadr1_gemm_t& d, cudaStream_t stream) {
     if (g.kmode != 0 || g.skip_mode != 0) fl *= 0.5;
     std::lock_guard<std::mutex> lk(g_prof.mu);
     g_prof.flops.push_back(fl);
+    g_prof.shapes.push_back({g.M, g.N, g.K, g.batch, g.a_mn, g.b_mn, g.epi, g.block_n});
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("gemm launch failed: %s", cudaGetErrorString(e));

@@ -10,7 +10,7 @@ void count_launch(int n = 1);
 int launch_gemm(const iadr1_gemm_t& d, cudaStream_t stream);
 int pick_block_n_public(int N, int b_mn);
 void gemm_profile_enable(int on);
-long long gemm_profile_collect(double* total_ms, double* total_flops, double* max_launch_ms);
+long long gemm_profile_collect(double* total_ms, double* total_flops, double* max_launch_ms, const char* csv_path);
 }  // namespace iadr1
 
 namespace iadr1 {

@@ -72,7 +72,9 @@ def header_prototypes(path: str = HEADER) -> dict:
         if args and args != "void":
             for a in args.split(","):
                 a = " ".join(a.split())
-                if "*" in a:
+                if "char*" in a.replace(" *", "*"):
+                    types.append(C.c_char_p)
+                elif "*" in a:
                     types.append(C.c_void_p)
                 else:
                     base = " ".join(a.replace("const ", "").split()[:-1])

@@ -62,7 +62,8 @@ int iadr1_set_pdl(int on);
 /* Live roofline support: time every (non-graph-captured) GEMM launch with CUDA events on its own stream and count its
  * algorithmic FLOPs. Collect after a device synchronise.                                                            */
 int iadr1_gemm_profile_enable(int on);
-int iadr1_gemm_profile_collect(double* total_ms, double* total_flops, double* max_launch_ms, long long* launches);
+int iadr1_gemm_profile_collect(double* total_ms, double* total_flops, double* max_launch_ms, long long* launches,
+                               const char* csv_path /* optional: per-shape breakdown */);
 
 /* ---- row kernels (HBM-bound; bf16 activations, fp32 statistics) ------------------------------------------------
  * RMSNorm: HF Qwen2_5_VLRMSNorm.forward, modeling_qwen2_5_vl.py:57-71 (decoder :775-776,:849; vision blocks; merger ln_q).
