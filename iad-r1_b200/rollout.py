@@ -148,31 +148,44 @@ class RolloutEngine:
         self.out_tokens.fill_(self.cfg.pad_token_id)
         plen = np.zeros(self.R, dtype=np.int32)
         delta = np.zeros(self.R, dtype=np.int32)
-        # ---- prefill: one sequence per group through the training forward kernels; K/V land in the shared prefix cache
-        for gi, pr in enumerate(prompts):
-            ids = np.asarray(pr["input_ids"], dtype=np.int64).reshape(1, -1)
-            P = ids.shape[1]
-            if P > self.p_max:
-                raise ValueError(f"prompt of {P} tokens exceeds p_max={self.p_max}")
-            batch = vlm.prepare_batch(ids, pr.get("pixel_values"), pr.get("grid_thw"))
-            img = None
-            if batch["n_img_tokens"] > 0:
-                img, _ = vlm.vision_forward(batch["pixel_values"], batch["grid"], save=False)
-            nq, nkv, hd = t.num_heads, t.num_kv_heads, t.head_dim
+        # ---- prefill: ALL prompts in one right-padded [n, Pmax] pass through the training forward kernels (one vision
+        # tower call over every image, decoder GEMMs at M = n * Pmax); each layer's post-rotary K/V land in the shared
+        # prefix cache. Padding sits after the real tokens, so causal attention never lets it influence them.
+        from .geometry import mrope_position_ids
+        id_list = [np.asarray(pr["input_ids"], dtype=np.int64).reshape(-1) for pr in prompts]
+        lens = [len(x) for x in id_list]
+        Pmax = max(lens)
+        if Pmax > self.p_max:
+            raise ValueError(f"prompt of {Pmax} tokens exceeds p_max={self.p_max}")
+        ids = np.full((n, Pmax), self.cfg.pad_token_id, dtype=np.int64)
+        am = np.zeros((n, Pmax), dtype=np.int64)
+        for i, x in enumerate(id_list):
+            ids[i, :lens[i]], am[i, :lens[i]] = x, 1
+        pvs = [pr.get("pixel_values") for pr in prompts if pr.get("pixel_values") is not None]
+        grids = [g_ for pr in prompts if pr.get("grid_thw") is not None
+                 for g_ in (pr["grid_thw"].tolist() if torch.is_tensor(pr["grid_thw"]) else pr["grid_thw"])]
+        pv = torch.cat([x.to(vlm.device) for x in pvs], 0) if pvs else None
+        pos, _ = mrope_position_ids(ids, grids, self.cfg, am)
+        batch = vlm.prepare_batch(ids, pv, grids if grids else None, position_ids=torch.from_numpy(pos), attention_mask=am)
+        img = None
+        if batch["n_img_tokens"] > 0:
+            img, _ = vlm.vision_forward(batch["pixel_values"], batch["grid"], save=False)
+        nq, nkv, hd = t.num_heads, t.num_kv_heads, t.head_dim
 
-            def sink(layer, qkv, gi=gi, P=P):
-                kv = qkv.view(P, nq + 2 * nkv, hd)
-                self.kp[layer, gi, :P].copy_(kv[:, nq:nq + nkv])
-                self.vp[layer, gi, :P].copy_(kv[:, nq + nkv:])
+        def sink(layer, qkv):
+            kv = qkv.view(n, Pmax, nq + 2 * nkv, hd)
+            self.kp[layer, :n, :Pmax].copy_(kv[:, :, nq:nq + nkv])
+            self.vp[layer, :n, :Pmax].copy_(kv[:, :, nq + nkv:])
 
-            h, _ = vlm.decoder_forward(batch["src_index"], img, vlm.full_attention(1, P), batch["cos"], batch["sin"],
-                                       save=False, kv_sink=sink)
-            self.h[gi * G:(gi + 1) * G].copy_(h[P - 1].float()[None, :].expand(G, -1))
+        h, _ = vlm.decoder_forward(batch["src_index"], img, vlm.full_attention(n, Pmax), batch["cos"], batch["sin"],
+                                   save=False, kv_sink=sink)
+        h = h.view(n, Pmax, -1)
+        for gi in range(n):
+            P = lens[gi]
+            self.h[gi * G:(gi + 1) * G].copy_(h[gi, P - 1].float()[None, :].expand(G, -1))
             plen[gi * G:(gi + 1) * G] = P
-            # rope delta (max position + 1 - P): generated token k sits at position P + k + delta on all three axes
-            from .geometry import mrope_position_ids
-            _, d = mrope_position_ids(ids, batch["grid"], self.cfg)
-            delta[gi * G:(gi + 1) * G] = int(d[0])
+            # generated token k of this row sits at position P + k + delta on all three axes
+            delta[gi * G:(gi + 1) * G] = int(pos[:, gi, :P].max()) + 1 - P
         for gi in range(n, self.n_groups):  # unused groups: mark rows finished so they only emit pad
             self.finished[gi * G:(gi + 1) * G] = 1
             plen[gi * G:(gi + 1) * G] = 1

@@ -192,3 +192,33 @@ def test_data_parallel_plumbing_gloo_world2(tmp_path):
                         "127.0.0.1", "--master-port", "29517", str(script)], capture_output=True, text=True, env=env, timeout=180)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_sft_example_encoding_labels_assistant_only():
+    """ref: llamafactory/data/processors/supervised.py:34-88 - labels are IGNORE_INDEX everywhere but assistant turns."""
+    from iad_r1_b200.config import tiny_config
+    from iad_r1_b200.sft_trainer import IGNORE_INDEX, SFTArguments, encode_supervised_example
+    from iad_r1_b200.synthetic import SyntheticProcessor, synthetic_image
+    cfg = tiny_config()
+    proc = SyntheticProcessor(cfg)
+    ex = {"messages": [{"role": "user", "content": "<image>Is there a defect?"}, {"role": "assistant", "content": "yes a scratch"}],
+          "images": [synthetic_image(0, 112)]}
+    enc = encode_supervised_example(ex, proc, 512, None, 512 * 512)
+    ids, lab = enc["input_ids"], enc["labels"]
+    assert (ids == cfg.image_token_id).sum() == 16 and enc["pixel_values"].shape[0] == 64
+    sup = lab != IGNORE_INDEX
+    assert sup.sum() >= 3 and (lab[sup] == ids[sup]).all()
+    first = int(np.argmax(sup))
+    assert not sup[:first].any() and (ids[:first] == cfg.image_token_id).sum() == 16   # prompt + image unlabelled
+    assert ids[sup][-2] == cfg.eos_token_id or cfg.eos_token_id in ids[sup]              # end-of-turn is supervised
+    with pytest.raises(ValueError):
+        SFTArguments(stage="dpo")
+    from transformers import HfArgumentParser
+    with pytest.raises(ValueError):
+        HfArgumentParser(SFTArguments).parse_args_into_dataclasses(args=["--not_a_flag", "1"])
+    argv = ("--deepspeed z.json --stage sft --do_train --model_name_or_path /m --dataset D --image_dir /i --template qwen2_vl "
+            "--finetuning_type full --output_dir /o --overwrite_cache --overwrite_output_dir --warmup_steps 100 --weight_decay 0.1 "
+            "--per_device_train_batch_size 1 --gradient_accumulation_steps 2 --ddp_timeout 90000 --learning_rate 1e-5 "
+            "--lr_scheduler_type cosine --logging_steps 5 --cutoff_len 4096 --save_steps 365 --plot_loss --num_train_epochs 1 --bf16").split()
+    (a,) = HfArgumentParser(SFTArguments).parse_args_into_dataclasses(args=argv)
+    assert a.cutoff_len == 4096 and a.lr_scheduler_type == "cosine" and a.bf16 and a.plot_loss

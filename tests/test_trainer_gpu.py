@@ -112,3 +112,28 @@ def test_all_masked_gradient_is_zero(cuda):
     tr.train()
     assert torch.equal(before, tr.params.flat)
     assert tr.ref_model is None
+
+
+def test_sft_trainer_reduces_loss(cuda, tmp_path):
+    """PA-SFT step: teacher-forced CE on assistant tokens through the same kernels; a few steps on two
+    fixed examples must lower the loss, frozen-tower quirk Q17 holds for the qwen2_vl family only."""
+    from iad_r1_b200.config import tiny_config
+    from iad_r1_b200.sft_trainer import PASFTTrainer, SFTArguments
+    from iad_r1_b200.synthetic import SyntheticProcessor, synthetic_image
+    for family, frozen in (("qwen2_5_vl", False), ("qwen2_vl", True)):
+        cfg = tiny_config(family)
+        data = [{"messages": [{"role": "user", "content": "<image>Is there a defect in the image?"},
+                              {"role": "assistant", "content": "<think> the surface is scratch </think> <answer> yes </answer>"}],
+                 "images": [synthetic_image(i, 112)]} for i in range(2)]
+        args = SFTArguments(output_dir=str(tmp_path / family), do_train=True, learning_rate=2e-3, lr_scheduler_type="cosine",
+                            warmup_steps=1, weight_decay=0.1, gradient_accumulation_steps=2, logging_steps=1, max_steps=6,
+                            save_strategy="no", cutoff_len=512, bf16=True)
+        tr = PASFTTrainer(cfg, args, train_dataset=data, processing_class=SyntheticProcessor(cfg))
+        vis_before = tr.params.p["visual.blocks.0.qkv.weight"].clone()
+        txt_before = tr.params.p["layers.0.qkv.weight"].clone()
+        tr.train()
+        losses = [l["loss"] for l in tr.state.log_history if "loss" in l]
+        assert len(losses) == 6 and losses[-1] < losses[0] - 0.2, losses
+        assert tr.freeze_vision == frozen
+        assert torch.equal(vis_before, tr.params.p["visual.blocks.0.qkv.weight"]) == frozen
+        assert not torch.equal(txt_before, tr.params.p["layers.0.qkv.weight"])
