@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--model", default="qwen2.5-vl-3b")
     ap.add_argument("--ga", type=int, default=8,
                     help="gradient_accumulation_steps = groups rolled out together per rank (reference scripts use 2)")
+    ap.add_argument("--groups-per-pass", type=int, default=2,
+                    help="per_device_train_batch_size: groups packed into one forward/backward pass")
     ap.add_argument("--completion-len", type=int, default=512)
     ap.add_argument("--image-size", type=int, default=448)
     ap.add_argument("--num-generations", type=int, default=8)
@@ -154,7 +156,8 @@ def run_reference(args):
 
 def workload_config(args, cfg, world):
     return {"workload": f"{args.model} SC-GRPO G={args.num_generations}, one {args.image_size}x{args.image_size} synthetic "
-                        f"image per prompt, C={args.completion_len} (fixed length), per_device_batch=1, grad_accum={args.ga}, "
+                        f"image per prompt, C={args.completion_len} (fixed length), {args.ga} groups per optimizer step per GPU "
+                        f"(per_device_batch={min(args.groups_per_pass, args.ga)} x grad_accum={args.ga // max(1, min(args.groups_per_pass, args.ga))}), "
                         f"beta=0.04 (reference model on), random-init weights",
             "groups_per_step": world * args.ga, "parallelism": f"dp{world}",
             "l2": "working set (7.5 GB bf16 weights + activations) >> 126 MB L2; no explicit flush needed"}
@@ -174,7 +177,10 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     cfg = PRESETS[args.model]()
     G, GA, Cl = args.num_generations, args.ga, args.completion_len
-    targs = GRPOConfig(output_dir="/tmp/iadr1_bench", per_device_train_batch_size=1, gradient_accumulation_steps=GA,
+    bs = max(1, min(args.groups_per_pass, GA))
+    if GA % bs:
+        raise SystemExit("--ga must be a multiple of --groups-per-pass")
+    targs = GRPOConfig(output_dir="/tmp/iadr1_bench", per_device_train_batch_size=bs, gradient_accumulation_steps=GA // bs,
                        num_generations=G, max_prompt_length=4096, max_completion_length=Cl, bf16=True, beta=0.04,
                        logging_steps=0, save_strategy="no", rollout_forbid_eos=True, temperature=0.9, seed=42)
     proc = SyntheticProcessor(cfg, max_pixels=480000)
@@ -208,8 +214,8 @@ def run_ours(args):
         comps = trainer._rollout([e for _, e in win])
         for (ex, e), c in zip(win, comps):
             trainer._rollout_cache[id(ex)] = (e, c)
-        for ex, _ in win:
-            trainer.training_step([ex])
+        for j in range(0, GA, bs):
+            trainer.training_step([ex for ex, _ in win[j:j + bs]])
         trainer.optimizer_step()
 
     for i in range(args.warmup):
@@ -254,8 +260,8 @@ def run_ours(args):
         def step_e2e(i):
             win = host[i * GA:(i + 1) * GA]
             trainer.prepare_window(win)            # PIL -> HF image processor -> pinned host -> H2D -> rollout
-            for ex in win:
-                trainer.training_step([ex])        # completions D2H for the Python reward callbacks
+            for j in range(0, GA, bs):
+                trainer.training_step(win[j:j + bs])   # completions D2H for the Python reward callbacks
             trainer.optimizer_step()
 
         step_e2e(0)  # warm the host path once (PIL / processor caches)

@@ -273,6 +273,33 @@ class VLM:
                     sel_index=torch.from_numpy(rows.reshape(-1)).to(self.device),
                     labels=torch.from_numpy(comp.reshape(-1).astype(np.int32)).to(self.device))
 
+    def prepare_groups(self, groups: list):
+        """Pack several shared-prefix groups (each a dict prompt_ids / completion_ids / pixel_values / grid_thw) into one
+        token stream. Returns the merged batch; `group_slices` gives each group's range in the flattened log-probs."""
+        parts = [self.prepare_group(g_["prompt_ids"], g_["completion_ids"], g_["pixel_values"], g_["grid_thw"]) for g_ in groups]
+        if len(parts) == 1:
+            parts[0]["group_slices"] = [(0, parts[0]["G"] * parts[0]["C"])]
+            return parts[0]
+        tok_off, img_off, lp_off = 0, 0, 0
+        src, sel, slices = [], [], []
+        for b in parts:
+            s_ = b["src_index"].clone()
+            neg = s_ < 0
+            s_[neg] -= img_off          # -1 - (row + img_off)
+            src.append(s_)
+            sel.append(b["sel_index"] + tok_off)
+            n_lp = b["G"] * b["C"]
+            slices.append((lp_off, lp_off + n_lp))
+            tok_off += b["N"]
+            img_off += b["n_img_tokens"]
+            lp_off += n_lp
+        pvs = [b["pixel_values"] for b in parts if b["pixel_values"] is not None]
+        return dict(shared=True, N=tok_off, attn=ops.MultiGroupAttention([b["attn"] for b in parts]),
+                    grid=[g_ for b in parts for g_ in b["grid"]], cos=torch.cat([b["cos"] for b in parts]),
+                    sin=torch.cat([b["sin"] for b in parts]), src_index=torch.cat(src), n_img_tokens=img_off,
+                    pixel_values=torch.cat([x.to(self.device) for x in pvs]) if pvs else None,
+                    sel_index=torch.cat(sel), labels=torch.cat([b["labels"] for b in parts]), group_slices=slices)
+
     def logprobs_forward(self, batch: dict, sel_index: torch.Tensor, labels: torch.Tensor, temperature: float = 1.0,
                          save: bool = True):
         """log p(labels[j] | prefix) at hidden-state rows sel_index[j] (flattened b*T + t). Returns (logp fp32, ctx)."""

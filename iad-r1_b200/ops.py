@@ -271,10 +271,10 @@ class SharedPrefixAttention:
         self.c_lo = torch.zeros(G * C, dtype=torch.int32, device=device)
         self.c_hi = (self.Pp + (torch.arange(G * C, device=device) % C) + 1).to(torch.int32)
 
-    def forward(self, qkv):
+    def forward(self, qkv, out=None):
         P, G, C, nq, nkv, hd, g, D, Pp, Tk = self.P, self.G, self.C, self.nq, self.nkv, self.hd, self.g, self.D, self.Pp, self.Tk
         GC = G * C
-        attn = torch.empty(self.n_tokens, nq * hd, dtype=bf16, device=qkv.device)
+        attn = torch.empty(self.n_tokens, nq * hd, dtype=bf16, device=qkv.device) if out is None else out
         _, Pm = attention_fwd(qkv[:P], self.prefix, self.p_lo, self.p_hi, out=attn[:P])
         S = torch.empty(nq, GC, Tk, dtype=bf16, device=qkv.device)
         k_off, v_off = nq * hd, (nq + nkv) * hd
@@ -292,12 +292,12 @@ class SharedPrefixAttention:
                        ldc=nq * hd, c_bs_lo=hd, c_bs_hi=C * nq * hd, kmode=1, residual=out)
         return attn, (Pm, S)
 
-    def backward(self, dattn, qkv, saved):
+    def backward(self, dattn, qkv, saved, out=None):
         P, G, C, nq, nkv, hd, g, D, Pp, Tk = self.P, self.G, self.C, self.nq, self.nkv, self.hd, self.g, self.D, self.Pp, self.Tk
         GC, QH = G * C, nq * hd
         Pm, S = saved
         dev = qkv.device
-        dqkv = torch.empty(self.n_tokens, D, dtype=bf16, device=dev)
+        dqkv = torch.empty(self.n_tokens, D, dtype=bf16, device=dev) if out is None else out
         attention_bwd(dattn[:P], qkv[:P], Pm, self.prefix, self.p_lo, self.p_hi, dqkv=dqkv[:P])
         k_off, v_off = nq * hd, (nq + nkv) * hd
         dP = torch.empty_like(S)
@@ -332,6 +332,34 @@ class SharedPrefixAttention:
                        ldc=QH, c_bs_lo=hd, c_bs_hi=C * QH, kmode=2)
         group_sum(tc[0], dqkv[P:, k_off:], GC, nkv, g, hd, QH, D)
         group_sum(tc[1], dqkv[P:, v_off:], GC, nkv, g, hd, QH, D)
+        return dqkv
+
+
+class MultiGroupAttention:
+    """Several independent groups packed back to back in one token stream ([group 0 layout | group 1 layout | ...]):
+    every row-wise kernel and dense product then runs once over all of them (bigger M, one weight-gradient
+    read-modify-write per pass instead of one per group), attention runs group by group on slices."""
+
+    def __init__(self, groups):
+        self.groups = groups
+        self.offsets = [0]
+        for g_ in groups:
+            self.offsets.append(self.offsets[-1] + g_.n_tokens)
+        self.n_tokens = self.offsets[-1]
+
+    def forward(self, qkv):
+        t0 = self.groups[0]
+        out = torch.empty(self.n_tokens, t0.nq * t0.hd, dtype=bf16, device=qkv.device)
+        saved = []
+        for g_, a, b in zip(self.groups, self.offsets[:-1], self.offsets[1:]):
+            _, s_ = g_.forward(qkv[a:b], out=out[a:b])
+            saved.append(s_)
+        return out, saved
+
+    def backward(self, dattn, qkv, saved):
+        dqkv = torch.empty(self.n_tokens, self.groups[0].D, dtype=bf16, device=qkv.device)
+        for g_, s_, a, b in zip(self.groups, saved, self.offsets[:-1], self.offsets[1:]):
+            g_.backward(dattn[a:b], qkv[a:b], s_, out=dqkv[a:b])
         return dqkv
 
 

@@ -220,46 +220,56 @@ class SCGRPOTrainer(TrainerCore):
     # the hot path: one micro-step (ref: sc_grpo_trainer.py:586-819)
     # ---------------------------------------------------------------------------------------------------------------
     def compute_loss(self, model=None, inputs=None, return_outputs=False, num_items_in_batch=None):
+        """`inputs`: the micro-batch, a list of `per_device_train_batch_size` examples (the reference uses 1). Each example
+        is its own GRPO group (advantages are normalised inside the group); with the shared-prefix layout all groups of
+        the micro-batch are packed into ONE forward/backward pass. Returns the mean of the group losses."""
         if return_outputs:
             raise ValueError("The GRPOTrainer does not support returning outputs")
-        losses = []
+        G, dev, a = self.num_generations, self.device, self.args
+        items = []
         for example in inputs:
-            losses.append(self._group_loss(example))
+            cached = self._rollout_cache.pop(id(example), None)
+            if cached is None:
+                enc = self._encode_prompt(example)
+                completion_ids = self._rollout([enc])[0]
+            else:
+                enc, completion_ids = cached
+            items.append((example, enc, completion_ids))
+        temp = a.temperature if a.loss_mode == "clip" else 1.0   # Q1: SC mode does not temperature-scale the logits
+        if a.shared_prefix:
+            batch = self.model.prepare_groups([dict(prompt_ids=enc["input_ids"], completion_ids=c, pixel_values=enc["pixel_values"],
+                                                    grid_thw=enc["grid_thw"]) for _, enc, c in items])
+            rows, labels, slices = batch["sel_index"], batch["labels"], batch["group_slices"]
+            logps_all, ref_all = self._score(batch, rows, labels, temp)
+            per_group = [(logps_all[lo:hi], None if ref_all is None else ref_all[lo:hi]) for lo, hi in slices]
+        else:
+            per_group = []
+            for _, enc, c in items:          # reference layout: the full [G, P + C] batch, one group per pass
+                P, C = len(enc["input_ids"]), c.shape[1]
+                T = P + C
+                ids = torch.cat([torch.from_numpy(enc["input_ids"]).to(dev)[None, :].expand(G, -1), c.long()], 1)  # :681-683
+                batch = self.model.prepare_batch(ids, enc["pixel_values"], enc["grid_thw"], prompt_len=P)
+                rows = (torch.arange(G, device=dev)[:, None] * T + (P - 1) + torch.arange(C, device=dev)[None, :]).reshape(-1).to(torch.int32)
+                per_group.append(self._score(batch, rows, c.reshape(-1).to(torch.int32).contiguous(), temp))
+        losses = [self._group_loss(ex, c, lp.view(G, -1), None if rf is None else rf.view(G, -1))
+                  for (ex, _, c), (lp, rf) in zip(items, per_group)]
         return torch.stack(losses).mean()
 
-    def _group_loss(self, example: dict) -> torch.Tensor:
-        G, dev, a = self.num_generations, self.device, self.args
-        cached = self._rollout_cache.pop(id(example), None)
-        if cached is None:
-            enc = self._encode_prompt(example)
-            completion_ids = self._rollout([enc])[0]
-        else:
-            enc, completion_ids = cached
-        prompt_ids = enc["input_ids"]
-        P, C = len(prompt_ids), completion_ids.shape[1]
-        T = P + C
-        comp_long = completion_ids.long()
-        mask = grpo_loss.completion_mask(comp_long, self.processing_class.eos_token_id)          # :722-726
-        if a.shared_prefix:
-            # one prompt + G completions in the shared-prefix layout: the prompt's hidden states are computed once
-            batch = self.model.prepare_group(prompt_ids, completion_ids, enc["pixel_values"], enc["grid_thw"])
-            rows, labels = batch["sel_index"], batch["labels"]
-        else:
-            ids = torch.cat([torch.from_numpy(prompt_ids).to(dev)[None, :].expand(G, -1), comp_long], 1)  # :681-683
-            batch = self.model.prepare_batch(ids, enc["pixel_values"], enc["grid_thw"], prompt_len=P)
-            rows = (torch.arange(G, device=dev)[:, None] * T + (P - 1) + torch.arange(C, device=dev)[None, :]).reshape(-1).to(torch.int32)
-            labels = completion_ids.reshape(-1).to(torch.int32).contiguous()
-        temp = a.temperature if a.loss_mode == "clip" else 1.0   # Q1: SC mode does not temperature-scale the logits
-        anchor = torch.zeros((), device=dev, requires_grad=True)
+    def _score(self, batch, rows, labels, temp):
+        """Policy log-probs (with the CUDA backward attached) and reference log-probs (no grad), :733-743."""
+        anchor = torch.zeros((), device=self.device, requires_grad=True)
         with self._phase("policy_fwd"):
-            logps = _LogProbFn.apply(anchor, self.model, batch, rows, labels, temp).view(G, C)      # :733-735
+            logps = _LogProbFn.apply(anchor, self.model, batch, rows, labels, temp)
+        ref_logps = None
         if self.ref_model is not None:
             with torch.no_grad(), self._phase("ref_fwd"):
-                ref_logps, _ = self.ref_model.logprobs_forward(batch, rows, labels, temp, save=False)  # :737-743
-                ref_logps = ref_logps.view(G, C)
-        else:
-            ref_logps = None
+                ref_logps, _ = self.ref_model.logprobs_forward(batch, rows, labels, temp, save=False)
+        return logps, ref_logps
 
+    def _group_loss(self, example: dict, completion_ids: torch.Tensor, logps: torch.Tensor, ref_logps) -> torch.Tensor:
+        """Mask, rewards, advantages and loss of ONE group from its [G, C] log-probs (ref: :722-726, :746-798)."""
+        G, dev, a = self.num_generations, self.device, self.args
+        mask = grpo_loss.completion_mask(completion_ids.long(), self.processing_class.eos_token_id)          # :722-726
         # ---- rewards on decoded text (CPU Python callbacks, verbatim convention :749-781) ----
         with self._phase("rewards"):
             texts = self.processing_class.batch_decode(completion_ids.cpu(), skip_special_tokens=True)

@@ -137,3 +137,32 @@ def test_sft_trainer_reduces_loss(cuda, tmp_path):
         assert tr.freeze_vision == frozen
         assert torch.equal(vis_before, tr.params.p["visual.blocks.0.qkv.weight"]) == frozen
         assert not torch.equal(txt_before, tr.params.p["layers.0.qkv.weight"])
+
+
+def test_multi_group_pass_equals_single_group_passes(cuda):
+    """Packing two groups into one forward/backward (per_device_train_batch_size=2) gives the same log-probs and the
+    same accumulated gradient as two single-group passes (up to bf16 summation order in the weight-gradient GEMMs)."""
+    from iad_r1_b200.synthetic import synthetic_dataset
+    cfg, tr = _tiny_trainer(cuda)
+    data = synthetic_dataset(2, 112)
+    encs = [tr._encode_prompt(ex) for ex in data]
+    torch.manual_seed(0)
+    comps = [torch.randint(10, 900, (4, 10), device=cuda, dtype=torch.int32) for _ in range(2)]
+    groups = [dict(prompt_ids=e["input_ids"], completion_ids=c, pixel_values=e["pixel_values"], grid_thw=e["grid_thw"])
+              for e, c in zip(encs, comps)]
+    merged = tr.model.prepare_groups(groups)
+    lp_m, ctx_m = tr.model.logprobs_forward(merged, merged["sel_index"], merged["labels"])
+    d = torch.randn_like(lp_m)
+    tr.params.zero_grad()
+    tr.model.logprobs_backward(d, ctx_m)
+    g_merged = tr.params.grad_flat.clone()
+    tr.params.zero_grad()
+    lps = []
+    for g_, (lo, hi) in zip(groups, merged["group_slices"]):
+        b = tr.model.prepare_groups([g_])
+        lp, ctx = tr.model.logprobs_forward(b, b["sel_index"], b["labels"])
+        lps.append(lp)
+        tr.model.logprobs_backward(d[lo:hi].contiguous(), ctx)
+    assert (torch.cat(lps) - lp_m).abs().max().item() < 2e-3
+    rel = ((tr.params.grad_flat - g_merged).norm() / g_merged.norm()).item()
+    assert rel < 2e-2, rel
