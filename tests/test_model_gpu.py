@@ -4,8 +4,8 @@ every parameter) against the HF Transformers oracle frozen in tests/golden/tiny_
 Tolerances (stated, per BASELINE.json north_star): the product computes in bf16 with fp32 accumulation/statistics and
 fp32 log-probs; the oracle is HF in fp32 on the same bf16-valued weights. The reference itself runs HF in bf16
 (`logp_bf16_ref` in the fixture), so the yardstick is the reference's own bf16 error:
-  * log-probs:  max|ours - fp32| <= max(2 x max|HF-bf16 - fp32|, 0.02)
-  * gradients:  ||ours - fp32||_F / ||fp32||_F <= 0.06 per tensor (0.02 typical), cosine >= 0.998
+  * log-probs:  max|ours - fp32| <= 0.01 absolute (measured 2-4e-3; the reference's own bf16 path is off by ~3e-2)
+  * gradients:  ||ours - fp32||_F / ||fp32||_F <= 0.03 per tensor (measured <= 0.013), cosine >= 0.999
 """
 import os
 
@@ -55,7 +55,7 @@ def test_logprobs_and_grads_match_hf(cuda, family):
     err = (logp - fix["logp_fp32"]).abs()[mask].max().item()
     ref_err = (fix["logp_bf16_ref"] - fix["logp_fp32"]).abs()[mask].max().item()
     print(f"\n[{family}] logp max err vs fp32 oracle: {err:.5f} (HF bf16 reference-form err: {ref_err:.5f})")
-    assert err <= max(2 * ref_err, 0.02)
+    assert err <= 0.01 and err < ref_err
 
     # loss in Python on our log-probs == oracle loss (reference lines 746-798)
     from iad_r1_b200 import grpo_loss
@@ -80,7 +80,7 @@ def test_logprobs_and_grads_match_hf(cuda, family):
         cosv = torch.nn.functional.cosine_similarity(g.flatten(), gref.flatten(), dim=0).item()
         if rel > worst[0]:
             worst = (rel, name)
-        assert rel <= 0.06 and cosv >= 0.998, f"{name}: rel err {rel:.4f}, cos {cosv:.5f}"
+        assert rel <= 0.03 and cosv >= 0.999, f"{name}: rel err {rel:.4f}, cos {cosv:.5f}"
     print(f"[{family}] worst gradient rel err {worst[0]:.4f} at {worst[1]} over {len(fix['grads'])} tensors")
 
 
@@ -99,7 +99,7 @@ def test_shared_prefix_layout_matches_hf(cuda, family):
     err = (logp - fix["logp_fp32"]).abs()[mask].max().item()
     ref_err = (fix["logp_bf16_ref"] - fix["logp_fp32"]).abs()[mask].max().item()
     print(f"\n[{family}] shared-prefix logp max err vs fp32 oracle: {err:.5f} (HF bf16 err {ref_err:.5f})")
-    assert err <= max(2 * ref_err, 0.02)
+    assert err <= 0.01 and err < ref_err
     vlm.logprobs_backward(fix["dlogp"].reshape(-1).to(cuda), ctx)
     torch.cuda.synchronize()
     ours = {ps.canonical_name(k): v for k, v in ps.hf_named_tensors("g")}
@@ -113,7 +113,7 @@ def test_shared_prefix_layout_matches_hf(cuda, family):
         rel = ((g - gref).norm() / (gref.norm() + 1e-12)).item()
         cosv = torch.nn.functional.cosine_similarity(g.flatten(), gref.flatten(), dim=0).item()
         worst = max(worst, (rel, name))
-        assert rel <= 0.06 and cosv >= 0.998, f"{name}: rel err {rel:.4f}, cos {cosv:.5f}"
+        assert rel <= 0.03 and cosv >= 0.999, f"{name}: rel err {rel:.4f}, cos {cosv:.5f}"
     print(f"[{family}] shared-prefix worst gradient rel err {worst[0]:.4f} at {worst[1]}")
 
 

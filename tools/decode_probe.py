@@ -68,6 +68,7 @@ R, H, I, nq, nkv, hd = eng.R, t.hidden_size, t.intermediate_size, t.num_heads, t
 eng.state[0] = 300  # mid-rollout context
 b = "layers.0."
 sk_qkv, sk_o, sk_d = _split_for(t.qkv_dim, H), _split_for(H, nq * hd), _split_for(H, I)
+gu32 = torch.zeros(R, 2 * I, dtype=torch.float32, device=dev)
 items = {
     "decode_embed": lambda: lib.iadr1_decode_embed(p["embed_tokens.weight"].data_ptr(), eng.tok.data_ptr(), eng.h.data_ptr(), R, H, L.stream_ptr()),
     "rmsnorm_f32in(+zero)": lambda: lib.iadr1_rmsnorm_f32in(eng.h.data_ptr(), p[b + "ln1.weight"].data_ptr(), eng.xn.data_ptr(), R, H, 1e-6, eng.qkv.data_ptr(), t.qkv_dim, L.stream_ptr()),
@@ -82,6 +83,12 @@ items = {
     f"gemm o split{sk_o}": lambda: eng._skinny(p[b + "o.weight"], eng.attn, eng.h, split_k=sk_o, atomic=True),
     "gemm gate_up": lambda: eng._skinny(p[b + "gate_up.weight"], eng.xn, eng.gu),
     "gemm gate_up 86ctas": lambda: L.gemm(p[b + "gate_up.weight"], eng.xn, out=eng.gu, trans_out=True, block_n=eng.block_n, max_ctas=86),
+    "gemm gate_up split2 f32 atomic": lambda: L.gemm(p[b + "gate_up.weight"], eng.xn, out=gu32, trans_out=True, split_k=2, atomic=True, block_n=eng.block_n, a_static=True),
+    "gemm gate_up split3 f32 atomic": lambda: L.gemm(p[b + "gate_up.weight"], eng.xn, out=gu32, trans_out=True, split_k=3, atomic=True, block_n=eng.block_n, a_static=True),
+    "gemm gate_up f32 no split": lambda: L.gemm(p[b + "gate_up.weight"], eng.xn, out=gu32, trans_out=True, block_n=eng.block_n, a_static=True),
+    "gemm qkv split3": lambda: eng._skinny(p[b + "qkv.weight"], eng.xn, eng.qkv, split_k=3, atomic=True, bias=p[b + "qkv.bias"]),
+    "gemm down split4": lambda: eng._skinny(p[b + "down.weight"], eng.act, eng.h, split_k=4, atomic=True),
+    "gemm down split18": lambda: eng._skinny(p[b + "down.weight"], eng.act, eng.h, split_k=18, atomic=True),
     "act_mul": lambda: ops.act_mul_fwd(eng.gu, I, ops.ACT_SILU, gated=True, out=eng.act),
     f"gemm down split{sk_d}": lambda: eng._skinny(p[b + "down.weight"], eng.act, eng.h, split_k=sk_d, atomic=True),
     "gemm lm_head": lambda: eng._skinny(vlm.params.lm_head, eng.xn, eng.logits),
