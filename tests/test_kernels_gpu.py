@@ -355,3 +355,62 @@ def test_sampler_support_and_distribution(ops):
                                      fin.data_ptr(), out.data_ptr(), c_max, V + 5, 0, 0, 1, L.stream_ptr()))
     assert torch.equal(t1, t2)
     assert len(set(t1.tolist())) > 1, "rows must draw independently"
+
+
+# ---------------------------------------------------------------------------------------------- decode attention
+def _rot_half_f(x):
+    h = x.shape[-1] // 2
+    return torch.cat((-x[..., h:], x[..., :h]), -1)
+
+
+@pytest.mark.parametrize("nq,nkv,hd", [(8, 1, 128), (12, 2, 128), (14, 2, 128), (4, 2, 64), (4, 2, 32)])
+def test_decode_attention_fused(ops, nq, nkv, hd):
+    """The one-launch decode attention (rotary + KV append + split-KV attention + merge; tensor-core path for hd=128,
+    scalar path otherwise) against a torch restatement: per row, keys = shared prompt prefix of its group + its own slab +
+    the token being decoded."""
+    from iad_r1_b200 import lib as L
+    torch.manual_seed(nq * 7 + hd)
+    dev = "cuda"
+    R, p_max, c_max, step = 5, 200, 100, 57
+    plen = torch.tensor([150, 200, 37, 37, 1], dtype=torch.int32, device=dev)
+    grp = torch.tensor([0, 0, 1, 1, 2], dtype=torch.int32, device=dev)
+    delta = torch.tensor([-20, -20, 0, 0, 3], dtype=torch.int32, device=dev)
+    D = (nq + 2 * nkv) * hd
+    qkv = torch.randn(R, D, device=dev)
+    kp, vp = rnd(3, p_max, nkv, hd), rnd(3, p_max, nkv, hd)
+    kc, vc = rnd(R, c_max, nkv, hd), rnd(R, c_max, nkv, hd)
+    kc0, vc0 = kc.clone(), vc.clone()
+    max_pos = p_max + c_max + 8
+    ang = torch.arange(max_pos, device=dev, dtype=torch.float32)[:, None] * (1.0 / (1e6 ** (torch.arange(0, hd, 2, device=dev).float() / hd)))
+    emb = torch.cat((ang, ang), -1)
+    cos_t, sin_t = emb.cos().contiguous(), emb.sin().contiguous()
+    state = torch.tensor([step, 0, R, 0, 0, 0, 0, 0], dtype=torch.int32, device=dev)
+    nsplit = (p_max + c_max + 127) // 128
+    part = torch.zeros(R, nq, nsplit, hd + 2, device=dev)
+    tickets = torch.zeros(R * nkv, dtype=torch.int32, device=dev)
+    out = torch.zeros(R, nq * hd, dtype=bf16, device=dev)
+    scale = hd ** -0.5
+    for _ in range(2):  # second call checks the ticket re-arm
+        kc.copy_(kc0); vc.copy_(vc0)
+        L.check(L.lib().iadr1_decode_attention_fused(
+            qkv.data_ptr(), cos_t.data_ptr(), sin_t.data_ptr(), delta.data_ptr(), kp.data_ptr(), vp.data_ptr(), kc.data_ptr(),
+            vc.data_ptr(), state.data_ptr(), grp.data_ptr(), plen.data_ptr(), part.data_ptr(), tickets.data_ptr(), out.data_ptr(),
+            R, nq, nkv, hd, p_max, c_max, nsplit, max_pos, scale, L.stream_ptr()))
+    torch.cuda.synchronize()
+    assert (tickets == 0).all()
+    g = nq // nkv
+    for r in range(R):
+        P = int(plen[r]); pos = P + step + int(delta[r])
+        c, s_ = cos_t[pos].to(bf16), sin_t[pos].to(bf16)
+        x = qkv[r].to(bf16).view(nq + 2 * nkv, hd)
+        qk = (x[:nq + nkv] * c) + (_rot_half_f(x[:nq + nkv]) * s_)          # bf16 arithmetic, as HF
+        q, knew, vnew = qk[:nq].float(), qk[nq:], x[nq + nkv:]
+        assert torch.equal(kc[r, step], knew) and torch.equal(vc[r, step], vnew), "KV append"
+        assert torch.equal(kc[r, :step], kc0[r, :step]) and torch.equal(kc[r, step + 1:], kc0[r, step + 1:])
+        K = torch.cat([kp[grp[r], :P], kc0[r, :step], knew[None]], 0).float()   # [ctx, nkv, hd]
+        V = torch.cat([vp[grp[r], :P], vc0[r, :step], vnew[None]], 0).float()
+        for h in range(nq):
+            kvh = h // g
+            p_ = torch.softmax((K[:, kvh] @ q[h]) * scale, 0)
+            ref = p_ @ V[:, kvh]
+            close(out[r].view(nq, hd)[h], ref, 2 ** -6, f"decode attention row {r} head {h}")
