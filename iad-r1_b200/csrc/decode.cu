@@ -529,13 +529,16 @@ __global__ void __launch_bounds__(128) decode_attn_fused_kernel(
 
 
 // ------------------------------------------------------------------------------------------------
-// Tensor-core variant of the fused decode attention for head_dim 128 (the decoder of every Qwen2(.5)-VL size).
-// Same contract, grid and partial/ticket protocol as decode_attn_fused_kernel; what changes is step 3: the `gq` query
-// heads of the kv head form the M dimension (padded to 16) of mma.sync m16n8k16 tiles, so one K/V row read from shared
-// memory serves all heads at once (the scalar kernel was shared-memory-bandwidth bound: every head re-read K through
-// LDS and broadcast q from LDS). Chunk = 128 keys, one 32-key tile per warp:
-//   S[16 x 32] = Q[16 x 128] K^T   (32 mma)  ->  masked softmax on the fragments (quad shuffles)  ->
-//   O[16 x 128] += P[16 x 32] V    (32 mma), P re-used from the S accumulators as the A operand (bf16).
+// Tensor-core fused decode attention (head_dim 64 / 128): the kernel the rollout graph runs.
+// Same contract and partial/ticket protocol as decode_attn_fused_kernel; what differs:
+//   * the `gq` query heads of the kv head form the M dimension (padded to 16) of mma.sync m16n8k16 tiles, so one K/V
+//     row read from shared memory serves all heads at once (the scalar kernel re-read K through LDS per head);
+//   * the grid is sized for ONE wave (rows x kv heads x nsplit <= 3 CTAs per SM) and each CTA walks ITS balanced share
+//     of the context [sp * per, (sp + 1) * per), per = ceil16(ctx / nsplit), in 64-key chunks through a double-buffered
+//     cp.async pipeline, so loads of chunk c + 1 overlap the MMAs of chunk c (the first version staged one fixed
+//     128-key chunk per CTA, ran 2+ waves and idled the tensor pipe while loading);
+//   * per chunk each warp owns 16 keys:  S[16 x 16] = Q K^T  ->  online softmax on the fragments (quad shuffles)  ->
+//     O[16 x HD] += P V, P re-used from the S accumulators as the bf16 A operand.
 // Q, K and V tiles sit in shared memory with their 16-byte pieces XOR-swizzled by (row & 7): ldmatrix (plain for Q/K,
 // .trans for V) is bank-conflict free.
 // ------------------------------------------------------------------------------------------------
@@ -560,13 +563,14 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<const uint32_t*>(&v);
 }
 
+template <int HD>
 __global__ void __launch_bounds__(128) decode_attn_mma_kernel(
     const float* __restrict__ qkv, const float* __restrict__ cos_tab, const float* __restrict__ sin_tab,
     const int* __restrict__ rope_delta, const bf16* __restrict__ kp, const bf16* __restrict__ vp, bf16* __restrict__ kc,
     bf16* __restrict__ vc, const int* __restrict__ state, const int* __restrict__ row_group,
     const int* __restrict__ row_plen, float* __restrict__ part, int* __restrict__ tickets, bf16* __restrict__ out, int nq,
     int nkv, int p_max, int c_max, int max_pos, float scale) {
-  constexpr int HD = 128, HALF = 64, PPR = 16, CHUNK = 128, MAXG = 8;
+  constexpr int HALF = HD / 2, PPR = HD / 8, CK = 64, MAXG = 8, NKS = HD / 16, NOB = HD / 8, EPL = HD / 32;
   const int r = blockIdx.x, kvh = blockIdx.y, sp = blockIdx.z, nsplit = gridDim.z;
   const int gq = nq / nkv;
   const int lane = threadIdx.x & 31;
@@ -574,8 +578,10 @@ __global__ void __launch_bounds__(128) decode_attn_mma_kernel(
   const int P = row_plen[r];
   const int step = state[ST_STEP];
   const int ctx = P + step + 1;
-  const int k0 = sp * CHUNK, k1 = min(ctx, k0 + CHUNK);
-  const int nkeys = max(0, k1 - k0);
+  const int per = (((ctx + nsplit - 1) / nsplit) + 15) & ~15;
+  const int k0 = min(ctx, sp * per), k1 = min(ctx, k0 + per);
+  const int nkeys = k1 - k0;
+  const int nchunks = (nkeys + CK - 1) / CK;
   const int grp = row_group[r];
   const int qkv_dim = (nq + 2 * nkv) * HD;
   const float* xrow = qkv + (long long)r * qkv_dim;
@@ -591,158 +597,169 @@ __global__ void __launch_bounds__(128) decode_attn_mma_kernel(
     return bf16r(a + b);
   };
   __shared__ __align__(128) bf16 sQ[16 * HD];             // 16 query rows (heads, zero-padded), swizzled pieces
-  __shared__ float sm_mrg[4][MAXG][HD + 2];
+  __shared__ __align__(16) bf16 sNew[2][HD];              // this step's rotated k and v (linear)
   __shared__ int s_last;
-  extern __shared__ __align__(128) uint8_t sm_kv_raw[];
-  bf16* sK = reinterpret_cast<bf16*>(sm_kv_raw);          // [CHUNK][HD] swizzled
-  bf16* sV = sK + CHUNK * HD;                             // [CHUNK][HD] swizzled
+  extern __shared__ __align__(128) uint8_t sm_kv_raw[];   // 2 stages x {K [CK][HD], V [CK][HD]}, swizzled
+  bf16* sKV = reinterpret_cast<bf16*>(sm_kv_raw);
+  constexpr int STAGE = 2 * CK * HD;                      // elements per stage
 
-  // ---- stage K/V (cache rows written >= 2 kernels ago: before the PDL wait) ----
-  for (int q = threadIdx.x; q < CHUNK * PPR; q += blockDim.x) {
-    const int jj = q / PPR, piece = q % PPR;
-    const int j = k0 + jj;
-    bf16* kd = sK + jj * HD + ((piece ^ (jj & 7)) << 3);
-    bf16* vd = sV + jj * HD + ((piece ^ (jj & 7)) << 3);
-    if (jj < nkeys && j != ctx - 1) {
-      const bf16* krow;
-      const bf16* vrow;
-      if (j < P) {
-        krow = kp + (((long long)grp * p_max + j) * nkv + kvh) * HD;
-        vrow = vp + (((long long)grp * p_max + j) * nkv + kvh) * HD;
+  // cache rows of chunk c -> stage buffer; the token being decoded (key ctx - 1) is patched in from sNew later
+  auto stage = [&](int c) {
+    bf16* sK = sKV + (c & 1) * STAGE;
+    bf16* sV = sK + CK * HD;
+    const int base = k0 + c * CK;
+    for (int q = threadIdx.x; q < CK * PPR; q += 128) {
+      const int jj = q / PPR, piece = q % PPR;
+      const int j = base + jj;
+      const int off = jj * HD + ((piece ^ (jj & 7)) << 3);
+      if (j < k1) {
+        if (j != ctx - 1) {
+          const long long row = (j < P) ? (((long long)grp * p_max + j) * nkv + kvh) * HD
+                                        : (((long long)r * c_max + (j - P)) * nkv + kvh) * HD;
+          cp_async16(sK + off, ((j < P) ? kp : kc) + row + piece * 8);
+          cp_async16(sV + off, ((j < P) ? vp : vc) + row + piece * 8);
+        }
       } else {
-        krow = kc + (((long long)r * c_max + (j - P)) * nkv + kvh) * HD;
-        vrow = vc + (((long long)r * c_max + (j - P)) * nkv + kvh) * HD;
+        *reinterpret_cast<uint4*>(sK + off) = make_uint4(0, 0, 0, 0);   // beyond the range: finite zeros (masked below)
+        *reinterpret_cast<uint4*>(sV + off) = make_uint4(0, 0, 0, 0);
       }
-      cp_async16(kd, krow + piece * 8);
-      cp_async16(vd, vrow + piece * 8);
-    } else if (jj >= nkeys) {
-      *reinterpret_cast<uint4*>(kd) = make_uint4(0, 0, 0, 0);   // rows beyond the chunk: finite zeros (masked below)
-      *reinterpret_cast<uint4*>(vd) = make_uint4(0, 0, 0, 0);
     }
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  // chunk 0 holds cache rows written by earlier decode steps / the prefill: requested before the PDL wait
+  if (nchunks > 0) stage(0);
   pdl_wait();
   if (threadIdx.x == 0) pdl_trigger();
   // ---- rotated, pre-scaled queries as bf16 rows (row = head within the group) ----
-  for (int i = threadIdx.x; i < 16 * HD; i += blockDim.x) {
+  for (int i = threadIdx.x; i < 16 * HD; i += 128) {
     const int h = i / HD, d = i % HD;
     const float v = (h < gq) ? rot(xrow + (long long)(kvh * gq + h) * HD, d) * scale : 0.f;
     sQ[h * HD + ((((d >> 3) ^ (h & 7)) << 3) | (d & 7))] = __float2bfloat16(v);
   }
-  if (ctx - 1 >= k0 && ctx - 1 < k1 && warp == 0) {
-    const int jj = ctx - 1 - k0;
+  const bool has_new = (ctx - 1 >= k0) && (ctx - 1 < k1);
+  if (has_new && warp == 3) {
     const float* knew = xrow + (long long)(nq + kvh) * HD;
     const float* vnew = xrow + (long long)(nq + nkv + kvh) * HD;
     bf16* kdst = kc + (((long long)r * c_max + step) * nkv + kvh) * HD;
     bf16* vdst = vc + (((long long)r * c_max + step) * nkv + kvh) * HD;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int d = lane * 4 + e;
+    for (int e = 0; e < EPL; ++e) {
+      const int d = lane * EPL + e;
       const bf16 kb = __float2bfloat16(rot(knew, d));
       const bf16 vb = __float2bfloat16(vnew[d]);
-      const int sw = jj * HD + ((((d >> 3) ^ (jj & 7)) << 3) | (d & 7));
-      sK[sw] = kb;
-      sV[sw] = vb;
+      sNew[0][d] = kb;
+      sNew[1][d] = vb;
       kdst[d] = kb;
       vdst[d] = vb;
     }
   }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-
-  // ---- this warp's 32-key tile ----
-  const int t0 = warp * 32;
-  float sacc[4][4];
+  uint32_t qa[NKS][4];
 #pragma unroll
-  for (int nb = 0; nb < 4; ++nb)
-#pragma unroll
-    for (int e = 0; e < 4; ++e) sacc[nb][e] = 0.f;
-  if (t0 < nkeys) {
-    // S = Q K^T : A = Q fragments per 16-dim k-step, B = K rows (keys) x dims
-#pragma unroll
-    for (int ks = 0; ks < 8; ++ks) {
-      uint32_t a[4];
-      {
-        const int row = (lane & 7) + ((lane >> 3) & 1) * 8;
-        const int piece = ks * 2 + (lane >> 4);
-        ldsm_x4(a, sQ + row * HD + ((piece ^ (row & 7)) << 3));
-      }
-      if ((ks & 1) == 0) {
-        // one ldmatrix.x4 covers two k-steps of one 8-key block; issue per n-block
-      }
-#pragma unroll
-      for (int nb = 0; nb < 4; ++nb) {
-        uint32_t b[4];
-        // matrices: (keys nb*8.., dims ks*16 + 0), (.., + 8) and two unused halves of the next k-step are skipped by
-        // loading exactly the two pieces of THIS k-step twice-addressed: lanes 0-15 give pieces 2ks, 2ks+1
-        const int key = t0 + nb * 8 + (lane & 7);
-        const int piece = ks * 2 + ((lane >> 3) & 1);
-        ldsm_x4(b, sK + key * HD + ((piece ^ (key & 7)) << 3));   // lanes 16-31 repeat the same two matrices
-        mma_bf16_16816(sacc[nb], a, b[0], b[1]);
-      }
-    }
+  for (int ks = 0; ks < NKS; ++ks) {
+    const int row = (lane & 7) + ((lane >> 3) & 1) * 8;
+    const int piece = ks * 2 + (lane >> 4);
+    ldsm_x4(qa[ks], sQ + row * HD + ((piece ^ (row & 7)) << 3));
   }
-  // masked softmax on the fragments: thread holds rows (lane/4) [c0,c1] and (lane/4 + 8) [c2,c3]; only rows < gq count
-  const int row_lo = lane >> 2;
-  float mloc = -INFINITY;
+  float oacc[NOB][4];
 #pragma unroll
-  for (int nb = 0; nb < 4; ++nb) {
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int key = t0 + nb * 8 + (lane & 3) * 2 + e;
-      if (key >= nkeys) sacc[nb][e] = -INFINITY;
-      mloc = fmaxf(mloc, sacc[nb][e]);
-    }
-  }
-  mloc = fmaxf(mloc, __shfl_xor_sync(0xffffffffu, mloc, 1));
-  mloc = fmaxf(mloc, __shfl_xor_sync(0xffffffffu, mloc, 2));
-  float lloc = 0.f;
-  uint32_t pa[2][4];   // P as A fragments for the two 16-key k-steps of P.V
-#pragma unroll
-  for (int nb = 0; nb < 4; ++nb) {
-    const float p0 = (mloc == -INFINITY) ? 0.f : __expf(sacc[nb][0] - mloc);
-    const float p1 = (mloc == -INFINITY) ? 0.f : __expf(sacc[nb][1] - mloc);
-    lloc += p0 + p1;
-    // rows +8 (c2, c3) are padding heads: probabilities forced to 0
-    pa[nb >> 1][(nb & 1) * 2 + 0] = pack_bf16x2(p0, p1);
-    pa[nb >> 1][(nb & 1) * 2 + 1] = 0u;
-  }
-  lloc += __shfl_xor_sync(0xffffffffu, lloc, 1);
-  lloc += __shfl_xor_sync(0xffffffffu, lloc, 2);
-  // O = P V : B = V^T fragments via ldmatrix.trans
-  float oacc[16][4];
-#pragma unroll
-  for (int nb = 0; nb < 16; ++nb)
+  for (int nb = 0; nb < NOB; ++nb)
 #pragma unroll
     for (int e = 0; e < 4; ++e) oacc[nb][e] = 0.f;
-  if (t0 < nkeys) {
+  float mrun = -INFINITY, lrun = 0.f;      // of query row lane / 4 (rows >= 8 are padding)
+
+  for (int c = 0; c < nchunks; ++c) {
+    if (c + 1 < nchunks) stage(c + 1);
+    bf16* sK = sKV + (c & 1) * STAGE;
+    bf16* sV = sK + CK * HD;
+    const int cbase = k0 + c * CK;
+    if (has_new && ctx - 1 >= cbase && ctx - 1 < cbase + CK && threadIdx.x < 2 * PPR) {
+      const int jj = ctx - 1 - cbase;
+      const int which = threadIdx.x / PPR, piece = threadIdx.x % PPR;
+      bf16* dst = (which ? sV : sK) + jj * HD + ((piece ^ (jj & 7)) << 3);
+      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(&sNew[which][piece * 8]);
+    }
+    if (c + 1 < nchunks) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    const int t0 = warp * 16;                   // this warp's 16 keys of the chunk
+    const int nk = min(CK, k1 - cbase);         // valid keys in the chunk
+    if (t0 < nk) {
+      float sacc[2][4];
 #pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
+      for (int nb = 0; nb < 2; ++nb)
 #pragma unroll
-      for (int nb = 0; nb < 16; nb += 2) {
+        for (int e = 0; e < 4; ++e) sacc[nb][e] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < NKS; ++ks) {
         uint32_t b[4];
-        const int key = t0 + ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int key = t0 + (lane & 7) + ((lane >> 4) & 1) * 8;
+        const int piece = ks * 2 + ((lane >> 3) & 1);
+        ldsm_x4(b, sK + key * HD + ((piece ^ (key & 7)) << 3));
+        mma_bf16_16816(sacc[0], qa[ks], b[0], b[1]);
+        mma_bf16_16816(sacc[1], qa[ks], b[2], b[3]);
+      }
+      float mloc = -INFINITY;
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int key = t0 + nb * 8 + (lane & 3) * 2 + e;
+          if (key >= nk) sacc[nb][e] = -INFINITY;
+          mloc = fmaxf(mloc, sacc[nb][e]);
+        }
+      mloc = fmaxf(mloc, __shfl_xor_sync(0xffffffffu, mloc, 1));
+      mloc = fmaxf(mloc, __shfl_xor_sync(0xffffffffu, mloc, 2));
+      const float mnew = fmaxf(mrun, mloc);     // finite: key t0 is valid
+      const float corr = (mrun == -INFINITY) ? 0.f : __expf(mrun - mnew);
+      uint32_t pa[4];
+      float lloc = 0.f;
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb) {
+        const float p0 = __expf(sacc[nb][0] - mnew);
+        const float p1 = __expf(sacc[nb][1] - mnew);
+        lloc += p0 + p1;
+        pa[nb * 2 + 0] = pack_bf16x2(p0, p1);
+        pa[nb * 2 + 1] = 0u;                    // rows + 8: padding heads
+      }
+      lloc += __shfl_xor_sync(0xffffffffu, lloc, 1);
+      lloc += __shfl_xor_sync(0xffffffffu, lloc, 2);
+      lrun = lrun * corr + lloc;
+      mrun = mnew;
+#pragma unroll
+      for (int nb = 0; nb < NOB; ++nb) {
+        oacc[nb][0] *= corr;
+        oacc[nb][1] *= corr;
+      }
+#pragma unroll
+      for (int nb = 0; nb < NOB; nb += 2) {
+        uint32_t b[4];
+        const int key = t0 + (lane & 7) + ((lane >> 3) & 1) * 8;
         const int piece = nb + (lane >> 4);
         ldsm_x4_trans(b, sV + key * HD + ((piece ^ (key & 7)) << 3));
-        mma_bf16_16816(oacc[nb], pa[ks], b[0], b[1]);
-        mma_bf16_16816(oacc[nb + 1], pa[ks], b[2], b[3]);
+        mma_bf16_16816(oacc[nb], pa, b[0], b[1]);
+        mma_bf16_16816(oacc[nb + 1], pa, b[2], b[3]);
       }
     }
+    __syncthreads();                            // buffer (c & 1) is re-filled by the next iteration's stage(c + 2)
   }
-  // ---- merge the 4 warps (rows = heads < gq live in c0/c1 of the lanes with lane/4 == head) ----
+  // ---- merge the 4 warps (rows = heads < gq live in c0/c1 of the lanes with lane/4 == head); staging memory re-used
+  float (*sm_mrg)[MAXG][HD + 2] = reinterpret_cast<float (*)[MAXG][HD + 2]>(sm_kv_raw);
+  const int row_lo = lane >> 2;
   if (row_lo < MAXG) {
 #pragma unroll
-    for (int nb = 0; nb < 16; ++nb) {
+    for (int nb = 0; nb < NOB; ++nb) {
       sm_mrg[warp][row_lo][nb * 8 + (lane & 3) * 2 + 0] = oacc[nb][0];
       sm_mrg[warp][row_lo][nb * 8 + (lane & 3) * 2 + 1] = oacc[nb][1];
     }
     if ((lane & 3) == 0) {
-      sm_mrg[warp][row_lo][HD] = mloc;
-      sm_mrg[warp][row_lo][HD + 1] = lloc;
+      sm_mrg[warp][row_lo][HD] = mrun;
+      sm_mrg[warp][row_lo][HD + 1] = lrun;
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < gq * HD; i += blockDim.x) {
+  for (int i = threadIdx.x; i < gq * HD; i += 128) {
     const int h = i / HD, d = i % HD;
     float m = -INFINITY;
 #pragma unroll
@@ -751,9 +768,9 @@ __global__ void __launch_bounds__(128) decode_attn_mma_kernel(
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
       const float mw = sm_mrg[w][h][HD];
-      const float c = (mw == -INFINITY) ? 0.f : __expf(mw - m);
-      a += sm_mrg[w][h][d] * c;
-      l += sm_mrg[w][h][HD + 1] * c;
+      const float cf = (mw == -INFINITY) ? 0.f : __expf(mw - m);
+      a += sm_mrg[w][h][d] * cf;
+      l += sm_mrg[w][h][HD + 1] * cf;
     }
     float* dst = part + (((long long)r * nq + kvh * gq + h) * nsplit + sp) * (HD + 2);
     dst[d] = a;
@@ -785,25 +802,36 @@ __global__ void __launch_bounds__(128) decode_attn_mma_kernel(
     float m = ms;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    const float c = (ms == -INFINITY) ? 0.f : __expf(ms - m);
-    s_c[h][lane] = c;
-    const float l = wsum(ls * c);
+    const float cf = (ms == -INFINITY) ? 0.f : __expf(ms - m);
+    s_c[h][lane] = cf;
+    const float l = wsum(ls * cf);
     if (lane == 0) s_invl[h] = 1.f / l;
   }
   __syncthreads();
-  float a8[MAXG];
+  constexpr int OUTS = (MAXG * HD + 127) / 128;
+  float a8[OUTS];
 #pragma unroll
-  for (int oo = 0; oo < MAXG; ++oo) a8[oo] = 0.f;
+  for (int oo = 0; oo < OUTS; ++oo) a8[oo] = 0.f;
   const float* pbase = part + ((long long)r * nq + kvh * gq) * nsplit * (HD + 2);
 #pragma unroll 2
   for (int s2 = 0; s2 < nsplit; ++s2) {
 #pragma unroll
-    for (int oo = 0; oo < MAXG; ++oo)
-      if (oo < gq) a8[oo] += __ldcg(pbase + ((long long)oo * nsplit + s2) * (HD + 2) + threadIdx.x) * s_c[oo][s2];
+    for (int oo = 0; oo < OUTS; ++oo) {
+      const int o = threadIdx.x + 128 * oo;
+      if (o < gq * HD) {
+        const int h = o / HD, d = o % HD;
+        a8[oo] += __ldcg(pbase + ((long long)h * nsplit + s2) * (HD + 2) + d) * s_c[h][s2];
+      }
+    }
   }
 #pragma unroll
-  for (int oo = 0; oo < MAXG; ++oo)
-    if (oo < gq) out[((long long)r * nq + kvh * gq + oo) * HD + threadIdx.x] = __float2bfloat16(a8[oo] * s_invl[oo]);
+  for (int oo = 0; oo < OUTS; ++oo) {
+    const int o = threadIdx.x + 128 * oo;
+    if (o < gq * HD) {
+      const int h = o / HD, d = o % HD;
+      out[((long long)r * nq + kvh * gq + h) * HD + d] = __float2bfloat16(a8[oo] * s_invl[h]);
+    }
+  }
 }
 
 template <int HD>
@@ -1166,25 +1194,32 @@ int iadr1_decode_attention_fused(const float* qkv, const float* cos_tab, const f
   if (rows <= 0) return 0;
   if (nq % nkv || nq / nkv > 8) return set_error("decode_attention_fused: group size %d unsupported (max 8)", nq / nkv);
   if (nsplit < 1 || nsplit > 32) return set_error("decode_attention_fused: nsplit %d out of range (1..32)", nsplit);
-  const int chunk = (p_max + c_max + nsplit - 1) / nsplit;
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t kv_smem = (size_t)chunk * hd * 4;
-  if (kv_smem > 160 * 1024) return set_error("decode_attention_fused: context too long for one staging buffer (chunk %d)", chunk);
   static const int dbg = getenv("IADR1_ATTN_DEBUG") ? atoi(getenv("IADR1_ATTN_DEBUG")) : 0;  // phase-skipping, probes only
   static const bool use_mma = !(getenv("IADR1_DECODE_ATTN") && std::string(getenv("IADR1_DECODE_ATTN")) == "scalar");
-  if (hd == 128 && use_mma && chunk <= 128) {
-    // tensor-core path: chunk fixed at 128 keys -> nsplit must cover p_max + c_max
-    static bool attr = false;
-    if (!attr) {
-      cudaFuncSetAttribute(decode_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-      attr = true;
+  if ((hd == 128 || hd == 64) && use_mma) {
+    // tensor-core path: any nsplit; every CTA walks its balanced share of the live context in 64-key chunks
+    const size_t smem = (size_t)2 * 2 * 64 * hd * 2;
+    if (hd == 128) {
+      static bool attr = false;
+      if (!attr) {
+        cudaFuncSetAttribute(decode_attn_mma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+      }
+      launch_kernel(decode_attn_mma_kernel<128>, dim3(rows, nkv, nsplit), dim3(128), smem, st, qkv, cos_tab, sin_tab,
+                    rope_delta, (const bf16*)kp, (const bf16*)vp, (bf16*)kc, (bf16*)vc, state, row_group, row_plen, part,
+                    tickets, (bf16*)out, nq, nkv, p_max, c_max, max_pos, scale);
+    } else {
+      launch_kernel(decode_attn_mma_kernel<64>, dim3(rows, nkv, nsplit), dim3(128), smem, st, qkv, cos_tab, sin_tab,
+                    rope_delta, (const bf16*)kp, (const bf16*)vp, (bf16*)kc, (bf16*)vc, state, row_group, row_plen, part,
+                    tickets, (bf16*)out, nq, nkv, p_max, c_max, max_pos, scale);
     }
-    launch_kernel(decode_attn_mma_kernel, dim3(rows, nkv, nsplit), dim3(128), (size_t)64 * 1024, st, qkv, cos_tab, sin_tab,
-                  rope_delta, (const bf16*)kp, (const bf16*)vp, (bf16*)kc, (bf16*)vc, state, row_group, row_plen, part,
-                  tickets, (bf16*)out, nq, nkv, p_max, c_max, max_pos, scale);
     IADR1_CHECK_LAUNCH("decode_attention_mma");
     return 0;
   }
+  const int chunk = (p_max + c_max + nsplit - 1) / nsplit;
+  const size_t kv_smem = (size_t)chunk * hd * 4;
+  if (kv_smem > 160 * 1024) return set_error("decode_attention_fused: context too long for one staging buffer (chunk %d)", chunk);
 #define IADR1_DECODE_FUSED(HD)                                                                                       \
   do {                                                                                                               \
     if (kv_smem > 48 * 1024)                                                                                         \

@@ -63,8 +63,13 @@ class RolloutEngine:
         self.qkv = torch.zeros(R, t.qkv_dim, dtype=f32, device=dev)
         self.q = torch.zeros(R, t.num_heads * hd, dtype=bf16, device=dev)
         self.attn = torch.zeros(R, t.num_heads * hd, dtype=bf16, device=dev)
-        keys_per_cta = int(os.environ.get("IADR1_DECODE_KEYS_PER_CTA", "128"))
-        self.nsplit = max(1, min(32, (p_max + c_max + keys_per_cta - 1) // keys_per_cta))   # ~128 keys (4 tiles) per CTA
+        if hd in (64, 128):
+            # tensor-core kernel: ONE wave of (row, kv head, split) CTAs at 3 CTAs per SM; each CTA pipelines its balanced
+            # share of the live context (decode.cu: decode_attn_mma_kernel)
+            ctas = int(os.environ.get("IADR1_DECODE_ATTN_CTAS", str(3 * NUM_SMS)))
+            self.nsplit = max(1, min(16, ctas // (R * nkv)))
+        else:
+            self.nsplit = max(1, min(32, (p_max + c_max + 127) // 128))   # scalar kernel: one 128-key chunk per CTA
         self.part = torch.zeros(R, t.num_heads, self.nsplit, hd + 2, dtype=f32, device=dev)
         self.tickets = torch.zeros(R * nkv, dtype=i32, device=dev)
         self.gu = torch.zeros(R, 2 * I, dtype=bf16, device=dev)

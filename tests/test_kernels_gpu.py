@@ -363,9 +363,10 @@ def _rot_half_f(x):
     return torch.cat((-x[..., h:], x[..., :h]), -1)
 
 
-@pytest.mark.parametrize("nq,nkv,hd", [(8, 1, 128), (12, 2, 128), (14, 2, 128), (4, 2, 64), (4, 2, 32)])
-def test_decode_attention_fused(ops, nq, nkv, hd):
-    """The one-launch decode attention (rotary + KV append + split-KV attention + merge; tensor-core path for hd=128,
+@pytest.mark.parametrize("nq,nkv,hd,nsplit", [(8, 1, 128, 3), (12, 2, 128, 1), (14, 2, 128, 13), (16, 2, 128, 5),
+                                              (4, 2, 64, 3), (14, 2, 64, 2), (4, 2, 32, 0)])
+def test_decode_attention_fused(ops, nq, nkv, hd, nsplit):
+    """The one-launch decode attention (rotary + KV append + split-KV attention + merge; tensor-core path for hd=64/128,
     scalar path otherwise) against a torch restatement: per row, keys = shared prompt prefix of its group + its own slab +
     the token being decoded."""
     from iad_r1_b200 import lib as L
@@ -385,7 +386,7 @@ def test_decode_attention_fused(ops, nq, nkv, hd):
     emb = torch.cat((ang, ang), -1)
     cos_t, sin_t = emb.cos().contiguous(), emb.sin().contiguous()
     state = torch.tensor([step, 0, R, 0, 0, 0, 0, 0], dtype=torch.int32, device=dev)
-    nsplit = (p_max + c_max + 127) // 128
+    nsplit = nsplit or (p_max + c_max + 127) // 128     # tensor-core path: any split count; scalar path: 128-key chunks
     part = torch.zeros(R, nq, nsplit, hd + 2, device=dev)
     tickets = torch.zeros(R * nkv, dtype=torch.int32, device=dev)
     out = torch.zeros(R, nq * hd, dtype=bf16, device=dev)
