@@ -34,6 +34,26 @@ int iadr1_set_pdl(int on) {
   iadr1::pdl_set(on != 0);
   return 0;
 }
+int iadr1_trace(int op, unsigned long long* out, int max_words) {
+  static unsigned long long* buf = nullptr;
+  const size_t words = 2 + 2 * 8190;
+  if (op == 1) {          // install + reset
+    if (!buf && cudaMalloc(&buf, words * 8) != cudaSuccess) return iadr1::set_error("trace: cudaMalloc failed");
+    cudaMemset(buf, 0, words * 8);
+    iadr1::trace_install_decode(buf);
+    iadr1::trace_install_gemm(buf);
+    iadr1::trace_install_rowops(buf);
+  } else if (op == 0) {   // remove
+    iadr1::trace_install_decode(nullptr);
+    iadr1::trace_install_gemm(nullptr);
+    iadr1::trace_install_rowops(nullptr);
+  } else if (op == 2) {   // collect (device must be idle)
+    if (!buf || !out) return iadr1::set_error("trace: nothing to collect");
+    const size_t n = (size_t)max_words < words ? (size_t)max_words : words;
+    if (cudaMemcpy(out, buf, n * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return iadr1::set_error("trace: copy failed");
+  }
+  return 0;
+}
 int iadr1_gemm_profile_enable(int on) {
   iadr1::gemm_profile_enable(on);
   return 0;

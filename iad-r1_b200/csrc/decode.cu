@@ -90,8 +90,8 @@ template <> struct RawVec<1> {
 // h[r][:] = float(embed[tok[r]][:])
 __global__ void decode_embed_kernel(const bf16* __restrict__ embed, const int* __restrict__ tok, float* __restrict__ h,
                                     int H) {
+  if (threadIdx.x == 0) pdl_trigger();   // dependents may become resident (and prefetch) right away
   pdl_wait();
-  if (threadIdx.x == 0) pdl_trigger();
   const int r = blockIdx.x;
   const bf16* src = embed + (long long)tok[r] * H;
   for (int c = threadIdx.x; c < H; c += blockDim.x) h[(long long)r * H + c] = __bfloat162float(src[c]);
@@ -100,6 +100,7 @@ __global__ void decode_embed_kernel(const bf16* __restrict__ embed, const int* _
 // RMSNorm with fp32 input (the decode residual stream) -> bf16, same rounding order as Qwen2RMSNorm.
 __global__ void rmsnorm_f32in_kernel(const float* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y,
                                      int cols, float eps, float* __restrict__ zero_buf, int zero_per_row) {
+  if (threadIdx.x == 0) pdl_trigger();   // dependents may become resident (and prefetch) right away
   __shared__ float red[32];
   const long long row = blockIdx.x;
   const float* xr = x + row * cols;
@@ -112,7 +113,6 @@ __global__ void rmsnorm_f32in_kernel(const float* __restrict__ x, const bf16* __
     if (c < cols) wv[i] = __bfloat162float(w[c]);   // static weights: requested before the PDL wait (DRAM miss hidden)
   }
   pdl_wait();
-  if (threadIdx.x == 0) pdl_trigger();
 #pragma unroll
   for (int i = 0; i < MAXE; ++i) {
     const int c = threadIdx.x + i * blockDim.x;
@@ -292,6 +292,7 @@ __global__ void __launch_bounds__(128) decode_attn_fused_kernel(
     bf16* __restrict__ vc, const int* __restrict__ state, const int* __restrict__ row_group,
     const int* __restrict__ row_plen, float* __restrict__ part, int* __restrict__ tickets, bf16* __restrict__ out, int nq,
     int nkv, int p_max, int c_max, int chunk, int max_pos, float scale, int dbg) {
+  if (threadIdx.x == 0) pdl_trigger();   // dependents may become resident (and prefetch) right away
   constexpr int DPL = HD / 32;
   constexpr int MAXG = 8;
   constexpr int HPW = 2;             // heads per warp (MAXG / 4 warps)
@@ -353,7 +354,6 @@ __global__ void __launch_bounds__(128) decode_attn_fused_kernel(
   // everything above reads only scalars / tables / cache rows written at least two kernels ago; the qkv row below is
   // produced by the immediately preceding GEMM
   pdl_wait();
-  if (threadIdx.x == 0) pdl_trigger();
   for (int i = threadIdx.x; i < gq * HD; i += blockDim.x) {
     const int h = i / HD, d = i % HD;
     sm_q[h][d] = (dbg & 1) ? 0.f : rot(xrow + (long long)(kvh * gq + h) * HD, d) * scale;
@@ -570,6 +570,7 @@ __global__ void __launch_bounds__(128) decode_attn_mma_kernel(
     bf16* __restrict__ vc, const int* __restrict__ state, const int* __restrict__ row_group,
     const int* __restrict__ row_plen, float* __restrict__ part, int* __restrict__ tickets, bf16* __restrict__ out, int nq,
     int nkv, int p_max, int c_max, int max_pos, float scale) {
+  if (threadIdx.x == 0) pdl_trigger();   // dependents may become resident (and prefetch) right away
   constexpr int HALF = HD / 2, PPR = HD / 8, CK = 64, MAXG = 8, NKS = HD / 16, NOB = HD / 8, EPL = HD / 32;
   const int r = blockIdx.x, kvh = blockIdx.y, sp = blockIdx.z, nsplit = gridDim.z;
   const int gq = nq / nkv;
@@ -630,7 +631,6 @@ __global__ void __launch_bounds__(128) decode_attn_mma_kernel(
   // chunk 0 holds cache rows written by earlier decode steps / the prefill: requested before the PDL wait
   if (nchunks > 0) stage(0);
   pdl_wait();
-  if (threadIdx.x == 0) pdl_trigger();
   // ---- rotated, pre-scaled queries as bf16 rows (row = head within the group) ----
   for (int i = threadIdx.x; i < 16 * HD; i += 128) {
     const int h = i / HD, d = i % HD;
@@ -908,6 +908,7 @@ __global__ void __launch_bounds__(1024) sample_kernel(const float* __restrict__ 
                                                       int* __restrict__ tok, int* __restrict__ finished,
                                                       int* __restrict__ out_tokens, int c_max, int eos_id, int pad_id,
                                                       int forbid_eos, int first) {
+  if (threadIdx.x == 0) pdl_trigger();   // dependents may become resident (and prefetch) right away
   __shared__ float s_red[32];
   __shared__ int s_cnt[8][32];
   __shared__ int s_count, s_nsurv;
@@ -916,7 +917,6 @@ __global__ void __launch_bounds__(1024) sample_kernel(const float* __restrict__ 
   __shared__ float s_val[kMaxKeep], s_sorted[kMaxKeep];
   __shared__ int s_idx[kMaxKeep], s_sidx[kMaxKeep];
   pdl_wait();
-  if (threadIdx.x == 0) pdl_trigger();
   const int r = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const float* lg = logits + (long long)r * V;
@@ -1124,12 +1124,40 @@ __global__ void __launch_bounds__(1024) sample_kernel(const float* __restrict__ 
   }
 }
 
-__global__ void decode_advance_kernel(int* state) {
+// act[r][c] = bf16(silu(gate)) * up from the fp32 gate|up accumulator of the stream-K product (values rounded to bf16
+// first: the training forward stores that product in bf16), and the accumulator is cleared for the next layer.
+__global__ void decode_silu_mul_f32_kernel(float* __restrict__ gu, bf16* __restrict__ out, int rows, int cols) {
+  if (threadIdx.x == 0) pdl_trigger();   // dependents may become resident (and prefetch) right away
   pdl_wait();
-  pdl_trigger();
+  const int nvec = cols >> 2;
+  const int total = rows * nvec;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int r = i / nvec, v = i - r * nvec;
+    float4* gp = reinterpret_cast<float4*>(gu + (long long)r * 2 * cols) + v;
+    float4* up = reinterpret_cast<float4*>(gu + (long long)r * 2 * cols + cols) + v;
+    const float4 g = *gp, u = *up;
+    *gp = make_float4(0.f, 0.f, 0.f, 0.f);
+    *up = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto f = [](float gg, float uu) {
+      gg = bf16r(gg);
+      return bf16r(gg / (1.f + __expf(-gg))) * bf16r(uu);
+    };
+    __nv_bfloat162 o0 = __floats2bfloat162_rn(f(g.x, u.x), f(g.y, u.y));
+    __nv_bfloat162 o1 = __floats2bfloat162_rn(f(g.z, u.z), f(g.w, u.w));
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&o0);
+    o.y = *reinterpret_cast<uint32_t*>(&o1);
+    *reinterpret_cast<uint2*>(out + (long long)r * cols + v * 4) = o;
+  }
+}
+
+__global__ void decode_advance_kernel(int* state) {
+  if (threadIdx.x == 0) pdl_trigger();   // dependents may become resident (and prefetch) right away
+  pdl_wait();
   state[ST_STEP] += 1;
 }
 
+void trace_install_decode(unsigned long long* p) { trace_install_tu(p); }
 }  // namespace iadr1
 
 using namespace iadr1;
@@ -1138,7 +1166,10 @@ extern "C" {
 
 int iadr1_decode_embed(const void* embed, const int* tok, float* h, int rows, int H, void* stream) {
   if (rows <= 0) return 0;
-  launch_kernel(decode_embed_kernel, dim3(rows), dim3(256), 0, (cudaStream_t)stream, (const bf16*)embed, tok, h, H);
+  // First kernel of a decode step: launched WITHOUT the programmatic-serialization attribute, i.e. it starts only after
+  // the previous step (sampler, step counter) has fully completed. Every later kernel of the step may become resident
+  // early and read the step counter before its own dependency wait; this launch is what makes that safe.
+  decode_embed_kernel<<<dim3(rows), dim3(256), 0, (cudaStream_t)stream>>>((const bf16*)embed, tok, h, H);
   IADR1_CHECK_LAUNCH("decode_embed");
   return 0;
 }
@@ -1246,6 +1277,16 @@ const float* logits, int rows, int V, float temperature, int top_k, float top_p,
   launch_kernel(sample_kernel, dim3(rows), dim3(1024), 0, (cudaStream_t)stream, logits, V, 1.f / temperature, top_k,
                 top_p, seed, state, tok, finished, out_tokens, c_max, eos_id, pad_id, forbid_eos, first);
   IADR1_CHECK_LAUNCH("sample");
+  return 0;
+}
+
+int iadr1_decode_silu_mul_f32(float* gu, void* out, int rows, int cols, void* stream) {
+  if (rows <= 0) return 0;
+  if (cols % 4) return set_error("decode_silu_mul_f32: cols must be a multiple of 4");
+  const int total = rows * (cols / 4);
+  const int grid = (total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8;
+  launch_kernel(decode_silu_mul_f32_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, gu, (bf16*)out, rows, cols);
+  IADR1_CHECK_LAUNCH("decode_silu_mul_f32");
   return 0;
 }
 

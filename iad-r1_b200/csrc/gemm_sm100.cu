@@ -32,7 +32,6 @@ static constexpr int BM = 128;
 static constexpr int BK = 64;
 static constexpr int kThreads = 256;
 static constexpr int kMaxStages = 12;
-static constexpr int kAccStride = 256;  // TMEM columns per accumulator stage
 
 struct TileInfo {
   int z, m0, n0, n_blk, kb_begin, kb_end, split;
@@ -68,6 +67,51 @@ __device__ __forceinline__ TileInfo decode_tile(const GemmArgs& g, int t, int ti
   ti.skip = g.skip_mode && (ti.n0 > ti.m0 + BM - 1 + g.causal_off);
   return ti;
 }
+
+// Work iterator shared by the three warp roles. Tile mode: output tiles (x split_k x batch) round-robin over the
+// persistent CTAs. Stream-K mode (g.stream_k; single problem, full K, atomic fp32 output): the tiles_m * tiles_n * nkb
+// k-block units are cut into gridDim.x equal contiguous runs, so every SM streams the same number of weight bytes
+// even when the tile count is not a multiple of the SM count (the decode gate_up product: 172 tiles on 148 SMs);
+// a run crossing a tile boundary yields one segment per tile, each added atomically into C.
+struct WorkIter {
+  int cursor, end, stride;
+  __device__ __forceinline__ WorkIter(const GemmArgs& g, int total_tiles, int tiles_mn) {
+    if (g.stream_k) {
+      const int nkb = (g.K + BK - 1) / BK;
+      const int units = tiles_mn * nkb;
+      const int per = (units + (int)gridDim.x - 1) / (int)gridDim.x;
+      cursor = min(units, (int)blockIdx.x * per);
+      end = min(units, cursor + per);
+      stride = 0;
+    } else {
+      cursor = blockIdx.x;
+      end = total_tiles;
+      stride = gridDim.x;
+    }
+  }
+  __device__ __forceinline__ bool next(const GemmArgs& g, int tiles_m, int tiles_n, TileInfo& ti) {
+    if (cursor >= end) return false;
+    if (!g.stream_k) {
+      ti = decode_tile(g, cursor, tiles_m, tiles_n);
+      cursor += stride;
+      return true;
+    }
+    const int nkb = (g.K + BK - 1) / BK;
+    const int tile = cursor / nkb;
+    const int kb = cursor - tile * nkb;
+    const int len = min(nkb - kb, end - cursor);
+    ti.z = 0;
+    ti.n_blk = tile / tiles_m;
+    ti.m0 = (tile - ti.n_blk * tiles_m) * BM;
+    ti.n0 = ti.n_blk * g.block_n;
+    ti.kb_begin = kb;
+    ti.kb_end = kb + len;
+    ti.split = kb ? 1 : 0;   // bias / residual are added by the segment that starts the tile
+    ti.skip = false;
+    cursor += len;
+    return true;
+  }
+};
 
 template <int W>
 __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const TileInfo& ti, const uint32_t (&v)[W], int m,
@@ -204,12 +248,19 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const TileInfo
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+// kMinCtas = 2 is the decode-chain variant: <= 128 registers, a short smem ring and a TMEM allocation sized to the two
+// block_n-wide accumulator stages, so that under programmatic dependent launch the NEXT kernel's CTAs become resident
+// (and request their first weight tiles) while this kernel's CTAs are still draining.
+template <int kMinCtas>
+__global__ void __launch_bounds__(kThreads, kMinCtas)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
+  // Programmatic dependent launch: let the next kernel's CTAs become resident as early as resources allow. Every
+  // dependent still executes griddepcontrol.wait (full completion + flush of this grid) before touching our output.
+  if (threadIdx.x == 0) pdl_trigger();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int a_bytes = BM * BK * 2;                 // 16 KiB
@@ -241,7 +292,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, 512);
+    tmem_alloc(tmem_slot, g.tmem_cols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -276,8 +327,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       // Programmatic dependent launch: weights (A, when a_static) of the first tile's first stages are requested
       // BEFORE waiting for the preceding kernel, so their HBM latency overlaps that kernel's tail.
       int npre = 0;
-      if (g.a_static && blockIdx.x < total_tiles) {
-        const TileInfo t0 = decode_tile(g, blockIdx.x, tiles_m, tiles_n);
+      TileInfo t0;
+      WorkIter it0(g, total_tiles, tiles_m * tiles_n);
+      if (g.a_static && it0.next(g, tiles_m, tiles_n, t0)) {
         if (!t0.skip) {
           npre = min(g.stages, t0.kb_end - t0.kb_begin);
           for (int i = 0; i < npre; ++i) {
@@ -288,8 +340,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       }
       pdl_wait();
       bool first_tile = true;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const TileInfo ti = decode_tile(g, t, tiles_m, tiles_n);
+      TileInfo ti;
+      WorkIter it(g, total_tiles, tiles_m * tiles_n);
+      while (it.next(g, tiles_m, tiles_n, ti)) {
         if (ti.skip) continue;
         const int zlo = ti.z % g.batch_lo, zhi = ti.z / g.batch_lo;
         const int zlo_b = zlo / g.b_lo_div;
@@ -320,12 +373,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       uint32_t ph = 0;
       int as = 0;
       uint32_t aph = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const TileInfo ti = decode_tile(g, t, tiles_m, tiles_n);
+      TileInfo ti;
+      WorkIter it(g, total_tiles, tiles_m * tiles_n);
+      while (it.next(g, tiles_m, tiles_n, ti)) {
         if (ti.skip) continue;
         mbar_wait(&tempty_bar[as], aph ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * kAccStride;
+        const uint32_t d_tmem = tmem_base + as * (g.tmem_cols >> 1);
         for (int kb = ti.kb_begin; kb < ti.kb_end; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
@@ -348,21 +402,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     pdl_wait();
-    if (threadIdx.x == 128) pdl_trigger();
     const int q = warp & 3;
     const bool vec_ok = ((g.ldc & 7) == 0) && ((g.c_bs_lo & 7) == 0) && ((g.c_bs_hi & 7) == 0) &&
                         ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) &&
                         (g.residual == nullptr || (reinterpret_cast<uintptr_t>(g.residual) & 15) == 0);
     int as = 0;
     uint32_t aph = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const TileInfo ti = decode_tile(g, t, tiles_m, tiles_n);
+    TileInfo ti;
+    WorkIter it(g, total_tiles, tiles_m * tiles_n);
+    while (it.next(g, tiles_m, tiles_n, ti)) {
       if (ti.skip) continue;
       const bool have_acc = ti.kb_end > ti.kb_begin;
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
       const int m = ti.m0 + q * 32 + lane;
-      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * kAccStride;
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * (g.tmem_cols >> 1);
       float run_max = -INFINITY, run_sum = 0.f, tgt = 0.f, row_lse = 0.f, row_g = 0.f;
       bool tgt_found = false;
       int label = -1;
@@ -372,6 +426,41 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           row_lse = g.lse[m];
           row_g = g.gscale[m];
         }
+      }
+      if (g.bulk_red) {
+        // Transposed fp32 accumulate-into-C via the TMA unit: the tile is staged as sC[n][128 m] (lanes = consecutive m:
+        // conflict-free stores) and every decode row n is added to C^T[n][m0 .. m0 + 128) by ONE bulk reduction.
+        float* sC = reinterpret_cast<float*>(smem + (size_t)g.stages * stage_bytes + 512);
+        const int ml = q * 32 + lane;
+        float bias_m = 0.f;
+        if (g.bias != nullptr && ti.split == 0 && g.bias_per_m && m < g.M) bias_m = __bfloat162float(g.bias[m]);
+        for (int c0 = 0; c0 < g.block_n; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(taddr + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float x = have_acc ? g.alpha * __uint_as_float(v[j]) : 0.f;
+            x += bias_m;
+            if (g.bias != nullptr && ti.split == 0 && !g.bias_per_m && ti.n0 + c0 + j < g.N)
+              x += __bfloat162float(g.bias[ti.n0 + c0 + j]);
+            sC[(c0 + j) * BM + ml] = x;
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[as]);
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        const int mw = min(BM, g.M - ti.m0);          // live features of this tile (multiple of 4, checked on the host)
+        const int nrows = min(g.block_n, g.N - ti.n0);
+        for (int n = threadIdx.x - 128; n < nrows; n += 128)
+          bulk_reduce_add_f32(reinterpret_cast<float*>(g.C) + (long long)(ti.n0 + n) * g.ldc + ti.m0, sC + n * BM,
+                              (uint32_t)mw * 4u);
+        bulk_commit();
+        bulk_wait_read0();                            // staging tile may be overwritten by the next segment
+        named_bar_sync(1, 128);
+        if (++as == 2) { as = 0; aph ^= 1; }
+        continue;
       }
       int c0 = 0;
       for (; c0 + 32 <= g.block_n; c0 += 32) {
@@ -399,11 +488,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
   }
 
+  if (g.bulk_red && warp >= 4) bulk_wait0();   // this thread's bulk reductions have been performed
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, g.tmem_cols);
   }
 }
 
@@ -602,6 +692,10 @@ int launch_gemm(const iadr1_gemm_t& d, cudaStream_t stream) {
   g.residual = reinterpret_cast<const __nv_bfloat16*>(d.residual);
   g.labels = d.labels; g.part_max = d.part_max; g.part_sum = d.part_sum; g.tgt_logit = d.tgt_logit;
   g.lse = d.lse; g.gscale = d.gscale;
+  g.stream_k = d.stream_k;
+  if (g.stream_k && !(g.atomic && g.c_f32 && g.batch == 1 && g.kmode == 0 && g.skip_mode == 0 && g.split_k == 1 &&
+                      g.epi == EPI_STORE))
+    return set_error("gemm: stream_k needs a single full-K problem with atomic f32 output and split_k == 1");
   if (g.split_k > 1 && !(g.atomic && g.c_f32)) return set_error("gemm: split_k > 1 needs atomic f32 output");
   if (g.atomic && !g.c_f32) return set_error("gemm: atomic output must be f32");
   if (g.batch % g.batch_lo) return set_error("gemm: batch must be a multiple of batch_lo");
@@ -615,13 +709,24 @@ int launch_gemm(const iadr1_gemm_t& d, cudaStream_t stream) {
   const int a_bytes = BM * BK * 2;
   const int b_bytes = g.block_n * BK * 2;
   const int stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023);
-  const int smem_budget = 227 * 1024 - 1024 - 512;
+  // TMEM: two accumulator stages of block_n fp32 columns; the co-resident variant allocates only what it needs
+  g.tmem_cols = 512;
+  if (d.co_resident) {
+    if (g.block_n > 128) return set_error("gemm: co_resident needs block_n <= 128");
+    g.tmem_cols = 32;
+    while (g.tmem_cols < 2 * g.block_n) g.tmem_cols <<= 1;
+  }
+  // transposed fp32 atomic accumulation goes through bulk reductions (needs a [block_n][128] fp32 staging tile)
+  g.bulk_red = g.trans_c && g.atomic && g.c_f32 && g.epi == EPI_STORE && g.residual == nullptr && g.batch == 1 &&
+               (g.M % 4 == 0) && (g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) && !d.no_bulk_red;
+  const int epi_bytes = g.bulk_red ? g.block_n * BM * 4 : 0;
+  const int smem_budget = (d.co_resident ? 113 : 227) * 1024 - 1024 - 512 - epi_bytes;
   int stages = smem_budget / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (d.stages > 0 && d.stages < stages) stages = d.stages;
   if (stages < 2) return set_error("gemm: not enough shared memory for 2 stages");
   g.stages = stages;
-  const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + 512;
+  const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + 512 + epi_bytes;
 
   const int nb_hi = g.batch / g.batch_lo;
   const int nb_lo_b = (g.batch_lo + g.b_lo_div - 1) / g.b_lo_div;
@@ -645,8 +750,10 @@ int launch_gemm(const iadr1_gemm_t& d, cudaStream_t stream) {
 
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
     if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(gemm smem): %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -654,10 +761,14 @@ int launch_gemm(const iadr1_gemm_t& d, cudaStream_t stream) {
   const int tiles_n = (g.N + g.block_n - 1) / g.block_n;
   const long long total = (long long)tiles_m * tiles_n * g.split_k * g.batch;
   int grid = (int)(total < (long long)num_sms() ? total : num_sms());
+  if (g.stream_k) grid = num_sms();   // every SM takes an equal run of k-block units (K / 64 >= 1 each tile)
   if (d.max_ctas > 0 && grid > d.max_ctas) grid = d.max_ctas;
   cudaEvent_t pe0, pe1;
   const bool timed = prof_begin(stream, &pe0, &pe1);
-  launch_kernel(gemm_bf16_tcgen05_kernel, dim3(grid), dim3(kThreads), smem_bytes, stream, tmA, tmB, g);
+  if (d.co_resident)
+    launch_kernel(gemm_bf16_tcgen05_kernel<2>, dim3(grid), dim3(kThreads), smem_bytes, stream, tmA, tmB, g);
+  else
+    launch_kernel(gemm_bf16_tcgen05_kernel<1>, dim3(grid), dim3(kThreads), smem_bytes, stream, tmA, tmB, g);
   if (timed) {
     cudaEventRecord(pe1, stream);
     // algorithmic FLOPs: causal products count only the unmasked half
@@ -673,4 +784,5 @@ int launch_gemm(const iadr1_gemm_t& d, cudaStream_t stream) {
   return 0;
 }
 
+void trace_install_gemm(unsigned long long* p) { trace_install_tu(p); }
 }  // namespace iadr1

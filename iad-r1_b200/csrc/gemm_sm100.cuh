@@ -18,11 +18,14 @@ struct GemmArgs {
   int b_lo_div;   // B's lo batch coordinate is (z % batch_lo) / b_lo_div (grouped-query sharing)
   int block_n;    // multiple of 16, <= 256
   int stages;
+  int tmem_cols;  // TMEM columns allocated (power of two >= 2 * block_n); accumulator stage s lives at s * tmem_cols / 2
   int a_mn, b_mn; // operand majorness: 0 = K-major (reduction dim contiguous), 1 = MN-major
   int kmode;      // 0 full K; 1: k < m0 + 128 + causal_off (rows attend to keys <= row + off); 2: k >= m0 - causal_off
   int skip_mode;  // 1: skip output tiles with n0 > m0 + 127 + causal_off (fully masked)
   int causal_off;
   int split_k;    // >= 1; > 1 requires atomic f32 output
+  int bulk_red;   // transposed fp32 atomic output via cp.reduce.async.bulk from a staged tile (decode products)
+  int stream_k;   // 1: k-block units split evenly over the CTAs (see WorkIter); atomic f32 output, split_k == 1
   int epi;
   int c_f32, trans_c, accumulate, atomic;
   int bias_per_m;

@@ -374,8 +374,8 @@ __device__ __forceinline__ float act_grad(int act, float g) {
 // gate at gu[r*ld + c], up at gu[r*ld + up_off + c] (up_off < 0: ungated), out[r*out_ld + c]; cols % 8 == 0.
 __global__ void act_mul_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict__ out, long long rows, int cols,
                                    long long ld, long long up_off, long long out_ld, int act) {
+  if (threadIdx.x == 0) pdl_trigger();   // dependents may become resident (and prefetch) right away
   pdl_wait();   // no-op unless launched with the programmatic-serialization attribute (rollout decode chain)
-  if (threadIdx.x == 0) pdl_trigger();
   const int nvec = cols >> 3;
   const long long total = rows * nvec;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -597,6 +597,7 @@ static inline int grid_for(long long work, int block, int cap_mult = 8) {
   return (int)g;
 }
 
+void trace_install_rowops(unsigned long long* p) { trace_install_tu(p); }
 }  // namespace iadr1
 
 using namespace iadr1;

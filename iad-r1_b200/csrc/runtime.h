@@ -20,6 +20,9 @@ namespace iadr1 {
 // Every kernel launched this way executes `pdl_wait()` before touching data its predecessor produces.
 bool pdl_enabled();
 void pdl_set(bool on);
+void trace_install_decode(unsigned long long* p);
+void trace_install_gemm(unsigned long long* p);
+void trace_install_rowops(unsigned long long* p);
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
@@ -42,7 +45,30 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
 
 #if defined(__CUDACC__)
 namespace iadr1 {
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Decode-chain timeline probe (tools/decode_probe.py): when a trace buffer is installed, thread 0 of CTA 0 of every
+// kernel records %globaltimer on reaching the dependency wait (= how early the CTA was resident) and on leaving it
+// (= the instant its predecessor finished); successive "leave" stamps are the per-kernel critical-path times INSIDE
+// the CUDA graph. buf[0] = record count, records {reach, leave} from buf[2]. One pointer copy per translation unit.
+static __device__ unsigned long long* g_trace_buf = nullptr;
+static inline void trace_install_tu(unsigned long long* p) { cudaMemcpyToSymbol(g_trace_buf, &p, sizeof(p)); }
+__device__ __forceinline__ void pdl_wait() {
+  unsigned long long* tb = nullptr;
+  unsigned long long t0 = 0;
+  if (threadIdx.x == 0 && (blockIdx.x | blockIdx.y | blockIdx.z) == 0) {
+    tb = g_trace_buf;
+    if (tb) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (tb) {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    const unsigned long long i = atomicAdd(tb, 1ull);
+    if (i < 8190ull) {
+      tb[2 + 2 * i] = t0;
+      tb[3 + 2 * i] = t1;
+    }
+  }
+}
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 }  // namespace iadr1
 #endif

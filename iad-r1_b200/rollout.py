@@ -72,22 +72,30 @@ class RolloutEngine:
             self.nsplit = max(1, min(32, (p_max + c_max + 127) // 128))   # scalar kernel: one 128-key chunk per CTA
         self.part = torch.zeros(R, t.num_heads, self.nsplit, hd + 2, dtype=f32, device=dev)
         self.tickets = torch.zeros(R * nkv, dtype=i32, device=dev)
-        self.gu = torch.zeros(R, 2 * I, dtype=bf16, device=dev)
+        # fp32 gate|up accumulator of the stream-K product; decode_silu_mul_f32 leaves it zero for the next layer
+        self.block_n = max(16, ops.ceil_to(R, 16))
+        self.co_resident = os.environ.get("IADR1_DECODE_CORES", "0") != "0" and self.block_n <= 128
+        self.no_bulk_red = os.environ.get("IADR1_DECODE_BULKRED", "1") == "0"
+        self.gu_mode = os.environ.get("IADR1_DECODE_GU", "streamk")      # streamk | f32 | bf16 (probe A/B)
+        self.gu = torch.zeros(R, 2 * I, dtype=bf16 if self.gu_mode == "bf16" else f32, device=dev)
         self.act = torch.zeros(R, I, dtype=bf16, device=dev)
         self.logits = torch.zeros(R, V, dtype=f32, device=dev)
         self.max_pos = p_max + c_max + 8
         self.cos_tab, self.sin_tab = decode_rope_table(t, self.max_pos, dev)
-        self.block_n = max(16, ops.ceil_to(R, 16))
         self._graph = None
         self._seed = 0
         self.replays = 0            # graph replays so far (bench.py counts kernels = replays * kernels_per_step)
         self.kernels_per_step = 0
 
     # ---------------------------------------------------------------------------------------------------------------
-    def _skinny(self, W, x, out, split_k=1, atomic=False, bias=None):
-        """out[R, F] (+)= x[R, K] @ W[F, K]^T with W as the 128-row MMA operand (swap-AB), transposed store."""
+    def _skinny(self, W, x, out, split_k=1, atomic=False, bias=None, stream_k=False):
+        """out[R, F] (+)= x[R, K] @ W[F, K]^T with W as the 128-row MMA operand (swap-AB), transposed store.
+        stream_k: the weight's k-blocks are spread evenly over all SMs (fp32 atomics into `out`)."""
+        if stream_k:
+            split_k, atomic = 1, True
         L.gemm(W, x, out=out, trans_out=True, split_k=split_k, atomic=atomic or split_k > 1, bias=bias, bias_per_m=True,
-               block_n=self.block_n, a_static=True)
+               block_n=self.block_n, a_static=True, stream_k=stream_k, co_resident=self.co_resident,
+               no_bulk_red=self.no_bulk_red)
 
     def _head_and_sample(self, first: int):
         t, p, lib = self.cfg.text, self.vlm.p, L.lib()
@@ -130,8 +138,12 @@ class RolloutEngine:
             self._skinny(p[b + "o.weight"], self.attn, self.h, split_k=sk_o, atomic=True)        # h += attn @ Wo^T
             L.check(lib.iadr1_rmsnorm_f32in(self.h.data_ptr(), p[b + "ln2.weight"].data_ptr(), self.xn.data_ptr(), R, H,
                                             t.rms_norm_eps, None, 0, s), "rmsnorm_f32in")
-            self._skinny(p[b + "gate_up.weight"], self.xn, self.gu)
-            ops.act_mul_fwd(self.gu, I, ops.ACT_SILU, gated=True, out=self.act)
+            if self.gu_mode == "bf16":
+                self._skinny(p[b + "gate_up.weight"], self.xn, self.gu)
+                ops.act_mul_fwd(self.gu, I, ops.ACT_SILU, gated=True, out=self.act)
+            else:
+                self._skinny(p[b + "gate_up.weight"], self.xn, self.gu, atomic=True, stream_k=self.gu_mode == "streamk")
+                L.check(lib.iadr1_decode_silu_mul_f32(self.gu.data_ptr(), self.act.data_ptr(), R, I, s), "decode_silu_mul_f32")
             self._skinny(p[b + "down.weight"], self.act, self.h, split_k=sk_d, atomic=True)      # h += mlp
         self._head_and_sample(first=0)
         L.check(lib.iadr1_decode_advance(self.state.data_ptr(), s), "decode_advance")
@@ -150,6 +162,7 @@ class RolloutEngine:
         self._seed = int(seed)
         self.state.zero_()
         self.finished.zero_()
+        self.gu.zero_()
         self.out_tokens.fill_(self.cfg.pad_token_id)
         plen = np.zeros(self.R, dtype=np.int32)
         delta = np.zeros(self.R, dtype=np.int32)

@@ -52,6 +52,9 @@ typedef struct iadr1_gemm_t {
   const float* lse; const float* gscale;
   int block_n, stages, max_ctas;     /* 0 = library heuristics */
   int a_static;                      /* A (weights) is not produced by the preceding kernel: prefetchable under PDL */
+  int stream_k;                      /* split the K-block units evenly over all SMs (atomic fp32 C, split_k = 1) */
+  int no_bulk_red;                   /* probes: force per-lane atomics instead of bulk reductions for transposed fp32 atomic C */
+  int co_resident;                   /* decode chain: <= 113 KB smem, <= 128 regs, minimal TMEM so two CTAs fit per SM */
 } iadr1_gemm_t;
 int iadr1_gemm_bf16(const iadr1_gemm_t* desc, void* stream);
 /* block_n the library would choose for an N-wide product (sizes the EPI_LSE partial buffers). */
@@ -61,6 +64,10 @@ int iadr1_gemm_pick_block_n(int N, int b_mn);
 int iadr1_set_pdl(int on);
 /* Live roofline support: time every (non-graph-captured) GEMM launch with CUDA events on its own stream and count its
  * algorithmic FLOPs. Collect after a device synchronise.                                                            */
+/* Decode-chain timeline probe: op 1 installs + clears a device trace buffer (thread 0 of CTA 0 of every PDL-aware
+ * kernel then stamps %globaltimer before / after its dependency wait), op 0 removes it, op 2 copies it to `out`
+ * (word 0 = record count, records {reach, leave} from word 2). Diagnostics only; off by default.                   */
+int iadr1_trace(int op, unsigned long long* out, int max_words);
 int iadr1_gemm_profile_enable(int on);
 int iadr1_gemm_profile_collect(double* total_ms, double* total_flops, double* max_launch_ms, long long* launches,
                                const char* csv_path /* optional: per-shape breakdown */);
@@ -142,6 +149,9 @@ int iadr1_decode_attention_fused(const float* qkv, const float* cos_tab, const f
 int iadr1_sample(const float* logits, int rows, int V, float temperature, int top_k, float top_p,
                  unsigned long long seed, int* state, int* tok, int* finished, int* out_tokens, int c_max, int eos_id,
                  int pad_id, int forbid_eos, int first, void* stream);
+/* Decode-step SwiGLU on the fp32 gate|up accumulator [rows][2*cols] of the stream-K gate_up product (Qwen2MLP,
+ * modeling_qwen2_5_vl.py:611-624): out bf16 [rows][cols]; the accumulator is zeroed for the next layer.              */
+int iadr1_decode_silu_mul_f32(float* gu, void* out, int rows, int cols, void* stream);
 int iadr1_decode_advance(int* state, void* stream);
 
 #ifdef __cplusplus

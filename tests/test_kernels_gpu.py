@@ -65,6 +65,30 @@ def test_gemm_epilogues(ops):
           x.float() @ w.float().t() + bm.float(), 1e-5, "decode swap-AB")
 
 
+@pytest.mark.parametrize("F,K,R", [(22016, 2048, 64), (2560, 2048, 64), (2048, 11008, 16), (1000, 200, 8), (128, 64, 24)])
+def test_gemm_stream_k(ops, F, K, R):
+    """Stream-K schedule of the decode products (k-block units spread evenly over the SMs, fp32 atomics, bias added once
+    per tile) and the fp32 SwiGLU that consumes + clears the accumulator."""
+    from iad_r1_b200 import lib as L
+    torch.manual_seed(F + K)
+    w, x, bm = rnd(F, K, scale=0.05), rnd(R, K), rnd(F)
+    out = torch.zeros(R, F, device="cuda")
+    L.gemm(w, x, out=out, trans_out=True, atomic=True, stream_k=True, block_n=max(16, (R + 15) // 16 * 16), bias=bm,
+           bias_per_m=True, a_static=True, co_resident=(F % 256 == 0))   # + the two-CTAs-per-SM decode variant
+    close(out, x.float() @ w.float().t() + bm.float(), 1e-4, "stream-k")
+    with pytest.raises(L.NativeLibraryError):
+        L.gemm(w, x, trans_out=True, stream_k=True)       # needs atomic fp32 output
+    if F % 8 == 0:
+        I = F // 2
+        gu = out.clone()
+        act = torch.empty(R, I, dtype=bf16, device="cuda")
+        L.check(L.lib().iadr1_decode_silu_mul_f32(gu.data_ptr(), act.data_ptr(), R, I, L.stream_ptr()))
+        g, u = out[:, :I].to(bf16).float(), out[:, I:].to(bf16).float()
+        want = (torch.nn.functional.silu(g).to(bf16).float() * u).to(bf16)
+        close(act, want, 2 ** -7, "silu_mul_f32")
+        assert (gu == 0).all(), "accumulator must be cleared"
+
+
 def test_gemm_empty_and_errors(ops):
     from iad_r1_b200 import lib as L
     a, b = rnd(0, 64), rnd(16, 64)

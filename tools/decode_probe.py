@@ -48,13 +48,53 @@ def timeit(fn, n=20, reps=10):
     return e0.elapsed_time(e1) / (n * reps) * 1000  # us
 
 
+NEW = int(os.environ.get("PROBE_NEW_TOKENS", "64"))
 for graph in (False, True):
     eng = RolloutEngine(vlm, groups, G, 320, C, forbid_eos=True, use_cuda_graph=graph)
-    out, st = eng.generate(encs, seed=1, max_new_tokens=64)
-    out, st = eng.generate(encs, seed=2, max_new_tokens=64)
+    out, st = eng.generate(encs, seed=1, max_new_tokens=NEW)
+    out, st = eng.generate(encs, seed=2, max_new_tokens=NEW)
     print(f"R={eng.R} layers={layers} graph={graph}: {st['decode_ms'] / st['steps'] * 1000:.1f} us per decode step "
           f"({st['decode_ms'] / st['steps'] * 1000 / layers:.1f} us per layer incl. head)", flush=True)
 
+if os.environ.get("PROBE_TRACE"):
+    # in-graph timeline: per-kernel critical-path time = gap between successive dependency-resolved stamps
+    import ctypes, numpy as np
+    lib = L.lib()
+    nwords = 2 + 2 * 8190
+    buf = (ctypes.c_ulonglong * nwords)()
+    nk = eng.kernels_per_step
+    names = ["embed"] + ["rms1", "qkv", "attn", "o", "rms2", "gate_up", "silu", "down"] * layers + ["rms_f", "lm_head", "sample", "advance"]
+    assert nk == len(names), (nk, len(names))
+    eng.state[0] = int(os.environ.get("PROBE_CTX_STEP", "256"))
+    torch.cuda.synchronize()
+    L.check(lib.iadr1_trace(1, None, 0))
+    reps = 20
+    for _ in range(reps):
+        eng._graph.replay()
+    torch.cuda.synchronize()
+    L.check(lib.iadr1_trace(2, buf, nwords))
+    L.check(lib.iadr1_trace(0, None, 0))
+    a = np.frombuffer(buf, dtype=np.uint64)
+    n = int(a[0])
+    rec = a[2:2 + 2 * n].reshape(n, 2).astype(np.int64)
+    assert n == reps * nk, (n, reps, nk)
+    rec = rec.reshape(reps, nk, 2)[2:]                      # drop warm-up replays
+    leave = rec[:, :, 1]
+    dur = np.diff(np.concatenate([leave, leave[:, -1:] ], 1), axis=1)[:, :-1]     # kernel k: leave[k+1] - leave[k]
+    early = (rec[:, :, 1] - rec[:, :, 0])                    # how long CTA 0 sat resident before its dependency resolved
+    agg = {}
+    for k, nm in enumerate(names[:-1]):
+        agg.setdefault(nm, []).append((dur[:, k].mean() / 1e3, early[:, k].mean() / 1e3))
+    print(f"in-graph timeline at completion step {int(eng.state[0])} (R={eng.R}, {layers} layers), us: critical-path time | resident-before-ready")
+    tot = 0
+    for nm, v in agg.items():
+        d, e = np.mean([x[0] for x in v]), np.mean([x[1] for x in v])
+        tot += d * len(v)
+        print(f"  {nm:8s} x{len(v):3d}  {d:7.2f} | {e:6.2f}")
+    print(f"  step total {(leave[:, -1] - leave[:, 0]).mean() / 1e3:.1f} us (sum of parts {tot:.1f})")
+    sys.exit(0)
+if os.environ.get("PROBE_STEP_ONLY"):
+    sys.exit(0)
 t, p, lib = cfg.text, vlm.p, L.lib()
 
 
@@ -81,15 +121,17 @@ items = {
         eng.row_plen.data_ptr(), eng.part.data_ptr(), eng.tickets.data_ptr(), eng.attn.data_ptr(), R, nq, nkv, hd, eng.p_max,
         eng.c_max, eng.nsplit, eng.max_pos, hd ** -0.5, L.stream_ptr()),
     f"gemm o split{sk_o}": lambda: eng._skinny(p[b + "o.weight"], eng.attn, eng.h, split_k=sk_o, atomic=True),
-    "gemm gate_up": lambda: eng._skinny(p[b + "gate_up.weight"], eng.xn, eng.gu),
-    "gemm gate_up 86ctas": lambda: L.gemm(p[b + "gate_up.weight"], eng.xn, out=eng.gu, trans_out=True, block_n=eng.block_n, max_ctas=86),
+    "gemm gate_up stream-k f32 atomic": lambda: eng._skinny(p[b + "gate_up.weight"], eng.xn, eng.gu, atomic=True, stream_k=True),
+    "gemm qkv stream-k": lambda: eng._skinny(p[b + "qkv.weight"], eng.xn, eng.qkv, stream_k=True, bias=p[b + "qkv.bias"]),
+    "gemm o stream-k": lambda: eng._skinny(p[b + "o.weight"], eng.attn, eng.h, stream_k=True),
+    "gemm down stream-k": lambda: eng._skinny(p[b + "down.weight"], eng.act, eng.h, stream_k=True),
+    "silu_mul_f32": lambda: lib.iadr1_decode_silu_mul_f32(eng.gu.data_ptr(), eng.act.data_ptr(), R, I, L.stream_ptr()),
     "gemm gate_up split2 f32 atomic": lambda: L.gemm(p[b + "gate_up.weight"], eng.xn, out=gu32, trans_out=True, split_k=2, atomic=True, block_n=eng.block_n, a_static=True),
     "gemm gate_up split3 f32 atomic": lambda: L.gemm(p[b + "gate_up.weight"], eng.xn, out=gu32, trans_out=True, split_k=3, atomic=True, block_n=eng.block_n, a_static=True),
     "gemm gate_up f32 no split": lambda: L.gemm(p[b + "gate_up.weight"], eng.xn, out=gu32, trans_out=True, block_n=eng.block_n, a_static=True),
     "gemm qkv split3": lambda: eng._skinny(p[b + "qkv.weight"], eng.xn, eng.qkv, split_k=3, atomic=True, bias=p[b + "qkv.bias"]),
     "gemm down split4": lambda: eng._skinny(p[b + "down.weight"], eng.act, eng.h, split_k=4, atomic=True),
     "gemm down split18": lambda: eng._skinny(p[b + "down.weight"], eng.act, eng.h, split_k=18, atomic=True),
-    "act_mul": lambda: ops.act_mul_fwd(eng.gu, I, ops.ACT_SILU, gated=True, out=eng.act),
     f"gemm down split{sk_d}": lambda: eng._skinny(p[b + "down.weight"], eng.act, eng.h, split_k=sk_d, atomic=True),
     "gemm lm_head": lambda: eng._skinny(vlm.params.lm_head, eng.xn, eng.logits),
     "sample": lambda: lib.iadr1_sample(eng.logits.data_ptr(), R, t.vocab_size, 0.9, 50, 0.9, 1, eng.state.data_ptr(), eng.tok.data_ptr(),
