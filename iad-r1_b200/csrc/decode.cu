@@ -628,14 +628,37 @@ __global__ void __launch_bounds__(128) decode_attn_mma_kernel(
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
-  // chunk 0 holds cache rows written by earlier decode steps / the prefill: requested before the PDL wait
+  // chunks 0 and 1 hold cache rows written by earlier decode steps / the prefill: requested before the PDL wait
   if (nchunks > 0) stage(0);
+  if (nchunks > 1) stage(1);
   pdl_wait();
   // ---- rotated, pre-scaled queries as bf16 rows (row = head within the group) ----
-  for (int i = threadIdx.x; i < 16 * HD; i += 128) {
-    const int h = i / HD, d = i % HD;
-    const float v = (h < gq) ? rot(xrow + (long long)(kvh * gq + h) * HD, d) * scale : 0.f;
-    sQ[h * HD + ((((d >> 3) ^ (h & 7)) << 3) | (d & 7))] = __float2bfloat16(v);
+  {
+    // thread = one head-dim column d of up to MAXG heads: all global loads are issued before the first use (one L2
+    // round trip instead of one per head)
+    constexpr int TPH = 128 / HD;               // threads per column group
+    constexpr int HPT = MAXG / TPH;             // heads per thread
+    const int d = threadIdx.x % HD, hsel = threadIdx.x / HD;
+    const int dp = d < HALF ? d + HALF : d - HALF;
+    const float cd = bf16r(cs[d]), sd = bf16r(sn[d]);
+    float xv[HPT], xpv[HPT];
+#pragma unroll
+    for (int hh = 0; hh < HPT; ++hh) {
+      const int h = hh * TPH + hsel;
+      const float* xh = xrow + (long long)(kvh * gq + min(h, gq - 1)) * HD;
+      xv[hh] = xh[d];
+      xpv[hh] = xh[dp];
+    }
+#pragma unroll
+    for (int hh = 0; hh < HPT; ++hh) {
+      const int h = hh * TPH + hsel;
+      const float a = bf16r(bf16r(xv[hh]) * cd);
+      const float xp = bf16r(xpv[hh]);
+      const float b = bf16r((d < HALF ? -xp : xp) * sd);
+      const float v = (h < gq) ? bf16r(a + b) * scale : 0.f;
+      sQ[h * HD + ((((d >> 3) ^ (h & 7)) << 3) | (d & 7))] = __float2bfloat16(v);
+      sQ[(h + 8) * HD + ((((d >> 3) ^ (h & 7)) << 3) | (d & 7))] = __float2bfloat16(0.f);   // padding rows 8..15
+    }
   }
   const bool has_new = (ctx - 1 >= k0) && (ctx - 1 < k1);
   if (has_new && warp == 3) {
@@ -670,7 +693,6 @@ __global__ void __launch_bounds__(128) decode_attn_mma_kernel(
   float mrun = -INFINITY, lrun = 0.f;      // of query row lane / 4 (rows >= 8 are padding)
 
   for (int c = 0; c < nchunks; ++c) {
-    if (c + 1 < nchunks) stage(c + 1);
     bf16* sK = sKV + (c & 1) * STAGE;
     bf16* sV = sK + CK * HD;
     const int cbase = k0 + c * CK;
@@ -742,7 +764,8 @@ __global__ void __launch_bounds__(128) decode_attn_mma_kernel(
         mma_bf16_16816(oacc[nb + 1], pa, b[2], b[3]);
       }
     }
-    __syncthreads();                            // buffer (c & 1) is re-filled by the next iteration's stage(c + 2)
+    __syncthreads();                            // every warp is done with buffer (c & 1):
+    if (c + 2 < nchunks) stage(c + 2);          // re-fill it two chunks ahead
   }
   // ---- merge the 4 warps (rows = heads < gq live in c0/c1 of the lanes with lane/4 == head); staging memory re-used
   float (*sm_mrg)[MAXG][HD + 2] = reinterpret_cast<float (*)[MAXG][HD + 2]>(sm_kv_raw);

@@ -308,7 +308,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const uint32_t tx_bytes = a_bytes + b_bytes;
       auto load_a = [&](const TileInfo& ti, int kb, int stg, int zlo, int zhi) {
         uint8_t* sa = smem + (size_t)stg * stage_bytes;
-        if (!g.a_mn) {
+        if (g.epi == EPI_SWIGLU) {
+          // rows [f0, f0 + 64) of the gate block and of the up block form ONE 128-row MMA tile (TMEM lanes 0-63 / 64-127)
+          const int f0 = ti.m0 >> 1;
+          tma_load_4d(sa, &tmA, &full_bar[stg], kb * BK, f0, zlo, zhi);
+          tma_load_4d(sa + 8192, &tmA, &full_bar[stg], kb * BK, g.up_row_off + f0, zlo, zhi);
+        } else if (!g.a_mn) {
           tma_load_4d(sa, &tmA, &full_bar[stg], kb * BK, ti.m0, zlo, zhi);
         } else {
           tma_load_4d(sa, &tmA, &full_bar[stg], ti.m0, kb * BK, zlo, zhi);
@@ -420,12 +425,46 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       float run_max = -INFINITY, run_sum = 0.f, tgt = 0.f, row_lse = 0.f, row_g = 0.f;
       bool tgt_found = false;
       int label = -1;
-      if (g.epi != EPI_STORE && m < g.M) {
+      if ((g.epi == EPI_LSE || g.epi == EPI_DLOGITS) && m < g.M) {
         label = g.labels[m];
         if (g.epi == EPI_DLOGITS) {
           row_lse = g.lse[m];
           row_g = g.gscale[m];
         }
+      }
+      if (g.epi == EPI_SWIGLU) {
+        // out[n][f] = bf16(silu(gate)) * up for the tile's 64 features: both halves meet in the staging tile
+        float* sC = reinterpret_cast<float*>(smem + (size_t)g.stages * stage_bytes + 512);
+        const int ml = q * 32 + lane;
+        for (int c0 = 0; c0 < g.block_n; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(taddr + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) sC[(c0 + j) * BM + ml] = have_acc ? g.alpha * __uint_as_float(v[j]) : 0.f;
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[as]);
+        named_bar_sync(1, 128);
+        const int f0 = ti.m0 >> 1;
+        const int nrows = min(g.block_n, g.N - ti.n0);
+        __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(g.C);
+        for (int i = threadIdx.x - 128; i < nrows * 32; i += 128) {
+          const int n = i >> 5, f = (i & 31) * 2;
+          const float2 gg = *reinterpret_cast<const float2*>(sC + n * BM + f);
+          const float2 uu = *reinterpret_cast<const float2*>(sC + n * BM + 64 + f);
+          auto act = [](float gv, float uv) {
+            gv = __bfloat162float(__float2bfloat16(gv));
+            const float sv = __bfloat162float(__float2bfloat16(gv / (1.f + __expf(-gv))));
+            return sv * __bfloat162float(__float2bfloat16(uv));
+          };
+          if (f0 + f < (g.M >> 1))
+            *reinterpret_cast<__nv_bfloat162*>(outp + (long long)(ti.n0 + n) * g.ldc + f0 + f) =
+                __floats2bfloat162_rn(act(gg.x, uu.x), act(gg.y, uu.y));
+        }
+        named_bar_sync(1, 128);
+        if (++as == 2) { as = 0; aph ^= 1; }
+        continue;
       }
       if (g.bulk_red) {
         // Transposed fp32 accumulate-into-C via the TMA unit: the tile is staged as sC[n][128 m] (lanes = consecutive m:
@@ -692,6 +731,13 @@ int launch_gemm(const iadr1_gemm_t& d, cudaStream_t stream) {
   g.residual = reinterpret_cast<const __nv_bfloat16*>(d.residual);
   g.labels = d.labels; g.part_max = d.part_max; g.part_sum = d.part_sum; g.tgt_logit = d.tgt_logit;
   g.lse = d.lse; g.gscale = d.gscale;
+  g.up_row_off = d.up_row_off;
+  if (g.epi == EPI_SWIGLU) {
+    // d.M = 2 * I rows of the fused gate|up weight; tile t covers features [64 t, 64 t + 64) of both halves
+    if (g.a_mn || g.b_mn || g.batch != 1 || g.split_k != 1 || g.atomic || g.c_f32 || d.stream_k || g.kmode || g.skip_mode ||
+        (d.M % 128) || d.up_row_off * 2 != d.M || (d.ldc % 2))
+      return set_error("gemm: swiglu epilogue needs K-major operands, bf16 C, M = 2 * up_row_off, M %% 128 == 0");
+  }
   g.stream_k = d.stream_k;
   if (g.stream_k && !(g.atomic && g.c_f32 && g.batch == 1 && g.kmode == 0 && g.skip_mode == 0 && g.split_k == 1 &&
                       g.epi == EPI_STORE))
@@ -719,7 +765,7 @@ int launch_gemm(const iadr1_gemm_t& d, cudaStream_t stream) {
   // transposed fp32 atomic accumulation goes through bulk reductions (needs a [block_n][128] fp32 staging tile)
   g.bulk_red = g.trans_c && g.atomic && g.c_f32 && g.epi == EPI_STORE && g.residual == nullptr && g.batch == 1 &&
                (g.M % 4 == 0) && (g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) && !d.no_bulk_red;
-  const int epi_bytes = g.bulk_red ? g.block_n * BM * 4 : 0;
+  const int epi_bytes = (g.bulk_red || g.epi == EPI_SWIGLU) ? g.block_n * BM * 4 : 0;
   const int smem_budget = (d.co_resident ? 113 : 227) * 1024 - 1024 - 512 - epi_bytes;
   int stages = smem_budget / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
@@ -735,7 +781,7 @@ int launch_gemm(const iadr1_gemm_t& d, cudaStream_t stream) {
   // dims: {contiguous, rows, batch_lo, batch_hi}
   if (!g.a_mn)
     rc = make_map(&tmA, d.A, d.K, d.M, g.batch_lo, nb_hi, d.lda, d.a_bs_lo ? d.a_bs_lo : d.lda,
-                  d.a_bs_hi ? d.a_bs_hi : d.lda, BK, BM);
+                  d.a_bs_hi ? d.a_bs_hi : d.lda, BK, g.epi == EPI_SWIGLU ? 64 : BM);
   else
     rc = make_map(&tmA, d.A, d.M, d.K, g.batch_lo, nb_hi, d.lda, d.a_bs_lo ? d.a_bs_lo : d.lda,
                   d.a_bs_hi ? d.a_bs_hi : d.lda, 64, BK);
@@ -761,6 +807,7 @@ int launch_gemm(const iadr1_gemm_t& d, cudaStream_t stream) {
   const int tiles_n = (g.N + g.block_n - 1) / g.block_n;
   const long long total = (long long)tiles_m * tiles_n * g.split_k * g.batch;
   int grid = (int)(total < (long long)num_sms() ? total : num_sms());
+  if (d.co_resident) grid = (int)(total < 2LL * num_sms() ? total : 2LL * num_sms());   // two CTAs per SM stream concurrently
   if (g.stream_k) grid = num_sms();   // every SM takes an equal run of k-block units (K / 64 >= 1 each tile)
   if (d.max_ctas > 0 && grid > d.max_ctas) grid = d.max_ctas;
   cudaEvent_t pe0, pe1;

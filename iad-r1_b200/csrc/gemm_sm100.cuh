@@ -8,6 +8,7 @@ namespace iadr1 {
 enum GemmEpilogue : int {
   EPI_STORE = 0,     // C = alpha * acc (+ bias) (+ residual), bf16 or f32, optional f32 accumulate / atomic / transposed
   EPI_LSE = 1,       // per-row partial (max, sum exp) over this tile's columns + target-logit pick  (fused lm_head)
+  EPI_SWIGLU = 3,    // A = [gate rows; up rows] (M = 2I): C^T[n][f] = bf16(silu(gate_f . b_n)) * (up_f . b_n), bf16 (decode MLP)
   EPI_DLOGITS = 2,   // C = (exp(alpha*acc - lse[m]) - [n == label[m]]) * gscale[m]  as bf16         (lm_head bwd)
 };
 
@@ -24,6 +25,7 @@ struct GemmArgs {
   int skip_mode;  // 1: skip output tiles with n0 > m0 + 127 + causal_off (fully masked)
   int causal_off;
   int split_k;    // >= 1; > 1 requires atomic f32 output
+  int up_row_off; // EPI_SWIGLU: row offset of the up block inside A (= I)
   int bulk_red;   // transposed fp32 atomic output via cp.reduce.async.bulk from a staged tile (decode products)
   int stream_k;   // 1: k-block units split evenly over the CTAs (see WorkIter); atomic f32 output, split_k == 1
   int epi;

@@ -36,7 +36,7 @@ class GemmDesc(C.Structure):
         ("lse_tiles_n", C.c_int),
         ("lse", C.c_void_p), ("gscale", C.c_void_p),
         ("block_n", C.c_int), ("stages", C.c_int), ("max_ctas", C.c_int), ("a_static", C.c_int),
-        ("stream_k", C.c_int), ("no_bulk_red", C.c_int), ("co_resident", C.c_int),
+        ("stream_k", C.c_int), ("up_row_off", C.c_int), ("no_bulk_red", C.c_int), ("co_resident", C.c_int),
     ]
 
 
@@ -170,6 +170,26 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None, *, b
     d.block_n, d.stages, d.max_ctas, d.a_static = block_n, stages, max_ctas, int(a_static)
     d.stream_k, d.co_resident, d.no_bulk_red = int(stream_k), int(co_resident), int(no_bulk_red)
     check(lib().iadr1_gemm_bf16(C.byref(d), stream_ptr()), "iadr1_gemm_bf16")
+    return out
+
+
+def gemm_swiglu(w_gate_up: torch.Tensor, x: torch.Tensor, out: torch.Tensor, *, block_n: int = 0, a_static: bool = True,
+                co_resident: bool = True) -> torch.Tensor:
+    """Decode MLP front half in one launch: out[R, I] = bf16(silu(x @ Wg^T)) * (x @ Wu^T) with w_gate_up = [Wg; Wu]
+    ([2I, K] row-major, the training layout) as the 128-row MMA operand (64 gate + 64 up rows per tile)."""
+    M2, K = w_gate_up.shape
+    R, K2 = x.shape
+    if K != K2 or tuple(out.shape) != (R, M2 // 2) or out.dtype != torch.bfloat16:
+        raise ValueError("gemm_swiglu: shape/dtype mismatch")
+    d = GemmDesc()
+    d.M, d.N, d.K = M2, R, K
+    d.batch = d.batch_lo = d.b_lo_div = 1
+    d.A, d.lda, d.a_mn = _mat(w_gate_up, "w_gate_up")
+    d.B, d.ldb, d.b_mn = _mat(x, "x")
+    d.C, d.ldc = out.data_ptr(), out.stride(0)
+    d.split_k, d.alpha, d.epi, d.up_row_off = 1, 1.0, 3, M2 // 2
+    d.block_n, d.a_static, d.co_resident = block_n, int(a_static), int(co_resident)
+    check(lib().iadr1_gemm_bf16(C.byref(d), stream_ptr()), "iadr1_gemm_bf16(swiglu)")
     return out
 
 

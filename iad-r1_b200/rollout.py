@@ -76,8 +76,8 @@ class RolloutEngine:
         self.block_n = max(16, ops.ceil_to(R, 16))
         self.co_resident = os.environ.get("IADR1_DECODE_CORES", "0") != "0" and self.block_n <= 128
         self.no_bulk_red = os.environ.get("IADR1_DECODE_BULKRED", "1") == "0"
-        self.gu_mode = os.environ.get("IADR1_DECODE_GU", "streamk")      # streamk | f32 | bf16 (probe A/B)
-        self.gu = torch.zeros(R, 2 * I, dtype=bf16 if self.gu_mode == "bf16" else f32, device=dev)
+        self.gu_mode = os.environ.get("IADR1_DECODE_GU", "fused")      # fused | streamk | f32 | bf16 (probe A/B)
+        self.gu = torch.zeros(R, 2 * I, dtype=f32 if self.gu_mode in ("streamk", "f32") else bf16, device=dev)
         self.act = torch.zeros(R, I, dtype=bf16, device=dev)
         self.logits = torch.zeros(R, V, dtype=f32, device=dev)
         self.max_pos = p_max + c_max + 8
@@ -138,7 +138,10 @@ class RolloutEngine:
             self._skinny(p[b + "o.weight"], self.attn, self.h, split_k=sk_o, atomic=True)        # h += attn @ Wo^T
             L.check(lib.iadr1_rmsnorm_f32in(self.h.data_ptr(), p[b + "ln2.weight"].data_ptr(), self.xn.data_ptr(), R, H,
                                             t.rms_norm_eps, None, 0, s), "rmsnorm_f32in")
-            if self.gu_mode == "bf16":
+            if self.gu_mode.startswith("fused"):
+                L.gemm_swiglu(p[b + "gate_up.weight"], self.xn, self.act, block_n=self.block_n,
+                              co_resident=self.gu_mode == "fused")
+            elif self.gu_mode == "bf16":
                 self._skinny(p[b + "gate_up.weight"], self.xn, self.gu)
                 ops.act_mul_fwd(self.gu, I, ops.ACT_SILU, gated=True, out=self.act)
             else:

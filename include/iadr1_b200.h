@@ -47,12 +47,14 @@ typedef struct iadr1_gemm_t {
   const void* bias; int bias_per_m;  /* bf16 [N] (or [M] when bias_per_m) */
   const void* residual;              /* bf16, indexed like C */
   int kmode, skip_mode, causal_off;  /* causal trimming for attention products, see gemm_sm100.cuh */
-  int epi;                           /* 0 store, 1 row log-sum-exp partials, 2 softmax-gradient (lm_head backward) */
+  int epi;                           /* 0 store, 1 row log-sum-exp partials, 2 softmax-gradient (lm_head backward), 3 SwiGLU */
   const int* labels; float* part_max; float* part_sum; float* tgt_logit; int lse_tiles_n;
   const float* lse; const float* gscale;
   int block_n, stages, max_ctas;     /* 0 = library heuristics */
   int a_static;                      /* A (weights) is not produced by the preceding kernel: prefetchable under PDL */
   int stream_k;                      /* split the K-block units evenly over all SMs (atomic fp32 C, split_k = 1) */
+  int up_row_off;                    /* epi 3 (decode SwiGLU): A holds gate rows [0, I) then up rows [I, 2I); M = 2I, up_row_off = I;
+                                        C is bf16 [N][ldc] with C[n][f] = silu(gate_f . b_n) * (up_f . b_n)            */
   int no_bulk_red;                   /* probes: force per-lane atomics instead of bulk reductions for transposed fp32 atomic C */
   int co_resident;                   /* decode chain: <= 113 KB smem, <= 128 regs, minimal TMEM so two CTAs fit per SM */
 } iadr1_gemm_t;

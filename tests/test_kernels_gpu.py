@@ -89,6 +89,20 @@ def test_gemm_stream_k(ops, F, K, R):
         assert (gu == 0).all(), "accumulator must be cleared"
 
 
+@pytest.mark.parametrize("I,K,R", [(11008, 2048, 64), (4864, 896, 56), (256, 128, 8)])
+def test_gemm_swiglu(ops, I, K, R):
+    """Decode MLP front half in one launch (gate and up rows of the fused weight share a 128-row MMA tile, SwiGLU in the
+    epilogue) vs the two-step torch form with the same bf16 rounding points as Qwen2MLP."""
+    from iad_r1_b200 import lib as L
+    torch.manual_seed(I + K)
+    w, x = rnd(2 * I, K, scale=0.05), rnd(R, K)
+    out = torch.empty(R, I, dtype=bf16, device="cuda")
+    L.gemm_swiglu(w, x, out, block_n=max(16, (R + 15) // 16 * 16))
+    gu = (x.float() @ w.float().t()).to(bf16).float()
+    want = (torch.nn.functional.silu(gu[:, :I]).to(bf16).float() * gu[:, I:]).to(bf16)
+    close(out, want, 2 ** -6, "swiglu")
+
+
 def test_gemm_empty_and_errors(ops):
     from iad_r1_b200 import lib as L
     a, b = rnd(0, 64), rnd(16, 64)

@@ -63,7 +63,10 @@ if os.environ.get("PROBE_TRACE"):
     nwords = 2 + 2 * 8190
     buf = (ctypes.c_ulonglong * nwords)()
     nk = eng.kernels_per_step
-    names = ["embed"] + ["rms1", "qkv", "attn", "o", "rms2", "gate_up", "silu", "down"] * layers + ["rms_f", "lm_head", "sample", "advance"]
+    per_layer = ["rms1", "qkv", "attn", "o", "rms2", "gate_up", "silu", "down"]
+    if eng.gu_mode.startswith("fused"):
+        per_layer.remove("silu")
+    names = ["embed"] + per_layer * layers + ["rms_f", "lm_head", "sample", "advance"]
     assert nk == len(names), (nk, len(names))
     eng.state[0] = int(os.environ.get("PROBE_CTX_STEP", "256"))
     torch.cuda.synchronize()
