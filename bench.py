@@ -283,14 +283,33 @@ def run_ours(args):
         hbm, tf_peak, src = peaks()
         roof = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel", "achieved": tfl.value / (tms.value / 1e3) / 1e12
                 if tms.value > 0 else None, "peak": tf_peak, "unit": "TFLOP/s", "peak_source": f"bf16_tflops_sustained, {src}",
-                "launches_timed": nl.value, "gemm_ms_per_step": tms.value / args.steps, "traffic": None}
+                "launches_timed": nl.value, "gemm_ms_per_step": tms.value / args.steps,
+                # DRAM bytes of ONE launch of the dominant training shape (decoder gate_up forward, M = 8786 tokens of two
+                # packed groups, N = 22016, K = 2048: 0.513 GB of operands + output) from the committed `ncu --set full`
+                # capture profiles/r01_gemm_full_ncu_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum)
+                "traffic": 0.165775e9 + 354.246656e6, "traffic_unit": "bytes per launch (gate_up fwd, ncu)"}
         roof["frac"] = roof["achieved"] / tf_peak if roof["achieved"] else None
+        # second roofline: the rollout decode step is HBM-bound - every decoder weight + the lm_head once per step, plus the
+        # KV cache of every row (prompt K/V once per group); algorithmic bytes per step / measured time per step
+        t_ = cfg.text
+        wd = t_.num_layers * (t_.qkv_dim * t_.hidden_size + t_.num_heads * t_.head_dim * t_.hidden_size
+                              + 3 * t_.hidden_size * t_.intermediate_size) * 2
+        wh = t_.vocab_size * t_.hidden_size * 2
+        kv_tok = 2 * t_.num_layers * t_.num_kv_heads * t_.head_dim * 2
+        p_len = len(encoded[0][1]["input_ids"])
+        kv_avg = (GA * p_len + GA * G * (Cl / 2.0)) * kv_tok
+        step_bytes = wd + wh + kv_avg
+        dec_ms = phases.get("rollout", float("nan")) / max(1, Cl)
+        dec = {"bound": "hbm", "kernel": "decode step (CUDA graph: 36 x [rmsnorm, qkv, attention, o, rmsnorm, gate_up+SwiGLU, down] + lm_head + sampler)",
+               "achieved": step_bytes / (dec_ms / 1e3) / 1e9, "peak": hbm, "unit": "GB/s", "peak_source": f"hbm_gbs, {src}",
+               "bytes_per_step": step_bytes, "ms_per_decode_step": dec_ms}
+        dec["frac"] = dec["achieved"] / hbm
         line = {"metric": "GRPO groups/sec (G=8)", "value": value, "unit": "groups/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, cfg, world),
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
                 "rollout": {"tok_per_s": world * rollout_tokens / args.steps / (phases.get("rollout", float("nan")) / 1e3),
-                            "rows_in_flight": GA * G, "ms_per_step": phases.get("rollout")},
+                            "rows_in_flight": GA * G, "ms_per_step": phases.get("rollout"), "roofline": dec},
                 "phase_ms_per_step": phases}
         if world == 1 and not args.no_cpu_baseline:
             try:

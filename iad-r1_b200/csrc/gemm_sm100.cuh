@@ -26,6 +26,7 @@ struct GemmArgs {
   int causal_off;
   int split_k;    // >= 1; > 1 requires atomic f32 output
   int up_row_off; // EPI_SWIGLU: row offset of the up block inside A (= I)
+  int raster_n;   // 1: consecutive tiles walk N first (A streamed once), 0: M first (B streamed once)
   int bulk_red;   // transposed fp32 atomic output via cp.reduce.async.bulk from a staged tile (decode products)
   int stream_k;   // 1: k-block units split evenly over the CTAs (see WorkIter); atomic f32 output, split_k == 1
   int epi;

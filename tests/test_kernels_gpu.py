@@ -59,6 +59,8 @@ def test_gemm_epilogues(ops):
     close(acc, want + 2.0, 1e-5, "accumulate")
     close(L.gemm(a, b, split_k=3, out_dtype=f32, bias=bias), want + bias.float(), 1e-5, "split-k atomic + bias once")
     close(L.gemm(a, b, trans_out=True), want.t(), 2 ** -7, "transposed store")
+    close(L.gemm(a, b, raster=2), want, 2 ** -7, "N-fastest tile order")
+    close(L.gemm(a, b, raster=1, bias=bias), want + bias.float(), 2 ** -7, "M-fastest tile order")
     w, x = rnd(2048, 1024), rnd(8, 1024)
     bm = rnd(2048)
     close(L.gemm(w, x, trans_out=True, split_k=4, out_dtype=f32, block_n=16, bias=bm, bias_per_m=True),

@@ -34,6 +34,32 @@ cases = [
     ("decode down stream... split-K bulk-reduce R=64", lambda: L.gemm(w_dn, ar, out=h32, trans_out=True, split_k=9, atomic=True, block_n=64, a_static=True)),
     ("decode lm_head R=64", lambda: L.gemm(w_head, xr, out=logits, trans_out=True, block_n=64, a_static=True)),
 ]
+if os.environ.get("TIME"):
+    # A/B of the tile order on the training shapes (CUDA events, 10 back-to-back launches; operands >> L2)
+    tcases = [
+        ("gate_up fwd", lambda r: L.gemm(x, w_gu, raster=r), 2.0 * M * 2 * I * H),
+        ("down fwd", lambda r: L.gemm(act, w_dn, raster=r), 2.0 * M * H * I),
+        ("gate_up dgrad", lambda r: L.gemm(dy, w_gu.t(), raster=r), 2.0 * M * 2 * I * H),
+        ("down dgrad", lambda r: L.gemm(x, w_dn.t(), raster=r), 2.0 * M * H * I),
+        ("gate_up wgrad", lambda r: L.gemm(dy.t(), x.t(), out=gw, accumulate=True, raster=r), 2.0 * M * 2 * I * H),
+        ("down wgrad", lambda r: L.gemm(x.t(), act.t(), out=gw.view(-1)[: H * I].view(H, I), accumulate=True, raster=r), 2.0 * M * H * I),
+    ]
+    for name, fn, fl in tcases:
+        line = f"{name:14s}"
+        for r in (1, 2, 0):
+            for _ in range(3):
+                fn(r)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                fn(r)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            line += f"  raster={r}: {ms * 1e3:7.1f} us {fl / ms / 1e9:7.1f} TFLOP/s"
+        print(line, flush=True)
+    sys.exit(0)
 for name, fn in cases:       # warm-up pass (tensor-map cache, attributes)
     fn()
 torch.cuda.synchronize()
