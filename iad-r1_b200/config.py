@@ -27,6 +27,7 @@ class TextConfig:
 @dataclass
 class VisionConfig:
     kind: str                 # "qwen2_5_vl" (RMSNorm, SwiGLU+bias, windowed attention) | "qwen2_vl" (LayerNorm, quick-GELU MLP)
+                              # | "siglip" (LLaVA-OneVision tower: LayerNorm, tanh-GELU MLP, learned position table, no rotary)
     depth: int
     hidden_size: int
     num_heads: int
@@ -38,6 +39,11 @@ class VisionConfig:
     in_channels: int = 3
     window_size: int = 112
     fullatt_block_indexes: tuple = (7, 15, 23, 31)
+    image_size: int = 0       # siglip: side of one crop in pixels (384 -> 27 x 27 = 729 tokens per crop)
+
+    @property
+    def tokens_per_crop(self) -> int:
+        return (self.image_size // self.patch_size) ** 2
 
     @property
     def head_dim(self) -> int:
@@ -48,6 +54,11 @@ class VisionConfig:
         return self.in_channels * self.temporal_patch_size * self.patch_size * self.patch_size
 
     @property
+    def patch_dim_padded(self) -> int:
+        """K of the patch-embedding GEMM rounded up to 8 elements (SigLIP: 3*14*14 = 588 -> 592; Qwen: 1176)."""
+        return (self.patch_dim + 7) // 8 * 8
+
+    @property
     def intermediate_padded(self) -> int:
         """MLP width rounded up to 8 elements so every row / half-row starts 16-byte aligned (3420 -> 3424)."""
         return (self.intermediate_size + 7) // 8 * 8
@@ -55,7 +66,7 @@ class VisionConfig:
 
 @dataclass
 class VLMConfig:
-    family: str               # "qwen2_5_vl" | "qwen2_vl"
+    family: str               # "qwen2_5_vl" | "qwen2_vl" | "llava_onevision"
     text: TextConfig
     vision: VisionConfig
     image_token_id: int = 151655
@@ -73,8 +84,10 @@ class VLMConfig:
     @staticmethod
     def from_hf_dict(d: dict) -> "VLMConfig":
         mt = d.get("model_type", "")
+        if mt == "llava_onevision":
+            return VLMConfig._from_llava_onevision(d)
         if mt not in ("qwen2_5_vl", "qwen2_vl"):
-            raise ValueError(f"unsupported model_type {mt!r} (supported: qwen2_5_vl, qwen2_vl)")
+            raise ValueError(f"unsupported model_type {mt!r} (supported: qwen2_5_vl, qwen2_vl, llava_onevision)")
         t = d.get("text_config") or d
         rope = t.get("rope_parameters") or t.get("rope_scaling") or d.get("rope_scaling") or {}
         theta = rope.get("rope_theta", t.get("rope_theta", d.get("rope_theta", 1e6)))
@@ -108,9 +121,61 @@ class VLMConfig:
                          eos_token_id=d.get("eos_token_id", 151645) if not isinstance(d.get("eos_token_id"), list) else d["eos_token_id"][0],
                          pad_token_id=d.get("pad_token_id") or 151643)
 
+    @staticmethod
+    def _from_llava_onevision(d: dict) -> "VLMConfig":
+        """LlavaOnevisionConfig: Qwen2 text model (1-D rotary) + SigLIP tower + 2-layer GELU projector + anyres packing
+        (HF modeling_llava_onevision.py:137-156, 292-355)."""
+        t, v = d["text_config"], d["vision_config"]
+        if d.get("vision_feature_select_strategy", "full") != "full" or d.get("vision_feature_layer", -1) != -1:
+            raise ValueError("llava_onevision: only vision_feature_layer=-1 / select_strategy='full' is supported")
+        if str(d.get("vision_aspect_ratio", "anyres_max_9")) != "anyres_max_9":
+            raise ValueError("llava_onevision: only vision_aspect_ratio='anyres_max_9' is supported")
+        nh = t["num_attention_heads"]
+        rope = t.get("rope_parameters") or {}
+        text = TextConfig(
+            vocab_size=t["vocab_size"], hidden_size=t["hidden_size"], intermediate_size=t["intermediate_size"],
+            num_layers=t["num_hidden_layers"], num_heads=nh, num_kv_heads=t.get("num_key_value_heads", nh),
+            head_dim=t.get("head_dim") or t["hidden_size"] // nh, rms_norm_eps=t.get("rms_norm_eps", 1e-6),
+            rope_theta=float(rope.get("rope_theta", t.get("rope_theta", 1e6))), mrope_section=(),
+            tie_word_embeddings=bool(d.get("tie_word_embeddings", t.get("tie_word_embeddings", False))))
+        vision = VisionConfig(
+            kind="siglip", depth=v["num_hidden_layers"], hidden_size=v["hidden_size"], num_heads=v["num_attention_heads"],
+            intermediate_size=v["intermediate_size"], out_hidden_size=text.hidden_size, patch_size=v.get("patch_size", 14),
+            spatial_merge_size=1, temporal_patch_size=1, in_channels=v.get("num_channels", 3), window_size=0,
+            fullatt_block_indexes=(), image_size=v.get("image_size", 384))
+        eos = d.get("eos_token_id", t.get("eos_token_id", 151645))
+        return VLMConfig(family="llava_onevision", text=text, vision=vision,
+                         image_token_id=d.get("image_token_index", d.get("image_token_id", 151646)),
+                         video_token_id=d.get("video_token_index", d.get("video_token_id", 151647)),
+                         vision_start_token_id=-1, vision_end_token_id=-1,
+                         eos_token_id=eos[0] if isinstance(eos, list) else eos,
+                         pad_token_id=d.get("pad_token_id") or t.get("pad_token_id") or 151643,
+                         extra={"image_grid_pinpoints": [list(x) for x in d["image_grid_pinpoints"]],
+                                "vision_layer_norm_eps": v.get("layer_norm_eps", 1e-6)})
+
     def to_hf_dict(self) -> dict:
         """config.json in the 4.51-era flat schema the reference's `from_pretrained` expects."""
         t, v = self.text, self.vision
+        if self.family == "llava_onevision":
+            return {
+                "model_type": "llava_onevision", "architectures": ["LlavaOnevisionForConditionalGeneration"],
+                "image_token_index": self.image_token_id, "video_token_index": self.video_token_id,
+                "image_grid_pinpoints": self.extra["image_grid_pinpoints"], "vision_feature_layer": -1,
+                "vision_feature_select_strategy": "full", "vision_aspect_ratio": "anyres_max_9",
+                "projector_hidden_act": "gelu", "multimodal_projector_bias": True,
+                "tie_word_embeddings": t.tie_word_embeddings, "torch_dtype": "bfloat16",
+                "text_config": {"model_type": "qwen2", "vocab_size": t.vocab_size, "hidden_size": t.hidden_size,
+                                "intermediate_size": t.intermediate_size, "num_hidden_layers": t.num_layers,
+                                "num_attention_heads": t.num_heads, "num_key_value_heads": t.num_kv_heads,
+                                "rms_norm_eps": t.rms_norm_eps, "rope_theta": t.rope_theta, "hidden_act": "silu",
+                                "max_position_embeddings": 32768, "tie_word_embeddings": t.tie_word_embeddings,
+                                "eos_token_id": self.eos_token_id, "pad_token_id": self.pad_token_id},
+                "vision_config": {"model_type": "siglip_vision_model", "hidden_size": v.hidden_size,
+                                  "intermediate_size": v.intermediate_size, "num_hidden_layers": v.depth,
+                                  "num_attention_heads": v.num_heads, "patch_size": v.patch_size, "image_size": v.image_size,
+                                  "num_channels": v.in_channels, "hidden_act": "gelu_pytorch_tanh",
+                                  "layer_norm_eps": self.extra.get("vision_layer_norm_eps", 1e-6), "vision_use_head": False},
+            }
         d = {
             "model_type": self.family,
             "architectures": ["Qwen2_5_VLForConditionalGeneration" if self.family == "qwen2_5_vl" else "Qwen2VLForConditionalGeneration"],
@@ -154,6 +219,15 @@ PRESETS = {
                                      VisionConfig(kind="qwen2_vl", depth=32, hidden_size=1280, num_heads=16,
                                                   intermediate_size=5120, out_hidden_size=1536, window_size=0,
                                                   fullatt_block_indexes=())),
+    # LLaVA-OneVision-Qwen2-0.5B-SI: Qwen2-0.5B + SigLIP-so400m/14-384 (26 encoder layers used), anyres_max_9
+    "llava-ov-0.5b": lambda: VLMConfig(
+        "llava_onevision", TextConfig(151936, 896, 4864, 24, 14, 2, 64, mrope_section=(), tie_word_embeddings=True),
+        VisionConfig(kind="siglip", depth=26, hidden_size=1152, num_heads=16, intermediate_size=4304, out_hidden_size=896,
+                     patch_size=14, spatial_merge_size=1, temporal_patch_size=1, window_size=0, fullatt_block_indexes=(),
+                     image_size=384),
+        image_token_id=151646, video_token_id=151647, vision_start_token_id=-1, vision_end_token_id=-1,
+        extra={"image_grid_pinpoints": [[384 * a, 384 * b] for a in range(1, 7) for b in range(1, 7)],
+               "vision_layer_norm_eps": 1e-6}),
 }
 
 
@@ -162,6 +236,17 @@ def tiny_config(family: str = "qwen2_5_vl") -> VLMConfig:
     full vision blocks, ragged MLP width, tied head) - the parity-test geometry (tests/golden)."""
     text = TextConfig(vocab_size=1024, hidden_size=128, intermediate_size=256, num_layers=2, num_heads=4, num_kv_heads=2,
                       head_dim=32, mrope_section=(4, 6, 6), tie_word_embeddings=True)
+    if family == "llava_onevision":
+        # head_dim 24 (not a power of two, like SigLIP's 72), 4 x 4 tokens per 56-pixel crop, 2 x 2 anyres grid
+        text = TextConfig(vocab_size=1024, hidden_size=128, intermediate_size=256, num_layers=2, num_heads=4,
+                          num_kv_heads=2, head_dim=32, mrope_section=(), tie_word_embeddings=True)
+        vis = VisionConfig(kind="siglip", depth=2, hidden_size=96, num_heads=4, intermediate_size=200, out_hidden_size=128,
+                           patch_size=14, spatial_merge_size=1, temporal_patch_size=1, window_size=0,
+                           fullatt_block_indexes=(), image_size=56)
+        return VLMConfig(family, text, vis, image_token_id=1001, video_token_id=1002, vision_start_token_id=-1,
+                         vision_end_token_id=-1, eos_token_id=1005, pad_token_id=1006,
+                         extra={"image_grid_pinpoints": [[56, 56], [56, 112], [112, 56], [112, 112], [168, 56], [56, 168]],
+                                "vision_layer_norm_eps": 1e-6})
     if family == "qwen2_5_vl":
         vis = VisionConfig(kind="qwen2_5_vl", depth=2, hidden_size=64, num_heads=4, intermediate_size=108,
                            out_hidden_size=128, window_size=56, fullatt_block_indexes=(1,))

@@ -191,3 +191,128 @@ def embed_source_index(input_ids: np.ndarray, image_token_id: int, rows_share_im
         out[b, is_img] = -1 - (cursor + np.arange(n))
         cursor += n
     return out.reshape(-1).astype(np.int32)
+
+
+# ---- LLaVA-OneVision: anyres geometry (HF image_processing_utils.select_best_resolution, modeling_llava_onevision.py
+# :159-187 get_anyres_image_grid_shape, :227-267 unpad_image, :292-355 pack_image_features) ---------------------------------
+def select_best_resolution(original_size, possible_resolutions):
+    """original_size (h, w); returns the (h, w) pinpoint with the largest effective resolution, ties -> least waste."""
+    oh, ow = original_size
+    best, best_eff, best_waste = None, -1, float("inf")
+    for h, w in possible_resolutions:
+        scale = min(w / ow, h / oh)
+        dw, dh = int(ow * scale), int(oh * scale)
+        eff = min(dw * dh, ow * oh)
+        waste = w * h - eff
+        if eff > best_eff or (eff == best_eff and waste < best_waste):
+            best, best_eff, best_waste = (h, w), eff, waste
+    return best
+
+
+def llava_image_layout(cfg: VLMConfig, image_hw):
+    """For one image of size (H, W): (n_crops incl. the base crop, crop grid (gh, gw), kept feature-grid rows / cols after
+    unpadding as slices). Raises for images large enough to need the bilinear shrink of anyres_max_9."""
+    v = cfg.vision
+    side = v.image_size // v.patch_size                       # 27 feature rows / cols per crop
+    bh, bw = select_best_resolution(image_hw, cfg.extra["image_grid_pinpoints"])
+    gh, gw = bh // v.image_size, bw // v.image_size
+    cur_h, cur_w = gh * side, gw * side
+    oh, ow = image_hw
+    if ow / oh > cur_w / cur_h:
+        new_h = int(round(oh * (cur_w / ow), 7))
+        pad = (cur_h - new_h) // 2
+        rows, cols = (pad, cur_h - pad), (0, cur_w)
+    else:
+        new_w = int(round(ow * (cur_h / oh), 7))
+        pad = (cur_w - new_w) // 2
+        rows, cols = (0, cur_h), (pad, cur_w - pad)
+    kh, kw = rows[1] - rows[0], cols[1] - cols[0]
+    if (kh * kw / (9 * side * side)) ** 0.5 > 1.1:
+        raise NotImplementedError("anyres_max_9 bilinear feature shrink (image spanning > 9 crops) is not implemented")
+    return gh * gw + 1, (gh, gw), rows, cols
+
+
+def llava_pack_index(cfg: VLMConfig, image_hw):
+    """Row map of pack_image_features for one image: packed token i takes projected-feature row idx[i] (relative to the
+    image's first feature row; crop 0 = base crop, then the grid crops row-major), or the `image_newline` vector where
+    idx[i] == -1: [base crop tokens | for every kept feature-grid row: its kept columns, newline]."""
+    v = cfg.vision
+    side = v.image_size // v.patch_size
+    tpc = side * side
+    n_crops, (gh, gw), rows, cols = llava_image_layout(cfg, image_hw)
+    idx = [np.arange(tpc, dtype=np.int64)]
+    ys = np.arange(rows[0], rows[1])
+    xs = np.arange(cols[0], cols[1])
+    crop = 1 + (ys[:, None] // side) * gw + (xs[None, :] // side)
+    body = crop * tpc + (ys[:, None] % side) * side + (xs[None, :] % side)
+    body = np.concatenate([body, np.full((len(ys), 1), -1, dtype=np.int64)], 1)
+    idx.append(body.reshape(-1))
+    return np.concatenate(idx).astype(np.int32), n_crops
+
+
+def image_token_count(cfg: VLMConfig, grid_entry) -> int:
+    """Number of placeholder tokens one image expands to. grid_entry: (t, h, w) patch grid for the Qwen families;
+    (n_crops, H, W) with the ORIGINAL image size in pixels for LLaVA-OneVision."""
+    if cfg.family == "llava_onevision":
+        return len(llava_pack_index(cfg, (int(grid_entry[1]), int(grid_entry[2])))[0])
+    t, h, w = grid_entry
+    return int(t * h * w) // cfg.vision.spatial_merge_size ** 2
+
+
+def position_ids(input_ids: np.ndarray, grid_thw: list, cfg: VLMConfig, attention_mask: np.ndarray | None = None,
+                 prompt_len: int | None = None):
+    """Family dispatch: M-RoPE ids for Qwen2(.5)-VL; plain 1-D positions (cumulative count of unmasked tokens, the
+    Qwen2 text model under LLaVA-OneVision) replicated on the three axes otherwise. Returns ([3, B, T], deltas [B])."""
+    if cfg.family != "llava_onevision":
+        return mrope_position_ids(input_ids, grid_thw, cfg, attention_mask, prompt_len)
+    B, T = input_ids.shape
+    am = np.ones((B, T), dtype=np.int64) if attention_mask is None else attention_mask.astype(np.int64)
+    p = np.cumsum(am, 1) - 1
+    p[am == 0] = 1
+    pos = np.broadcast_to(p[None], (3, B, T)).astype(np.int64).copy()
+    deltas = (am.sum(1) - T).astype(np.int64)
+    return pos, deltas
+
+
+class SiglipGeometry:
+    """What the LLaVA-OneVision vision path derives from the image sizes: per-crop attention segments (SigLIP attends
+    within one 384 x 384 crop), the tiled position-table index, and the anyres packing index over all images."""
+
+    def __init__(self, cfg: VLMConfig, grid: list, device):
+        tpc = cfg.vision.tokens_per_crop
+        packs, base, n_crops_total = [], 0, 0
+        for n_crops, h, w in grid:
+            idx, n = llava_pack_index(cfg, (int(h), int(w)))
+            if n != int(n_crops):
+                raise ValueError(f"image of size {(h, w)} needs {n} crops, processor supplied {n_crops}")
+            packs.append(np.where(idx >= 0, idx + base, -1))
+            base += n * tpc
+            n_crops_total += n
+        self.n_crops = n_crops_total
+        self.n_patches = n_crops_total * tpc
+        pack = np.concatenate(packs) if packs else np.zeros(0, dtype=np.int64)
+        self.n_tokens = len(pack)
+        self.pack_index = torch.from_numpy(pack.astype(np.int32)).to(device)
+        lo = (np.arange(self.n_patches) // tpc * tpc).astype(np.int32)
+        self.full_lo = torch.from_numpy(lo).to(device)
+        self.full_hi = torch.from_numpy(lo + tpc).to(device)
+
+
+def siglip_geometry(cfg: VLMConfig, grid, device) -> SiglipGeometry:
+    key = ("siglip", cfg.vision.image_size, cfg.vision.patch_size, tuple(map(tuple, grid)), str(device))
+    g = _GEOM_CACHE.get(key)
+    if g is None:
+        if len(_GEOM_CACHE) > 64:
+            _GEOM_CACHE.clear()
+        g = _GEOM_CACHE[key] = SiglipGeometry(cfg, [tuple(int(x) for x in r) for r in grid], device)
+    return g
+
+
+def patchify_crops(pixel_values: torch.Tensor, patch: int) -> torch.Tensor:
+    """[n_crops, C, S, S] -> [n_crops * (S/patch)^2, C * patch * patch]: the rows the SigLIP Conv2d(k = stride = patch)
+    patch embedding multiplies, in (crop, grid row, grid col) order with (channel, py, px) columns - so that the
+    convolution is ONE GEMM against the flattened kernel (modeling_siglip.py:116-186)."""
+    n, c, s, _ = pixel_values.shape
+    g = s // patch
+    x = pixel_values.reshape(n, c, g, patch, g, patch).permute(0, 2, 4, 1, 3, 5)
+    return x.reshape(n * g * g, c * patch * patch).contiguous()

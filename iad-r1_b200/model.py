@@ -14,7 +14,8 @@ import torch
 
 from . import ops
 from .config import VLMConfig
-from .geometry import VisionGeometry, embed_source_index, mrope_position_ids, text_rope_tables, vision_geometry
+from .geometry import (VisionGeometry, embed_source_index, image_token_count, position_ids as family_position_ids,
+                       siglip_geometry, text_rope_tables, vision_geometry)
 from .params import ParamStore
 
 bf16, f32 = torch.bfloat16, torch.float32
@@ -57,6 +58,8 @@ class VLM:
     def vision_forward(self, pixel_values: torch.Tensor, grid_thw, save: bool = True):
         """pixel_values [Np, C*tp*ps*ps] (any float dtype) -> image embeddings [Np/merge^2, H_text] bf16."""
         v, p = self.cfg.vision, self.p
+        if v.kind == "siglip":
+            return self._siglip_forward(pixel_values, grid_thw, save)
         geo = vision_geometry(v, grid_thw, self.device)
         E, nh, hd, Ip = v.hidden_size, v.num_heads, v.head_dim, v.intermediate_padded
         unit = v.spatial_merge_size ** 2
@@ -116,6 +119,8 @@ class VLM:
     def vision_backward(self, d_out: torch.Tensor, ctx: VisionCtx):
         """Accumulates vision-tower gradients into the fp32 grad buffer given d(image embeddings) bf16."""
         v, p, g, geo = self.cfg.vision, self.p, self.g, ctx.geo
+        if v.kind == "siglip":
+            return self._siglip_backward(d_out, ctx)
         E, nh, hd, Ip = v.hidden_size, v.num_heads, v.head_dim, v.intermediate_padded
         unit = v.spatial_merge_size ** 2
         Np = geo.n_patches
@@ -161,6 +166,85 @@ class VLM:
         if geo.reverse_index is not None:
             dx = ops.gather_rows(dx.view(Np // unit, unit * E), geo.reverse_index).view(Np, E)
         ops.linear_bwd(dx, ctx.px, p["visual.patch_embed.weight"], g["visual.patch_embed.weight"], need_dx=False)
+
+    # ---- LLaVA-OneVision: SigLIP tower -> 2-layer GELU projector -> anyres packing -----------------------------------
+    def _siglip_forward(self, pixel_values: torch.Tensor, grid, save: bool):
+        """pixel_values [n_crops * 729, 3*14*14] (crop 0 of every image = the base crop) -> packed image embeddings
+        [n_image_tokens, H_text] bf16. HF: SiglipVisionEmbeddings (modeling_siglip.py:116-186: Conv2d patch embed with bias +
+        learned position table), SiglipEncoderLayer x depth (pre-LN attention + tanh-GELU MLP), hidden_states[-1] WITHOUT
+        post_layernorm (modeling_llava_onevision.py:405-417), LlavaOnevisionMultiModalProjector (:137-156), pack_image_features
+        (:292-355: crops re-tiled to one feature map, unpadded, `image_newline` appended to every row)."""
+        v, p = self.cfg.vision, self.p
+        geo = siglip_geometry(self.cfg, grid, self.device)
+        E, nh, hd, Ip, tpc = v.hidden_size, v.num_heads, v.head_dim, v.intermediate_padded, v.tokens_per_crop
+        eps = float(self.cfg.extra.get("vision_layer_norm_eps", 1e-6))
+        Np, nc = geo.n_patches, geo.n_crops
+        if pixel_values.shape[0] != Np:
+            raise ValueError(f"pixel_values has {pixel_values.shape[0]} patches, the image sizes imply {Np}")
+        px = pixel_values.to(device=self.device, dtype=bf16)
+        if v.patch_dim_padded != v.patch_dim:                      # K of the patch GEMM: 588 -> 592 (zero columns)
+            px = torch.nn.functional.pad(px, (0, v.patch_dim_padded - v.patch_dim))
+        px = px.contiguous()
+        pos = p["visual.pos_embed.weight"].repeat(nc, 1)          # position table tiled over the crops (residual operand)
+        x = ops.linear_fwd(px, p["visual.patch_embed.weight"], bias=p["visual.patch_embed.bias"], residual=pos)
+        sh = ops.AttnShape(nc, tpc, nh, nh, hd, causal=False)     # attention within one crop
+        lo = torch.zeros(tpc, dtype=torch.int32, device=self.device)
+        hi = torch.full((tpc,), tpc, dtype=torch.int32, device=self.device)
+        ctx = VisionCtx()
+        ctx.geo, ctx.px, ctx.blocks, ctx.sh, ctx.lo, ctx.hi = geo, px, [], sh, lo, hi
+        for i in range(v.depth):
+            b = f"visual.blocks.{i}."
+            xn, m1, r1 = ops.layernorm_fwd(x, p[b + "norm1.weight"], p[b + "norm1.bias"], eps)
+            qkv = ops.linear_fwd(xn, p[b + "qkv.weight"], bias=p[b + "qkv.bias"])
+            attn, P = ops.attention_fwd(qkv, sh, lo, hi)
+            x_mid = ops.linear_fwd(attn, p[b + "proj.weight"], bias=p[b + "proj.bias"], residual=x)
+            xn2, m2, r2 = ops.layernorm_fwd(x_mid, p[b + "norm2.weight"], p[b + "norm2.bias"], eps)
+            h1 = ops.linear_fwd(xn2, p[b + "fc1.weight"], bias=p[b + "fc1.bias"])
+            act = ops.act_mul_fwd(h1, Ip, ops.ACT_GELU_TANH, gated=False)
+            x_out = ops.linear_fwd(act, p[b + "fc2.weight"], bias=p[b + "fc2.bias"], residual=x_mid)
+            if save:
+                ctx.blocks.append((x, (m1, r1), xn, qkv, P, attn, x_mid, (m2, r2), xn2, h1, act))
+            x = x_out
+        H = v.out_hidden_size
+        m1_ = ops.linear_fwd(x, p["visual.merger.fc1.weight"], bias=p["visual.merger.fc1.bias"])
+        a1 = ops.act_mul_fwd(m1_, H, ops.ACT_GELU, gated=False)
+        feat = ops.linear_fwd(a1, p["visual.merger.fc2.weight"], bias=p["visual.merger.fc2.bias"])
+        out = ops.gather_rows(feat, geo.pack_index, alt=p["image_newline"].view(1, H))
+        if save:
+            ctx.x_last, ctx.m1, ctx.a1 = x, m1_, a1
+        return out, (ctx if save else None)
+
+    def _siglip_backward(self, d_out: torch.Tensor, ctx: VisionCtx):
+        v, p, g, geo = self.cfg.vision, self.p, self.g, ctx.geo
+        E, Ip, tpc, H = v.hidden_size, v.intermediate_padded, v.tokens_per_crop, v.out_hidden_size
+        Np, nc = geo.n_patches, geo.n_crops
+        # un-pack: features dropped by the unpadding get zero gradient, image_newline collects one row per feature-map row
+        dfeat32 = torch.zeros(Np, H, dtype=f32, device=self.device)
+        ops.scatter_add_rows(d_out, geo.pack_index, dfeat32, g["image_newline"].view(1, H))
+        dfeat = ops.cast_f32_bf16(dfeat32)
+        da1 = ops.linear_bwd(dfeat, ctx.a1, p["visual.merger.fc2.weight"], g["visual.merger.fc2.weight"],
+                             g["visual.merger.fc2.bias"])
+        dm1 = ops.act_mul_bwd(da1, ctx.m1, H, ops.ACT_GELU, gated=False)
+        dx = ops.linear_bwd(dm1, ctx.x_last, p["visual.merger.fc1.weight"], g["visual.merger.fc1.weight"],
+                            g["visual.merger.fc1.bias"])
+        for i in reversed(range(v.depth)):
+            b = f"visual.blocks.{i}."
+            x, st1, xn, qkv, P, attn, x_mid, st2, xn2, h1, act = ctx.blocks[i]
+            dact = ops.linear_bwd(dx, act, p[b + "fc2.weight"], g[b + "fc2.weight"], g[b + "fc2.bias"])
+            dh1 = ops.act_mul_bwd(dact, h1, Ip, ops.ACT_GELU_TANH, gated=False, dgu=h1)
+            dxn2 = ops.linear_bwd(dh1, xn2, p[b + "fc1.weight"], g[b + "fc1.weight"], g[b + "fc1.bias"])
+            ops.layernorm_bwd(dxn2, x_mid, p[b + "norm2.weight"], st2[0], st2[1], dx, g[b + "norm2.weight"],
+                              g[b + "norm2.bias"], add_dx=True)
+            dattn = ops.linear_bwd(dx, attn, p[b + "proj.weight"], g[b + "proj.weight"], g[b + "proj.bias"])
+            dqkv = ops.attention_bwd(dattn, qkv, P, ctx.sh, ctx.lo, ctx.hi)
+            dxn = ops.linear_bwd(dqkv, xn, p[b + "qkv.weight"], g[b + "qkv.weight"], g[b + "qkv.bias"])
+            ops.layernorm_bwd(dxn, x, p[b + "norm1.weight"], st1[0], st1[1], dx, g[b + "norm1.weight"],
+                              g[b + "norm1.bias"], add_dx=True)
+            ctx.blocks[i] = None
+        # x0 = patch_embed(px) + bias + pos[tile]: the table's gradient is the sum over crops
+        ops.colsum(dx.view(nc, tpc * E), g["visual.pos_embed.weight"].view(tpc * E))
+        ops.linear_bwd(dx, ctx.px, p["visual.patch_embed.weight"], g["visual.patch_embed.weight"],
+                       g["visual.patch_embed.bias"], need_dx=False)
 
     # =============================================================================================================
     # decoder
@@ -229,15 +313,14 @@ class VLM:
         B, T = ids_np.shape
         grid = [tuple(int(x) for x in r) for r in (grid_thw.tolist() if torch.is_tensor(grid_thw) else grid_thw)] \
             if grid_thw is not None else []
-        unit = self.cfg.vision.spatial_merge_size ** 2
-        n_img_tokens = sum(t * h * w for t, h, w in grid) // unit
+        n_img_tokens = sum(image_token_count(self.cfg, g_) for g_ in grid)
         pl = T if prompt_len is None else prompt_len
         per_row = int((ids_np[0, :pl] == self.cfg.image_token_id).sum()) if B else 0
         share = B > 1 and per_row == n_img_tokens
         if position_ids is None:
             am = attention_mask.detach().cpu().numpy() if torch.is_tensor(attention_mask) else attention_mask
             g_rows = grid * B if share else grid
-            position_ids, _ = mrope_position_ids(ids_np, g_rows, self.cfg, am, prompt_len)
+            position_ids, _ = family_position_ids(ids_np, g_rows, self.cfg, am, prompt_len)
             position_ids = torch.from_numpy(position_ids)
         cos, sin = text_rope_tables(position_ids, self.cfg.text, self.device)
         src = torch.from_numpy(embed_source_index(ids_np, self.cfg.image_token_id, share, n_img_tokens, prompt_len)).to(self.device)
@@ -254,9 +337,8 @@ class VLM:
         P = pr.shape[1]
         grid = [tuple(int(x) for x in r) for r in (grid_thw.tolist() if torch.is_tensor(grid_thw) else grid_thw)] \
             if grid_thw is not None else []
-        unit = self.cfg.vision.spatial_merge_size ** 2
-        n_img_tokens = sum(t * h * w for t, h, w in grid) // unit
-        pos_p, delta = mrope_position_ids(pr, grid, self.cfg)
+        n_img_tokens = sum(image_token_count(self.cfg, g_) for g_ in grid)
+        pos_p, delta = family_position_ids(pr, grid, self.cfg)
         nxt = int(pos_p.max()) + 1 if P else 0
         pos_c = np.broadcast_to((nxt + np.arange(C))[None, None, :], (3, G, C)).reshape(3, 1, G * C)
         pos = torch.from_numpy(np.concatenate([pos_p, pos_c], axis=2))

@@ -61,7 +61,10 @@ class ParamStore:
     def _declare(self):
         t, v = self.cfg.text, self.cfg.vision
         E, Ip = v.hidden_size, v.intermediate_padded
-        self._add("visual.patch_embed.weight", (E, v.patch_dim), True)
+        self._add("visual.patch_embed.weight", (E, v.patch_dim_padded), True)   # pad columns stay exactly zero
+        if v.kind == "siglip":
+            self._add("visual.patch_embed.bias", (E,), False)
+            self._add("visual.pos_embed.weight", (v.tokens_per_crop, E), False)   # learned table: no weight decay
         for i in range(v.depth):
             b = f"visual.blocks.{i}."
             self._add(b + "qkv.weight", (3 * E, E), True)
@@ -83,13 +86,24 @@ class ParamStore:
                 self._add(b + "fc2.weight", (E, Ip), True)
                 self._add(b + "fc2.bias", (E,), False)
         m = v.spatial_merge_size ** 2 * E
-        self._add("visual.merger.ln_q.weight", (E,), False)
-        if v.kind == "qwen2_vl":
-            self._add("visual.merger.ln_q.bias", (E,), False)
-        self._add("visual.merger.fc1.weight", (m, m), True)
-        self._add("visual.merger.fc1.bias", (m,), False)
-        self._add("visual.merger.fc2.weight", (v.out_hidden_size, m), True)
-        self._add("visual.merger.fc2.bias", (v.out_hidden_size,), False)
+        if v.kind == "siglip":
+            # SigLIP's post_layernorm is NOT on the path (features = last encoder layer output); kept for round trips.
+            self._add("visual.post_layernorm.weight", (E,), False)
+            self._add("visual.post_layernorm.bias", (E,), False)
+            # LlavaOnevisionMultiModalProjector: Linear(E -> H) GELU Linear(H -> H); + the anyres row separator
+            self._add("visual.merger.fc1.weight", (v.out_hidden_size, E), True)
+            self._add("visual.merger.fc1.bias", (v.out_hidden_size,), False)
+            self._add("visual.merger.fc2.weight", (v.out_hidden_size, v.out_hidden_size), True)
+            self._add("visual.merger.fc2.bias", (v.out_hidden_size,), False)
+            self._add("image_newline", (v.out_hidden_size,), False)
+        else:
+            self._add("visual.merger.ln_q.weight", (E,), False)
+            if v.kind == "qwen2_vl":
+                self._add("visual.merger.ln_q.bias", (E,), False)
+            self._add("visual.merger.fc1.weight", (m, m), True)
+            self._add("visual.merger.fc1.bias", (m,), False)
+            self._add("visual.merger.fc2.weight", (v.out_hidden_size, m), True)
+            self._add("visual.merger.fc2.bias", (v.out_hidden_size,), False)
         self._add("embed_tokens.weight", (t.vocab_size, t.hidden_size), True)
         for i in range(t.num_layers):
             b = f"layers.{i}."
@@ -128,6 +142,10 @@ class ParamStore:
         src = {"p": self.p, "g": self.g}[which]
         t, v = self.cfg.text, self.cfg.vision
         E, I, Ip = v.hidden_size, v.intermediate_size, v.intermediate_padded
+        if v.kind == "siglip":
+            yield from self._hf_named_siglip(src)
+            yield from self._hf_named_text(src, "language_model.model.", "language_model.lm_head.weight")
+            return
         yield "visual.patch_embed.proj.weight", src["visual.patch_embed.weight"]
         for i in range(v.depth):
             b, hb = f"visual.blocks.{i}.", f"visual.blocks.{i}."
@@ -158,11 +176,47 @@ class ParamStore:
         yield "visual.merger.mlp.0.bias", src["visual.merger.fc1.bias"]
         yield "visual.merger.mlp.2.weight", src["visual.merger.fc2.weight"]
         yield "visual.merger.mlp.2.bias", src["visual.merger.fc2.bias"]
-        yield "model.embed_tokens.weight", src["embed_tokens.weight"]
+        yield from self._hf_named_text(src, "model.", "lm_head.weight")
+
+    def _hf_named_siglip(self, src):
+        """LLaVA-OneVision 4.51-era names: vision_tower.vision_model.*, multi_modal_projector.*, image_newline."""
+        v = self.cfg.vision
+        E = v.hidden_size
+        vb = "vision_tower.vision_model."
+        yield vb + "embeddings.patch_embedding.weight", src["visual.patch_embed.weight"][:, :v.patch_dim]
+        yield vb + "embeddings.patch_embedding.bias", src["visual.patch_embed.bias"]
+        yield vb + "embeddings.position_embedding.weight", src["visual.pos_embed.weight"]
+        for i in range(v.depth):
+            b, hb = f"visual.blocks.{i}.", f"{vb}encoder.layers.{i}."
+            w, bi = src[b + "qkv.weight"], src[b + "qkv.bias"]
+            for j, nm in enumerate(("q_proj", "k_proj", "v_proj")):
+                yield hb + f"self_attn.{nm}.weight", w[j * E:(j + 1) * E]
+                yield hb + f"self_attn.{nm}.bias", bi[j * E:(j + 1) * E]
+            yield hb + "self_attn.out_proj.weight", src[b + "proj.weight"]
+            yield hb + "self_attn.out_proj.bias", src[b + "proj.bias"]
+            yield hb + "layer_norm1.weight", src[b + "norm1.weight"]
+            yield hb + "layer_norm1.bias", src[b + "norm1.bias"]
+            yield hb + "layer_norm2.weight", src[b + "norm2.weight"]
+            yield hb + "layer_norm2.bias", src[b + "norm2.bias"]
+            yield hb + "mlp.fc1.weight", src[b + "fc1.weight"]
+            yield hb + "mlp.fc1.bias", src[b + "fc1.bias"]
+            yield hb + "mlp.fc2.weight", src[b + "fc2.weight"]
+            yield hb + "mlp.fc2.bias", src[b + "fc2.bias"]
+        yield vb + "post_layernorm.weight", src["visual.post_layernorm.weight"]
+        yield vb + "post_layernorm.bias", src["visual.post_layernorm.bias"]
+        yield "multi_modal_projector.linear_1.weight", src["visual.merger.fc1.weight"]
+        yield "multi_modal_projector.linear_1.bias", src["visual.merger.fc1.bias"]
+        yield "multi_modal_projector.linear_2.weight", src["visual.merger.fc2.weight"]
+        yield "multi_modal_projector.linear_2.bias", src["visual.merger.fc2.bias"]
+        yield "image_newline", src["image_newline"]
+
+    def _hf_named_text(self, src, prefix, head_name):
+        t = self.cfg.text
+        yield prefix + "embed_tokens.weight", src["embed_tokens.weight"]
         nq, nkv, hd = t.num_heads * t.head_dim, t.num_kv_heads * t.head_dim, t.head_dim
         Ti = t.intermediate_size
         for i in range(t.num_layers):
-            b, hb = f"layers.{i}.", f"model.layers.{i}."
+            b, hb = f"layers.{i}.", f"{prefix}layers.{i}."
             w, bi = src[b + "qkv.weight"], src[b + "qkv.bias"]
             yield hb + "self_attn.q_proj.weight", w[:nq]
             yield hb + "self_attn.k_proj.weight", w[nq:nq + nkv]
@@ -176,13 +230,22 @@ class ParamStore:
             yield hb + "mlp.down_proj.weight", src[b + "down.weight"]
             yield hb + "input_layernorm.weight", src[b + "ln1.weight"]
             yield hb + "post_attention_layernorm.weight", src[b + "ln2.weight"]
-        yield "model.norm.weight", src["norm.weight"]
+        yield prefix + "norm.weight", src["norm.weight"]
         if not t.tie_word_embeddings:
-            yield "lm_head.weight", src["lm_head.weight"]
+            yield head_name, src["lm_head.weight"]
 
-    @staticmethod
-    def canonical_name(name: str) -> str:
+    def canonical_name(self, name: str) -> str:
         """Map transformers-5.x key names (`model.visual.*`, `model.language_model.*`) onto the 4.51 layout."""
+        if self.cfg.family == "llava_onevision":
+            # 5.x: model.vision_tower.*, model.multi_modal_projector.*, model.image_newline, model.language_model.*, lm_head.*
+            if name.startswith("model.language_model."):
+                return "language_model.model." + name[len("model.language_model."):]
+            if name == "lm_head.weight":
+                return "language_model.lm_head.weight"
+            if name.startswith("model.") and not name.startswith("model.layers") and not name.startswith("model.embed") \
+                    and not name.startswith("model.norm"):
+                return name[len("model."):]
+            return name
         if name.startswith("model.visual."):
             return name[len("model."):]
         if name.startswith("model.language_model."):
@@ -196,12 +259,12 @@ class ParamStore:
         with torch.no_grad():
             for name, view in self.hf_named_tensors("p"):
                 if name not in sd:
-                    if name == "lm_head.weight" or not strict:
+                    if name.endswith("lm_head.weight") or not strict:
                         continue
                     missing.append(name)
                     continue
                 src = sd[name]
-                if name == "visual.patch_embed.proj.weight":
+                if name in ("visual.patch_embed.proj.weight", "vision_tower.vision_model.embeddings.patch_embedding.weight"):
                     src = src.reshape(src.shape[0], -1)
                 if tuple(src.shape) != tuple(view.shape):
                     raise ValueError(f"{name}: checkpoint shape {tuple(src.shape)} != model shape {tuple(view.shape)}")
@@ -217,6 +280,9 @@ class ParamStore:
             if name == "visual.patch_embed.proj.weight":
                 v = self.cfg.vision
                 tns = tns.view(v.hidden_size, v.in_channels, v.temporal_patch_size, v.patch_size, v.patch_size)
+            elif name == "vision_tower.vision_model.embeddings.patch_embedding.weight":
+                v = self.cfg.vision
+                tns = tns.view(v.hidden_size, v.in_channels, v.patch_size, v.patch_size)
             sd[name] = tns
         return sd
 
@@ -228,7 +294,7 @@ class ParamStore:
             for name, view in self.hf_named_tensors("p"):
                 if name.endswith("bias"):
                     continue
-                if "norm" in name or "ln_q" in name:
+                if ("norm" in name and "weight" in name) or "ln_q" in name:
                     view.fill_(1.0)
                 else:
                     view.copy_(torch.empty(view.shape, dtype=torch.float32, device=self.device)

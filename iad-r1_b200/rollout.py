@@ -172,7 +172,7 @@ class RolloutEngine:
         # ---- prefill: ALL prompts in one right-padded [n, Pmax] pass through the training forward kernels (one vision
         # tower call over every image, decoder GEMMs at M = n * Pmax); each layer's post-rotary K/V land in the shared
         # prefix cache. Padding sits after the real tokens, so causal attention never lets it influence them.
-        from .geometry import mrope_position_ids
+        from .geometry import position_ids as mrope_position_ids   # family dispatch (M-RoPE or plain 1-D positions)
         id_list = [np.asarray(pr["input_ids"], dtype=np.int64).reshape(-1) for pr in prompts]
         lens = [len(x) for x in id_list]
         Pmax = max(lens)

@@ -26,6 +26,24 @@ def hf_config(cfg, attn_implementation="eager"):
     common = dict(image_token_id=cfg.image_token_id, video_token_id=cfg.video_token_id,
                   vision_start_token_id=cfg.vision_start_token_id, vision_end_token_id=cfg.vision_end_token_id,
                   tie_word_embeddings=t.tie_word_embeddings)
+    if cfg.family == "llava_onevision":
+        from transformers import LlavaOnevisionConfig
+        c = LlavaOnevisionConfig(
+            text_config=dict(model_type="qwen2", vocab_size=t.vocab_size, hidden_size=t.hidden_size,
+                             intermediate_size=t.intermediate_size, num_hidden_layers=t.num_layers,
+                             num_attention_heads=t.num_heads, num_key_value_heads=t.num_kv_heads,
+                             max_position_embeddings=32768, rms_norm_eps=t.rms_norm_eps, rope_theta=t.rope_theta,
+                             tie_word_embeddings=t.tie_word_embeddings, use_sliding_window=False),
+            vision_config=dict(model_type="siglip_vision_model", hidden_size=v.hidden_size, intermediate_size=v.intermediate_size,
+                               num_hidden_layers=v.depth, num_attention_heads=v.num_heads, patch_size=v.patch_size,
+                               image_size=v.image_size, num_channels=v.in_channels, hidden_act="gelu_pytorch_tanh",
+                               layer_norm_eps=cfg.extra.get("vision_layer_norm_eps", 1e-6), vision_use_head=False),
+            image_token_index=cfg.image_token_id, video_token_index=cfg.video_token_id,
+            image_grid_pinpoints=cfg.extra["image_grid_pinpoints"], vision_feature_layer=-1,
+            vision_feature_select_strategy="full", vision_aspect_ratio="anyres_max_9", projector_hidden_act="gelu",
+            multimodal_projector_bias=True, tie_word_embeddings=t.tie_word_embeddings)
+        c._attn_implementation = attn_implementation
+        return c
     if cfg.family == "qwen2_5_vl":
         from transformers import Qwen2_5_VLConfig
         vis = dict(depth=v.depth, hidden_size=v.hidden_size, intermediate_size=v.intermediate_size, num_heads=v.num_heads,
@@ -47,7 +65,9 @@ def hf_config(cfg, attn_implementation="eager"):
 def build_hf_model(cfg, seed=0, dtype=torch.float32, attn_implementation="eager"):
     """Random-init HF model (initializer_range 0.02, HF `_init_weights`), weights rounded to bf16 values so that the
     fp32 oracle and the bf16 product path hold bit-identical parameters."""
-    if cfg.family == "qwen2_5_vl":
+    if cfg.family == "llava_onevision":
+        from transformers import LlavaOnevisionForConditionalGeneration as Cls
+    elif cfg.family == "qwen2_5_vl":
         from transformers import Qwen2_5_VLForConditionalGeneration as Cls
     else:
         from transformers import Qwen2VLForConditionalGeneration as Cls
@@ -72,6 +92,15 @@ def hf_logits(model, input_ids, pixel_values, grid_thw, position_ids, attention_
     if pixel_values is not None:
         kw["pixel_values"] = pixel_values.to(next(model.parameters()).dtype)
         kw["image_grid_thw"] = grid_thw
+    return model(**kw).logits
+
+
+def hf_logits_llava(model, input_ids, pixel_values, image_sizes, position_ids, attention_mask=None):
+    """LLaVA-OneVision: pixel_values [B, n_crops, 3, S, S] (crop 0 = base crop), image_sizes [B, 2] (H, W)."""
+    kw = dict(input_ids=input_ids, position_ids=position_ids, use_cache=False,
+              pixel_values=pixel_values.to(next(model.parameters()).dtype), image_sizes=image_sizes)
+    if attention_mask is not None:
+        kw["attention_mask"] = attention_mask
     return model(**kw).logits
 
 

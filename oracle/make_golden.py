@@ -12,9 +12,9 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from iad_r1_b200.config import tiny_config  # noqa: E402
-from iad_r1_b200.geometry import mrope_position_ids  # noqa: E402
+from iad_r1_b200.geometry import mrope_position_ids, position_ids as family_position_ids, image_token_count, patchify_crops  # noqa: E402
 from oracle import grpo_ref  # noqa: E402
-from oracle.hf_oracle import build_hf_model, hf_logits, per_token_logps  # noqa: E402
+from oracle.hf_oracle import build_hf_model, hf_logits, hf_logits_llava, per_token_logps  # noqa: E402
 
 
 def synthetic_batch(cfg, G=4, C=12, grid=(1, 8, 8), seed=0):
@@ -37,14 +37,38 @@ def synthetic_batch(cfg, G=4, C=12, grid=(1, 8, 8), seed=0):
     return ids, P, px
 
 
+def synthetic_batch_llava(cfg, G=4, C=12, image_hw=(80, 100), seed=0):
+    """LLaVA-OneVision twin: one (H, W) image -> anyres crops [n_crops, 3, S, S] (bf16-valued), prompt with the packed
+    number of <image> placeholders (unpadding drops feature rows for this aspect ratio), G completions."""
+    rng = np.random.RandomState(seed)
+    n_crops = 5
+    n_img = image_token_count(cfg, (n_crops, image_hw[0], image_hw[1]))
+    prompt = list(rng.randint(10, 900, size=6)) + [cfg.image_token_id] * n_img + list(rng.randint(10, 900, size=5))
+    P = len(prompt)
+    comp = rng.randint(10, 900, size=(G, C))
+    for g, e in enumerate([None, 7, C - 1, 2][:G]):
+        if e is not None:
+            comp[g, e] = cfg.eos_token_id
+            comp[g, e + 1:] = cfg.pad_token_id
+    ids = np.concatenate([np.tile(np.array(prompt)[None], (G, 1)), comp], 1).astype(np.int64)
+    gen = torch.Generator().manual_seed(seed + 7)
+    S = cfg.vision.image_size
+    crops = torch.randn(n_crops, cfg.vision.in_channels, S, S, generator=gen).to(torch.bfloat16).float()
+    return ids, P, crops, (n_crops, image_hw[0], image_hw[1])
+
+
 def main():
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
-    for family in ("qwen2_5_vl", "qwen2_vl"):
+    for family in ("qwen2_5_vl", "qwen2_vl", "llava_onevision"):
         cfg = tiny_config(family)
         G, C, grid = 4, 12, (1, 8, 8)
-        ids, P, px = synthetic_batch(cfg, G, C, grid)
-        pos, deltas = mrope_position_ids(ids, [grid] * G, cfg)
+        if family == "llava_onevision":
+            ids, P, crops, grid = synthetic_batch_llava(cfg, G, C)
+            px = patchify_crops(crops, cfg.vision.patch_size)
+        else:
+            ids, P, px = synthetic_batch(cfg, G, C, grid)
+        pos, deltas = family_position_ids(ids, [grid] * G, cfg)
         ids_t, pos_t = torch.from_numpy(ids), torch.from_numpy(pos)
         grid_t = torch.tensor([grid] * G)
         comp = ids_t[:, P:]
@@ -53,12 +77,20 @@ def main():
 
         model = build_hf_model(cfg, seed=0, dtype=torch.float32)
         sd = {k: v.detach().to(torch.bfloat16).clone() for k, v in model.state_dict().items()}
-        logits = hf_logits(model, ids_t, px.repeat(G, 1), grid_t, pos_t, attn_mask)
+        if family == "llava_onevision":
+            sizes = torch.tensor([[grid[1], grid[2]]] * G)
+
+            def fwd(m):
+                return hf_logits_llava(m, ids_t, crops[None].repeat(G, 1, 1, 1, 1), sizes, pos_t[0], attn_mask)
+        else:
+            def fwd(m):
+                return hf_logits(m, ids_t, px.repeat(G, 1), grid_t, pos_t, attn_mask)
+        logits = fwd(model)
         logp = per_token_logps(logits, ids_t)[:, P - 1:]            # [G, C] fp32 oracle
         # reference-form bf16 pass (what the reference actually runs: bf16 model, bf16 log_softmax)
         m16 = build_hf_model(cfg, seed=0, dtype=torch.bfloat16)
         with torch.no_grad():
-            logp16 = per_token_logps(hf_logits(m16, ids_t, px.repeat(G, 1), grid_t, pos_t, attn_mask), ids_t)[:, P - 1:]
+            logp16 = per_token_logps(fwd(m16), ids_t)[:, P - 1:]
         del m16
         gen = torch.Generator().manual_seed(11)
         ref_logp = (logp.detach() + 0.3 * torch.randn(G, C, generator=gen)).contiguous()

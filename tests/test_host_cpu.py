@@ -147,6 +147,64 @@ def test_param_store_hf_names_roundtrip_cpu():
     assert ps.n_decay % 8 == 0 and all(o % 8 == 0 for o in ps.offsets.values())
 
 
+def test_llava_onevision_host_geometry_matches_hf():
+    """anyres bookkeeping of LLaVA-OneVision restated on the host (geometry.py) against the HF functions it follows:
+    select_best_resolution, and pack_image_features' row map (crop re-tiling, unpadding, image_newline per row)."""
+    transformers = pytest.importorskip("transformers")
+    from transformers.image_processing_utils import select_best_resolution as hf_sbr
+    from transformers.models.llava_onevision import modeling_llava_onevision as M
+    from iad_r1_b200.config import PRESETS, tiny_config, VLMConfig
+    from iad_r1_b200 import geometry as G
+    full = PRESETS["llava-ov-0.5b"]()
+    assert VLMConfig.from_hf_dict(full.to_hf_dict()).to_hf_dict() == full.to_hf_dict()
+    for hw in [(448, 448), (600, 800), (100, 80), (1000, 300), (384, 384), (500, 1500)]:
+        assert G.select_best_resolution(hw, full.extra["image_grid_pinpoints"]) == hf_sbr(hw, full.extra["image_grid_pinpoints"])
+    assert G.image_token_count(full, (5, 448, 448)) == 3699          # SURVEY.md section 8: 729 + 54 * (54 + 1)
+    cfg = tiny_config("llava_onevision")
+    tpc, H = cfg.vision.tokens_per_crop, 8
+
+    class _Cfg:                                                      # the only fields pack_image_features reads
+        class vision_config:
+            image_size, patch_size = cfg.vision.image_size, cfg.vision.patch_size
+        image_grid_pinpoints = cfg.extra["image_grid_pinpoints"]
+
+    class _Self:
+        config = _Cfg
+    for hw in [(80, 100), (100, 80), (56, 56), (112, 112), (60, 160), (150, 50)]:
+        idx, n_crops = G.llava_pack_index(cfg, hw)
+        feat = torch.arange(n_crops * tpc * H, dtype=torch.float32).view(n_crops, tpc, H)
+        newline = -torch.ones(H)
+        want, lens = M.LlavaOnevisionModel.pack_image_features(_Self, [feat], torch.tensor([hw]), image_newline=newline)
+        flat = feat.view(-1, H)
+        got = torch.where(torch.from_numpy(idx)[:, None] >= 0, flat[torch.from_numpy(idx).clamp(min=0).long()], newline[None])
+        assert torch.equal(got, want[0]) and int(lens[0]) == len(idx) == G.image_token_count(cfg, (n_crops, *hw)), hw
+    # plain 1-D positions with padding (Qwen2 under LLaVA): cumulative count of unmasked tokens
+    am = np.array([[0, 0, 1, 1, 1], [1, 1, 1, 1, 1]])
+    pos, delta = G.position_ids(np.zeros((2, 5), dtype=np.int64), [], cfg, am)
+    assert pos[0, 0].tolist() == [1, 1, 0, 1, 2] and pos[2, 1].tolist() == [0, 1, 2, 3, 4] and delta.tolist() == [-2, 0]
+    # patchify = the Conv2d patch embedding as a GEMM
+    x = torch.randn(3, 3, 56, 56)
+    w = torch.randn(96, 3, 14, 14)
+    ref = torch.nn.functional.conv2d(x, w, stride=14).flatten(2).transpose(1, 2).reshape(3 * 16, 96)
+    assert torch.allclose(G.patchify_crops(x, 14) @ w.reshape(96, -1).t(), ref, atol=1e-4)
+
+
+def test_param_store_llava_names_roundtrip_cpu():
+    from iad_r1_b200.config import tiny_config
+    from iad_r1_b200.params import ParamStore
+    fix = torch.load(os.path.join(ROOT, "tests", "golden", "tiny_llava_onevision.pt"), map_location="cpu", weights_only=False)
+    ps = ParamStore(tiny_config("llava_onevision"), "cpu", with_grads=True)
+    ps.load_hf_state_dict(fix["state_dict"])
+    sd = ps.hf_state_dict()
+    seen = 0
+    for k, v in fix["state_dict"].items():
+        k = ps.canonical_name(k)
+        if not k.endswith("lm_head.weight"):
+            assert torch.equal(sd[k].reshape(v.shape), v), k
+            seen += 1
+    assert seen == len(sd)
+
+
 def test_checkpoint_roundtrip(tmp_path):
     from iad_r1_b200.checkpoint import load_pretrained, save_pretrained
     from iad_r1_b200.config import tiny_config

@@ -38,7 +38,7 @@ def _sel(fix, dev):
     return rows, labels
 
 
-@pytest.mark.parametrize("family", ["qwen2_5_vl", "qwen2_vl"])
+@pytest.mark.parametrize("family", ["qwen2_5_vl", "qwen2_vl", "llava_onevision"])
 def test_logprobs_and_grads_match_hf(cuda, family):
     fix = _load(family)
     cfg, ps, vlm = _build(fix, cuda)
@@ -72,10 +72,15 @@ def test_logprobs_and_grads_match_hf(cuda, family):
     worst = (0.0, None)
     for name, gref in fix["grads"].items():
         name = ps.canonical_name(name)
-        if name == "lm_head.weight":
+        if name.endswith("lm_head.weight"):
             continue
         g = ours[name].float().cpu().reshape(gref.shape)
         gref = gref.float()
+        if name.endswith("k_proj.bias") and "vision_tower" in name:
+            # softmax is invariant to a shift of every key along q, so d/d(k bias) is exactly 0 in exact arithmetic: the
+            # oracle holds ~1e-9 rounding noise here, ours must be negligible next to the q bias gradient
+            assert g.norm() <= 1e-2 * ours[name.replace("k_proj", "q_proj")].float().norm().cpu() + 1e-6, name
+            continue
         rel = ((g - gref).norm() / (gref.norm() + 1e-12)).item()
         cosv = torch.nn.functional.cosine_similarity(g.flatten(), gref.flatten(), dim=0).item()
         if rel > worst[0]:
@@ -84,7 +89,7 @@ def test_logprobs_and_grads_match_hf(cuda, family):
     print(f"[{family}] worst gradient rel err {worst[0]:.4f} at {worst[1]} over {len(fix['grads'])} tensors")
 
 
-@pytest.mark.parametrize("family", ["qwen2_5_vl", "qwen2_vl"])
+@pytest.mark.parametrize("family", ["qwen2_5_vl", "qwen2_vl", "llava_onevision"])
 def test_shared_prefix_layout_matches_hf(cuda, family):
     """The production layout [prompt | G completions] (prompt computed once, ops.SharedPrefixAttention) against the same
     HF oracle fixture, which runs the reference's full [G, P + C] batch: same log-probs, same gradients."""
@@ -106,10 +111,12 @@ def test_shared_prefix_layout_matches_hf(cuda, family):
     worst = (0.0, None)
     for name, gref in fix["grads"].items():
         name = ps.canonical_name(name)
-        if name == "lm_head.weight":
+        if name.endswith("lm_head.weight"):
             continue
         g = ours[name].float().cpu().reshape(gref.shape)
         gref = gref.float()
+        if name.endswith("k_proj.bias") and "vision_tower" in name:
+            continue   # exactly zero in exact arithmetic (see the full-layout test)
         rel = ((g - gref).norm() / (gref.norm() + 1e-12)).item()
         cosv = torch.nn.functional.cosine_similarity(g.flatten(), gref.flatten(), dim=0).item()
         worst = max(worst, (rel, name))
@@ -117,12 +124,13 @@ def test_shared_prefix_layout_matches_hf(cuda, family):
     print(f"[{family}] shared-prefix worst gradient rel err {worst[0]:.4f} at {worst[1]}")
 
 
-def test_hf_state_dict_roundtrip(cuda):
-    fix = _load("qwen2_5_vl")
+@pytest.mark.parametrize("family", ["qwen2_5_vl", "llava_onevision"])
+def test_hf_state_dict_roundtrip(cuda, family):
+    fix = _load(family)
     cfg, ps, vlm = _build(fix, cuda)
     sd = ps.hf_state_dict()
     for k, v in fix["state_dict"].items():
         k = ps.canonical_name(k)
-        if k == "lm_head.weight":
+        if k.endswith("lm_head.weight"):
             continue
         assert torch.equal(sd[k].cpu().reshape(v.shape), v), k

@@ -96,11 +96,11 @@ def test_advantages_and_losses_match_oracle():
     assert torch.isnan(P.group_advantages(torch.ones(1, 1), 1)[0]).all()
 
 
-@pytest.mark.parametrize("family", ["qwen2_5_vl", "qwen2_vl"])
+@pytest.mark.parametrize("family", ["qwen2_5_vl", "qwen2_vl", "llava_onevision"])
 def test_golden_fixture_is_self_consistent(family):
     """The committed fixture reproduces from its own parts with the oracle (guards against a stale / edited fixture)."""
     fix = torch.load(os.path.join(GOLD, f"tiny_{family}.pt"), map_location="cpu", weights_only=False)
-    mask = R.completion_mask_ref(fix["input_ids"][:, fix["P"]:], {"qwen2_5_vl": 1005, "qwen2_vl": 1005}[family])
+    mask = R.completion_mask_ref(fix["input_ids"][:, fix["P"]:], 1005)
     assert torch.equal(mask, fix["completion_mask"])
     adv, _, _ = R.advantages_ref(fix["rewards_per_func"], fix["G"])
     assert torch.allclose(adv, fix["advantages"])
