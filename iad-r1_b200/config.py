@@ -238,8 +238,9 @@ def tiny_config(family: str = "qwen2_5_vl") -> VLMConfig:
                       head_dim=32, mrope_section=(4, 6, 6), tie_word_embeddings=True)
     if family == "llava_onevision":
         # head_dim 24 (not a power of two, like SigLIP's 72), 4 x 4 tokens per 56-pixel crop, 2 x 2 anyres grid
-        text = TextConfig(vocab_size=1024, hidden_size=128, intermediate_size=256, num_layers=2, num_heads=4,
-                          num_kv_heads=2, head_dim=32, mrope_section=(), tie_word_embeddings=True)
+        # text head_dim 64 (as Qwen2-0.5B): the rollout takes the tensor-core decode-attention path on the twin too
+        text = TextConfig(vocab_size=1024, hidden_size=128, intermediate_size=256, num_layers=2, num_heads=2,
+                          num_kv_heads=1, head_dim=64, mrope_section=(), tie_word_embeddings=True)
         vis = VisionConfig(kind="siglip", depth=2, hidden_size=96, num_heads=4, intermediate_size=200, out_hidden_size=128,
                            patch_size=14, spatial_merge_size=1, temporal_patch_size=1, window_size=0,
                            fullatt_block_indexes=(), image_size=56)

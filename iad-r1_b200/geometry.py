@@ -313,6 +313,30 @@ def patchify_crops(pixel_values: torch.Tensor, patch: int) -> torch.Tensor:
     patch embedding multiplies, in (crop, grid row, grid col) order with (channel, py, px) columns - so that the
     convolution is ONE GEMM against the flattened kernel (modeling_siglip.py:116-186)."""
     n, c, s, _ = pixel_values.shape
-    g = s // patch
-    x = pixel_values.reshape(n, c, g, patch, g, patch).permute(0, 2, 4, 1, 3, 5)
+    g = s // patch                 # a VALID convolution: 384 = 27 * 14 + 6, the last 6 pixel rows / columns are unused
+    x = pixel_values[:, :, :g * patch, :g * patch].reshape(n, c, g, patch, g, patch).permute(0, 2, 4, 1, 3, 5)
     return x.reshape(n * g * g, c * patch * patch).contiguous()
+
+
+def vision_inputs_from_processor(cfg: VLMConfig, enc) -> tuple:
+    """(pixel_values, grid) in the layout the vision kernels take, from a processor's output mapping.
+    Qwen processors already emit patch rows + `image_grid_thw`. LLaVA-OneVision processors emit crops
+    `pixel_values [n_images, n_crops_max, C, S, S]` (padded over images) + `image_sizes [n_images, 2]`: each image keeps
+    its own crops, which are cut into patch rows; grid entries become (n_crops, H, W)."""
+    pv = enc.get("pixel_values") if hasattr(enc, "get") else None
+    if pv is None:
+        return None, None
+    if "image_grid_thw" in enc:
+        g = enc["image_grid_thw"]
+        return pv, (g.tolist() if torch.is_tensor(g) else g)
+    if cfg.family != "llava_onevision" or "image_sizes" not in enc:
+        raise ValueError("processor output has pixel_values but neither image_grid_thw nor image_sizes")
+    sizes = enc["image_sizes"].tolist() if torch.is_tensor(enc["image_sizes"]) else enc["image_sizes"]
+    if pv.dim() == 4:
+        pv = pv[None]
+    rows, grid = [], []
+    for i, (h, w) in enumerate(sizes):
+        n, _, _, _ = llava_image_layout(cfg, (int(h), int(w)))
+        rows.append(patchify_crops(pv[i, :n], cfg.vision.patch_size))
+        grid.append((n, int(h), int(w)))
+    return torch.cat(rows, 0), grid

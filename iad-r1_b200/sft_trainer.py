@@ -28,6 +28,7 @@ from . import lib as L
 from .checkpoint import load_pretrained
 from .config import VLMConfig
 from .model import VLM
+from .geometry import vision_inputs_from_processor
 from .params import ParamStore
 from .trainer_base import TrainerCore, TrainerState
 
@@ -104,7 +105,8 @@ def load_sharegpt_dataset(name: str, dataset_dir: str = "data") -> list:
         return json.load(f)
 
 
-def encode_supervised_example(example: dict, processor, cutoff_len: int, image_dir: Optional[str], image_resolution: int):
+def encode_supervised_example(example: dict, processor, cutoff_len: int, image_dir: Optional[str], image_resolution: int,
+                              cfg=None):
     """messages -> (input_ids [T], labels [T] with IGNORE_INDEX outside assistant turns, pixel_values, grid_thw).
     Restates processors/supervised.py:34-88 for the multimodal single-image layout used by Expert-AD stage 1."""
     from PIL import Image
@@ -146,9 +148,9 @@ def encode_supervised_example(example: dict, processor, cutoff_len: int, image_d
         end = tok(k + 1, False)["input_ids"].shape[1]
         labels[start:end] = ids[start:end]
     ids, labels = ids[:cutoff_len], labels[:cutoff_len]
-    return dict(input_ids=ids.numpy().astype(np.int64), labels=labels.numpy().astype(np.int64),
-                pixel_values=full.get("pixel_values"),
-                grid_thw=full["image_grid_thw"].tolist() if "image_grid_thw" in full else None)
+    pv, grid = (full.get("pixel_values"), full["image_grid_thw"].tolist() if "image_grid_thw" in full else None) \
+        if cfg is None else vision_inputs_from_processor(cfg, full)
+    return dict(input_ids=ids.numpy().astype(np.int64), labels=labels.numpy().astype(np.int64), pixel_values=pv, grid_thw=grid)
 
 
 class PASFTTrainer(TrainerCore):
@@ -229,7 +231,7 @@ class PASFTTrainer(TrainerCore):
             win = bs * GA
             for w in range(0, len(order) - win + 1, win):
                 encs = [encode_supervised_example(self.train_dataset[j], self.processing_class, a.cutoff_len, a.image_dir,
-                                                  a.image_resolution) for j in order[w:w + win]]
+                                                  a.image_resolution, cfg=self.cfg) for j in order[w:w + win]]
                 n_items = max(1, sum(int((e["labels"][1:] != IGNORE_INDEX).sum()) for e in encs))
                 step_loss = torch.zeros((), device=self.device)
                 for e in encs:

@@ -30,12 +30,20 @@ class _Encoding(dict):
 
 class SyntheticProcessor:
     def __init__(self, cfg: VLMConfig, min_pixels: int = 3136, max_pixels: int = 12845056):
-        from transformers import Qwen2VLImageProcessor
         self.cfg = cfg
-        self.image_processor = Qwen2VLImageProcessor(min_pixels=min_pixels, max_pixels=max_pixels,
-                                                     patch_size=cfg.vision.patch_size,
-                                                     temporal_patch_size=cfg.vision.temporal_patch_size,
-                                                     merge_size=cfg.vision.spatial_merge_size)
+        self.llava = cfg.family == "llava_onevision"
+        if self.llava:
+            # the REAL HF anyres image processor (best-resolution select, resize + pad, 384-pixel crops + base crop)
+            from transformers import LlavaOnevisionImageProcessor
+            S = cfg.vision.image_size
+            self.image_processor = LlavaOnevisionImageProcessor(image_grid_pinpoints=cfg.extra["image_grid_pinpoints"],
+                                                                size={"height": S, "width": S})
+        else:
+            from transformers import Qwen2VLImageProcessor
+            self.image_processor = Qwen2VLImageProcessor(min_pixels=min_pixels, max_pixels=max_pixels,
+                                                         patch_size=cfg.vision.patch_size,
+                                                         temporal_patch_size=cfg.vision.temporal_patch_size,
+                                                         merge_size=cfg.vision.spatial_merge_size)
         self.pad_token_id, self.eos_token_id = cfg.pad_token_id, cfg.eos_token_id
         self.pad_token, self.eos_token = "<|endoftext|>", "<|im_end|>"
         self.tokenizer = self
@@ -57,7 +65,8 @@ class SyntheticProcessor:
             else:
                 for part in c:
                     if part.get("type") == "image":
-                        out.append("<|vision_start|><|image_pad|><|vision_end|>")
+                        # llava-onevision chat template: a bare <image> placeholder followed by a newline
+                        out.append("<|image_pad|>\n" if self.llava else "<|vision_start|><|image_pad|><|vision_end|>")
                     elif part.get("type") == "text":
                         out.append(part["text"])
             out.append("<|im_end|>\n")
@@ -82,17 +91,25 @@ class SyntheticProcessor:
         texts = [text] if isinstance(text, str) else list(text)
         enc = {}
         grids = []
+        counts = []
         if images is not None and len(images) > 0:
             im = self.image_processor(images=list(images), return_tensors="pt")
-            enc["pixel_values"], enc["image_grid_thw"] = im["pixel_values"], im["image_grid_thw"]
-            grids = im["image_grid_thw"].tolist()
-        merge = self.cfg.vision.spatial_merge_size ** 2
+            if self.llava:
+                from .geometry import image_token_count, llava_image_layout
+                enc["pixel_values"], enc["image_sizes"] = im["pixel_values"], im["image_sizes"]
+                for h, w in im["image_sizes"].tolist():
+                    n_crops = llava_image_layout(self.cfg, (h, w))[0]
+                    counts.append(image_token_count(self.cfg, (n_crops, h, w)))
+            else:
+                enc["pixel_values"], enc["image_grid_thw"] = im["pixel_values"], im["image_grid_thw"]
+                merge = self.cfg.vision.spatial_merge_size ** 2
+                counts = [g[0] * g[1] * g[2] // merge for g in im["image_grid_thw"].tolist()]
         rows, cursor = [], 0
         for t in texts:
-            while "<|image_pad|>" in t and cursor < len(grids):
-                g = grids[cursor]
+            while "<|image_pad|>" in t and cursor < len(counts):
+                n_tok = counts[cursor]
                 cursor += 1
-                t = t.replace("<|image_pad|>", "<|placeholder|>" * (g[0] * g[1] * g[2] // merge), 1)
+                t = t.replace("<|image_pad|>", "<|placeholder|>" * n_tok, 1)
             rows.append(self._tok(t.replace("<|placeholder|>", "<|image_pad|>")))
         P = max(len(r) for r in rows)
         ids = np.full((len(rows), P), self.pad_token_id, dtype=np.int64)

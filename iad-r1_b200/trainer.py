@@ -28,6 +28,7 @@ from .checkpoint import load_pretrained, save_pretrained
 from .config import VLMConfig
 from .grpo_config import GRPOConfig
 from .model import VLM
+from .geometry import vision_inputs_from_processor
 from .params import ParamStore
 from .rollout import RolloutEngine
 from .trainer_base import TrainerCore, TrainerState
@@ -91,10 +92,12 @@ class SCGRPOTrainer(TrainerCore):
         if isinstance(model, str):
             self.model_id = model
             mid = model.lower()
-            families = ("qwen2-vl", "qwen2_vl", "qwen2vl", "qwen2.5-vl", "qwen2.5_vl", "qwen2.5vl")
+            # family by substring of the model id, as the reference does (sc_grpo_trainer.py:116-137)
+            families = ("qwen2-vl", "qwen2_vl", "qwen2vl", "qwen2.5-vl", "qwen2.5_vl", "qwen2.5vl",
+                        "llava-ov", "llava_ov", "llava_si", "llava-onevision", "llava_onevision")
             if not any(k in mid for k in families):
-                # the reference raises ValueError for unknown families (sc_grpo_trainer.py:141-144); LLaVA families: §8f
-                raise ValueError(f"Unsupported model: {model} (B200 path supports Qwen2-VL / Qwen2.5-VL)")
+                # the reference raises ValueError for unknown families (sc_grpo_trainer.py:141-144); LLaVA-1.5 / -Next: §8f
+                raise ValueError(f"Unsupported model: {model} (B200 path supports Qwen2-VL / Qwen2.5-VL / LLaVA-OneVision)")
             self.cfg, self.params = load_pretrained(model, self.device)
         elif isinstance(model, VLMConfig):
             self.model_id = model.family
@@ -178,11 +181,10 @@ class SCGRPOTrainer(TrainerCore):
             ids = ids[enc["attention_mask"][0].bool()]
         if self.max_prompt_length is not None:
             ids = ids[-self.max_prompt_length:]  # Q14: ids only; cutting into image tokens raises downstream
-        pv = enc.get("pixel_values")
+        pv, grid = vision_inputs_from_processor(self.cfg, enc)
         if pv is not None and not pv.is_cuda:
             pv = pv.pin_memory().to(self.device, non_blocking=True)   # pinned staging -> async H2D
-        return dict(input_ids=ids.numpy().astype(np.int64), pixel_values=pv,
-                    grid_thw=enc["image_grid_thw"].tolist() if "image_grid_thw" in enc else None, text=text)
+        return dict(input_ids=ids.numpy().astype(np.int64), pixel_values=pv, grid_thw=grid, text=text)
 
     def _engine_for(self, n_groups: int, p_len: int) -> RolloutEngine:
         e = self._engine

@@ -5,12 +5,12 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _tiny_trainer(cuda, **over):
+def _tiny_trainer(cuda, family="qwen2_5_vl", **over):
     from iad_r1_b200.config import tiny_config
     from iad_r1_b200.grpo_config import GRPOConfig
     from iad_r1_b200.synthetic import SyntheticProcessor, format_reward, make_noise_reward
     from iad_r1_b200.trainer import SCGRPOTrainer
-    cfg = tiny_config("qwen2_5_vl")
+    cfg = tiny_config(family)
     kw = dict(output_dir="/tmp/iadr1_test", per_device_train_batch_size=1, gradient_accumulation_steps=2,
               num_generations=4, max_completion_length=16, max_prompt_length=512, learning_rate=1e-3, beta=0.04,
               logging_steps=1, save_strategy="no", max_steps=2, seed=7)
@@ -20,17 +20,18 @@ def _tiny_trainer(cuda, **over):
     return cfg, SCGRPOTrainer(model=cfg, reward_funcs=[format_reward, make_noise_reward(0)], args=args, processing_class=proc)
 
 
-def test_decode_matches_training_forward(cuda):
+@pytest.mark.parametrize("family", ["qwen2_5_vl", "llava_onevision"])
+def test_decode_matches_training_forward(cuda, family):
     """Teacher-forcing check of the whole rollout path: the log-prob the DECODE kernels assign to each sampled token
     (KV cache, prefix sharing, rope deltas, split-K atomics, fp32 residual) equals the TRAINING forward's log-prob of the
     same token. Tolerance 0.05 abs (decode keeps an fp32 residual stream, training rounds it to bf16 as HF does)."""
     from iad_r1_b200.rollout import RolloutEngine
     from iad_r1_b200.synthetic import synthetic_dataset
-    cfg, tr = _tiny_trainer(cuda)
+    cfg, tr = _tiny_trainer(cuda, family)
     data = synthetic_dataset(2, 112)
     encs = [tr._encode_prompt(ex) for ex in data]
     G, C = 4, 12
-    eng = RolloutEngine(tr.model, 2, G, 128, C, temperature=0.9, top_k=50, top_p=0.9, use_cuda_graph=False)
+    eng = RolloutEngine(tr.model, 2, G, 192, C, temperature=0.9, top_k=50, top_p=0.9, use_cuda_graph=False)
     rec = []
     out, stats = eng.generate(encs, seed=3, logits_hook=lambda s, lg: rec.append(lg.clone()))
     assert out.shape == (2 * G, C) and len(rec) == C
@@ -71,9 +72,10 @@ def test_cuda_graph_rollout_equals_eager(cuda):
     assert (outs[0] == outs[1]).float().mean().item() > 0.9
 
 
-def test_trainer_two_steps(cuda):
+@pytest.mark.parametrize("family", ["qwen2_5_vl", "llava_onevision"])
+def test_trainer_two_steps(cuda, family):
     from iad_r1_b200.synthetic import synthetic_dataset
-    cfg, tr = _tiny_trainer(cuda)
+    cfg, tr = _tiny_trainer(cuda, family)
     tr.train_dataset = synthetic_dataset(8, 112)
     before = tr.params.flat.clone()
     ref_before = tr.ref_model.params.flat.clone()
@@ -120,7 +122,7 @@ def test_sft_trainer_reduces_loss(cuda, tmp_path):
     from iad_r1_b200.config import tiny_config
     from iad_r1_b200.sft_trainer import PASFTTrainer, SFTArguments
     from iad_r1_b200.synthetic import SyntheticProcessor, synthetic_image
-    for family, frozen in (("qwen2_5_vl", False), ("qwen2_vl", True)):
+    for family, frozen in (("qwen2_5_vl", False), ("qwen2_vl", True), ("llava_onevision", False)):
         cfg = tiny_config(family)
         data = [{"messages": [{"role": "user", "content": "<image>Is there a defect in the image?"},
                               {"role": "assistant", "content": "<think> the surface is scratch </think> <answer> yes </answer>"}],
