@@ -160,7 +160,8 @@ def workload_config(args, cfg, world):
                         f"(per_device_batch={min(args.groups_per_pass, args.ga)} x grad_accum={args.ga // max(1, min(args.groups_per_pass, args.ga))}), "
                         f"beta=0.04 (reference model on), random-init weights",
             "groups_per_step": world * args.ga, "parallelism": f"dp{world}",
-            "l2": "working set (7.5 GB bf16 weights + activations) >> 126 MB L2; no explicit flush needed"}
+            "l2": "working set (bf16 weights of policy + reference and GBs of activations per pass) >> 126 MB L2; "
+                  "no explicit flush needed"}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -300,7 +301,7 @@ def run_ours(args):
         kv_avg = (GA * p_len + GA * G * (Cl / 2.0)) * kv_tok
         step_bytes = wd + wh + kv_avg
         dec_ms = phases.get("rollout", float("nan")) / max(1, Cl)
-        dec = {"bound": "hbm", "kernel": "decode step (CUDA graph: 36 x [rmsnorm, qkv, attention, o, rmsnorm, gate_up+SwiGLU, down] + lm_head + sampler)",
+        dec = {"bound": "hbm", "kernel": f"decode step (CUDA graph: {t_.num_layers} x [rmsnorm, qkv, attention, o, rmsnorm, gate_up+SwiGLU, down] + lm_head + sampler)",
                "achieved": step_bytes / (dec_ms / 1e3) / 1e9, "peak": hbm, "unit": "GB/s", "peak_source": f"hbm_gbs, {src}",
                "bytes_per_step": step_bytes, "ms_per_decode_step": dec_ms}
         dec["frac"] = dec["achieved"] / hbm

@@ -20,6 +20,13 @@ def completion_mask(completion_ids: torch.Tensor, eos_token_id: int) -> torch.Te
     return (torch.arange(C, device=completion_ids.device)[None, :] <= first[:, None]).int()
 
 
+def mask_truncated(mask: torch.Tensor, completion_ids: torch.Tensor, eos_token_id: int) -> torch.Tensor:
+    """`mask_truncated_completions` (ref: trl/trl/trainer/grpo_trainer.py:976-989): rows that never produced EOS are
+    dropped from the loss entirely."""
+    truncated = ~(completion_ids == eos_token_id).any(1)
+    return mask * (~truncated).int()[:, None]
+
+
 def group_advantages(rewards_per_func: torch.Tensor, num_generations: int, scale_rewards: bool = True,
                      reward_weights: torch.Tensor | None = None):
     """rewards_per_func [B*G, n_funcs] -> (advantages [B*G], rewards [B*G], per-row group std [B*G])."""

@@ -153,6 +153,9 @@ class SCGRPOTrainer(TrainerCore):
         self.callbacks = callbacks or []
         self._engine: Optional[RolloutEngine] = None
         self._rollout_cache: dict = {}
+        self._old_logps: dict = {}
+        if args.num_iterations > 1 and args.loss_mode != "clip":
+            raise ValueError("num_iterations > 1 needs loss_mode='clip' (the SC loss has no old-policy ratio)")
         self._sumsq = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._opt_step = 0
         self.phase_ms = defaultdict(float)
@@ -209,6 +212,7 @@ class SCGRPOTrainer(TrainerCore):
         return [out[i * G:(i + 1) * G] for i in range(len(encoded))]
 
     _rollout_calls = 0
+    _iteration = 0           # policy iteration inside the current generated window (num_iterations > 1)
 
     def prepare_window(self, examples: list):
         """Batched-rollout mode: roll out every group of the coming accumulation window together (the weights they are
@@ -229,11 +233,14 @@ class SCGRPOTrainer(TrainerCore):
             raise ValueError("The GRPOTrainer does not support returning outputs")
         G, dev, a = self.num_generations, self.device, self.args
         items = []
+        keep = self._iteration + 1 < max(1, a.num_iterations)   # the window is re-used for the next policy iteration
         for example in inputs:
-            cached = self._rollout_cache.pop(id(example), None)
+            cached = self._rollout_cache.get(id(example)) if keep else self._rollout_cache.pop(id(example), None)
             if cached is None:
                 enc = self._encode_prompt(example)
                 completion_ids = self._rollout([enc])[0]
+                if keep:
+                    self._rollout_cache[id(example)] = (enc, completion_ids)
             else:
                 enc, completion_ids = cached
             items.append((example, enc, completion_ids))
@@ -272,6 +279,17 @@ class SCGRPOTrainer(TrainerCore):
         """Mask, rewards, advantages and loss of ONE group from its [G, C] log-probs (ref: :722-726, :746-798)."""
         G, dev, a = self.num_generations, self.device, self.args
         mask = grpo_loss.completion_mask(completion_ids.long(), self.processing_class.eos_token_id)          # :722-726
+        if a.mask_truncated_completions and a.loss_mode == "clip":
+            mask = grpo_loss.mask_truncated(mask, completion_ids.long(), self.processing_class.eos_token_id)
+        # multi-iteration GRPO (trl grpo_trainer.py:872-901, 1066-1089): the first pass over a window records the
+        # log-probs the completions were sampled under; later passes clip the ratio against them
+        old_logps = None
+        if a.loss_mode == "clip" and a.num_iterations > 1:
+            if self._iteration == 0:
+                self._old_logps[id(example)] = logps.detach().clone()
+            old_logps = self._old_logps[id(example)]
+            if self._iteration + 1 >= a.num_iterations:
+                self._old_logps.pop(id(example), None)
         # ---- rewards on decoded text (CPU Python callbacks, verbatim convention :749-781) ----
         with self._phase("rewards"):
             texts = self.processing_class.batch_decode(completion_ids.cpu(), skip_special_tokens=True)
@@ -288,7 +306,7 @@ class SCGRPOTrainer(TrainerCore):
         if a.loss_mode == "sc":
             loss, mean_kl = grpo_loss.sc_grpo_loss(logps, ref_logps, adv, mask, self.beta)       # :796-798
         else:
-            loss, mean_kl = grpo_loss.clip_grpo_loss(logps, None, ref_logps, adv, mask, self.beta, a.epsilon,
+            loss, mean_kl = grpo_loss.clip_grpo_loss(logps, old_logps, ref_logps, adv, mask, self.beta, a.epsilon,
                                                      a.epsilon_high if a.epsilon_high is not None else a.epsilon,
                                                      a.loss_type, self.max_completion_length)
         # ---- metrics (:801-817); kept as device scalars, reduced across ranks at log time ----
@@ -323,9 +341,18 @@ class SCGRPOTrainer(TrainerCore):
                 window = [[self.train_dataset[j] for j in mb] for mb in micro[w:w + GA]]
                 if a.batched_rollout:
                     self.prepare_window([ex for mb in window for ex in mb])
-                for mb in window:
-                    tr_loss.append(self.training_step(mb))
-                self.optimizer_step()
+                # num_iterations optimizer steps per generated window (vendored TRL `num_iterations`, clip mode only)
+                n_iter = max(1, a.num_iterations) if a.loss_mode == "clip" else 1
+                for it in range(n_iter):
+                    self._iteration = it
+                    for mb in window:
+                        tr_loss.append(self.training_step(mb))
+                    self.optimizer_step()
+                    if self.state.global_step >= self.state.max_steps:
+                        break
+                self._iteration = 0
+                self._rollout_cache.clear()
+                self._old_logps.clear()
                 self.state.epoch = epoch + (w + GA) / max(1, len(micro))
                 if a.logging_steps and self.state.global_step % max(1, int(a.logging_steps)) == 0:
                     loss_val = torch.stack(tr_loss).mean().item()

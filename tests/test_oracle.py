@@ -70,6 +70,17 @@ def test_completion_mask_injected_ids():
     assert torch.equal(completion_mask(comp, eos), m)
 
 
+def test_mask_truncated_completions_kat():
+    """TRL's injected-completion case (ref: trl/tests/test_grpo_trainer.py:959-1008): ids [1..8] (no EOS, truncated),
+    [9,10,11,EOS,pad x4], [12..18,EOS]; with mask_truncated_completions the first row leaves the loss."""
+    from iad_r1_b200 import grpo_loss as P
+    eos, pad = 151645, 151643
+    comp = torch.tensor([[1, 2, 3, 4, 5, 6, 7, 8], [9, 10, 11, eos, pad, pad, pad, pad], [12, 13, 14, 15, 16, 17, 18, eos]])
+    m = P.completion_mask(comp, eos)
+    assert m.tolist() == [[1] * 8, [1, 1, 1, 1, 0, 0, 0, 0], [1] * 8]
+    assert P.mask_truncated(m, comp, eos).tolist() == [[0] * 8, [1, 1, 1, 1, 0, 0, 0, 0], [1] * 8]
+
+
 def test_advantages_and_losses_match_oracle():
     from iad_r1_b200 import grpo_loss as P
     torch.manual_seed(1)

@@ -93,6 +93,31 @@ def test_trainer_two_steps(cuda, family):
     assert logs[0]["kl"] < 1e-3  # first step: reference == policy
 
 
+def test_clip_mode_multi_iteration(cuda):
+    """Vendored-TRL semantics behind GRPOConfig.num_iterations (ref: trl/trl/trainer/grpo_trainer.py:872-901, 1182-1219):
+    one rollout per window, num_iterations optimizer steps over it, the ratio of the 2nd pass is taken against the
+    log-probs recorded in the 1st; truncated rows are masked out when mask_truncated_completions is set."""
+    from iad_r1_b200.synthetic import synthetic_dataset
+    cfg, tr = _tiny_trainer(cuda, loss_mode="clip", num_iterations=2, max_steps=4, loss_type="bnpo",
+                            mask_truncated_completions=False, learning_rate=5e-3)
+    tr.train_dataset = synthetic_dataset(8, 112)
+    calls = []
+    orig = tr._rollout
+    tr._rollout = lambda enc: (calls.append(len(enc)), orig(enc))[1]
+    out = tr.train()
+    assert out["global_step"] == 4
+    assert len(calls) == 2, "two windows -> two rollouts for four optimizer steps"
+    assert not tr._rollout_cache and not tr._old_logps
+    assert torch.isfinite(tr.params.flat.float()).all()
+    # all rows truncated (EOS forbidden) + mask_truncated_completions -> zero loss, zero gradient, parameters unchanged
+    cfg, tr = _tiny_trainer(cuda, loss_mode="clip", mask_truncated_completions=True, rollout_forbid_eos=True, beta=0.0,
+                            max_steps=1, loss_type="grpo")
+    tr.train_dataset = synthetic_dataset(4, 112)
+    before = tr.params.flat.clone()
+    tr.train()
+    assert torch.equal(before, tr.params.flat)
+
+
 def test_all_masked_gradient_is_zero(cuda):
     """TRL's 'no parameter change when every advantage is zero' twin (ref: trl/tests/test_grpo_trainer.py:1010-1047):
     a constant reward gives zero advantages, and with beta = 0 the gradient must vanish exactly."""
