@@ -212,9 +212,7 @@ def run_ours(args):
 
     def step_resident(i):
         win = encoded[i * GA:(i + 1) * GA]
-        comps = trainer._rollout([e for _, e in win])
-        for (ex, e), c in zip(win, comps):
-            trainer._rollout_cache[id(ex)] = (e, c)
+        trainer.prepare_window([ex for ex, _ in win], encoded=[e for _, e in win])   # pre-encoded prompts, HBM-resident pixels
         for j in range(0, GA, bs):
             trainer.training_step([ex for ex, _ in win[j:j + bs]])
         trainer.optimizer_step()

@@ -151,6 +151,18 @@ class VisionGeometry:
 
         self.full_lo, self.full_hi = ranges(cu_full)
         self.win_lo, self.win_hi = ranges(cu_win)
+
+        # equal-length segments (every image the same grid / every window full): attention runs as a BATCH of
+        # [segment x segment] problems instead of one masked [Np x Np] product (448 x 448: 16 windows of 64 patches)
+        def uniform(cu):
+            d = np.diff(cu)
+            return int(d[0]) if len(d) and (d == d[0]).all() and d[0] % 8 == 0 else 0
+
+        self.full_seg, self.win_seg = uniform(cu_full), uniform(cu_win)
+        self.seg_ranges = {}
+        for L_ in {self.full_seg, self.win_seg} - {0}:
+            self.seg_ranges[L_] = (torch.zeros(L_, dtype=torch.int32, device=device),
+                                   torch.full((L_,), L_, dtype=torch.int32, device=device))
         if window_index is not None:
             self.window_index = torch.from_numpy(window_index.astype(np.int32)).to(device)
             self.reverse_index = torch.from_numpy(np.argsort(window_index).astype(np.int32)).to(device)

@@ -107,6 +107,7 @@ class GRPOConfig:
     rollout_top_k: int = 50
     batched_rollout: bool = True               # roll out every group of an accumulation window in one decode batch
     shared_prefix: bool = True                 # score a group as [prompt | G completions]: the prompt is computed once
+    window_vision: bool = True                 # vision tower fwd/bwd once per accumulation window (batched_rollout only)
     rollout_forbid_eos: bool = False           # benchmarking only: fixed-length completions
     rollout_seed: Optional[int] = None
 

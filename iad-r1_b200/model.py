@@ -70,14 +70,20 @@ class VLM:
         x = ops.linear_fwd(px, p["visual.patch_embed.weight"])
         if geo.window_index is not None:
             x = ops.gather_rows(x.view(Np // unit, unit * E), geo.window_index).view(Np, E)
-        sh = ops.AttnShape(1, Np, nh, nh, hd, causal=False)
+        sh_masked = ops.AttnShape(1, Np, nh, nh, hd, causal=False)
         ctx = VisionCtx()
-        ctx.geo, ctx.px, ctx.blocks, ctx.sh = geo, px, [], sh
+        ctx.geo, ctx.px, ctx.blocks = geo, px, []
         q25 = v.kind == "qwen2_5_vl"
         for i in range(v.depth):
             b = f"visual.blocks.{i}."
             full = (not q25) or (i in v.fullatt_block_indexes)
-            lo, hi = (geo.full_lo, geo.full_hi) if full else (geo.win_lo, geo.win_hi)
+            seg = geo.full_seg if full else geo.win_seg
+            if seg:      # equal-length segments: a batch of [seg x seg] attention problems (no masked-out work)
+                sh = ops.AttnShape(Np // seg, seg, nh, nh, hd, causal=False)
+                lo, hi = geo.seg_ranges[seg]
+            else:        # ragged segments: one [Np x Np] product with per-row key ranges
+                sh = sh_masked
+                lo, hi = (geo.full_lo, geo.full_hi) if full else (geo.win_lo, geo.win_hi)
             if q25:
                 xn, st1 = ops.rmsnorm_fwd(x, p[b + "norm1.weight"], 1e-6)
             else:
@@ -99,7 +105,7 @@ class VLM:
                 act = ops.act_mul_fwd(gu, Ip, ops.ACT_QUICK_GELU, gated=False)
                 x_out = ops.linear_fwd(act, p[b + "fc2.weight"], bias=p[b + "fc2.bias"], residual=x_mid)
             if save:
-                ctx.blocks.append((x, st1, xn, qkv, P, attn, x_mid, st2, xn2, gu, act, lo, hi))
+                ctx.blocks.append((x, st1, xn, qkv, P, attn, x_mid, st2, xn2, gu, act, lo, hi, sh))
             x = x_out
         if q25:
             xq, stq = ops.rmsnorm_fwd(x, p["visual.merger.ln_q.weight"], 1e-6)
@@ -141,7 +147,7 @@ class VLM:
                               g["visual.merger.ln_q.weight"], g["visual.merger.ln_q.bias"], add_dx=False)
         for i in reversed(range(v.depth)):
             b = f"visual.blocks.{i}."
-            x, st1, xn, qkv, P, attn, x_mid, st2, xn2, gu, act, lo, hi = ctx.blocks[i]
+            x, st1, xn, qkv, P, attn, x_mid, st2, xn2, gu, act, lo, hi, sh = ctx.blocks[i]
             if q25:
                 dact = ops.linear_bwd(dx, act, p[b + "down.weight"], g[b + "down.weight"], g[b + "down.bias"])
                 dgu = ops.act_mul_bwd(dact, gu, Ip, ops.ACT_SILU, gated=True, dgu=gu)
@@ -154,7 +160,7 @@ class VLM:
                 ops.layernorm_bwd(dxn2, x_mid, p[b + "norm2.weight"], st2[0], st2[1], dx, g[b + "norm2.weight"],
                                   g[b + "norm2.bias"], add_dx=True)
             dattn = ops.linear_bwd(dx, attn, p[b + "proj.weight"], g[b + "proj.weight"], g[b + "proj.bias"])
-            dqkv = ops.attention_bwd(dattn, qkv, P, ctx.sh, lo, hi)
+            dqkv = ops.attention_bwd(dattn, qkv, P, sh, lo, hi)
             ops.rope_(dqkv, geo.cos, geo.sin, 2 * nh, hd, bf16_ops=0, backward=True)
             dxn = ops.linear_bwd(dqkv, xn, p[b + "qkv.weight"], g[b + "qkv.weight"], g[b + "qkv.bias"])
             if q25:
@@ -383,11 +389,19 @@ class VLM:
                     sel_index=torch.cat(sel), labels=torch.cat([b["labels"] for b in parts]), group_slices=slices)
 
     def logprobs_forward(self, batch: dict, sel_index: torch.Tensor, labels: torch.Tensor, temperature: float = 1.0,
-                         save: bool = True):
-        """log p(labels[j] | prefix) at hidden-state rows sel_index[j] (flattened b*T + t). Returns (logp fp32, ctx)."""
+                         save: bool = True, image_embeds: torch.Tensor | None = None, dimg_sink=None):
+        """log p(labels[j] | prefix) at hidden-state rows sel_index[j] (flattened b*T + t). Returns (logp fp32, ctx).
+        `image_embeds` [n_img_tokens, H]: features of this batch's images computed elsewhere (the trainer runs the vision
+        tower ONCE per accumulation window); their gradient is then handed to `dimg_sink(fp32 [n_img_tokens, H])` instead
+        of being pushed through the tower here."""
         img, vctx = (None, None)
         if batch["n_img_tokens"] > 0:
-            img, vctx = self.vision_forward(batch["pixel_values"], batch["grid"], save=save)
+            if image_embeds is not None:
+                if image_embeds.shape[0] != batch["n_img_tokens"]:
+                    raise ValueError(f"image_embeds has {image_embeds.shape[0]} rows, the batch needs {batch['n_img_tokens']}")
+                img = image_embeds
+            else:
+                img, vctx = self.vision_forward(batch["pixel_values"], batch["grid"], save=save)
         attn = batch["attn"] if batch.get("shared") else self.full_attention(batch["B"], batch["T"])
         h, dctx = self.decoder_forward(batch["src_index"], img, attn, batch["cos"], batch["sin"], save=save)
         hsel = ops.gather_rows(h, sel_index)
@@ -396,7 +410,8 @@ class VLM:
         ctx = None
         if save:
             ctx = dict(vctx=vctx, dctx=dctx, hsel=hsel, hn=hn, rf=rf, lse=lse, labels=labels, sel_index=sel_index,
-                       temperature=temperature, N=attn.n_tokens, n_img=batch["n_img_tokens"])
+                       temperature=temperature, N=attn.n_tokens, n_img=batch["n_img_tokens"],
+                       dimg_sink=dimg_sink if image_embeds is not None else None)
         return logp, ctx
 
     def logprobs_backward(self, dlogp: torch.Tensor, ctx: dict):
@@ -411,5 +426,7 @@ class VLM:
         ops.scatter_add_rows(dhsel, ctx["sel_index"], dh32, None)
         dh = ops.cast_f32_bf16(dh32)
         dimg32 = self.decoder_backward(dh, ctx["dctx"], ctx["n_img"])
-        if dimg32 is not None and ctx["vctx"] is not None:
+        if dimg32 is not None and ctx.get("dimg_sink") is not None:
+            ctx["dimg_sink"](dimg32)
+        elif dimg32 is not None and ctx["vctx"] is not None:
             self.vision_backward(ops.cast_f32_bf16(dimg32), ctx["vctx"])

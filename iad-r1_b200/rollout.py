@@ -154,7 +154,7 @@ class RolloutEngine:
     # ---------------------------------------------------------------------------------------------------------------
     @torch.no_grad()
     def generate(self, prompts: list, seed: int = 0, max_new_tokens: int | None = None, sync_every: int = 32,
-                 logits_hook=None):
+                 logits_hook=None, image_embeds: torch.Tensor | None = None):
         """prompts: list (<= max_groups) of dicts {input_ids [P] (list/array), pixel_values, grid_thw}.
         Returns (completion_ids int32 [n_groups_used * G, C] on device, stats dict)."""
         n = len(prompts)
@@ -190,7 +190,8 @@ class RolloutEngine:
         batch = vlm.prepare_batch(ids, pv, grids if grids else None, position_ids=torch.from_numpy(pos), attention_mask=am)
         img = None
         if batch["n_img_tokens"] > 0:
-            img, _ = vlm.vision_forward(batch["pixel_values"], batch["grid"], save=False)
+            # `image_embeds`: the trainer already ran the vision tower over the window's images (same weights)
+            img = image_embeds if image_embeds is not None else vlm.vision_forward(batch["pixel_values"], batch["grid"], save=False)[0]
         nq, nkv, hd = t.num_heads, t.num_kv_heads, t.head_dim
 
         def sink(layer, qkv):

@@ -57,8 +57,9 @@ class _LogProbFn(torch.autograd.Function):
     drives model.logprobs_backward."""
 
     @staticmethod
-    def forward(ctx, anchor, vlm, batch, rows, labels, temperature):
-        logp, saved = vlm.logprobs_forward(batch, rows, labels, temperature, save=True)
+    def forward(ctx, anchor, vlm, batch, rows, labels, temperature, image_embeds=None, dimg_sink=None):
+        logp, saved = vlm.logprobs_forward(batch, rows, labels, temperature, save=True, image_embeds=image_embeds,
+                                           dimg_sink=dimg_sink)
         ctx.vlm, ctx.saved = vlm, saved
         return logp
 
@@ -66,7 +67,7 @@ class _LogProbFn(torch.autograd.Function):
     def backward(ctx, dlogp):
         ctx.vlm.logprobs_backward(dlogp.contiguous(), ctx.saved)
         ctx.saved = None
-        return None, None, None, None, None, None
+        return None, None, None, None, None, None, None, None
 
 
 class SCGRPOTrainer(TrainerCore):
@@ -199,28 +200,84 @@ class SCGRPOTrainer(TrainerCore):
                                              top_p=a.rollout_top_p, forbid_eos=a.rollout_forbid_eos)
         return e
 
-    def _rollout(self, encoded: list) -> list:
+    def _rollout(self, encoded: list, image_embeds=None) -> list:
         """Sample G completions for each encoded prompt in ONE decode batch. Returns a list of [G, C] int32 tensors."""
         eng = self._engine_for(len(encoded), max(len(e["input_ids"]) for e in encoded))
         seed = self.args.rollout_seed if self.args.rollout_seed is not None else self.args.seed
         seed = (seed * 1000003 + self.state.global_step * 8191 + self.rank * 131 + self._rollout_calls) & 0x7FFFFFFF
         self._rollout_calls += 1
         with self._phase("rollout"):
-            out, stats = eng.generate(encoded, seed=seed)
+            out, stats = eng.generate(encoded, seed=seed, image_embeds=image_embeds)
         G = self.num_generations
         self.total_rollout_tokens += out.numel()
         return [out[i * G:(i + 1) * G] for i in range(len(encoded))]
 
     _rollout_calls = 0
+    _window = None           # per-window vision state (features, saved activations, gradient accumulator)
     _iteration = 0           # policy iteration inside the current generated window (num_iterations > 1)
 
-    def prepare_window(self, examples: list):
+    def prepare_window(self, examples: list, encoded: Optional[list] = None):
         """Batched-rollout mode: roll out every group of the coming accumulation window together (the weights they are
-        sampled from are the weights at the start of the optimizer step, as in the reference: Q12)."""
-        enc = [self._encode_prompt(ex) for ex in examples]
-        comps = self._rollout(enc)
+        sampled from are the weights at the start of the optimizer step, as in the reference: Q12).
+
+        The vision tower also runs ONCE per window here: policy features of all the window's images in one pass (saved for
+        the backward; the same features feed the rollout prefill and every scoring pass - the reference runs the tower
+        G times per forward on tiled pixels, :624-628), reference-model features in one no-grad pass. The gradient of the
+        policy features is accumulated over the window's passes and pushed through the tower once, before the optimizer
+        step (`_flush_window_vision`)."""
+        enc = [self._encode_prompt(ex) for ex in examples] if encoded is None else encoded
+        self._window = None
+        img = None
+        if self.args.window_vision and all(e["pixel_values"] is not None for e in enc):
+            from .geometry import image_token_count
+            pv = torch.cat([e["pixel_values"].to(self.device) for e in enc], 0)
+            grids = [g_ for e in enc for g_ in e["grid_thw"]]
+            with self._phase("vision_fwd"):
+                img, vctx = self.model.vision_forward(pv, grids, save=True)
+                ref_img = None
+                if self.ref_model is not None:
+                    with torch.no_grad():
+                        ref_img, _ = self.ref_model.vision_forward(pv, grids, save=False)
+            slices, off = {}, 0
+            for ex, e in zip(examples, enc):
+                n = sum(image_token_count(self.cfg, g_) for g_ in e["grid_thw"])
+                slices[id(ex)] = (off, off + n)
+                off += n
+            self._window = dict(img=img, ref_img=ref_img, vctx=vctx, slices=slices,
+                                dimg=torch.zeros(off, self.cfg.text.hidden_size, dtype=torch.float32, device=self.device))
+        comps = self._rollout(enc, image_embeds=img)
         for ex, e, c in zip(examples, enc, comps):
             self._rollout_cache[id(ex)] = (e, c)
+
+    def _window_features(self, examples: list):
+        """(policy image embeds, reference image embeds, gradient sink) for a micro-batch whose groups all belong to the
+        current window, else (None, None, None) -> the pass runs its own vision tower."""
+        w = self._window
+        if w is None or w["vctx"] is None or any(id(ex) not in w["slices"] for ex in examples):
+            return None, None, None
+        rng = [w["slices"][id(ex)] for ex in examples]
+        img = torch.cat([w["img"][lo:hi] for lo, hi in rng], 0)
+        ref = torch.cat([w["ref_img"][lo:hi] for lo, hi in rng], 0) if w["ref_img"] is not None else None
+
+        def sink(dimg32):
+            o = 0
+            for lo, hi in rng:
+                w["dimg"][lo:hi] += dimg32[o:o + hi - lo]
+                o += hi - lo
+        return img, ref, sink
+
+    def _flush_window_vision(self):
+        """Vision-tower backward of the whole window (once), then the window's features are stale (weights change)."""
+        w = self._window
+        if w is not None and w["vctx"] is not None:
+            from . import ops
+            with self._phase("backward"):
+                self.model.vision_backward(ops.cast_f32_bf16(w["dimg"]), w["vctx"])
+        self._window = None
+
+    def optimizer_step(self):
+        self._flush_window_vision()
+        super().optimizer_step()
 
     # ---------------------------------------------------------------------------------------------------------------
     # the hot path: one micro-step (ref: sc_grpo_trainer.py:586-819)
@@ -249,7 +306,7 @@ class SCGRPOTrainer(TrainerCore):
             batch = self.model.prepare_groups([dict(prompt_ids=enc["input_ids"], completion_ids=c, pixel_values=enc["pixel_values"],
                                                     grid_thw=enc["grid_thw"]) for _, enc, c in items])
             rows, labels, slices = batch["sel_index"], batch["labels"], batch["group_slices"]
-            logps_all, ref_all = self._score(batch, rows, labels, temp)
+            logps_all, ref_all = self._score(batch, rows, labels, temp, self._window_features([ex for ex, _, _ in items]))
             per_group = [(logps_all[lo:hi], None if ref_all is None else ref_all[lo:hi]) for lo, hi in slices]
         else:
             per_group = []
@@ -264,15 +321,16 @@ class SCGRPOTrainer(TrainerCore):
                   for (ex, _, c), (lp, rf) in zip(items, per_group)]
         return torch.stack(losses).mean()
 
-    def _score(self, batch, rows, labels, temp):
+    def _score(self, batch, rows, labels, temp, window_feats=(None, None, None)):
         """Policy log-probs (with the CUDA backward attached) and reference log-probs (no grad), :733-743."""
+        img, ref_img, sink = window_feats
         anchor = torch.zeros((), device=self.device, requires_grad=True)
         with self._phase("policy_fwd"):
-            logps = _LogProbFn.apply(anchor, self.model, batch, rows, labels, temp)
+            logps = _LogProbFn.apply(anchor, self.model, batch, rows, labels, temp, img, sink)
         ref_logps = None
         if self.ref_model is not None:
             with torch.no_grad(), self._phase("ref_fwd"):
-                ref_logps, _ = self.ref_model.logprobs_forward(batch, rows, labels, temp, save=False)
+                ref_logps, _ = self.ref_model.logprobs_forward(batch, rows, labels, temp, save=False, image_embeds=ref_img)
         return logps, ref_logps
 
     def _group_loss(self, example: dict, completion_ids: torch.Tensor, logps: torch.Tensor, ref_logps) -> torch.Tensor:

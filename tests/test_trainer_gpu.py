@@ -93,6 +93,33 @@ def test_trainer_two_steps(cuda, family):
     assert logs[0]["kl"] < 1e-3  # first step: reference == policy
 
 
+@pytest.mark.parametrize("family", ["qwen2_5_vl", "llava_onevision"])
+def test_window_vision_matches_per_pass_vision(cuda, family):
+    """Running the vision tower once per accumulation window (features shared by the rollout prefill and every scoring
+    pass, one backward over the accumulated feature gradient) gives the same completions and the same accumulated
+    gradient as running it inside every pass (bf16 summation order aside)."""
+    from iad_r1_b200.synthetic import synthetic_dataset
+    data = synthetic_dataset(4, 112)
+    grads, comps = [], []
+    for wv in (True, False):
+        cfg, tr = _tiny_trainer(cuda, family, window_vision=wv, per_device_train_batch_size=2, gradient_accumulation_steps=2)
+        tr.prepare_window(data)
+        assert (tr._window is not None) == wv
+        comps.append(torch.cat([tr._rollout_cache[id(ex)][1] for ex in data]))
+        for j in range(0, 4, 2):
+            tr.training_step(data[j:j + 2])
+        tr._flush_window_vision()
+        torch.cuda.synchronize()
+        grads.append(tr.params.grad_flat.clone())
+    assert torch.equal(comps[0], comps[1]), "same features -> same sampled completions"
+    cosv = torch.nn.functional.cosine_similarity(grads[0], grads[1], dim=0).item()
+    rel = ((grads[0] - grads[1]).norm() / grads[1].norm()).item()
+    print(f"\n[{family}] window-vision vs per-pass gradient: cos {cosv:.6f}, rel {rel:.4f}")
+    assert cosv > 0.9995 and rel < 0.03
+    vis = tr.params.g["visual.blocks.0.qkv.weight"]
+    assert vis.abs().sum() > 0
+
+
 def test_clip_mode_multi_iteration(cuda):
     """Vendored-TRL semantics behind GRPOConfig.num_iterations (ref: trl/trl/trainer/grpo_trainer.py:872-901, 1182-1219):
     one rollout per window, num_iterations optimizer steps over it, the ratio of the 2nd pass is taken against the
@@ -103,7 +130,7 @@ def test_clip_mode_multi_iteration(cuda):
     tr.train_dataset = synthetic_dataset(8, 112)
     calls = []
     orig = tr._rollout
-    tr._rollout = lambda enc: (calls.append(len(enc)), orig(enc))[1]
+    tr._rollout = lambda enc, **kw: (calls.append(len(enc)), orig(enc, **kw))[1]
     out = tr.train()
     assert out["global_step"] == 4
     assert len(calls) == 2, "two windows -> two rollouts for four optimizer steps"
