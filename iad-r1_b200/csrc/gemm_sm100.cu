@@ -784,8 +784,14 @@ int launch_gemm(const iadr1_gemm_t& d, cudaStream_t stream) {
   const int stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023);
   // TMEM: two accumulator stages of block_n fp32 columns; the co-resident variant allocates only what it needs
   g.tmem_cols = 512;
-  if (d.co_resident) {
-    if (g.block_n > 128) return set_error("gemm: co_resident needs block_n <= 128");
+  bool co_resident = d.co_resident != 0;
+  {
+    // two CTAs per SM only when a >= 3-stage ring (plus the epilogue staging tile) fits in half the shared memory
+    const int epi_b = (g.trans_c && g.atomic && g.c_f32) || g.epi == EPI_SWIGLU ? g.block_n * BM * 4 : 0;
+    const int stage_b = BM * BK * 2 + ((g.block_n * BK * 2 + 1023) & ~1023);
+    if (g.block_n > 128 || (113 * 1024 - 1024 - 512 - epi_b) / stage_b < 3) co_resident = false;
+  }
+  if (co_resident) {
     g.tmem_cols = 32;
     while (g.tmem_cols < 2 * g.block_n) g.tmem_cols <<= 1;
   }
@@ -793,7 +799,7 @@ int launch_gemm(const iadr1_gemm_t& d, cudaStream_t stream) {
   g.bulk_red = g.trans_c && g.atomic && g.c_f32 && g.epi == EPI_STORE && g.residual == nullptr && g.batch == 1 &&
                (g.M % 4 == 0) && (g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) && !d.no_bulk_red;
   const int epi_bytes = (g.bulk_red || g.epi == EPI_SWIGLU) ? g.block_n * BM * 4 : 0;
-  const int smem_budget = (d.co_resident ? 113 : 227) * 1024 - 1024 - 512 - epi_bytes;
+  const int smem_budget = (co_resident ? 113 : 227) * 1024 - 1024 - 512 - epi_bytes;
   int stages = smem_budget / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (d.stages > 0 && d.stages < stages) stages = d.stages;
@@ -834,12 +840,12 @@ int launch_gemm(const iadr1_gemm_t& d, cudaStream_t stream) {
   const int tiles_n = (g.N + g.block_n - 1) / g.block_n;
   const long long total = (long long)tiles_m * tiles_n * g.split_k * g.batch;
   int grid = (int)(total < (long long)num_sms() ? total : num_sms());
-  if (d.co_resident) grid = (int)(total < 2LL * num_sms() ? total : 2LL * num_sms());   // two CTAs per SM stream concurrently
+  if (co_resident) grid = (int)(total < 2LL * num_sms() ? total : 2LL * num_sms());   // two CTAs per SM stream concurrently
   if (g.stream_k) grid = num_sms();   // every SM takes an equal run of k-block units (K / 64 >= 1 each tile)
   if (d.max_ctas > 0 && grid > d.max_ctas) grid = d.max_ctas;
   cudaEvent_t pe0, pe1;
   const bool timed = prof_begin(stream, &pe0, &pe1);
-  if (d.co_resident)
+  if (co_resident)
     launch_kernel(gemm_bf16_tcgen05_kernel<2>, dim3(grid), dim3(kThreads), smem_bytes, stream, tmA, tmB, g);
   else
     launch_kernel(gemm_bf16_tcgen05_kernel<1>, dim3(grid), dim3(kThreads), smem_bytes, stream, tmA, tmB, g);
