@@ -38,8 +38,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="qwen2.5-vl-3b")
-    ap.add_argument("--ga", type=int, default=8,
-                    help="gradient_accumulation_steps = groups rolled out together per rank (reference scripts use 2)")
+    ap.add_argument("--ga", type=int, default=16,
+                    help="groups per optimizer step per rank = groups rolled out together (G x ga rows decode in lock-step; "
+                         "the reference scripts use per_device_batch 1 x grad_accum 2)")
     ap.add_argument("--groups-per-pass", type=int, default=2,
                     help="per_device_train_batch_size: groups packed into one forward/backward pass")
     ap.add_argument("--completion-len", type=int, default=512)

@@ -563,15 +563,15 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<const uint32_t*>(&v);
 }
 
-template <int HD>
-__global__ void __launch_bounds__(128) decode_attn_mma_kernel(
+template <int HD, int NW>
+__global__ void __launch_bounds__(NW * 32) decode_attn_mma_kernel(
     const float* __restrict__ qkv, const float* __restrict__ cos_tab, const float* __restrict__ sin_tab,
     const int* __restrict__ rope_delta, const bf16* __restrict__ kp, const bf16* __restrict__ vp, bf16* __restrict__ kc,
     bf16* __restrict__ vc, const int* __restrict__ state, const int* __restrict__ row_group,
     const int* __restrict__ row_plen, float* __restrict__ part, int* __restrict__ tickets, bf16* __restrict__ out, int nq,
     int nkv, int p_max, int c_max, int max_pos, float scale) {
   if (threadIdx.x == 0) pdl_trigger();   // dependents may become resident (and prefetch) right away
-  constexpr int HALF = HD / 2, PPR = HD / 8, CK = 64, MAXG = 8, NKS = HD / 16, NOB = HD / 8, EPL = HD / 32;
+  constexpr int HALF = HD / 2, PPR = HD / 8, NT = NW * 32, CK = 16 * NW, MAXG = 8, NKS = HD / 16, NOB = HD / 8, EPL = HD / 32;
   const int r = blockIdx.x, kvh = blockIdx.y, sp = blockIdx.z, nsplit = gridDim.z;
   const int gq = nq / nkv;
   const int lane = threadIdx.x & 31;
@@ -609,7 +609,7 @@ __global__ void __launch_bounds__(128) decode_attn_mma_kernel(
     bf16* sK = sKV + (c & 1) * STAGE;
     bf16* sV = sK + CK * HD;
     const int base = k0 + c * CK;
-    for (int q = threadIdx.x; q < CK * PPR; q += 128) {
+    for (int q = threadIdx.x; q < CK * PPR; q += NT) {
       const int jj = q / PPR, piece = q % PPR;
       const int j = base + jj;
       const int off = jj * HD + ((piece ^ (jj & 7)) << 3);
@@ -636,32 +636,37 @@ __global__ void __launch_bounds__(128) decode_attn_mma_kernel(
   {
     // thread = one head-dim column d of up to MAXG heads: all global loads are issued before the first use (one L2
     // round trip instead of one per head)
-    constexpr int TPH = 128 / HD;               // threads per column group
+    constexpr int CPT = HD > NT ? HD / NT : 1;  // columns per thread (NT < HD: a thread owns several columns)
+    constexpr int TPH = NT > HD ? NT / HD : 1;  // thread groups sharing the column range, each taking every TPH-th head
     constexpr int HPT = MAXG / TPH;             // heads per thread
-    const int d = threadIdx.x % HD, hsel = threadIdx.x / HD;
-    const int dp = d < HALF ? d + HALF : d - HALF;
-    const float cd = bf16r(cs[d]), sd = bf16r(sn[d]);
-    float xv[HPT], xpv[HPT];
+    const int hsel = TPH > 1 ? threadIdx.x / HD : 0;
 #pragma unroll
-    for (int hh = 0; hh < HPT; ++hh) {
-      const int h = hh * TPH + hsel;
-      const float* xh = xrow + (long long)(kvh * gq + min(h, gq - 1)) * HD;
-      xv[hh] = xh[d];
-      xpv[hh] = xh[dp];
-    }
+    for (int cc = 0; cc < CPT; ++cc) {
+      const int d = (TPH > 1 ? threadIdx.x % HD : threadIdx.x) + cc * NT;
+      const int dp = d < HALF ? d + HALF : d - HALF;
+      const float cd = bf16r(cs[d]), sd = bf16r(sn[d]);
+      float xv[HPT], xpv[HPT];
 #pragma unroll
-    for (int hh = 0; hh < HPT; ++hh) {
-      const int h = hh * TPH + hsel;
-      const float a = bf16r(bf16r(xv[hh]) * cd);
-      const float xp = bf16r(xpv[hh]);
-      const float b = bf16r((d < HALF ? -xp : xp) * sd);
-      const float v = (h < gq) ? bf16r(a + b) * scale : 0.f;
-      sQ[h * HD + ((((d >> 3) ^ (h & 7)) << 3) | (d & 7))] = __float2bfloat16(v);
-      sQ[(h + 8) * HD + ((((d >> 3) ^ (h & 7)) << 3) | (d & 7))] = __float2bfloat16(0.f);   // padding rows 8..15
+      for (int hh = 0; hh < HPT; ++hh) {
+        const int h = hh * TPH + hsel;
+        const float* xh = xrow + (long long)(kvh * gq + min(h, gq - 1)) * HD;
+        xv[hh] = xh[d];
+        xpv[hh] = xh[dp];
+      }
+#pragma unroll
+      for (int hh = 0; hh < HPT; ++hh) {
+        const int h = hh * TPH + hsel;
+        const float a = bf16r(bf16r(xv[hh]) * cd);
+        const float xp = bf16r(xpv[hh]);
+        const float b = bf16r((d < HALF ? -xp : xp) * sd);
+        const float v = (h < gq) ? bf16r(a + b) * scale : 0.f;
+        sQ[h * HD + ((((d >> 3) ^ (h & 7)) << 3) | (d & 7))] = __float2bfloat16(v);
+        sQ[(h + 8) * HD + ((((d >> 3) ^ (h & 7)) << 3) | (d & 7))] = __float2bfloat16(0.f);   // padding rows 8..15
+      }
     }
   }
   const bool has_new = (ctx - 1 >= k0) && (ctx - 1 < k1);
-  if (has_new && warp == 3) {
+  if (has_new && warp == NW - 1) {
     const float* knew = xrow + (long long)(nq + kvh) * HD;
     const float* vnew = xrow + (long long)(nq + nkv + kvh) * HD;
     bf16* kdst = kc + (((long long)r * c_max + step) * nkv + kvh) * HD;
@@ -768,7 +773,7 @@ __global__ void __launch_bounds__(128) decode_attn_mma_kernel(
     if (c + 2 < nchunks) stage(c + 2);          // re-fill it two chunks ahead
   }
   // ---- merge the 4 warps (rows = heads < gq live in c0/c1 of the lanes with lane/4 == head); staging memory re-used
-  float (*sm_mrg)[MAXG][HD + 2] = reinterpret_cast<float (*)[MAXG][HD + 2]>(sm_kv_raw);
+  float (*sm_mrg)[MAXG][HD + 2] = reinterpret_cast<float (*)[MAXG][HD + 2]>(sm_kv_raw);   // NW x MAXG x (HD + 2) floats <= staging
   const int row_lo = lane >> 2;
   if (row_lo < MAXG) {
 #pragma unroll
@@ -782,14 +787,14 @@ __global__ void __launch_bounds__(128) decode_attn_mma_kernel(
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < gq * HD; i += 128) {
+  for (int i = threadIdx.x; i < gq * HD; i += NT) {
     const int h = i / HD, d = i % HD;
     float m = -INFINITY;
 #pragma unroll
-    for (int w = 0; w < 4; ++w) m = fmaxf(m, sm_mrg[w][h][HD]);
+    for (int w = 0; w < NW; ++w) m = fmaxf(m, sm_mrg[w][h][HD]);
     float a = 0.f, l = 0.f;
 #pragma unroll
-    for (int w = 0; w < 4; ++w) {
+    for (int w = 0; w < NW; ++w) {
       const float mw = sm_mrg[w][h][HD];
       const float cf = (mw == -INFINITY) ? 0.f : __expf(mw - m);
       a += sm_mrg[w][h][d] * cf;
@@ -818,7 +823,7 @@ __global__ void __launch_bounds__(128) decode_attn_mma_kernel(
   constexpr int MAXS = 32;
   __shared__ float s_c[MAXG][MAXS];
   __shared__ float s_invl[MAXG];
-  for (int h = warp; h < gq; h += 4) {
+  for (int h = warp; h < gq; h += NW) {
     const float* p = part + ((long long)r * nq + kvh * gq + h) * nsplit * (HD + 2);
     const float ms = (lane < nsplit) ? __ldcg(p + lane * (HD + 2) + HD) : -INFINITY;
     const float ls = (lane < nsplit) ? __ldcg(p + lane * (HD + 2) + HD + 1) : 0.f;
@@ -831,7 +836,7 @@ __global__ void __launch_bounds__(128) decode_attn_mma_kernel(
     if (lane == 0) s_invl[h] = 1.f / l;
   }
   __syncthreads();
-  constexpr int OUTS = (MAXG * HD + 127) / 128;
+  constexpr int OUTS = (MAXG * HD + NT - 1) / NT;
   float a8[OUTS];
 #pragma unroll
   for (int oo = 0; oo < OUTS; ++oo) a8[oo] = 0.f;
@@ -840,7 +845,7 @@ __global__ void __launch_bounds__(128) decode_attn_mma_kernel(
   for (int s2 = 0; s2 < nsplit; ++s2) {
 #pragma unroll
     for (int oo = 0; oo < OUTS; ++oo) {
-      const int o = threadIdx.x + 128 * oo;
+      const int o = threadIdx.x + NT * oo;
       if (o < gq * HD) {
         const int h = o / HD, d = o % HD;
         a8[oo] += __ldcg(pbase + ((long long)h * nsplit + s2) * (HD + 2) + d) * s_c[h][s2];
@@ -849,7 +854,7 @@ __global__ void __launch_bounds__(128) decode_attn_mma_kernel(
   }
 #pragma unroll
   for (int oo = 0; oo < OUTS; ++oo) {
-    const int o = threadIdx.x + 128 * oo;
+    const int o = threadIdx.x + NT * oo;
     if (o < gq * HD) {
       const int h = o / HD, d = o % HD;
       out[((long long)r * nq + kvh * gq + h) * HD + d] = __float2bfloat16(a8[oo] * s_invl[h]);
@@ -1247,27 +1252,33 @@ int iadr1_decode_attention_fused(const float* qkv, const float* cos_tab, const f
                                  void* stream) {
   if (rows <= 0) return 0;
   if (nq % nkv || nq / nkv > 8) return set_error("decode_attention_fused: group size %d unsupported (max 8)", nq / nkv);
-  if (nsplit < 1 || nsplit > 32) return set_error("decode_attention_fused: nsplit %d out of range (1..32)", nsplit);
+  if (nsplit == 0 || nsplit > 32 || nsplit < -32) return set_error("decode_attention_fused: nsplit %d out of range", nsplit);
   cudaStream_t st = (cudaStream_t)stream;
   static const int dbg = getenv("IADR1_ATTN_DEBUG") ? atoi(getenv("IADR1_ATTN_DEBUG")) : 0;  // phase-skipping, probes only
   static const bool use_mma = !(getenv("IADR1_DECODE_ATTN") && std::string(getenv("IADR1_DECODE_ATTN")) == "scalar");
   if ((hd == 128 || hd == 64) && use_mma) {
-    // tensor-core path: any nsplit; every CTA walks its balanced share of the live context in 64-key chunks
-    const size_t smem = (size_t)2 * 2 * 64 * hd * 2;
-    if (hd == 128) {
-      static bool attr = false;
-      if (!attr) {
-        cudaFuncSetAttribute(decode_attn_mma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = true;
-      }
-      launch_kernel(decode_attn_mma_kernel<128>, dim3(rows, nkv, nsplit), dim3(128), smem, st, qkv, cos_tab, sin_tab,
-                    rope_delta, (const bf16*)kp, (const bf16*)vp, (bf16*)kc, (bf16*)vc, state, row_group, row_plen, part,
-                    tickets, (bf16*)out, nq, nkv, p_max, c_max, max_pos, scale);
-    } else {
-      launch_kernel(decode_attn_mma_kernel<64>, dim3(rows, nkv, nsplit), dim3(128), smem, st, qkv, cos_tab, sin_tab,
-                    rope_delta, (const bf16*)kp, (const bf16*)vp, (bf16*)kc, (bf16*)vc, state, row_group, row_plen, part,
-                    tickets, (bf16*)out, nq, nkv, p_max, c_max, max_pos, scale);
-    }
+    // tensor-core path: any nsplit; every CTA walks its balanced share of the live context in 16 * NW-key chunks.
+    // nsplit < 0 selects the 2-warp variant (32-key chunks, half the shared memory: twice the CTAs per SM).
+    const int nw = nsplit < 0 ? 2 : 4;
+    nsplit = nsplit < 0 ? -nsplit : nsplit;
+    if (nsplit > 32) return set_error("decode_attention_fused: nsplit %d out of range (1..32)", nsplit);
+    const size_t smem = (size_t)2 * 2 * 16 * nw * hd * 2;
+#define IADR1_DECODE_MMA(HD, NW)                                                                                     \
+  do {                                                                                                               \
+    static bool attr = false;                                                                                        \
+    if (!attr) {                                                                                                     \
+      cudaFuncSetAttribute(decode_attn_mma_kernel<HD, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+      attr = true;                                                                                                   \
+    }                                                                                                                \
+    launch_kernel(decode_attn_mma_kernel<HD, NW>, dim3(rows, nkv, nsplit), dim3(NW * 32), smem, st, qkv, cos_tab,    \
+                  sin_tab, rope_delta, (const bf16*)kp, (const bf16*)vp, (bf16*)kc, (bf16*)vc, state, row_group,     \
+                  row_plen, part, tickets, (bf16*)out, nq, nkv, p_max, c_max, max_pos, scale);                       \
+  } while (0)
+    if (hd == 128 && nw == 4) IADR1_DECODE_MMA(128, 4);
+    else if (hd == 128) IADR1_DECODE_MMA(128, 2);
+    else if (nw == 4) IADR1_DECODE_MMA(64, 4);
+    else IADR1_DECODE_MMA(64, 2);
+#undef IADR1_DECODE_MMA
     IADR1_CHECK_LAUNCH("decode_attention_mma");
     return 0;
   }

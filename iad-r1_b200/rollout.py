@@ -66,10 +66,18 @@ class RolloutEngine:
         if hd in (64, 128):
             # tensor-core kernel: ONE wave of (row, kv head, split) CTAs at 3 CTAs per SM; each CTA pipelines its balanced
             # share of the live context (decode.cu: decode_attn_mma_kernel)
-            ctas = int(os.environ.get("IADR1_DECODE_ATTN_CTAS", str(3 * NUM_SMS)))
-            self.nsplit = max(1, min(16, ctas // (R * nkv)))
+            # 4-warp CTAs (64-key chunks, 3 per SM) by default; IADR1_DECODE_ATTN_NW=2 selects 2-warp CTAs (32-key chunks,
+            # 5 per SM, finer context splits) for experiments
+            nw = int(os.environ.get("IADR1_DECODE_ATTN_NW", "0"))
+            s4 = max(1, min(16, 3 * NUM_SMS // (R * nkv)))
+            s2 = max(1, min(16, 5 * NUM_SMS // (R * nkv)))
+            if nw == 0:
+                nw = 4     # measured (profiles/r01_decode_timeline.txt): the 2-warp variant is slower at R = 64 and R = 128
+            self.nsplit = s4 if nw == 4 else s2
+            self.attn_nw = nw
         else:
             self.nsplit = max(1, min(32, (p_max + c_max + 127) // 128))   # scalar kernel: one 128-key chunk per CTA
+            self.attn_nw = 4
         self.part = torch.zeros(R, t.num_heads, self.nsplit, hd + 2, dtype=f32, device=dev)
         self.tickets = torch.zeros(R * nkv, dtype=i32, device=dev)
         # fp32 gate|up accumulator of the stream-K product; decode_silu_mul_f32 leaves it zero for the next layer
@@ -133,8 +141,8 @@ class RolloutEngine:
                 self.qkv.data_ptr(), self.cos_tab.data_ptr(), self.sin_tab.data_ptr(), self.rope_delta.data_ptr(),
                 self.kp[i].data_ptr(), self.vp[i].data_ptr(), self.kc[i].data_ptr(), self.vc[i].data_ptr(),
                 self.state.data_ptr(), self.row_group.data_ptr(), self.row_plen.data_ptr(), self.part.data_ptr(),
-                self.tickets.data_ptr(), self.attn.data_ptr(), R, nq, nkv, hd, self.p_max, self.c_max, self.nsplit,
-                self.max_pos, float(hd) ** -0.5, s), "decode_attention_fused")
+                self.tickets.data_ptr(), self.attn.data_ptr(), R, nq, nkv, hd, self.p_max, self.c_max,
+                -self.nsplit if self.attn_nw == 2 else self.nsplit, self.max_pos, float(hd) ** -0.5, s), "decode_attention_fused")
             self._skinny(p[b + "o.weight"], self.attn, self.h, split_k=sk_o, atomic=True)        # h += attn @ Wo^T
             L.check(lib.iadr1_rmsnorm_f32in(self.h.data_ptr(), p[b + "ln2.weight"].data_ptr(), self.xn.data_ptr(), R, H,
                                             t.rms_norm_eps, None, 0, s), "rmsnorm_f32in")

@@ -404,7 +404,8 @@ def _rot_half_f(x):
 
 
 @pytest.mark.parametrize("nq,nkv,hd,nsplit", [(8, 1, 128, 3), (12, 2, 128, 1), (14, 2, 128, 13), (16, 2, 128, 5),
-                                              (4, 2, 64, 3), (14, 2, 64, 2), (4, 2, 32, 0)])
+                                              (4, 2, 64, 3), (14, 2, 64, 2), (4, 2, 32, 0),
+                                              (16, 2, 128, -2), (14, 2, 128, -7), (14, 2, 64, -3), (4, 2, 64, -1)])
 def test_decode_attention_fused(ops, nq, nkv, hd, nsplit):
     """The one-launch decode attention (rotary + KV append + split-KV attention + merge; tensor-core path for hd=64/128,
     scalar path otherwise) against a torch restatement: per row, keys = shared prompt prefix of its group + its own slab +
@@ -426,8 +427,8 @@ def test_decode_attention_fused(ops, nq, nkv, hd, nsplit):
     emb = torch.cat((ang, ang), -1)
     cos_t, sin_t = emb.cos().contiguous(), emb.sin().contiguous()
     state = torch.tensor([step, 0, R, 0, 0, 0, 0, 0], dtype=torch.int32, device=dev)
-    nsplit = nsplit or (p_max + c_max + 127) // 128     # tensor-core path: any split count; scalar path: 128-key chunks
-    part = torch.zeros(R, nq, nsplit, hd + 2, device=dev)
+    nsplit = nsplit or (p_max + c_max + 127) // 128     # tensor-core path: any split count (negative: the 2-warp
+    part = torch.zeros(R, nq, abs(nsplit), hd + 2, device=dev)   # variant); scalar path: 128-key chunks
     tickets = torch.zeros(R * nkv, dtype=torch.int32, device=dev)
     out = torch.zeros(R, nq * hd, dtype=bf16, device=dev)
     scale = hd ** -0.5
