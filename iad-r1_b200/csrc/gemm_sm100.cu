@@ -441,36 +441,42 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
       }
       if (g.epi == EPI_SWIGLU) {
-        // out[n][f] = bf16(silu(gate)) * up for the tile's 64 features: both halves meet in the staging tile
+        // out[n][f] = bf16(silu(gate)) * up for the tile's 64 features: both halves meet in the staging tile, which holds
+        // 64 decode rows at a time (so that block_n = 128 still leaves room for two CTAs per SM)
         float* sC = reinterpret_cast<float*>(smem + (size_t)g.stages * stage_bytes + 512);
         const int ml = q * 32 + lane;
-        for (int c0 = 0; c0 < g.block_n; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(taddr + c0, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) sC[(c0 + j) * BM + ml] = have_acc ? g.alpha * __uint_as_float(v[j]) : 0.f;
-        }
-        tc_fence_before();
-        mbar_arrive(&tempty_bar[as]);
-        named_bar_sync(1, 128);
         const int f0 = ti.m0 >> 1;
-        const int nrows = min(g.block_n, g.N - ti.n0);
         __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(g.C);
-        for (int i = threadIdx.x - 128; i < nrows * 32; i += 128) {
-          const int n = i >> 5, f = (i & 31) * 2;
-          const float2 gg = *reinterpret_cast<const float2*>(sC + n * BM + f);
-          const float2 uu = *reinterpret_cast<const float2*>(sC + n * BM + 64 + f);
-          auto act = [](float gv, float uv) {
-            gv = __bfloat162float(__float2bfloat16(gv));
-            const float sv = __bfloat162float(__float2bfloat16(gv / (1.f + __expf(-gv))));
-            return sv * __bfloat162float(__float2bfloat16(uv));
-          };
-          if (f0 + f < (g.M >> 1))
-            *reinterpret_cast<__nv_bfloat162*>(outp + (long long)(ti.n0 + n) * g.ldc + f0 + f) =
-                __floats2bfloat162_rn(act(gg.x, uu.x), act(gg.y, uu.y));
+        for (int cb = 0; cb < g.block_n; cb += 64) {
+          const int ncols = min(64, g.block_n - cb);
+          for (int c0 = 0; c0 < ncols; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(taddr + cb + c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sC[(c0 + j) * BM + ml] = have_acc ? g.alpha * __uint_as_float(v[j]) : 0.f;
+          }
+          if (cb + 64 >= g.block_n) {           // accumulator fully read: hand the TMEM stage back to the MMA warp
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[as]);
+          }
+          named_bar_sync(1, 128);
+          const int nrows = min(ncols, g.N - ti.n0 - cb);
+          for (int i = threadIdx.x - 128; i < nrows * 32; i += 128) {
+            const int n = i >> 5, f = (i & 31) * 2;
+            const float2 gg = *reinterpret_cast<const float2*>(sC + n * BM + f);
+            const float2 uu = *reinterpret_cast<const float2*>(sC + n * BM + 64 + f);
+            auto act = [](float gv, float uv) {
+              gv = __bfloat162float(__float2bfloat16(gv));
+              const float sv = __bfloat162float(__float2bfloat16(gv / (1.f + __expf(-gv))));
+              return sv * __bfloat162float(__float2bfloat16(uv));
+            };
+            if (f0 + f < (g.M >> 1))
+              *reinterpret_cast<__nv_bfloat162*>(outp + (long long)(ti.n0 + cb + n) * g.ldc + f0 + f) =
+                  __floats2bfloat162_rn(act(gg.x, uu.x), act(gg.y, uu.y));
+          }
+          named_bar_sync(1, 128);
         }
-        named_bar_sync(1, 128);
         if (++as == 2) { as = 0; aph ^= 1; }
         continue;
       }
@@ -787,8 +793,10 @@ int launch_gemm(const iadr1_gemm_t& d, cudaStream_t stream) {
   bool co_resident = d.co_resident != 0;
   {
     // two CTAs per SM only when a >= 3-stage ring (plus the epilogue staging tile) fits in half the shared memory
-    const int epi_b = (g.trans_c && g.atomic && g.c_f32) || g.epi == EPI_SWIGLU ? g.block_n * BM * 4 : 0;
+    const int epi_b = g.epi == EPI_SWIGLU ? (g.block_n < 64 ? g.block_n : 64) * BM * 4
+                                          : ((g.trans_c && g.atomic && g.c_f32) ? g.block_n * BM * 4 : 0);
     const int stage_b = BM * BK * 2 + ((g.block_n * BK * 2 + 1023) & ~1023);
+    // needs a >= 3-stage ring per CTA (measured: 2 stages x 2 CTAs is slower than 6 stages x 1 CTA at block_n = 128)
     if (g.block_n > 128 || (113 * 1024 - 1024 - 512 - epi_b) / stage_b < 3) co_resident = false;
   }
   if (co_resident) {
@@ -798,7 +806,7 @@ int launch_gemm(const iadr1_gemm_t& d, cudaStream_t stream) {
   // transposed fp32 atomic accumulation goes through bulk reductions (needs a [block_n][128] fp32 staging tile)
   g.bulk_red = g.trans_c && g.atomic && g.c_f32 && g.epi == EPI_STORE && g.residual == nullptr && g.batch == 1 &&
                (g.M % 4 == 0) && (g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) && !d.no_bulk_red;
-  const int epi_bytes = (g.bulk_red || g.epi == EPI_SWIGLU) ? g.block_n * BM * 4 : 0;
+  const int epi_bytes = g.epi == EPI_SWIGLU ? (g.block_n < 64 ? g.block_n : 64) * BM * 4 : (g.bulk_red ? g.block_n * BM * 4 : 0);
   const int smem_budget = (co_resident ? 113 : 227) * 1024 - 1024 - 512 - epi_bytes;
   int stages = smem_budget / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;

@@ -91,7 +91,7 @@ def test_gemm_stream_k(ops, F, K, R):
         assert (gu == 0).all(), "accumulator must be cleared"
 
 
-@pytest.mark.parametrize("I,K,R", [(11008, 2048, 64), (4864, 896, 56), (256, 128, 8)])
+@pytest.mark.parametrize("I,K,R", [(11008, 2048, 64), (4864, 896, 56), (256, 128, 8), (11008, 2048, 128), (1024, 512, 100)])
 def test_gemm_swiglu(ops, I, K, R):
     """Decode MLP front half in one launch (gate and up rows of the fused weight share a 128-row MMA tile, SwiGLU in the
     epilogue) vs the two-step torch form with the same bf16 rounding points as Qwen2MLP."""
