@@ -323,6 +323,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           tma_load_4d(sa + 8192, &tmA, &full_bar[stg], kb * BK, g.up_row_off + f0, zlo, zhi);
         } else if (!g.a_mn) {
           tma_load_4d(sa, &tmA, &full_bar[stg], kb * BK, ti.m0, zlo, zhi);
+        } else if (g.a_chunked) {
+          // MN-major tile as ONE box {64 mn, BK k, 2 chunks} of the 3-D view [mn / 64][k][64]: same smem image as the two
+          // 2-D boxes below, a third of the TMA instructions per k-block (the producer thread was issue-bound)
+          tma_load_5d(sa, &tmA, &full_bar[stg], 0, kb * BK, ti.m0 >> 6, zlo, zhi);
         } else {
           tma_load_4d(sa, &tmA, &full_bar[stg], ti.m0, kb * BK, zlo, zhi);
           tma_load_4d(sa + 8192, &tmA, &full_bar[stg], ti.m0 + 64, kb * BK, zlo, zhi);
@@ -332,6 +336,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         uint8_t* sb = smem + (size_t)stg * stage_bytes + a_bytes;
         if (!g.b_mn) {
           tma_load_4d(sb, &tmB, &full_bar[stg], kb * BK, ti.n0, zlo_b, zhi);
+        } else if (g.b_chunked) {
+          tma_load_5d(sb, &tmB, &full_bar[stg], 0, kb * BK, ti.n0 >> 6, zlo_b, zhi);
         } else {
           for (int j = 0; j < g.block_n / 64; ++j)
             tma_load_4d(sb + j * 8192, &tmB, &full_bar[stg], ti.n0 + 64 * j, kb * BK, zlo_b, zhi);
@@ -581,10 +587,10 @@ struct MapKey {
 };
 
 static int make_map(CUtensorMap* out, const void* ptr, long long d0, long long d1, long long d2, long long d3,
-                    long long s1, long long s2, long long s3, int b0, int b1) {
+                    long long s1, long long s2, long long s3, int b0, int b1, int b2 = 1) {
   static std::map<MapKey, CUtensorMap> cache;
   static std::mutex mu;
-  MapKey key{ptr, d0, d1, d2, d3, s1, s2, s3, b0, b1};
+  MapKey key{ptr, d0, d1, d2, d3, s1, s2, s3, b0, b1 + (b2 << 16)};
   {
     std::lock_guard<std::mutex> lk(mu);
     auto it = cache.find(key);
@@ -601,7 +607,7 @@ static int make_map(CUtensorMap* out, const void* ptr, long long d0, long long d
                      s3);
   cuuint64_t dims[4] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2, (cuuint64_t)d3};
   cuuint64_t strides[3] = {(cuuint64_t)s1 * 2, (cuuint64_t)s2 * 2, (cuuint64_t)s3 * 2};
-  cuuint32_t box[4] = {(cuuint32_t)b0, (cuuint32_t)b1, 1, 1};
+  cuuint32_t box[4] = {(cuuint32_t)b0, (cuuint32_t)b1, (cuuint32_t)b2, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -609,6 +615,41 @@ static int make_map(CUtensorMap* out, const void* ptr, long long d0, long long d
   if (r != CUDA_SUCCESS)
     return set_error("cuTensorMapEncodeTiled failed (%d) dims=%lld,%lld,%lld,%lld strides=%lld,%lld,%lld box=%d,%d",
                      (int)r, d0, d1, d2, d3, s1, s2, s3, b0, b1);
+  std::lock_guard<std::mutex> lk(mu);
+  if (cache.size() > 8192) cache.clear();
+  cache[key] = *out;
+  return 0;
+}
+
+// Rank-5 map of an MN-major operand through the view [batch_hi][batch_lo][mn / 64][k][64]; box {64, BK, chunks, 1, 1}.
+static int make_map_chunked(CUtensorMap* out, const void* ptr, long long mn, long long k, long long n_lo, long long n_hi,
+                            long long ld, long long bs_lo, long long bs_hi, int chunks) {
+  static std::map<MapKey, CUtensorMap> cache;
+  static std::mutex mu;
+  MapKey key{ptr, mn, k, n_lo, n_hi, ld, bs_lo, bs_hi, chunks, -5};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return 0;
+    }
+  }
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error("cuTensorMapEncodeTiled entry point not found (no CUDA driver?)");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return set_error("gemm operand not 16-byte aligned");
+  if (((ld * 2) & 15) || ((bs_lo * 2) & 15) || ((bs_hi * 2) & 15))
+    return set_error("gemm operand strides must be multiples of 8 elements (ld=%lld bs_lo=%lld bs_hi=%lld)", ld, bs_lo, bs_hi);
+  cuuint64_t dims[5] = {64, (cuuint64_t)k, (cuuint64_t)(mn / 64), (cuuint64_t)n_lo, (cuuint64_t)n_hi};
+  cuuint64_t strides[4] = {(cuuint64_t)ld * 2, 128, (cuuint64_t)bs_lo * 2, (cuuint64_t)bs_hi * 2};
+  cuuint32_t box[5] = {64, (cuuint32_t)BK, (cuuint32_t)chunks, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error("cuTensorMapEncodeTiled(chunked) failed (%d) mn=%lld k=%lld batch=%lld,%lld ld=%lld", (int)r, mn, k, n_lo,
+                     n_hi, ld);
   std::lock_guard<std::mutex> lk(mu);
   if (cache.size() > 8192) cache.clear();
   cache[key] = *out;
@@ -815,6 +856,9 @@ int launch_gemm(const iadr1_gemm_t& d, cudaStream_t stream) {
   g.stages = stages;
   const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + 512 + epi_bytes;
 
+  // MN-major operands whose MN extent is a multiple of 64: one box of the chunked view per k-block
+  g.a_chunked = g.a_mn && (d.M % 64 == 0) && !d.no_chunked_maps;
+  g.b_chunked = g.b_mn && (d.N % 64 == 0) && !d.no_chunked_maps;
   const int nb_hi = g.batch / g.batch_lo;
   const int nb_lo_b = (g.batch_lo + g.b_lo_div - 1) / g.b_lo_div;
   CUtensorMap tmA, tmB;
@@ -823,6 +867,9 @@ int launch_gemm(const iadr1_gemm_t& d, cudaStream_t stream) {
   if (!g.a_mn)
     rc = make_map(&tmA, d.A, d.K, d.M, g.batch_lo, nb_hi, d.lda, d.a_bs_lo ? d.a_bs_lo : d.lda,
                   d.a_bs_hi ? d.a_bs_hi : d.lda, BK, g.epi == EPI_SWIGLU ? 64 : BM);
+  else if (g.a_chunked)
+    rc = make_map_chunked(&tmA, d.A, d.M, d.K, g.batch_lo, nb_hi, d.lda, d.a_bs_lo ? d.a_bs_lo : d.lda,
+                          d.a_bs_hi ? d.a_bs_hi : d.lda, BM / 64);
   else
     rc = make_map(&tmA, d.A, d.M, d.K, g.batch_lo, nb_hi, d.lda, d.a_bs_lo ? d.a_bs_lo : d.lda,
                   d.a_bs_hi ? d.a_bs_hi : d.lda, 64, BK);
@@ -830,6 +877,9 @@ int launch_gemm(const iadr1_gemm_t& d, cudaStream_t stream) {
   if (!g.b_mn)
     rc = make_map(&tmB, d.B, d.K, d.N, nb_lo_b, nb_hi, d.ldb, d.b_bs_lo ? d.b_bs_lo : d.ldb,
                   d.b_bs_hi ? d.b_bs_hi : d.ldb, BK, g.block_n);
+  else if (g.b_chunked)
+    rc = make_map_chunked(&tmB, d.B, d.N, d.K, nb_lo_b, nb_hi, d.ldb, d.b_bs_lo ? d.b_bs_lo : d.ldb,
+                          d.b_bs_hi ? d.b_bs_hi : d.ldb, g.block_n / 64);
   else
     rc = make_map(&tmB, d.B, d.N, d.K, nb_lo_b, nb_hi, d.ldb, d.b_bs_lo ? d.b_bs_lo : d.ldb,
                   d.b_bs_hi ? d.b_bs_hi : d.ldb, 64, BK);

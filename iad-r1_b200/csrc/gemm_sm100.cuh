@@ -21,6 +21,7 @@ struct GemmArgs {
   int stages;
   int tmem_cols;  // TMEM columns allocated (power of two >= 2 * block_n); accumulator stage s lives at s * tmem_cols / 2
   int a_mn, b_mn; // operand majorness: 0 = K-major (reduction dim contiguous), 1 = MN-major
+  int a_chunked, b_chunked;  // MN-major operand addressed through the 3-D view [mn / 64][k][64]: one TMA box per k-block
   int kmode;      // 0 full K; 1: k < m0 + 128 + causal_off (rows attend to keys <= row + off); 2: k >= m0 - causal_off
   int skip_mode;  // 1: skip output tiles with n0 > m0 + 127 + causal_off (fully masked)
   int causal_off;

@@ -36,7 +36,7 @@ class GemmDesc(C.Structure):
         ("lse_tiles_n", C.c_int),
         ("lse", C.c_void_p), ("gscale", C.c_void_p),
         ("block_n", C.c_int), ("stages", C.c_int), ("max_ctas", C.c_int), ("a_static", C.c_int),
-        ("stream_k", C.c_int), ("up_row_off", C.c_int), ("raster", C.c_int), ("no_bulk_red", C.c_int), ("co_resident", C.c_int),
+        ("stream_k", C.c_int), ("up_row_off", C.c_int), ("raster", C.c_int), ("no_chunked_maps", C.c_int), ("no_bulk_red", C.c_int), ("co_resident", C.c_int),
     ]
 
 
@@ -134,7 +134,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None, *, b
          alpha: float = 1.0, accumulate: bool = False, out_dtype=torch.bfloat16, split_k: int = 1,
          atomic: bool | None = None, trans_out: bool = False, bias_per_m: bool = False, block_n: int = 0, stages: int = 0,
          max_ctas: int = 0, a_static: bool = False, stream_k: bool = False,
-         co_resident: bool = False, no_bulk_red: bool = False, raster: int = 0) -> torch.Tensor:
+         co_resident: bool = False, no_bulk_red: bool = False, raster: int = 0,
+         no_chunked_maps: bool = False) -> torch.Tensor:
     """out[M,N] (+)= alpha * a[M,K] @ b[N,K]^T (+ bias) (+ residual).
 
     ``a`` and ``b`` are 2-D bf16 *views*; either of their dims may be the contiguous one, so ``x @ W.T`` is
@@ -169,6 +170,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None, *, b
     d.residual = _ptr(residual)
     d.block_n, d.stages, d.max_ctas, d.a_static = block_n, stages, max_ctas, int(a_static)
     d.stream_k, d.co_resident, d.no_bulk_red, d.raster = int(stream_k), int(co_resident), int(no_bulk_red), raster
+    d.no_chunked_maps = int(no_chunked_maps)
     check(lib().iadr1_gemm_bf16(C.byref(d), stream_ptr()), "iadr1_gemm_bf16")
     return out
 

@@ -56,6 +56,7 @@ typedef struct iadr1_gemm_t {
   int up_row_off;                    /* epi 3 (decode SwiGLU): A holds gate rows [0, I) then up rows [I, 2I); M = 2I, up_row_off = I;
                                         C is bf16 [N][ldc] with C[n][f] = silu(gate_f . b_n) * (up_f . b_n)            */
   int raster;                        /* tile order: 0 library heuristic, 1 M fastest (B streamed once), 2 N fastest (A streamed once) */
+  int no_chunked_maps;               /* probes: MN-major operands as 64-column 2-D boxes (several TMA instructions per k-block) */
   int no_bulk_red;                   /* probes: force per-lane atomics instead of bulk reductions for transposed fp32 atomic C */
   int co_resident;                   /* decode chain: <= 113 KB smem, <= 128 regs, minimal TMEM so two CTAs fit per SM */
 } iadr1_gemm_t;
