@@ -74,6 +74,8 @@ class RolloutEngine:
             if nw == 0:
                 nw = 4     # measured (profiles/r01_decode_timeline.txt): the 2-warp variant is slower at R = 64 and R = 128
             self.nsplit = s4 if nw == 4 else s2
+            if os.environ.get("IADR1_DECODE_ATTN_NSPLIT"):
+                self.nsplit = max(1, min(16, int(os.environ["IADR1_DECODE_ATTN_NSPLIT"])))
             self.attn_nw = nw
         else:
             self.nsplit = max(1, min(32, (p_max + c_max + 127) // 128))   # scalar kernel: one 128-key chunk per CTA
