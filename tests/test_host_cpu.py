@@ -205,16 +205,28 @@ def test_param_store_llava_names_roundtrip_cpu():
     assert seen == len(sd)
 
 
-def test_checkpoint_roundtrip(tmp_path):
+@pytest.mark.parametrize("family", ["qwen2_vl", "qwen2_5_vl", "llava_onevision"])
+def test_checkpoint_roundtrip(tmp_path, family):
+    """save_model -> HF-layout directory -> load (what SC_GRPO_*.sh:25 does with the PA-SFT output), and the written
+    directory loads into the HF class itself with the same tensors (the reference's from_pretrained path)."""
     from iad_r1_b200.checkpoint import load_pretrained, save_pretrained
     from iad_r1_b200.config import tiny_config
     from iad_r1_b200.params import ParamStore
-    ps = ParamStore(tiny_config("qwen2_vl"), "cpu")
+    ps = ParamStore(tiny_config(family), "cpu")
     ps.init_random(seed=3)
     save_pretrained(ps, str(tmp_path / "ckpt"))
     cfg2, ps2 = load_pretrained(str(tmp_path / "ckpt"), "cpu", with_grads=False, with_optimizer=False)
     assert cfg2.text == ps.cfg.text and cfg2.vision == ps.cfg.vision
     assert torch.equal(ps.flat, ps2.flat)
+    # every tensor of the written state dict has the name and shape the HF model expects
+    from oracle.hf_oracle import build_hf_model
+    hf = build_hf_model(ps.cfg, seed=0, dtype=torch.float32)
+    want = {ps.canonical_name(k): tuple(v.shape) for k, v in hf.state_dict().items()}
+    got = {k: tuple(v.shape) for k, v in ps.hf_state_dict().items()}
+    for k, shp in got.items():
+        assert want.get(k) == shp, (k, shp, want.get(k))
+    missing = [k for k in want if k not in got and not k.endswith("lm_head.weight")]
+    assert not missing, missing[:5]
 
 
 _DDP = r'''
