@@ -147,7 +147,7 @@ def run_reference(args):
     t0 = time.time()
     gps, info, t_s = cpu_reference_sample(args, cfg, steps=max(1, args.steps), warmup=min(args.warmup, 1))
     line = {"metric": "GRPO groups/sec (G=8)", "value": gps, "unit": "groups/s", "impl": "reference", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / gps, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * args.ga / gps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, cfg, 1), "cpu_baseline": info,
             "e2e": {"value": gps, "unit": "groups/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -159,16 +159,37 @@ class VisionGeometry:
             return int(d[0]) if len(d) and (d == d[0]).all() and d[0] % 8 == 0 else 0
 
         self.full_seg, self.win_seg = uniform(cu_full), uniform(cu_win)
+        # ragged case: attention runs image by image (patch range + key ranges relative to the image), never as one masked
+        # [Np_total x Np_total] product over all images of a batch
+        self.image_ranges, a = [], 0
+        for t, h, w in grid_thw:
+            self.image_ranges.append((a, a + t * h * w))
+            a += t * h * w
+        self._rel = {}
         self.seg_ranges = {}
         for L_ in {self.full_seg, self.win_seg} - {0}:
             self.seg_ranges[L_] = (torch.zeros(L_, dtype=torch.int32, device=device),
                                    torch.full((L_,), L_, dtype=torch.int32, device=device))
+        self._abs = {"full": (self.full_lo, self.full_hi), "win": (self.win_lo, self.win_hi)}
         if window_index is not None:
             self.window_index = torch.from_numpy(window_index.astype(np.int32)).to(device)
             self.reverse_index = torch.from_numpy(np.argsort(window_index).astype(np.int32)).to(device)
         else:
             self.window_index = self.reverse_index = None
 
+
+def _relative_ranges(self, kind: str, j: int):
+    """(lo, hi) key ranges of image j's patches, relative to the image's first patch."""
+    key = (kind, j)
+    r = self._rel.get(key)
+    if r is None:
+        a, b = self.image_ranges[j]
+        lo, hi = self._abs[kind]
+        r = self._rel[key] = ((lo[a:b] - a).contiguous(), (hi[a:b] - a).contiguous())
+    return r
+
+
+VisionGeometry.relative_ranges = _relative_ranges
 
 _GEOM_CACHE: dict = {}
 

@@ -78,9 +78,12 @@ class VLM:
             b = f"visual.blocks.{i}."
             full = (not q25) or (i in v.fullatt_block_indexes)
             seg = geo.full_seg if full else geo.win_seg
+            per_image = False
             if seg:      # equal-length segments: a batch of [seg x seg] attention problems (no masked-out work)
                 sh = ops.AttnShape(Np // seg, seg, nh, nh, hd, causal=False)
                 lo, hi = geo.seg_ranges[seg]
+            elif len(geo.image_ranges) > 1:   # ragged segments, several images: masked attention image by image
+                per_image, sh, lo, hi = True, None, None, None
             else:        # ragged segments: one [Np x Np] product with per-row key ranges
                 sh = sh_masked
                 lo, hi = (geo.full_lo, geo.full_hi) if full else (geo.win_lo, geo.win_hi)
@@ -91,7 +94,16 @@ class VLM:
                 st1 = (m1, r1)
             qkv = ops.linear_fwd(xn, p[b + "qkv.weight"], bias=p[b + "qkv.bias"])
             ops.rope_(qkv, geo.cos, geo.sin, 2 * nh, hd, bf16_ops=0)
-            attn, P = ops.attention_fwd(qkv, sh, lo, hi)
+            if per_image:
+                attn = torch.empty(Np, nh * hd, dtype=bf16, device=self.device)
+                P, sh = [], ("full" if full else "win")
+                for j, (a_, b_) in enumerate(geo.image_ranges):
+                    lo_j, hi_j = geo.relative_ranges(sh, j)
+                    _, P_j = ops.attention_fwd(qkv[a_:b_], ops.AttnShape(1, b_ - a_, nh, nh, hd, causal=False), lo_j, hi_j,
+                                               out=attn[a_:b_])
+                    P.append(P_j if save else None)
+            else:
+                attn, P = ops.attention_fwd(qkv, sh, lo, hi)
             x_mid = ops.linear_fwd(attn, p[b + "proj.weight"], bias=p[b + "proj.bias"], residual=x)
             if q25:
                 xn2, st2 = ops.rmsnorm_fwd(x_mid, p[b + "norm2.weight"], 1e-6)
@@ -160,7 +172,14 @@ class VLM:
                 ops.layernorm_bwd(dxn2, x_mid, p[b + "norm2.weight"], st2[0], st2[1], dx, g[b + "norm2.weight"],
                                   g[b + "norm2.bias"], add_dx=True)
             dattn = ops.linear_bwd(dx, attn, p[b + "proj.weight"], g[b + "proj.weight"], g[b + "proj.bias"])
-            dqkv = ops.attention_bwd(dattn, qkv, P, sh, lo, hi)
+            if isinstance(P, list):     # per-image masked attention (ragged segments, several images)
+                dqkv = torch.empty_like(qkv)
+                for j, (a_, b_) in enumerate(geo.image_ranges):
+                    lo_j, hi_j = geo.relative_ranges(sh, j)
+                    ops.attention_bwd(dattn[a_:b_], qkv[a_:b_], P[j], ops.AttnShape(1, b_ - a_, nh, nh, hd, causal=False),
+                                      lo_j, hi_j, dqkv=dqkv[a_:b_])
+            else:
+                dqkv = ops.attention_bwd(dattn, qkv, P, sh, lo, hi)
             ops.rope_(dqkv, geo.cos, geo.sin, 2 * nh, hd, bf16_ops=0, backward=True)
             dxn = ops.linear_bwd(dqkv, xn, p[b + "qkv.weight"], g[b + "qkv.weight"], g[b + "qkv.bias"])
             if q25:

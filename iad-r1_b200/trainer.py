@@ -230,21 +230,40 @@ class SCGRPOTrainer(TrainerCore):
         img = None
         if self.args.window_vision and all(e["pixel_values"] is not None for e in enc):
             from .geometry import image_token_count
-            pv = torch.cat([e["pixel_values"].to(self.device) for e in enc], 0)
-            grids = [g_ for e in enc for g_ in e["grid_thw"]]
-            with self._phase("vision_fwd"):
-                img, vctx = self.model.vision_forward(pv, grids, save=True)
-                ref_img = None
-                if self.ref_model is not None:
-                    with torch.no_grad():
-                        ref_img, _ = self.ref_model.vision_forward(pv, grids, save=False)
+            H = self.cfg.text.hidden_size
             slices, off = {}, 0
             for ex, e in zip(examples, enc):
                 n = sum(image_token_count(self.cfg, g_) for g_ in e["grid_thw"])
                 slices[id(ex)] = (off, off + n)
                 off += n
-            self._window = dict(img=img, ref_img=ref_img, vctx=vctx, slices=slices,
-                                dimg=torch.zeros(off, self.cfg.text.hidden_size, dtype=torch.float32, device=self.device))
+            img = torch.empty(off, H, dtype=torch.bfloat16, device=self.device)
+            ref_img = torch.empty_like(img) if self.ref_model is not None else None
+            # one tower pass per set of prompts with IDENTICAL image grids: equal-length attention segments keep the
+            # batched (un-masked) attention path, and mixed image sizes never build one [Np_total x Np_total] score matrix
+            by_grid = {}
+            for i, e in enumerate(enc):
+                by_grid.setdefault(tuple(tuple(int(x) for x in g_) for g_ in e["grid_thw"]), []).append(i)
+            parts = []
+            with self._phase("vision_fwd"):
+                for idxs in by_grid.values():
+                    pv = torch.cat([enc[i]["pixel_values"].to(self.device) for i in idxs], 0)
+                    grids = [g_ for i in idxs for g_ in enc[i]["grid_thw"]]
+                    rng = [slices[id(examples[i])] for i in idxs]
+                    f, vctx = self.model.vision_forward(pv, grids, save=True)
+                    o = 0
+                    for lo, hi in rng:
+                        img[lo:hi] = f[o:o + hi - lo]
+                        o += hi - lo
+                    if ref_img is not None:
+                        with torch.no_grad():
+                            rf, _ = self.ref_model.vision_forward(pv, grids, save=False)
+                        o = 0
+                        for lo, hi in rng:
+                            ref_img[lo:hi] = rf[o:o + hi - lo]
+                            o += hi - lo
+                    parts.append((vctx, rng))
+            self._window = dict(img=img, ref_img=ref_img, vctx=parts, slices=slices,
+                                dimg=torch.zeros(off, H, dtype=torch.float32, device=self.device))
         comps = self._rollout(enc, image_embeds=img)
         for ex, e, c in zip(examples, enc, comps):
             self._rollout_cache[id(ex)] = (e, c)
@@ -272,7 +291,10 @@ class SCGRPOTrainer(TrainerCore):
         if w is not None and w["vctx"] is not None:
             from . import ops
             with self._phase("backward"):
-                self.model.vision_backward(ops.cast_f32_bf16(w["dimg"]), w["vctx"])
+                d = ops.cast_f32_bf16(w["dimg"])
+                for vctx, rng in w["vctx"]:
+                    dpart = d if len(w["vctx"]) == 1 and len(rng) == len(w["slices"]) else torch.cat([d[lo:hi] for lo, hi in rng], 0)
+                    self.model.vision_backward(dpart, vctx)
         self._window = None
 
     def optimizer_step(self):

@@ -134,3 +134,37 @@ def test_hf_state_dict_roundtrip(cuda, family):
         if k.endswith("lm_head.weight"):
             continue
         assert torch.equal(sd[k].cpu().reshape(v.shape), v), k
+
+
+def test_vision_tower_mixed_image_sizes(cuda):
+    """Several images of DIFFERENT grids in one vision-tower call (a real accumulation window): attention runs image by
+    image on the ragged segments - same features and the same parameter gradient as one call per image."""
+    from iad_r1_b200.config import tiny_config
+    from iad_r1_b200.model import VLM
+    from iad_r1_b200.params import ParamStore
+    cfg = tiny_config("qwen2_5_vl")
+    torch.manual_seed(0)
+    grids = [(1, 8, 8), (1, 10, 8), (1, 8, 8)]
+    pxs = [torch.randn(t * h * w, cfg.vision.patch_dim, device=cuda).to(torch.bfloat16) for t, h, w in grids]
+
+    def run(batched):
+        ps = ParamStore(cfg, cuda, with_grads=True)
+        ps.init_random(seed=1)
+        vlm = VLM(cfg, ps)
+        if batched:
+            out, ctx = vlm.vision_forward(torch.cat(pxs), grids)
+            vlm.vision_backward(torch.ones_like(out) * 0.01, ctx)
+            return out, ps.grad_flat.clone()
+        outs = []
+        for px, g in zip(pxs, grids):
+            o, ctx = vlm.vision_forward(px, [g])
+            vlm.vision_backward(torch.ones_like(o) * 0.01, ctx)
+            outs.append(o)
+        return torch.cat(outs), ps.grad_flat.clone()
+
+    o1, g1 = run(True)
+    o2, g2 = run(False)
+    torch.cuda.synchronize()
+    assert (o1.float() - o2.float()).abs().max().item() <= 2 ** -7 * o2.float().abs().max().item()
+    rel = ((g1 - g2).norm() / g2.norm()).item()
+    assert rel < 0.02, rel
