@@ -105,7 +105,8 @@ __global__ void rmsnorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __res
 // dx (+)= rstd * (dy*w - xhat * mean(dy*w*xhat));  dw[c] += sum_rows dy * xhat   (fp32 atomics, one per CTA per column)
 // Each CTA walks `rows_per_cta` rows so the dw partial stays in registers.
 template <int MAX_VEC>
-__global__ void rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+__global__ void __launch_bounds__(256, MAX_VEC == 1 ? 4 : 1)   // 4 CTAs per SM: the host sizes the grid for ONE wave of 148 x 4
+rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                    const bf16* __restrict__ w, const float* __restrict__ rstd, bf16* __restrict__ dx,
                                    float* __restrict__ dw, int rows, int cols, long long ld, int rows_per_cta,
                                    int add_dx) {
@@ -122,20 +123,39 @@ __global__ void rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __re
   }
   const int r0 = blockIdx.x * rows_per_cta;
   const int r1 = min(rows, r0 + rows_per_cta);
-  for (int row = r0; row < r1; ++row) {
+  // Software-pipelined over the rows: the raw x / dy / dx vectors of row r + 1 are requested before row r's block
+  // reduction, so the HBM latency of every row but the first hides behind the previous row's arithmetic and barriers
+  // (the un-pipelined loop paid two dependent DRAM round trips per row: 83 us on [8786, 2048] against a 22 us roofline).
+  bf16x8 nx[MAX_VEC], ng[MAX_VEC], nd[MAX_VEC];
+  auto fetch = [&](int row) {
     const bf16x8* xr = reinterpret_cast<const bf16x8*>(x + (long long)row * ld);
     const bf16x8* gr = reinterpret_cast<const bf16x8*>(dy + (long long)row * ld);
+    const bf16x8* dr = reinterpret_cast<const bf16x8*>(dx + (long long)row * ld);
+#pragma unroll
+    for (int i = 0; i < MAX_VEC; ++i) {
+      const int v = threadIdx.x + i * blockDim.x;
+      if (v < nvec) {
+        nx[i] = xr[v];
+        ng[i] = gr[v];
+        if (add_dx) nd[i] = dr[v];
+      }
+    }
+  };
+  if (r0 < r1) fetch(r0);
+  for (int row = r0; row < r1; ++row) {
     bf16x8* dxr = reinterpret_cast<bf16x8*>(dx + (long long)row * ld);
     const float rs = rstd[row];
     float xh[MAX_VEC][8], gw[MAX_VEC][8];
+    bf16x8 cd[MAX_VEC];
     float dot = 0.f;
 #pragma unroll
     for (int i = 0; i < MAX_VEC; ++i) {
       const int v = threadIdx.x + i * blockDim.x;
       if (v < nvec) {
         float g[8];
-        unpack8(xr[v], xh[i]);
-        unpack8(gr[v], g);
+        unpack8(nx[i], xh[i]);
+        unpack8(ng[i], g);
+        cd[i] = nd[i];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           xh[i][j] *= rs;
@@ -145,13 +165,14 @@ __global__ void rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __re
         }
       }
     }
+    if (row + 1 < r1) fetch(row + 1);
     dot = block_sum(dot, red) / (float)cols;
 #pragma unroll
     for (int i = 0; i < MAX_VEC; ++i) {
       const int v = threadIdx.x + i * blockDim.x;
       if (v < nvec) {
         float o[8];
-        if (add_dx) unpack8(dxr[v], o);
+        if (add_dx) unpack8(cd[i], o);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float d = rs * (gw[i][j] - xh[i][j] * dot);
@@ -333,6 +354,47 @@ __global__ void rope_kernel(bf16* __restrict__ x, const float* __restrict__ cs, 
     }
     p[d] = __float2bfloat16(o1);
     p[d + half] = __float2bfloat16(o2);
+  }
+}
+
+// Vectorised form (half % 8 == 0, 16-byte aligned rows): one thread = 8 consecutive dims of both halves of one head -
+// two 16-byte loads / stores of x and four float4 loads of the table (the two halves of the table are equal, so only the
+// first is read). Same arithmetic, ~4x fewer memory instructions than the scalar kernel (54 -> ~15 us on [8786, 20, 128]).
+__global__ void rope_vec8_kernel(bf16* __restrict__ x, const float* __restrict__ cs, const float* __restrict__ sn,
+                                 long long tokens, int heads, int hd, long long tok_stride, int bf16_ops, float sign) {
+  const int half = hd >> 1;
+  const int vph = half >> 3;  // 8-wide vectors per half head
+  const long long total = tokens * heads * vph;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vph);
+    const long long th = i / vph;
+    const int h = (int)(th % heads);
+    const long long t = th / heads;
+    bf16* p = x + t * tok_stride + (long long)h * hd + v * 8;
+    float x1[8], x2[8], c[8], s_[8], o1[8], o2[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(p), x1);
+    unpack8(*reinterpret_cast<const bf16x8*>(p + half), x2);
+    const float4* cp = reinterpret_cast<const float4*>(cs + t * hd + v * 8);
+    const float4* sp = reinterpret_cast<const float4*>(sn + t * hd + v * 8);
+    const float4 c0 = cp[0], c1 = cp[1], s0 = sp[0], s1 = sp[1];
+    c[0] = c0.x; c[1] = c0.y; c[2] = c0.z; c[3] = c0.w; c[4] = c1.x; c[5] = c1.y; c[6] = c1.z; c[7] = c1.w;
+    s_[0] = s0.x; s_[1] = s0.y; s_[2] = s0.z; s_[3] = s0.w; s_[4] = s1.x; s_[5] = s1.y; s_[6] = s1.z; s_[7] = s1.w;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float cj = c[j], sj = sign * s_[j];
+      if (bf16_ops) {
+        cj = bf16_round(cj);
+        sj = bf16_round(sj);
+        o1[j] = bf16_round(x1[j] * cj) + bf16_round(-x2[j] * sj);
+        o2[j] = bf16_round(x2[j] * cj) + bf16_round(x1[j] * sj);
+      } else {
+        o1[j] = x1[j] * cj - x2[j] * sj;
+        o2[j] = x2[j] * cj + x1[j] * sj;
+      }
+    }
+    *reinterpret_cast<bf16x8*>(p) = pack8(o1);
+    *reinterpret_cast<bf16x8*>(p + half) = pack8(o2);
   }
 }
 
@@ -667,6 +729,13 @@ int iadr1_rope(void* x, const float* cos_t, const float* sin_t, long long tokens
   if (tokens <= 0 || heads <= 0) return 0;
   if (hd % 2) return set_error("rope: head_dim must be even");
   const long long work = tokens * heads * (hd / 2);
+  if ((hd / 2) % 8 == 0 && tok_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(cos_t) & 15) == 0 && (reinterpret_cast<uintptr_t>(sin_t) & 15) == 0) {
+    rope_vec8_kernel<<<grid_for(work / 8, 256, 16), 256, 0, (cudaStream_t)stream>>>(
+        (bf16*)x, cos_t, sin_t, tokens, heads, hd, tok_stride, bf16_ops, backward ? -1.f : 1.f);
+    IADR1_CHECK_LAUNCH("rope");
+    return 0;
+  }
   rope_kernel<<<grid_for(work, 256, 16), 256, 0, (cudaStream_t)stream>>>((bf16*)x, cos_t, sin_t, tokens, heads, hd,
                                                                          tok_stride, bf16_ops, backward ? -1.f : 1.f);
   IADR1_CHECK_LAUNCH("rope");

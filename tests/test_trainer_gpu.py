@@ -220,3 +220,29 @@ def test_multi_group_pass_equals_single_group_passes(cuda):
     assert (torch.cat(lps) - lp_m).abs().max().item() < 2e-3
     rel = ((tr.params.grad_flat - g_merged).norm() / g_merged.norm()).item()
     assert rel < 2e-2, rel
+
+
+def test_two_image_prompt_layouts_agree(cuda):
+    """The 1-shot prompt of the reference (`--single_img 0`: a reference image and a test image in one user turn,
+    ref: train/stage_rl/grpo_ad.py:92-116) - two images of different sizes per prompt: the shared-prefix layout and the
+    reference [G, P + C] layout give the same log-probs, and a trainer step runs on it."""
+    from iad_r1_b200.synthetic import synthetic_dataset, synthetic_image
+    cfg, tr = _tiny_trainer(cuda, max_steps=1, gradient_accumulation_steps=1)
+    rows = synthetic_dataset(2, 112)
+    for i, ex in enumerate(rows):
+        ex["image"] = [synthetic_image(10 + i, 112), synthetic_image(20 + i, 84)]
+        ex["prompt"][0]["content"] = [{"type": "image"}, {"type": "image"}, ex["prompt"][0]["content"][-1]]
+    enc = tr._encode_prompt(rows[0])
+    assert len(enc["grid_thw"]) == 2 and enc["grid_thw"][0] != enc["grid_thw"][1]
+    G, C, P = 4, 6, len(enc["input_ids"])
+    comp = torch.randint(10, 900, (G, C), device=cuda, dtype=torch.int32)
+    b1 = tr.model.prepare_group(enc["input_ids"], comp, enc["pixel_values"], enc["grid_thw"])
+    lp1, _ = tr.model.logprobs_forward(b1, b1["sel_index"], b1["labels"], save=False)
+    ids = torch.cat([torch.from_numpy(enc["input_ids"]).to(cuda)[None].expand(G, -1), comp.long()], 1)
+    b2 = tr.model.prepare_batch(ids, enc["pixel_values"], enc["grid_thw"], prompt_len=P)
+    sel = (torch.arange(G, device=cuda)[:, None] * (P + C) + (P - 1) + torch.arange(C, device=cuda)[None]).reshape(-1).to(torch.int32)
+    lp2, _ = tr.model.logprobs_forward(b2, sel, comp.reshape(-1).contiguous(), save=False)
+    assert (lp1 - lp2).abs().max().item() < 0.02
+    tr.train_dataset = rows
+    out = tr.train()
+    assert out["global_step"] == 1 and torch.isfinite(tr.params.flat.float()).all()
