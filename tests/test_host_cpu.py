@@ -292,3 +292,22 @@ def test_sft_example_encoding_labels_assistant_only():
             "--lr_scheduler_type cosine --logging_steps 5 --cutoff_len 4096 --save_steps 365 --plot_loss --num_train_epochs 1 --bf16").split()
     (a,) = HfArgumentParser(SFTArguments).parse_args_into_dataclasses(args=argv)
     assert a.cutoff_len == 4096 and a.lr_scheduler_type == "cosine" and a.bf16 and a.plot_loss
+
+
+@pytest.mark.slow
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) prints ONE JSON line with the contract keys:
+    same metric / unit / config as our arm, impl = reference, a cpu_baseline block and a zero-copy e2e block."""
+    import json
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    for k in ("metric", "value", "unit", "impl", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["unit"] == "groups/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in line["config"] and "qwen2.5-vl-3b" in line["config"]["workload"]
