@@ -105,6 +105,21 @@ def load_sharegpt_dataset(name: str, dataset_dir: str = "data") -> list:
         return json.load(f)
 
 
+def infer_seqlen(source_len: int, target_len: int, cutoff_len: int):
+    """Lengths of one (prompt, answer) turn after truncation to `cutoff_len` tokens: a short answer keeps all of itself
+    and the prompt is cut; a short prompt keeps all of itself and the answer is cut; otherwise both shrink in proportion
+    (ref: train/stage_sft/llamafactory/data/processors/processor_utils.py:51-65, KATs in tests/test_host_cpu.py)."""
+    if target_len * 2 < cutoff_len:
+        max_target = cutoff_len
+    elif source_len * 2 < cutoff_len:
+        max_target = cutoff_len - source_len
+    else:
+        max_target = int(cutoff_len * (target_len / (source_len + target_len)))
+    new_target = min(max_target, target_len)
+    new_source = min(max(cutoff_len - new_target, 0), source_len)
+    return new_source, new_target
+
+
 def encode_supervised_example(example: dict, processor, cutoff_len: int, image_dir: Optional[str], image_resolution: int,
                               cfg=None):
     """messages -> (input_ids [T], labels [T] with IGNORE_INDEX outside assistant turns, pixel_values, grid_thw).
@@ -140,14 +155,26 @@ def encode_supervised_example(example: dict, processor, cutoff_len: int, image_d
 
     full = tok(len(msgs), False)
     ids = full["input_ids"][0]
-    labels = torch.full_like(ids, IGNORE_INDEX)
+    # (source, target) token spans per assistant turn, then the reference's per-turn truncation: every turn gets what is
+    # left of cutoff_len, split between its prompt and its answer by infer_seqlen (processors/supervised.py:50-74)
+    pairs, prev_end = [], 0
     for k, m in enumerate(msgs):
         if m["role"] != "assistant":
             continue
         start = tok(k, True)["input_ids"].shape[1]
         end = tok(k + 1, False)["input_ids"].shape[1]
-        labels[start:end] = ids[start:end]
-    ids, labels = ids[:cutoff_len], labels[:cutoff_len]
+        pairs.append((prev_end, start, end))
+        prev_end = end
+    out_ids, out_labels, total = [], [], 0
+    for a, b, c in pairs:
+        if total >= cutoff_len:
+            break
+        src_len, tgt_len = infer_seqlen(b - a, c - b, cutoff_len - total)
+        out_ids += ids[a:a + src_len].tolist() + ids[b:b + tgt_len].tolist()
+        out_labels += [IGNORE_INDEX] * src_len + ids[b:b + tgt_len].tolist()
+        total += src_len + tgt_len
+    ids = torch.tensor(out_ids, dtype=torch.int64)
+    labels = torch.tensor(out_labels, dtype=torch.int64)
     pv, grid = (full.get("pixel_values"), full["image_grid_thw"].tolist() if "image_grid_thw" in full else None) \
         if cfg is None else vision_inputs_from_processor(cfg, full)
     return dict(input_ids=ids.numpy().astype(np.int64), labels=labels.numpy().astype(np.int64), pixel_values=pv, grid_thw=grid)

@@ -294,6 +294,37 @@ def test_sft_example_encoding_labels_assistant_only():
     assert a.cutoff_len == 4096 and a.lr_scheduler_type == "cosine" and a.bf16 and a.plot_loss
 
 
+def test_sft_truncation_follows_reference_infer_seqlen():
+    """Per-turn truncation to cutoff_len (ref: llamafactory/data/processors/processor_utils.py:51-65 `infer_seqlen`,
+    supervised.py:50-74). The expected tuples were produced by the reference function itself in this container."""
+    from iad_r1_b200.config import tiny_config
+    from iad_r1_b200.sft_trainer import IGNORE_INDEX, encode_supervised_example, infer_seqlen
+    from iad_r1_b200.synthetic import SyntheticProcessor
+    kats = [((10, 5, 100), (10, 5)), ((300, 50, 100), (86, 14)), ((30, 500, 100), (30, 70)), ((300, 300, 100), (50, 50)),
+            ((1, 1, 0), (0, 0)), ((4000, 600, 4096), (3496, 600)), ((4000, 600, 1000), (870, 130)), ((50, 49, 100), (50, 49)),
+            ((100, 10, 19), (18, 1)), ((7, 93, 50), (7, 43))]
+    for args, want in kats:
+        assert infer_seqlen(*args) == want, args
+    proc = SyntheticProcessor(tiny_config())
+    ex = {"messages": [{"role": "user", "content": "is the first surface scratch " * 6},
+                       {"role": "assistant", "content": "yes a scratch top left " * 5},
+                       {"role": "user", "content": "and the second image " * 4},
+                       {"role": "assistant", "content": "no defect " * 8}], "images": []}
+    full = encode_supervised_example(ex, proc, 4096, None, 512 * 512)
+    n = len(full["input_ids"])
+    assert (full["labels"] != IGNORE_INDEX).sum() > 0 and len(full["labels"]) == n
+    for cutoff in (n, n - 7, n // 2, 24, 9):
+        enc = encode_supervised_example(ex, proc, cutoff, None, 512 * 512)
+        ids, lab = enc["input_ids"], enc["labels"]
+        assert len(ids) == len(lab) <= cutoff
+        sup = lab != IGNORE_INDEX
+        assert (lab[sup] == ids[sup]).all()
+        if cutoff >= n:
+            assert (ids == full["input_ids"]).all() and (lab == full["labels"]).all()
+        else:
+            assert len(ids) == cutoff, (cutoff, len(ids))       # the budget is used up exactly while tokens remain
+
+
 @pytest.mark.slow
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` (the CPU arm the driver runs beside ours) prints ONE JSON line with the contract keys:
