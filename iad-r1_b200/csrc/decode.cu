@@ -142,136 +142,6 @@ __global__ void rmsnorm_f32in_kernel(const float* __restrict__ x, const bf16* __
     y[row * cols + c] = __float2bfloat16(__bfloat162float(w[c]) * bf16r(bf16r(xr[c]) * rstd));
 }
 
-// qkv f32 [R, (nq + 2 nkv) * hd] (bias already added) -> rotary on q,k (HF bf16 op order) -> q bf16 [R, nq*hd],
-// k,v appended to the row's completion slab at slot ST_STEP. Position = P[row] + step + rope_delta[row].
-__global__ void decode_rope_append_kernel(const float* __restrict__ qkv, const float* __restrict__ cos_tab,
-                                          const float* __restrict__ sin_tab, const int* __restrict__ rope_delta,
-                                          const int* __restrict__ row_plen, const int* __restrict__ state,
-                                          bf16* __restrict__ q_out,
-                                          bf16* __restrict__ kc, bf16* __restrict__ vc, int nq, int nkv, int hd,
-                                          int c_max, int max_pos) {
-  const int r = blockIdx.x;
-  const int head = blockIdx.y;  // [0,nq) q, [nq,nq+nkv) k, [nq+nkv, nq+2nkv) v
-  const int step = state[ST_STEP];
-  int pos = row_plen[r] + step + rope_delta[r];
-  pos = max(0, min(max_pos - 1, pos));
-  const int qkv_dim = (nq + 2 * nkv) * hd;
-  const float* src = qkv + (long long)r * qkv_dim + (long long)head * hd;
-  const int half = hd >> 1;
-  if (head < nq + nkv) {
-    for (int d = threadIdx.x; d < half; d += blockDim.x) {
-      const float x1 = bf16r(src[d]), x2 = bf16r(src[d + half]);
-      const float c1 = bf16r(cos_tab[(long long)pos * hd + d]), c2 = bf16r(cos_tab[(long long)pos * hd + d + half]);
-      const float s1 = bf16r(sin_tab[(long long)pos * hd + d]), s2 = bf16r(sin_tab[(long long)pos * hd + d + half]);
-      const float o1 = bf16r(x1 * c1) + bf16r(-x2 * s1);
-      const float o2 = bf16r(x2 * c2) + bf16r(x1 * s2);
-      bf16* dst = (head < nq) ? q_out + (long long)r * nq * hd + (long long)head * hd
-                              : kc + (((long long)r * c_max + step) * nkv + (head - nq)) * hd;
-      dst[d] = __float2bfloat16(o1);
-      dst[d + half] = __float2bfloat16(o2);
-    }
-  } else {
-    bf16* dst = vc + (((long long)r * c_max + step) * nkv + (head - nq - nkv)) * hd;
-    for (int d = threadIdx.x; d < hd; d += blockDim.x) dst[d] = __float2bfloat16(src[d]);
-  }
-}
-
-// Split-KV decode attention. Grid (R, nkv, nsplit); 4 warps; each warp owns a strided subset of the chunk's keys and
-// serves all `gq` query heads of this kv head (K/V rows are read once per group, not once per head).
-template <int HD>
-__global__ void __launch_bounds__(128) decode_attn_partial_kernel(
-    const bf16* __restrict__ q, const bf16* __restrict__ kp, const bf16* __restrict__ vp, const bf16* __restrict__ kc,
-    const bf16* __restrict__ vc, const int* __restrict__ state, const int* __restrict__ row_group,
-    const int* __restrict__ row_plen, float* __restrict__ part, int nq, int nkv, int p_max, int c_max, int chunk, float scale) {
-  constexpr int DPL = HD / 32;  // dims per lane
-  constexpr int MAXG = 8;
-  const int r = blockIdx.x, kvh = blockIdx.y, sp = blockIdx.z, nsplit = gridDim.z;
-  const int gq = nq / nkv;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int P = row_plen[r];
-  const int ctx = P + state[ST_STEP] + 1;
-  const int k0 = sp * chunk, k1 = min(ctx, k0 + chunk);
-  const int grp = row_group[r];
-
-  float qv[MAXG][DPL], acc[MAXG][DPL], mrun[MAXG], lrun[MAXG];
-#pragma unroll
-  for (int h = 0; h < MAXG; ++h) {
-    mrun[h] = -INFINITY;
-    lrun[h] = 0.f;
-#pragma unroll
-    for (int d = 0; d < DPL; ++d) {
-      acc[h][d] = 0.f;
-      qv[h][d] = (h < gq) ? __bfloat162float(q[((long long)r * nq + kvh * gq + h) * HD + lane * DPL + d]) * scale : 0.f;
-    }
-  }
-  for (int j = k0 + warp; j < k1; j += 4) {
-    const bf16* krow;
-    const bf16* vrow;
-    if (j < P) {
-      krow = kp + (((long long)grp * p_max + j) * nkv + kvh) * HD;
-      vrow = vp + (((long long)grp * p_max + j) * nkv + kvh) * HD;
-    } else {
-      krow = kc + (((long long)r * c_max + (j - P)) * nkv + kvh) * HD;
-      vrow = vc + (((long long)r * c_max + (j - P)) * nkv + kvh) * HD;
-    }
-    float kf[DPL], vf[DPL];
-#pragma unroll
-    for (int d = 0; d < DPL; ++d) {
-      kf[d] = __bfloat162float(krow[lane * DPL + d]);
-      vf[d] = __bfloat162float(vrow[lane * DPL + d]);
-    }
-#pragma unroll
-    for (int h = 0; h < MAXG; ++h) {
-      if (h < gq) {
-        float s = 0.f;
-#pragma unroll
-        for (int d = 0; d < DPL; ++d) s += qv[h][d] * kf[d];
-        s = wsum(s);
-        const float mn = fmaxf(mrun[h], s);
-        const float corr = __expf(mrun[h] - mn);
-        const float p = __expf(s - mn);
-        lrun[h] = lrun[h] * corr + p;
-#pragma unroll
-        for (int d = 0; d < DPL; ++d) acc[h][d] = acc[h][d] * corr + p * vf[d];
-        mrun[h] = mn;
-      }
-    }
-  }
-  // merge the 4 warps through shared memory
-  __shared__ float sm_m[4][MAXG], sm_l[4][MAXG], sm_acc[4][MAXG][HD];
-  if (lane == 0) {
-#pragma unroll
-    for (int h = 0; h < MAXG; ++h) {
-      sm_m[warp][h] = mrun[h];
-      sm_l[warp][h] = lrun[h];
-    }
-  }
-#pragma unroll
-  for (int h = 0; h < MAXG; ++h)
-#pragma unroll
-    for (int d = 0; d < DPL; ++d) sm_acc[warp][h][lane * DPL + d] = acc[h][d];
-  __syncthreads();
-  // part layout: [R][nq][nsplit][HD + 2]  (acc..., m, l)
-  for (int i = threadIdx.x; i < gq * HD; i += blockDim.x) {
-    const int h = i / HD, d = i % HD;
-    const float m = fmaxf(fmaxf(sm_m[0][h], sm_m[1][h]), fmaxf(sm_m[2][h], sm_m[3][h]));
-    float a = 0.f, l = 0.f;
-#pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      const float c = (sm_m[w][h] == -INFINITY) ? 0.f : __expf(sm_m[w][h] - m);
-      a += sm_acc[w][h][d] * c;
-      l += sm_l[w][h] * c;
-    }
-    float* dst = part + (((long long)r * nq + kvh * gq + h) * nsplit + sp) * (HD + 2);
-    dst[d] = a;
-    if (d == 0) {
-      dst[HD] = m;
-      dst[HD + 1] = l;
-    }
-  }
-}
-
-
 // ------------------------------------------------------------------------------------------------
 // Fused decode attention: rotary on q/k (HF bf16 op order) + KV append + split-KV attention + combine in ONE launch.
 // Grid (R, nkv, nsplit), 4 warps. Per CTA:
@@ -862,23 +732,6 @@ __global__ void __launch_bounds__(NW * 32) decode_attn_mma_kernel(
   }
 }
 
-template <int HD>
-__global__ void decode_attn_combine_kernel(const float* __restrict__ part, bf16* __restrict__ out, int nsplit) {
-  const long long rh = blockIdx.x;  // row * nq + head
-  const float* p = part + rh * nsplit * (HD + 2);
-  float m = -INFINITY;
-  for (int s = 0; s < nsplit; ++s) m = fmaxf(m, p[s * (HD + 2) + HD]);
-  for (int d = threadIdx.x; d < HD; d += blockDim.x) {
-    float a = 0.f, l = 0.f;
-    for (int s = 0; s < nsplit; ++s) {
-      const float ms = p[s * (HD + 2) + HD];
-      const float c = (ms == -INFINITY) ? 0.f : __expf(ms - m);
-      a += p[s * (HD + 2) + d] * c;
-      l += p[s * (HD + 2) + HD + 1] * c;
-    }
-    out[rh * HD + d] = __float2bfloat16(a / l);
-  }
-}
 
 // ------------------------------------------------------------------------------------------------
 // Fused sampler: one CTA per row over fp32 logits[V].
@@ -1208,40 +1061,6 @@ int iadr1_rmsnorm_f32in(const float* x, const void* w, void* y, int rows, int co
   launch_kernel(rmsnorm_f32in_kernel, dim3(rows), dim3(256), 0, (cudaStream_t)stream, x, (const bf16*)w, (bf16*)y, cols,
                 eps, zero_buf, zero_buf ? zero_per_row : 0);
   IADR1_CHECK_LAUNCH("rmsnorm_f32in");
-  return 0;
-}
-
-int iadr1_decode_rope_append(const float* qkv, const float* cos_tab, const float* sin_tab, const int* rope_delta,
-                             const int* row_plen, const int* state, void* q_out, void* kc, void* vc, int rows, int nq, int nkv, int hd,
-                             int c_max, int max_pos, void* stream) {
-  if (rows <= 0) return 0;
-  decode_rope_append_kernel<<<dim3(rows, nq + 2 * nkv), 64, 0, (cudaStream_t)stream>>>(
-      qkv, cos_tab, sin_tab, rope_delta, row_plen, state, (bf16*)q_out, (bf16*)kc, (bf16*)vc, nq, nkv, hd, c_max, max_pos);
-  IADR1_CHECK_LAUNCH("decode_rope_append");
-  return 0;
-}
-
-int iadr1_decode_attention(const void* q, const void* kp, const void* vp, const void* kc, const void* vc,
-                           const int* state, const int* row_group, const int* row_plen, float* part, void* out, int rows, int nq, int nkv,
-                           int hd, int p_max, int c_max, int nsplit, float scale, void* stream) {
-  if (rows <= 0) return 0;
-  if (nq % nkv || nq / nkv > 8) return set_error("decode_attention: group size %d unsupported (max 8)", nq / nkv);
-  const int chunk = (p_max + c_max + nsplit - 1) / nsplit;
-  cudaStream_t st = (cudaStream_t)stream;
-#define IADR1_DECODE_ATTN(HD)                                                                                        \
-  do {                                                                                                               \
-    decode_attn_partial_kernel<HD><<<dim3(rows, nkv, nsplit), 128, 0, st>>>(                                         \
-        (const bf16*)q, (const bf16*)kp, (const bf16*)vp, (const bf16*)kc, (const bf16*)vc, state, row_group, row_plen, \
-        part, nq, nkv, p_max, c_max, chunk, scale);                                                                  \
-    IADR1_CHECK_LAUNCH("decode_attn_partial");                                                                       \
-    decode_attn_combine_kernel<HD><<<rows * nq, HD < 64 ? 32 : 64, 0, st>>>(part, (bf16*)out, nsplit);               \
-  } while (0)
-  if (hd == 128) IADR1_DECODE_ATTN(128);
-  else if (hd == 64) IADR1_DECODE_ATTN(64);
-  else if (hd == 32) IADR1_DECODE_ATTN(32);
-  else return set_error("decode_attention: head_dim %d unsupported (32, 64 or 128)", hd);
-#undef IADR1_DECODE_ATTN
-  IADR1_CHECK_LAUNCH("decode_attn_combine");
   return 0;
 }
 

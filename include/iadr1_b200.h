@@ -137,13 +137,10 @@ int iadr1_decode_embed(const void* embed, const int* tok, float* h, int rows, in
 /* zero_buf (optional): rows x zero_per_row fp32 cleared in the same launch (the next split-K GEMM's target).        */
 int iadr1_rmsnorm_f32in(const float* x, const void* w, void* y, int rows, int cols, float eps, float* zero_buf,
                         int zero_per_row, void* stream);
-int iadr1_decode_rope_append(const float* qkv, const float* cos_tab, const float* sin_tab, const int* rope_delta,
-                             const int* row_plen, const int* state, void* q_out, void* kc, void* vc, int rows, int nq, int nkv, int hd,
-                             int c_max, int max_pos, void* stream);
-int iadr1_decode_attention(const void* q, const void* kp, const void* vp, const void* kc, const void* vc,
-                           const int* state, const int* row_group, const int* row_plen, float* part, void* out, int rows, int nq, int nkv,
-                           int hd, int p_max, int c_max, int nsplit, float scale, void* stream);
-/* One launch: rotary on q/k + KV append + split-KV attention over (shared prompt prefix, row slab) + split merge.   */
+/* One launch: rotary on q/k + KV append + split-KV attention over (shared prompt prefix, row slab) + split merge.
+ * head_dim 64 / 128: tensor-core kernel, nsplit > 0 = 4-warp CTAs (64-key chunks), nsplit < 0 = |nsplit| splits with 2-warp
+ * CTAs (32-key chunks); other head sizes: scalar kernel, nsplit = ceil((p_max + c_max) / 128).
+ * part: fp32 [rows][nq][|nsplit|][hd + 2] scratch; tickets: int32 [rows * nkv], zero before the first call.           */
 int iadr1_decode_attention_fused(const float* qkv, const float* cos_tab, const float* sin_tab, const int* rope_delta,
                                  const void* kp, const void* vp, void* kc, void* vc, const int* state,
                                  const int* row_group, const int* row_plen, float* part, int* tickets, void* out, int rows,
