@@ -118,9 +118,15 @@ def cpu_reference_sample(args, cfg_full, steps=1, warmup=0):
     proc = SyntheticProcessor(twin, max_pixels=480000)
     ex = synthetic_dataset(1, args.image_size)[0]
     enc = proc(text=[proc.apply_chat_template(ex["prompt"])], images=ex["image"])
-    ids, px, grid = enc["input_ids"][0], enc["pixel_values"], enc["image_grid_thw"].tolist()
+    ids = enc["input_ids"][0]
+    if twin.family == "llava_onevision":      # HF layout: crops + image sizes
+        px, grid = enc["pixel_values"], enc["image_sizes"].tolist()
+        Np = px.shape[1] * twin.vision.tokens_per_crop
+    else:
+        px, grid = enc["pixel_values"], enc["image_grid_thw"].tolist()
+        Np = px.shape[0]
     ref = CPUReference(twin, seed=0, threads=cores)
-    P, Np = ids.shape[0], px.shape[0]
+    P = ids.shape[0]
     times = []
     for i in range(warmup + steps):
         dt, _ = ref.group_step(ids, px, grid, G, C_s, lambda comp: torch.randn(comp.shape[0]).tolist(), seed=i)

@@ -31,7 +31,11 @@ def reference_form_flops(cfg, G, P, C, n_patches):
     mlp = (3 if v.kind == "qwen2_5_vl" else 2) * E * v.intermediate_size
     Wblk = 4 * E * E + mlp
     m = v.spatial_merge_size ** 2 * E
-    Fv = 2 * n_patches * (v.patch_dim * E + v.depth * Wblk) + 2 * (n_patches // v.spatial_merge_size ** 2) * (m * m + m * v.out_hidden_size)
+    if v.kind == "siglip":   # projector: Linear(E -> H) + Linear(H -> H) per patch token
+        head = 2 * n_patches * (E * v.out_hidden_size + v.out_hidden_size ** 2)
+    else:                    # merger: two Linears over 4-patch units
+        head = 2 * (n_patches // v.spatial_merge_size ** 2) * (m * m + m * v.out_hidden_size)
+    Fv = 2 * n_patches * (v.patch_dim * E + v.depth * Wblk) + head
     attn = t.num_layers * 2 * T * T * t.num_heads * t.head_dim
     fwd = G * (2 * T * (Wd + Wh) + attn + Fv)
     train = 4 * fwd
@@ -50,23 +54,25 @@ class CPUReference:
         self.opt = torch.optim.AdamW(self.policy.parameters(), lr=1e-6, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0)
 
     def group_step(self, prompt_ids, pixel_values, grid_thw, G, C, reward_fn, beta=0.04, seed=0):
-        """prompt_ids [P] LongTensor, pixel_values [Np, patch_dim] float, grid_thw [[t,h,w]]. Returns (seconds, loss)."""
+        """prompt_ids [P] LongTensor; Qwen families: pixel_values [Np, patch_dim] float + grid_thw [[t,h,w]];
+        LLaVA-OneVision: pixel_values [1, n_crops, 3, S, S] + grid_thw = image_sizes [[H, W]]. Returns (seconds, loss)."""
         cfg = self.cfg
         t0 = time.perf_counter()
         torch.manual_seed(seed)
         ids = prompt_ids[None, :].repeat(G, 1)                                   # sc_grpo_trainer.py:624-628
-        px = pixel_values.repeat(G, 1)
-        grid = torch.tensor(grid_thw * G)
+        if cfg.family == "llava_onevision":
+            mm = dict(pixel_values=pixel_values.repeat(G, 1, 1, 1, 1), image_sizes=torch.tensor(grid_thw * G))
+        else:
+            mm = dict(pixel_values=pixel_values.repeat(G, 1), image_grid_thw=torch.tensor(grid_thw * G))
         P = ids.shape[1]
         with torch.no_grad():                                                      # stands in for vLLM, :343-358, :667
-            out = self.policy.generate(input_ids=ids, pixel_values=px, image_grid_thw=grid,
-                                       attention_mask=torch.ones_like(ids), do_sample=True, temperature=0.9, top_k=50,
-                                       top_p=0.9, max_new_tokens=C, min_new_tokens=C, pad_token_id=cfg.pad_token_id,
-                                       eos_token_id=cfg.eos_token_id)
+            out = self.policy.generate(input_ids=ids, attention_mask=torch.ones_like(ids), do_sample=True, temperature=0.9,
+                                       top_k=50, top_p=0.9, max_new_tokens=C, min_new_tokens=C,
+                                       pad_token_id=cfg.pad_token_id, eos_token_id=cfg.eos_token_id, **mm)
         comp = out[:, P:]
         mask = grpo_ref.completion_mask_ref(comp, cfg.eos_token_id)
         attn = torch.cat([torch.ones(G, P, dtype=torch.long), mask.long()], 1)
-        kw = dict(input_ids=out, attention_mask=attn, pixel_values=px, image_grid_thw=grid, use_cache=False)
+        kw = dict(input_ids=out, attention_mask=attn, use_cache=False, **mm)
         logps = per_token_logps(self.policy(**kw).logits, out)[:, P - 1:]          # :733-735
         with torch.no_grad():
             ref_logps = per_token_logps(self.ref(**kw).logits, out)[:, P - 1:]     # :737-743

@@ -138,3 +138,26 @@ def test_golden_fixture_regenerates_from_hf():
                        fix["position_ids"], fix["attention_mask"])
     lp = per_token_logps(logits, fix["input_ids"])[:, P - 1:]
     assert torch.allclose(lp, fix["logp_fp32"], atol=1e-5)
+
+
+@pytest.mark.parametrize("family", ["qwen2_5_vl", "llava_onevision"])
+def test_cpu_reference_group_step_runs(family):
+    """The reference-form CPU step (HF generate + two log-prob forwards + restated loss + autograd + AdamW) that bench.py
+    times as `cpu_baseline` / `--impl reference`, on the tiny twins of both processor layouts."""
+    pytest.importorskip("transformers")
+    from iad_r1_b200.config import tiny_config
+    from iad_r1_b200.synthetic import SyntheticProcessor, synthetic_dataset
+    from oracle.cpu_reference import CPUReference, reference_form_flops
+    cfg = tiny_config(family)
+    proc = SyntheticProcessor(cfg)
+    ex = synthetic_dataset(1, 112)[0]
+    enc = proc(text=[proc.apply_chat_template(ex["prompt"])], images=ex["image"])
+    ids = enc["input_ids"][0]
+    px, grid = (enc["pixel_values"], enc["image_sizes"].tolist()) if family == "llava_onevision" else \
+        (enc["pixel_values"], enc["image_grid_thw"].tolist())
+    ref = CPUReference(cfg, seed=0, threads=2)
+    before = [p.detach().clone() for p in ref.policy.parameters()]
+    dt, loss = ref.group_step(ids, px, grid, 4, 6, lambda comp: torch.randn(comp.shape[0]).tolist(), seed=0)
+    assert dt > 0 and loss == loss
+    assert any(not torch.equal(a, b) for a, b in zip(before, ref.policy.parameters())), "AdamW step must move the policy"
+    assert reference_form_flops(cfg, 4, ids.shape[0], 6, 80) > 0
