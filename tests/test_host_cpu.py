@@ -128,6 +128,39 @@ def test_vision_geometry_matches_hf():
         assert torch.equal(geo.reverse_index.long(), torch.argsort(wi))
 
 
+def test_vision_geometry_segments_and_llava_packing_offsets():
+    """Host bookkeeping behind the batched vision attention and the window-level tower pass: equal-length segment
+    detection, per-image relative key ranges for ragged batches, and the anyres packing index over several images."""
+    from iad_r1_b200.config import PRESETS, tiny_config
+    from iad_r1_b200 import geometry as G
+    v = PRESETS["qwen2.5-vl-3b"]().vision
+    geo = G.VisionGeometry(v, [(1, 32, 32)] * 3, "cpu")
+    assert geo.full_seg == 1024 and geo.win_seg == 64 and geo.n_patches == 3072       # 448 x 448: 16 windows of 64 patches
+    lo, hi = geo.seg_ranges[64]
+    assert lo.tolist() == [0] * 64 and hi.tolist() == [64] * 64
+    tv = tiny_config("qwen2_5_vl").vision
+    rag = G.VisionGeometry(tv, [(1, 8, 8), (1, 10, 8)], "cpu")
+    assert rag.full_seg == 0 and rag.image_ranges == [(0, 64), (64, 144)]
+    for kind in ("full", "win"):
+        for j, (a, b) in enumerate(rag.image_ranges):
+            lo_j, hi_j = rag.relative_ranges(kind, j)
+            lo_abs, hi_abs = rag._abs[kind]
+            assert torch.equal(lo_j + a, lo_abs[a:b]) and torch.equal(hi_j + a, hi_abs[a:b])
+            assert int(lo_j.min()) >= 0 and int(hi_j.max()) <= b - a                   # keys never leave the image
+    cfg = tiny_config("llava_onevision")
+    tpc = cfg.vision.tokens_per_crop
+    sg = G.SiglipGeometry(cfg, [(5, 80, 100), (2, 56, 56)], "cpu")
+    i0, n0 = G.llava_pack_index(cfg, (80, 100))
+    i1, n1 = G.llava_pack_index(cfg, (56, 56))
+    assert (n0, n1) == (5, 2) and sg.n_crops == 7 and sg.n_patches == 7 * tpc and sg.n_tokens == len(i0) + len(i1)
+    pk = sg.pack_index.numpy()
+    assert (pk[:len(i0)] == i0).all()
+    second = pk[len(i0):]
+    assert (second[i1 >= 0] == i1[i1 >= 0] + n0 * tpc).all() and (second[i1 < 0] == -1).all()
+    with pytest.raises(ValueError):
+        G.SiglipGeometry(cfg, [(3, 80, 100)], "cpu")                                  # crop count must match the image size
+
+
 def test_param_store_hf_names_roundtrip_cpu():
     from iad_r1_b200.config import tiny_config
     from iad_r1_b200.params import ParamStore
