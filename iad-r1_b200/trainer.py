@@ -70,6 +70,25 @@ class _LogProbFn(torch.autograd.Function):
         return None, None, None, None, None, None, None, None
 
 
+def call_reward_funcs(reward_funcs, example: dict, texts: list, current_step: int) -> torch.Tensor:
+    """Calls every reward callback with the reference's convention (ref: train/stage_rl/trainer/sc_grpo_trainer.py:749-781):
+    `reward_func(prompts=[prompt] * G, completions=..., current_step=global_step, **{column: [value] * G})` where
+    completions are `[[{"role": "assistant", "content": text}]]` for conversational prompts (plain strings otherwise) and
+    every dataset column except `prompt` / `completion` is repeated G times (Q10). Returns fp32 [G, n_funcs] on the CPU.
+    Callbacks are called verbatim, not wrapped: a callback that returns the wrong number of rewards (Q9) raises here, as
+    the tensor assignment does in the reference."""
+    G = len(texts)
+    conv = is_conversational(example)
+    completions = [[{"role": "assistant", "content": c}] for c in texts] if conv else list(texts)
+    prompts = [example["prompt"] for _ in range(G)]
+    reward_kwargs = {k: [example[k]] * G for k in example.keys() if k not in ("prompt", "completion")}
+    out = torch.zeros(G, len(reward_funcs), dtype=torch.float32)
+    for i, rf in enumerate(reward_funcs):
+        r = rf(prompts=prompts, completions=completions, current_step=current_step, **reward_kwargs)
+        out[:, i] = torch.tensor(r, dtype=torch.float32)
+    return out
+
+
 class SCGRPOTrainer(TrainerCore):
     def __init__(self, model, reward_funcs, args: GRPOConfig = None, train_dataset=None, eval_dataset=None,
                  processing_class=None, reward_processing_classes=None, callbacks=None, optimizers=(None, None),
@@ -373,14 +392,7 @@ class SCGRPOTrainer(TrainerCore):
         # ---- rewards on decoded text (CPU Python callbacks, verbatim convention :749-781) ----
         with self._phase("rewards"):
             texts = self.processing_class.batch_decode(completion_ids.cpu(), skip_special_tokens=True)
-            conv = is_conversational(example)
-            completions = [[{"role": "assistant", "content": c}] for c in texts] if conv else texts
-            prompts = [example["prompt"] for _ in range(G)]
-            rewards_per_func = torch.zeros(G, len(self.reward_funcs), device=dev)
-            reward_kwargs = {k: [example[k]] * G for k in example.keys() if k not in ("prompt", "completion")}
-            for i, rf in enumerate(self.reward_funcs):
-                out = rf(prompts=prompts, completions=completions, current_step=self.state.global_step, **reward_kwargs)
-                rewards_per_func[:, i] = torch.tensor(out, dtype=torch.float32, device=dev)
+            rewards_per_func = call_reward_funcs(self.reward_funcs, example, texts, self.state.global_step).to(dev)
         rw = torch.tensor(a.reward_weights, device=dev) if (a.reward_weights and a.loss_mode == "clip") else None
         adv, rewards, std = grpo_loss.group_advantages(rewards_per_func, G, a.scale_rewards or a.loss_mode == "sc", rw)  # :784-793
         if a.loss_mode == "sc":

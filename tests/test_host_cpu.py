@@ -375,3 +375,73 @@ def test_bench_reference_arm_contract():
     assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in line["config"] and "qwen2.5-vl-3b" in line["config"]["workload"]
+
+
+def _reference_rewards():
+    """The reference's own reward callbacks (train/stage_rl/reward.py + reward_process/), imported from /root/reference
+    behind a stub for `sentence_transformers` (only description_reward, unused by the default registry, needs it).
+    CPU-container only: the reference tree does not exist on the GPU box."""
+    import importlib
+    import types
+    ref = "/root/reference/train/stage_rl"
+    if not os.path.isdir(ref):
+        pytest.skip("reference tree not present")
+    if "sentence_transformers" not in sys.modules:
+        stub = types.ModuleType("sentence_transformers")
+        stub.SentenceTransformer = lambda *a, **k: None
+        stub.models = types.SimpleNamespace()
+        stub.util = types.SimpleNamespace()
+        sys.modules["sentence_transformers"] = stub
+    sys.path.insert(0, ref)
+    try:
+        return importlib.import_module("reward")
+    except Exception as e:      # anything else the reference imports at module scope
+        pytest.skip(f"reference reward module not importable here: {type(e).__name__}: {e}")
+    finally:
+        sys.path.remove(ref)
+
+
+def test_reference_reward_callbacks_drop_in(capsys):
+    """Boundary (b): the reference's UNMODIFIED accuracy_reward / consistency_reward run through our calling convention
+    (ref: sc_grpo_trainer.py:749-781, Q10) and through `SCGRPOTrainer._group_loss` - rewards, group advantages (unbiased
+    std + 1e-4, :784-793) and the SC loss (:796-798) come out as the reference's arithmetic gives them."""
+    reward = _reference_rewards()
+    from collections import defaultdict
+    from contextlib import nullcontext
+    from types import SimpleNamespace
+    from iad_r1_b200 import grpo_loss
+    from iad_r1_b200.grpo_config import GRPOConfig
+    from iad_r1_b200.trainer import SCGRPOTrainer, call_reward_funcs
+    from oracle import grpo_ref
+    yes = "<think>a</think><location>top left corner</location><type>scratch</type><answer>yes</answer>"
+    texts = [yes, "<think>a</think><answer>no</answer>", "<think>a</think><location>center</location><type>hole</type><answer>yes</answer>",
+             "no tags at all"]
+    example = {"prompt": [{"role": "user", "content": [{"type": "image"}, {"type": "text", "text": "q"}]}], "image": ["/x.png"],
+               "solution": "<answer>yes</answer><location>upper left</location><type>scratch</type>", "problem": "q", "id": 7}
+    funcs = [reward.accuracy_reward, reward.consistency_reward]
+    r = call_reward_funcs(funcs, example, texts, current_step=3)
+    capsys.readouterr()                                    # the reference callbacks print debug lines
+    assert r.shape == (4, 2)
+    assert r[0, 0].item() == 2.0 and r[0, 1].item() == 1.0   # right answer (1) + (type 1.0 + location 1) / 2; format ok
+    assert r[1].tolist() == [0.0, 0.0] and r[3].tolist() == [0.0, 0.0]
+    assert 1.0 <= r[2, 0].item() < 2.0 and r[2, 1].item() == 1.0
+    # the same callbacks through the trainer's per-group loss on the CPU (a stand-in `self`: no CUDA needed for this part)
+    G, C = 4, 5
+    eos = 99
+    comp = torch.tensor([[5, 6, 7, eos, 0], [5, 6, eos, 0, 0], [1, 2, 3, 4, 5], [eos, 0, 0, 0, 0]])
+    proc = SimpleNamespace(eos_token_id=eos, batch_decode=lambda ids, skip_special_tokens=True: texts)
+    args = GRPOConfig(output_dir="/tmp/x", num_generations=G, beta=0.04)
+    me = SimpleNamespace(num_generations=G, device=torch.device("cpu"), args=args, processing_class=proc, reward_funcs=funcs,
+                         state=SimpleNamespace(global_step=3), beta=0.04, _metrics=defaultdict(list), _iteration=0, _old_logps={},
+                         max_completion_length=C, _phase=lambda name: nullcontext())
+    torch.manual_seed(0)
+    logps = (torch.randn(G, C) - 3).requires_grad_(True)
+    ref_logps = logps.detach() + 0.1 * torch.randn(G, C)
+    loss = SCGRPOTrainer._group_loss(me, example, comp, logps, ref_logps)
+    capsys.readouterr()
+    mask = grpo_ref.completion_mask_ref(comp, eos)
+    adv, _, _ = grpo_ref.advantages_ref(r, G)
+    want, kl = grpo_ref.sc_grpo_loss_ref(logps.detach(), ref_logps, adv, mask, 0.04)
+    assert torch.allclose(loss.detach(), want, atol=1e-6)
+    assert abs(me._metrics["reward"][0].item() - r.sum(1).mean().item()) < 1e-6
+    assert set(me._metrics) >= {"completion_length", "rewards/accuracy_reward", "rewards/consistency_reward", "reward", "reward_std", "kl"}
