@@ -231,6 +231,18 @@ PRESETS = {
 }
 
 
+def depth_reduced(cfg: VLMConfig, text_layers: int = 2, vision_depth: int = 2) -> VLMConfig:
+    """TRUE widths (hidden sizes, head dims, GQA ratios, MLP widths, vocabulary) at reduced depth: the geometry of the
+    true-width parity tests and of the CPU baseline's bounded sample. Qwen2.5-VL keeps one windowed and one full-attention
+    vision block."""
+    import copy
+    c = copy.deepcopy(cfg)
+    c.text.num_layers = text_layers
+    c.vision.depth = vision_depth
+    c.vision.fullatt_block_indexes = (vision_depth - 1,) if c.vision.kind == "qwen2_5_vl" else ()
+    return c
+
+
 def tiny_config(family: str = "qwen2_5_vl") -> VLMConfig:
     """A few-hundred-k-parameter twin with every structural feature of the real model (GQA, M-RoPE sections, windowed +
     full vision blocks, ragged MLP width, tied head) - the parity-test geometry (tests/golden)."""

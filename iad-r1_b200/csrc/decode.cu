@@ -27,6 +27,8 @@ enum StateWord : int {
   ST_STEP = 0,       // index of the completion token fed this step (KV slot); logits predict token ST_STEP + 1
   ST_RESERVED = 1,
   ST_UNFINISHED = 2, // rows that have not produced EOS yet (host polls for early exit)
+  ST_SEED_LO = 4,    // per-generate() sampling seed kept in DEVICE memory (XORed with the kernel's seed argument): a
+  ST_SEED_HI = 5,    // captured CUDA graph replays with frozen arguments, so the seed must not live in them
   ST_WORDS = 8
 };
 
@@ -984,7 +986,9 @@ __global__ void __launch_bounds__(1024) sample_kernel(const float* __restrict__ 
       ++nkeep;
     }
     curandStatePhilox4_32_10_t rng;
-    curand_init(seed, (unsigned long long)r, (unsigned long long)out_pos, &rng);
+    const unsigned long long dev_seed = (unsigned long long)(unsigned int)state[ST_SEED_LO] |
+                                        ((unsigned long long)(unsigned int)state[ST_SEED_HI] << 32);
+    curand_init(seed ^ dev_seed, (unsigned long long)r, (unsigned long long)out_pos, &rng);
     const float u = curand_uniform(&rng) * kept;  // (0, kept]
     float c = 0.f;
     int pick = nkeep - 1;

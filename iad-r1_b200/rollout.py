@@ -113,8 +113,9 @@ class RolloutEngine:
         L.check(lib.iadr1_rmsnorm_f32in(self.h.data_ptr(), p["norm.weight"].data_ptr(), self.xn.data_ptr(), self.R,
                                         t.hidden_size, t.rms_norm_eps, None, 0, s), "rmsnorm_f32in")
         self._skinny(self.vlm.params.lm_head, self.xn, self.logits)
+        # seed argument 0: the per-call seed lives in state[4:6] on the device (a captured graph freezes its arguments)
         L.check(lib.iadr1_sample(self.logits.data_ptr(), self.R, t.vocab_size, self.temperature, self.top_k, self.top_p,
-                                 self._seed, self.state.data_ptr(), self.tok.data_ptr(), self.finished.data_ptr(),
+                                 0, self.state.data_ptr(), self.tok.data_ptr(), self.finished.data_ptr(),
                                  self.out_tokens.data_ptr(), self.c_max, self.cfg.eos_token_id, self.cfg.pad_token_id,
                                  int(self.forbid_eos), first, s), "sample")
 
@@ -172,8 +173,11 @@ class RolloutEngine:
             raise ValueError(f"need 1..{self.n_groups} prompts, got {n}")
         C = self.c_max if max_new_tokens is None else min(max_new_tokens, self.c_max)
         t, vlm, G = self.cfg.text, self.vlm, self.G
-        self._seed = int(seed)
+        self._seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         self.state.zero_()
+        lo, hi = self._seed & 0xFFFFFFFF, self._seed >> 32
+        self.state[4:6] = torch.tensor([lo - (1 << 32) if lo >= (1 << 31) else lo, hi - (1 << 32) if hi >= (1 << 31) else hi],
+                                       dtype=i32, device=self.state.device)
         self.finished.zero_()
         self.gu.zero_()
         self.out_tokens.fill_(self.cfg.pad_token_id)

@@ -111,13 +111,17 @@ class SCGRPOTrainer(TrainerCore):
         # ---- model / reference ----------------------------------------------------------------------------------------
         if isinstance(model, str):
             self.model_id = model
-            mid = model.lower()
-            # family by substring of the model id, as the reference does (sc_grpo_trainer.py:116-137)
-            families = ("qwen2-vl", "qwen2_vl", "qwen2vl", "qwen2.5-vl", "qwen2.5_vl", "qwen2.5vl",
-                        "llava-ov", "llava_ov", "llava_si", "llava-onevision", "llava_onevision")
-            if not any(k in mid for k in families):
-                # the reference raises ValueError for unknown families (sc_grpo_trainer.py:141-144); LLaVA-1.5 / -Next: §8f
-                raise ValueError(f"Unsupported model: {model} (B200 path supports Qwen2-VL / Qwen2.5-VL / LLaVA-OneVision)")
+            # The family comes from config.json's model_type (the reference's own PA-SFT output directories, e.g.
+            # `Qwen_Intruct_2_5_VL_3B_Expert_AD_PA_SFT`, match none of its substring keys). The reference picks the HF class
+            # by substring of the id (sc_grpo_trainer.py:116-137) and falls through to AutoModelForCausalLM otherwise; the
+            # substring test survives here only as the error message for a path WITHOUT a readable config.json.
+            if not os.path.isfile(os.path.join(model, "config.json")):
+                families = ("qwen2-vl", "qwen2_vl", "qwen2vl", "qwen2.5-vl", "qwen2.5_vl", "qwen2.5vl", "qwen2_5_vl",
+                            "llava-ov", "llava_ov", "llava_si", "llava-onevision", "llava_onevision")
+                hint = "" if any(k in model.lower() for k in families) else \
+                    " (and the id names none of the supported families: Qwen2-VL / Qwen2.5-VL / LLaVA-OneVision)"
+                raise ValueError(f"Unsupported model: {model}: no config.json under that path{hint}; there is no hub access "
+                                 f"on the training box, pass a local checkpoint directory")
             self.cfg, self.params = load_pretrained(model, self.device)
         elif isinstance(model, VLMConfig):
             self.model_id = model.family

@@ -146,7 +146,9 @@ int iadr1_decode_attention_fused(const float* qkv, const float* cos_tab, const f
                                  const int* row_group, const int* row_plen, float* part, int* tickets, void* out, int rows,
                                  int nq, int nkv, int hd, int p_max, int c_max, int nsplit, int max_pos, float scale,
                                  void* stream);
-/* temperature -> top-k (ties kept) -> top-p -> multinomial; SamplingParams at sc_grpo_trainer.py:353-358.           */
+/* temperature -> top-k (ties kept) -> top-p -> multinomial; SamplingParams at sc_grpo_trainer.py:353-358.
+ * The Philox seed is `seed ^ (state[4] | state[5] << 32)`: callers that replay a captured graph keep the per-call seed
+ * in the device-resident state words and pass seed = 0 (graph arguments are frozen at capture).                     */
 int iadr1_sample(const float* logits, int rows, int V, float temperature, int top_k, float top_p,
                  unsigned long long seed, int* state, int* tok, int* finished, int* out_tokens, int c_max, int eos_id,
                  int pad_id, int forbid_eos, int first, void* stream);

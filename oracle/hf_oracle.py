@@ -84,9 +84,12 @@ def build_hf_model(cfg, seed=0, dtype=torch.float32, attn_implementation="eager"
     return m.to(dtype).eval()
 
 
-def hf_logits(model, input_ids, pixel_values, grid_thw, position_ids, attention_mask=None):
-    """`model(**inputs).logits` with explicit 4.51.3-semantics position ids."""
+def hf_logits(model, input_ids, pixel_values, grid_thw, position_ids, attention_mask=None, logits_to_keep=0):
+    """`model(**inputs).logits` with explicit 4.51.3-semantics position ids. `logits_to_keep=n` keeps only the last n
+    positions' logits (same values; used at true vocabulary width, where [G, T, 151936] fp32 would not fit the test box)."""
     kw = dict(input_ids=input_ids, position_ids=position_ids, use_cache=False)
+    if logits_to_keep:
+        kw["logits_to_keep"] = int(logits_to_keep)
     if attention_mask is not None:
         kw["attention_mask"] = attention_mask
     if pixel_values is not None:
@@ -95,13 +98,22 @@ def hf_logits(model, input_ids, pixel_values, grid_thw, position_ids, attention_
     return model(**kw).logits
 
 
-def hf_logits_llava(model, input_ids, pixel_values, image_sizes, position_ids, attention_mask=None):
+def hf_logits_llava(model, input_ids, pixel_values, image_sizes, position_ids, attention_mask=None, logits_to_keep=0):
     """LLaVA-OneVision: pixel_values [B, n_crops, 3, S, S] (crop 0 = base crop), image_sizes [B, 2] (H, W)."""
     kw = dict(input_ids=input_ids, position_ids=position_ids, use_cache=False,
               pixel_values=pixel_values.to(next(model.parameters()).dtype), image_sizes=image_sizes)
+    if logits_to_keep:
+        kw["logits_to_keep"] = int(logits_to_keep)
     if attention_mask is not None:
         kw["attention_mask"] = attention_mask
     return model(**kw).logits
+
+
+def completion_logps(tail_logits, input_ids, C):
+    """Log-probs of the last C tokens of every row from the logits of the last C + 1 positions (`logits_to_keep=C + 1`):
+    the same slice `_get_per_token_logps` + `[:, P - 1:]` keeps (sc_grpo_trainer.py:505-514, 734)."""
+    lp = tail_logits[:, :-1, :].float().log_softmax(-1)
+    return torch.gather(lp, 2, input_ids[:, -C:].unsqueeze(-1)).squeeze(-1)
 
 
 def per_token_logps(logits, input_ids):

@@ -226,10 +226,41 @@ def test_softmax_rows_and_bwd(ops):
     assert (S.masked_select(~mask.expand(Z, -1, -1)) == 0).all()
     dP = rnd(Z, Tq, Tk)
     dP[:, :, 40:] = float("inf")
+    dP0 = dP.clone()
     P = S.clone()
     ops.softmax_bwd_rows_(P, dP, lo, hi, Tq, Tk, Tk, Tq * Tk, Z)
-    dPf = torch.nan_to_num(dP.float(), posinf=0.0)
     assert torch.isfinite(dP).all()
+    # values under the ranged mask: dS = P * (dP - rowsum(P * dP)) inside [lo, hi), exact zeros outside
+    Pf = S.float()
+    dPf = torch.nan_to_num(dP0.float(), posinf=0.0).masked_fill(~mask, 0.0)
+    ref_ds = Pf * (dPf - (Pf * dPf).sum(-1, keepdim=True))
+    close(dP, ref_ds, 2 ** -6, "softmax bwd (ranged mask)")
+    assert (dP.masked_select(~mask.expand(Z, -1, -1)) == 0).all()
+
+
+def test_softmax_hole_mask_fwd_bwd(ops):
+    """The shared-prefix score layout [prefix keys | alignment gap (hole) | own-row keys]: the hole columns are masked in
+    the forward and carry exact zeros through the backward (ops.SharedPrefixAttention)."""
+    torch.manual_seed(6)
+    Z, Tq, P, Pp, Cc = 4, 48, 21, 24, 48
+    Tk = Pp + Cc
+    S = rnd(Z, Tq, Tk, scale=2.0)
+    S0 = S.clone()
+    lo = torch.zeros(Tq, device="cuda", dtype=torch.int32)
+    hi = (Pp + torch.arange(Tq, device="cuda") % Cc + 1).to(torch.int32)
+    ops.softmax_rows_(S, lo, hi, Tq, Tk, Tk, Tq * Tk, Z, hole=(P, Pp))
+    k = torch.arange(Tk, device="cuda")
+    mask = (k[None, :] < hi[:, None]) & ~((k[None, :] >= P) & (k[None, :] < Pp))
+    Sf = S0.float().requires_grad_(True)
+    ref = torch.softmax(Sf.masked_fill(~mask, float("-inf")), -1)
+    close(S, ref, 2 ** -7, "softmax (hole)")
+    assert (S.masked_select(~mask.expand(Z, -1, -1)) == 0).all()
+    dP = rnd(Z, Tq, Tk)
+    ref.backward(dP.float())
+    d = dP.clone()
+    ops.softmax_bwd_rows_(S.clone(), d, lo, hi, Tq, Tk, Tk, Tq * Tk, Z, hole=(P, Pp))
+    close(d, Sf.grad, 2 ** -5, "softmax bwd (hole)")
+    assert (d.masked_select(~mask.expand(Z, -1, -1)) == 0).all()
 
 
 def test_softmax_bwd_values(ops):

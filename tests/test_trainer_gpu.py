@@ -72,6 +72,26 @@ def test_cuda_graph_rollout_equals_eager(cuda):
     assert (outs[0] == outs[1]).float().mean().item() > 0.9
 
 
+def test_cuda_graph_rollout_follows_the_seed(cuda):
+    """the captured decode graph froze the seed of the first generate() call, so tokens 1..C-1 of every later
+    rollout reused one Philox stream. The seed now lives in device memory: a second call with another seed must change the
+    tokens BEYOND position 0, and the graph engine must agree with the eager engine for that second seed."""
+    from iad_r1_b200.rollout import RolloutEngine
+    from iad_r1_b200.synthetic import synthetic_dataset
+    cfg, tr = _tiny_trainer(cuda)
+    enc = [tr._encode_prompt(synthetic_dataset(1, 112)[0])]
+    res = {}
+    for graph in (True, False):
+        eng = RolloutEngine(tr.model, 1, 4, 128, 24, use_cuda_graph=graph, forbid_eos=True)
+        a, _ = eng.generate(enc, seed=5)
+        b, _ = eng.generate(enc, seed=6)          # graph engine: replays the graph captured during the seed=5 call
+        a2, _ = eng.generate(enc, seed=5)
+        assert torch.equal(a, a2), "same seed must reproduce the rollout"
+        assert (a[:, 1:] != b[:, 1:]).float().mean().item() > 0.3, "tokens past position 0 ignore the seed"
+        res[graph] = b
+    assert (res[True] == res[False]).float().mean().item() > 0.9
+
+
 @pytest.mark.parametrize("family", ["qwen2_5_vl", "llava_onevision"])
 def test_trainer_two_steps(cuda, family):
     from iad_r1_b200.synthetic import synthetic_dataset
@@ -253,3 +273,39 @@ def test_two_image_prompt_layouts_agree(cuda):
     tr.train_dataset = rows
     out = tr.train()
     assert out["global_step"] == 1 and torch.isfinite(tr.params.flat.float()).all()
+
+
+@pytest.mark.parametrize("family", ["llava_onevision", "qwen2_5_vl"])
+def test_two_stage_pa_sft_then_sc_grpo(cuda, tmp_path, family):
+    """BASELINE config 5, the chain of the reference's launch scripts: PA-SFT writes an HF-layout directory
+    (`--output_dir`, PA_SFT_*.sh), SC-GRPO is pointed at it by path (`MODEL_NAME_OR_PATH=<PA-SFT dir>`,
+    ref: scripts/train/SC_GRPO/SC_GRPO_LLaVA_OneVision_SI_0.5B.sh:25). The directory name matches none of the family
+    substrings (as the reference's `..._PA_SFT` names do not): the family is read from config.json."""
+    from iad_r1_b200.config import tiny_config
+    from iad_r1_b200.grpo_config import GRPOConfig
+    from iad_r1_b200.sft_trainer import PASFTTrainer, SFTArguments
+    from iad_r1_b200.synthetic import SyntheticProcessor, format_reward, make_noise_reward, synthetic_dataset, synthetic_image
+    from iad_r1_b200.trainer import SCGRPOTrainer
+    cfg = tiny_config(family)
+    sft_dir = str(tmp_path / "Expert_AD_PA_SFT")
+    data = [{"messages": [{"role": "user", "content": "<image>Is there a defect in the image?"},
+                          {"role": "assistant", "content": "<think> the surface is scratch </think> <answer> yes </answer>"}],
+             "images": [synthetic_image(i, 112)]} for i in range(2)]
+    sargs = SFTArguments(output_dir=sft_dir, do_train=True, learning_rate=1e-3, gradient_accumulation_steps=1, logging_steps=1,
+                         max_steps=2, save_strategy="no", cutoff_len=512, bf16=True)
+    sft = PASFTTrainer(cfg, sargs, train_dataset=data, processing_class=SyntheticProcessor(cfg))
+    sft.train()
+    sft.save_model(sft_dir)
+    stage1 = sft.params.flat.clone()
+    del sft
+    gargs = GRPOConfig(output_dir=str(tmp_path / "grpo"), per_device_train_batch_size=1, gradient_accumulation_steps=2,
+                       num_generations=4, max_completion_length=12, learning_rate=1e-3, beta=0.04, logging_steps=1,
+                       save_strategy="no", max_steps=1, seed=3)
+    tr = SCGRPOTrainer(model=sft_dir, reward_funcs=[format_reward, make_noise_reward(0)], args=gargs,
+                       processing_class=SyntheticProcessor(cfg), train_dataset=synthetic_dataset(2, 112))
+    assert tr.cfg.family == family
+    assert torch.equal(tr.params.flat, stage1), "stage 2 must start from the stage-1 weights bit for bit"
+    assert torch.equal(tr.ref_model.params.flat, stage1), "the KL reference is the PA-SFT policy"
+    out = tr.train()
+    assert out["global_step"] == 1 and not torch.equal(tr.params.flat, stage1)
+    assert torch.isfinite(tr.params.flat.float()).all()
