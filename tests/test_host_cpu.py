@@ -445,3 +445,44 @@ def test_reference_reward_callbacks_drop_in(capsys):
     assert torch.allclose(loss.detach(), want, atol=1e-6)
     assert abs(me._metrics["reward"][0].item() - r.sum(1).mean().item()) < 1e-6
     assert set(me._metrics) >= {"completion_length", "rewards/accuracy_reward", "rewards/consistency_reward", "reward", "reward_std", "kl"}
+
+
+def test_fmha_plan_host_logic():
+    """Work lists of the fused attention (iad-r1_b200/fmha.py): the query tiles reach every allowed (query, key) pair and
+    the key tiles of the backward cover every allowed pair exactly once (split items add, overlaps would double count)."""
+    import numpy as np
+    from iad_r1_b200 import fmha
+    r1, p1, s1 = fmha.shared_prefix_geometry(140, 2, 70, 0)
+    r2, p2, s2 = fmha.shared_prefix_geometry(90, 2, 130, 280)
+    lo = np.arange(552) // 64 * 64
+    layouts = {
+        "shared": fmha.shared_prefix_geometry(297, 3, 150),
+        "two_groups": (np.concatenate([r1, r2]), p1 + p2, s1 + s2),
+        "windows": (fmha.range_rows(lo, np.minimum(lo + 64, 552)), None, None),
+        "causal": (fmha.causal_rows(2, 200), [(0, 200), (200, 400)], [(0, 200), (200, 400)]),
+    }
+    for name, (rng, probs, segs) in layouts.items():
+        qi, ki = fmha.build_items(rng, probs, segs, nkv=2)
+        N = rng.shape[0]
+        mask = fmha.reference_mask(rng)
+        cover = np.zeros((N, N), dtype=np.int32)
+        for q0, nr, kv0, kv1, p0, p1_ in qi:
+            assert 0 < nr <= 128
+            rows = slice(q0, q0 + nr)
+            if kv1 > kv0:
+                cover[rows, kv0:min(N, kv0 + (kv1 - kv0 + 127) // 128 * 128)] += 1
+            if p1_ > p0:
+                cover[rows, p0:min(N, p0 + (p1_ - p0 + 127) // 128 * 128)] += 1
+        assert (cover[mask] >= 1).all(), name
+        # every query row belongs to exactly one query tile
+        rows_cov = np.zeros(N, dtype=np.int32)
+        for q0, nr, *_ in qi:
+            rows_cov[q0:q0 + nr] += 1
+        assert (rows_cov == 1).all(), name
+        kcover = np.zeros((N, N), dtype=np.int32)
+        for k0, nk, q0, q1 in ki:
+            assert 0 < nk <= 128 and q1 > q0
+            kcover[q0:q1, k0:k0 + nk] += 1
+        assert (kcover[mask] == 1).all() and kcover.max() == 1, name
+    with __import__("pytest").raises(ValueError):
+        fmha.build_items(np.array([[0, 0, 0, 0]], dtype=np.int32))
