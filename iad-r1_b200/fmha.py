@@ -28,8 +28,9 @@ def build_items(rng: np.ndarray, q_problems=None, k_segments=None, nkv: int = 1,
     """rng int32 [N, 4] = (lo, hi, plo, phi) per query row. Returns (q_items [n, 6], k_items [m, 4]) int32.
 
     q_items: 128-row query tiles {q0, nrows, kv0, kv1, p0, p1} (tiles never straddle two `q_problems`), heaviest first.
-    k_items: {k0, nkeys, q0, q1}: 128-key tiles of every key segment with the contiguous range of query rows that may attend
-    to them, long query ranges split so that no unit dominates the backward's critical path, heaviest first."""
+    k_items: {k0, nkeys, q0, q1, f0, f1}: 128-key tiles of every key segment with the contiguous range of query rows that may
+    attend to them (q0 rounded down to a multiple of 4), long query ranges split so that no unit dominates the backward's
+    critical path, heaviest first; 64-query tiles f0 <= t < f1 of the range are allowed in full."""
     N = rng.shape[0]
     lo, hi, plo, phi = (rng[:, i].astype(np.int64) for i in range(4))
     has1, has2 = hi > lo, phi > plo
@@ -61,6 +62,7 @@ def build_items(rng: np.ndarray, q_problems=None, k_segments=None, nkv: int = 1,
             idx = np.flatnonzero(att)
             if len(idx):
                 tiles.append((k0, k1 - k0, int(idx[0]), int(idx[-1]) + 1))
+    tiles = [(k0, nk, q0 & ~3, q1) for k0, nk, q0, q1 in tiles]     # q0 % 4 == 0: 16-byte aligned 64-query vector copies
     total_qt = sum((q1 - q0 + 63) // 64 for _, _, q0, q1 in tiles)
     max_qt = max(2, -(-total_qt * max(1, nkv) // max(1, n_sms)))       # 64-query tiles per unit
     k_items = []
@@ -68,22 +70,75 @@ def build_items(rng: np.ndarray, q_problems=None, k_segments=None, nkv: int = 1,
         step = max_qt * 64
         for a in range(q0, q1, step):
             b = min(a + step, q1)
-            k_items.append(((b - a + 63) // 64, k0, nk, a, b))
+            nqt = (b - a + 63) // 64
+            # 64-query tiles whose every (query, key) pair is allowed: the kernel skips the mask arithmetic there
+            f0 = f1 = 0
+            if nk == 128:
+                qq = np.arange(a, a + nqt * 64)
+                inb = qq < b
+                qc = np.minimum(qq, N - 1)
+                ok = inb & (((lo[qc] <= k0) & (hi[qc] >= k0 + nk) & has1[qc]) | ((plo[qc] <= k0) & (phi[qc] >= k0 + nk) & has2[qc]))
+                full = ok.reshape(nqt, 64).all(1)
+                best, cur = (0, 0), None
+                for t in range(nqt + 1):          # longest run of full tiles
+                    if t < nqt and full[t]:
+                        cur = t if cur is None else cur
+                    elif cur is not None:
+                        if t - cur > best[1] - best[0]:
+                            best = (cur, t)
+                        cur = None
+                f0, f1 = best
+            k_items.append((nqt, k0, nk, a, b, f0, f1))
     k_items.sort(key=lambda x: -x[0])
     qi = np.array([x[1:] for x in q_items], dtype=np.int32).reshape(-1, 6)
-    ki = np.array([x[1:] for x in k_items], dtype=np.int32).reshape(-1, 4)
+    ki = np.array([x[1:] for x in k_items], dtype=np.int32).reshape(-1, 6)
     return qi, ki
 
 
+def lpt_schedule(costs: np.ndarray, n_cta: int = NUM_SMS) -> np.ndarray:
+    """Longest-processing-time assignment of units (cost[u] known on the host) to persistent CTAs.
+    Returns int32 [n + 1 + n_units]: n = number of CTAs used, offsets [n + 1], then the unit ids CTA by CTA."""
+    import heapq
+    n_units = len(costs)
+    n = max(1, min(n_cta, n_units))
+    order = np.argsort(-np.asarray(costs, dtype=np.int64), kind="stable")
+    heap = [(0, c) for c in range(n)]
+    lists = [[] for _ in range(n)]
+    for u in order:
+        load, c = heapq.heappop(heap)
+        lists[c].append(int(u))
+        heapq.heappush(heap, (load + int(costs[u]), c))
+    offs = np.zeros(n + 1, dtype=np.int32)
+    offs[1:] = np.cumsum([len(x) for x in lists])
+    return np.concatenate([offs, np.array([u for x in lists for u in x], dtype=np.int32)]).astype(np.int32)
+
+
 class FmhaPlan:
-    def __init__(self, rng: np.ndarray, device, q_problems=None, k_segments=None, nkv: int = 1):
+    """Device-resident tables of one token layout for a given head configuration (nq query heads, nkv kv heads)."""
+
+    def __init__(self, rng: np.ndarray, device, q_problems=None, k_segments=None, nkv: int = 1, nq: int | None = None):
         rng = np.ascontiguousarray(rng, dtype=np.int32)
-        self.n_tokens = rng.shape[0]
+        self.n_tokens = N = rng.shape[0]
+        nq = nkv if nq is None else nq
+        self.nq, self.nkv = nq, nkv
         qi, ki = build_items(rng, q_problems, k_segments, nkv)
-        self.rng = torch.from_numpy(rng).to(device)
+        self.npad = (N + 3) // 4 * 4 + 64      # row stride of the head-major lse2 / delta; the range table is padded alike
+        self.rng = torch.from_numpy(np.concatenate([rng, np.zeros((self.npad - N, 4), dtype=np.int32)])).to(device)
         self.q_items = torch.from_numpy(qi).to(device)
         self.k_items = torch.from_numpy(ki).to(device)
         self.n_q, self.n_k = qi.shape[0], ki.shape[0]
+        # CTA schedules: unit = item * heads + head; cost = inner iterations + a fixed per-unit overhead
+        span = lambda a, b, t: np.where(b > a, (b - a + t - 1) // t, 0)
+        c_fwd = span(qi[:, 2], qi[:, 3], 128) + span(qi[:, 4], qi[:, 5], 128) + 1
+        c_dq = span(qi[:, 2], qi[:, 3], 64) + span(qi[:, 4], qi[:, 5], 64) + 2
+        nqt = (ki[:, 3] - ki[:, 2] + 63) // 64
+        c_kv = (2 * nqt - (ki[:, 5] - ki[:, 4])) * (nq // nkv) + 6      # masked tiles cost about twice a full one
+        s_fwd, s_dq, s_kv = lpt_schedule(np.repeat(c_fwd, nq)), lpt_schedule(np.repeat(c_dq, nq)), lpt_schedule(np.repeat(c_kv, nkv))
+        self.n_cta_fwd, self.n_cta_dq, self.n_cta_kv = (int(min(NUM_SMS, len(qi) * nq)), int(min(NUM_SMS, len(qi) * nq)),
+                                                        int(min(NUM_SMS, len(ki) * nkv)))
+        self.sched_fwd = torch.from_numpy(s_fwd).to(device)
+        self.sched_dq = torch.from_numpy(s_dq).to(device)
+        self.sched_kv = torch.from_numpy(s_kv).to(device)
         # algorithmic FLOPs of one forward per (head, head_dim): 4 * (#unmasked score entries) * hd
         r = rng.astype(np.int64)
         self.pairs = int(np.maximum(r[:, 1] - r[:, 0], 0).sum() + np.maximum(r[:, 3] - r[:, 2], 0).sum())
@@ -124,7 +179,7 @@ _PV_N = int(os.environ.get("IADR1_FMHA_PVN", "0"))
 
 
 def fmha_fwd(qkv: torch.Tensor, plan: FmhaPlan, nq: int, nkv: int, hd: int, scale: float, out: torch.Tensor | None = None):
-    """qkv bf16 [N, (nq + 2 nkv) * hd] (contiguous) -> (out bf16 [N, nq * hd], lse2 fp32 [N, nq])."""
+    """qkv bf16 [N, (nq + 2 nkv) * hd] (contiguous) -> (out bf16 [N, nq * hd], lse2 fp32 [nq, npad] head-major)."""
     N = plan.n_tokens
     if qkv.shape != (N, (nq + 2 * nkv) * hd) or qkv.dtype != bf16 or not qkv.is_contiguous():
         raise ValueError(f"fmha_fwd: qkv must be contiguous bf16 [{N}, {(nq + 2 * nkv) * hd}], got {tuple(qkv.shape)} {qkv.dtype}")
@@ -132,9 +187,12 @@ def fmha_fwd(qkv: torch.Tensor, plan: FmhaPlan, nq: int, nkv: int, hd: int, scal
         out = torch.empty(N, nq * hd, dtype=bf16, device=qkv.device)
     elif out.shape != (N, nq * hd) or not out.is_contiguous():
         raise ValueError("fmha_fwd: out must be contiguous [N, nq * hd]")
-    lse2 = torch.empty(N, nq, dtype=f32, device=qkv.device)
+    lse2 = torch.zeros(nq, plan.npad, dtype=f32, device=qkv.device)
+    if (plan.nq, plan.nkv) != (nq, nkv):
+        raise ValueError(f"fmha: plan built for {plan.nq}/{plan.nkv} heads, called with {nq}/{nkv}")
     L.check(L.lib().iadr1_fmha_fwd(qkv.data_ptr(), N, nq, nkv, hd, plan.rng.data_ptr(), plan.q_items.data_ptr(), plan.n_q,
-                                   out.data_ptr(), lse2.data_ptr(), scale, _PV_N, L.stream_ptr()), "fmha_fwd")
+                                   plan.sched_fwd.data_ptr(), plan.n_cta_fwd, out.data_ptr(), lse2.data_ptr(), plan.npad, scale, _PV_N,
+                                   L.stream_ptr()), "fmha_fwd")
     return out, lse2
 
 
@@ -148,12 +206,13 @@ def fmha_bwd(dout: torch.Tensor, qkv: torch.Tensor, out: torch.Tensor, lse2: tor
         dqkv = torch.empty(N, D, dtype=bf16, device=qkv.device)
     elif dqkv.shape != (N, D) or not dqkv.is_contiguous():
         raise ValueError("fmha_bwd: dqkv must be contiguous [N, D]")
-    delta = torch.empty(N, nq, dtype=f32, device=qkv.device)
+    delta = torch.zeros(nq, plan.npad, dtype=f32, device=qkv.device)
     dkv32 = torch.empty(N, 2 * nkv * hd, dtype=f32, device=qkv.device)
     L.check(L.lib().iadr1_fmha_bwd(qkv.data_ptr(), dout.data_ptr(), out.data_ptr(), lse2.data_ptr(), N, nq, nkv, hd,
-                                   plan.rng.data_ptr(), plan.q_items.data_ptr(), plan.n_q, plan.k_items.data_ptr(), plan.n_k,
-                                   dqkv.data_ptr(), delta.data_ptr(), dkv32.data_ptr(), scale, _PV_N, L.stream_ptr()),
-            "fmha_bwd")
+                                   plan.rng.data_ptr(), plan.q_items.data_ptr(), plan.n_q, plan.sched_dq.data_ptr(),
+                                   plan.n_cta_dq, plan.k_items.data_ptr(), plan.n_k, plan.sched_kv.data_ptr(), plan.n_cta_kv,
+                                   dqkv.data_ptr(), delta.data_ptr(), dkv32.data_ptr(), plan.npad, scale, _PV_N,
+                                   L.stream_ptr()), "fmha_bwd")
     return dqkv
 
 

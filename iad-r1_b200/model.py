@@ -79,7 +79,12 @@ class VLM:
             full = (not q25) or (i in v.fullatt_block_indexes)
             seg = geo.full_seg if full else geo.win_seg
             per_image = False
-            if seg:      # equal-length segments: a batch of [seg x seg] attention problems (no masked-out work)
+            fused = None
+            if ops.F.supported(hd):
+                # fused tcgen05 attention over per-patch key ranges (windows or whole images; any number of images)
+                lo, hi = (geo.full_lo, geo.full_hi) if full else (geo.win_lo, geo.win_hi)
+                fused = sh = ops.range_attention(geo, "full" if full else "win", lo, hi, nh, nh, hd)
+            elif seg:    # equal-length segments: a batch of [seg x seg] attention problems (no masked-out work)
                 sh = ops.AttnShape(Np // seg, seg, nh, nh, hd, causal=False)
                 lo, hi = geo.seg_ranges[seg]
             elif len(geo.image_ranges) > 1:   # ragged segments, several images: masked attention image by image
@@ -94,7 +99,9 @@ class VLM:
                 st1 = (m1, r1)
             qkv = ops.linear_fwd(xn, p[b + "qkv.weight"], bias=p[b + "qkv.bias"])
             ops.rope_(qkv, geo.cos, geo.sin, 2 * nh, hd, bf16_ops=0)
-            if per_image:
+            if fused is not None:
+                attn, P = fused.forward(qkv)
+            elif per_image:
                 attn = torch.empty(Np, nh * hd, dtype=bf16, device=self.device)
                 P, sh = [], ("full" if full else "win")
                 for j, (a_, b_) in enumerate(geo.image_ranges):
@@ -172,7 +179,9 @@ class VLM:
                 ops.layernorm_bwd(dxn2, x_mid, p[b + "norm2.weight"], st2[0], st2[1], dx, g[b + "norm2.weight"],
                                   g[b + "norm2.bias"], add_dx=True)
             dattn = ops.linear_bwd(dx, attn, p[b + "proj.weight"], g[b + "proj.weight"], g[b + "proj.bias"])
-            if isinstance(P, list):     # per-image masked attention (ragged segments, several images)
+            if isinstance(sh, ops.F.FusedAttention):
+                dqkv = sh.backward(dattn, qkv, P)
+            elif isinstance(P, list):     # per-image masked attention (ragged segments, several images)
                 dqkv = torch.empty_like(qkv)
                 for j, (a_, b_) in enumerate(geo.image_ranges):
                     lo_j, hi_j = geo.relative_ranges(sh, j)
@@ -215,13 +224,14 @@ class VLM:
         sh = ops.AttnShape(nc, tpc, nh, nh, hd, causal=False)     # attention within one crop
         lo = torch.zeros(tpc, dtype=torch.int32, device=self.device)
         hi = torch.full((tpc,), tpc, dtype=torch.int32, device=self.device)
+        fused = ops.range_attention(geo, "crops", geo.full_lo, geo.full_hi, nh, nh, hd) if ops.F.supported(hd) else None
         ctx = VisionCtx()
-        ctx.geo, ctx.px, ctx.blocks, ctx.sh, ctx.lo, ctx.hi = geo, px, [], sh, lo, hi
+        ctx.geo, ctx.px, ctx.blocks, ctx.sh, ctx.lo, ctx.hi, ctx.fused = geo, px, [], sh, lo, hi, fused
         for i in range(v.depth):
             b = f"visual.blocks.{i}."
             xn, m1, r1 = ops.layernorm_fwd(x, p[b + "norm1.weight"], p[b + "norm1.bias"], eps)
             qkv = ops.linear_fwd(xn, p[b + "qkv.weight"], bias=p[b + "qkv.bias"])
-            attn, P = ops.attention_fwd(qkv, sh, lo, hi)
+            attn, P = fused.forward(qkv) if fused is not None else ops.attention_fwd(qkv, sh, lo, hi)
             x_mid = ops.linear_fwd(attn, p[b + "proj.weight"], bias=p[b + "proj.bias"], residual=x)
             xn2, m2, r2 = ops.layernorm_fwd(x_mid, p[b + "norm2.weight"], p[b + "norm2.bias"], eps)
             h1 = ops.linear_fwd(xn2, p[b + "fc1.weight"], bias=p[b + "fc1.bias"])
@@ -261,7 +271,8 @@ class VLM:
             ops.layernorm_bwd(dxn2, x_mid, p[b + "norm2.weight"], st2[0], st2[1], dx, g[b + "norm2.weight"],
                               g[b + "norm2.bias"], add_dx=True)
             dattn = ops.linear_bwd(dx, attn, p[b + "proj.weight"], g[b + "proj.weight"], g[b + "proj.bias"])
-            dqkv = ops.attention_bwd(dattn, qkv, P, ctx.sh, ctx.lo, ctx.hi)
+            dqkv = ctx.fused.backward(dattn, qkv, P) if ctx.fused is not None else \
+                ops.attention_bwd(dattn, qkv, P, ctx.sh, ctx.lo, ctx.hi)
             dxn = ops.linear_bwd(dqkv, xn, p[b + "qkv.weight"], g[b + "qkv.weight"], g[b + "qkv.bias"])
             ops.layernorm_bwd(dxn, x, p[b + "norm1.weight"], st1[0], st1[1], dx, g[b + "norm1.weight"],
                               g[b + "norm1.bias"], add_dx=True)

@@ -8,8 +8,10 @@ from __future__ import annotations
 
 import ctypes as C
 
+import numpy as np
 import torch
 
+from . import fmha as F
 from . import lib as L
 
 bf16 = torch.bfloat16
@@ -232,19 +234,61 @@ def attention_bwd(dattn, qkv, P, sh: AttnShape, lo, hi, dqkv=None):
     return dqkv
 
 
+# ---- fused attention plans (csrc/fmha_sm100.cu): built once per token layout, cached ----------------------------------
+_PLAN_CACHE: dict = {}
+
+
+def _cached_plan(key, build):
+    p = _PLAN_CACHE.get(key)
+    if p is None:
+        if len(_PLAN_CACHE) > 256:
+            _PLAN_CACHE.clear()
+        p = _PLAN_CACHE[key] = build()
+    return p
+
+
+def range_attention(owner, tag, lo, hi, nq, nkv, hd):
+    """Fused attention over per-row key ranges [lo[t], hi[t]) (vision windows / whole images / SigLIP crops; absolute token
+    indices, any number of images in one stream). The plan is cached on `owner` (the geometry object the ranges belong to)."""
+    cache = owner.__dict__.setdefault("_fused_attn", {})
+    key = (tag, nq, nkv, hd)
+    fa = cache.get(key)
+    if fa is None:
+        rng = F.range_rows(lo.cpu().numpy().astype(np.int64), hi.cpu().numpy().astype(np.int64))
+        fa = cache[key] = F.FusedAttention(F.FmhaPlan(rng, lo.device, nkv=nkv, nq=nq), nq, nkv, hd)
+    return fa
+
+
 class FullAttention:
-    """B sequences of T tokens, causal (or ranged) attention inside each sequence."""
+    """B sequences of T tokens, causal attention inside each sequence. Fused tcgen05 kernels when the head size allows
+    (fmha.supported), else the composed QK^T -> softmax -> PV products."""
 
     def __init__(self, B, T, nq, nkv, hd, lo, hi, causal=True):
         self.sh = AttnShape(B, T, nq, nkv, hd, causal)
         self.lo, self.hi = lo, hi
         self.n_tokens = B * T
+        self.fused = None
+        if causal and F.supported(hd):
+            dev = lo.device
+            seqs = [(b * T, (b + 1) * T) for b in range(B)]
+            plan = _cached_plan(("causal", B, T, nq, nkv, str(dev)),
+                                lambda: F.FmhaPlan(F.causal_rows(B, T), dev, seqs, seqs, nkv=nkv, nq=nq))
+            self.fused = F.FusedAttention(plan, nq, nkv, hd)
 
     def forward(self, qkv):
+        if self.fused is not None:
+            return self.fused.forward(qkv)
         return attention_fwd(qkv, self.sh, self.lo, self.hi)
 
     def backward(self, dattn, qkv, saved):
+        if self.fused is not None:
+            return self.fused.backward(dattn, qkv, saved)
         return attention_bwd(dattn, qkv, saved, self.sh, self.lo, self.hi)
+
+
+def _plan_args(geom, device):
+    rng, probs, segs = geom
+    return rng, device, probs, segs
 
 
 class SharedPrefixAttention:
@@ -270,8 +314,15 @@ class SharedPrefixAttention:
         self.p_hi = torch.arange(1, P + 1, dtype=torch.int32, device=device)
         self.c_lo = torch.zeros(G * C, dtype=torch.int32, device=device)
         self.c_hi = (self.Pp + (torch.arange(G * C, device=device) % C) + 1).to(torch.int32)
+        self.fused = None
+        if F.supported(hd):
+            plan = _cached_plan(("shared", P, G, C, nq, nkv, str(device)),
+                                lambda: F.FmhaPlan(*_plan_args(F.shared_prefix_geometry(P, G, C), device), nkv=nkv, nq=nq))
+            self.fused = F.FusedAttention(plan, nq, nkv, hd)
 
     def forward(self, qkv, out=None):
+        if self.fused is not None:
+            return self.fused.forward(qkv, out=out)
         P, G, C, nq, nkv, hd, g, D, Pp, Tk = self.P, self.G, self.C, self.nq, self.nkv, self.hd, self.g, self.D, self.Pp, self.Tk
         GC = G * C
         attn = torch.empty(self.n_tokens, nq * hd, dtype=bf16, device=qkv.device) if out is None else out
@@ -293,6 +344,8 @@ class SharedPrefixAttention:
         return attn, (Pm, S)
 
     def backward(self, dattn, qkv, saved, out=None):
+        if self.fused is not None:
+            return self.fused.backward(dattn, qkv, saved, out=out)
         P, G, C, nq, nkv, hd, g, D, Pp, Tk = self.P, self.G, self.C, self.nq, self.nkv, self.hd, self.g, self.D, self.Pp, self.Tk
         GC, QH = G * C, nq * hd
         Pm, S = saved
@@ -346,8 +399,27 @@ class MultiGroupAttention:
         for g_ in groups:
             self.offsets.append(self.offsets[-1] + g_.n_tokens)
         self.n_tokens = self.offsets[-1]
+        # fused kernels: ONE plan over all packed groups (one launch per pass instead of one per group)
+        self.fused = None
+        if all(getattr(g_, "fused", None) is not None and isinstance(g_, SharedPrefixAttention) for g_ in groups):
+            t0 = groups[0]
+            dev = t0.p_lo.device
+
+            def build():
+                rngs, probs, segs = [], [], []
+                for g_, base in zip(groups, self.offsets):
+                    r, p_, s_ = F.shared_prefix_geometry(g_.P, g_.G, g_.C, base)
+                    rngs.append(r)
+                    probs += p_
+                    segs += s_
+                return F.FmhaPlan(np.concatenate(rngs), dev, probs, segs, nkv=t0.nkv, nq=t0.nq)
+
+            plan = _cached_plan(("multi", tuple((g_.P, g_.G, g_.C) for g_ in groups), t0.nq, t0.nkv, str(dev)), build)
+            self.fused = F.FusedAttention(plan, t0.nq, t0.nkv, t0.hd)
 
     def forward(self, qkv):
+        if self.fused is not None:
+            return self.fused.forward(qkv)
         t0 = self.groups[0]
         out = torch.empty(self.n_tokens, t0.nq * t0.hd, dtype=bf16, device=qkv.device)
         saved = []
@@ -357,6 +429,8 @@ class MultiGroupAttention:
         return out, saved
 
     def backward(self, dattn, qkv, saved):
+        if self.fused is not None:
+            return self.fused.backward(dattn, qkv, saved)
         dqkv = torch.empty(self.n_tokens, self.groups[0].D, dtype=bf16, device=qkv.device)
         for g_, s_, a, b in zip(self.groups, saved, self.offsets[:-1], self.offsets[1:]):
             g_.backward(dattn[a:b], qkv[a:b], s_, out=dqkv[a:b])

@@ -161,21 +161,31 @@ int iadr1_decode_advance(int* state, void* stream);
  * with `--attn_implementation flash_attention_2` (ref: scripts/train/SC_GRPO/SC_GRPO_Qwen_Instruct_2_5_VL_3B.sh:58; HF
  * modeling_qwen2_5_vl.py:214-286 vision attention, :704-760 decoder attention).
  *   qkv     bf16 [n_tokens][(nq + 2 nkv) * hd]: q heads, then k heads, then v heads of every token (post-rotary)
- *   ranges  int32 [n_tokens][4]: query row t attends keys [lo, hi) u [plo, phi) (token indices into the same buffer; the two
+ *   ranges  int32 [>= n_tokens + 64][4] (tail rows zero): query row t attends keys [lo, hi) u [plo, phi) (token indices into the same buffer; the two
  *           ranges must be disjoint): causal rows, the shared-prefix GRPO layout, vision windows / crops, packed groups
  *   items   forward / dQ work items, int32 [n][6] = {q0, nrows <= 128, kv0, kv1, p0, p1}: rows [q0, q0 + nrows) walk the
  *           key tiles of [p0, p1) (masked by plo / phi) and of [kv0, kv1) (masked by lo / hi); built by the host
- *   out     bf16 [n_tokens][nq * hd];  lse2 fp32 [n_tokens][nq]: log2-domain log-sum-exp of the scaled scores
+ *   sched   int32 [n_cta + 1 + n_units]: offsets of every CTA into the unit list that follows; unit = item * nq + head
+ *           (the host balances the CTAs: the cost of every unit is known from its item)
+ *   out     bf16 [n_tokens][nq * hd];  lse2 fp32 [nq][npad] (head-major): log2-domain log-sum-exp of the scaled scores;
+ *           npad = a multiple of 4 >= n_tokens + 64 (the backward bulk-copies 64 consecutive rows of a head)
  *   pv_n    0 = library choice; N of the P.V-type products (multiple of 16 in [hd, 128])                                   */
 int iadr1_fmha_fwd(const void* qkv, long long n_tokens, int nq, int nkv, int hd, const int* ranges, const int* items,
-                   int n_items, void* out, float* lse2, float scale, int pv_n, void* stream);
+                   int n_items, const int* sched, int n_cta, void* out, float* lse2, long long npad, float scale, int pv_n,
+                   void* stream);
+/* Timeline probe (tools/fmha_probe.py --trace): device buffer of 3 * 64 * 8 int64 that CTA 0 of the dK/dV kernel fills with
+ * clock64() stamps per role and iteration; NULL switches it off.                                                        */
+int iadr1_fmha_set_trace(long long* device_buf);
 /* Backward: dqkv bf16 [n_tokens][(nq + 2 nkv) * hd] receives dQ | dK | dV (GQA heads and shared-prefix rows reduced inside).
- *   k_items int32 [n][4] = {k0, nkeys <= 128, q0, q1}: key tile [k0, k0 + nkeys) and the query rows [q0, q1) that may attend
- *           to it (a key tile may appear in several items with disjoint query ranges; their results are added)
- *   delta   fp32 [n_tokens][nq] scratch;  dkv32 fp32 [n_tokens][2 * nkv * hd] scratch (zeroed and filled here)                */
+ *   k_items int32 [n][6] = {k0, nkeys <= 128, q0, q1, f0, f1}: key tile [k0, k0 + nkeys) and the query rows [q0, q1) that may
+ *           attend to it (q0 % 4 == 0; a key tile may appear in several items with disjoint query ranges; their results are
+ *           added); 64-query tiles f0 <= t < f1 of the range are allowed in full (no mask arithmetic)
+ *   q_sched / k_sched: CTA schedules of the dQ kernel (unit = item * nq + head) and the dK/dV kernel (unit = item * nkv + kv head)
+ *   delta   fp32 [nq][npad] scratch;  dkv32 fp32 [n_tokens][2 * nkv * hd] scratch (zeroed and filled here)                    */
 int iadr1_fmha_bwd(const void* qkv, const void* dout, const void* out, const float* lse2, long long n_tokens, int nq, int nkv,
-                   int hd, const int* ranges, const int* q_items, int n_q_items, const int* k_items, int n_k_items, void* dqkv,
-                   float* delta, float* dkv32, float scale, int pv_n, void* stream);
+                   int hd, const int* ranges, const int* q_items, int n_q_items, const int* q_sched, int n_q_cta,
+                   const int* k_items, int n_k_items, const int* k_sched, int n_k_cta, void* dqkv, float* delta, float* dkv32,
+                   long long npad, float scale, int pv_n, void* stream);
 
 #ifdef __cplusplus
 }

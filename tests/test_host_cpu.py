@@ -480,9 +480,12 @@ def test_fmha_plan_host_logic():
             rows_cov[q0:q0 + nr] += 1
         assert (rows_cov == 1).all(), name
         kcover = np.zeros((N, N), dtype=np.int32)
-        for k0, nk, q0, q1 in ki:
-            assert 0 < nk <= 128 and q1 > q0
+        for k0, nk, q0, q1, f0, f1 in ki:
+            assert 0 < nk <= 128 and q1 > q0 and q0 % 4 == 0
             kcover[q0:q1, k0:k0 + nk] += 1
+            for t in range(f0, f1):     # tiles flagged "allowed in full" really are
+                assert mask[q0 + 64 * t:q0 + 64 * t + 64, k0:k0 + nk].all() and q0 + 64 * t + 64 <= q1 and nk == 128, name
         assert (kcover[mask] == 1).all() and kcover.max() == 1, name
+        assert sum(f1 - f0 for *_, f0, f1 in ki) > 0 or name in ("windows",), name
     with __import__("pytest").raises(ValueError):
         fmha.build_items(np.array([[0, 0, 0, 0]], dtype=np.int32))

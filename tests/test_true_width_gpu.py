@@ -10,8 +10,8 @@ head_dim 128 / 80 / 72 / 64, the V = 151936 fused lm_head, and the tensor-core d
 `<64>` of the rollout - the rollout's DECODE logits are compared with HF logits of the same prompt + sampled tokens.
 
 Tolerances: log-probs vs the fp32 oracle no worse than 1.25 x the error of the reference's OWN bf16 path (HF in bf16 with
-bf16 log_softmax, run on the same inputs in the same test) and <= 0.05 abs; gradients <= 3 % relative Frobenius error per
-tensor, cosine >= 0.999 (as tests/test_model_gpu.py); decode logits <= 0.03 abs (bf16 weights/activations, fp32 residual stream, logits of
+bf16 log_softmax, run on the same inputs in the same test) and <= 0.05 abs; gradients <= max(3 %, 1.25 x the error of the
+reference's own bf16 backward on that tensor) relative Frobenius error per tensor, cosine >= 0.999; decode logits <= 0.03 abs (bf16 weights/activations, fp32 residual stream, logits of
 magnitude ~1)."""
 import numpy as np
 import pytest
@@ -61,11 +61,15 @@ def _hf_tail_logits(case, ids_t, pos_t, attn_mask, keep):
                      logits_to_keep=keep)
 
 
-def _compare_grads(ps, ref_grads, tag):
+def _compare_grads(ps, ref_grads, tag, rel16):
+    """Per tensor: relative Frobenius error vs the fp32 oracle <= max(3 %, 1.25 x the error of the reference's own bf16
+    backward on that tensor) and cosine >= 0.999. (The attention k-bias gradient is a sum of softmax-gradient rows that
+    cancel to zero in exact arithmetic - the most rounding-sensitive tensor for ANY bf16 implementation.)"""
     ours = {ps.canonical_name(k): v for k, v in ps.hf_named_tensors("g")}
     worst = (0.0, None)
-    for name, gref in ref_grads.items():
-        name = ps.canonical_name(name)
+    for hf_name, gref in ref_grads.items():
+        name = ps.canonical_name(hf_name)
+        tol = max(0.03, 1.25 * rel16.get(hf_name, 0.0))
         if name.endswith("lm_head.weight"):
             continue
         g = ours[name].float().cpu().reshape(gref.shape)
@@ -75,7 +79,7 @@ def _compare_grads(ps, ref_grads, tag):
         rel = ((g - gref).norm() / (gref.norm() + 1e-12)).item()
         cosv = torch.nn.functional.cosine_similarity(g.flatten(), gref.flatten(), dim=0).item()
         worst = max(worst, (rel, name))
-        assert rel <= 0.03 and cosv >= 0.999, f"[{tag}] {name}: rel err {rel:.4f}, cos {cosv:.5f}"
+        assert rel <= tol and cosv >= 0.999, f"[{tag}] {name}: rel err {rel:.4f} (tol {tol:.4f}), cos {cosv:.5f}"
     print(f"[{tag}] worst gradient rel err {worst[0]:.4f} at {worst[1]} over {len(ref_grads)} tensors")
 
 
@@ -106,14 +110,23 @@ def test_true_width_logprobs_and_grads_match_hf(cuda, model):
     # (sc_grpo_trainer.py:505-514 under --bf16), run on the GPU as the reference does
     import copy
     hf16 = copy.deepcopy(hf).to(torch.bfloat16).to(cuda)
+    hf16.zero_grad(set_to_none=True)
     case16 = dict(case, hf=hf16, px=case["px"].to(cuda), crops=None if case["crops"] is None else case["crops"].to(cuda))
-    with torch.no_grad():
-        t16 = _hf_tail_logits(case16, case["ids"].to(cuda), case["pos"].to(cuda), case["attn_mask"].to(cuda), C + 1)
-        lp16 = torch.gather(t16[:, :-1].log_softmax(-1), 2, case["ids"][:, -C:].to(cuda).unsqueeze(-1)).squeeze(-1).float().cpu()
-    del hf16, case16, t16
+    t16 = _hf_tail_logits(case16, case["ids"].to(cuda), case["pos"].to(cuda), case["attn_mask"].to(cuda), C + 1)
+    lp16_dev = torch.gather(t16[:, :-1].log_softmax(-1), 2, case["ids"][:, -C:].to(cuda).unsqueeze(-1)).squeeze(-1)
+    lp16_dev.backward(dlogp.to(cuda).to(lp16_dev.dtype))     # the reference's own bf16 backward of the same loss gradient
+    lp16 = lp16_dev.detach().float().cpu()
+    rel16 = {}
+    for k, p_ in hf16.named_parameters():
+        if p_.grad is not None and k in ref_grads:
+            gr = ref_grads[k].float()
+            rel16[k] = ((p_.grad.float().cpu() - gr).norm() / (gr.norm() + 1e-12)).item()
+    del hf16, case16, t16, lp16_dev
     torch.cuda.empty_cache()
     err16 = (lp16 - logp_ref.detach()).abs()[mask]
-    print(f"\n[{model}] HF bf16 (reference-form) vs HF fp32: max {err16.max().item():.5f} mean {err16.mean().item():.5f}")
+    worst16 = max(rel16.items(), key=lambda kv: kv[1])
+    print(f"\n[{model}] HF bf16 (reference-form) vs HF fp32: logp max {err16.max().item():.5f} mean {err16.mean().item():.5f}; "
+          f"worst gradient rel err {worst16[1]:.4f} at {worst16[0]}")
 
     # ---- product, both token layouts
     failures = []
@@ -140,7 +153,7 @@ def test_true_width_logprobs_and_grads_match_hf(cuda, model):
             failures.append(f"{model}/{layout}: logp err max {err:.5f} mean {mean:.5f} (HF bf16: {err16.max().item():.5f} / {err16.mean().item():.5f})")
         vlm.logprobs_backward(dlogp.reshape(-1).to(cuda), ctx)
         torch.cuda.synchronize()
-        _compare_grads(ps, ref_grads, f"{model}/{layout}")
+        _compare_grads(ps, ref_grads, f"{model}/{layout}", rel16)
         del ps, vlm, ctx
     assert not failures, failures
 
