@@ -11,7 +11,7 @@ head_dim 128 / 80 / 72 / 64, the V = 151936 fused lm_head, and the tensor-core d
 
 Tolerances: log-probs vs the fp32 oracle no worse than 1.25 x the error of the reference's OWN bf16 path (HF in bf16 with
 bf16 log_softmax, run on the same inputs in the same test) and <= 0.05 abs; gradients <= max(3 %, 1.25 x the error of the
-reference's own bf16 backward on that tensor) relative Frobenius error per tensor, cosine >= 0.999; decode logits <= 0.03 abs (bf16 weights/activations, fp32 residual stream, logits of
+reference's own bf16 backward on that tensor) relative Frobenius error per tensor, cosine >= min(0.999, 1 - tol^2); decode logits <= 0.03 abs (bf16 weights/activations, fp32 residual stream, logits of
 magnitude ~1)."""
 import numpy as np
 import pytest
@@ -79,7 +79,8 @@ def _compare_grads(ps, ref_grads, tag, rel16):
         rel = ((g - gref).norm() / (gref.norm() + 1e-12)).item()
         cosv = torch.nn.functional.cosine_similarity(g.flatten(), gref.flatten(), dim=0).item()
         worst = max(worst, (rel, name))
-        assert rel <= tol and cosv >= 0.999, f"[{tag}] {name}: rel err {rel:.4f} (tol {tol:.4f}), cos {cosv:.5f}"
+        cos_min = min(0.999, 1.0 - tol * tol)      # a relative error r of random direction costs about r^2 / 2 of cosine
+        assert rel <= tol and cosv >= cos_min, f"[{tag}] {name}: rel err {rel:.4f} (tol {tol:.4f}), cos {cosv:.5f}"
     print(f"[{tag}] worst gradient rel err {worst[0]:.4f} at {worst[1]} over {len(ref_grads)} tensors")
 
 
