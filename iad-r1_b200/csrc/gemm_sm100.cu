@@ -330,7 +330,12 @@ __global__ void __launch_bounds__(kThreads, kMinCtas)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by pointer arithmetic on the __shared__ array (keeps the shared address space). Launches that need
+  // every byte (g.smem_tight: two co-resident CTAs with a 3-stage ring) request no slack and rely on the window base being
+  // 1 KiB aligned, which holds with no static shared memory - checked here instead of assumed.
+  const uint32_t smem_pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  if (g.smem_tight && smem_pad != 0) __trap();
+  uint8_t* smem = smem_raw + smem_pad;
 
   // Programmatic dependent launch: let the next kernel's CTAs become resident as early as resources allow. Every
   // dependent still executes griddepcontrol.wait (full completion + flush of this grid) before touching our output.
@@ -519,8 +524,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const int ml = q * 32 + lane;
         const int f0 = ti.m0 >> 1;
         __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(g.C);
-        for (int cb = 0; cb < g.block_n; cb += 64) {
-          const int ncols = min(64, g.block_n - cb);
+        const int chunk = g.swiglu_rows;         // decode rows staged at a time (64, or 32 when two CTAs share an SM)
+        for (int cb = 0; cb < g.block_n; cb += chunk) {
+          const int ncols = min(chunk, g.block_n - cb);
           for (int c0 = 0; c0 < ncols; c0 += 16) {
             uint32_t v[16];
             tmem_ld_32x32b_x16(taddr + cb + c0, v);
@@ -528,7 +534,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
             for (int j = 0; j < 16; ++j) sC[(c0 + j) * BM + ml] = have_acc ? g.alpha * __uint_as_float(v[j]) : 0.f;
           }
-          if (cb + 64 >= g.block_n) {           // accumulator fully read: hand the TMEM stage back to the MMA warp
+          if (cb + chunk >= g.block_n) {        // accumulator fully read: hand the TMEM stage back to the MMA warp
             tc_fence_before();
             mbar_arrive(&tempty_bar[as]);
           }
@@ -914,11 +920,21 @@ int launch_gemm(const iadr1_gemm_t& d, cudaStream_t stream) {
   bool co_resident = d.co_resident != 0;
   {
     // two CTAs per SM only when a >= 3-stage ring (plus the epilogue staging tile) fits in half the shared memory
-    const int epi_b = g.epi == EPI_SWIGLU ? (g.block_n < 64 ? g.block_n : 64) * BM * 4
-                                          : ((g.trans_c && g.atomic && g.c_f32) ? g.block_n * BM * 4 : 0);
+    g.swiglu_rows = g.block_n < 64 ? g.block_n : 64;
+    int epi_b = g.epi == EPI_SWIGLU ? g.swiglu_rows * BM * 4 : ((g.trans_c && g.atomic && g.c_f32) ? g.block_n * BM * 4 : 0);
     const int stage_b = BM * BK * 2 + ((g.block_n * BK * 2 + 1023) & ~1023);
     // needs a >= 3-stage ring per CTA (measured: 2 stages x 2 CTAs is slower than 6 stages x 1 CTA at block_n = 128)
-    if (g.block_n > 128 || (113 * 1024 - 1024 - 512 - epi_b) / stage_b < 3) co_resident = false;
+    if (g.block_n > 128 || (113 * 1024 - 1024 - 512 - epi_b) / stage_b < 3) {
+      // SwiGLU at 128 decode rows: 3 x 32 KiB of ring + a 32-row staging tile + barriers is 115200 bytes - it fits the
+      // 115712 bytes two resident CTAs can have only without the 1 KiB alignment slack (172 tiles on 148 SMs: one CTA per
+      // SM means two waves, two per SM stream all tiles concurrently)
+      if (co_resident && g.epi == EPI_SWIGLU && g.block_n <= 128 && 3 * stage_b + 32 * BM * 4 + 512 <= 113 * 1024) {
+        g.swiglu_rows = 32;
+        g.smem_tight = 1;
+      } else {
+        co_resident = false;
+      }
+    }
   }
   if (co_resident) {
     g.tmem_cols = 32;
@@ -927,14 +943,15 @@ int launch_gemm(const iadr1_gemm_t& d, cudaStream_t stream) {
   // transposed fp32 atomic accumulation goes through bulk reductions (needs a [block_n][128] fp32 staging tile)
   g.bulk_red = g.trans_c && g.atomic && g.c_f32 && g.epi == EPI_STORE && g.residual == nullptr && g.batch == 1 &&
                (g.M % 4 == 0) && (g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) && !d.no_bulk_red;
-  const int epi_bytes = g.epi == EPI_SWIGLU ? (g.block_n < 64 ? g.block_n : 64) * BM * 4 : (g.bulk_red ? g.block_n * BM * 4 : 0);
-  const int smem_budget = (co_resident ? 113 : 227) * 1024 - 1024 - 512 - epi_bytes;
+  const int epi_bytes = g.epi == EPI_SWIGLU ? g.swiglu_rows * BM * 4 : (g.bulk_red ? g.block_n * BM * 4 : 0);
+  const int smem_slack = g.smem_tight ? 0 : 1024;
+  const int smem_budget = (co_resident ? 113 : 227) * 1024 - smem_slack - 512 - epi_bytes;
   int stages = smem_budget / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (d.stages > 0 && d.stages < stages) stages = d.stages;
   if (stages < 2) return set_error("gemm: not enough shared memory for 2 stages");
   g.stages = stages;
-  const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + 512 + epi_bytes;
+  const size_t smem_bytes = (size_t)stages * stage_bytes + smem_slack + 512 + epi_bytes;
 
   // MN-major operands whose MN extent is a multiple of 64: one box of the chunked view per k-block
   g.a_chunked = g.a_mn && (d.M % 64 == 0) && !d.no_chunked_maps;

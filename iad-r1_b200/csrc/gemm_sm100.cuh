@@ -30,6 +30,8 @@ struct GemmArgs {
   int raster_n;   // 1: consecutive tiles walk N first (A streamed once), 0: M first (B streamed once)
   int bulk_red;   // transposed fp32 atomic output via cp.reduce.async.bulk from a staged tile (decode products)
   int stream_k;   // 1: k-block units split evenly over the CTAs (see WorkIter); atomic f32 output, split_k == 1
+  int swiglu_rows; // EPI_SWIGLU: decode rows staged per epilogue pass (64, or 32 for the two-CTAs-per-SM form at 128 rows)
+  int smem_tight;  // dynamic shared memory requested without alignment slack (kernel traps unless the base is 1 KiB aligned)
   int epi;
   int c_f32, trans_c, accumulate, atomic;
   int bias_per_m;
