@@ -34,9 +34,9 @@ def load_state_dict(path: str) -> dict:
     return sd
 
 
-def load_pretrained(path: str, device, with_grads=True, with_optimizer=True):
+def load_pretrained(path: str, device, with_grads=True, with_optimizer=True, moment_dtype=torch.float32):
     cfg = load_config(path)
-    ps = ParamStore(cfg, device, with_grads=with_grads, with_optimizer=with_optimizer)
+    ps = ParamStore(cfg, device, with_grads=with_grads, with_optimizer=with_optimizer, moment_dtype=moment_dtype)
     ps.load_hf_state_dict(load_state_dict(path))
     return cfg, ps
 

@@ -43,7 +43,7 @@ class GRPOConfig:
     bf16: bool = False
     fp16: bool = False
     tf32: Optional[bool] = None
-    gradient_checkpointing: bool = False      # ignored: all activations stay resident in HBM (no recompute)
+    gradient_checkpointing: bool = False      # honoured through `activation_recompute` (below): "auto" recomputes only when needed
     deepspeed: Optional[str] = None           # ignored: plain data parallel replaces ZeRO-3
     ddp_timeout: int = 1800
     report_to: Union[None, str, list[str]] = "none"
@@ -109,6 +109,10 @@ class GRPOConfig:
     shared_prefix: bool = True                 # score a group as [prompt | G completions]: the prompt is computed once
     window_vision: bool = True                 # vision tower fwd/bwd once per accumulation window (batched_rollout only)
     rollout_forbid_eos: bool = False           # benchmarking only: fixed-length completions
+    activation_recompute: str = "auto"         # per-layer recompute in the backward ("on" | "off" | "auto": only for models
+                                               # whose unsharded state leaves too little HBM, e.g. Qwen2.5-VL-7B; 3B keeps
+                                               # every activation resident even when --gradient_checkpointing is passed)
+    optimizer_moments: str = "auto"            # "fp32" | "bf16" (stochastic rounding) | "auto" (bf16 only when fp32 cannot fit)
     rollout_seed: Optional[int] = None
 
     def __post_init__(self):

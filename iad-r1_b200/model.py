@@ -1,6 +1,7 @@
 """The VLM forward / backward, written as explicit kernel sequences over the C ABI (ops.py) - no torch.nn modules,
-no autograd graph, no recompute: every activation the backward needs is kept in HBM (180 GB makes
-`--gradient_checkpointing` unnecessary; DESIGN.md "HBM layout").
+no autograd graph. By default every activation the backward needs is kept in HBM (180 GB makes
+`--gradient_checkpointing` unnecessary for the 0.5-3 B models); `VLM.recompute` switches the decoder to per-layer
+recompute (only layer inputs stay resident) for models whose state fills the device (Qwen2.5-VL-7B; DESIGN.md "HBM layout").
 
 This is the B200-native stand-in for `model(**inputs).logits` and autograd's backward over it
 (ref: train/stage_rl/trainer/sc_grpo_trainer.py:505; HF modeling_qwen2_5_vl.py:455-518 vision tower, :778-827 decoder
@@ -37,6 +38,7 @@ class VLM:
         self.params = params
         self.p = params.p
         self.device = params.device
+        self.recompute = False      # per-layer activation recompute in the decoder backward (set by the trainers)
         self._zero_row = torch.zeros(1, max(cfg.text.hidden_size, cfg.vision.hidden_size), dtype=bf16, device=self.device)
         self._causal_cache = {}
 
@@ -300,22 +302,34 @@ class VLM:
         ctx = DecoderCtx()
         ctx.layers, ctx.attn, ctx.cos, ctx.sin, ctx.src_index = [], attn, cos, sin, src_index
         for i in range(t.num_layers):
-            b = f"layers.{i}."
-            xn, r1 = ops.rmsnorm_fwd(h, p[b + "ln1.weight"], t.rms_norm_eps, save_rstd=save)
-            qkv = ops.linear_fwd(xn, p[b + "qkv.weight"], bias=p[b + "qkv.bias"])
-            ops.rope_(qkv, cos, sin, nq + nkv, hd, bf16_ops=1)
-            if kv_sink is not None:
-                kv_sink(i, qkv)
-            a_out, a_saved = attn.forward(qkv)
-            h_mid = ops.linear_fwd(a_out, p[b + "o.weight"], residual=h)
-            xn2, r2 = ops.rmsnorm_fwd(h_mid, p[b + "ln2.weight"], t.rms_norm_eps, save_rstd=save)
-            gu = ops.linear_fwd(xn2, p[b + "gate_up.weight"])
-            act = ops.act_mul_fwd(gu, I, ops.ACT_SILU, gated=True)
-            h_out = ops.linear_fwd(act, p[b + "down.weight"], residual=h_mid)
-            if save:
-                ctx.layers.append((h, r1, xn, qkv, a_saved, a_out, h_mid, r2, xn2, gu, act))
-            h = h_out
+            if save and self.recompute:
+                # activation recompute (what `--gradient_checkpointing` asks of the reference, SC_GRPO_*.sh:57): only the
+                # layer INPUT stays resident; the backward re-runs this layer's forward before differentiating it
+                ctx.layers.append((h,))
+                h, _ = self._layer_forward(i, h, attn, cos, sin, False, kv_sink)
+            else:
+                h, saved = self._layer_forward(i, h, attn, cos, sin, save, kv_sink)
+                if save:
+                    ctx.layers.append(saved)
         return h, (ctx if save else None)
+
+    def _layer_forward(self, i, h, attn, cos, sin, save, kv_sink=None):
+        """One decoder layer (HF Qwen2_5_VLDecoderLayer, modeling_qwen2_5_vl.py:778-827). Returns (h_out, saved tuple)."""
+        t, p = self.cfg.text, self.p
+        I, nq, nkv, hd = t.intermediate_size, t.num_heads, t.num_kv_heads, t.head_dim
+        b = f"layers.{i}."
+        xn, r1 = ops.rmsnorm_fwd(h, p[b + "ln1.weight"], t.rms_norm_eps, save_rstd=save)
+        qkv = ops.linear_fwd(xn, p[b + "qkv.weight"], bias=p[b + "qkv.bias"])
+        ops.rope_(qkv, cos, sin, nq + nkv, hd, bf16_ops=1)
+        if kv_sink is not None:
+            kv_sink(i, qkv)
+        a_out, a_saved = attn.forward(qkv)
+        h_mid = ops.linear_fwd(a_out, p[b + "o.weight"], residual=h)
+        xn2, r2 = ops.rmsnorm_fwd(h_mid, p[b + "ln2.weight"], t.rms_norm_eps, save_rstd=save)
+        gu = ops.linear_fwd(xn2, p[b + "gate_up.weight"])
+        act = ops.act_mul_fwd(gu, I, ops.ACT_SILU, gated=True)
+        h_out = ops.linear_fwd(act, p[b + "down.weight"], residual=h_mid)
+        return h_out, ((h, r1, xn, qkv, a_saved, a_out, h_mid, r2, xn2, gu, act) if save else None)
 
     def decoder_backward(self, dh: torch.Tensor, ctx: DecoderCtx, n_image_rows: int):
         """dh [B*T, H] bf16 (consumed in place). Returns d(image embeddings) fp32 [n_image_rows, H] or None."""
@@ -323,6 +337,8 @@ class VLM:
         I, nq, nkv, hd = t.intermediate_size, t.num_heads, t.num_kv_heads, t.head_dim
         for i in reversed(range(t.num_layers)):
             b = f"layers.{i}."
+            if len(ctx.layers[i]) == 1:       # recompute this layer's activations from its saved input
+                _, ctx.layers[i] = self._layer_forward(i, ctx.layers[i][0], ctx.attn, ctx.cos, ctx.sin, True)
             h, r1, xn, qkv, P, attn, h_mid, r2, xn2, gu, act = ctx.layers[i]
             dact = ops.linear_bwd(dh, act, p[b + "down.weight"], g[b + "down.weight"])
             dgu = ops.act_mul_bwd(dact, gu, I, ops.ACT_SILU, gated=True, dgu=gu)

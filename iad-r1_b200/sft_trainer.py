@@ -188,14 +188,18 @@ class PASFTTrainer(TrainerCore):
         self._setup_distributed()
         torch.manual_seed(args.seed)
         if isinstance(model, str):
-            self.cfg, self.params = load_pretrained(model, self.device)
+            from .checkpoint import load_config
+            mdt = ParamStore.plan_moment_dtype(load_config(model), self.device, False, "auto")
+            self.cfg, self.params = load_pretrained(model, self.device, moment_dtype=mdt)
         elif isinstance(model, VLMConfig):
             self.cfg = model
-            self.params = ParamStore(model, self.device, with_grads=True, with_optimizer=True)
+            self.params = ParamStore(model, self.device, with_grads=True, with_optimizer=True,
+                                     moment_dtype=ParamStore.plan_moment_dtype(model, self.device, False, "auto"))
             self.params.init_random(seed=args.seed)
         else:
             self.cfg, self.params = model.cfg, model
         self.model = VLM(self.cfg, self.params)
+        self.model.recompute = self.params.exp_avg.dtype == torch.bfloat16   # models whose state fills the device (7B)
         if processing_class is None:
             from transformers import AutoProcessor
             processing_class = AutoProcessor.from_pretrained(model)

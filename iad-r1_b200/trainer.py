@@ -122,11 +122,14 @@ class SCGRPOTrainer(TrainerCore):
                     " (and the id names none of the supported families: Qwen2-VL / Qwen2.5-VL / LLaVA-OneVision)"
                 raise ValueError(f"Unsupported model: {model}: no config.json under that path{hint}; there is no hub access "
                                  f"on the training box, pass a local checkpoint directory")
-            self.cfg, self.params = load_pretrained(model, self.device)
+            from .checkpoint import load_config
+            mdt = ParamStore.plan_moment_dtype(load_config(model), self.device, args.beta != 0.0, args.optimizer_moments)
+            self.cfg, self.params = load_pretrained(model, self.device, moment_dtype=mdt)
         elif isinstance(model, VLMConfig):
             self.model_id = model.family
             self.cfg = model
-            self.params = ParamStore(model, self.device, with_grads=True, with_optimizer=True)
+            mdt = ParamStore.plan_moment_dtype(model, self.device, args.beta != 0.0, args.optimizer_moments)
+            self.params = ParamStore(model, self.device, with_grads=True, with_optimizer=True, moment_dtype=mdt)
             self.params.init_random(seed=args.seed)
         elif isinstance(model, ParamStore):
             self.model_id, self.cfg, self.params = model.cfg.family, model.cfg, model
@@ -135,6 +138,10 @@ class SCGRPOTrainer(TrainerCore):
         if self.params.grad_flat is None or self.params.master is None:
             raise ValueError("the policy ParamStore needs with_grads=True, with_optimizer=True")
         self.model = VLM(self.cfg, self.params)
+        # per-layer activation recompute (what --gradient_checkpointing asks the reference for): "auto" switches it on only
+        # when the moments had to drop to bf16, i.e. the unsharded state already takes most of the device
+        rc = args.activation_recompute
+        self.model.recompute = rc == "on" or (rc == "auto" and self.params.exp_avg.dtype == torch.bfloat16)
         self.beta = args.beta
         # Q11: the reference always builds a frozen copy of the initial policy (sc_grpo_trainer.py:152-182). With
         # beta == 0 its only use (beta * KL) vanishes, so it is skipped and `kl` is logged as 0.
@@ -185,10 +192,11 @@ class SCGRPOTrainer(TrainerCore):
         self.phase_ms = defaultdict(float)
         self._timers = []
         self.total_rollout_tokens = 0
-        for flag, val in (("deepspeed", args.deepspeed), ("gradient_checkpointing", args.gradient_checkpointing)):
-            if val and self.is_main:
-                print(f"[iadr1-b200] note: --{flag} is accepted for script compatibility and ignored "
-                      f"(plain data parallel, all activations resident in HBM)")
+        if args.deepspeed and self.is_main:
+            print("[iadr1-b200] note: --deepspeed is accepted for script compatibility and ignored (plain data parallel)")
+        if self.is_main and (args.gradient_checkpointing or self.model.recompute):
+            print(f"[iadr1-b200] activation recompute: {'on' if self.model.recompute else 'off (every activation stays resident)'}"
+                  f"; Adam moments: {str(self.params.exp_avg.dtype).replace('torch.', '')}")
 
     # ---------------------------------------------------------------------------------------------------------------
     # prompt encoding + rollout

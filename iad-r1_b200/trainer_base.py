@@ -104,6 +104,13 @@ class TrainerCore:
             for lo, hi, wd in self._trainable_ranges():
                 if hi <= lo:
                     continue
+                if ps.exp_avg.dtype == torch.bfloat16:
+                    L.check(lib.iadr1_adamw_step_bf16m(
+                        ps.master[lo:].data_ptr(), ps.flat[lo:].data_ptr(), ps.grad_flat[lo:].data_ptr(),
+                        ps.exp_avg[lo:].data_ptr(), ps.exp_avg_sq[lo:].data_ptr(), hi - lo, lr, a.adam_beta1, a.adam_beta2,
+                        a.adam_epsilon, wd, self._opt_step, scale, self._sumsq.data_ptr(),
+                        a.max_grad_norm if a.max_grad_norm else 0.0, 1, (a.seed << 20) + lo, s), "adamw_step_bf16m")
+                    continue
                 L.check(lib.iadr1_adamw_step(ps.master[lo:].data_ptr(), ps.flat[lo:].data_ptr(), ps.grad_flat[lo:].data_ptr(),
                                              ps.exp_avg[lo:].data_ptr(), ps.exp_avg_sq[lo:].data_ptr(), hi - lo, lr,
                                              a.adam_beta1, a.adam_beta2, a.adam_epsilon, wd, self._opt_step, scale,

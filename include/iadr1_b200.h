@@ -130,6 +130,12 @@ int iadr1_sumsq_f32(const float* g, long long n, float* out, void* stream);
 int iadr1_adamw_step(float* p32, void* p16, float* g, float* m, float* v, long long n, float lr, float beta1,
                      float beta2, float eps, float weight_decay, int step, float grad_scale, const float* sumsq,
                      float max_norm, int zero_grad, void* stream);
+/* The same step with exp_avg / exp_avg_sq stored in bf16 under stochastic rounding (seeded counter hash): 8 bytes per
+ * parameter less optimizer state - the form that fits Qwen2.5-VL-7B on one 180 GB GPU without sharding (the reference shards
+ * with ZeRO-3, ref: scripts/train/zero3.json:14-33).                                                                   */
+int iadr1_adamw_step_bf16m(float* p32, void* p16, float* g, void* m16, void* v16, long long n, float lr, float beta1,
+                           float beta2, float eps, float weight_decay, int step, float grad_scale, const float* sumsq,
+                           float max_norm, int zero_grad, unsigned long long seed, void* stream);
 
 /* ---- rollout: replaces vLLM `LLM.generate` (sc_grpo_trainer.py:343-358, 667). State words: [0] step,
  * [2] unfinished rows; per-row prompt lengths in row_plen. All per-step inputs live on the device so one step is CUDA-graph replayable.        */

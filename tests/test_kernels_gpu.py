@@ -381,6 +381,44 @@ def test_adamw_matches_torch(ops):
 
 
 # ---------------------------------------------------------------------------------------------- sampler
+def test_adamw_bf16_moments_track_fp32(ops):
+    """AdamW with bf16 moments under stochastic rounding (the 7B memory plan) follows the fp32-moment kernel: after 200 steps
+    of the same gradient stream the parameters agree to a small fraction of the distance travelled, and the bf16 second
+    moment has not frozen (round-to-nearest would: beta2 = 0.999 moves it by a quarter of a bf16 ulp per step)."""
+    from iad_r1_b200 import lib as L
+    torch.manual_seed(9)
+    n = 1 << 16
+    p0 = torch.randn(n, device="cuda")
+    st = {}
+    for kind in ("fp32", "bf16"):
+        dt = torch.float32 if kind == "fp32" else bf16
+        st[kind] = dict(p32=p0.clone(), p16=p0.to(bf16), m=torch.zeros(n, device="cuda", dtype=dt), v=torch.zeros(n, device="cuda", dtype=dt))
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    base = torch.randn(n, device="cuda", generator=gen) * 0.5
+    for step in range(1, 201):
+        g = base + torch.randn(n, device="cuda", generator=gen)
+        for kind, s_ in st.items():
+            gg = g.clone()
+            if kind == "fp32":
+                L.check(L.lib().iadr1_adamw_step(s_["p32"].data_ptr(), s_["p16"].data_ptr(), gg.data_ptr(), s_["m"].data_ptr(),
+                                                 s_["v"].data_ptr(), n, 1e-3, 0.9, 0.999, 1e-8, 0.01, step, 1.0, None, 0.0, 1,
+                                                 L.stream_ptr()), "adamw")
+            else:
+                L.check(L.lib().iadr1_adamw_step_bf16m(s_["p32"].data_ptr(), s_["p16"].data_ptr(), gg.data_ptr(), s_["m"].data_ptr(),
+                                                       s_["v"].data_ptr(), n, 1e-3, 0.9, 0.999, 1e-8, 0.01, step, 1.0, None, 0.0, 1,
+                                                       7, L.stream_ptr()), "adamw_bf16m")
+            assert (gg == 0).all()
+    torch.cuda.synchronize()
+    moved = (st["fp32"]["p32"] - p0).abs().mean().item()
+    diff = (st["fp32"]["p32"] - st["bf16"]["p32"]).abs()
+    print(f"\nadamw bf16 moments: mean |dp| {moved:.4f}, mean |p_bf16m - p_fp32m| {diff.mean().item():.2e}, max {diff.max().item():.2e}")
+    assert diff.mean().item() < 0.01 * moved and diff.max().item() < 0.1 * moved
+    rel_v = (st["bf16"]["v"].float() - st["fp32"]["v"]) / st["fp32"]["v"]
+    # noise at the bf16 rounding level (a random walk damped by beta2), and UNBIASED: no systematic drift of exp_avg_sq
+    assert rel_v.abs().mean().item() < 0.03 and abs(rel_v.mean().item()) < 2e-3, (rel_v.abs().mean().item(), rel_v.mean().item())
+    assert (st["bf16"]["p16"].float() - st["bf16"]["p32"]).abs().max().item() <= 2 ** -7 * st["bf16"]["p32"].abs().max().item()
+
+
 def test_sampler_support_and_distribution(ops):
     from iad_r1_b200 import lib as L
     torch.manual_seed(8)

@@ -309,3 +309,30 @@ def test_two_stage_pa_sft_then_sc_grpo(cuda, tmp_path, family):
     out = tr.train()
     assert out["global_step"] == 1 and not torch.equal(tr.params.flat, stage1)
     assert torch.isfinite(tr.params.flat.float()).all()
+
+
+def test_activation_recompute_gives_the_same_gradient(cuda):
+    """Per-layer recompute (`activation_recompute="on"`, what --gradient_checkpointing asks of the reference and the 7B memory
+    plan switches on) re-runs the same deterministic kernels: log-probs and the accumulated gradient equal the
+    resident-activation path's."""
+    from iad_r1_b200.synthetic import synthetic_dataset
+    cfg, tr = _tiny_trainer(cuda)
+    data = synthetic_dataset(1, 112)
+    enc = tr._encode_prompt(data[0])
+    torch.manual_seed(0)
+    comp = torch.randint(10, 900, (4, 10), device=cuda, dtype=torch.int32)
+    batch = tr.model.prepare_groups([dict(prompt_ids=enc["input_ids"], completion_ids=comp, pixel_values=enc["pixel_values"],
+                                          grid_thw=enc["grid_thw"])])
+    res = []
+    for rc in (False, True):
+        tr.model.recompute = rc
+        tr.params.zero_grad()
+        lp, ctx = tr.model.logprobs_forward(batch, batch["sel_index"], batch["labels"])
+        if rc:
+            assert all(len(x) == 1 for x in ctx["dctx"].layers), "only the layer inputs may stay resident"
+        tr.model.logprobs_backward(torch.linspace(-1, 1, lp.numel(), device=cuda), ctx)
+        torch.cuda.synchronize()
+        res.append((lp.clone(), tr.params.grad_flat.clone()))
+    assert torch.equal(res[0][0], res[1][0])
+    rel = ((res[0][1] - res[1][1]).norm() / res[0][1].norm()).item()
+    assert rel < 1e-5, rel
