@@ -152,7 +152,7 @@ def run_reference(args):
     cfg = PRESETS[args.model]()
     t0 = time.time()
     gps, info, t_s = cpu_reference_sample(args, cfg, steps=max(1, args.steps), warmup=min(args.warmup, 1))
-    line = {"metric": "GRPO groups/sec (G=8)", "value": gps, "unit": "groups/s", "impl": "reference", "n_gpus": args.gpus,
+    line = {"metric": f"GRPO groups/sec (G={args.num_generations})", "value": gps, "unit": "groups/s", "impl": "reference", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * args.ga / gps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, cfg, 1), "cpu_baseline": info,
@@ -310,7 +310,7 @@ def run_ours(args):
                "achieved": step_bytes / (dec_ms / 1e3) / 1e9, "peak": hbm, "unit": "GB/s", "peak_source": f"hbm_gbs, {src}",
                "bytes_per_step": step_bytes, "ms_per_decode_step": dec_ms}
         dec["frac"] = dec["achieved"] / hbm
-        line = {"metric": "GRPO groups/sec (G=8)", "value": value, "unit": "groups/s", "n_gpus": world, "steps": args.steps,
+        line = {"metric": f"GRPO groups/sec (G={G})", "value": value, "unit": "groups/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, cfg, world),
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,

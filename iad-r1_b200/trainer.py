@@ -14,6 +14,7 @@ from __future__ import annotations
 import json
 import math
 import os
+import sys
 import time
 import warnings
 from collections import defaultdict
@@ -193,10 +194,11 @@ class SCGRPOTrainer(TrainerCore):
         self._timers = []
         self.total_rollout_tokens = 0
         if args.deepspeed and self.is_main:
-            print("[iadr1-b200] note: --deepspeed is accepted for script compatibility and ignored (plain data parallel)")
+            print("[iadr1-b200] note: --deepspeed is accepted for script compatibility and ignored (plain data parallel)",
+                  file=sys.stderr)
         if self.is_main and (args.gradient_checkpointing or self.model.recompute):
             print(f"[iadr1-b200] activation recompute: {'on' if self.model.recompute else 'off (every activation stays resident)'}"
-                  f"; Adam moments: {str(self.params.exp_avg.dtype).replace('torch.', '')}")
+                  f"; Adam moments: {str(self.params.exp_avg.dtype).replace('torch.', '')}", file=sys.stderr)
 
     # ---------------------------------------------------------------------------------------------------------------
     # prompt encoding + rollout
