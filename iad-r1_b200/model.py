@@ -39,6 +39,7 @@ class VLM:
         self.p = params.p
         self.device = params.device
         self.recompute = False      # per-layer activation recompute in the decoder backward (set by the trainers)
+        self.on_layer_grad_ready = None   # callback(layer) once a decoder layer's weight gradients are complete (all-reduce overlap)
         self._zero_row = torch.zeros(1, max(cfg.text.hidden_size, cfg.vision.hidden_size), dtype=bf16, device=self.device)
         self._causal_cache = {}
 
@@ -350,6 +351,8 @@ class VLM:
             dxn = ops.linear_bwd(dqkv, xn, p[b + "qkv.weight"], g[b + "qkv.weight"], g[b + "qkv.bias"])
             ops.rmsnorm_bwd(dxn, h, p[b + "ln1.weight"], r1, dh, g[b + "ln1.weight"], add_dx=True)
             ctx.layers[i] = None  # free this layer's activations as the sweep passes
+            if self.on_layer_grad_ready is not None:
+                self.on_layer_grad_ready(i)
         dimg = None
         if n_image_rows > 0:
             dimg = torch.zeros(n_image_rows, t.hidden_size, dtype=f32, device=self.device)

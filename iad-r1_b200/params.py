@@ -138,6 +138,16 @@ class ParamStore:
         if not t.tie_word_embeddings:
             self._add("lm_head.weight", (t.vocab_size, t.hidden_size), True)
 
+    def layer_matrix_range(self, i: int):
+        """[lo, hi) of decoder layer i's weight matrices in the flat buffers (contiguous: qkv, o, gate_up, down)."""
+        t = self.cfg.text
+        lo = self.offsets[f"layers.{i}.qkv.weight"]
+        if i + 1 < t.num_layers:
+            hi = self.offsets[f"layers.{i + 1}.qkv.weight"]
+        else:
+            hi = self.offsets["lm_head.weight"] if "lm_head.weight" in self.offsets else self.n_decay
+        return lo, hi
+
     def _views(self, flat):
         out = {}
         for n, shape in self.shapes.items():

@@ -427,8 +427,11 @@ class SCGRPOTrainer(TrainerCore):
 
     def training_step(self, inputs: list) -> torch.Tensor:
         loss = self.compute_loss(self.model, inputs)
+        GA = self.args.gradient_accumulation_steps
+        self.arm_overlap(self._micro_idx == GA - 1)      # last micro-step: layers' gradients go to NCCL as they retire
+        self._micro_idx += 1
         with self._phase("backward"):
-            (loss / self.args.gradient_accumulation_steps).backward()
+            (loss / GA).backward()
         return loss.detach()
 
     def train(self, resume_from_checkpoint=None):

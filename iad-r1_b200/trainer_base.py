@@ -27,6 +27,21 @@ class TrainerState:
         self.num_input_tokens_seen = 0
 
 
+def complement_ranges(done: list, n: int) -> list:
+    """Sub-ranges of [0, n) not covered by the (disjoint) ranges in `done`, in ascending order."""
+    out, cur = [], 0
+    for lo, hi in sorted(done):
+        if lo > cur:
+            out.append((cur, lo))
+        cur = max(cur, hi)
+    if cur < n:
+        out.append((cur, n))
+    return out
+
+
+GRAD_BUCKET_ELEMS = 64 << 20      # 256 MB of fp32 per NCCL call (SURVEY.md C2)
+
+
 class TrainerCore:
     # ---------------------------------------------------------------------------------------------------------------
     def _setup_distributed(self):
@@ -43,6 +58,48 @@ class TrainerCore:
             torch.distributed.init_process_group("nccl", timeout=datetime.timedelta(seconds=self.args.ddp_timeout),
                                                  device_id=self.device)
         L.lib()
+        self._comm, self._comm_stream, self._reduced, self._micro_idx = None, None, [], 0
+        if self.world > 1:
+            self._setup_grad_comm()
+
+    def _setup_grad_comm(self):
+        """Own NCCL communicator for the gradient (C ABI: iadr1_comm_create / iadr1_grad_allreduce): rank 0 draws the unique
+        id, torch.distributed carries its 128 bytes to the other ranks."""
+        import ctypes as C
+        lib = L.lib()
+        uid = torch.zeros(128, dtype=torch.uint8, device=self.device)
+        if self.rank == 0:
+            buf = (C.c_ubyte * 128)()
+            L.check(lib.iadr1_comm_unique_id(buf), "comm_unique_id")
+            uid.copy_(torch.tensor(list(buf), dtype=torch.uint8))
+        torch.distributed.broadcast(uid, src=0)
+        raw = (C.c_ubyte * 128)(*uid.cpu().tolist())
+        comm = C.c_void_p()
+        L.check(lib.iadr1_comm_create(raw, self.rank, self.world, C.byref(comm)), "comm_create")
+        self._comm, self._comm_stream = comm, torch.cuda.Stream(device=self.device)
+
+    # ---- overlapped gradient all-reduce -------------------------------------------------------------------------------
+    def _enqueue_grad_range(self, lo: int, hi: int):
+        """Sum grad[lo, hi) over the ranks on the communication stream, ordered after everything the compute stream has
+        enqueued so far (the range must be final: no later kernel of this optimizer step writes it)."""
+        if self._comm is None or hi <= lo:
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        self._comm_stream.wait_event(ev)
+        g = self.params.grad_flat
+        L.check(L.lib().iadr1_grad_allreduce(self._comm, g.data_ptr() + 4 * lo, hi - lo, GRAD_BUCKET_ELEMS,
+                                             self._comm_stream.cuda_stream), "grad_allreduce")
+        self._reduced.append((lo, hi))
+
+    def _layer_grad_ready(self, i: int):
+        lo, hi = self.params.layer_matrix_range(i)
+        self._enqueue_grad_range(lo, hi)
+
+    def arm_overlap(self, last_micro_step: bool):
+        """During the LAST micro-step of an accumulation window every decoder layer's gradient is final as soon as the
+        backward sweep leaves the layer: its range goes to NCCL right away (layers retire last -> first)."""
+        self.model.on_layer_grad_ready = self._layer_grad_ready if (last_micro_step and self._comm is not None) else None
 
     def _phase(self, name):
         trainer = self
@@ -90,10 +147,17 @@ class TrainerCore:
     def optimizer_step(self):
         ps, a, lib = self.params, self.args, L.lib()
         s = L.stream_ptr()
+        self.model.on_layer_grad_ready = None
+        self._micro_idx = 0
         with self._phase("allreduce"):
             if self.world > 1:
-                # the ONLY data-path collective: sum of the flat fp32 gradient over NVLink
-                torch.distributed.all_reduce(ps.grad_flat)
+                # the ONLY data-path collective: sum of the flat fp32 gradient over NVLink. Decoder-layer
+                # ranges were enqueued during the last backward (arm_overlap); what is left - vision tower, embeddings,
+                # norms and biases - goes now; the phase timer therefore shows the EXPOSED communication time
+                for lo, hi in complement_ranges(self._reduced, ps.numel):
+                    self._enqueue_grad_range(lo, hi)
+                torch.cuda.current_stream().wait_stream(self._comm_stream)
+                self._reduced = []
         with self._phase("optimizer"):
             scale = 1.0 / self.world
             self._sumsq.zero_()

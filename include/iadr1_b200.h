@@ -125,6 +125,17 @@ int iadr1_cast_f32_bf16(const float* src, void* dst, long long n, void* stream);
 int iadr1_lse_finalize(const float* pmax, const float* psum, const float* tgt, int tiles_n, int M, float* lse,
                        float* logp, void* stream);
 
+/* ---- the one data-path collective: gradient all-reduce over NVLink ---------------------------
+ * Replaces ZeRO-3's per-parameter reduce-scatter / all-gather (ref: scripts/train/zero3.json:14-33). NCCL is bound at run time
+ * (the libnccl.so.2 the process carries); `comm` is an ncclComm_t created here from a 128-byte ncclUniqueId that rank 0
+ * generates and the host distributes. iadr1_grad_allreduce sums grad[0, n) in place, cut into buckets of bucket_elems
+ * (0 = one call), ordered on `stream` - the trainer enqueues each decoder layer's range on a side stream as soon as the
+ * backward sweep retires the layer, so the transfer overlaps the rest of the backward.                               */
+int iadr1_comm_unique_id(void* out128);
+int iadr1_comm_create(const void* unique_id128, int rank, int world, void** comm_out);
+int iadr1_comm_destroy(void* comm);
+int iadr1_grad_allreduce(void* comm, float* grad, long long n, long long bucket_elems, void* stream);
+
 /* ---- optimizer: replaces torch.optim.AdamW inside DeepSpeed ZeRO-3 + clip_grad_norm_ ------------ */
 int iadr1_sumsq_f32(const float* g, long long n, float* out, void* stream);
 int iadr1_adamw_step(float* p32, void* p16, float* g, float* m, float* v, long long n, float lr, float beta1,

@@ -489,3 +489,25 @@ def test_fmha_plan_host_logic():
         assert sum(f1 - f0 for *_, f0, f1 in ki) > 0 or name in ("windows",), name
     with __import__("pytest").raises(ValueError):
         fmha.build_items(np.array([[0, 0, 0, 0]], dtype=np.int32))
+
+
+def test_gradient_bucket_bookkeeping():
+    """Overlapped all-reduce (trainer_base): decoder-layer matrix ranges are disjoint, retire last -> first, and together with
+    the remainder computed at the optimizer step cover the flat gradient exactly once."""
+    from iad_r1_b200.config import tiny_config
+    from iad_r1_b200.params import ParamStore
+    from iad_r1_b200.trainer_base import complement_ranges
+    for fam in ("qwen2_5_vl", "llava_onevision"):
+        cfg = tiny_config(fam)
+        ps = ParamStore(cfg, "meta")
+        done = [ps.layer_matrix_range(i) for i in reversed(range(cfg.text.num_layers))]
+        for (lo, hi), i in zip(done, reversed(range(cfg.text.num_layers))):
+            assert lo == ps.offsets[f"layers.{i}.qkv.weight"] and hi > lo and hi <= ps.n_decay
+            names = [n for n, o in ps.offsets.items() if lo <= o < hi]
+            assert sorted(names) == sorted(f"layers.{i}.{k}.weight" for k in ("qkv", "o", "gate_up", "down")), names
+        rest = complement_ranges(done, ps.numel)
+        cover = sorted(done + rest)
+        assert cover[0][0] == 0 and cover[-1][1] == ps.numel
+        assert all(a[1] == b[0] for a, b in zip(cover, cover[1:]))
+    assert complement_ranges([], 10) == [(0, 10)] and complement_ranges([(0, 10)], 10) == []
+    assert complement_ranges([(2, 4), (6, 8)], 10) == [(0, 2), (4, 6), (8, 10)]
