@@ -109,6 +109,7 @@ class GRPOConfig:
     shared_prefix: bool = True                 # score a group as [prompt | G completions]: the prompt is computed once
     window_vision: bool = True                 # vision tower fwd/bwd once per accumulation window (batched_rollout only)
     rollout_forbid_eos: bool = False           # benchmarking only: fixed-length completions
+    gpu_image_preprocess: bool = True          # Qwen families: resize / normalise / patchify on the GPU (csrc/preprocess.cu)
     activation_recompute: str = "auto"         # per-layer recompute in the backward ("on" | "off" | "auto": only for models
                                                # whose unsharded state leaves too little HBM, e.g. Qwen2.5-VL-7B; 3B keeps
                                                # every activation resident even when --gradient_checkpointing is passed)

@@ -177,6 +177,7 @@ class SCGRPOTrainer(TrainerCore):
         self.reward_funcs = reward_funcs
         self.reward_processing_classes = reward_processing_classes or [None] * len(reward_funcs)
 
+        self.max_pixels, self.min_pixels = max_pixels or 12845056, min_pixels or 3136
         self.max_prompt_length = args.max_prompt_length
         self.max_completion_length = args.max_completion_length
         self.num_generations = args.num_generations
@@ -211,6 +212,24 @@ class SCGRPOTrainer(TrainerCore):
         if img is not None:
             for im in (img if isinstance(img, list) else [img]):
                 images.append(Image.open(im) if isinstance(im, str) else im)
+        gpu_pv = None
+        if images and self.args.gpu_image_preprocess and self.cfg.family in ("qwen2_vl", "qwen2_5_vl"):
+            # image half of the processor call on the GPU: the host decodes to uint8 and sizes the grid; the
+            # text half (placeholder expansion + tokenisation) is what the processor does with `images=None`
+            from .preprocess import OPENAI_CLIP_MEAN, OPENAI_CLIP_STD, qwen_preprocess_gpu
+            ip = getattr(self.processing_class, "image_processor", None)
+            size = getattr(ip, "size", None) or {}
+            minp = getattr(ip, "min_pixels", None) or size.get("shortest_edge") or self.min_pixels
+            maxp = getattr(ip, "max_pixels", None) or size.get("longest_edge") or self.max_pixels
+            gpu_pv, gpu_grid = qwen_preprocess_gpu(images, self.cfg.vision, self.device, int(minp), int(maxp),
+                                                   tuple(getattr(ip, "image_mean", None) or OPENAI_CLIP_MEAN),
+                                                   tuple(getattr(ip, "image_std", None) or OPENAI_CLIP_STD))
+            tok = getattr(self.processing_class, "image_token", "<|image_pad|>")
+            merge2 = self.cfg.vision.spatial_merge_size ** 2
+            for g_ in gpu_grid:
+                text = text.replace(tok, "<|iadr1_placeholder|>" * (g_[1] * g_[2] // merge2), 1)
+            text = text.replace("<|iadr1_placeholder|>", tok)
+            images = []
         enc = self.processing_class(text=[text], images=images if images else None, return_tensors="pt", padding=True,
                                     padding_side="left", add_special_tokens=False)
         ids = enc["input_ids"][0]
@@ -218,7 +237,7 @@ class SCGRPOTrainer(TrainerCore):
             ids = ids[enc["attention_mask"][0].bool()]
         if self.max_prompt_length is not None:
             ids = ids[-self.max_prompt_length:]  # Q14: ids only; cutting into image tokens raises downstream
-        pv, grid = vision_inputs_from_processor(self.cfg, enc)
+        pv, grid = (gpu_pv, gpu_grid) if gpu_pv is not None else vision_inputs_from_processor(self.cfg, enc)
         if pv is not None and not pv.is_cuda:
             pv = pv.pin_memory().to(self.device, non_blocking=True)   # pinned staging -> async H2D
         return dict(input_ids=ids.numpy().astype(np.int64), pixel_values=pv, grid_thw=grid, text=text)

@@ -125,6 +125,15 @@ int iadr1_cast_f32_bf16(const float* src, void* dst, long long n, void* stream);
 int iadr1_lse_finalize(const float* pmax, const float* psum, const float* tgt, int tiles_n, int M, float* lse,
                        float* logp, void* stream);
 
+/* ---- image preprocessing on the GPU (Qwen2-VL / Qwen2.5-VL): replaces the CPU image half of the processor call
+ * (ref: train/stage_rl/trainer/sc_grpo_trainer.py:614-621; HF image_processing_qwen2_vl.py:148-232). rgb_u8: device uint8
+ * [in_h][in_w][3]; the image is resized to out_h x out_w (multiples of patch * merge, from smart_resize on the host) with
+ * Pillow's antialiased bicubic, rescaled by 1/255, normalised with mean3 / std3 (HOST pointers to 3 floats) and written as
+ * bf16 patch rows [out_h/patch * out_w/patch][3 * tps * patch * patch] in merge-block-major order. scratch_u8: device
+ * uint8 [in_h * out_w * 3 + out_h * out_w * 3], needed only when the size changes.                                    */
+int iadr1_image_preprocess_qwen(const void* rgb_u8, int in_h, int in_w, int out_h, int out_w, int patch, int merge, int tps,
+                                const float* mean3, const float* std3, void* scratch_u8, void* out_bf16, void* stream);
+
 /* ---- the one data-path collective: gradient all-reduce over NVLink ---------------------------
  * Replaces ZeRO-3's per-parameter reduce-scatter / all-gather (ref: scripts/train/zero3.json:14-33). NCCL is bound at run time
  * (the libnccl.so.2 the process carries); `comm` is an ncclComm_t created here from a 128-byte ncclUniqueId that rank 0

@@ -511,3 +511,12 @@ def test_gradient_bucket_bookkeeping():
         assert all(a[1] == b[0] for a, b in zip(cover, cover[1:]))
     assert complement_ranges([], 10) == [(0, 10)] and complement_ranges([(0, 10)], 10) == []
     assert complement_ranges([(2, 4), (6, 8)], 10) == [(0, 2), (4, 6), (8, 10)]
+
+
+def test_smart_resize_matches_hf():
+    """Host half of the GPU image preprocessing: the target-size rule equals HF's `smart_resize`."""
+    from transformers.models.qwen2_vl.image_processing_qwen2_vl import smart_resize as hf_smart_resize
+    from iad_r1_b200.preprocess import smart_resize
+    for h, w in [(448, 448), (224, 224), (300, 500), (1000, 700), (90, 120), (37, 2000), (4000, 3000), (28, 28), (15, 15)]:
+        for mx in (480000, 12845056):
+            assert smart_resize(h, w, 28, 3136, mx) == tuple(hf_smart_resize(h, w, 28, 3136, mx)), (h, w, mx)

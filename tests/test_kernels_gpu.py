@@ -525,3 +525,36 @@ def test_decode_attention_fused(ops, nq, nkv, hd, nsplit):
             p_ = torch.softmax((K[:, kvh] @ q[h]) * scale, 0)
             ref = p_ @ V[:, kvh]
             close(out[r].view(nq, hd)[h], ref, 2 ** -6, f"decode attention row {r} head {h}")
+
+
+# ---------------------------------------------------------------------------------------------- image preprocessing
+@pytest.mark.parametrize("hw,max_pixels", [((448, 448), 480000), ((300, 500), 480000), ((1000, 700), 480000), ((90, 120), 12845056)])
+def test_image_preprocess_matches_hf_processor(ops, hw, max_pixels):
+    """GPU resize + normalise + patchify (csrc/preprocess.cu) against HF `Qwen2VLImageProcessor` (PIL bicubic) on the same
+    uint8 image: same grid, identical values when no resize is needed (up to the bf16 store), within 2 grey levels
+    (2 / 255 / std ~ 0.03) when Pillow's fixed-point resampling rounds differently from the fp32 kernel."""
+    import numpy as np
+    from PIL import Image
+    from transformers import Qwen2VLImageProcessor
+    from iad_r1_b200.config import tiny_config
+    from iad_r1_b200.preprocess import qwen_preprocess_gpu, smart_resize
+    rng = np.random.RandomState(hw[0])
+    # smooth + noisy content: low-frequency gradient plus noise exercises the antialiasing window
+    yy, xx = np.mgrid[0:hw[0], 0:hw[1]]
+    img = (127 + 80 * np.sin(yy / 23.0)[..., None] * np.cos(xx / 17.0)[..., None] + rng.randint(-40, 40, (hw[0], hw[1], 3))).clip(0, 255).astype(np.uint8)
+    v = tiny_config("qwen2_5_vl").vision
+    hf = Qwen2VLImageProcessor(min_pixels=3136, max_pixels=max_pixels, patch_size=v.patch_size,
+                               temporal_patch_size=v.temporal_patch_size, merge_size=v.spatial_merge_size)
+    ref = hf(images=[Image.fromarray(img)], return_tensors="pt")
+    pv, grid = qwen_preprocess_gpu([Image.fromarray(img)], v, torch.device("cuda"), 3136, max_pixels)
+    assert [list(g) for g in ref["image_grid_thw"].tolist()] == grid
+    th, tw = smart_resize(hw[0], hw[1], 28, 3136, max_pixels)
+    assert (grid[0][1] * 14, grid[0][2] * 14) == (th, tw)
+    want = ref["pixel_values"].float().cuda()
+    got = pv.float()
+    assert got.shape == want.shape
+    err = (got - want).abs()
+    if (th, tw) == hw:
+        assert err.max().item() <= 2 ** -7 * want.abs().max().item()
+    else:
+        assert err.max().item() <= 0.035 and err.mean().item() <= 0.004, (err.max().item(), err.mean().item())
