@@ -1,0 +1,528 @@
+// Model-level entry points of the C ABI (SURVEY.md §8b "B-inner"): the layer loops of the decoder forward / backward,
+// the fused lm_head log-prob / cross-entropy head and the rollout's decode step as SINGLE calls over weights registered
+// once by pointer. They stand in for the three Python call sites of the reference's hot path:
+//   `model(**inputs).logits`     ref: train/stage_rl/trainer/sc_grpo_trainer.py:505   -> iadr1_decoder_fwd + iadr1_logprob_fwd
+//   `loss.backward()`            (HF Trainer.training_step)                           -> iadr1_logprob_bwd + iadr1_decoder_bwd
+//   `self.llm.generate(...)`     ref: train/stage_rl/trainer/sc_grpo_trainer.py:667   -> iadr1_prefill + iadr1_decode_step
+// Conventions as everywhere in this library: raw device pointers owned by the caller, a caller-provided workspace whose
+// size the library reports, nothing allocated here, work ordered on the passed stream.
+#include "runtime.h"
+
+#include <cstdio>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace iadr1 {
+
+typedef unsigned short bf16_t;   // storage only
+
+struct Weight {
+  const void* p = nullptr;
+  float* g = nullptr;
+};
+
+struct Model {
+  iadr1_model_cfg_t c;
+  std::unordered_map<std::string, Weight> w;
+  const Weight* find(const std::string& n) const {
+    auto it = w.find(n);
+    return it == w.end() ? nullptr : &it->second;
+  }
+};
+
+struct Arena {      // bump allocator over the caller's workspace (base == nullptr: size computation only)
+  char* base;
+  size_t off = 0;
+  explicit Arena(void* b) : base(static_cast<char*>(b)) {}
+  void* take(size_t bytes) {
+    void* p = base ? base + off : nullptr;
+    off += (bytes + 255) & ~size_t(255);
+    return p;
+  }
+};
+
+// ---- dense products over row-major buffers (the forms ops.py uses) --------------------------------------------------
+static int linear_fwd(const void* x, const void* W, void* out, long long M, int N, int K, const void* bias, const void* residual,
+                      cudaStream_t s) {
+  iadr1_gemm_t d;
+  memset(&d, 0, sizeof(d));
+  d.M = (int)M; d.N = N; d.K = K;
+  d.batch = d.batch_lo = d.b_lo_div = 1;
+  d.A = x; d.lda = K;
+  d.B = W; d.ldb = K;
+  d.C = out; d.ldc = N;
+  d.split_k = 1; d.alpha = 1.f;
+  d.bias = bias; d.residual = residual;
+  return launch_gemm(d, s);
+}
+// dx[M, K] = dy[M, N] @ W[N, K]
+static int linear_dgrad(const void* dy, const void* W, void* dx, long long M, int N, int K, cudaStream_t s) {
+  iadr1_gemm_t d;
+  memset(&d, 0, sizeof(d));
+  d.M = (int)M; d.N = K; d.K = N;
+  d.batch = d.batch_lo = d.b_lo_div = 1;
+  d.A = dy; d.lda = N;
+  d.B = W; d.ldb = K; d.b_mn = 1;
+  d.C = dx; d.ldc = K;
+  d.split_k = 1; d.alpha = 1.f;
+  return launch_gemm(d, s);
+}
+// dW32[N, K] += dy[M, N]^T @ x[M, K]
+static int linear_wgrad(const void* dy, const void* x, float* dW, long long M, int N, int K, cudaStream_t s) {
+  if (!dW) return 0;
+  iadr1_gemm_t d;
+  memset(&d, 0, sizeof(d));
+  d.M = N; d.N = K; d.K = (int)M;
+  d.batch = d.batch_lo = d.b_lo_div = 1;
+  d.A = dy; d.lda = N; d.a_mn = 1;
+  d.B = x; d.ldb = K; d.b_mn = 1;
+  d.C = dW; d.ldc = K; d.c_f32 = 1; d.accumulate = 1;
+  d.split_k = 1; d.alpha = 1.f;
+  return launch_gemm(d, s);
+}
+
+__global__ void scale_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n, float scale) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = src[i] * scale;
+}
+static int scale_f32(const float* src, float* dst, long long n, float scale, cudaStream_t s) {
+  if (n <= 0) return 0;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 1184) blocks = 1184;
+  scale_f32_kernel<<<(int)blocks, 256, 0, s>>>(src, dst, n, scale);
+  IADR1_CHECK_LAUNCH("scale_f32");
+  return 0;
+}
+
+#define TRY(expr)            \
+  do {                       \
+    int rc__ = (expr);       \
+    if (rc__) return rc__;   \
+  } while (0)
+
+// ---- decoder ---------------------------------------------------------------------------------------------------------
+struct LayerBuf {
+  float* r1; void* xn; void* qkv; float* lse2; void* a_out; void* h_mid; float* r2; void* xn2; void* gu; void* act;
+};
+struct DecoderLayout {
+  std::vector<void*> h;          // h[i] = input of layer i, h[L] = output
+  std::vector<LayerBuf> lb;      // one per layer (mode 1) or a single shared one (modes 0, 2)
+  void* dact; void* dx; void* dattn; void* dqkv; float* delta; float* dkv32;   // backward scratch (modes 1, 2)
+  size_t bytes;
+};
+
+static LayerBuf take_layer(Arena& a, const iadr1_model_cfg_t& c, long long N, long long npad) {
+  const long long H = c.hidden, I = c.inter, D = (long long)(c.nq + 2 * c.nkv) * c.hd, QH = (long long)c.nq * c.hd;
+  LayerBuf b;
+  b.r1 = static_cast<float*>(a.take(N * 4));
+  b.xn = a.take(N * H * 2);
+  b.qkv = a.take(N * D * 2);
+  b.lse2 = static_cast<float*>(a.take((size_t)c.nq * npad * 4));
+  b.a_out = a.take(N * QH * 2);
+  b.h_mid = a.take(N * H * 2);
+  b.r2 = static_cast<float*>(a.take(N * 4));
+  b.xn2 = a.take(N * H * 2);
+  b.gu = a.take(N * 2 * I * 2);
+  b.act = a.take(N * I * 2);
+  return b;
+}
+
+// mode 0: forward only (two ping-pong hidden buffers, one layer scratch); 1: every activation resident; 2: layer inputs
+// resident + one layer scratch (recompute in the backward)
+static DecoderLayout decoder_layout(const iadr1_model_cfg_t& c, long long N, long long npad, int mode, void* base) {
+  Arena a(base);
+  DecoderLayout L;
+  const long long H = c.hidden, I = c.inter, D = (long long)(c.nq + 2 * c.nkv) * c.hd, QH = (long long)c.nq * c.hd;
+  L.h.resize(c.layers + 1);
+  if (mode == 0) {
+    void* p0 = a.take(N * H * 2);
+    void* p1 = a.take(N * H * 2);
+    for (int i = 0; i <= c.layers; ++i) L.h[i] = (i & 1) ? p1 : p0;
+  } else {
+    for (int i = 0; i <= c.layers; ++i) L.h[i] = a.take(N * H * 2);
+  }
+  if (mode == 1) {
+    for (int i = 0; i < c.layers; ++i) L.lb.push_back(take_layer(a, c, N, npad));
+  } else {
+    L.lb.push_back(take_layer(a, c, N, npad));
+  }
+  L.dact = L.dx = L.dattn = L.dqkv = nullptr;
+  L.delta = L.dkv32 = nullptr;
+  if (mode != 0) {
+    L.dact = a.take(N * I * 2);
+    L.dx = a.take(N * H * 2);
+    L.dattn = a.take(N * QH * 2);
+    L.dqkv = a.take(N * D * 2);
+    L.delta = static_cast<float*>(a.take((size_t)c.nq * npad * 4));
+    L.dkv32 = static_cast<float*>(a.take((size_t)N * 2 * c.nkv * c.hd * 4));
+  }
+  L.bytes = a.off;
+  return L;
+}
+
+struct LayerW {
+  const Weight *ln1, *qkv, *qkv_b, *o, *ln2, *gu, *down;
+};
+static int layer_weights(const Model& m, int i, LayerW& w) {
+  const std::string b = "layers." + std::to_string(i) + ".";
+  w.ln1 = m.find(b + "ln1.weight"); w.qkv = m.find(b + "qkv.weight"); w.qkv_b = m.find(b + "qkv.bias");
+  w.o = m.find(b + "o.weight"); w.ln2 = m.find(b + "ln2.weight"); w.gu = m.find(b + "gate_up.weight");
+  w.down = m.find(b + "down.weight");
+  if (!w.ln1 || !w.qkv || !w.qkv_b || !w.o || !w.ln2 || !w.gu || !w.down)
+    return set_error("decoder layer %d: weights not bound (iadr1_bind_weights)", i);
+  return 0;
+}
+
+static int layer_fwd(const Model& m, int i, const void* h_in, void* h_out, const LayerBuf& b, bool save, long long N,
+                     const float* cos, const float* sin, const iadr1_attn_plan_t* plan, const iadr1_kv_sink_t* sink,
+                     cudaStream_t s) {
+  const iadr1_model_cfg_t& c = m.c;
+  const int H = c.hidden, I = c.inter, D = (c.nq + 2 * c.nkv) * c.hd, QH = c.nq * c.hd;
+  LayerW w;
+  TRY(layer_weights(m, i, w));
+  TRY(iadr1_rmsnorm_fwd(h_in, w.ln1->p, b.xn, save ? b.r1 : nullptr, N, H, H, H, c.rms_eps, s));
+  TRY(linear_fwd(b.xn, w.qkv->p, b.qkv, N, D, H, w.qkv_b->p, nullptr, s));
+  TRY(iadr1_rope(b.qkv, cos, sin, N, c.nq + c.nkv, c.hd, D, 1, 0, s));
+  if (sink && sink->kp) {
+    // rollout prefill: post-rotary K / V rows of every prompt go to the shared-prefix cache [layer][group][p_max][nkv][hd]
+    const long long kvw = (long long)c.nkv * c.hd;
+    for (int gi = 0; gi < sink->n_groups; ++gi) {
+      const char* src = static_cast<const char*>(b.qkv) + ((long long)gi * sink->p_len * D + QH) * 2;
+      char* kd = static_cast<char*>(sink->kp) + ((long long)i * sink->layer_stride + (long long)gi * sink->p_max * kvw) * 2;
+      char* vd = static_cast<char*>(sink->vp) + ((long long)i * sink->layer_stride + (long long)gi * sink->p_max * kvw) * 2;
+      if (cudaMemcpy2DAsync(kd, kvw * 2, src, (size_t)D * 2, kvw * 2, sink->p_len, cudaMemcpyDeviceToDevice, s) != cudaSuccess ||
+          cudaMemcpy2DAsync(vd, kvw * 2, src + kvw * 2, (size_t)D * 2, kvw * 2, sink->p_len, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+        return set_error("prefill: KV copy failed");
+    }
+  }
+  const float scale = 1.f / sqrtf((float)c.hd);
+  TRY(iadr1_fmha_fwd(b.qkv, N, c.nq, c.nkv, c.hd, plan->ranges, plan->q_items, plan->n_q, plan->sched_fwd, plan->n_cta_fwd,
+                     b.a_out, b.lse2, plan->npad, scale, 0, s));
+  TRY(linear_fwd(b.a_out, w.o->p, b.h_mid, N, H, QH, nullptr, h_in, s));
+  TRY(iadr1_rmsnorm_fwd(b.h_mid, w.ln2->p, b.xn2, save ? b.r2 : nullptr, N, H, H, H, c.rms_eps, s));
+  TRY(linear_fwd(b.xn2, w.gu->p, b.gu, N, 2 * I, H, nullptr, nullptr, s));
+  TRY(iadr1_act_mul_fwd(b.gu, b.act, N, I, 2 * I, I, I, 0, s));
+  TRY(linear_fwd(b.act, w.down->p, h_out, N, H, I, nullptr, b.h_mid, s));
+  return 0;
+}
+
+}  // namespace iadr1
+
+using namespace iadr1;
+
+extern "C" {
+
+int iadr1_model_create(const iadr1_model_cfg_t* cfg, void** handle) {
+  if (!cfg || !handle) return set_error("model_create: null argument");
+  if (cfg->hidden <= 0 || cfg->layers <= 0 || cfg->nq <= 0 || cfg->nkv <= 0 || cfg->nq % cfg->nkv || cfg->hd % 8)
+    return set_error("model_create: bad text geometry");
+  Model* m = new Model();
+  m->c = *cfg;
+  *handle = m;
+  return 0;
+}
+
+int iadr1_model_destroy(void* handle) {
+  delete static_cast<Model*>(handle);
+  return 0;
+}
+
+int iadr1_bind_weights(void* handle, const char* name, const void* param_bf16, float* grad_f32) {
+  if (!handle || !name || !param_bf16) return set_error("bind_weights: null argument");
+  Weight w;
+  w.p = param_bf16;
+  w.g = grad_f32;
+  static_cast<Model*>(handle)->w[name] = w;
+  return 0;
+}
+
+int iadr1_decoder_workspace_bytes(void* handle, long long n_tokens, long long npad, int mode, long long* bytes) {
+  if (!handle || !bytes) return set_error("decoder_workspace_bytes: null argument");
+  *bytes = (long long)decoder_layout(static_cast<Model*>(handle)->c, n_tokens, npad, mode, nullptr).bytes;
+  return 0;
+}
+
+int iadr1_decoder_fwd(void* handle, const int* src_index, const void* image_embeds, long long n_tokens, const float* cos_t,
+                      const float* sin_t, const iadr1_attn_plan_t* plan, void* workspace, int mode,
+                      const iadr1_kv_sink_t* sink, void** h_last, void* stream) {
+  if (!handle || !plan || !workspace) return set_error("decoder_fwd: null argument");
+  Model& m = *static_cast<Model*>(handle);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long long N = n_tokens;
+  if (plan->n_tokens != N) return set_error("decoder_fwd: attention plan covers %lld tokens, called with %lld", plan->n_tokens, N);
+  DecoderLayout L = decoder_layout(m.c, N, plan->npad, mode, workspace);
+  const Weight* emb = m.find("embed_tokens.weight");
+  if (!emb) return set_error("decoder_fwd: embed_tokens.weight not bound");
+  const int H = m.c.hidden;
+  TRY(iadr1_gather_rows(emb->p, image_embeds, src_index, L.h[0], N, H, H, H, H, s));
+  for (int i = 0; i < m.c.layers; ++i) {
+    const LayerBuf& b = mode == 1 ? L.lb[i] : L.lb[0];
+    TRY(layer_fwd(m, i, L.h[i], L.h[i + 1], b, mode == 1, N, cos_t, sin_t, plan, sink, s));
+  }
+  if (h_last) *h_last = L.h[m.c.layers];
+  return 0;
+}
+
+int iadr1_decoder_bwd(void* handle, void* dh, const int* src_index, const float* cos_t, const float* sin_t,
+                      const iadr1_attn_plan_t* plan, void* workspace, int mode, long long n_tokens, float* dimg32,
+                      iadr1_layer_cb on_layer_done, void* cb_user, void* stream) {
+  if (!handle || !plan || !workspace || !dh) return set_error("decoder_bwd: null argument");
+  if (mode != 1 && mode != 2) return set_error("decoder_bwd: the forward ran without saving (mode %d)", mode);
+  Model& m = *static_cast<Model*>(handle);
+  const iadr1_model_cfg_t& c = m.c;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long long N = n_tokens;
+  const int H = c.hidden, I = c.inter, D = (c.nq + 2 * c.nkv) * c.hd, QH = c.nq * c.hd;
+  DecoderLayout L = decoder_layout(c, N, plan->npad, mode, workspace);
+  const float scale = 1.f / sqrtf((float)c.hd);
+  for (int i = c.layers - 1; i >= 0; --i) {
+    const LayerBuf& b = mode == 1 ? L.lb[i] : L.lb[0];
+    LayerW w;
+    TRY(layer_weights(m, i, w));
+    if (mode == 2)      // recompute this layer's activations from its saved input (h[i + 1] is rewritten with the same values)
+      TRY(layer_fwd(m, i, L.h[i], L.h[i + 1], b, true, N, cos_t, sin_t, plan, nullptr, s));
+    // MLP
+    TRY(linear_dgrad(dh, w.down->p, L.dact, N, H, I, s));
+    TRY(linear_wgrad(dh, b.act, w.down->g, N, H, I, s));
+    TRY(iadr1_act_mul_bwd(L.dact, b.gu, b.gu, N, I, 2 * I, I, I, 0, s));
+    TRY(linear_dgrad(b.gu, w.gu->p, L.dx, N, 2 * I, H, s));
+    TRY(linear_wgrad(b.gu, b.xn2, w.gu->g, N, 2 * I, H, s));
+    TRY(iadr1_rmsnorm_bwd(L.dx, b.h_mid, w.ln2->p, b.r2, dh, w.ln2->g, N, H, H, 1, s));
+    // attention
+    TRY(linear_dgrad(dh, w.o->p, L.dattn, N, H, QH, s));
+    TRY(linear_wgrad(dh, b.a_out, w.o->g, N, H, QH, s));
+    TRY(iadr1_fmha_bwd(b.qkv, L.dattn, b.a_out, b.lse2, N, c.nq, c.nkv, c.hd, plan->ranges, plan->q_items, plan->n_q,
+                       plan->sched_dq, plan->n_cta_dq, plan->k_items, plan->n_k, plan->sched_kv, plan->n_cta_kv, L.dqkv, L.delta,
+                       L.dkv32, plan->npad, scale, 0, s));
+    TRY(iadr1_rope(L.dqkv, cos_t, sin_t, N, c.nq + c.nkv, c.hd, D, 0, 1, s));
+    TRY(linear_dgrad(L.dqkv, w.qkv->p, L.dx, N, D, H, s));
+    TRY(linear_wgrad(L.dqkv, b.xn, w.qkv->g, N, D, H, s));
+    if (w.qkv_b->g) TRY(iadr1_colsum(L.dqkv, w.qkv_b->g, N, D, D, s));
+    TRY(iadr1_rmsnorm_bwd(L.dx, L.h[i], w.ln1->p, b.r1, dh, w.ln1->g, N, H, H, 1, s));
+    if (on_layer_done) on_layer_done(i, cb_user);
+  }
+  const Weight* emb = m.find("embed_tokens.weight");
+  if (!emb) return set_error("decoder_bwd: embed_tokens.weight not bound");
+  TRY(iadr1_scatter_add_rows(dh, src_index, emb->g, dimg32, N, H, H, H, H, s));
+  return 0;
+}
+
+// ---- fused lm_head -> log-softmax -> gather (and its backward); the SFT cross-entropy is the same head ------------------
+}  // extern "C"
+
+struct HeadLayout {
+  void* hsel; float* rf; void* hn; float* pmax; float* psum; float* tgt; float* lse; float* gscale; void* dlogits; void* dhn; void* dhsel;
+  long long tiles; int bn; size_t bytes;
+};
+static HeadLayout head_layout(const iadr1_model_cfg_t& c, long long M, void* base, bool backward) {
+  HeadLayout L;
+  L.bn = pick_block_n_public(c.vocab, 0);
+  L.tiles = (c.vocab + L.bn - 1) / L.bn;
+  Arena a(base);
+  L.hsel = a.take(M * c.hidden * 2);
+  L.rf = static_cast<float*>(a.take(M * 4));
+  L.hn = a.take(M * c.hidden * 2);
+  L.pmax = static_cast<float*>(a.take(M * L.tiles * 4));
+  L.psum = static_cast<float*>(a.take(M * L.tiles * 4));
+  L.tgt = static_cast<float*>(a.take(M * 4));
+  L.lse = static_cast<float*>(a.take(M * 4));
+  L.gscale = nullptr; L.dlogits = L.dhn = L.dhsel = nullptr;
+  if (backward) {
+    L.gscale = static_cast<float*>(a.take(M * 4));
+    L.dlogits = a.take((size_t)M * c.vocab * 2);
+    L.dhn = a.take(M * c.hidden * 2);
+    L.dhsel = a.take(M * c.hidden * 2);
+  }
+  L.bytes = a.off;
+  return L;
+}
+
+static const Weight* head_weight(const Model& m) {
+  const Weight* w = m.find("lm_head.weight");
+  return w ? w : m.find("embed_tokens.weight");      // tied embeddings
+}
+
+extern "C" {
+
+// the backward's workspace (backward = 1) must be the one the forward ran in: it holds hsel / hn / lse
+int iadr1_logprob_workspace_bytes(void* handle, long long m_rows, int backward, long long* bytes) {
+  if (!handle || !bytes) return set_error("logprob_workspace_bytes: null argument");
+  *bytes = (long long)head_layout(static_cast<Model*>(handle)->c, m_rows, nullptr, backward != 0).bytes;
+  return 0;
+}
+
+// logp[j] = log_softmax(norm(h[sel[j]]) @ E^T / temperature)[labels[j]]; lse is kept in the workspace for the backward
+int iadr1_logprob_fwd(void* handle, const void* h, const int* sel_index, const int* labels, long long m_rows, float temperature,
+                      void* workspace, float* logp, void* stream) {
+  if (!handle || !workspace) return set_error("logprob_fwd: null argument");
+  Model& m = *static_cast<Model*>(handle);
+  const iadr1_model_cfg_t& c = m.c;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  HeadLayout L = head_layout(c, m_rows, workspace, false);
+  const Weight* E = head_weight(m);
+  const Weight* nw = m.find("norm.weight");
+  if (!E || !nw) return set_error("logprob_fwd: lm_head / norm.weight not bound");
+  const int H = c.hidden;
+  TRY(iadr1_gather_rows(h, nullptr, sel_index, L.hsel, m_rows, H, H, 0, H, s));
+  TRY(iadr1_rmsnorm_fwd(L.hsel, nw->p, L.hn, L.rf, m_rows, H, H, H, c.rms_eps, s));
+  if (cudaMemsetAsync(L.tgt, 0, m_rows * 4, s) != cudaSuccess) return set_error("logprob_fwd: memset failed");
+  iadr1_gemm_t d;
+  memset(&d, 0, sizeof(d));
+  d.M = (int)m_rows; d.N = c.vocab; d.K = H;
+  d.batch = d.batch_lo = d.b_lo_div = 1;
+  d.A = L.hn; d.lda = H;
+  d.B = E->p; d.ldb = H;
+  d.split_k = 1; d.alpha = 1.f / temperature;
+  d.epi = 1;
+  d.labels = labels; d.part_max = L.pmax; d.part_sum = L.psum; d.tgt_logit = L.tgt; d.lse_tiles_n = (int)L.tiles;
+  d.block_n = L.bn;
+  TRY(launch_gemm(d, s));
+  TRY(iadr1_lse_finalize(L.pmax, L.psum, L.tgt, (int)L.tiles, (int)m_rows, L.lse, logp, s));
+  return 0;
+}
+
+}  // extern "C"
+
+// dh32 [n_tokens][H] fp32 (zeroed by the caller) receives the scatter-ADD of d(hidden) at rows sel_index; `sign` = +1 when
+// dsrc is d(loss)/d(logp), -1 when it is d(loss)/d(nll)
+static int head_bwd(void* handle, const float* dlogp, float sign, const int* sel_index, const int* labels, long long m_rows,
+                    float temperature, void* workspace, float* dh32, void* stream) {
+  if (!handle || !workspace) return set_error("logprob_bwd: null argument");
+  Model& m = *static_cast<Model*>(handle);
+  const iadr1_model_cfg_t& c = m.c;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  HeadLayout L = head_layout(c, m_rows, workspace, true);
+  const Weight* E = head_weight(m);
+  const Weight* nw = m.find("norm.weight");
+  if (!E || !nw) return set_error("logprob_bwd: lm_head / norm.weight not bound");
+  const int H = c.hidden, V = c.vocab;
+  TRY(scale_f32(dlogp, L.gscale, m_rows, -sign / temperature, s));          // kernel forms (softmax - onehot) * gscale
+  iadr1_gemm_t d;
+  memset(&d, 0, sizeof(d));
+  d.M = (int)m_rows; d.N = V; d.K = H;
+  d.batch = d.batch_lo = d.b_lo_div = 1;
+  d.A = L.hn; d.lda = H;
+  d.B = E->p; d.ldb = H;
+  d.C = L.dlogits; d.ldc = V;
+  d.split_k = 1; d.alpha = 1.f / temperature;
+  d.epi = 2;
+  d.labels = labels; d.lse = L.lse; d.gscale = L.gscale;
+  TRY(launch_gemm(d, s));
+  TRY(linear_dgrad(L.dlogits, E->p, L.dhn, m_rows, V, H, s));
+  TRY(linear_wgrad(L.dlogits, L.hn, E->g, m_rows, V, H, s));
+  TRY(iadr1_rmsnorm_bwd(L.dhn, L.hsel, nw->p, L.rf, L.dhsel, nw->g, m_rows, H, H, 0, s));
+  TRY(iadr1_scatter_add_rows(L.dhsel, sel_index, dh32, nullptr, m_rows, H, H, H, 0, s));
+  return 0;
+}
+
+extern "C" {
+
+int iadr1_logprob_bwd(void* handle, const float* dlogp, const int* sel_index, const int* labels, long long m_rows,
+                      float temperature, void* workspace, float* dh32, void* stream) {
+  return head_bwd(handle, dlogp, 1.f, sel_index, labels, m_rows, temperature, workspace, dh32, stream);
+}
+
+// SFT head (HF ForCausalLMLoss, ref: train/stage_sft/llamafactory/train/sft/trainer.py:92-107): token cross-entropy is the
+// negated log-prob of the label; the two entry points share the kernels with the log-prob head.
+int iadr1_ce_fwd(void* handle, const void* h, const int* sel_index, const int* labels, long long m_rows, void* workspace,
+                 float* nll, void* stream) {
+  TRY(iadr1_logprob_fwd(handle, h, sel_index, labels, m_rows, 1.f, workspace, nll, stream));
+  return scale_f32(nll, nll, m_rows, -1.f, static_cast<cudaStream_t>(stream));
+}
+int iadr1_ce_bwd(void* handle, const float* dnll, const int* sel_index, const int* labels, long long m_rows, void* workspace,
+                 float* dh32, void* stream) {
+  return head_bwd(handle, dnll, -1.f, sel_index, labels, m_rows, 1.f, workspace, dh32, stream);   // d(nll) = -d(logp)
+}
+
+// ---- rollout: prefill = forward-only decoder pass that also fills the shared-prefix KV cache ------------------------------
+int iadr1_prefill(void* handle, const int* src_index, const void* image_embeds, long long n_tokens, const float* cos_t,
+                  const float* sin_t, const iadr1_attn_plan_t* plan, void* workspace, const iadr1_kv_sink_t* sink, void** h_last,
+                  void* stream) {
+  if (!sink || !sink->kp || !sink->vp) return set_error("prefill: KV sink required");
+  if ((long long)sink->n_groups * sink->p_len != n_tokens) return set_error("prefill: n_groups * p_len must equal n_tokens");
+  return iadr1_decoder_fwd(handle, src_index, image_embeds, n_tokens, cos_t, sin_t, plan, workspace, 0, sink, h_last, stream);
+}
+
+// One decode step of all rows in flight (the body the rollout captures into a CUDA graph): embed -> L x [rmsnorm, qkv,
+// rotary + KV append + attention, o, rmsnorm, gate_up + SwiGLU, down] -> rmsnorm -> lm_head -> sampler -> advance.
+static int skinny(const void* W, const void* x, void* out, int F, int K, int R, int split_k, const void* bias, int block_n,
+                  cudaStream_t s) {
+  iadr1_gemm_t d;
+  memset(&d, 0, sizeof(d));
+  d.M = F; d.N = R; d.K = K;
+  d.batch = d.batch_lo = d.b_lo_div = 1;
+  d.A = W; d.lda = K;
+  d.B = x; d.ldb = K;
+  d.C = out; d.ldc = F; d.c_f32 = 1; d.trans_c = 1;
+  d.atomic = split_k > 0 ? 1 : 0;
+  d.split_k = split_k > 0 ? split_k : 1;
+  d.alpha = 1.f;
+  d.bias = bias; d.bias_per_m = 1;
+  d.block_n = block_n; d.a_static = 1;
+  return launch_gemm(d, s);
+}
+static int split_for(int m_feat, int k) {
+  const int tiles = (m_feat + 127) / 128, nkb = (k + 63) / 64;
+  int sp = 148 / (tiles > 0 ? tiles : 1);
+  if (sp > nkb) sp = nkb;
+  return sp < 1 ? 1 : sp;
+}
+
+int iadr1_decode_head(void* handle, const iadr1_decode_t* e, int first, void* stream) {
+  Model& m = *static_cast<Model*>(handle);
+  const iadr1_model_cfg_t& c = m.c;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const Weight* nw = m.find("norm.weight");
+  const Weight* E = head_weight(m);
+  if (!nw || !E) return set_error("decode_head: weights not bound");
+  TRY(iadr1_rmsnorm_f32in(e->h, nw->p, e->xn, e->R, c.hidden, c.rms_eps, nullptr, 0, s));
+  TRY(skinny(E->p, e->xn, e->logits, c.vocab, c.hidden, e->R, 0, nullptr, e->block_n, s));
+  return iadr1_sample(e->logits, e->R, c.vocab, e->temperature, e->top_k, e->top_p, 0ull, e->state, e->tok, e->finished,
+                      e->out_tokens, e->c_max, e->eos_id, e->pad_id, e->forbid_eos, first, s);
+}
+
+int iadr1_decode_step(void* handle, const iadr1_decode_t* e, void* stream) {
+  if (!handle || !e) return set_error("decode_step: null argument");
+  Model& m = *static_cast<Model*>(handle);
+  const iadr1_model_cfg_t& c = m.c;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int H = c.hidden, I = c.inter, D = (c.nq + 2 * c.nkv) * c.hd, QH = c.nq * c.hd, R = e->R;
+  const Weight* emb = m.find("embed_tokens.weight");
+  if (!emb) return set_error("decode_step: embed_tokens.weight not bound");
+  TRY(iadr1_decode_embed(emb->p, e->tok, e->h, R, H, s));
+  const int sk_qkv = split_for(D, H), sk_o = split_for(H, QH), sk_d = split_for(H, I);
+  const long long kvw = (long long)c.nkv * c.hd;
+  for (int i = 0; i < c.layers; ++i) {
+    LayerW w;
+    TRY(layer_weights(m, i, w));
+    TRY(iadr1_rmsnorm_f32in(e->h, w.ln1->p, e->xn, R, H, c.rms_eps, e->qkv, D, s));
+    TRY(skinny(w.qkv->p, e->xn, e->qkv, D, H, R, sk_qkv, w.qkv_b->p, e->block_n, s));
+    const char* kp = static_cast<const char*>(e->kp) + (long long)i * e->n_groups * e->p_max * kvw * 2;
+    const char* vp = static_cast<const char*>(e->vp) + (long long)i * e->n_groups * e->p_max * kvw * 2;
+    char* kc = static_cast<char*>(e->kc) + (long long)i * R * e->c_max * kvw * 2;
+    char* vc = static_cast<char*>(e->vc) + (long long)i * R * e->c_max * kvw * 2;
+    TRY(iadr1_decode_attention_fused(e->qkv, e->cos_tab, e->sin_tab, e->rope_delta, kp, vp, kc, vc, e->state, e->row_group,
+                                     e->row_plen, e->part, e->tickets, e->attn, R, c.nq, c.nkv, c.hd, e->p_max, e->c_max,
+                                     e->nsplit, e->max_pos, 1.f / sqrtf((float)c.hd), s));
+    TRY(skinny(w.o->p, e->attn, e->h, H, QH, R, sk_o, nullptr, e->block_n, s));
+    TRY(iadr1_rmsnorm_f32in(e->h, w.ln2->p, e->xn, R, H, c.rms_eps, nullptr, 0, s));
+    {
+      iadr1_gemm_t d;
+      memset(&d, 0, sizeof(d));
+      d.M = 2 * I; d.N = R; d.K = H;
+      d.batch = d.batch_lo = d.b_lo_div = 1;
+      d.A = w.gu->p; d.lda = H;
+      d.B = e->xn; d.ldb = H;
+      d.C = e->act; d.ldc = I;
+      d.split_k = 1; d.alpha = 1.f; d.epi = 3; d.up_row_off = I;
+      d.block_n = e->block_n; d.a_static = 1; d.co_resident = 1;
+      TRY(launch_gemm(d, s));
+    }
+    TRY(skinny(w.down->p, e->act, e->h, H, I, R, sk_d, nullptr, e->block_n, s));
+  }
+  TRY(iadr1_decode_head(handle, e, 0, stream));
+  return iadr1_decode_advance(e->state, s);
+}
+
+}  // extern "C"

@@ -58,7 +58,8 @@ def lib():
 
 
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "iadr1_b200.h")
-_CTYPES = {"int": C.c_int, "long long": C.c_longlong, "float": C.c_float, "unsigned long long": C.c_ulonglong}
+_CTYPES = {"int": C.c_int, "long long": C.c_longlong, "float": C.c_float, "unsigned long long": C.c_ulonglong,
+           "iadr1_layer_cb": C.c_void_p}
 
 
 def header_prototypes(path: str = HEADER) -> dict:

@@ -40,12 +40,21 @@ class VLM:
         self.device = params.device
         self.recompute = False      # per-layer activation recompute in the decoder backward (set by the trainers)
         self.on_layer_grad_ready = None   # callback(layer) once a decoder layer's weight gradients are complete (all-reduce overlap)
+        self._native = None               # model-level C ABI handle (native.NativeModel), created on first use
         self._zero_row = torch.zeros(1, max(cfg.text.hidden_size, cfg.vision.hidden_size), dtype=bf16, device=self.device)
         self._causal_cache = {}
 
     @property
     def g(self):
         return self.params.g
+
+    @property
+    def native(self):
+        """Handle of the model-level C ABI (decoder / head / rollout layer loops in C++, csrc/model.cu)."""
+        if self._native is None:
+            from .native import NativeModel
+            self._native = NativeModel(self.cfg, self.params)
+        return self._native
 
     def _causal_ranges(self, T):
         r = self._causal_cache.get(T)
@@ -299,8 +308,31 @@ class VLM:
         one prompt + G completions). kv_sink(layer, qkv) sees each layer's post-rotary fused qkv buffer (rollout prefill)."""
         t, p = self.cfg.text, self.p
         H, I, nq, nkv, hd = t.hidden_size, t.intermediate_size, t.num_heads, t.num_kv_heads, t.head_dim
+        fused = getattr(attn, "fused", None)
+        if fused is not None:
+            # ONE call into the model-level C ABI: embedding gather + every decoder layer (iadr1_decoder_fwd / iadr1_prefill);
+            # activations live in one workspace tensor that the context keeps until the backward
+            from .native import KvSink
+            mode = 0 if not save else (2 if self.recompute else 1)
+            sink = None
+            if kv_sink is not None:
+                kp, vp = kv_sink["kp"], kv_sink["vp"]
+                sink = KvSink(kp.data_ptr(), vp.data_ptr(), kv_sink["n"], kv_sink["p_len"], kp.shape[2], kp.stride(0))
+            h, ws = self.native.decoder_fwd(src_index, image_embeds, cos, sin, fused.plan, mode, sink, prefill=sink is not None)
+            ctx = DecoderCtx()
+            ctx.native, ctx.ws, ctx.mode, ctx.plan = True, ws, mode, fused.plan
+            ctx.cos, ctx.sin, ctx.src_index, ctx.layers = cos, sin, src_index, None
+            return h, (ctx if save else None)
+        if isinstance(kv_sink, dict):     # composed-attention path: the sink as per-layer copies
+            kd, n_, pl_ = kv_sink, kv_sink["n"], kv_sink["p_len"]
+
+            def kv_sink(layer, qkv):
+                kv = qkv.view(n_, pl_, nq + 2 * nkv, hd)
+                kd["kp"][layer, :n_, :pl_].copy_(kv[:, :, nq:nq + nkv])
+                kd["vp"][layer, :n_, :pl_].copy_(kv[:, :, nq + nkv:])
         h = ops.gather_rows(p["embed_tokens.weight"], src_index, alt=image_embeds)
         ctx = DecoderCtx()
+        ctx.native = False
         ctx.layers, ctx.attn, ctx.cos, ctx.sin, ctx.src_index = [], attn, cos, sin, src_index
         for i in range(t.num_layers):
             if save and self.recompute:
@@ -336,6 +368,11 @@ class VLM:
         """dh [B*T, H] bf16 (consumed in place). Returns d(image embeddings) fp32 [n_image_rows, H] or None."""
         t, p, g = self.cfg.text, self.p, self.g
         I, nq, nkv, hd = t.intermediate_size, t.num_heads, t.num_kv_heads, t.head_dim
+        if getattr(ctx, "native", False):
+            dimg = torch.zeros(n_image_rows, t.hidden_size, dtype=f32, device=self.device) if n_image_rows > 0 else None
+            self.native.decoder_bwd(dh, ctx.src_index, ctx.cos, ctx.sin, ctx.plan, ctx.ws, ctx.mode, dimg, self.on_layer_grad_ready)
+            ctx.ws = None
+            return dimg
         for i in reversed(range(t.num_layers)):
             b = f"layers.{i}."
             if len(ctx.layers[i]) == 1:       # recompute this layer's activations from its saved input
@@ -453,12 +490,12 @@ class VLM:
                 img, vctx = self.vision_forward(batch["pixel_values"], batch["grid"], save=save)
         attn = batch["attn"] if batch.get("shared") else self.full_attention(batch["B"], batch["T"])
         h, dctx = self.decoder_forward(batch["src_index"], img, attn, batch["cos"], batch["sin"], save=save)
-        hsel = ops.gather_rows(h, sel_index)
-        hn, rf = ops.rmsnorm_fwd(hsel, self.p["norm.weight"], self.cfg.text.rms_norm_eps, save_rstd=save)
-        logp, lse = ops.logprob_fwd(hn, self.params.lm_head, labels, temperature)
+        # final norm + fused lm_head -> log-softmax -> gather in one C call (iadr1_logprob_fwd); its workspace keeps what the
+        # backward needs (selected rows, their norm, the row log-sum-exp)
+        logp, hws = self.native.logprob_fwd(h, sel_index, labels, temperature, for_backward=save)
         ctx = None
         if save:
-            ctx = dict(vctx=vctx, dctx=dctx, hsel=hsel, hn=hn, rf=rf, lse=lse, labels=labels, sel_index=sel_index,
+            ctx = dict(vctx=vctx, dctx=dctx, hws=hws, labels=labels, sel_index=sel_index,
                        temperature=temperature, N=attn.n_tokens, n_img=batch["n_img_tokens"],
                        dimg_sink=dimg_sink if image_embeds is not None else None)
         return logp, ctx
@@ -466,13 +503,10 @@ class VLM:
     def logprobs_backward(self, dlogp: torch.Tensor, ctx: dict):
         """Back-propagates d(loss)/d(logp) [M] through lm_head, decoder and vision tower into the fp32 grad buffer."""
         t = self.cfg.text
-        dhn = ops.logprob_bwd(dlogp, ctx["hn"], self.params.lm_head, ctx["labels"], ctx["lse"], self.params.lm_head_grad,
-                              ctx["temperature"])
-        dhsel = torch.empty_like(dhn)
-        ops.rmsnorm_bwd(dhn, ctx["hsel"], self.p["norm.weight"], ctx["rf"], dhsel, self.g["norm.weight"], add_dx=False)
-        # scatter-ADD back to token rows (the last prompt position is selected once per row in the shared layout)
-        dh32 = torch.zeros(ctx["N"], t.hidden_size, dtype=f32, device=self.device)
-        ops.scatter_add_rows(dhsel, ctx["sel_index"], dh32, None)
+        # lm_head / final-norm backward + scatter-ADD back to token rows (the last prompt position is selected once per row in
+        # the shared layout) in one C call (iadr1_logprob_bwd)
+        dh32 = self.native.logprob_bwd(dlogp, ctx["sel_index"], ctx["labels"], ctx["temperature"], ctx["hws"], ctx["N"])
+        ctx["hws"] = None
         dh = ops.cast_f32_bf16(dh32)
         dimg32 = self.decoder_backward(dh, ctx["dctx"], ctx["n_img"])
         if dimg32 is not None and ctx.get("dimg_sink") is not None:

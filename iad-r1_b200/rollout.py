@@ -93,6 +93,10 @@ class RolloutEngine:
         self.max_pos = p_max + c_max + 8
         self.cos_tab, self.sin_tab = decode_rope_table(t, self.max_pos, dev)
         self._graph = None
+        self._dstate = None
+        # the C++ decode step covers the default configuration; probe modes (IADR1_DECODE_*) keep the per-kernel Python body
+        self._native_ok = (self.gu_mode == "fused" and not self.co_resident and not self.no_bulk_red
+                           and os.environ.get("IADR1_DECODE_NATIVE", "1") != "0")
         self._seed = 0
         self.replays = 0            # graph replays so far (bench.py counts kernels = replays * kernels_per_step)
         self.kernels_per_step = 0
@@ -108,6 +112,10 @@ class RolloutEngine:
                no_bulk_red=self.no_bulk_red)
 
     def _head_and_sample(self, first: int):
+        if self._native_ok:
+            import ctypes as C
+            L.check(L.lib().iadr1_decode_head(self.vlm.native.handle, C.byref(self._native_state()), first, L.stream_ptr()), "decode_head")
+            return
         t, p, lib = self.cfg.text, self.vlm.p, L.lib()
         s = L.stream_ptr()
         L.check(lib.iadr1_rmsnorm_f32in(self.h.data_ptr(), p["norm.weight"].data_ptr(), self.xn.data_ptr(), self.R,
@@ -127,7 +135,26 @@ class RolloutEngine:
         finally:
             lib.iadr1_set_pdl(0)
 
+    def _native_state(self):
+        """ctypes view of the engine for the model-level C ABI (iadr1_decode_step / iadr1_decode_head)."""
+        if self._dstate is None:
+            from .native import DecodeState
+            c = self.cfg
+            self._dstate = DecodeState(
+                self.R, self.n_groups, self.p_max, self.c_max, -self.nsplit if self.attn_nw == 2 else self.nsplit, self.max_pos,
+                self.block_n, self.kp.data_ptr(), self.vp.data_ptr(), self.kc.data_ptr(), self.vc.data_ptr(),
+                self.state.data_ptr(), self.tok.data_ptr(), self.finished.data_ptr(), self.out_tokens.data_ptr(),
+                self.rope_delta.data_ptr(), self.row_plen.data_ptr(), self.row_group.data_ptr(), self.h.data_ptr(),
+                self.xn.data_ptr(), self.qkv.data_ptr(), self.attn.data_ptr(), self.part.data_ptr(), self.tickets.data_ptr(),
+                self.act.data_ptr(), self.logits.data_ptr(), self.cos_tab.data_ptr(), self.sin_tab.data_ptr(),
+                self.temperature, self.top_k, self.top_p, c.eos_token_id, c.pad_token_id, int(self.forbid_eos))
+        return self._dstate
+
     def _decode_step_body(self):
+        if self._native_ok:
+            import ctypes as C
+            L.check(L.lib().iadr1_decode_step(self.vlm.native.handle, C.byref(self._native_state()), L.stream_ptr()), "decode_step")
+            return
         t, p, lib = self.cfg.text, self.vlm.p, L.lib()
         R, H, I, nq, nkv, hd = self.R, t.hidden_size, t.intermediate_size, t.num_heads, t.num_kv_heads, t.head_dim
         s = L.stream_ptr()
@@ -208,10 +235,7 @@ class RolloutEngine:
             img = image_embeds if image_embeds is not None else vlm.vision_forward(batch["pixel_values"], batch["grid"], save=False)[0]
         nq, nkv, hd = t.num_heads, t.num_kv_heads, t.head_dim
 
-        def sink(layer, qkv):
-            kv = qkv.view(n, Pmax, nq + 2 * nkv, hd)
-            self.kp[layer, :n, :Pmax].copy_(kv[:, :, nq:nq + nkv])
-            self.vp[layer, :n, :Pmax].copy_(kv[:, :, nq + nkv:])
+        sink = dict(kp=self.kp, vp=self.vp, n=n, p_len=Pmax)      # every layer's post-rotary K / V -> shared-prefix cache
 
         h, _ = vlm.decoder_forward(batch["src_index"], img, vlm.full_attention(n, Pmax), batch["cos"], batch["sin"],
                                    save=False, kv_sink=sink)

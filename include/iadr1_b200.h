@@ -213,6 +213,74 @@ int iadr1_fmha_bwd(const void* qkv, const void* dout, const void* out, const flo
                    const int* k_items, int n_k_items, const int* k_sched, int n_k_cta, void* dqkv, float* delta, float* dkv32,
                    long long npad, float scale, int pv_n, void* stream);
 
+/* ==== model-level entry points ("B-inner"): one call per reference call site =======================
+ * Weights are registered ONCE by pointer under the names of the flat parameter store ("embed_tokens.weight",
+ * "layers.<i>.{qkv,o,gate_up,down,ln1,ln2}.weight", "layers.<i>.qkv.bias", "norm.weight", optional "lm_head.weight");
+ * grad_f32 (may be NULL for a frozen model) is the fp32 gradient view the backward accumulates into.
+ * Workspaces are caller-owned; *_workspace_bytes reports the size for a token count. One handle per process / GPU, calls
+ * serialised on the passed stream, no global state besides the thread-local error string.                            */
+typedef struct iadr1_model_cfg_t {
+  int vocab, hidden, inter, layers, nq, nkv, hd;   /* decoder geometry (HF config.json: vocab_size, hidden_size, ...)   */
+  float rms_eps;
+} iadr1_model_cfg_t;
+/* Device-resident tables of one token layout for the fused attention (built by the host, see iadr1_fmha_fwd / _bwd). */
+typedef struct iadr1_attn_plan_t {
+  const int* ranges; const int* q_items; int n_q; const int* sched_fwd; int n_cta_fwd; const int* sched_dq; int n_cta_dq;
+  const int* k_items; int n_k; const int* sched_kv; int n_cta_kv; long long npad; long long n_tokens;
+} iadr1_attn_plan_t;
+/* Rollout prefill: post-rotary K / V of prompt g (rows [g * p_len, (g + 1) * p_len) of the token stream) go to
+ * kp / vp [layer][group][p_max][nkv][hd]; layer_stride = elements between consecutive layers.                        */
+typedef struct iadr1_kv_sink_t { void* kp; void* vp; int n_groups; int p_len; int p_max; long long layer_stride; } iadr1_kv_sink_t;
+/* State of the in-rank rollout engine (all device pointers; R rows decode in lock-step, see the decode-step kernels). */
+typedef struct iadr1_decode_t {
+  int R, n_groups, p_max, c_max, nsplit, max_pos, block_n;
+  const void* kp; const void* vp; void* kc; void* vc;       /* [layers][n_groups][p_max][nkv][hd], [layers][R][c_max][nkv][hd] */
+  int* state; int* tok; int* finished; int* out_tokens; const int* rope_delta; const int* row_plen; const int* row_group;
+  float* h; void* xn; float* qkv; void* attn; float* part; int* tickets; void* act; float* logits;
+  const float* cos_tab; const float* sin_tab;
+  float temperature; int top_k; float top_p; int eos_id, pad_id, forbid_eos;
+} iadr1_decode_t;
+typedef void (*iadr1_layer_cb)(int layer, void* user);
+
+int iadr1_model_create(const iadr1_model_cfg_t* cfg, void** handle);
+int iadr1_model_destroy(void* handle);
+int iadr1_bind_weights(void* handle, const char* name, const void* param_bf16, float* grad_f32);
+/* Decoder stack over a flat token stream (replaces the decoder half of `model(**inputs).logits`,
+ * ref: train/stage_rl/trainer/sc_grpo_trainer.py:505; HF modeling_qwen2_5_vl.py:778-827 per layer).
+ * src_index[t] >= 0: token id, < 0: row -1 - src_index[t] of image_embeds. mode 0: forward only; 1: every activation the
+ * backward needs stays in the workspace; 2: only layer inputs stay (the backward recomputes each layer).
+ * *h_last points (inside the workspace) at the last hidden states [n_tokens][hidden] (pre final norm).               */
+int iadr1_decoder_workspace_bytes(void* handle, long long n_tokens, long long npad, int mode, long long* bytes);
+int iadr1_decoder_fwd(void* handle, const int* src_index, const void* image_embeds, long long n_tokens, const float* cos_t,
+                      const float* sin_t, const iadr1_attn_plan_t* plan, void* workspace, int mode,
+                      const iadr1_kv_sink_t* sink, void** h_last, void* stream);
+/* dh bf16 [n_tokens][hidden] is consumed in place; weight gradients accumulate into the bound fp32 views; dimg32 (may be
+ * NULL) receives d(image_embeds); on_layer_done(layer, user) fires on the host after layer `layer`'s kernels are enqueued
+ * (its weight gradients are then final in stream order: the trainer hands the range to iadr1_grad_allreduce).          */
+int iadr1_decoder_bwd(void* handle, void* dh, const int* src_index, const float* cos_t, const float* sin_t,
+                      const iadr1_attn_plan_t* plan, void* workspace, int mode, long long n_tokens, float* dimg32,
+                      iadr1_layer_cb on_layer_done, void* cb_user, void* stream);
+/* hidden -> selected-token log-prob through final norm + fused lm_head (never materialising [rows, vocab] logits in the
+ * forward): replaces `_get_per_token_logps` (ref: sc_grpo_trainer.py:505-514). The backward runs in the forward's workspace. */
+int iadr1_logprob_workspace_bytes(void* handle, long long m_rows, int backward, long long* bytes);
+int iadr1_logprob_fwd(void* handle, const void* h, const int* sel_index, const int* labels, long long m_rows, float temperature,
+                      void* workspace, float* logp, void* stream);
+int iadr1_logprob_bwd(void* handle, const float* dlogp, const int* sel_index, const int* labels, long long m_rows,
+                      float temperature, void* workspace, float* dh32, void* stream);
+/* SFT head: per-token cross-entropy nll = -log p(label) (HF ForCausalLMLoss; ref: llamafactory/train/sft/trainer.py:92-107). */
+int iadr1_ce_fwd(void* handle, const void* h, const int* sel_index, const int* labels, long long m_rows, void* workspace,
+                 float* nll, void* stream);
+int iadr1_ce_bwd(void* handle, const float* dnll, const int* sel_index, const int* labels, long long m_rows, void* workspace,
+                 float* dh32, void* stream);
+/* Rollout (replaces `self.llm.generate`, ref: sc_grpo_trainer.py:343-358, 667): prefill = forward-only decoder pass over the
+ * right-padded prompts that fills the shared-prefix KV cache; decode_head = final norm + lm_head + sampler on e->h;
+ * decode_step = one lock-step token for all R rows (the body the engine captures into a CUDA graph).                   */
+int iadr1_prefill(void* handle, const int* src_index, const void* image_embeds, long long n_tokens, const float* cos_t,
+                  const float* sin_t, const iadr1_attn_plan_t* plan, void* workspace, const iadr1_kv_sink_t* sink, void** h_last,
+                  void* stream);
+int iadr1_decode_head(void* handle, const iadr1_decode_t* e, int first, void* stream);
+int iadr1_decode_step(void* handle, const iadr1_decode_t* e, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

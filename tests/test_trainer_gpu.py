@@ -328,8 +328,11 @@ def test_activation_recompute_gives_the_same_gradient(cuda):
         tr.model.recompute = rc
         tr.params.zero_grad()
         lp, ctx = tr.model.logprobs_forward(batch, batch["sel_index"], batch["labels"])
+        assert ctx["dctx"].mode == (2 if rc else 1)
+        ws_bytes = ctx["dctx"].ws.numel()
         if rc:
-            assert all(len(x) == 1 for x in ctx["dctx"].layers), "only the layer inputs may stay resident"
+            assert ws_bytes < 0.8 * res_bytes, "only the layer inputs (+ one layer of scratch) may stay resident"
+        res_bytes = ws_bytes
         tr.model.logprobs_backward(torch.linspace(-1, 1, lp.numel(), device=cuda), ctx)
         torch.cuda.synchronize()
         res.append((lp.clone(), tr.params.grad_flat.clone()))
