@@ -256,11 +256,19 @@ class PASFTTrainer(TrainerCore):
         per_rank = len(self.train_dataset) // self.world
         steps_per_epoch = max(1, per_rank // (bs * GA))
         self.state.max_steps = a.max_steps if a.max_steps > 0 else int(math.ceil(a.num_train_epochs * steps_per_epoch))
+        if per_rank < bs * GA:
+            raise ValueError(f"this rank's shard holds {per_rank} examples, one optimizer step needs "
+                             f"per_device_train_batch_size * gradient_accumulation_steps = {bs * GA}")
         t0, epoch, losses = time.time(), 0, []
+        skip = 0
+        resume = resume_from_checkpoint or a.resume_from_checkpoint
+        if resume:
+            self.load_checkpoint(resume)
+            epoch, skip = self.state.global_step // steps_per_epoch, self.state.global_step % steps_per_epoch
         while self.state.global_step < self.state.max_steps:
             order = self._epoch_order(epoch)
             win = bs * GA
-            for w in range(0, len(order) - win + 1, win):
+            for w in range(skip * win, len(order) - win + 1, win):
                 encs = [encode_supervised_example(self.train_dataset[j], self.processing_class, a.cutoff_len, a.image_dir,
                                                   a.image_resolution, cfg=self.cfg) for j in order[w:w + win]]
                 n_items = max(1, sum(int((e["labels"][1:] != IGNORE_INDEX).sum()) for e in encs))
@@ -275,10 +283,11 @@ class PASFTTrainer(TrainerCore):
                               "learning_rate": self._last_lr, "epoch": round(self.state.epoch, 4)})
                     losses = []
                 if a.save_strategy == "steps" and a.save_steps and self.state.global_step % max(1, int(a.save_steps)) == 0:
-                    self.save_model(os.path.join(a.output_dir, f"checkpoint-{self.state.global_step}"))
+                    self.save_checkpoint(os.path.join(a.output_dir, f"checkpoint-{self.state.global_step}"))
                 if self.state.global_step >= self.state.max_steps:
                     break
             epoch += 1
+            skip = 0
         self.flush_timers()
         return {"global_step": self.state.global_step, "train_runtime": time.time() - t0}
 

@@ -459,13 +459,24 @@ class SCGRPOTrainer(TrainerCore):
         per_rank = len(self.train_dataset) // self.world
         steps_per_epoch = max(1, per_rank // (bs * GA))
         self.state.max_steps = a.max_steps if a.max_steps > 0 else int(math.ceil(a.num_train_epochs * steps_per_epoch))
+        if per_rank < bs * GA:
+            raise ValueError(f"this rank's shard holds {per_rank} examples, one optimizer step needs "
+                             f"per_device_train_batch_size * gradient_accumulation_steps = {bs * GA}")
         t_start = time.time()
         epoch = 0
         tr_loss = []
+        skip_windows = 0
+        resume = resume_from_checkpoint or a.resume_from_checkpoint
+        if resume:
+            # continue where the checkpoint stopped: same epoch order (seeded), the windows already consumed are skipped
+            self.load_checkpoint(resume)
+            n_iter0 = max(1, a.num_iterations) if a.loss_mode == "clip" else 1
+            windows_done = self.state.global_step // n_iter0
+            epoch, skip_windows = windows_done // steps_per_epoch, windows_done % steps_per_epoch
         while self.state.global_step < self.state.max_steps:
             order = self._epoch_order(epoch)
             micro = [order[i:i + bs] for i in range(0, len(order) - bs + 1, bs)]
-            for w in range(0, len(micro) - GA + 1, GA):
+            for w in range(skip_windows * GA, len(micro) - GA + 1, GA):
                 window = [[self.train_dataset[j] for j in mb] for mb in micro[w:w + GA]]
                 if a.batched_rollout:
                     self.prepare_window([ex for mb in window for ex in mb])
@@ -488,10 +499,11 @@ class SCGRPOTrainer(TrainerCore):
                     self.log({"loss": loss_val, "grad_norm": float(self._grad_norm_dev.item()),
                               "learning_rate": self._last_lr, "epoch": round(self.state.epoch, 4)})
                 if a.save_strategy == "steps" and a.save_steps and self.state.global_step % max(1, int(a.save_steps)) == 0:
-                    self.save_model(os.path.join(a.output_dir, f"checkpoint-{self.state.global_step}"))
+                    self.save_checkpoint(os.path.join(a.output_dir, f"checkpoint-{self.state.global_step}"))
                 if self.state.global_step >= self.state.max_steps:
                     break
             epoch += 1
+            skip_windows = 0
         self.flush_timers()
         runtime = time.time() - t_start
         self.state.log_history.append({"train_runtime": runtime, "step": self.state.global_step})

@@ -211,6 +211,55 @@ class TrainerCore:
         if self.is_main:
             print(json.dumps({k: (round(v, 6) if isinstance(v, float) else v) for k, v in logs.items()}), flush=True)
 
+    # ---- checkpoints with optimizer state (resume) ----------------------------------------------------------------------
+    def save_checkpoint(self, ckpt_dir: str):
+        """`checkpoint-<step>` directory: HF-layout weights (save_model) + what a resume needs - fp32 master weights, both
+        Adam moments, the optimizer / scheduler counters and the trainer state (what the reference gets from the HF Trainer +
+        DeepSpeed checkpoints behind `--save_steps`, ref: scripts/train/SC_GRPO/SC_GRPO_Qwen_Instruct_2_5_VL_3B.sh:60). Every
+        rank holds identical optimizer state under plain data parallel, so rank 0 writes it."""
+        self.save_model(ckpt_dir)
+        if self.is_main:
+            ps = self.params
+            torch.save({"master": ps.master, "exp_avg": ps.exp_avg, "exp_avg_sq": ps.exp_avg_sq}, os.path.join(ckpt_dir, "optimizer.pt"))
+            state = {"global_step": self.state.global_step, "epoch": self.state.epoch, "opt_step": self._opt_step,
+                     "rollout_calls": getattr(self, "_rollout_calls", 0), "log_history": self.state.log_history,
+                     "max_steps": self.state.max_steps, "numel": ps.numel, "moment_dtype": str(ps.exp_avg.dtype)}
+            with open(os.path.join(ckpt_dir, "trainer_state.json"), "w") as f:
+                json.dump(state, f)
+            limit = getattr(self.args, "save_total_limit", None)
+            if limit:      # keep the newest `save_total_limit` checkpoints (HF Trainer semantics)
+                import re
+                import shutil
+                root = os.path.dirname(os.path.abspath(ckpt_dir))
+                found = sorted((int(m.group(1)), d) for d in os.listdir(root) if (m := re.fullmatch(r"checkpoint-(\d+)", d)))
+                for _, d in found[:-int(limit)]:
+                    shutil.rmtree(os.path.join(root, d), ignore_errors=True)
+        if self.world > 1:
+            torch.distributed.barrier()
+
+    def load_checkpoint(self, ckpt_dir: str):
+        """Restore weights are NOT re-read here (construct the trainer on the checkpoint directory or on the same initial
+        model): this restores master weights (and from them the bf16 working copy), moments, counters and state."""
+        path = os.path.join(ckpt_dir, "optimizer.pt")
+        if not os.path.isfile(path):
+            raise FileNotFoundError(f"{ckpt_dir} holds no optimizer.pt: not a resumable checkpoint (save_strategy='steps' writes them)")
+        with open(os.path.join(ckpt_dir, "trainer_state.json")) as f:
+            st = json.load(f)
+        ps = self.params
+        if st["numel"] != ps.numel:
+            raise ValueError(f"checkpoint has {st['numel']} parameters, the model {ps.numel}")
+        blob = torch.load(path, map_location=self.device, weights_only=True)
+        ps.master.copy_(blob["master"])
+        ps.exp_avg.copy_(blob["exp_avg"].to(ps.exp_avg.dtype))
+        ps.exp_avg_sq.copy_(blob["exp_avg_sq"].to(ps.exp_avg_sq.dtype))
+        ps.flat.copy_(ps.master.to(torch.bfloat16))
+        self.state.global_step, self.state.epoch = int(st["global_step"]), float(st["epoch"])
+        self.state.log_history = list(st.get("log_history", []))
+        self._opt_step = int(st["opt_step"])
+        if hasattr(self, "_rollout_calls"):
+            self._rollout_calls = int(st.get("rollout_calls", 0))
+        return st
+
     def save_model(self, output_dir: Optional[str] = None, _internal_call: bool = False):
         output_dir = output_dir or self.args.output_dir
         if self.is_main:

@@ -339,3 +339,40 @@ def test_activation_recompute_gives_the_same_gradient(cuda):
     assert torch.equal(res[0][0], res[1][0])
     rel = ((res[0][1] - res[1][1]).norm() / res[0][1].norm()).item()
     assert rel < 1e-5, rel
+
+
+def test_resume_from_checkpoint_continues_the_run(cuda, tmp_path):
+    """`--save_steps` checkpoints carry fp32 master weights, Adam moments and the step counters (trainer_base.save_checkpoint);
+    `train(resume_from_checkpoint=...)` continues with the same data order, learning-rate schedule and optimizer state: the
+    resumed run ends where the uninterrupted one does (PA-SFT: no sampling, so up to fp32 summation order)."""
+    import os
+    from iad_r1_b200.config import tiny_config
+    from iad_r1_b200.sft_trainer import PASFTTrainer, SFTArguments
+    from iad_r1_b200.synthetic import SyntheticProcessor, synthetic_image
+    cfg = tiny_config("qwen2_5_vl")
+    data = [{"messages": [{"role": "user", "content": "<image>Is there a defect in the image?"},
+                          {"role": "assistant", "content": f"<think> region {i} looks scratched </think> <answer> yes </answer>"}],
+             "images": [synthetic_image(i, 112)]} for i in range(6)]
+
+    def make(out, **kw):
+        args = SFTArguments(output_dir=str(out), do_train=True, learning_rate=2e-3, lr_scheduler_type="cosine", warmup_steps=1,
+                            weight_decay=0.1, gradient_accumulation_steps=2, logging_steps=1, max_steps=3, cutoff_len=512,
+                            bf16=True, **kw)
+        return PASFTTrainer(cfg, args, train_dataset=data, processing_class=SyntheticProcessor(cfg))
+
+    full = make(tmp_path / "full", save_strategy="steps", save_steps=2)
+    full.train()
+    ckpt = os.path.join(str(tmp_path / "full"), "checkpoint-2")
+    assert os.path.isfile(os.path.join(ckpt, "optimizer.pt")) and os.path.isfile(os.path.join(ckpt, "trainer_state.json"))
+    resumed = make(tmp_path / "resumed", save_strategy="no")
+    resumed.train(resume_from_checkpoint=ckpt)
+    assert resumed.state.global_step == 3 and resumed._opt_step == 3
+    d = (resumed.params.master - full.params.master).abs().max().item()
+    moved = (full.params.master - make(tmp_path / "init", save_strategy="no").params.master).abs().max().item()
+    print(f"\nresume: max |master_resumed - master_uninterrupted| = {d:.2e} (parameters moved by up to {moved:.2e})")
+    assert d <= 1e-3 * moved + 1e-7
+    l_full = [l["loss"] for l in full.state.log_history if "loss" in l]
+    l_res = [l["loss"] for l in resumed.state.log_history if "loss" in l]
+    assert len(l_res) == 3 and abs(l_res[-1] - l_full[-1]) < 1e-3
+    with pytest.raises(FileNotFoundError):
+        make(tmp_path / "bad", save_strategy="no").train(resume_from_checkpoint=str(tmp_path / "init"))
