@@ -105,79 +105,47 @@ def load_sharegpt_dataset(name: str, dataset_dir: str = "data") -> list:
         return json.load(f)
 
 
-def infer_seqlen(source_len: int, target_len: int, cutoff_len: int):
-    """Lengths of one (prompt, answer) turn after truncation to `cutoff_len` tokens: a short answer keeps all of itself
-    and the prompt is cut; a short prompt keeps all of itself and the answer is cut; otherwise both shrink in proportion
-    (ref: train/stage_sft/llamafactory/data/processors/processor_utils.py:51-65, KATs in tests/test_host_cpu.py)."""
-    if target_len * 2 < cutoff_len:
-        max_target = cutoff_len
-    elif source_len * 2 < cutoff_len:
-        max_target = cutoff_len - source_len
-    else:
-        max_target = int(cutoff_len * (target_len / (source_len + target_len)))
-    new_target = min(max_target, target_len)
-    new_source = min(max(cutoff_len - new_target, 0), source_len)
-    return new_source, new_target
+from .sft_data import infer_seqlen  # noqa: E402,F401  (re-exported: tests pin it with the reference function's outputs)
 
 
 def encode_supervised_example(example: dict, processor, cutoff_len: int, image_dir: Optional[str], image_resolution: int,
-                              cfg=None):
-    """messages -> (input_ids [T], labels [T] with IGNORE_INDEX outside assistant turns, pixel_values, grid_thw).
-    Restates processors/supervised.py:34-88 for the multimodal single-image layout used by Expert-AD stage 1."""
-    from PIL import Image
-    images = []
-    for im in example.get("images", []) or []:
-        if isinstance(im, str):
-            path = os.path.join(image_dir, im) if image_dir and os.path.isfile(os.path.join(image_dir, im)) else im
-            im = Image.open(path)   # data/aligner.py:52-53: join with image_dir when the joined file exists
-        if im.width * im.height > image_resolution:   # mm_plugin.py:108-123 (Q16): NEAREST pre-shrink
-            f = math.sqrt(image_resolution / (im.width * im.height))
-            im = im.resize((int(im.width * f), int(im.height * f)), resample=Image.NEAREST)
-        images.append(im.convert("RGB"))
-    msgs = []
-    for m in example["messages"]:
-        content = m["content"]
-        if isinstance(content, str) and "<image>" in content:
-            parts = content.split("<image>")
-            c = []
-            for i, ptxt in enumerate(parts):
-                if i > 0:
-                    c.append({"type": "image"})
-                if ptxt:
-                    c.append({"type": "text", "text": ptxt})
-            content = c
-        msgs.append({"role": m["role"], "content": content})
-
-    def tok(upto, gen):
-        text = processor.apply_chat_template(msgs[:upto], tokenize=False, add_generation_prompt=gen)
-        return processor(text=[text], images=images if images else None, return_tensors="pt", padding=True,
-                         padding_side="right", add_special_tokens=False)
-
-    full = tok(len(msgs), False)
-    ids = full["input_ids"][0]
-    # (source, target) token spans per assistant turn, then the reference's per-turn truncation: every turn gets what is
-    # left of cutoff_len, split between its prompt and its answer by infer_seqlen (processors/supervised.py:50-74)
-    pairs, prev_end = [], 0
-    for k, m in enumerate(msgs):
-        if m["role"] != "assistant":
-            continue
-        start = tok(k, True)["input_ids"].shape[1]
-        end = tok(k + 1, False)["input_ids"].shape[1]
-        pairs.append((prev_end, start, end))
-        prev_end = end
-    out_ids, out_labels, total = [], [], 0
-    for a, b, c in pairs:
-        if total >= cutoff_len:
-            break
-        src_len, tgt_len = infer_seqlen(b - a, c - b, cutoff_len - total)
-        out_ids += ids[a:a + src_len].tolist() + ids[b:b + tgt_len].tolist()
-        out_labels += [IGNORE_INDEX] * src_len + ids[b:b + tgt_len].tolist()
-        total += src_len + tgt_len
-    ids = torch.tensor(out_ids, dtype=torch.int64)
-    labels = torch.tensor(out_labels, dtype=torch.int64)
-    pv, grid = (full.get("pixel_values"), full["image_grid_thw"].tolist() if "image_grid_thw" in full else None) \
-        if cfg is None else vision_inputs_from_processor(cfg, full)
-    return dict(input_ids=ids.numpy().astype(np.int64), labels=labels.numpy().astype(np.int64), pixel_values=pv, grid_thw=grid)
+                              cfg=None, template: Optional[str] = None, device=None, gpu_preprocess: bool = False):
+    """One sharegpt row -> (input_ids [T], labels [T] with IGNORE_INDEX outside assistant answers, pixel_values, grid_thw)
+    through the native data path (sft_data.py): template -> `<image>` expansion -> per-turn token pairs -> truncation.
+    Multi-turn and multi-image rows are supported; the template defaults to the model family's
+    (ref: scripts/train/PA_SFT/*.sh:33)."""
+    from . import sft_data as D
+    from .geometry import image_token_count
+    family = cfg.family if cfg is not None else ("llava_onevision" if getattr(processor, "llava", False) else "qwen2_5_vl")
+    tpl = D.get_template(template, family)
+    images = D.load_images(example, image_dir, image_resolution, tpl.plugin)
+    pv, grid, seqlens = None, None, []
+    if images:
+        ip = processor.image_processor
+        if tpl.plugin == "qwen2_vl":
+            merge = getattr(ip, "merge_size", 2)
+            if gpu_preprocess and cfg is not None and device is not None:
+                from .preprocess import OPENAI_CLIP_MEAN, OPENAI_CLIP_STD, qwen_preprocess_gpu
+                size = getattr(ip, "size", None) or {}
+                pv, grid = qwen_preprocess_gpu(images, cfg.vision, device,
+                                               int(getattr(ip, "min_pixels", None) or size.get("shortest_edge") or 3136),
+                                               int(getattr(ip, "max_pixels", None) or size.get("longest_edge") or 12845056),
+                                               tuple(getattr(ip, "image_mean", None) or OPENAI_CLIP_MEAN),
+                                               tuple(getattr(ip, "image_std", None) or OPENAI_CLIP_STD))
+            else:
+                im = ip(images=images, return_tensors="pt")
+                pv, grid = im["pixel_values"], im["image_grid_thw"].tolist()
+            seqlens = [g[0] * g[1] * g[2] // merge ** 2 for g in grid]
+        else:
+            if cfg is None:
+                raise ValueError("the llava_next data path needs the model config (anyres token counts)")
+            im = ip(images=images, return_tensors="pt")
+            pv, grid = vision_inputs_from_processor(cfg, im)
+            seqlens = [image_token_count(cfg, g) for g in grid]
+    msgs = D.expand_image_placeholders(example["messages"], seqlens, tpl)
+    pair_ids = [(D.tokenize(processor, p), D.tokenize(processor, r)) for p, r in D.render_pairs(msgs, tpl)]
+    ids, labels = D.encode_pairs(pair_ids, cutoff_len)
+    return dict(input_ids=np.asarray(ids, dtype=np.int64), labels=np.asarray(labels, dtype=np.int64), pixel_values=pv, grid_thw=grid)
 
 
 class PASFTTrainer(TrainerCore):
@@ -270,7 +238,8 @@ class PASFTTrainer(TrainerCore):
             win = bs * GA
             for w in range(skip * win, len(order) - win + 1, win):
                 encs = [encode_supervised_example(self.train_dataset[j], self.processing_class, a.cutoff_len, a.image_dir,
-                                                  a.image_resolution, cfg=self.cfg) for j in order[w:w + win]]
+                                                  a.image_resolution, cfg=self.cfg, template=a.template, device=self.device,
+                                                  gpu_preprocess=True) for j in order[w:w + win]]
                 n_items = max(1, sum(int((e["labels"][1:] != IGNORE_INDEX).sum()) for e in encs))
                 step_loss = torch.zeros((), device=self.device)
                 for e in encs:

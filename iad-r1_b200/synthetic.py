@@ -12,7 +12,7 @@ import torch
 
 from .config import VLMConfig
 
-_SPECIAL = ("<|im_start|>", "<|im_end|>", "<|vision_start|>", "<|vision_end|>", "<|image_pad|>")
+_SPECIAL = ("<|im_start|>", "<|im_end|>", "<|vision_start|>", "<|vision_end|>", "<|image_pad|>", "<image>")
 _WORDS = ["<think>", "</think>", "<answer>", "</answer>", "<location>", "</location>", "<type>", "</type>", "yes", "no",
           "scratch", "top", "left", "center", "the", "defect", "surface", "image", "is", "a"]
 
@@ -50,7 +50,8 @@ class SyntheticProcessor:
         v = cfg.text.vocab_size
         self._lo, self._hi = min(1000, v // 4), min(100000, v - 64) if v > 2000 else v // 2
         self._special = {"<|vision_start|>": cfg.vision_start_token_id, "<|vision_end|>": cfg.vision_end_token_id,
-                         "<|image_pad|>": cfg.image_token_id, "<|im_end|>": cfg.eos_token_id, "<|im_start|>": self._lo - 1}
+                         "<|image_pad|>": cfg.image_token_id, "<image>": cfg.image_token_id,   # llava templates spell it <image>
+                         "<|im_end|>": cfg.eos_token_id, "<|im_start|>": self._lo - 1}
         self._word_ids = {w: self._lo + i for i, w in enumerate(_WORDS)}
         self._id_words = {i: w for w, i in self._word_ids.items()}
 

@@ -520,3 +520,57 @@ def test_smart_resize_matches_hf():
     for h, w in [(448, 448), (224, 224), (300, 500), (1000, 700), (90, 120), (37, 2000), (4000, 3000), (28, 28), (15, 15)]:
         for mx in (480000, 12845056):
             assert smart_resize(h, w, 28, 3136, mx) == tuple(hf_smart_resize(h, w, 28, 3136, mx)), (h, w, mx)
+
+
+def test_sft_native_data_path():
+    """PA-SFT data path without LLaMA-Factory (sft_data.py): chatml templates of `--template qwen2_vl` / `llava_next_qwen`
+    (ref: llamafactory/data/template.py:901-913, 1121-1133) with the default system prompt, `<image>` expansion per plugin
+    (mm_plugin.py:327-367, 850-897), multi-turn pairs with prompt masking, multi-image rows, pad-to-8 collation
+    (collator.py:79-161) and the reference's error messages for mismatched images."""
+    import numpy as np
+    from iad_r1_b200 import sft_data as D
+    from iad_r1_b200.config import tiny_config
+    from iad_r1_b200.sft_trainer import encode_supervised_example
+    from iad_r1_b200.synthetic import SyntheticProcessor, synthetic_image
+    tpl = D.get_template("qwen2_vl")
+    msgs = [{"role": "user", "content": "<image>first?"}, {"role": "assistant", "content": "yes"},
+            {"role": "user", "content": "and <image> this?"}, {"role": "assistant", "content": "no"}]
+    exp = D.expand_image_placeholders(msgs, [3, 2], tpl)
+    assert exp[0]["content"] == "<|vision_start|><|image_pad|><|image_pad|><|image_pad|><|vision_end|>first?"
+    assert exp[2]["content"] == "and <|vision_start|><|image_pad|><|image_pad|><|vision_end|> this?"
+    pairs = D.render_pairs(exp, tpl)
+    assert pairs[0][0] == ("<|im_start|>system\nYou are a helpful assistant.<|im_end|>\n<|im_start|>user\n" + exp[0]["content"] +
+                           "<|im_end|>\n<|im_start|>assistant\n")
+    assert pairs[0][1] == "yes<|im_end|>\n"
+    assert pairs[1] == ("<|im_start|>user\n" + exp[2]["content"] + "<|im_end|>\n<|im_start|>assistant\n", "no<|im_end|>\n")
+    sys_pairs = D.render_pairs([{"role": "system", "content": "Inspect parts."}] + exp[:2], tpl)
+    assert sys_pairs[0][0].startswith("<|im_start|>system\nInspect parts.<|im_end|>\n")
+    lt = D.get_template(None, "llava_onevision")
+    assert lt.name == "llava_next_qwen"
+    assert D.expand_image_placeholders(msgs[:2], [4], lt)[0]["content"] == "<image><image><image><image>first?"
+    for bad in ([3], [3, 2, 1]):
+        with pytest.raises(ValueError, match="number of <image> tokens|less than the number"):
+            D.expand_image_placeholders(msgs, bad, tpl)
+    with pytest.raises(ValueError):
+        D.get_template("llava_next_mistral")
+    ids, labels = D.encode_pairs([([1, 2, 3], [4, 5]), ([6], [7, 8, 9])], 100)
+    assert ids == [1, 2, 3, 4, 5, 6, 7, 8, 9] and labels == [-100, -100, -100, 4, 5, -100, 7, 8, 9]
+    col = D.collate([dict(input_ids=ids, labels=labels), dict(input_ids=[1, 2], labels=[-100, 2])], pad_token_id=0)
+    assert col["input_ids"].shape == (2, 16) and (col["labels"][1, 2:] == -100).all() and col["attention_mask"].sum() == 11
+    # end to end on the twins: two images in one conversation, two assistant turns
+    for fam in ("qwen2_5_vl", "llava_onevision"):
+        cfg = tiny_config(fam)
+        proc = SyntheticProcessor(cfg)
+        ex = {"messages": msgs, "images": [synthetic_image(0, 112), synthetic_image(1, 84)]}
+        enc = encode_supervised_example(ex, proc, 4096, None, 512 * 512, cfg=cfg)
+        ids, lab = enc["input_ids"], enc["labels"]
+        from iad_r1_b200.geometry import image_token_count
+        n_img = sum(image_token_count(cfg, g) for g in enc["grid_thw"])
+        assert (ids == cfg.image_token_id).sum() == n_img and len(enc["grid_thw"]) == 2
+        sup = lab != D.IGNORE_INDEX
+        assert (lab[sup] == ids[sup]).all() and (ids[sup] == cfg.eos_token_id).sum() == 2      # both answers + their <|im_end|>
+        assert not sup[ids == cfg.image_token_id].any()
+        # Q16: a large image is pre-shrunk with NEAREST below image_resolution pixels
+        big = synthetic_image(2, 448)
+        small = D.preshrink_image(big, 128 * 128, D.get_template(None, fam).plugin)
+        assert small.width * small.height <= 128 * 128 and D.preshrink_image(big, 10 ** 7, "llava_next").size == big.size
