@@ -1,7 +1,7 @@
 """Launches the dominant GEMM shapes of the step once each (after a warm-up pass) so that ONE `ncu --set full` capture
 yields DRAM traffic / tensor-pipe numbers per shape. Usage (GPU box, under ncu, -k regex:gemm_bf16 -s <warm> -c <n>):
     python tools/ncu_shapes.py            # prints the launch order it used
-Shapes are Qwen2.5-VL-3B, two groups per pass (M = 2 x 4393 tokens), and the R = 64 decode products."""
+Shapes are Qwen2.5-VL-3B, two groups per pass (M = 2 x 4393 tokens), and the decode products at ROWS (default 128) rows in flight."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -16,7 +16,7 @@ def rnd(*s):
     return (torch.randn(*s, device=dev) * 0.05).to(bf16)
 
 
-M, H, I, R, V = 8786 // 2 * 2, 2048, 11008, 64, 151936
+M, H, I, R, V = 8786 // 2 * 2, 2048, 11008, int(os.environ.get("ROWS", "128")), 151936
 x, w_gu, w_dn = rnd(M, H), rnd(2 * I, H), rnd(H, I)
 act, dy = rnd(M, I), rnd(M, 2 * I)
 gw = torch.zeros(2 * I, H, device=dev, dtype=f32)
@@ -30,9 +30,9 @@ cases = [
     ("train down fwd     [M,11008]x[2048,11008]^T", lambda: L.gemm(act, w_dn)),
     ("train gate_up dgrad [M,22016]x[22016,2048]", lambda: L.gemm(dy, w_gu.t())),
     ("train gate_up wgrad [22016,M]x[M,2048] f32 accumulate", lambda: L.gemm(dy.t(), x.t(), out=gw, accumulate=True)),
-    ("decode gate_up+SwiGLU R=64", lambda: L.gemm_swiglu(w_gu, xr, actr, block_n=64)),
-    ("decode down stream... split-K bulk-reduce R=64", lambda: L.gemm(w_dn, ar, out=h32, trans_out=True, split_k=9, atomic=True, block_n=64, a_static=True)),
-    ("decode lm_head R=64", lambda: L.gemm(w_head, xr, out=logits, trans_out=True, block_n=64, a_static=True)),
+    (f"decode gate_up+SwiGLU R={R}", lambda: L.gemm_swiglu(w_gu, xr, actr, block_n=R)),
+    (f"decode down split-K bulk-reduce R={R}", lambda: L.gemm(w_dn, ar, out=h32, trans_out=True, split_k=9, atomic=True, block_n=R, a_static=True)),
+    (f"decode lm_head R={R}", lambda: L.gemm(w_head, xr, out=logits, trans_out=True, block_n=R, a_static=True)),
 ]
 if os.environ.get("TIME"):
     # A/B of the tile order on the training shapes (CUDA events, 10 back-to-back launches; operands >> L2)
