@@ -526,3 +526,279 @@ int iadr1_decode_step(void* handle, const iadr1_decode_t* e, void* stream) {
 }
 
 }  // extern "C"
+
+// =====================================================================================================================
+// vision towers (Qwen2.5-VL: RMSNorm + SwiGLU + windowed / full attention; Qwen2-VL: LayerNorm + quick-GELU MLP, full
+// attention; SigLIP under LLaVA-OneVision: learned positions, LayerNorm, tanh-GELU MLP, projector + anyres packing):
+// patch embedding -> blocks -> merger / projector as one call each way. HF: modeling_qwen2_5_vl.py:455-518,
+// modeling_qwen2_vl.py (VisionTransformer), modeling_siglip.py:116-186 + modeling_llava_onevision.py:137-156, 292-355.
+// =====================================================================================================================
+namespace iadr1 {
+
+struct VBlockBuf {
+  float* st1; void* xn; void* qkv; float* lse2; void* attn; void* x_mid; float* st2; void* xn2; void* gu; void* act;
+};
+struct VisionLayout {
+  std::vector<void*> x;            // x[i] = input of block i, x[depth] = tower output
+  std::vector<VBlockBuf> bb;       // per block (save) or one shared
+  void* pos; float* stq; void* xq; void* m1; void* a1; void* feat;       // embedding residual, merger / projector
+  void* dx; void* dact; void* dxn; void* dattn; void* dqkv; float* delta; float* dkv32; void* dm1; void* dfeat; float* dfeat32;
+  size_t bytes;
+};
+
+static VisionLayout vision_layout(const iadr1_model_cfg_t& c, long long N, long long n_out, long long npad, int save, void* base) {
+  Arena a(base);
+  VisionLayout L;
+  const long long E = c.v_hidden, Ip = c.v_inter, W1 = c.v_kind == 0 ? 2 * Ip : Ip, Ho = c.v_out_hidden, unit = c.v_merge_unit;
+  L.x.resize(c.v_depth + 1);
+  if (save) {
+    for (int i = 0; i <= c.v_depth; ++i) L.x[i] = a.take(N * E * 2);
+  } else {
+    void* p0 = a.take(N * E * 2);
+    void* p1 = a.take(N * E * 2);
+    for (int i = 0; i <= c.v_depth; ++i) L.x[i] = (i & 1) ? p1 : p0;
+  }
+  const int nb = save ? c.v_depth : 1;
+  for (int i = 0; i < nb; ++i) {
+    VBlockBuf b;
+    b.st1 = static_cast<float*>(a.take(2 * N * 4));
+    b.xn = a.take(N * E * 2);
+    b.qkv = a.take(N * 3 * E * 2);
+    b.lse2 = static_cast<float*>(a.take((size_t)c.v_heads * npad * 4));
+    b.attn = a.take(N * E * 2);
+    b.x_mid = a.take(N * E * 2);
+    b.st2 = static_cast<float*>(a.take(2 * N * 4));
+    b.xn2 = a.take(N * E * 2);
+    b.gu = a.take(N * W1 * 2);
+    b.act = a.take(N * Ip * 2);
+    L.bb.push_back(b);
+  }
+  L.pos = c.v_kind == 2 ? a.take(N * E * 2) : nullptr;
+  L.stq = static_cast<float*>(a.take(2 * N * 4));
+  L.xq = a.take(N * E * 2);
+  const long long Mm = c.v_kind == 2 ? N : N / unit, Km = c.v_kind == 2 ? Ho : unit * E;      // merger rows / fc1 width
+  L.m1 = a.take(Mm * Km * 2);
+  L.a1 = a.take(Mm * Km * 2);
+  L.feat = a.take(Mm * Ho * 2);
+  L.dx = L.dact = L.dxn = L.dattn = L.dqkv = L.dm1 = L.dfeat = nullptr;
+  L.delta = L.dkv32 = L.dfeat32 = nullptr;
+  if (save) {
+    L.dx = a.take(N * E * 2);
+    L.dact = a.take(N * Ip * 2);
+    L.dxn = a.take(N * E * 2);
+    L.dattn = a.take(N * E * 2);
+    L.dqkv = a.take(N * 3 * E * 2);
+    L.delta = static_cast<float*>(a.take((size_t)c.v_heads * npad * 4));
+    L.dkv32 = static_cast<float*>(a.take((size_t)N * 2 * E * 4));
+    L.dm1 = a.take(Mm * Km * 2);
+    L.dfeat = a.take(Mm * Ho * 2);
+    L.dfeat32 = c.v_kind == 2 ? static_cast<float*>(a.take((size_t)N * Ho * 4)) : nullptr;
+  }
+  (void)n_out;
+  L.bytes = a.off;
+  return L;
+}
+
+struct VBlockW {
+  const Weight *n1, *n1b, *qkv, *qkvb, *proj, *projb, *n2, *n2b, *w1, *w1b, *w2, *w2b;
+};
+static int vblock_weights(const Model& m, int i, VBlockW& w) {
+  const std::string b = "visual.blocks." + std::to_string(i) + ".";
+  const bool q25 = m.c.v_kind == 0;
+  w.n1 = m.find(b + "norm1.weight"); w.n1b = m.find(b + "norm1.bias");
+  w.qkv = m.find(b + "qkv.weight"); w.qkvb = m.find(b + "qkv.bias");
+  w.proj = m.find(b + "proj.weight"); w.projb = m.find(b + "proj.bias");
+  w.n2 = m.find(b + "norm2.weight"); w.n2b = m.find(b + "norm2.bias");
+  w.w1 = m.find(b + (q25 ? "gate_up.weight" : "fc1.weight")); w.w1b = m.find(b + (q25 ? "gate_up.bias" : "fc1.bias"));
+  w.w2 = m.find(b + (q25 ? "down.weight" : "fc2.weight")); w.w2b = m.find(b + (q25 ? "down.bias" : "fc2.bias"));
+  if (!w.n1 || !w.qkv || !w.qkvb || !w.proj || !w.projb || !w.n2 || !w.w1 || !w.w1b || !w.w2 || !w.w2b || (!q25 && (!w.n1b || !w.n2b)))
+    return set_error("vision block %d: weights not bound", i);
+  return 0;
+}
+
+static int vnorm_fwd(const iadr1_model_cfg_t& c, const void* x, const Weight* w, const Weight* b, void* y, float* st, long long N,
+                     cudaStream_t s) {
+  const int E = c.v_hidden;
+  if (c.v_kind == 0) return iadr1_rmsnorm_fwd(x, w->p, y, st, N, E, E, E, c.v_eps, s);
+  return iadr1_layernorm_fwd(x, w->p, b->p, y, st, st + N, N, E, E, c.v_eps, s);
+}
+static int vnorm_bwd(const iadr1_model_cfg_t& c, const void* dy, const void* x, const Weight* w, const Weight* b, const float* st,
+                     void* dx, long long N, int add, cudaStream_t s) {
+  const int E = c.v_hidden;
+  if (c.v_kind == 0) return iadr1_rmsnorm_bwd(dy, x, w->p, st, dx, w->g, N, E, E, add, s);
+  return iadr1_layernorm_bwd(dy, x, w->p, st, st + N, dx, w->g, b->g, N, E, E, add, s);
+}
+// y = x @ W^T + b (+ residual) with the bias gradient as a column sum in the backward
+static int vlinear_bwd(const void* dy, const void* x, const Weight* W, const Weight* b, void* dx, long long M, int N, int K,
+                       cudaStream_t s) {
+  if (dx) TRY(linear_dgrad(dy, W->p, dx, M, N, K, s));
+  TRY(linear_wgrad(dy, x, W->g, M, N, K, s));
+  if (b && b->g) TRY(iadr1_colsum(dy, b->g, M, N, N, s));
+  return 0;
+}
+
+}  // namespace iadr1
+
+extern "C" {
+
+int iadr1_vision_workspace_bytes(void* handle, long long n_patches, long long n_out, long long npad, int save, long long* bytes) {
+  if (!handle || !bytes) return set_error("vision_workspace_bytes: null argument");
+  const iadr1_model_cfg_t& c = static_cast<Model*>(handle)->c;
+  if (c.v_kind < 0) return set_error("vision: the model was created without a vision tower");
+  *bytes = (long long)vision_layout(c, n_patches, n_out, npad, save, nullptr).bytes;
+  return 0;
+}
+
+int iadr1_vision_fwd(void* handle, const void* pixel_values, const iadr1_vision_geom_t* geo, void* workspace, int save, void* out,
+                     void* stream) {
+  if (!handle || !geo || !workspace || !out) return set_error("vision_fwd: null argument");
+  Model& m = *static_cast<Model*>(handle);
+  const iadr1_model_cfg_t& c = m.c;
+  if (c.v_kind < 0) return set_error("vision: the model was created without a vision tower");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long long N = geo->n_patches;
+  const int E = c.v_hidden, nh = c.v_heads, hd = E / nh, Ip = c.v_inter, W1 = c.v_kind == 0 ? 2 * Ip : Ip, Ho = c.v_out_hidden;
+  const int unit = c.v_merge_unit, Kp = c.v_patch_dim;
+  const iadr1_attn_plan_t* pf = geo->plan_full;
+  VisionLayout L = vision_layout(c, N, geo->n_out, pf->npad, save, workspace);
+  const Weight* pe = m.find("visual.patch_embed.weight");
+  if (!pe) return set_error("vision_fwd: visual.patch_embed.weight not bound");
+  const float scale = 1.f / sqrtf((float)hd);
+  // ---- patch embedding (Conv as one GEMM over patch rows)
+  if (c.v_kind == 2) {
+    const Weight *pb = m.find("visual.patch_embed.bias"), *pt = m.find("visual.pos_embed.weight");
+    if (!pb || !pt) return set_error("vision_fwd: SigLIP embedding weights not bound");
+    TRY(iadr1_gather_rows(pt->p, nullptr, geo->pos_index, L.pos, N, E, E, 0, E, s));       // position table tiled over the crops
+    TRY(linear_fwd(pixel_values, pe->p, L.x[0], N, E, Kp, pb->p, L.pos, s));
+  } else if (geo->window_index) {
+    TRY(linear_fwd(pixel_values, pe->p, L.x[c.v_depth], N, E, Kp, nullptr, nullptr, s));   // x[depth] as scratch
+    TRY(iadr1_gather_rows(L.x[c.v_depth], nullptr, geo->window_index, L.x[0], N / unit, unit * E, unit * E, 0, unit * E, s));
+  } else {
+    TRY(linear_fwd(pixel_values, pe->p, L.x[0], N, E, Kp, nullptr, nullptr, s));
+  }
+  // ---- blocks
+  for (int i = 0; i < c.v_depth; ++i) {
+    const VBlockBuf& b = save ? L.bb[i] : L.bb[0];
+    VBlockW w;
+    TRY(vblock_weights(m, i, w));
+    const bool full = c.v_kind != 0 || ((c.v_fullatt_mask >> i) & 1u);
+    const iadr1_attn_plan_t* plan = full ? pf : geo->plan_win;
+    if (!plan) return set_error("vision_fwd: missing attention plan for block %d", i);
+    TRY(vnorm_fwd(c, L.x[i], w.n1, w.n1b, b.xn, b.st1, N, s));
+    TRY(linear_fwd(b.xn, w.qkv->p, b.qkv, N, 3 * E, E, w.qkvb->p, nullptr, s));
+    if (geo->cos) TRY(iadr1_rope(b.qkv, geo->cos, geo->sin, N, 2 * nh, hd, 3 * E, 0, 0, s));
+    TRY(iadr1_fmha_fwd(b.qkv, N, nh, nh, hd, plan->ranges, plan->q_items, plan->n_q, plan->sched_fwd, plan->n_cta_fwd, b.attn,
+                       b.lse2, plan->npad, scale, 0, s));
+    TRY(linear_fwd(b.attn, w.proj->p, b.x_mid, N, E, E, w.projb->p, L.x[i], s));
+    TRY(vnorm_fwd(c, b.x_mid, w.n2, w.n2b, b.xn2, b.st2, N, s));
+    TRY(linear_fwd(b.xn2, w.w1->p, b.gu, N, W1, E, w.w1b->p, nullptr, s));
+    if (c.v_kind == 0) TRY(iadr1_act_mul_fwd(b.gu, b.act, N, Ip, 2 * Ip, Ip, Ip, 0, s));
+    else TRY(iadr1_act_mul_fwd(b.gu, b.act, N, Ip, Ip, -1, Ip, c.v_kind == 1 ? 2 : 3, s));
+    TRY(linear_fwd(b.act, w.w2->p, L.x[i + 1], N, E, Ip, w.w2b->p, b.x_mid, s));
+  }
+  const void* xl = L.x[c.v_depth];
+  const Weight *f1 = m.find("visual.merger.fc1.weight"), *f1b = m.find("visual.merger.fc1.bias");
+  const Weight *f2 = m.find("visual.merger.fc2.weight"), *f2b = m.find("visual.merger.fc2.bias");
+  if (!f1 || !f1b || !f2 || !f2b) return set_error("vision_fwd: merger / projector weights not bound");
+  if (c.v_kind == 2) {
+    // LlavaOnevisionMultiModalProjector on the last encoder layer's output, then anyres packing with image_newline
+    const Weight* nl = m.find("image_newline");
+    if (!nl) return set_error("vision_fwd: image_newline not bound");
+    TRY(linear_fwd(xl, f1->p, L.m1, N, Ho, E, f1b->p, nullptr, s));
+    TRY(iadr1_act_mul_fwd(L.m1, L.a1, N, Ho, Ho, -1, Ho, 1, s));
+    TRY(linear_fwd(L.a1, f2->p, L.feat, N, Ho, Ho, f2b->p, nullptr, s));
+    TRY(iadr1_gather_rows(L.feat, nl->p, geo->pack_index, out, geo->n_out, Ho, Ho, Ho, Ho, s));
+  } else {
+    const Weight *lq = m.find("visual.merger.ln_q.weight"), *lqb = m.find("visual.merger.ln_q.bias");
+    if (!lq || (c.v_kind == 1 && !lqb)) return set_error("vision_fwd: merger ln_q not bound");
+    TRY(vnorm_fwd(c, xl, lq, lqb, L.xq, L.stq, N, s));
+    const long long Mm = N / unit;
+    const int Km = unit * E;
+    TRY(linear_fwd(L.xq, f1->p, L.m1, Mm, Km, Km, f1b->p, nullptr, s));
+    TRY(iadr1_act_mul_fwd(L.m1, L.a1, Mm, Km, Km, -1, Km, 1, s));
+    if (geo->reverse_index) {
+      TRY(linear_fwd(L.a1, f2->p, L.feat, Mm, Ho, Km, f2b->p, nullptr, s));
+      TRY(iadr1_gather_rows(L.feat, nullptr, geo->reverse_index, out, Mm, Ho, Ho, 0, Ho, s));
+    } else {
+      TRY(linear_fwd(L.a1, f2->p, out, Mm, Ho, Km, f2b->p, nullptr, s));
+    }
+  }
+  return 0;
+}
+
+// d_out bf16 [n_out][out_hidden]; pixel_values as in the forward (the patch-embedding weight gradient needs them)
+int iadr1_vision_bwd(void* handle, const void* d_out, const void* pixel_values, const iadr1_vision_geom_t* geo, void* workspace,
+                     void* stream) {
+  if (!handle || !geo || !workspace || !d_out) return set_error("vision_bwd: null argument");
+  Model& m = *static_cast<Model*>(handle);
+  const iadr1_model_cfg_t& c = m.c;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long long N = geo->n_patches;
+  const int E = c.v_hidden, nh = c.v_heads, hd = E / nh, Ip = c.v_inter, W1 = c.v_kind == 0 ? 2 * Ip : Ip, Ho = c.v_out_hidden;
+  const int unit = c.v_merge_unit, Kp = c.v_patch_dim;
+  const iadr1_attn_plan_t* pf = geo->plan_full;
+  VisionLayout L = vision_layout(c, N, geo->n_out, pf->npad, 1, workspace);
+  const float scale = 1.f / sqrtf((float)hd);
+  const Weight *f1 = m.find("visual.merger.fc1.weight"), *f1b = m.find("visual.merger.fc1.bias");
+  const Weight *f2 = m.find("visual.merger.fc2.weight"), *f2b = m.find("visual.merger.fc2.bias");
+  const void* xl = L.x[c.v_depth];
+  if (c.v_kind == 2) {
+    const Weight* nl = m.find("image_newline");
+    // un-pack: dropped features get zero gradient, image_newline collects one row per feature-map row
+    if (cudaMemsetAsync(L.dfeat32, 0, (size_t)N * Ho * 4, s) != cudaSuccess) return set_error("vision_bwd: memset failed");
+    TRY(iadr1_scatter_add_rows(d_out, geo->pack_index, L.dfeat32, nl->g, geo->n_out, Ho, Ho, Ho, Ho, s));
+    TRY(iadr1_cast_f32_bf16(L.dfeat32, L.dfeat, N * Ho, s));
+    TRY(vlinear_bwd(L.dfeat, L.a1, f2, f2b, L.dm1, N, Ho, Ho, s));
+    TRY(iadr1_act_mul_bwd(L.dm1, L.m1, L.m1, N, Ho, Ho, -1, Ho, 1, s));
+    TRY(vlinear_bwd(L.m1, xl, f1, f1b, L.dx, N, Ho, E, s));
+  } else {
+    const Weight *lq = m.find("visual.merger.ln_q.weight"), *lqb = m.find("visual.merger.ln_q.bias");
+    const long long Mm = N / unit;
+    const int Km = unit * E;
+    const void* dfe = d_out;
+    if (geo->window_index) {      // inverse of the final un-permute
+      TRY(iadr1_gather_rows(d_out, nullptr, geo->window_index, L.dfeat, Mm, Ho, Ho, 0, Ho, s));
+      dfe = L.dfeat;
+    }
+    TRY(vlinear_bwd(dfe, L.a1, f2, f2b, L.dm1, Mm, Ho, Km, s));
+    TRY(iadr1_act_mul_bwd(L.dm1, L.m1, L.m1, Mm, Km, Km, -1, Km, 1, s));
+    TRY(vlinear_bwd(L.m1, L.xq, f1, f1b, L.dxn, Mm, Km, Km, s));      // dxn viewed [Mm, unit * E] = [N, E]
+    TRY(vnorm_bwd(c, L.dxn, xl, lq, lqb, L.stq, L.dx, N, 0, s));
+  }
+  for (int i = c.v_depth - 1; i >= 0; --i) {
+    const VBlockBuf& b = L.bb[i];
+    VBlockW w;
+    TRY(vblock_weights(m, i, w));
+    const bool full = c.v_kind != 0 || ((c.v_fullatt_mask >> i) & 1u);
+    const iadr1_attn_plan_t* plan = full ? pf : geo->plan_win;
+    TRY(vlinear_bwd(L.dx, b.act, w.w2, w.w2b, L.dact, N, E, Ip, s));
+    if (c.v_kind == 0) TRY(iadr1_act_mul_bwd(L.dact, b.gu, b.gu, N, Ip, 2 * Ip, Ip, Ip, 0, s));
+    else TRY(iadr1_act_mul_bwd(L.dact, b.gu, b.gu, N, Ip, Ip, -1, Ip, c.v_kind == 1 ? 2 : 3, s));
+    TRY(vlinear_bwd(b.gu, b.xn2, w.w1, w.w1b, L.dxn, N, W1, E, s));
+    TRY(vnorm_bwd(c, L.dxn, b.x_mid, w.n2, w.n2b, b.st2, L.dx, N, 1, s));
+    TRY(vlinear_bwd(L.dx, b.attn, w.proj, w.projb, L.dattn, N, E, E, s));
+    TRY(iadr1_fmha_bwd(b.qkv, L.dattn, b.attn, b.lse2, N, nh, nh, hd, plan->ranges, plan->q_items, plan->n_q, plan->sched_dq,
+                       plan->n_cta_dq, plan->k_items, plan->n_k, plan->sched_kv, plan->n_cta_kv, L.dqkv, L.delta, L.dkv32,
+                       plan->npad, scale, 0, s));
+    if (geo->cos) TRY(iadr1_rope(L.dqkv, geo->cos, geo->sin, N, 2 * nh, hd, 3 * E, 0, 1, s));
+    TRY(vlinear_bwd(L.dqkv, b.xn, w.qkv, w.qkvb, L.dxn, N, 3 * E, E, s));
+    TRY(vnorm_bwd(c, L.dxn, L.x[i], w.n1, w.n1b, b.st1, L.dx, N, 1, s));
+  }
+  const Weight* pe = m.find("visual.patch_embed.weight");
+  if (c.v_kind == 2) {
+    const Weight *pb = m.find("visual.patch_embed.bias"), *pt = m.find("visual.pos_embed.weight");
+    // x0 = patch_embed(px) + bias + pos[tile]: the table's gradient is the sum over crops
+    if (pt->g) TRY(iadr1_colsum(L.dx, pt->g, N / c.v_tokens_per_crop, c.v_tokens_per_crop * E, c.v_tokens_per_crop * E, s));
+    TRY(vlinear_bwd(L.dx, pixel_values, pe, pb, nullptr, N, E, Kp, s));
+  } else {
+    const void* dxe = L.dx;
+    if (geo->reverse_index) {
+      TRY(iadr1_gather_rows(L.dx, nullptr, geo->reverse_index, L.dxn, N / unit, unit * E, unit * E, 0, unit * E, s));
+      dxe = L.dxn;
+    }
+    TRY(linear_wgrad(dxe, pixel_values, pe->g, N, E, Kp, s));
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -329,6 +329,7 @@ class SiglipGeometry:
         lo = (np.arange(self.n_patches) // tpc * tpc).astype(np.int32)
         self.full_lo = torch.from_numpy(lo).to(device)
         self.full_hi = torch.from_numpy(lo + tpc).to(device)
+        self.pos_index = torch.from_numpy((np.arange(self.n_patches) % tpc).astype(np.int32)).to(device)   # learned-position row
 
 
 def siglip_geometry(cfg: VLMConfig, grid, device) -> SiglipGeometry:

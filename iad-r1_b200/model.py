@@ -76,9 +76,15 @@ class VLM:
         E, nh, hd, Ip = v.hidden_size, v.num_heads, v.head_dim, v.intermediate_padded
         unit = v.spatial_merge_size ** 2
         Np = geo.n_patches
+        q25_ = v.kind == "qwen2_5_vl"
         if pixel_values.shape[0] != Np:
             raise ValueError(f"pixel_values has {pixel_values.shape[0]} patches, image_grid_thw implies {Np}")
         px = pixel_values.to(device=self.device, dtype=bf16).contiguous()
+        if self._native_vision(hd):
+            # ONE call into the model-level C ABI (iadr1_vision_fwd): patch embedding, every block, merger
+            fa_full = ops.range_attention(geo, "full", geo.full_lo, geo.full_hi, nh, nh, hd)
+            fa_win = ops.range_attention(geo, "win", geo.win_lo, geo.win_hi, nh, nh, hd) if q25_ else None
+            return self._vision_native(px, geo, fa_full, fa_win, geo.n_tokens, save)
         x = ops.linear_fwd(px, p["visual.patch_embed.weight"])
         if geo.window_index is not None:
             x = ops.gather_rows(x.view(Np // unit, unit * E), geo.window_index).view(Np, E)
@@ -153,9 +159,26 @@ class VLM:
             ctx.x_last, ctx.stq, ctx.xq, ctx.m1, ctx.a1 = x, stq, xq, m1, a1
         return out, (ctx if save else None)
 
+    def _native_vision(self, hd: int) -> bool:
+        import os
+        return ops.F.supported(hd) and os.environ.get("IADR1_VISION", "native") != "python"
+
+    def _vision_native(self, px, geo, fa_full, fa_win, n_out, save):
+        cg = self.native.vision_geom(geo, fa_full.plan, fa_win.plan if fa_win is not None else None, n_out)
+        out, ws = self.native.vision_fwd(px, cg, fa_full.plan.npad, save)
+        if not save:
+            return out, None
+        ctx = VisionCtx()
+        ctx.native, ctx.geo, ctx.px, ctx.cgeom, ctx.ws = True, geo, px, cg, ws
+        return out, ctx
+
     def vision_backward(self, d_out: torch.Tensor, ctx: VisionCtx):
         """Accumulates vision-tower gradients into the fp32 grad buffer given d(image embeddings) bf16."""
         v, p, g, geo = self.cfg.vision, self.p, self.g, ctx.geo
+        if getattr(ctx, "native", False):
+            self.native.vision_bwd(d_out.contiguous(), ctx.px, ctx.cgeom, ctx.ws)
+            ctx.ws = None
+            return
         if v.kind == "siglip":
             return self._siglip_backward(d_out, ctx)
         E, nh, hd, Ip = v.hidden_size, v.num_heads, v.head_dim, v.intermediate_padded
@@ -231,6 +254,9 @@ class VLM:
         if v.patch_dim_padded != v.patch_dim:                      # K of the patch GEMM: 588 -> 592 (zero columns)
             px = torch.nn.functional.pad(px, (0, v.patch_dim_padded - v.patch_dim))
         px = px.contiguous()
+        if self._native_vision(hd):
+            fa = ops.range_attention(geo, "crops", geo.full_lo, geo.full_hi, nh, nh, hd)
+            return self._vision_native(px, geo, fa, None, geo.n_tokens, save)
         pos = p["visual.pos_embed.weight"].repeat(nc, 1)          # position table tiled over the crops (residual operand)
         x = ops.linear_fwd(px, p["visual.patch_embed.weight"], bias=p["visual.patch_embed.bias"], residual=pos)
         sh = ops.AttnShape(nc, tpc, nh, nh, hd, causal=False)     # attention within one crop

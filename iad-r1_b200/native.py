@@ -13,7 +13,10 @@ from . import lib as L
 
 class ModelCfg(C.Structure):
     _fields_ = [("vocab", C.c_int), ("hidden", C.c_int), ("inter", C.c_int), ("layers", C.c_int), ("nq", C.c_int),
-                ("nkv", C.c_int), ("hd", C.c_int), ("rms_eps", C.c_float)]
+                ("nkv", C.c_int), ("hd", C.c_int), ("rms_eps", C.c_float),
+                ("v_kind", C.c_int), ("v_depth", C.c_int), ("v_hidden", C.c_int), ("v_heads", C.c_int), ("v_inter", C.c_int),
+                ("v_out_hidden", C.c_int), ("v_patch_dim", C.c_int), ("v_merge_unit", C.c_int), ("v_tokens_per_crop", C.c_int),
+                ("v_fullatt_mask", C.c_uint), ("v_eps", C.c_float)]
 
 
 class AttnPlan(C.Structure):
@@ -41,6 +44,14 @@ class DecodeState(C.Structure):
                 ("pad_id", C.c_int), ("forbid_eos", C.c_int)]
 
 
+class VisionGeom(C.Structure):
+    _fields_ = [("n_patches", C.c_longlong), ("n_out", C.c_longlong), ("cos", C.c_void_p), ("sin", C.c_void_p),
+                ("window_index", C.c_void_p), ("reverse_index", C.c_void_p), ("plan_full", C.POINTER(AttnPlan)),
+                ("plan_win", C.POINTER(AttnPlan)), ("pos_index", C.c_void_p), ("pack_index", C.c_void_p)]
+
+
+V_KINDS = {"qwen2_5_vl": 0, "qwen2_vl": 1, "siglip": 2}
+
 LAYER_CB = C.CFUNCTYPE(None, C.c_int, C.c_void_p)
 
 
@@ -60,12 +71,17 @@ class NativeModel:
         t = cfg.text
         self.cfg, self.params = cfg, params
         self.handle = C.c_void_p()
+        v = cfg.vision
+        mask = 0
+        for i in v.fullatt_block_indexes:
+            mask |= 1 << i
         mc = ModelCfg(t.vocab_size, t.hidden_size, t.intermediate_size, t.num_layers, t.num_heads, t.num_kv_heads, t.head_dim,
-                      t.rms_norm_eps)
+                      t.rms_norm_eps, V_KINDS[v.kind], v.depth, v.hidden_size, v.num_heads, v.intermediate_padded,
+                      v.out_hidden_size, v.patch_dim_padded, v.spatial_merge_size ** 2,
+                      v.tokens_per_crop if v.kind == "siglip" else 0, mask,
+                      float(cfg.extra.get("vision_layer_norm_eps", 1e-6)))
         L.check(L.lib().iadr1_model_create(C.byref(mc), C.byref(self.handle)), "model_create")
         for name, w in params.p.items():
-            if name.startswith("visual.") or name == "image_newline":
-                continue
             g = params.g[name] if params.g is not None else None
             L.check(L.lib().iadr1_bind_weights(self.handle, name.encode(), w.data_ptr(), None if g is None else g.data_ptr()),
                     "bind_weights")
@@ -126,3 +142,32 @@ class NativeModel:
         L.check(L.lib().iadr1_logprob_bwd(self.handle, d.data_ptr(), sel_index.data_ptr(), labels.data_ptr(), int(sel_index.shape[0]),
                                           temperature, ws.data_ptr(), dh32.data_ptr(), L.stream_ptr()), "logprob_bwd")
         return dh32
+
+    # ---- vision tower ------------------------------------------------------------------------------------------------------
+    def vision_geom(self, geo, plan_full, plan_win, n_out: int) -> VisionGeom:
+        """ctypes view of a geometry object (geometry.VisionGeometry / SiglipGeometry) + its attention plans; cached on it."""
+        s = geo.__dict__.get("_cgeom")
+        if s is None:
+            def ptr(name):
+                t_ = getattr(geo, name, None)
+                return None if t_ is None else t_.data_ptr()
+            pf, pw = plan_struct(plan_full), (plan_struct(plan_win) if plan_win is not None else None)
+            s = VisionGeom(geo.n_patches, n_out, ptr("cos"), ptr("sin"), ptr("window_index"), ptr("reverse_index"), C.pointer(pf),
+                           C.pointer(pw) if pw is not None else None, ptr("pos_index"), ptr("pack_index"))
+            geo._cgeom = s
+        return s
+
+    def vision_fwd(self, px, cgeom: VisionGeom, npad: int, save: bool):
+        """px bf16 [n_patches, patch_dim_padded] -> (image embeddings bf16 [n_out, out_hidden], workspace)."""
+        nbytes = C.c_longlong()
+        L.check(L.lib().iadr1_vision_workspace_bytes(self.handle, cgeom.n_patches, cgeom.n_out, npad, int(save), C.byref(nbytes)),
+                "vision_workspace_bytes")
+        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=px.device)
+        out = torch.empty(cgeom.n_out, self.cfg.vision.out_hidden_size, dtype=torch.bfloat16, device=px.device)
+        L.check(L.lib().iadr1_vision_fwd(self.handle, px.data_ptr(), C.byref(cgeom), ws.data_ptr(), int(save), out.data_ptr(),
+                                         L.stream_ptr()), "vision_fwd")
+        return out, ws
+
+    def vision_bwd(self, d_out, px, cgeom: VisionGeom, ws):
+        L.check(L.lib().iadr1_vision_bwd(self.handle, d_out.data_ptr(), px.data_ptr(), C.byref(cgeom), ws.data_ptr(),
+                                         L.stream_ptr()), "vision_bwd")

@@ -222,6 +222,12 @@ int iadr1_fmha_bwd(const void* qkv, const void* dout, const void* out, const flo
 typedef struct iadr1_model_cfg_t {
   int vocab, hidden, inter, layers, nq, nkv, hd;   /* decoder geometry (HF config.json: vocab_size, hidden_size, ...)   */
   float rms_eps;
+  /* vision tower: v_kind -1 none, 0 qwen2_5_vl (RMSNorm, SwiGLU + bias, windowed / full attention), 1 qwen2_vl (LayerNorm,
+   * quick-GELU MLP), 2 siglip (LLaVA-OneVision: learned positions, LayerNorm, tanh-GELU MLP, projector + anyres packing).
+   * v_inter / v_patch_dim are the 8-element padded widths of the store; v_fullatt_mask bit i = block i attends the whole image */
+  int v_kind, v_depth, v_hidden, v_heads, v_inter, v_out_hidden, v_patch_dim, v_merge_unit, v_tokens_per_crop;
+  unsigned int v_fullatt_mask;
+  float v_eps;
 } iadr1_model_cfg_t;
 /* Device-resident tables of one token layout for the fused attention (built by the host, see iadr1_fmha_fwd / _bwd). */
 typedef struct iadr1_attn_plan_t {
@@ -241,6 +247,19 @@ typedef struct iadr1_decode_t {
   float temperature; int top_k; float top_p; int eos_id, pad_id, forbid_eos;
 } iadr1_decode_t;
 typedef void (*iadr1_layer_cb)(int layer, void* user);
+/* What the vision tower derives from the image grids (host-computed, device-resident; HF get_window_index / rot_pos_emb,
+ * modeling_qwen2_5_vl.py:382-453; pack_image_features, modeling_llava_onevision.py:292-355).                          */
+typedef struct iadr1_vision_geom_t {
+  long long n_patches;                 /* rows of pixel_values                                                       */
+  long long n_out;                     /* rows of the output: merged tokens (Qwen) / packed image tokens (LLaVA-OV)  */
+  const float* cos; const float* sin;  /* 2-D rotary tables fp32 [n_patches][head_dim]; NULL for SigLIP              */
+  const int* window_index;             /* Qwen2.5: merge units in window order [n_patches / unit]; else NULL         */
+  const int* reverse_index;            /* Qwen2.5: its inverse; else NULL                                            */
+  const iadr1_attn_plan_t* plan_full;  /* attention inside whole images / crops                                      */
+  const iadr1_attn_plan_t* plan_win;   /* attention inside windows (Qwen2.5); else NULL                              */
+  const int* pos_index;                /* SigLIP: row of the learned position table per patch                        */
+  const int* pack_index;               /* SigLIP: packed token -> projected feature row, or -1 = image_newline       */
+} iadr1_vision_geom_t;
 
 int iadr1_model_create(const iadr1_model_cfg_t* cfg, void** handle);
 int iadr1_model_destroy(void* handle);
@@ -260,6 +279,14 @@ int iadr1_decoder_fwd(void* handle, const int* src_index, const void* image_embe
 int iadr1_decoder_bwd(void* handle, void* dh, const int* src_index, const float* cos_t, const float* sin_t,
                       const iadr1_attn_plan_t* plan, void* workspace, int mode, long long n_tokens, float* dimg32,
                       iadr1_layer_cb on_layer_done, void* cb_user, void* stream);
+/* Vision tower + merger / projector (replaces `model.visual(pixel_values, grid_thw)` and the LLaVA-OneVision
+ * `get_image_features` + `pack_image_features`; HF modeling_qwen2_5_vl.py:455-518, modeling_llava_onevision.py:292-417).
+ * pixel_values bf16 [n_patches][v_patch_dim]; out bf16 [n_out][v_out_hidden]. save = 1 keeps what iadr1_vision_bwd needs.  */
+int iadr1_vision_workspace_bytes(void* handle, long long n_patches, long long n_out, long long npad, int save, long long* bytes);
+int iadr1_vision_fwd(void* handle, const void* pixel_values, const iadr1_vision_geom_t* geo, void* workspace, int save, void* out,
+                     void* stream);
+int iadr1_vision_bwd(void* handle, const void* d_out, const void* pixel_values, const iadr1_vision_geom_t* geo, void* workspace,
+                     void* stream);
 /* hidden -> selected-token log-prob through final norm + fused lm_head (never materialising [rows, vocab] logits in the
  * forward): replaces `_get_per_token_logps` (ref: sc_grpo_trainer.py:505-514). The backward runs in the forward's workspace. */
 int iadr1_logprob_workspace_bytes(void* handle, long long m_rows, int backward, long long* bytes);

@@ -226,3 +226,39 @@ def test_native_decoder_entry_points_match_python_layer_loop(cuda, monkeypatch):
     print(f"\nnative vs python layer loop: logp max diff {(lpn - lpc).abs().max().item():.2e}, grad rel diff {rel:.2e}; "
           f"host enqueue time per pass {tn:.2f} ms (C ABI) vs {tc:.2f} ms (per-kernel ctypes)")
     assert rel < 2e-2
+
+
+@pytest.mark.parametrize("family", ["qwen2_5_vl", "qwen2_vl", "llava_onevision"])
+def test_native_vision_entry_points_match_python_block_loop(cuda, monkeypatch, family):
+    """iadr1_vision_fwd / iadr1_vision_bwd (csrc/model.cu: patch embedding -> blocks -> merger / projector + packing as ONE
+    call each way) against the per-kernel Python block loop (IADR1_VISION=python) on the same weights and pixels: same image
+    embeddings and the same parameter gradients up to bf16 rounding, for all three towers (windowed Qwen2.5, LayerNorm +
+    quick-GELU Qwen2, SigLIP + projector + anyres packing)."""
+    from iad_r1_b200.config import tiny_config
+    from iad_r1_b200.model import VLM
+    from iad_r1_b200.params import ParamStore
+    fix = _load(family)
+    cfg = tiny_config(family)
+    px, grid = fix["pixel_values"], [tuple(fix["grid"])] * 2        # two images in one call
+    px = torch.cat([px, px.flip(0)])
+    res = {}
+    for mode in ("native", "python"):
+        monkeypatch.setenv("IADR1_VISION", mode)
+        ps = ParamStore(cfg, cuda, with_grads=True)
+        ps.load_hf_state_dict(fix["state_dict"])
+        vlm = VLM(cfg, ps)
+        out, ctx = vlm.vision_forward(px, grid, save=True)
+        assert bool(getattr(ctx, "native", False)) == (mode == "native")
+        torch.manual_seed(11)
+        d = (torch.randn(out.shape, device=cuda) * 0.05).to(torch.bfloat16)
+        vlm.vision_backward(d, ctx)
+        out_ns, _ = vlm.vision_forward(px, grid, save=False)       # the ping-pong (no-save) layout gives the same features
+        torch.cuda.synchronize()
+        assert torch.equal(out_ns, out)
+        res[mode] = (out.float().clone(), ps.grad_flat.clone())
+    monkeypatch.delenv("IADR1_VISION")
+    (on, gn), (op_, gp) = res["native"], res["python"]
+    assert (on - op_).abs().max().item() <= 2 ** -6 * op_.abs().max().item()
+    rel = ((gn - gp).norm() / gp.norm()).item()
+    print(f"\n{family}: native vision vs python block loop: out max diff {(on - op_).abs().max().item():.2e}, grad rel diff {rel:.2e}")
+    assert rel < 2e-2
