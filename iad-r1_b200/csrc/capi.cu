@@ -43,10 +43,12 @@ int iadr1_trace(int op, unsigned long long* out, int max_words) {
     iadr1::trace_install_decode(buf);
     iadr1::trace_install_gemm(buf);
     iadr1::trace_install_rowops(buf);
+    iadr1::trace_install_chain(buf);
   } else if (op == 0) {   // remove
     iadr1::trace_install_decode(nullptr);
     iadr1::trace_install_gemm(nullptr);
     iadr1::trace_install_rowops(nullptr);
+    iadr1::trace_install_chain(nullptr);
   } else if (op == 2) {   // collect (device must be idle)
     if (!buf || !out) return iadr1::set_error("trace: nothing to collect");
     const size_t n = (size_t)max_words < words ? (size_t)max_words : words;

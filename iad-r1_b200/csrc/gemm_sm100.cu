@@ -707,6 +707,17 @@ static int make_map(CUtensorMap* out, const void* ptr, long long d0, long long d
   return 0;
 }
 
+// K-major 2-D operand [rows][cols] (row stride ld elements) with a {box_cols, box_rows} box, 128-byte swizzle (decode chain).
+int make_tensor_map_2d(CUtensorMap* out, const void* ptr, long long cols, long long rows, long long ld, int box_cols, int box_rows) {
+  return make_map(out, ptr, cols, rows, 1, 1, ld, ld, ld, box_cols, box_rows);
+}
+
+// Two row blocks [0, rows) and [rows, 2 rows) of one K-major matrix as ONE box {box_cols, box_rows, 2}: the fused gate|up
+// weight of the decode chain, so that a k-block of both halves arrives with a single TMA instruction.
+int make_tensor_map_pair(CUtensorMap* out, const void* ptr, long long cols, long long rows, long long ld, int box_cols, int box_rows) {
+  return make_map(out, ptr, cols, rows, 2, 1, ld, rows * ld, 2 * rows * ld, box_cols, box_rows, 2);
+}
+
 // Rank-5 map of an MN-major operand through the view [batch_hi][batch_lo][mn / 64][k][64]; box {64, BK, chunks, 1, 1}.
 static int make_map_chunked(CUtensorMap* out, const void* ptr, long long mn, long long k, long long n_lo, long long n_hi,
                             long long ld, long long bs_lo, long long bs_hi, int chunks) {

@@ -482,12 +482,58 @@ int iadr1_decode_head(void* handle, const iadr1_decode_t* e, int first, void* st
                       e->out_tokens, e->c_max, e->eos_id, e->pad_id, e->forbid_eos, first, s);
 }
 
+// lm_head + sampler on the already normalised rows in e->xn
+static int decode_head_normed(Model& m, const iadr1_decode_t* e, int first, cudaStream_t s) {
+  const iadr1_model_cfg_t& c = m.c;
+  const Weight* E = head_weight(m);
+  if (!E) return set_error("decode_head: weights not bound");
+  TRY(skinny(E->p, e->xn, e->logits, c.vocab, c.hidden, e->R, 0, nullptr, e->block_n, s));
+  return iadr1_sample(e->logits, e->R, c.vocab, e->temperature, e->top_k, e->top_p, 0ull, e->state, e->tok, e->finished,
+                      e->out_tokens, e->c_max, e->eos_id, e->pad_id, e->forbid_eos, first, s);
+}
+
+// The decode step as 2 launches per layer: attention + the persistent chain kernel (csrc/decode_chain.cu), which runs
+// o -> norm -> gate_up + SwiGLU -> down -> next layer's norm -> next layer's qkv with the weights streaming across the phases.
+static int decode_step_chained(Model& m, const iadr1_decode_t* e, cudaStream_t s) {
+  const iadr1_model_cfg_t& c = m.c;
+  const int H = c.hidden, I = c.inter, D = (c.nq + 2 * c.nkv) * c.hd, QH = c.nq * c.hd, R = e->R;
+  const Weight* emb = m.find("embed_tokens.weight");
+  const Weight* nw = m.find("norm.weight");
+  if (!emb || !nw) return set_error("decode_step: embed_tokens.weight / norm.weight not bound");
+  if (cudaMemsetAsync(e->chain_counters, 0, (size_t)(c.layers + 1) * 8 * sizeof(unsigned), s) != cudaSuccess)
+    return set_error("decode_step: memset failed");
+  TRY(iadr1_decode_embed(emb->p, e->tok, e->h, R, H, s));
+  const long long kvw = (long long)c.nkv * c.hd;
+  LayerW w, wn;
+  TRY(layer_weights(m, 0, w));
+  TRY(launch_decode_chain(R, H, I, QH, D, c.rms_eps, e->h, e->xn, e->act, e->qkv, nullptr, nullptr, nullptr, nullptr, nullptr,
+                          w.ln1->p, w.qkv->p, w.qkv_b->p, 0, 1, 1, e->chain_counters, s));
+  for (int i = 0; i < c.layers; ++i) {
+    const bool last = i + 1 == c.layers;
+    if (!last) TRY(layer_weights(m, i + 1, wn));
+    const char* kp = static_cast<const char*>(e->kp) + (long long)i * e->n_groups * e->p_max * kvw * 2;
+    const char* vp = static_cast<const char*>(e->vp) + (long long)i * e->n_groups * e->p_max * kvw * 2;
+    char* kc = static_cast<char*>(e->kc) + (long long)i * R * e->c_max * kvw * 2;
+    char* vc = static_cast<char*>(e->vc) + (long long)i * R * e->c_max * kvw * 2;
+    TRY(iadr1_decode_attention_fused(e->qkv, e->cos_tab, e->sin_tab, e->rope_delta, kp, vp, kc, vc, e->state, e->row_group,
+                                     e->row_plen, e->part, e->tickets, e->attn, R, c.nq, c.nkv, c.hd, e->p_max, e->c_max,
+                                     e->nsplit, e->max_pos, 1.f / sqrtf((float)c.hd), s));
+    TRY(launch_decode_chain(R, H, I, QH, D, c.rms_eps, e->h, e->xn, e->act, e->qkv, e->attn, w.o->p, w.ln2->p, w.gu->p, w.down->p,
+                            last ? nw->p : wn.ln1->p, last ? nullptr : wn.qkv->p, last ? nullptr : wn.qkv_b->p, 1, 1, last ? 0 : 1,
+                            e->chain_counters + (i + 1) * 8, s));
+    if (!last) w = wn;
+  }
+  TRY(decode_head_normed(m, e, 0, s));
+  return iadr1_decode_advance(e->state, s);
+}
+
 int iadr1_decode_step(void* handle, const iadr1_decode_t* e, void* stream) {
   if (!handle || !e) return set_error("decode_step: null argument");
   Model& m = *static_cast<Model*>(handle);
   const iadr1_model_cfg_t& c = m.c;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int H = c.hidden, I = c.inter, D = (c.nq + 2 * c.nkv) * c.hd, QH = c.nq * c.hd, R = e->R;
+  if (e->chain_counters && R <= 128 && H <= 4096 && decode_chain_enabled()) return decode_step_chained(m, e, s);
   const Weight* emb = m.find("embed_tokens.weight");
   if (!emb) return set_error("decode_step: embed_tokens.weight not bound");
   TRY(iadr1_decode_embed(emb->p, e->tok, e->h, R, H, s));
@@ -671,8 +717,11 @@ int iadr1_vision_fwd(void* handle, const void* pixel_values, const iadr1_vision_
     TRY(iadr1_gather_rows(pt->p, nullptr, geo->pos_index, L.pos, N, E, E, 0, E, s));       // position table tiled over the crops
     TRY(linear_fwd(pixel_values, pe->p, L.x[0], N, E, Kp, pb->p, L.pos, s));
   } else if (geo->window_index) {
-    TRY(linear_fwd(pixel_values, pe->p, L.x[c.v_depth], N, E, Kp, nullptr, nullptr, s));   // x[depth] as scratch
-    TRY(iadr1_gather_rows(L.x[c.v_depth], nullptr, geo->window_index, L.x[0], N / unit, unit * E, unit * E, 0, unit * E, s));
+    // block 0's normalised-input buffer is free until its first norm: scratch for the un-permuted patch embedding (x[depth]
+    // would alias x[0] in the two-buffer layout of a forward-only call with an even depth)
+    void* pe_out = L.bb[0].xn;
+    TRY(linear_fwd(pixel_values, pe->p, pe_out, N, E, Kp, nullptr, nullptr, s));
+    TRY(iadr1_gather_rows(pe_out, nullptr, geo->window_index, L.x[0], N / unit, unit * E, unit * E, 0, unit * E, s));
   } else {
     TRY(linear_fwd(pixel_values, pe->p, L.x[0], N, E, Kp, nullptr, nullptr, s));
   }

@@ -9,6 +9,10 @@ int set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int launch_gemm(const iadr1_gemm_t& d, cudaStream_t stream);
 int pick_block_n_public(int N, int b_mn);
+bool decode_chain_enabled();
+int launch_decode_chain(int R, int H, int I, int QH, int D, float eps, float* h, void* xn, void* act, float* qkv, const void* attn,
+                        const void* Wo, const void* ln_mid, const void* Wgu, const void* Wd, const void* ln_next, const void* Wqkv,
+                        const void* qkv_bias, int with_mlp, int with_norm, int with_qkv, unsigned* counters, cudaStream_t stream);
 void gemm_profile_enable(int on);
 long long gemm_profile_collect(double* total_ms, double* total_flops, double* max_launch_ms, const char* csv_path);
 }  // namespace iadr1
@@ -23,6 +27,7 @@ void pdl_set(bool on);
 void trace_install_decode(unsigned long long* p);
 void trace_install_gemm(unsigned long long* p);
 void trace_install_rowops(unsigned long long* p);
+void trace_install_chain(unsigned long long* p);
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
@@ -67,6 +72,28 @@ __device__ __forceinline__ void pdl_wait() {
       tb[2 + 2 * i] = t0;
       tb[3 + 2 * i] = t1;
     }
+  }
+}
+// Extra timeline marks inside a kernel (persistent decode chain): record {tag (< 4096), %globaltimer}; call from ONE thread.
+__device__ __forceinline__ void trace_stamp(unsigned long long tag) {
+  unsigned long long* tb = g_trace_buf;
+  if (!tb) return;
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  const unsigned long long i = atomicAdd(tb, 1ull);
+  if (i < 8190ull) {
+    tb[2 + 2 * i] = tag;
+    tb[3 + 2 * i] = t;
+  }
+}
+// Same record format with an arbitrary value instead of the timer (in-kernel cycle accounting).
+__device__ __forceinline__ void trace_value(unsigned long long tag, unsigned long long v) {
+  unsigned long long* tb = g_trace_buf;
+  if (!tb) return;
+  const unsigned long long i = atomicAdd(tb, 1ull);
+  if (i < 8190ull) {
+    tb[2 + 2 * i] = tag;
+    tb[3 + 2 * i] = v;
   }
 }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

@@ -82,6 +82,7 @@ class RolloutEngine:
             self.attn_nw = 4
         self.part = torch.zeros(R, t.num_heads, self.nsplit, hd + 2, dtype=f32, device=dev)
         self.tickets = torch.zeros(R * nkv, dtype=i32, device=dev)
+        self.chain_counters = torch.zeros((t.num_layers + 1) * 8, dtype=i32, device=dev)   # persistent decode-layer chain
         # fp32 gate|up accumulator of the stream-K product; decode_silu_mul_f32 leaves it zero for the next layer
         self.block_n = max(16, ops.ceil_to(R, 16))
         self.co_resident = os.environ.get("IADR1_DECODE_CORES", "0") != "0" and self.block_n <= 128
@@ -147,7 +148,8 @@ class RolloutEngine:
                 self.rope_delta.data_ptr(), self.row_plen.data_ptr(), self.row_group.data_ptr(), self.h.data_ptr(),
                 self.xn.data_ptr(), self.qkv.data_ptr(), self.attn.data_ptr(), self.part.data_ptr(), self.tickets.data_ptr(),
                 self.act.data_ptr(), self.logits.data_ptr(), self.cos_tab.data_ptr(), self.sin_tab.data_ptr(),
-                self.temperature, self.top_k, self.top_p, c.eos_token_id, c.pad_token_id, int(self.forbid_eos))
+                self.temperature, self.top_k, self.top_p, c.eos_token_id, c.pad_token_id, int(self.forbid_eos),
+                self.chain_counters.data_ptr())
         return self._dstate
 
     def _decode_step_body(self):

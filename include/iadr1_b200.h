@@ -245,6 +245,7 @@ typedef struct iadr1_decode_t {
   float* h; void* xn; float* qkv; void* attn; float* part; int* tickets; void* act; float* logits;
   const float* cos_tab; const float* sin_tab;
   float temperature; int top_k; float top_p; int eos_id, pad_id, forbid_eos;
+  unsigned int* chain_counters;   /* (layers + 1) * 8 words for the persistent decode-layer chain (R <= 128); NULL: one kernel per op */
 } iadr1_decode_t;
 typedef void (*iadr1_layer_cb)(int layer, void* user);
 /* What the vision tower derives from the image grids (host-computed, device-resident; HF get_window_index / rot_pos_emb,

@@ -184,7 +184,7 @@ def test_true_width_rollout_logits_match_hf(cuda, model):
     pos, _ = family_position_ids(ids.numpy(), [case["grid"]] * G, cfg)
     with torch.no_grad():
         tail = _hf_tail_logits(case, ids, torch.from_numpy(pos), torch.ones_like(ids), C + 1)[:, :-1].float()   # [G, C, V]
-    worst_logit, worst_lp = 0.0, 0.0
+    worst_logit, worst_lp, worst_margin = 0.0, 0.0, 0.0
     for k in range(C):
         d = (rec[k] - tail[:, k]).abs().max().item()
         lp_dec = torch.log_softmax(rec[k], -1).gather(1, out[:G, k].long().cpu()[:, None])
@@ -195,8 +195,11 @@ def test_true_width_rollout_logits_match_hf(cuda, model):
         sc = tail[:, k] / 0.9
         kth = sc.topk(50, -1).values[:, -1]
         chosen = sc.gather(1, out[:G, k].long().cpu()[:, None]).squeeze(1)
-        assert (chosen >= kth - 0.05).all(), "sampled token outside HF's top-k set"
+        worst_margin = max(worst_margin, (kth - chosen).max().item())
     scale = tail.abs().max().item()
     print(f"\n[{model}] decode logits vs HF: max |diff| {worst_logit:.4f} (logit scale {scale:.2f}), "
           f"sampled-token log-prob max diff {worst_lp:.4f}")
+    print(f"[{model}] sampled token below HF's 50th score by at most {max(worst_margin, 0.0):.4f} (allowed: twice the logit error / temperature)")
     assert worst_logit <= 0.03 * max(1.0, scale) and worst_lp <= 0.03
+    # a sampled token may sit outside HF's top-k set only by what the logit error explains (both the token's and the k-th score move)
+    assert worst_margin <= 2 * worst_logit / 0.9 + 1e-3, "sampled token outside HF's top-k set"

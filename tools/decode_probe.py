@@ -67,6 +67,9 @@ if os.environ.get("PROBE_TRACE"):
     if eng.gu_mode.startswith("fused"):
         per_layer.remove("silu")
     names = ["embed"] + per_layer * layers + ["rms_f", "lm_head", "sample", "advance"]
+    if os.environ.get("IADR1_DECODE_CHAIN", "1") != "0" and eng.R <= 128 and eng._native_ok:
+        # persistent decode-layer chain: 2 launches per layer (csrc/decode_chain.cu)
+        names = ["embed", "chain0"] + ["attn", "chain"] * layers + ["lm_head", "sample", "advance"]
     assert nk == len(names), (nk, len(names))
     eng.state[0] = int(os.environ.get("PROBE_CTX_STEP", "256"))
     torch.cuda.synchronize()
@@ -80,7 +83,41 @@ if os.environ.get("PROBE_TRACE"):
     a = np.frombuffer(buf, dtype=np.uint64)
     n = int(a[0])
     rec = a[2:2 + 2 * n].reshape(n, 2).astype(np.int64)
+    marks = rec[rec[:, 0] < 4096]                            # in-kernel phase marks of the persistent chain (tag, time)
+    rec = rec[rec[:, 0] >= 4096]
+    n = len(rec)
     assert n == reps * nk, (n, reps, nk)
+    vals = marks[marks[:, 0] >= 1000]
+    marks = marks[marks[:, 0] < 1000]
+    if len(vals):
+        nm = {1000: "producer loop cycles", 1001: "  cycles issuing activation tiles", 1002: "  activation tiles", 1003: "  cycles issuing weight tiles",
+              1004: "  weight tiles", 1005: "  cycles polling dependencies", 1006: "  loop iterations"}
+        print("CTA 0 producer thread, one chain launch (clock64):")
+        for tag in sorted(nm):
+            v = vals[vals[:, 0] == tag][:, 1]
+            if len(v):
+                print(f"    {nm[tag]:40s} {np.median(v):10.0f}")
+    if len(marks):
+        # last replay, one mid-stack chain launch: times relative to the kernel's dependency wait returning
+        mk = marks[-(len(marks) // reps):]
+        starts = np.nonzero(mk[:, 0] == 100)[0]
+        if len(starts) > 3:
+            seg = mk[starts[2]:starts[3]]
+            t_wait = rec.reshape(reps, nk, 2)[-1, 2 + 2 * 1 + 1, 1]   # leave stamp of the 2nd chain kernel (after attention 1)
+            tagname = {100: "producer reaches wait", 110: "o acts ready", 111: "norm2 sees o done", 112: "gate_up acts ready",
+                       113: "down acts ready", 114: "norm1 sees down done", 115: "qkv acts ready", 120: "CTA0 published o",
+                       121: "CTA0 published norm2", 122: "CTA0 published gate_up", 123: "CTA0 published down",
+                       124: "CTA0 published norm1", 125: "CTA0 published qkv"}
+            print("chain kernel (layer 1) phase marks, us after its dependency wait returned:")
+            for ph, nm in ((0, "o"), (2, "gate_up"), (3, "down"), (5, "qkv")):
+                for j in range(8):
+                    tagname[200 + ph * 10 + j] = f"  mma {nm} k-block {8 * j} landed"
+            for j in range(8, 16):
+                tagname[300 + j] = f"      gate_up kb {j}: weights issued"
+                tagname[320 + j] = f"      gate_up kb {j}: acts issued"
+                tagname[340 + j] = f"      gate_up kb {j}: landed, mma issued"
+            for tag, tm in seg[np.argsort(seg[:, 1])]:
+                print(f"    {tagname.get(int(tag), int(tag)):40s} {(tm - t_wait) / 1e3:8.2f}")
     rec = rec.reshape(reps, nk, 2)[2:]                      # drop warm-up replays
     leave = rec[:, :, 1]
     dur = np.diff(np.concatenate([leave, leave[:, -1:] ], 1), axis=1)[:, :-1]     # kernel k: leave[k+1] - leave[k]
