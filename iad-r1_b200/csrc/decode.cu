@@ -435,7 +435,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<const uint32_t*>(&v);
 }
 
-template <int HD, int NW>
+template <int HD, int NW, int NS>
 __global__ void __launch_bounds__(NW * 32) decode_attn_mma_kernel(
     const float* __restrict__ qkv, const float* __restrict__ cos_tab, const float* __restrict__ sin_tab,
     const int* __restrict__ rope_delta, const bf16* __restrict__ kp, const bf16* __restrict__ vp, bf16* __restrict__ kc,
@@ -472,13 +472,13 @@ __global__ void __launch_bounds__(NW * 32) decode_attn_mma_kernel(
   __shared__ __align__(128) bf16 sQ[16 * HD];             // 16 query rows (heads, zero-padded), swizzled pieces
   __shared__ __align__(16) bf16 sNew[2][HD];              // this step's rotated k and v (linear)
   __shared__ int s_last;
-  extern __shared__ __align__(128) uint8_t sm_kv_raw[];   // 2 stages x {K [CK][HD], V [CK][HD]}, swizzled
+  extern __shared__ __align__(128) uint8_t sm_kv_raw[];   // NS stages x {K [CK][HD], V [CK][HD]}, swizzled
   bf16* sKV = reinterpret_cast<bf16*>(sm_kv_raw);
   constexpr int STAGE = 2 * CK * HD;                      // elements per stage
 
   // cache rows of chunk c -> stage buffer; the token being decoded (key ctx - 1) is patched in from sNew later
   auto stage = [&](int c) {
-    bf16* sK = sKV + (c & 1) * STAGE;
+    bf16* sK = sKV + (c % NS) * STAGE;
     bf16* sV = sK + CK * HD;
     const int base = k0 + c * CK;
     for (int q = threadIdx.x; q < CK * PPR; q += NT) {
@@ -501,8 +501,9 @@ __global__ void __launch_bounds__(NW * 32) decode_attn_mma_kernel(
   };
 
   // chunks 0 and 1 hold cache rows written by earlier decode steps / the prefill: requested before the PDL wait
-  if (nchunks > 0) stage(0);
-  if (nchunks > 1) stage(1);
+#pragma unroll
+  for (int c = 0; c < NS; ++c)
+    if (c < nchunks) stage(c);
   pdl_wait();
   // ---- rotated, pre-scaled queries as bf16 rows (row = head within the group) ----
   {
@@ -570,7 +571,7 @@ __global__ void __launch_bounds__(NW * 32) decode_attn_mma_kernel(
   float mrun = -INFINITY, lrun = 0.f;      // of query row lane / 4 (rows >= 8 are padding)
 
   for (int c = 0; c < nchunks; ++c) {
-    bf16* sK = sKV + (c & 1) * STAGE;
+    bf16* sK = sKV + (c % NS) * STAGE;
     bf16* sV = sK + CK * HD;
     const int cbase = k0 + c * CK;
     if (has_new && ctx - 1 >= cbase && ctx - 1 < cbase + CK && threadIdx.x < 2 * PPR) {
@@ -579,7 +580,9 @@ __global__ void __launch_bounds__(NW * 32) decode_attn_mma_kernel(
       bf16* dst = (which ? sV : sK) + jj * HD + ((piece ^ (jj & 7)) << 3);
       *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(&sNew[which][piece * 8]);
     }
-    if (c + 1 < nchunks) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    // chunks c + 1 .. c + NS - 1 may still be in flight
+    if (NS == 3 && c + 2 < nchunks) asm volatile("cp.async.wait_group 2;" ::: "memory");
+    else if (c + 1 < nchunks) asm volatile("cp.async.wait_group 1;" ::: "memory");
     else asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     const int t0 = warp * 16;                   // this warp's 16 keys of the chunk
@@ -641,8 +644,8 @@ __global__ void __launch_bounds__(NW * 32) decode_attn_mma_kernel(
         mma_bf16_16816(oacc[nb + 1], pa, b[2], b[3]);
       }
     }
-    __syncthreads();                            // every warp is done with buffer (c & 1):
-    if (c + 2 < nchunks) stage(c + 2);          // re-fill it two chunks ahead
+    __syncthreads();                            // every warp is done with this chunk's buffer:
+    if (c + NS < nchunks) stage(c + NS);        // re-fill it NS chunks ahead
   }
   // ---- merge the 4 warps (rows = heads < gq live in c0/c1 of the lanes with lane/4 == head); staging memory re-used
   float (*sm_mrg)[MAXG][HD + 2] = reinterpret_cast<float (*)[MAXG][HD + 2]>(sm_kv_raw);   // NW x MAXG x (HD + 2) floats <= staging
@@ -672,6 +675,10 @@ __global__ void __launch_bounds__(NW * 32) decode_attn_mma_kernel(
       a += sm_mrg[w][h][d] * cf;
       l += sm_mrg[w][h][HD + 1] * cf;
     }
+    if (nsplit == 1) {      // the whole context in one CTA: no partials, no ticket, no second pass
+      out[((long long)r * nq + kvh * gq + h) * HD + d] = __float2bfloat16(a / l);
+      continue;
+    }
     float* dst = part + (((long long)r * nq + kvh * gq + h) * nsplit + sp) * (HD + 2);
     dst[d] = a;
     if (d == 0) {
@@ -679,6 +686,7 @@ __global__ void __launch_bounds__(NW * 32) decode_attn_mma_kernel(
       dst[HD + 1] = l;
     }
   }
+  if (nsplit == 1) return;
   // ---- last CTA of this (row, kv head) merges the splits (same protocol as the scalar kernel) ----
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -732,6 +740,571 @@ __global__ void __launch_bounds__(NW * 32) decode_attn_mma_kernel(
       out[((long long)r * nq + kvh * gq + h) * HD + d] = __float2bfloat16(a8[oo] * s_invl[h]);
     }
   }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Shared-prefix decode attention (head_dim 64 / 128): the G rows of a GRPO group attend to the SAME prompt K/V
+// (ref: sc_grpo_trainer.py:351 `enable_prefix_caching`), so the prompt part of the context is processed once per group:
+//   * P-kind CTAs (group, 8-row block, kv head, prompt split): the 8 rows x gq query heads form 64 query rows = 4 full
+//     m16 MMA tiles (one per warp: 2 decode rows x 8 heads, no padding rows); every warp walks ALL keys of the chunk for
+//     its own 16 query rows (no cross-warp merge), K/V tiles are staged once for 8 rows instead of once per row;
+//   * C-kind CTAs (row, kv head, completion split): the row's own keys incl. the token being decoded (rotary + KV append),
+//     the per-row kernel's structure (warps split the keys of a chunk, merged in shared memory).
+// Both kinds write (o, m, l) partials per (row, head, slot); the last CTA to arrive for a (row, kv head) (atomic ticket over
+// psplit + csplit slots) merges them. One launch, one wave.
+// ------------------------------------------------------------------------------------------------
+// Merge of the split partials of up to 8 rows of one kv head by ONE CTA (the last to arrive for those rows). Everything is
+// laid out for few L2 round trips: one thread per (row, head) loads all its (m, l) pairs at once and derives the slot
+// weights; then every thread owns pairs of adjacent head-dim columns and has the loads of all slots of 4 pairs in flight.
+template <int HD>
+__device__ __forceinline__ void attn_merge_rows(const float* __restrict__ part, bf16* __restrict__ out, const int* rows, int n_rows,
+                                                int kvh, int nq, int gq, int nslots, float* s_coef /* [64][17] */) {
+  constexpr int NT = 128, CS = 17;     // slot weights of an item, then 1 / l at [16]
+  const int items = n_rows * gq;       // (row, head) pairs, <= 64
+  if ((int)threadIdx.x < items) {
+    const int ri = threadIdx.x / gq, h = threadIdx.x % gq;
+    const float* p = part + ((long long)rows[ri] * nq + kvh * gq + h) * nslots * (HD + 2) + HD;
+    float ms[16], ls[16];
+#pragma unroll
+    for (int s2 = 0; s2 < 16; ++s2) {
+      ms[s2] = (s2 < nslots) ? __ldcg(p + s2 * (HD + 2)) : -INFINITY;
+      ls[s2] = (s2 < nslots) ? __ldcg(p + s2 * (HD + 2) + 1) : 0.f;
+    }
+    float m = -INFINITY;
+#pragma unroll
+    for (int s2 = 0; s2 < 16; ++s2) m = fmaxf(m, ms[s2]);
+    float l = 0.f;
+#pragma unroll
+    for (int s2 = 0; s2 < 16; ++s2) {
+      const float cf = (ms[s2] == -INFINITY) ? 0.f : __expf(ms[s2] - m);
+      s_coef[threadIdx.x * CS + s2] = cf;
+      l += ls[s2] * cf;
+    }
+    s_coef[threadIdx.x * CS + 16] = 1.f / l;
+  }
+  __syncthreads();
+  constexpr int PAIRS = HD / 2;
+  const int total = items * PAIRS;
+  for (int base = threadIdx.x; base < total; base += NT * 4) {
+    float2 acc[4];
+    const float* src[4];
+    int item[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int o = min(base + u * NT, total - 1);
+      item[u] = o / PAIRS;
+      const int ri = item[u] / gq, h = item[u] % gq, d = (o % PAIRS) * 2;
+      src[u] = part + ((long long)rows[ri] * nq + kvh * gq + h) * nslots * (HD + 2) + d;
+      acc[u] = make_float2(0.f, 0.f);
+    }
+    for (int s2 = 0; s2 < nslots; s2 += 4) {
+      float2 v[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          v[u][k] = (s2 + k < nslots) ? __ldcg(reinterpret_cast<const float2*>(src[u] + (long long)(s2 + k) * (HD + 2))) : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float cf = (s2 + k < nslots) ? s_coef[item[u] * CS + s2 + k] : 0.f;
+          acc[u].x += v[u][k].x * cf;
+          acc[u].y += v[u][k].y * cf;
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int o = base + u * NT;
+      if (o < total) {
+        const int ri = item[u] / gq, h = item[u] % gq, d = (o % PAIRS) * 2;
+        const float inv = s_coef[item[u] * CS + 16];
+        *reinterpret_cast<__nv_bfloat162*>(out + ((long long)rows[ri] * nq + kvh * gq + h) * HD + d) =
+            __floats2bfloat162_rn(acc[u].x * inv, acc[u].y * inv);
+      }
+    }
+  }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(128, 3) decode_attn_grouped_kernel(
+    const float* __restrict__ qkv, const float* __restrict__ cos_tab, const float* __restrict__ sin_tab,
+    const int* __restrict__ rope_delta, const bf16* __restrict__ kp, const bf16* __restrict__ vp, bf16* __restrict__ kc,
+    bf16* __restrict__ vc, const int* __restrict__ state, const int* __restrict__ row_plen, float* __restrict__ part,
+    int* __restrict__ tickets, bf16* __restrict__ out, int G, int nq, int nkv, int p_max, int c_max, int max_pos, float scale,
+    int psplit, int csplit, int n_pblocks) {
+  if (threadIdx.x == 0) pdl_trigger();   // dependents may become resident (and prefetch) right away
+  constexpr int HALF = HD / 2, PPR = HD / 8, NT = 128, NW = 4, CK = 64, MAXG = 8, NKS = HD / 16, NOB = HD / 8, EPL = HD / 32;
+  constexpr int STAGE = 2 * CK * HD;                      // bf16 elements per stage: K [CK][HD] + V [CK][HD]
+  const int gq = nq / nkv, nslots = psplit + csplit;
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int step = state[ST_STEP];
+  const int qkv_dim = (nq + 2 * nkv) * HD;
+  __shared__ __align__(128) bf16 sQ[16 * HD];             // C-kind: 16 query rows (heads, zero-padded), swizzled pieces
+  __shared__ __align__(16) bf16 sNew[2][HD];              // C-kind: this step's rotated k and v (linear)
+  __shared__ int s_rows[8];
+  __shared__ int s_nrows;
+  extern __shared__ __align__(128) uint8_t sm_kv_raw[];   // 2 stages x {K, V}, swizzled
+  bf16* sKV = reinterpret_cast<bf16*>(sm_kv_raw);
+  float* s_coef = reinterpret_cast<float*>(sm_kv_raw);    // merge scratch (the staging area is idle by then)
+
+  if ((int)blockIdx.x < n_pblocks) {
+    // =========================== P-kind: the prompt keys of one group for a block of up to 8 rows ===========================
+    const int rblocks = (G + 7) / 8;
+    int t = blockIdx.x;
+    const int ps = t % psplit; t /= psplit;
+    const int kvh = t % nkv; t /= nkv;
+    const int rb = t % rblocks;
+    const int grp = t / rblocks;
+    const int r_base = grp * G + rb * 8, nrows = min(8, G - rb * 8);
+    const int P = row_plen[r_base];
+    const int per = (((P + psplit - 1) / psplit) + 15) & ~15;
+    const int k0 = min(P, ps * per), k1 = min(P, k0 + per);
+    const int nchunks = (k1 - k0 + CK - 1) / CK;
+    auto stage = [&](int c) {
+      bf16* sK = sKV + (c & 1) * STAGE;
+      bf16* sV = sK + CK * HD;
+      const int base = k0 + c * CK;
+      for (int q = threadIdx.x; q < CK * PPR; q += NT) {
+        const int jj = q / PPR, piece = q % PPR;
+        const int j = base + jj;
+        const int off = jj * HD + ((piece ^ (jj & 7)) << 3);
+        if (j < k1) {
+          const long long row = (((long long)grp * p_max + j) * nkv + kvh) * HD;
+          cp_async16(sK + off, kp + row + piece * 8);
+          cp_async16(sV + off, vp + row + piece * 8);
+        } else {
+          *reinterpret_cast<uint4*>(sK + off) = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(sV + off) = make_uint4(0, 0, 0, 0);
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (nchunks > 0) stage(0);                            // prompt K/V: written by the prefill, independent of this step
+    // rotary factors of the block's rows for this thread's head-dim column (positions are static per step)
+    constexpr int TPD = NT / HD;                          // threads per column (1 at hd 128, 2 at hd 64)
+    constexpr int QPT = 64 / TPD;                         // query rows per thread
+    const int d = threadIdx.x % HD, sub = threadIdx.x / HD;
+    const int dp = d < HALF ? d + HALF : d - HALF;
+    float cs8[8], sn8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = r_base + min(i, nrows - 1);
+      int pos = row_plen[r] + step + rope_delta[r];
+      pos = max(0, min(max_pos - 1, pos));
+      cs8[i] = bf16r(cos_tab[(long long)pos * HD + d]);
+      sn8[i] = bf16r(sin_tab[(long long)pos * HD + d]);
+    }
+    const bool tr = blockIdx.x == 0 && threadIdx.x == 0;
+    if (tr) trace_stamp(400);
+    pdl_wait();
+    if (tr) trace_stamp(401);
+    // raw fp32 queries of the block -> stage 1 (free until chunk 1 is requested): [row i][head h][HD]
+    float* raw = reinterpret_cast<float*>(sKV + STAGE);
+    {
+      constexpr int PCS = HD / 4;                         // 16-byte pieces per head
+      for (int q = threadIdx.x; q < 64 * PCS; q += NT) {
+        const int qrow = q / PCS, piece = q % PCS;
+        const int i = qrow >> 3, h = qrow & 7;
+        if (i < nrows && h < gq)
+          cp_async16(raw + qrow * HD + piece * 4, qkv + (long long)(r_base + i) * qkv_dim + (long long)(kvh * gq + h) * HD + piece * 4);
+        else
+          *reinterpret_cast<float4*>(raw + qrow * HD + piece * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    __nv_bfloat16 qv[QPT];
+#pragma unroll
+    for (int qq = 0; qq < QPT; ++qq) {
+      const int qrow = qq * TPD + sub, i = qrow >> 3;
+      const float xd = bf16r(raw[qrow * HD + d]);
+      const float xp = bf16r(raw[qrow * HD + dp]);
+      const float a_ = bf16r(xd * cs8[i]);
+      const float b_ = bf16r((d < HALF ? -xp : xp) * sn8[i]);
+      qv[qq] = __float2bfloat16(bf16r(a_ + b_) * scale);
+    }
+    __syncthreads();                                      // every raw value has been read: the tile is rewritten in place
+    bf16* sQ64 = reinterpret_cast<bf16*>(raw);            // [64][HD] bf16, 16-byte pieces swizzled by (row & 7)
+#pragma unroll
+    for (int qq = 0; qq < QPT; ++qq) {
+      const int qrow = qq * TPD + sub;
+      sQ64[qrow * HD + ((((d >> 3) ^ (qrow & 7)) << 3) | (d & 7))] = qv[qq];
+    }
+    __syncthreads();
+    uint32_t qa[NKS][4];
+#pragma unroll
+    for (int ks = 0; ks < NKS; ++ks) {
+      const int row = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+      const int piece = ks * 2 + (lane >> 4);
+      ldsm_x4(qa[ks], sQ64 + row * HD + ((piece ^ (row & 7)) << 3));
+    }
+    __syncthreads();                                      // stage 1 is free again
+    if (tr) trace_stamp(402);
+    if (nchunks > 1) stage(1);
+    float oacc[NOB][4];
+#pragma unroll
+    for (int nb = 0; nb < NOB; ++nb)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) oacc[nb][e] = 0.f;
+    float mA = -INFINITY, mB = -INFINITY, lA = 0.f, lB = 0.f;   // query rows lane / 4 and lane / 4 + 8 of the warp's tile
+    for (int c = 0; c < nchunks; ++c) {
+      bf16* sK = sKV + (c & 1) * STAGE;
+      bf16* sV = sK + CK * HD;
+      if (c + 1 < nchunks) asm volatile("cp.async.wait_group 1;" ::: "memory");
+      else asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+      const int nk = min(CK, k1 - (k0 + c * CK));
+      float sacc[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sacc[nt][e] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < NKS; ++ks) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t b[4];
+          const int key = j * 16 + (lane & 7) + ((lane >> 4) & 1) * 8;
+          const int piece = ks * 2 + ((lane >> 3) & 1);
+          ldsm_x4(b, sK + key * HD + ((piece ^ (key & 7)) << 3));
+          mma_bf16_16816(sacc[2 * j], qa[ks], b[0], b[1]);
+          mma_bf16_16816(sacc[2 * j + 1], qa[ks], b[2], b[3]);
+        }
+      }
+      float mlA = -INFINITY, mlB = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int key = nt * 8 + (lane & 3) * 2 + (e & 1);
+          if (key >= nk) sacc[nt][e] = -INFINITY;
+          if (e < 2) mlA = fmaxf(mlA, sacc[nt][e]);
+          else mlB = fmaxf(mlB, sacc[nt][e]);
+        }
+      mlA = fmaxf(mlA, __shfl_xor_sync(0xffffffffu, mlA, 1));
+      mlA = fmaxf(mlA, __shfl_xor_sync(0xffffffffu, mlA, 2));
+      mlB = fmaxf(mlB, __shfl_xor_sync(0xffffffffu, mlB, 1));
+      mlB = fmaxf(mlB, __shfl_xor_sync(0xffffffffu, mlB, 2));
+      const float mnA = fmaxf(mA, mlA), mnB = fmaxf(mB, mlB);       // finite: the chunk holds at least one valid key
+      const float cA = (mA == -INFINITY) ? 0.f : __expf(mA - mnA);
+      const float cB = (mB == -INFINITY) ? 0.f : __expf(mB - mnB);
+      float llA = 0.f, llB = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        sacc[nt][0] = __expf(sacc[nt][0] - mnA);
+        sacc[nt][1] = __expf(sacc[nt][1] - mnA);
+        sacc[nt][2] = __expf(sacc[nt][2] - mnB);
+        sacc[nt][3] = __expf(sacc[nt][3] - mnB);
+        llA += sacc[nt][0] + sacc[nt][1];
+        llB += sacc[nt][2] + sacc[nt][3];
+      }
+      llA += __shfl_xor_sync(0xffffffffu, llA, 1);
+      llA += __shfl_xor_sync(0xffffffffu, llA, 2);
+      llB += __shfl_xor_sync(0xffffffffu, llB, 1);
+      llB += __shfl_xor_sync(0xffffffffu, llB, 2);
+      lA = lA * cA + llA; lB = lB * cB + llB;
+      mA = mnA; mB = mnB;
+#pragma unroll
+      for (int nb = 0; nb < NOB; ++nb) {
+        oacc[nb][0] *= cA; oacc[nb][1] *= cA;
+        oacc[nb][2] *= cB; oacc[nb][3] *= cB;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t pa[4];
+        pa[0] = pack_bf16x2(sacc[2 * j][0], sacc[2 * j][1]);
+        pa[1] = pack_bf16x2(sacc[2 * j][2], sacc[2 * j][3]);
+        pa[2] = pack_bf16x2(sacc[2 * j + 1][0], sacc[2 * j + 1][1]);
+        pa[3] = pack_bf16x2(sacc[2 * j + 1][2], sacc[2 * j + 1][3]);
+#pragma unroll
+        for (int nb = 0; nb < NOB; nb += 2) {
+          uint32_t b[4];
+          const int key = j * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+          const int piece = nb + (lane >> 4);
+          ldsm_x4_trans(b, sV + key * HD + ((piece ^ (key & 7)) << 3));
+          mma_bf16_16816(oacc[nb], pa, b[0], b[1]);
+          mma_bf16_16816(oacc[nb + 1], pa, b[2], b[3]);
+        }
+      }
+      __syncthreads();
+      if (c + 2 < nchunks) stage(c + 2);
+    }
+    if (tr) trace_stamp(403);
+    // ---- partials straight from the fragments: rows A / B = decode rows 2 * warp, 2 * warp + 1; head = lane / 4
+    {
+      const int h = lane >> 2;
+#pragma unroll
+      for (int ab = 0; ab < 2; ++ab) {
+        const int i = 2 * warp + ab;
+        if (i < nrows && h < gq) {
+          float* dst = part + (((long long)(r_base + i) * nq + kvh * gq + h) * nslots + ps) * (HD + 2);
+#pragma unroll
+          for (int nb = 0; nb < NOB; ++nb)
+            *reinterpret_cast<float2*>(dst + nb * 8 + (lane & 3) * 2) = make_float2(oacc[nb][2 * ab], oacc[nb][2 * ab + 1]);
+          if ((lane & 3) == 0) {
+            dst[HD] = ab ? mB : mA;
+            dst[HD + 1] = ab ? lB : lA;
+          }
+        }
+      }
+    }
+    if (threadIdx.x == 0) s_nrows = 0;
+    __syncthreads();
+    if ((int)threadIdx.x < nrows) {
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      const int tk = atomicAdd(&tickets[(r_base + threadIdx.x) * nkv + kvh], 1);
+      if (tk == nslots - 1) {       // last arrival for this row: this CTA merges it
+        tickets[(r_base + threadIdx.x) * nkv + kvh] = 0;
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        s_rows[atomicAdd(&s_nrows, 1)] = r_base + threadIdx.x;
+      }
+    }
+    __syncthreads();
+    if (tr) trace_stamp(404);
+    if (s_nrows > 0) attn_merge_rows<HD>(part, out, s_rows, s_nrows, kvh, nq, gq, nslots, s_coef);
+    if (tr) trace_stamp(405 + (s_nrows > 0 ? 1 : 0));
+    return;
+  }
+
+  // =========================== C-kind: one row's own (completion) keys, incl. the token being decoded ===========================
+  int t = blockIdx.x - n_pblocks;
+  const int sp = t % csplit; t /= csplit;
+  const int kvh = t % nkv;
+  const int r = t / nkv;
+  const int P = row_plen[r];
+  const int ctx = step + 1;                               // completion keys 0 .. step (the last one is produced here)
+  const int per = (((ctx + csplit - 1) / csplit) + 15) & ~15;
+  const int k0 = min(ctx, sp * per), k1 = min(ctx, k0 + per);
+  const int nkeys = k1 - k0;
+  const int nchunks = (nkeys + CK - 1) / CK;
+  const float* xrow = qkv + (long long)r * qkv_dim;
+  int pos = P + step + rope_delta[r];
+  pos = max(0, min(max_pos - 1, pos));
+  const float* cs = cos_tab + (long long)pos * HD;
+  const float* sn = sin_tab + (long long)pos * HD;
+  auto rot = [&](const float* x, int d) -> float {
+    const float xd = bf16r(x[d]);
+    const float xp = bf16r(x[d < HALF ? d + HALF : d - HALF]);
+    const float a_ = bf16r(xd * bf16r(cs[d]));
+    const float b_ = bf16r((d < HALF ? -xp : xp) * bf16r(sn[d]));
+    return bf16r(a_ + b_);
+  };
+  auto stage = [&](int c) {
+    bf16* sK = sKV + (c & 1) * STAGE;
+    bf16* sV = sK + CK * HD;
+    const int base = k0 + c * CK;
+    for (int q = threadIdx.x; q < CK * PPR; q += NT) {
+      const int jj = q / PPR, piece = q % PPR;
+      const int j = base + jj;
+      const int off = jj * HD + ((piece ^ (jj & 7)) << 3);
+      if (j < k1) {
+        if (j != ctx - 1) {
+          const long long row = (((long long)r * c_max + j) * nkv + kvh) * HD;
+          cp_async16(sK + off, kc + row + piece * 8);
+          cp_async16(sV + off, vc + row + piece * 8);
+        }
+      } else {
+        *reinterpret_cast<uint4*>(sK + off) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(sV + off) = make_uint4(0, 0, 0, 0);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (nchunks > 0) stage(0);
+  if (nchunks > 1) stage(1);
+  const bool trc = (int)blockIdx.x == n_pblocks && threadIdx.x == 0;
+  if (trc) trace_stamp(410);
+  pdl_wait();
+  if (trc) trace_stamp(411);
+  {
+    constexpr int CPT = HD > NT ? HD / NT : 1;
+    constexpr int TPH = NT > HD ? NT / HD : 1;
+    constexpr int HPT = MAXG / TPH;
+    const int hsel = TPH > 1 ? threadIdx.x / HD : 0;
+#pragma unroll
+    for (int cc = 0; cc < CPT; ++cc) {
+      const int d = (TPH > 1 ? threadIdx.x % HD : threadIdx.x) + cc * NT;
+      const int dp = d < HALF ? d + HALF : d - HALF;
+      const float cd = bf16r(cs[d]), sd = bf16r(sn[d]);
+      float xv[HPT], xpv[HPT];
+#pragma unroll
+      for (int hh = 0; hh < HPT; ++hh) {
+        const int h = hh * TPH + hsel;
+        const float* xh = xrow + (long long)(kvh * gq + min(h, gq - 1)) * HD;
+        xv[hh] = xh[d];
+        xpv[hh] = xh[dp];
+      }
+#pragma unroll
+      for (int hh = 0; hh < HPT; ++hh) {
+        const int h = hh * TPH + hsel;
+        const float a_ = bf16r(bf16r(xv[hh]) * cd);
+        const float xp = bf16r(xpv[hh]);
+        const float b_ = bf16r((d < HALF ? -xp : xp) * sd);
+        const float v = (h < gq) ? bf16r(a_ + b_) * scale : 0.f;
+        sQ[h * HD + ((((d >> 3) ^ (h & 7)) << 3) | (d & 7))] = __float2bfloat16(v);
+        sQ[(h + 8) * HD + ((((d >> 3) ^ (h & 7)) << 3) | (d & 7))] = __float2bfloat16(0.f);
+      }
+    }
+  }
+  const bool has_new = (ctx - 1 >= k0) && (ctx - 1 < k1);
+  if (has_new && warp == NW - 1) {
+    const float* knew = xrow + (long long)(nq + kvh) * HD;
+    const float* vnew = xrow + (long long)(nq + nkv + kvh) * HD;
+    bf16* kdst = kc + (((long long)r * c_max + step) * nkv + kvh) * HD;
+    bf16* vdst = vc + (((long long)r * c_max + step) * nkv + kvh) * HD;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      const int d = lane * EPL + e;
+      const bf16 kb = __float2bfloat16(rot(knew, d));
+      const bf16 vb = __float2bfloat16(vnew[d]);
+      sNew[0][d] = kb;
+      sNew[1][d] = vb;
+      kdst[d] = kb;
+      vdst[d] = vb;
+    }
+  }
+  __syncthreads();
+  uint32_t qa[NKS][4];
+#pragma unroll
+  for (int ks = 0; ks < NKS; ++ks) {
+    const int row = (lane & 7) + ((lane >> 3) & 1) * 8;
+    const int piece = ks * 2 + (lane >> 4);
+    ldsm_x4(qa[ks], sQ + row * HD + ((piece ^ (row & 7)) << 3));
+  }
+  float oacc[NOB][4];
+#pragma unroll
+  for (int nb = 0; nb < NOB; ++nb)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) oacc[nb][e] = 0.f;
+  float mrun = -INFINITY, lrun = 0.f;
+  for (int c = 0; c < nchunks; ++c) {
+    bf16* sK = sKV + (c & 1) * STAGE;
+    bf16* sV = sK + CK * HD;
+    const int cbase = k0 + c * CK;
+    if (has_new && ctx - 1 >= cbase && ctx - 1 < cbase + CK && threadIdx.x < 2 * PPR) {
+      const int jj = ctx - 1 - cbase;
+      const int which = threadIdx.x / PPR, piece = threadIdx.x % PPR;
+      bf16* dst = (which ? sV : sK) + jj * HD + ((piece ^ (jj & 7)) << 3);
+      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(&sNew[which][piece * 8]);
+    }
+    if (c + 1 < nchunks) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    const int t0 = warp * 16;
+    const int nk = min(CK, k1 - cbase);
+    if (t0 < nk) {
+      float sacc[2][4];
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sacc[nb][e] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < NKS; ++ks) {
+        uint32_t b[4];
+        const int key = t0 + (lane & 7) + ((lane >> 4) & 1) * 8;
+        const int piece = ks * 2 + ((lane >> 3) & 1);
+        ldsm_x4(b, sK + key * HD + ((piece ^ (key & 7)) << 3));
+        mma_bf16_16816(sacc[0], qa[ks], b[0], b[1]);
+        mma_bf16_16816(sacc[1], qa[ks], b[2], b[3]);
+      }
+      float mloc = -INFINITY;
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int key = t0 + nb * 8 + (lane & 3) * 2 + e;
+          if (key >= nk) sacc[nb][e] = -INFINITY;
+          mloc = fmaxf(mloc, sacc[nb][e]);
+        }
+      mloc = fmaxf(mloc, __shfl_xor_sync(0xffffffffu, mloc, 1));
+      mloc = fmaxf(mloc, __shfl_xor_sync(0xffffffffu, mloc, 2));
+      const float mnew = fmaxf(mrun, mloc);
+      const float corr = (mrun == -INFINITY) ? 0.f : __expf(mrun - mnew);
+      uint32_t pa[4];
+      float lloc = 0.f;
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb) {
+        const float p0 = __expf(sacc[nb][0] - mnew);
+        const float p1 = __expf(sacc[nb][1] - mnew);
+        lloc += p0 + p1;
+        pa[nb * 2 + 0] = pack_bf16x2(p0, p1);
+        pa[nb * 2 + 1] = 0u;
+      }
+      lloc += __shfl_xor_sync(0xffffffffu, lloc, 1);
+      lloc += __shfl_xor_sync(0xffffffffu, lloc, 2);
+      lrun = lrun * corr + lloc;
+      mrun = mnew;
+#pragma unroll
+      for (int nb = 0; nb < NOB; ++nb) {
+        oacc[nb][0] *= corr;
+        oacc[nb][1] *= corr;
+      }
+#pragma unroll
+      for (int nb = 0; nb < NOB; nb += 2) {
+        uint32_t b[4];
+        const int key = t0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int piece = nb + (lane >> 4);
+        ldsm_x4_trans(b, sV + key * HD + ((piece ^ (key & 7)) << 3));
+        mma_bf16_16816(oacc[nb], pa, b[0], b[1]);
+        mma_bf16_16816(oacc[nb + 1], pa, b[2], b[3]);
+      }
+    }
+    __syncthreads();
+    if (c + 2 < nchunks) stage(c + 2);
+  }
+  if (trc) trace_stamp(412);
+  float (*sm_mrg)[MAXG][HD + 2] = reinterpret_cast<float (*)[MAXG][HD + 2]>(sm_kv_raw);
+  const int row_lo = lane >> 2;
+  if (row_lo < MAXG) {
+#pragma unroll
+    for (int nb = 0; nb < NOB; ++nb) {
+      sm_mrg[warp][row_lo][nb * 8 + (lane & 3) * 2 + 0] = oacc[nb][0];
+      sm_mrg[warp][row_lo][nb * 8 + (lane & 3) * 2 + 1] = oacc[nb][1];
+    }
+    if ((lane & 3) == 0) {
+      sm_mrg[warp][row_lo][HD] = mrun;
+      sm_mrg[warp][row_lo][HD + 1] = lrun;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < gq * HD; i += NT) {
+    const int h = i / HD, d = i % HD;
+    float m = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) m = fmaxf(m, sm_mrg[w][h][HD]);
+    float a_ = 0.f, l = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      const float mw = sm_mrg[w][h][HD];
+      const float cf = (mw == -INFINITY) ? 0.f : __expf(mw - m);
+      a_ += sm_mrg[w][h][d] * cf;
+      l += sm_mrg[w][h][HD + 1] * cf;
+    }
+    float* dst = part + (((long long)r * nq + kvh * gq + h) * nslots + psplit + sp) * (HD + 2);
+    dst[d] = a_;
+    if (d == 0) {
+      dst[HD] = m;
+      dst[HD + 1] = l;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    const int tk = atomicAdd(&tickets[r * nkv + kvh], 1);
+    s_nrows = (tk == nslots - 1);
+    s_rows[0] = r;
+    if (s_nrows) {
+      tickets[r * nkv + kvh] = 0;
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    }
+  }
+  __syncthreads();
+  if (trc) trace_stamp(413);
+  if (s_nrows > 0) attn_merge_rows<HD>(part, out, s_rows, 1, kvh, nq, gq, nslots, s_coef);
+  if (trc) trace_stamp(414 + (s_nrows > 0 ? 1 : 0));
 }
 
 
@@ -1085,22 +1658,31 @@ int iadr1_decode_attention_fused(const float* qkv, const float* cos_tab, const f
     const int nw = nsplit < 0 ? 2 : 4;
     nsplit = nsplit < 0 ? -nsplit : nsplit;
     if (nsplit > 32) return set_error("decode_attention_fused: nsplit %d out of range (1..32)", nsplit);
-    const size_t smem = (size_t)2 * 2 * 16 * nw * hd * 2;
-#define IADR1_DECODE_MMA(HD, NW)                                                                                     \
+    // three staging buffers (two chunks in flight behind the one being consumed) whenever the grid still fits one wave at
+    // the lower residency the extra shared memory allows; IADR1_DECODE_ATTN_STAGES=2 forces the two-buffer form
+    static const int forced = getenv("IADR1_DECODE_ATTN_STAGES") ? atoi(getenv("IADR1_DECODE_ATTN_STAGES")) : 0;
+    const size_t stage_b = (size_t)2 * 16 * nw * hd * 2;
+    const int per_sm3 = (int)((227 * 1024) / (3 * stage_b + 6 * 1024));
+    const bool three = nw == 4 && forced != 2 && per_sm3 >= 1 && (long long)rows * nkv * nsplit <= (long long)per_sm3 * 148;
+    const size_t smem = (three ? 3 : 2) * stage_b;
+#define IADR1_DECODE_MMA(HD, NW, NS)                                                                                 \
   do {                                                                                                               \
     static bool attr = false;                                                                                        \
     if (!attr) {                                                                                                     \
-      cudaFuncSetAttribute(decode_attn_mma_kernel<HD, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+      cudaFuncSetAttribute(decode_attn_mma_kernel<HD, NW, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                           (int)(NS * stage_b));                                                                     \
       attr = true;                                                                                                   \
     }                                                                                                                \
-    launch_kernel(decode_attn_mma_kernel<HD, NW>, dim3(rows, nkv, nsplit), dim3(NW * 32), smem, st, qkv, cos_tab,    \
+    launch_kernel(decode_attn_mma_kernel<HD, NW, NS>, dim3(rows, nkv, nsplit), dim3(NW * 32), smem, st, qkv, cos_tab, \
                   sin_tab, rope_delta, (const bf16*)kp, (const bf16*)vp, (bf16*)kc, (bf16*)vc, state, row_group,     \
                   row_plen, part, tickets, (bf16*)out, nq, nkv, p_max, c_max, max_pos, scale);                       \
   } while (0)
-    if (hd == 128 && nw == 4) IADR1_DECODE_MMA(128, 4);
-    else if (hd == 128) IADR1_DECODE_MMA(128, 2);
-    else if (nw == 4) IADR1_DECODE_MMA(64, 4);
-    else IADR1_DECODE_MMA(64, 2);
+    if (hd == 128 && nw == 4 && three) IADR1_DECODE_MMA(128, 4, 3);
+    else if (hd == 128 && nw == 4) IADR1_DECODE_MMA(128, 4, 2);
+    else if (hd == 128) IADR1_DECODE_MMA(128, 2, 2);
+    else if (nw == 4 && three) IADR1_DECODE_MMA(64, 4, 3);
+    else if (nw == 4) IADR1_DECODE_MMA(64, 4, 2);
+    else IADR1_DECODE_MMA(64, 2, 2);
 #undef IADR1_DECODE_MMA
     IADR1_CHECK_LAUNCH("decode_attention_mma");
     return 0;
@@ -1122,6 +1704,38 @@ int iadr1_decode_attention_fused(const float* qkv, const float* cos_tab, const f
   else return set_error("decode_attention_fused: head_dim %d unsupported (32, 64 or 128)", hd);
 #undef IADR1_DECODE_FUSED
   IADR1_CHECK_LAUNCH("decode_attention_fused");
+  return 0;
+}
+
+int iadr1_decode_attention_grouped(const float* qkv, const float* cos_tab, const float* sin_tab, const int* rope_delta,
+                                   const void* kp, const void* vp, void* kc, void* vc, const int* state, const int* row_plen,
+                                   float* part, int* tickets, void* out, int rows, int rows_per_group, int nq, int nkv, int hd,
+                                   int p_max, int c_max, int psplit, int csplit, int max_pos, float scale, void* stream) {
+  if (rows <= 0) return 0;
+  if (nq % nkv || nq / nkv > 8) return set_error("decode_attention_grouped: group size %d unsupported (max 8)", nq / nkv);
+  if (hd != 64 && hd != 128) return set_error("decode_attention_grouped: head_dim %d unsupported (64 or 128)", hd);
+  if (rows_per_group <= 0 || rows % rows_per_group) return set_error("decode_attention_grouped: rows must be a multiple of the group size");
+  if (psplit < 1 || csplit < 1 || psplit + csplit > 16) return set_error("decode_attention_grouped: bad splits %d + %d (at most 16 slots)", psplit, csplit);
+  const int n_groups = rows / rows_per_group, rblocks = (rows_per_group + 7) / 8;
+  const int n_pblocks = n_groups * rblocks * nkv * psplit;
+  const int grid = n_pblocks + rows * nkv * csplit;
+  const size_t smem = (size_t)2 * 2 * 64 * hd * 2;
+  cudaStream_t st = (cudaStream_t)stream;
+#define IADR1_DECODE_GROUPED(HD)                                                                                     \
+  do {                                                                                                               \
+    static bool attr = false;                                                                                        \
+    if (!attr) {                                                                                                     \
+      cudaFuncSetAttribute(decode_attn_grouped_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+      attr = true;                                                                                                   \
+    }                                                                                                                \
+    launch_kernel(decode_attn_grouped_kernel<HD>, dim3(grid), dim3(128), smem, st, qkv, cos_tab, sin_tab, rope_delta, \
+                  (const bf16*)kp, (const bf16*)vp, (bf16*)kc, (bf16*)vc, state, row_plen, part, tickets, (bf16*)out,  \
+                  rows_per_group, nq, nkv, p_max, c_max, max_pos, scale, psplit, csplit, n_pblocks);                   \
+  } while (0)
+  if (hd == 128) IADR1_DECODE_GROUPED(128);
+  else IADR1_DECODE_GROUPED(64);
+#undef IADR1_DECODE_GROUPED
+  IADR1_CHECK_LAUNCH("decode_attention_grouped");
   return 0;
 }
 

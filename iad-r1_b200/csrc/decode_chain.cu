@@ -82,10 +82,12 @@ __device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__floa
 
 struct Seg { int m0, kb0, kb1; };
 
-// This CTA's segments of one GEMM phase. Swapped products: the tiles x k-blocks units are cut into gridDim.x equal
-// contiguous runs (a run crossing a tile boundary yields one segment per tile). gate_up: whole-K tiles, round-robin.
+// This CTA's segments of one GEMM phase. Swapped products: every 128-feature tile is cut into `splits` k-ranges, one
+// (tile, k-range) per CTA - exactly ONE epilogue (staging + bulk reduction + publish) per CTA; equal contiguous runs of
+// k-block units (stream-K) balance the bytes a little better but make most CTAs cross a tile boundary and pay two. Only when
+// there are more tiles than CTAs do tiles go round-robin with the whole K. gate_up: whole-K tiles, round-robin.
 struct PhaseIter {
-  int swiglu, nkb, cur, end, step, ft;
+  int swiglu, nkb, cur, end, step, ft, per, splits;
   __device__ __forceinline__ void init(const ChainArgs& a, int p) {
     swiglu = (p == PH_GU);
     const int K = (p == PH_O) ? a.QH : (p == PH_DOWN ? a.I : a.H);
@@ -93,11 +95,13 @@ struct PhaseIter {
     ft = a.ft;
     if (!swiglu) {
       const int F = (p == PH_QKV) ? a.D : a.H;
-      const int units = ((F + CBM - 1) / CBM) * nkb;
-      const int per = (units + (int)gridDim.x - 1) / (int)gridDim.x;
-      cur = min(units, (int)blockIdx.x * per);
-      end = min(units, cur + per);
-      step = 0;
+      const int tiles = (F + CBM - 1) / CBM;
+      splits = max(1, min((int)gridDim.x / tiles, nkb));
+      per = (nkb + splits - 1) / splits;
+      splits = (nkb + per - 1) / per;               // drop empty k-ranges
+      cur = blockIdx.x;
+      end = tiles * splits;
+      step = gridDim.x;
     } else {
       cur = blockIdx.x;
       end = (a.I + a.ft - 1) / a.ft;
@@ -107,14 +111,12 @@ struct PhaseIter {
   __device__ __forceinline__ bool next(Seg& s) {
     if (cur >= end) return false;
     if (!swiglu) {
-      const int tile = cur / nkb, kb = cur - tile * nkb;
-      const int len = min(nkb - kb, end - cur);
-      s.m0 = tile * CBM; s.kb0 = kb; s.kb1 = kb + len;
-      cur += len;
+      const int tile = cur / splits, sp = cur - tile * splits;
+      s.m0 = tile * CBM; s.kb0 = sp * per; s.kb1 = min(nkb, s.kb0 + per);
     } else {
       s.m0 = cur * ft; s.kb0 = 0; s.kb1 = nkb;
-      cur += step;
     }
+    cur += step;
     return true;
   }
 };

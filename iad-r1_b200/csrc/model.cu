@@ -482,6 +482,24 @@ int iadr1_decode_head(void* handle, const iadr1_decode_t* e, int first, void* st
                       e->out_tokens, e->c_max, e->eos_id, e->pad_id, e->forbid_eos, first, s);
 }
 
+// rotary + KV append + attention of one layer for all rows in flight (shared-prefix form when the engine asks for it)
+static int decode_attention(const iadr1_model_cfg_t& c, const iadr1_decode_t* e, int i, cudaStream_t s) {
+  const long long kvw = (long long)c.nkv * c.hd;
+  const int R = e->R;
+  const char* kp = static_cast<const char*>(e->kp) + (long long)i * e->n_groups * e->p_max * kvw * 2;
+  const char* vp = static_cast<const char*>(e->vp) + (long long)i * e->n_groups * e->p_max * kvw * 2;
+  char* kc = static_cast<char*>(e->kc) + (long long)i * R * e->c_max * kvw * 2;
+  char* vc = static_cast<char*>(e->vc) + (long long)i * R * e->c_max * kvw * 2;
+  const float scale = 1.f / sqrtf((float)c.hd);
+  if (e->attn_psplit > 0 && e->nsplit > e->attn_psplit && (c.hd == 64 || c.hd == 128) && e->n_groups > 0 && R % e->n_groups == 0)
+    return iadr1_decode_attention_grouped(e->qkv, e->cos_tab, e->sin_tab, e->rope_delta, kp, vp, kc, vc, e->state, e->row_plen,
+                                          e->part, e->tickets, e->attn, R, R / e->n_groups, c.nq, c.nkv, c.hd, e->p_max, e->c_max,
+                                          e->attn_psplit, e->nsplit - e->attn_psplit, e->max_pos, scale, s);
+  return iadr1_decode_attention_fused(e->qkv, e->cos_tab, e->sin_tab, e->rope_delta, kp, vp, kc, vc, e->state, e->row_group,
+                                      e->row_plen, e->part, e->tickets, e->attn, R, c.nq, c.nkv, c.hd, e->p_max, e->c_max,
+                                      e->nsplit, e->max_pos, scale, s);
+}
+
 // lm_head + sampler on the already normalised rows in e->xn
 static int decode_head_normed(Model& m, const iadr1_decode_t* e, int first, cudaStream_t s) {
   const iadr1_model_cfg_t& c = m.c;
@@ -511,13 +529,7 @@ static int decode_step_chained(Model& m, const iadr1_decode_t* e, cudaStream_t s
   for (int i = 0; i < c.layers; ++i) {
     const bool last = i + 1 == c.layers;
     if (!last) TRY(layer_weights(m, i + 1, wn));
-    const char* kp = static_cast<const char*>(e->kp) + (long long)i * e->n_groups * e->p_max * kvw * 2;
-    const char* vp = static_cast<const char*>(e->vp) + (long long)i * e->n_groups * e->p_max * kvw * 2;
-    char* kc = static_cast<char*>(e->kc) + (long long)i * R * e->c_max * kvw * 2;
-    char* vc = static_cast<char*>(e->vc) + (long long)i * R * e->c_max * kvw * 2;
-    TRY(iadr1_decode_attention_fused(e->qkv, e->cos_tab, e->sin_tab, e->rope_delta, kp, vp, kc, vc, e->state, e->row_group,
-                                     e->row_plen, e->part, e->tickets, e->attn, R, c.nq, c.nkv, c.hd, e->p_max, e->c_max,
-                                     e->nsplit, e->max_pos, 1.f / sqrtf((float)c.hd), s));
+    TRY(decode_attention(c, e, i, s));
     TRY(launch_decode_chain(R, H, I, QH, D, c.rms_eps, e->h, e->xn, e->act, e->qkv, e->attn, w.o->p, w.ln2->p, w.gu->p, w.down->p,
                             last ? nw->p : wn.ln1->p, last ? nullptr : wn.qkv->p, last ? nullptr : wn.qkv_b->p, 1, 1, last ? 0 : 1,
                             e->chain_counters + (i + 1) * 8, s));
@@ -544,13 +556,7 @@ int iadr1_decode_step(void* handle, const iadr1_decode_t* e, void* stream) {
     TRY(layer_weights(m, i, w));
     TRY(iadr1_rmsnorm_f32in(e->h, w.ln1->p, e->xn, R, H, c.rms_eps, e->qkv, D, s));
     TRY(skinny(w.qkv->p, e->xn, e->qkv, D, H, R, sk_qkv, w.qkv_b->p, e->block_n, s));
-    const char* kp = static_cast<const char*>(e->kp) + (long long)i * e->n_groups * e->p_max * kvw * 2;
-    const char* vp = static_cast<const char*>(e->vp) + (long long)i * e->n_groups * e->p_max * kvw * 2;
-    char* kc = static_cast<char*>(e->kc) + (long long)i * R * e->c_max * kvw * 2;
-    char* vc = static_cast<char*>(e->vc) + (long long)i * R * e->c_max * kvw * 2;
-    TRY(iadr1_decode_attention_fused(e->qkv, e->cos_tab, e->sin_tab, e->rope_delta, kp, vp, kc, vc, e->state, e->row_group,
-                                     e->row_plen, e->part, e->tickets, e->attn, R, c.nq, c.nkv, c.hd, e->p_max, e->c_max,
-                                     e->nsplit, e->max_pos, 1.f / sqrtf((float)c.hd), s));
+    TRY(decode_attention(c, e, i, s));
     TRY(skinny(w.o->p, e->attn, e->h, H, QH, R, sk_o, nullptr, e->block_n, s));
     TRY(iadr1_rmsnorm_f32in(e->h, w.ln2->p, e->xn, R, H, c.rms_eps, nullptr, 0, s));
     {

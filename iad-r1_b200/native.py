@@ -41,7 +41,7 @@ class DecodeState(C.Structure):
                 ("tickets", C.c_void_p), ("act", C.c_void_p), ("logits", C.c_void_p),
                 ("cos_tab", C.c_void_p), ("sin_tab", C.c_void_p),
                 ("temperature", C.c_float), ("top_k", C.c_int), ("top_p", C.c_float), ("eos_id", C.c_int),
-                ("pad_id", C.c_int), ("forbid_eos", C.c_int), ("chain_counters", C.c_void_p)]
+                ("pad_id", C.c_int), ("forbid_eos", C.c_int), ("chain_counters", C.c_void_p), ("attn_psplit", C.c_int)]
 
 
 class VisionGeom(C.Structure):

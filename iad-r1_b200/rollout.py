@@ -77,9 +77,26 @@ class RolloutEngine:
             if os.environ.get("IADR1_DECODE_ATTN_NSPLIT"):
                 self.nsplit = max(1, min(16, int(os.environ["IADR1_DECODE_ATTN_NSPLIT"])))
             self.attn_nw = nw
+            # shared-prefix form (decode.cu: decode_attn_grouped_kernel): the prompt keys once per group in P-kind CTAs, each
+            # row's own keys in C-kind CTAs, all in one wave of <= 3 CTAs per SM; `part` then holds psplit + csplit slots
+            # (measured at 3B widths, P = 297, 128 rows: 31 us per layer against 22 us for the per-row kernel - building the
+            # 64-row query tile and merging 4-6 slots costs more than the shared staging saves while the prompt is about half
+            # of the context; it is the default only when the prompt dominates, e.g. LLaVA-OneVision's 3.7 k image tokens)
+            grouped = os.environ.get("IADR1_DECODE_ATTN_GROUPED", "auto")
+            if (grouped == "1" or (grouped == "auto" and p_max >= 4 * c_max)) and nw == 4:
+                budget, rblocks = 3 * NUM_SMS, (num_generations + 7) // 8
+                # prompt CTAs should take about as long as the row CTAs (mid-rollout: c_max / 2 keys): ~2 chunks of 64 keys each
+                ps = max(1, min(8, (p_max + 127) // 128))
+                if os.environ.get("IADR1_DECODE_ATTN_PSPLIT"):
+                    ps = max(1, min(8, int(os.environ["IADR1_DECODE_ATTN_PSPLIT"])))
+                while ps > 1 and max_groups * rblocks * nkv * ps > budget // 2:
+                    ps -= 1
+                cs_ = max(1, min(8, (budget - max_groups * rblocks * nkv * ps) // (R * nkv)))
+                self.attn_psplit, self.nsplit = ps, ps + cs_
         else:
             self.nsplit = max(1, min(32, (p_max + c_max + 127) // 128))   # scalar kernel: one 128-key chunk per CTA
             self.attn_nw = 4
+        self.attn_psplit = getattr(self, "attn_psplit", 0)
         self.part = torch.zeros(R, t.num_heads, self.nsplit, hd + 2, dtype=f32, device=dev)
         self.tickets = torch.zeros(R * nkv, dtype=i32, device=dev)
         self.chain_counters = torch.zeros((t.num_layers + 1) * 8, dtype=i32, device=dev)   # persistent decode-layer chain
@@ -149,7 +166,7 @@ class RolloutEngine:
                 self.xn.data_ptr(), self.qkv.data_ptr(), self.attn.data_ptr(), self.part.data_ptr(), self.tickets.data_ptr(),
                 self.act.data_ptr(), self.logits.data_ptr(), self.cos_tab.data_ptr(), self.sin_tab.data_ptr(),
                 self.temperature, self.top_k, self.top_p, c.eos_token_id, c.pad_token_id, int(self.forbid_eos),
-                self.chain_counters.data_ptr())
+                self.chain_counters.data_ptr(), self.attn_psplit)
         return self._dstate
 
     def _decode_step_body(self):

@@ -172,6 +172,14 @@ int iadr1_decode_attention_fused(const float* qkv, const float* cos_tab, const f
                                  const int* row_group, const int* row_plen, float* part, int* tickets, void* out, int rows,
                                  int nq, int nkv, int hd, int p_max, int c_max, int nsplit, int max_pos, float scale,
                                  void* stream);
+/* Shared-prefix form of the same step: the prompt keys are processed ONCE per group (8 rows x gq heads = full tensor-core
+ * tiles; K/V staged once for the group's rows), each row's own keys per row; `part` holds psplit + csplit slots per (row, head),
+ * `tickets` one counter per (row, kv head). Rows of a group are consecutive and share the prompt (vLLM prefix caching,
+ * ref: train/stage_rl/trainer/sc_grpo_trainer.py:351). head_dim 64 or 128.                                              */
+int iadr1_decode_attention_grouped(const float* qkv, const float* cos_tab, const float* sin_tab, const int* rope_delta,
+                                   const void* kp, const void* vp, void* kc, void* vc, const int* state, const int* row_plen,
+                                   float* part, int* tickets, void* out, int rows, int rows_per_group, int nq, int nkv, int hd,
+                                   int p_max, int c_max, int psplit, int csplit, int max_pos, float scale, void* stream);
 /* temperature -> top-k (ties kept) -> top-p -> multinomial; SamplingParams at sc_grpo_trainer.py:353-358.
  * The Philox seed is `seed ^ (state[4] | state[5] << 32)`: callers that replay a captured graph keep the per-call seed
  * in the device-resident state words and pass seed = 0 (graph arguments are frozen at capture).                     */
@@ -246,6 +254,7 @@ typedef struct iadr1_decode_t {
   const float* cos_tab; const float* sin_tab;
   float temperature; int top_k; float top_p; int eos_id, pad_id, forbid_eos;
   unsigned int* chain_counters;   /* (layers + 1) * 8 words for the persistent decode-layer chain (R <= 128); NULL: one kernel per op */
+  int attn_psplit;                /* > 0: shared-prefix decode attention with this many prompt splits; nsplit - attn_psplit completion splits */
 } iadr1_decode_t;
 typedef void (*iadr1_layer_cb)(int layer, void* user);
 /* What the vision tower derives from the image grids (host-computed, device-resident; HF get_window_index / rot_pos_emb,

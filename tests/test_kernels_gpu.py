@@ -527,6 +527,60 @@ def test_decode_attention_fused(ops, nq, nkv, hd, nsplit):
             close(out[r].view(nq, hd)[h], ref, 2 ** -6, f"decode attention row {r} head {h}")
 
 
+@pytest.mark.parametrize("nq,nkv,hd,G,n_groups,psplit,csplit,step", [
+    (16, 2, 128, 8, 2, 3, 1, 57), (16, 2, 128, 8, 2, 1, 2, 0), (14, 2, 128, 16, 1, 4, 2, 90), (12, 2, 128, 4, 3, 2, 1, 33),
+    (14, 2, 64, 8, 2, 2, 2, 64), (4, 2, 64, 3, 2, 5, 3, 17), (8, 1, 128, 1, 4, 2, 1, 5)])
+def test_decode_attention_grouped(ops, nq, nkv, hd, G, n_groups, psplit, csplit, step):
+    """Shared-prefix decode attention (prompt keys once per group in full m16 tiles of 2 rows x 8 heads, each row's own keys
+    per row, one launch, ticket merge over psplit + csplit slots) against the same torch restatement as the per-row kernel:
+    keys of a row = the prompt prefix of its group + its own slab + the token being decoded (rotary + KV append)."""
+    from iad_r1_b200 import lib as L
+    torch.manual_seed(nq * 7 + hd + G)
+    dev = "cuda"
+    R, p_max, c_max = G * n_groups, 200, 100
+    plens = [150, 200, 37, 1][:n_groups] if n_groups <= 4 else None
+    plen = torch.tensor([plens[r // G] for r in range(R)], dtype=torch.int32, device=dev)
+    delta = torch.tensor([(-20, 0, 3, 7)[r // G] for r in range(R)], dtype=torch.int32, device=dev)
+    D = (nq + 2 * nkv) * hd
+    qkv = torch.randn(R, D, device=dev)
+    kp, vp = rnd(n_groups, p_max, nkv, hd), rnd(n_groups, p_max, nkv, hd)
+    kc, vc = rnd(R, c_max, nkv, hd), rnd(R, c_max, nkv, hd)
+    kc0, vc0 = kc.clone(), vc.clone()
+    max_pos = p_max + c_max + 8
+    ang = torch.arange(max_pos, device=dev, dtype=torch.float32)[:, None] * (1.0 / (1e6 ** (torch.arange(0, hd, 2, device=dev).float() / hd)))
+    emb = torch.cat((ang, ang), -1)
+    cos_t, sin_t = emb.cos().contiguous(), emb.sin().contiguous()
+    state = torch.tensor([step, 0, R, 0, 0, 0, 0, 0], dtype=torch.int32, device=dev)
+    part = torch.zeros(R, nq, psplit + csplit, hd + 2, device=dev)
+    tickets = torch.zeros(R * nkv, dtype=torch.int32, device=dev)
+    out = torch.zeros(R, nq * hd, dtype=bf16, device=dev)
+    scale = hd ** -0.5
+    for _ in range(2):  # second call checks the ticket re-arm
+        kc.copy_(kc0); vc.copy_(vc0)
+        L.check(L.lib().iadr1_decode_attention_grouped(
+            qkv.data_ptr(), cos_t.data_ptr(), sin_t.data_ptr(), delta.data_ptr(), kp.data_ptr(), vp.data_ptr(), kc.data_ptr(),
+            vc.data_ptr(), state.data_ptr(), plen.data_ptr(), part.data_ptr(), tickets.data_ptr(), out.data_ptr(),
+            R, G, nq, nkv, hd, p_max, c_max, psplit, csplit, max_pos, scale, L.stream_ptr()))
+    torch.cuda.synchronize()
+    assert (tickets == 0).all()
+    g = nq // nkv
+    for r in range(R):
+        P = int(plen[r]); pos = P + step + int(delta[r])
+        c, s_ = cos_t[pos].to(bf16), sin_t[pos].to(bf16)
+        x = qkv[r].to(bf16).view(nq + 2 * nkv, hd)
+        qk = (x[:nq + nkv] * c) + (_rot_half_f(x[:nq + nkv]) * s_)          # bf16 arithmetic, as HF
+        q, knew, vnew = qk[:nq].float(), qk[nq:], x[nq + nkv:]
+        assert torch.equal(kc[r, step], knew) and torch.equal(vc[r, step], vnew), "KV append"
+        assert torch.equal(kc[r, :step], kc0[r, :step]) and torch.equal(kc[r, step + 1:], kc0[r, step + 1:])
+        K = torch.cat([kp[r // G, :P], kc0[r, :step], knew[None]], 0).float()   # [ctx, nkv, hd]
+        V = torch.cat([vp[r // G, :P], vc0[r, :step], vnew[None]], 0).float()
+        for h in range(nq):
+            kvh = h // g
+            p_ = torch.softmax((K[:, kvh] @ q[h]) * scale, 0)
+            ref = p_ @ V[:, kvh]
+            close(out[r].view(nq, hd)[h], ref, 2 ** -6, f"grouped decode attention row {r} head {h}")
+
+
 # ---------------------------------------------------------------------------------------------- image preprocessing
 @pytest.mark.parametrize("hw,max_pixels", [((448, 448), 480000), ((300, 500), 480000), ((1000, 700), 480000), ((90, 120), 12845056)])
 def test_image_preprocess_matches_hf_processor(ops, hw, max_pixels):

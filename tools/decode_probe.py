@@ -97,6 +97,22 @@ if os.environ.get("PROBE_TRACE"):
             v = vals[vals[:, 0] == tag][:, 1]
             if len(v):
                 print(f"    {nm[tag]:40s} {np.median(v):10.0f}")
+    am = marks[(marks[:, 0] >= 400) & (marks[:, 0] < 420)]
+    marks = marks[(marks[:, 0] < 400) | (marks[:, 0] >= 420)]
+    if len(am):
+        # grouped decode attention: first P-kind CTA (tags 400..406) and first C-kind CTA (410..415) of the last launches
+        nm = {400: "P-kind CTA 0 reaches wait", 401: "  wait returns", 402: "  Q tile built (64 rows)", 403: "  chunk loop done",
+              404: "  partials + tickets done", 405: "  end (no merge)", 406: "  end (merged rows)",
+              410: "C-kind CTA 0 reaches wait", 411: "  wait returns", 412: "  chunk loop done", 413: "  partials + ticket done",
+              414: "  end (no merge)", 415: "  end (merged)"}
+        for first, lo, hi in ((400, 400, 410), (410, 410, 420)):
+            sel = am[(am[:, 0] >= lo) & (am[:, 0] < hi)]
+            st_ = np.nonzero(sel[:, 0] == first)[0]
+            if len(st_) >= 3:
+                seg = sel[st_[-2]:st_[-1]]
+                t0 = seg[seg[:, 0] == first + 1][0, 1] if (seg[:, 0] == first + 1).any() else seg[0, 1]
+                for tag, tm in seg:
+                    print(f"    {nm.get(int(tag), int(tag)):32s} {(tm - t0) / 1e3:8.2f}")
     if len(marks):
         # last replay, one mid-stack chain launch: times relative to the kernel's dependency wait returning
         mk = marks[-(len(marks) // reps):]
