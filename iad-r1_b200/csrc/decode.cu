@@ -430,12 +430,18 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// Transposes an 8 x 8 matrix of b16 held one row-pair per lane (lane l: row l / 4, columns 2 (l % 4), + 1) across the warp.
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a) {
+  uint32_t d;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+  return d;
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&v);
 }
 
-template <int HD, int NW, int NS>
+template <int HD, int NW, int NS, int TR>
 __global__ void __launch_bounds__(NW * 32) decode_attn_mma_kernel(
     const float* __restrict__ qkv, const float* __restrict__ cos_tab, const float* __restrict__ sin_tab,
     const int* __restrict__ rope_delta, const bf16* __restrict__ kp, const bf16* __restrict__ vp, bf16* __restrict__ kc,
@@ -556,19 +562,37 @@ __global__ void __launch_bounds__(NW * 32) decode_attn_mma_kernel(
     }
   }
   __syncthreads();
-  uint32_t qa[NKS][4];
+  // TR = 1 ("transposed"): the 16 KEYS of a warp are the M rows of the MMA tiles and the (up to 8) query heads the N = 8
+  // columns - S^T = K Q^T, O^T = V^T P^T - so no tile row is padding: half the mma.sync instructions of the heads-as-M form
+  // (TR = 0: 8 heads padded to m16), which is what bounds this kernel (one m16n8k16 per ~32 cycles per SM sub-core).
+  constexpr int NOA = TR ? HD / 16 : HD / 8;
+  uint32_t qa[TR ? 1 : NKS][4];
+  uint32_t qb[TR ? NKS : 1][2];
+  if constexpr (TR) {
 #pragma unroll
-  for (int ks = 0; ks < NKS; ++ks) {
-    const int row = (lane & 7) + ((lane >> 3) & 1) * 8;
-    const int piece = ks * 2 + (lane >> 4);
-    ldsm_x4(qa[ks], sQ + row * HD + ((piece ^ (row & 7)) << 3));
+    for (int ks = 0; ks < NKS; ks += 2) {   // B fragments of Q^T: [n = head][k = d] rows of sQ, two k-steps per ldmatrix.x4
+      uint32_t t4[4];
+      const int row = lane & 7;
+      const int piece = ks * 2 + (lane >> 3);
+      ldsm_x4(t4, sQ + row * HD + ((piece ^ (row & 7)) << 3));
+      qb[ks][0] = t4[0]; qb[ks][1] = t4[1];
+      qb[ks + 1][0] = t4[2]; qb[ks + 1][1] = t4[3];
+    }
+  } else {
+#pragma unroll
+    for (int ks = 0; ks < NKS; ++ks) {
+      const int row = (lane & 7) + ((lane >> 3) & 1) * 8;
+      const int piece = ks * 2 + (lane >> 4);
+      ldsm_x4(qa[ks], sQ + row * HD + ((piece ^ (row & 7)) << 3));
+    }
   }
-  float oacc[NOB][4];
+  float oacc[NOA][4];
 #pragma unroll
-  for (int nb = 0; nb < NOB; ++nb)
+  for (int nb = 0; nb < NOA; ++nb)
 #pragma unroll
     for (int e = 0; e < 4; ++e) oacc[nb][e] = 0.f;
-  float mrun = -INFINITY, lrun = 0.f;      // of query row lane / 4 (rows >= 8 are padding)
+  float mrun = -INFINITY, lrun = 0.f;      // TR = 0: of query row lane / 4 (rows >= 8 are padding)
+  float mrun2[2] = {-INFINITY, -INFINITY}, lrun2[2] = {0.f, 0.f};   // TR = 1: of heads 2 * (lane % 4), + 1
 
   for (int c = 0; c < nchunks; ++c) {
     bf16* sK = sKV + (c % NS) * STAGE;
@@ -587,6 +611,57 @@ __global__ void __launch_bounds__(NW * 32) decode_attn_mma_kernel(
     __syncthreads();
     const int t0 = warp * 16;                   // this warp's 16 keys of the chunk
     const int nk = min(CK, k1 - cbase);         // valid keys in the chunk
+    if constexpr (TR) {
+    if (t0 < nk) {
+      float sacc[4] = {0.f, 0.f, 0.f, 0.f};     // S^T tile: keys t0 + lane / 4 (+ 8) x heads 2 * (lane % 4) (+ 1)
+#pragma unroll
+      for (int ks = 0; ks < NKS; ++ks) {
+        uint32_t a4[4];
+        const int key = t0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int piece = ks * 2 + (lane >> 4);
+        ldsm_x4(a4, sK + key * HD + ((piece ^ (key & 7)) << 3));
+        mma_bf16_16816(sacc, a4, qb[ks][0], qb[ks][1]);
+      }
+      if (t0 + (lane >> 2) >= nk) sacc[0] = sacc[1] = -INFINITY;
+      if (t0 + (lane >> 2) + 8 >= nk) sacc[2] = sacc[3] = -INFINITY;
+      uint32_t pb[2];
+      float corr[2], pv[4];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float m = fmaxf(sacc[e], sacc[2 + e]);   // over the 16 keys: lanes with the same lane % 4
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
+        const float mnew = fmaxf(mrun2[e], m);  // finite: key t0 is valid
+        corr[e] = (mrun2[e] == -INFINITY) ? 0.f : __expf(mrun2[e] - mnew);
+        pv[e] = __expf(sacc[e] - mnew);
+        pv[2 + e] = __expf(sacc[2 + e] - mnew);
+        float l = pv[e] + pv[2 + e];
+        l += __shfl_xor_sync(0xffffffffu, l, 4);
+        l += __shfl_xor_sync(0xffffffffu, l, 8);
+        l += __shfl_xor_sync(0xffffffffu, l, 16);
+        lrun2[e] = lrun2[e] * corr[e] + l;
+        mrun2[e] = mnew;
+      }
+      // P^T as the B operand: transpose the two 8 x 8 [key][head] tiles across the warp
+      pb[0] = movmatrix_trans(pack_bf16x2(pv[0], pv[1]));
+      pb[1] = movmatrix_trans(pack_bf16x2(pv[2], pv[3]));
+#pragma unroll
+      for (int mt = 0; mt < NOA; ++mt) {
+        oacc[mt][0] *= corr[0]; oacc[mt][1] *= corr[1];
+        oacc[mt][2] *= corr[0]; oacc[mt][3] *= corr[1];
+      }
+#pragma unroll
+      for (int mt = 0; mt < NOA; ++mt) {        // O^T[16 d x 8 heads] += V^T[16 d x 16 keys] P^T
+        uint32_t a4[4];
+        const int key = t0 + (lane & 7) + ((lane >> 4) & 1) * 8;
+        const int piece = mt * 2 + ((lane >> 3) & 1);
+        ldsm_x4_trans(a4, sV + key * HD + ((piece ^ (key & 7)) << 3));
+        mma_bf16_16816(oacc[mt], a4, pb[0], pb[1]);
+      }
+    }
+    }
+    if constexpr (!TR) {
     if (t0 < nk) {
       float sacc[2][4];
 #pragma unroll
@@ -644,15 +719,29 @@ __global__ void __launch_bounds__(NW * 32) decode_attn_mma_kernel(
         mma_bf16_16816(oacc[nb + 1], pa, b[2], b[3]);
       }
     }
+    }
     __syncthreads();                            // every warp is done with this chunk's buffer:
     if (c + NS < nchunks) stage(c + NS);        // re-fill it NS chunks ahead
   }
   // ---- merge the 4 warps (rows = heads < gq live in c0/c1 of the lanes with lane/4 == head); staging memory re-used
   float (*sm_mrg)[MAXG][HD + 2] = reinterpret_cast<float (*)[MAXG][HD + 2]>(sm_kv_raw);   // NW x MAXG x (HD + 2) floats <= staging
   const int row_lo = lane >> 2;
-  if (row_lo < MAXG) {
+  if constexpr (TR) {
 #pragma unroll
-    for (int nb = 0; nb < NOB; ++nb) {
+    for (int mt = 0; mt < NOA; ++mt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        sm_mrg[warp][(lane & 3) * 2 + (e & 1)][mt * 16 + row_lo + (e >> 1) * 8] = oacc[mt][e];
+    if (row_lo == 0) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        sm_mrg[warp][(lane & 3) * 2 + e][HD] = mrun2[e];
+        sm_mrg[warp][(lane & 3) * 2 + e][HD + 1] = lrun2[e];
+      }
+    }
+  } else if (row_lo < MAXG) {
+#pragma unroll
+    for (int nb = 0; nb < NOA; ++nb) {
       sm_mrg[warp][row_lo][nb * 8 + (lane & 3) * 2 + 0] = oacc[nb][0];
       sm_mrg[warp][row_lo][nb * 8 + (lane & 3) * 2 + 1] = oacc[nb][1];
     }
@@ -1665,24 +1754,29 @@ int iadr1_decode_attention_fused(const float* qkv, const float* cos_tab, const f
     const int per_sm3 = (int)((227 * 1024) / (3 * stage_b + 6 * 1024));
     const bool three = nw == 4 && forced != 2 && per_sm3 >= 1 && (long long)rows * nkv * nsplit <= (long long)per_sm3 * 148;
     const size_t smem = (three ? 3 : 2) * stage_b;
-#define IADR1_DECODE_MMA(HD, NW, NS)                                                                                 \
+    static const bool transposed = !(getenv("IADR1_DECODE_ATTN_TR") && atoi(getenv("IADR1_DECODE_ATTN_TR")) == 0);
+#define IADR1_DECODE_MMA(HD, NW, NS, TR)                                                                             \
   do {                                                                                                               \
     static bool attr = false;                                                                                        \
     if (!attr) {                                                                                                     \
-      cudaFuncSetAttribute(decode_attn_mma_kernel<HD, NW, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+      cudaFuncSetAttribute(decode_attn_mma_kernel<HD, NW, NS, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
                            (int)(NS * stage_b));                                                                     \
       attr = true;                                                                                                   \
     }                                                                                                                \
-    launch_kernel(decode_attn_mma_kernel<HD, NW, NS>, dim3(rows, nkv, nsplit), dim3(NW * 32), smem, st, qkv, cos_tab, \
+    launch_kernel(decode_attn_mma_kernel<HD, NW, NS, TR>, dim3(rows, nkv, nsplit), dim3(NW * 32), smem, st, qkv, cos_tab, \
                   sin_tab, rope_delta, (const bf16*)kp, (const bf16*)vp, (bf16*)kc, (bf16*)vc, state, row_group,     \
                   row_plen, part, tickets, (bf16*)out, nq, nkv, p_max, c_max, max_pos, scale);                       \
   } while (0)
-    if (hd == 128 && nw == 4 && three) IADR1_DECODE_MMA(128, 4, 3);
-    else if (hd == 128 && nw == 4) IADR1_DECODE_MMA(128, 4, 2);
-    else if (hd == 128) IADR1_DECODE_MMA(128, 2, 2);
-    else if (nw == 4 && three) IADR1_DECODE_MMA(64, 4, 3);
-    else if (nw == 4) IADR1_DECODE_MMA(64, 4, 2);
-    else IADR1_DECODE_MMA(64, 2, 2);
+    if (hd == 128 && nw == 4 && three && transposed) IADR1_DECODE_MMA(128, 4, 3, 1);
+    else if (hd == 128 && nw == 4 && three) IADR1_DECODE_MMA(128, 4, 3, 0);
+    else if (hd == 128 && nw == 4 && transposed) IADR1_DECODE_MMA(128, 4, 2, 1);
+    else if (hd == 128 && nw == 4) IADR1_DECODE_MMA(128, 4, 2, 0);
+    else if (hd == 128) IADR1_DECODE_MMA(128, 2, 2, 0);
+    else if (nw == 4 && three && transposed) IADR1_DECODE_MMA(64, 4, 3, 1);
+    else if (nw == 4 && three) IADR1_DECODE_MMA(64, 4, 3, 0);
+    else if (nw == 4 && transposed) IADR1_DECODE_MMA(64, 4, 2, 1);
+    else if (nw == 4) IADR1_DECODE_MMA(64, 4, 2, 0);
+    else IADR1_DECODE_MMA(64, 2, 2, 0);
 #undef IADR1_DECODE_MMA
     IADR1_CHECK_LAUNCH("decode_attention_mma");
     return 0;
