@@ -315,7 +315,7 @@ def run_ours(args):
         kv_avg = (GA * p_len + GA * G * (Cl / 2.0)) * kv_tok
         step_bytes = wd + wh + kv_avg
         dec_ms = phases.get("rollout", float("nan")) / max(1, Cl)
-        dec = {"bound": "hbm", "kernel": f"decode step (CUDA graph: {t_.num_layers} x [rmsnorm, qkv, attention, o, rmsnorm, gate_up+SwiGLU, down] + lm_head + sampler)",
+        dec = {"bound": "hbm", "kernel": f"decode step (CUDA graph: {t_.num_layers} x [attention, persistent chain: o -> rmsnorm -> gate_up+SwiGLU -> down -> rmsnorm -> qkv] + lm_head + sampler)",
                "achieved": step_bytes / (dec_ms / 1e3) / 1e9, "peak": hbm, "unit": "GB/s", "peak_source": f"hbm_gbs, {src}",
                "bytes_per_step": step_bytes, "ms_per_decode_step": dec_ms}
         dec["frac"] = dec["achieved"] / hbm
