@@ -13,8 +13,25 @@ from .params import ParamStore
 
 
 def load_config(path: str) -> VLMConfig:
+    """config.json -> VLMConfig. The ORIGINAL dict (and generation_config.json when present) is carried in `cfg.extra` so that a
+    later `save_pretrained` writes it back unchanged (bos / sliding-window / max_position_embeddings / the full eos list ...:
+    HF and vLLM consumers of the saved directory get the source checkpoint's defaults), and the rollout stops on every id of the
+    generation config's eos list, as the reference's vLLM engine does."""
     with open(os.path.join(path, "config.json")) as f:
-        return VLMConfig.from_hf_dict(json.load(f))
+        raw = json.load(f)
+    cfg = VLMConfig.from_hf_dict(raw)
+    cfg.extra["hf_config"] = raw
+    gpath = os.path.join(path, "generation_config.json")
+    if os.path.exists(gpath):
+        with open(gpath) as f:
+            gen = json.load(f)
+        cfg.extra["generation_config"] = gen
+        eos = gen.get("eos_token_id")
+        if isinstance(eos, list):
+            cfg.extra["eos_token_ids"] = [int(x) for x in eos]
+        elif eos is not None:
+            cfg.extra["eos_token_ids"] = [int(eos)]
+    return cfg
 
 
 def load_state_dict(path: str) -> dict:
@@ -46,7 +63,10 @@ def save_pretrained(ps: ParamStore, path: str, max_shard_bytes: int = 5 * 2 ** 3
     from safetensors.torch import save_file
     os.makedirs(path, exist_ok=True)
     with open(os.path.join(path, "config.json"), "w") as f:
-        json.dump(ps.cfg.to_hf_dict(), f, indent=2)
+        json.dump(ps.cfg.extra.get("hf_config") or ps.cfg.to_hf_dict(), f, indent=2)   # the loaded config travels unchanged
+    if ps.cfg.extra.get("generation_config"):
+        with open(os.path.join(path, "generation_config.json"), "w") as f:
+            json.dump(ps.cfg.extra["generation_config"], f, indent=2)
     sd = {k: v.cpu() for k, v in ps.hf_state_dict().items()}
     shards, cur, cur_bytes = [], {}, 0
     for k, v in sd.items():

@@ -25,7 +25,7 @@ using bf16 = __nv_bfloat16;
 // Device-resident rollout state (int32 words). Host writes it once per rollout.
 enum StateWord : int {
   ST_STEP = 0,       // index of the completion token fed this step (KV slot); logits predict token ST_STEP + 1
-  ST_RESERVED = 1,
+  ST_EOS2 = 1,       // second stop token + 1 (generation_config.json lists several eos ids; 0 = none)
   ST_UNFINISHED = 2, // rows that have not produced EOS yet (host polls for early exit)
   ST_SEED_LO = 4,    // per-generate() sampling seed kept in DEVICE memory (XORed with the kernel's seed argument): a
   ST_SEED_HI = 5,    // captured CUDA graph replays with frozen arguments, so the seed must not live in them
@@ -1417,7 +1417,7 @@ constexpr int kMaxCand = 2048;  // candidate pool for the top-k selection
 // Applies `f(x, index)` to every logit of the row with 16-byte loads, four requests in flight per thread (the scan is
 // L2-latency-bound, not bandwidth-bound).
 template <typename F>
-__device__ __forceinline__ void scan_row(const float* __restrict__ lg, int V, int eos_id, int forbid_eos, F f) {
+__device__ __forceinline__ void scan_row(const float* __restrict__ lg, int V, int eos_id, int eos2, int forbid_eos, F f) {
   const int V4 = ((reinterpret_cast<uintptr_t>(lg) & 15) == 0) ? (V >> 2) : 0;
   const float4* lg4 = reinterpret_cast<const float4*>(lg);
   for (int i0 = threadIdx.x; i0 < V4; i0 += 4 * blockDim.x) {
@@ -1435,12 +1435,12 @@ __device__ __forceinline__ void scan_row(const float* __restrict__ lg, int V, in
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int idx = 4 * i + e;
-          f((forbid_eos && idx == eos_id) ? -INFINITY : xs[e], idx);
+          f((forbid_eos && (idx == eos_id || idx == eos2)) ? -INFINITY : xs[e], idx);
         }
       }
     }
   }
-  for (int i = 4 * V4 + threadIdx.x; i < V; i += blockDim.x) f((forbid_eos && i == eos_id) ? -INFINITY : lg[i], i);
+  for (int i = 4 * V4 + threadIdx.x; i < V; i += blockDim.x) f((forbid_eos && (i == eos_id || i == eos2)) ? -INFINITY : lg[i], i);
 }
 
 // Top-k threshold search without sorting or histograms: (1) row max; (2) how many logits lie within delta_i of the max,
@@ -1467,6 +1467,7 @@ __global__ void __launch_bounds__(1024) sample_kernel(const float* __restrict__ 
   const float* lg = logits + (long long)r * V;
   // `first`: logits come from the prefill (predict completion token 0); else they predict token step + 1.
   const int out_pos = first ? 0 : state[ST_STEP] + 1;
+  const int eos2 = state[ST_EOS2] - 1;
   if (out_pos >= c_max) return;
   if (finished[r]) {
     if (threadIdx.x == 0) {
@@ -1478,7 +1479,7 @@ __global__ void __launch_bounds__(1024) sample_kernel(const float* __restrict__ 
   const int k = min(max(top_k, 1), 128);
   // ---- (1) row max ----
   float mx = -INFINITY;
-  scan_row(lg, V, eos_id, forbid_eos, [&](float x, int) { mx = fmaxf(mx, x); });
+  scan_row(lg, V, eos_id, eos2, forbid_eos, [&](float x, int) { mx = fmaxf(mx, x); });
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if (lane == 0) s_red[warp] = mx;
@@ -1493,7 +1494,7 @@ __global__ void __launch_bounds__(1024) sample_kernel(const float* __restrict__ 
     const float base = round == 0 ? 1.f : (round == 1 ? 16.f : 256.f);
     const float dl[8] = {base, 2 * base, 3 * base, 4 * base, 6 * base, 8 * base, 12 * base, 16 * base};
     int c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    scan_row(lg, V, eos_id, forbid_eos, [&](float x, int) {
+    scan_row(lg, V, eos_id, eos2, forbid_eos, [&](float x, int) {
       const float d = mx - x;
 #pragma unroll
       for (int t = 0; t < 8; ++t) c[t] += (d <= dl[t]) ? 1 : 0;
@@ -1535,7 +1536,7 @@ __global__ void __launch_bounds__(1024) sample_kernel(const float* __restrict__ 
     for (int it = 0; it < 40 && !found; ++it) {
       const float mid = 0.5f * (lo_thr + hi_thr);
       int c0 = 0;
-      scan_row(lg, V, eos_id, forbid_eos, [&](float x, int) { c0 += (x >= mid) ? 1 : 0; });
+      scan_row(lg, V, eos_id, eos2, forbid_eos, [&](float x, int) { c0 += (x >= mid) ? 1 : 0; });
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) c0 += __shfl_xor_sync(0xffffffffu, c0, o);
       if (lane == 0) s_cnt[0][warp] = c0;
@@ -1557,7 +1558,7 @@ __global__ void __launch_bounds__(1024) sample_kernel(const float* __restrict__ 
   // ---- (3) gather the pool, exact k-th value by rank counting (ties kept) ----
   if (threadIdx.x == 0) { s_count = 0; s_nsurv = 0; }
   __syncthreads();
-  scan_row(lg, V, eos_id, forbid_eos, [&](float x, int i) {
+  scan_row(lg, V, eos_id, eos2, forbid_eos, [&](float x, int i) {
     if (x >= thr && x > -INFINITY) {
       const int slot = atomicAdd(&s_count, 1);
       if (slot < kMaxCand) {
@@ -1664,7 +1665,7 @@ __global__ void __launch_bounds__(1024) sample_kernel(const float* __restrict__ 
     const int t = s_sidx[pick];
     out_tokens[(long long)r * c_max + out_pos] = t;
     tok[r] = t;
-    if (t == eos_id) {
+    if (t == eos_id || t == eos2) {
       finished[r] = 1;
       atomicSub(&state[ST_UNFINISHED], 1);
     }

@@ -224,6 +224,12 @@ class RolloutEngine:
         lo, hi = self._seed & 0xFFFFFFFF, self._seed >> 32
         self.state[4:6] = torch.tensor([lo - (1 << 32) if lo >= (1 << 31) else lo, hi - (1 << 32) if hi >= (1 << 31) else hi],
                                        dtype=i32, device=self.state.device)
+        # every id of generation_config.json's eos list stops a row (the sampler takes one id as an argument, a second one
+        # through the device state)
+        eos_ids = [int(x) for x in self.cfg.extra.get("eos_token_ids", [])] if hasattr(self.cfg, "extra") else []
+        others = [x for x in eos_ids if x != self.cfg.eos_token_id]
+        if others:
+            self.state[1] = others[0] + 1
         self.finished.zero_()
         self.gu.zero_()
         self.out_tokens.fill_(self.cfg.pad_token_id)

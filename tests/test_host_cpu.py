@@ -574,3 +574,31 @@ def test_sft_native_data_path():
         big = synthetic_image(2, 448)
         small = D.preshrink_image(big, 128 * 128, D.get_template(None, fam).plugin)
         assert small.width * small.height <= 128 * 128 and D.preshrink_image(big, 10 ** 7, "llava_next").size == big.size
+
+
+def test_checkpoint_keeps_the_source_config_and_generation_config(tmp_path):
+    """A directory written by `save_pretrained` carries the SOURCE checkpoint's config.json (keys this path does not model: bos,
+    sliding window, max positions, eos lists) and generation_config.json unchanged, and the loaded config exposes every stop id of
+    the generation config (the reference's vLLM engine stops on all of them)."""
+    import json
+    from iad_r1_b200.checkpoint import load_config, save_pretrained
+    from iad_r1_b200.config import tiny_config
+    from iad_r1_b200.params import ParamStore
+    src = tmp_path / "src"
+    src.mkdir()
+    raw = tiny_config("qwen2_5_vl").to_hf_dict()
+    raw.update({"bos_token_id": 7, "sliding_window": 4096, "max_window_layers": 3, "max_position_embeddings": 32768,
+                "initializer_range": 0.02})
+    gen = {"eos_token_id": [raw["eos_token_id"], 1001], "pad_token_id": raw["pad_token_id"], "do_sample": True, "top_k": 1}
+    (src / "config.json").write_text(json.dumps(raw))
+    (src / "generation_config.json").write_text(json.dumps(gen))
+    cfg = load_config(str(src))
+    assert cfg.extra["eos_token_ids"] == [raw["eos_token_id"], 1001]
+    ps = ParamStore(cfg, "cpu")
+    ps.init_random(seed=0)
+    out = tmp_path / "out"
+    save_pretrained(ps, str(out))
+    assert json.loads((out / "config.json").read_text()) == raw
+    assert json.loads((out / "generation_config.json").read_text()) == gen
+    cfg2 = load_config(str(out))
+    assert cfg2.text.hidden_size == cfg.text.hidden_size and cfg2.extra["eos_token_ids"] == [raw["eos_token_id"], 1001]
