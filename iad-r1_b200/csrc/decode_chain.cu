@@ -143,7 +143,7 @@ struct LoadCursor {
 __device__ __forceinline__ void wait_counter(const unsigned* c, unsigned target) {
   unsigned long long spins = 0;
   while (ld_acquire(c) < target) {
-    if (++spins > (1ull << 26)) __trap();
+    if (++spins > (1ull << 21)) __trap();   // ~1 s of polling: a legitimate wait is < 1 ms
   }
 }
 
