@@ -81,9 +81,9 @@ class RolloutEngine:
             # row's own keys in C-kind CTAs, all in one wave of <= 3 CTAs per SM; `part` then holds psplit + csplit slots
             # (measured at 3B widths, P = 297, 128 rows: 31 us per layer against 22 us for the per-row kernel - building the
             # 64-row query tile and merging 4-6 slots costs more than the shared staging saves while the prompt is about half
-            # of the context; it is the default only when the prompt dominates, e.g. LLaVA-OneVision's 3.7 k image tokens)
+            # of the context; it is the default only when a LONG prompt dominates (p_max >= 4 c_max and >= 1024 keys), e.g. LLaVA-OneVision's 3.7 k image tokens)
             grouped = os.environ.get("IADR1_DECODE_ATTN_GROUPED", "auto")
-            if (grouped == "1" or (grouped == "auto" and p_max >= 4 * c_max)) and nw == 4:
+            if (grouped == "1" or (grouped == "auto" and p_max >= 4 * c_max and p_max >= 1024)) and nw == 4:
                 budget, rblocks = 3 * NUM_SMS, (num_generations + 7) // 8
                 # prompt CTAs should take about as long as the row CTAs (mid-rollout: c_max / 2 keys): ~2 chunks of 64 keys each
                 ps = max(1, min(8, (p_max + 127) // 128))
