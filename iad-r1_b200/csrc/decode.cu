@@ -446,11 +446,14 @@ __global__ void __launch_bounds__(NW * 32) decode_attn_mma_kernel(
     const float* __restrict__ qkv, const float* __restrict__ cos_tab, const float* __restrict__ sin_tab,
     const int* __restrict__ rope_delta, const bf16* __restrict__ kp, const bf16* __restrict__ vp, bf16* __restrict__ kc,
     bf16* __restrict__ vc, const int* __restrict__ state, const int* __restrict__ row_group,
-    const int* __restrict__ row_plen, float* __restrict__ part, int* __restrict__ tickets, bf16* __restrict__ out, int nq,
-    int nkv, int p_max, int c_max, int max_pos, float scale) {
+    const int* __restrict__ row_plen, const int* __restrict__ finished, float* __restrict__ part, int* __restrict__ tickets,
+    bf16* __restrict__ out, int nq, int nkv, int p_max, int c_max, int max_pos, float scale) {
   if (threadIdx.x == 0) pdl_trigger();   // dependents may become resident (and prefetch) right away
   constexpr int HALF = HD / 2, PPR = HD / 8, NT = NW * 32, CK = 16 * NW, MAXG = 8, NKS = HD / 16, NOB = HD / 8, EPL = HD / 32;
   const int r = blockIdx.x, kvh = blockIdx.y, sp = blockIdx.z, nsplit = gridDim.z;
+  // a row that has produced EOS only emits padding from now on: no K/V traffic, no append (its hidden state is never used;
+  // `finished` was written by the previous step's sampler, which the step's first kernel orders before everything here)
+  if (finished != nullptr && finished[r]) return;
   const int gq = nq / nkv;
   const int lane = threadIdx.x & 31;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -920,9 +923,9 @@ template <int HD>
 __global__ void __launch_bounds__(128, 3) decode_attn_grouped_kernel(
     const float* __restrict__ qkv, const float* __restrict__ cos_tab, const float* __restrict__ sin_tab,
     const int* __restrict__ rope_delta, const bf16* __restrict__ kp, const bf16* __restrict__ vp, bf16* __restrict__ kc,
-    bf16* __restrict__ vc, const int* __restrict__ state, const int* __restrict__ row_plen, float* __restrict__ part,
-    int* __restrict__ tickets, bf16* __restrict__ out, int G, int nq, int nkv, int p_max, int c_max, int max_pos, float scale,
-    int psplit, int csplit, int n_pblocks) {
+    bf16* __restrict__ vc, const int* __restrict__ state, const int* __restrict__ row_plen, const int* __restrict__ finished,
+    float* __restrict__ part, int* __restrict__ tickets, bf16* __restrict__ out, int G, int nq, int nkv, int p_max, int c_max,
+    int max_pos, float scale, int psplit, int csplit, int n_pblocks) {
   if (threadIdx.x == 0) pdl_trigger();   // dependents may become resident (and prefetch) right away
   constexpr int HALF = HD / 2, PPR = HD / 8, NT = 128, NW = 4, CK = 64, MAXG = 8, NKS = HD / 16, NOB = HD / 8, EPL = HD / 32;
   constexpr int STAGE = 2 * CK * HD;                      // bf16 elements per stage: K [CK][HD] + V [CK][HD]
@@ -1128,7 +1131,7 @@ __global__ void __launch_bounds__(128, 3) decode_attn_grouped_kernel(
 #pragma unroll
       for (int ab = 0; ab < 2; ++ab) {
         const int i = 2 * warp + ab;
-        if (i < nrows && h < gq) {
+        if (i < nrows && h < gq && !(finished != nullptr && finished[r_base + i])) {
           float* dst = part + (((long long)(r_base + i) * nq + kvh * gq + h) * nslots + ps) * (HD + 2);
 #pragma unroll
           for (int nb = 0; nb < NOB; ++nb)
@@ -1142,7 +1145,7 @@ __global__ void __launch_bounds__(128, 3) decode_attn_grouped_kernel(
     }
     if (threadIdx.x == 0) s_nrows = 0;
     __syncthreads();
-    if ((int)threadIdx.x < nrows) {
+    if ((int)threadIdx.x < nrows && !(finished != nullptr && finished[r_base + threadIdx.x])) {   // finished rows: no slot, no ticket
       asm volatile("fence.acq_rel.gpu;" ::: "memory");
       const int tk = atomicAdd(&tickets[(r_base + threadIdx.x) * nkv + kvh], 1);
       if (tk == nslots - 1) {       // last arrival for this row: this CTA merges it
@@ -1163,6 +1166,7 @@ __global__ void __launch_bounds__(128, 3) decode_attn_grouped_kernel(
   const int sp = t % csplit; t /= csplit;
   const int kvh = t % nkv;
   const int r = t / nkv;
+  if (finished != nullptr && finished[r]) return;         // the row only emits padding from now on
   const int P = row_plen[r];
   const int ctx = step + 1;                               // completion keys 0 .. step (the last one is produced here)
   const int per = (((ctx + csplit - 1) / csplit) + 15) & ~15;
@@ -1733,9 +1737,9 @@ int iadr1_rmsnorm_f32in(const float* x, const void* w, void* y, int rows, int co
 
 int iadr1_decode_attention_fused(const float* qkv, const float* cos_tab, const float* sin_tab, const int* rope_delta,
                                  const void* kp, const void* vp, void* kc, void* vc, const int* state,
-                                 const int* row_group, const int* row_plen, float* part, int* tickets, void* out, int rows,
-                                 int nq, int nkv, int hd, int p_max, int c_max, int nsplit, int max_pos, float scale,
-                                 void* stream) {
+                                 const int* row_group, const int* row_plen, const int* finished, float* part, int* tickets,
+                                 void* out, int rows, int nq, int nkv, int hd, int p_max, int c_max, int nsplit, int max_pos,
+                                 float scale, void* stream) {
   if (rows <= 0) return 0;
   if (nq % nkv || nq / nkv > 8) return set_error("decode_attention_fused: group size %d unsupported (max 8)", nq / nkv);
   if (nsplit == 0 || nsplit > 32 || nsplit < -32) return set_error("decode_attention_fused: nsplit %d out of range", nsplit);
@@ -1766,7 +1770,7 @@ int iadr1_decode_attention_fused(const float* qkv, const float* cos_tab, const f
     }                                                                                                                \
     launch_kernel(decode_attn_mma_kernel<HD, NW, NS, TR>, dim3(rows, nkv, nsplit), dim3(NW * 32), smem, st, qkv, cos_tab, \
                   sin_tab, rope_delta, (const bf16*)kp, (const bf16*)vp, (bf16*)kc, (bf16*)vc, state, row_group,     \
-                  row_plen, part, tickets, (bf16*)out, nq, nkv, p_max, c_max, max_pos, scale);                       \
+                  row_plen, finished, part, tickets, (bf16*)out, nq, nkv, p_max, c_max, max_pos, scale);             \
   } while (0)
     if (hd == 128 && nw == 4 && three && transposed) IADR1_DECODE_MMA(128, 4, 3, 1);
     else if (hd == 128 && nw == 4 && three) IADR1_DECODE_MMA(128, 4, 3, 0);
@@ -1804,8 +1808,9 @@ int iadr1_decode_attention_fused(const float* qkv, const float* cos_tab, const f
 
 int iadr1_decode_attention_grouped(const float* qkv, const float* cos_tab, const float* sin_tab, const int* rope_delta,
                                    const void* kp, const void* vp, void* kc, void* vc, const int* state, const int* row_plen,
-                                   float* part, int* tickets, void* out, int rows, int rows_per_group, int nq, int nkv, int hd,
-                                   int p_max, int c_max, int psplit, int csplit, int max_pos, float scale, void* stream) {
+                                   const int* finished, float* part, int* tickets, void* out, int rows, int rows_per_group, int nq,
+                                   int nkv, int hd, int p_max, int c_max, int psplit, int csplit, int max_pos, float scale,
+                                   void* stream) {
   if (rows <= 0) return 0;
   if (nq % nkv || nq / nkv > 8) return set_error("decode_attention_grouped: group size %d unsupported (max 8)", nq / nkv);
   if (hd != 64 && hd != 128) return set_error("decode_attention_grouped: head_dim %d unsupported (64 or 128)", hd);
@@ -1824,8 +1829,8 @@ int iadr1_decode_attention_grouped(const float* qkv, const float* cos_tab, const
       attr = true;                                                                                                   \
     }                                                                                                                \
     launch_kernel(decode_attn_grouped_kernel<HD>, dim3(grid), dim3(128), smem, st, qkv, cos_tab, sin_tab, rope_delta, \
-                  (const bf16*)kp, (const bf16*)vp, (bf16*)kc, (bf16*)vc, state, row_plen, part, tickets, (bf16*)out,  \
-                  rows_per_group, nq, nkv, p_max, c_max, max_pos, scale, psplit, csplit, n_pblocks);                   \
+                  (const bf16*)kp, (const bf16*)vp, (bf16*)kc, (bf16*)vc, state, row_plen, finished, part, tickets,    \
+                  (bf16*)out, rows_per_group, nq, nkv, p_max, c_max, max_pos, scale, psplit, csplit, n_pblocks);       \
   } while (0)
   if (hd == 128) IADR1_DECODE_GROUPED(128);
   else IADR1_DECODE_GROUPED(64);

@@ -493,10 +493,10 @@ static int decode_attention(const iadr1_model_cfg_t& c, const iadr1_decode_t* e,
   const float scale = 1.f / sqrtf((float)c.hd);
   if (e->attn_psplit > 0 && e->nsplit > e->attn_psplit && (c.hd == 64 || c.hd == 128) && e->n_groups > 0 && R % e->n_groups == 0)
     return iadr1_decode_attention_grouped(e->qkv, e->cos_tab, e->sin_tab, e->rope_delta, kp, vp, kc, vc, e->state, e->row_plen,
-                                          e->part, e->tickets, e->attn, R, R / e->n_groups, c.nq, c.nkv, c.hd, e->p_max, e->c_max,
+                                          e->finished, e->part, e->tickets, e->attn, R, R / e->n_groups, c.nq, c.nkv, c.hd, e->p_max, e->c_max,
                                           e->attn_psplit, e->nsplit - e->attn_psplit, e->max_pos, scale, s);
   return iadr1_decode_attention_fused(e->qkv, e->cos_tab, e->sin_tab, e->rope_delta, kp, vp, kc, vc, e->state, e->row_group,
-                                      e->row_plen, e->part, e->tickets, e->attn, R, c.nq, c.nkv, c.hd, e->p_max, e->c_max,
+                                      e->row_plen, e->finished, e->part, e->tickets, e->attn, R, c.nq, c.nkv, c.hd, e->p_max, e->c_max,
                                       e->nsplit, e->max_pos, scale, s);
 }
 

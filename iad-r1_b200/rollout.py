@@ -189,7 +189,7 @@ class RolloutEngine:
             L.check(lib.iadr1_decode_attention_fused(
                 self.qkv.data_ptr(), self.cos_tab.data_ptr(), self.sin_tab.data_ptr(), self.rope_delta.data_ptr(),
                 self.kp[i].data_ptr(), self.vp[i].data_ptr(), self.kc[i].data_ptr(), self.vc[i].data_ptr(),
-                self.state.data_ptr(), self.row_group.data_ptr(), self.row_plen.data_ptr(), self.part.data_ptr(),
+                self.state.data_ptr(), self.row_group.data_ptr(), self.row_plen.data_ptr(), self.finished.data_ptr(), self.part.data_ptr(),
                 self.tickets.data_ptr(), self.attn.data_ptr(), R, nq, nkv, hd, self.p_max, self.c_max,
                 -self.nsplit if self.attn_nw == 2 else self.nsplit, self.max_pos, float(hd) ** -0.5, s), "decode_attention_fused")
             self._skinny(p[b + "o.weight"], self.attn, self.h, split_k=sk_o, atomic=True)        # h += attn @ Wo^T

@@ -169,17 +169,18 @@ int iadr1_rmsnorm_f32in(const float* x, const void* w, void* y, int rows, int co
  * part: fp32 [rows][nq][|nsplit|][hd + 2] scratch; tickets: int32 [rows * nkv], zero before the first call.           */
 int iadr1_decode_attention_fused(const float* qkv, const float* cos_tab, const float* sin_tab, const int* rope_delta,
                                  const void* kp, const void* vp, void* kc, void* vc, const int* state,
-                                 const int* row_group, const int* row_plen, float* part, int* tickets, void* out, int rows,
-                                 int nq, int nkv, int hd, int p_max, int c_max, int nsplit, int max_pos, float scale,
-                                 void* stream);
+                                 const int* row_group, const int* row_plen, const int* finished, float* part, int* tickets,
+                                 void* out, int rows, int nq, int nkv, int hd, int p_max, int c_max, int nsplit, int max_pos,
+                                 float scale, void* stream);   /* finished (may be NULL): rows that have produced EOS are skipped */
 /* Shared-prefix form of the same step: the prompt keys are processed ONCE per group (8 rows x gq heads = full tensor-core
  * tiles; K/V staged once for the group's rows), each row's own keys per row; `part` holds psplit + csplit slots per (row, head),
  * `tickets` one counter per (row, kv head). Rows of a group are consecutive and share the prompt (vLLM prefix caching,
  * ref: train/stage_rl/trainer/sc_grpo_trainer.py:351). head_dim 64 or 128.                                              */
 int iadr1_decode_attention_grouped(const float* qkv, const float* cos_tab, const float* sin_tab, const int* rope_delta,
                                    const void* kp, const void* vp, void* kc, void* vc, const int* state, const int* row_plen,
-                                   float* part, int* tickets, void* out, int rows, int rows_per_group, int nq, int nkv, int hd,
-                                   int p_max, int c_max, int psplit, int csplit, int max_pos, float scale, void* stream);
+                                   const int* finished, float* part, int* tickets, void* out, int rows, int rows_per_group, int nq,
+                                   int nkv, int hd, int p_max, int c_max, int psplit, int csplit, int max_pos, float scale,
+                                   void* stream);
 /* temperature -> top-k (ties kept) -> top-p -> multinomial; SamplingParams at sc_grpo_trainer.py:353-358.
  * The Philox seed is `seed ^ (state[4] | state[5] << 32)`: callers that replay a captured graph keep the per-call seed
  * in the device-resident state words and pass seed = 0 (graph arguments are frozen at capture).                     */

@@ -505,7 +505,7 @@ def test_decode_attention_fused(ops, nq, nkv, hd, nsplit):
         kc.copy_(kc0); vc.copy_(vc0)
         L.check(L.lib().iadr1_decode_attention_fused(
             qkv.data_ptr(), cos_t.data_ptr(), sin_t.data_ptr(), delta.data_ptr(), kp.data_ptr(), vp.data_ptr(), kc.data_ptr(),
-            vc.data_ptr(), state.data_ptr(), grp.data_ptr(), plen.data_ptr(), part.data_ptr(), tickets.data_ptr(), out.data_ptr(),
+            vc.data_ptr(), state.data_ptr(), grp.data_ptr(), plen.data_ptr(), None, part.data_ptr(), tickets.data_ptr(), out.data_ptr(),
             R, nq, nkv, hd, p_max, c_max, nsplit, max_pos, scale, L.stream_ptr()))
     torch.cuda.synchronize()
     assert (tickets == 0).all()
@@ -555,16 +555,22 @@ def test_decode_attention_grouped(ops, nq, nkv, hd, G, n_groups, psplit, csplit,
     tickets = torch.zeros(R * nkv, dtype=torch.int32, device=dev)
     out = torch.zeros(R, nq * hd, dtype=bf16, device=dev)
     scale = hd ** -0.5
+    fin = torch.zeros(R, dtype=torch.int32, device=dev)       # rows that already produced EOS are skipped entirely
+    if R > 2:
+        fin[1] = 1
     for _ in range(2):  # second call checks the ticket re-arm
         kc.copy_(kc0); vc.copy_(vc0)
         L.check(L.lib().iadr1_decode_attention_grouped(
             qkv.data_ptr(), cos_t.data_ptr(), sin_t.data_ptr(), delta.data_ptr(), kp.data_ptr(), vp.data_ptr(), kc.data_ptr(),
-            vc.data_ptr(), state.data_ptr(), plen.data_ptr(), part.data_ptr(), tickets.data_ptr(), out.data_ptr(),
+            vc.data_ptr(), state.data_ptr(), plen.data_ptr(), fin.data_ptr(), part.data_ptr(), tickets.data_ptr(), out.data_ptr(),
             R, G, nq, nkv, hd, p_max, c_max, psplit, csplit, max_pos, scale, L.stream_ptr()))
     torch.cuda.synchronize()
     assert (tickets == 0).all()
     g = nq // nkv
     for r in range(R):
+        if int(fin[r]):
+            assert torch.equal(kc[r], kc0[r]) and torch.equal(vc[r], vc0[r]) and (out[r] == 0).all(), "finished row must be untouched"
+            continue
         P = int(plen[r]); pos = P + step + int(delta[r])
         c, s_ = cos_t[pos].to(bf16), sin_t[pos].to(bf16)
         x = qkv[r].to(bf16).view(nq + 2 * nkv, hd)

@@ -174,7 +174,7 @@ items = {
     "attn_fused": lambda: lib.iadr1_decode_attention_fused(
         eng.qkv.data_ptr(), eng.cos_tab.data_ptr(), eng.sin_tab.data_ptr(), eng.rope_delta.data_ptr(), eng.kp[0].data_ptr(),
         eng.vp[0].data_ptr(), eng.kc[0].data_ptr(), eng.vc[0].data_ptr(), eng.state.data_ptr(), eng.row_group.data_ptr(),
-        eng.row_plen.data_ptr(), eng.part.data_ptr(), eng.tickets.data_ptr(), eng.attn.data_ptr(), R, nq, nkv, hd, eng.p_max,
+        eng.row_plen.data_ptr(), None, eng.part.data_ptr(), eng.tickets.data_ptr(), eng.attn.data_ptr(), R, nq, nkv, hd, eng.p_max,
         eng.c_max, (-eng.nsplit if eng.attn_nw == 2 else eng.nsplit), eng.max_pos, hd ** -0.5, L.stream_ptr()),
     f"gemm o split{sk_o}": lambda: eng._skinny(p[b + "o.weight"], eng.attn, eng.h, split_k=sk_o, atomic=True),
     "gemm gate_up stream-k f32 atomic": lambda: eng._skinny(p[b + "gate_up.weight"], eng.xn, eng.gu, atomic=True, stream_k=True),
