@@ -71,7 +71,27 @@ class _LogProbFn(torch.autograd.Function):
         return None, None, None, None, None, None, None, None
 
 
-def call_reward_funcs(reward_funcs, example: dict, texts: list, current_step: int) -> torch.Tensor:
+def _is_reward_model(rf) -> bool:
+    """A reward *model* in the reference's sense (sc_grpo_trainer.py:232-236): a sequence-classification network, not a callback."""
+    return isinstance(rf, torch.nn.Module)
+
+
+def _reward_model_scores(model, tokenizer, example: dict, completions, conv: bool) -> torch.Tensor:
+    """ref: sc_grpo_trainer.py:759-772 - prompt + completion rendered with the reward tokenizer's chat template, right-padded,
+    `logits[:, 0]` of an `AutoModelForSequenceClassification(num_labels=1)` under inference mode. This branch is library code
+    (Transformers / torch) exactly as in the reference: reward scoring is not on the hot path this repository replaces."""
+    if conv:
+        texts = [tokenizer.apply_chat_template(list(example["prompt"]) + c, tokenize=False) for c in completions]
+    else:
+        texts = [example["prompt"] + c for c in completions]
+    enc = tokenizer(texts, return_tensors="pt", padding=True, padding_side="right", add_special_tokens=False)
+    dev = next(model.parameters()).device
+    enc = {k: v.to(dev) for k, v in enc.items()}
+    with torch.inference_mode():
+        return model(**enc).logits[:, 0].float().cpu()
+
+
+def call_reward_funcs(reward_funcs, example: dict, texts: list, current_step: int, reward_processing_classes=None) -> torch.Tensor:
     """Calls every reward callback with the reference's convention (ref: train/stage_rl/trainer/sc_grpo_trainer.py:749-781):
     `reward_func(prompts=[prompt] * G, completions=..., current_step=global_step, **{column: [value] * G})` where
     completions are `[[{"role": "assistant", "content": text}]]` for conversational prompts (plain strings otherwise) and
@@ -85,6 +105,9 @@ def call_reward_funcs(reward_funcs, example: dict, texts: list, current_step: in
     reward_kwargs = {k: [example[k]] * G for k in example.keys() if k not in ("prompt", "completion")}
     out = torch.zeros(G, len(reward_funcs), dtype=torch.float32)
     for i, rf in enumerate(reward_funcs):
+        if _is_reward_model(rf):
+            out[:, i] = _reward_model_scores(rf, reward_processing_classes[i], example, completions, conv)
+            continue
         r = rf(prompts=prompts, completions=completions, current_step=current_step, **reward_kwargs)
         out[:, i] = torch.tensor(r, dtype=torch.float32)
     return out
@@ -170,12 +193,31 @@ class SCGRPOTrainer(TrainerCore):
         # ---- rewards ------------------------------------------------------------------------------------------------------
         if not isinstance(reward_funcs, list):
             reward_funcs = [reward_funcs]
-        for rf in reward_funcs:
-            if not callable(rf):
-                raise NotImplementedError("reward *models* (str / PreTrainedModel) are not supported; pass callables "
-                                          "(sc_grpo_trainer.py:232-236 branch, SURVEY.md §8f item 4)")
+        reward_funcs = list(reward_funcs)
+        for i, rf in enumerate(reward_funcs):
+            if isinstance(rf, str):       # a reward MODEL id / directory (sc_grpo_trainer.py:232-236)
+                from transformers import AutoModelForSequenceClassification
+                reward_funcs[i] = AutoModelForSequenceClassification.from_pretrained(rf, num_labels=1, torch_dtype=torch.bfloat16)
+            elif not callable(rf):
+                raise ValueError(f"reward_funcs[{i}] must be a callable, a model id or a torch module, got {type(rf)}")
         self.reward_funcs = reward_funcs
-        self.reward_processing_classes = reward_processing_classes or [None] * len(reward_funcs)
+        if reward_processing_classes is None:
+            reward_processing_classes = [None] * len(reward_funcs)
+        elif not isinstance(reward_processing_classes, list):
+            reward_processing_classes = [reward_processing_classes]
+        elif len(reward_processing_classes) != len(reward_funcs):
+            raise ValueError("The number of reward processing classes must match the number of reward functions.")
+        for i, (rpc, rf) in enumerate(zip(reward_processing_classes, reward_funcs)):
+            if _is_reward_model(rf):      # :248-258: tokenizer of the reward model, pad = eos when missing, pad id into its config
+                if rpc is None:
+                    from transformers import AutoTokenizer
+                    rpc = AutoTokenizer.from_pretrained(rf.config._name_or_path)
+                if rpc.pad_token_id is None:
+                    rpc.pad_token = rpc.eos_token
+                rf.config.pad_token_id = rpc.pad_token_id
+                rf.to(self.device).eval()
+                reward_processing_classes[i] = rpc
+        self.reward_processing_classes = reward_processing_classes
 
         self.max_pixels, self.min_pixels = max_pixels or 12845056, min_pixels or 3136
         self.max_prompt_length = args.max_prompt_length
@@ -425,7 +467,8 @@ class SCGRPOTrainer(TrainerCore):
         # ---- rewards on decoded text (CPU Python callbacks, verbatim convention :749-781) ----
         with self._phase("rewards"):
             texts = self.processing_class.batch_decode(completion_ids.cpu(), skip_special_tokens=True)
-            rewards_per_func = call_reward_funcs(self.reward_funcs, example, texts, self.state.global_step).to(dev)
+            rewards_per_func = call_reward_funcs(self.reward_funcs, example, texts, self.state.global_step,
+                                                  getattr(self, "reward_processing_classes", None)).to(dev)
         rw = torch.tensor(a.reward_weights, device=dev) if (a.reward_weights and a.loss_mode == "clip") else None
         adv, rewards, std = grpo_loss.group_advantages(rewards_per_func, G, a.scale_rewards or a.loss_mode == "sc", rw)  # :784-793
         if a.loss_mode == "sc":
@@ -438,7 +481,9 @@ class SCGRPOTrainer(TrainerCore):
         m = self._metrics
         m["completion_length"].append(mask.sum(1).float().mean().detach())
         for i, rf in enumerate(self.reward_funcs):
-            m[f"rewards/{rf.__name__}"].append(rewards_per_func[:, i].mean().detach())
+            # :806-810: a reward model is named after its checkpoint directory, a callback after the function
+            name = rf.config._name_or_path.split("/")[-1] if _is_reward_model(rf) else rf.__name__
+            m[f"rewards/{name}"].append(rewards_per_func[:, i].mean().detach())
         m["reward"].append(rewards.mean().detach())
         m["reward_std"].append(std.mean().detach())
         m["kl"].append(mean_kl.detach())

@@ -602,3 +602,42 @@ def test_checkpoint_keeps_the_source_config_and_generation_config(tmp_path):
     assert json.loads((out / "generation_config.json").read_text()) == gen
     cfg2 = load_config(str(out))
     assert cfg2.text.hidden_size == cfg.text.hidden_size and cfg2.extra["eos_token_ids"] == [raw["eos_token_id"], 1001]
+
+
+def test_reward_model_branch_scores_prompt_plus_completion():
+    """Reward MODELS (ref: sc_grpo_trainer.py:232-258, 759-772): a sequence-classification network scores the chat-templated
+    prompt + completion, right-padded, `logits[:, 0]`; callbacks and models can be mixed in one reward list."""
+    import torch
+    from iad_r1_b200.trainer import call_reward_funcs
+
+    class Tok:
+        pad_token_id = 0
+
+        def apply_chat_template(self, messages, tokenize=False):
+            return " | ".join(f"{m['role']}:{m['content'] if isinstance(m['content'], str) else m['content'][-1]['text']}" for m in messages)
+
+        def __call__(self, texts, return_tensors, padding, padding_side, add_special_tokens):
+            assert padding_side == "right" and add_special_tokens is False
+            n = max(len(t) for t in texts)
+            ids = torch.zeros(len(texts), n, dtype=torch.long)
+            for i, t in enumerate(texts):
+                ids[i, :len(t)] = torch.tensor([ord(c) % 97 + 1 for c in t])
+            return {"input_ids": ids, "attention_mask": (ids > 0).long()}
+
+    class RM(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.tensor(0.5))
+
+        def forward(self, input_ids, attention_mask):
+            class O:
+                pass
+            o = O()
+            o.logits = (attention_mask.sum(1, keepdim=True).float() * self.w)      # score = 0.5 * length of the rendered text
+            return o
+
+    example = {"prompt": [{"role": "user", "content": [{"type": "image"}, {"type": "text", "text": "q"}]}], "solution": "<answer>no</answer>"}
+    texts = ["abc", "abcdef"]
+    r = call_reward_funcs([RM(), lambda prompts, completions, current_step, **kw: [1.0] * len(prompts)], example, texts, 0, [Tok(), None])
+    rendered = [len(Tok().apply_chat_template(example["prompt"] + [{"role": "assistant", "content": t}])) for t in texts]
+    assert r.shape == (2, 2) and torch.allclose(r[:, 0], torch.tensor(rendered, dtype=torch.float32) * 0.5) and (r[:, 1] == 1).all()
