@@ -361,6 +361,7 @@ class SCGRPOTrainer(TrainerCore):
         comps = self._rollout(enc, image_embeds=img)
         for ex, e, c in zip(examples, enc, comps):
             self._rollout_cache[id(ex)] = (e, c)
+            self._host_completions(ex, c)      # the rollout has just synchronised: a free host copy for the reward callbacks
 
     def _window_features(self, examples: list):
         """(policy image embeds, reference image embeds, gradient sink) for a micro-batch whose groups all belong to the
@@ -412,11 +413,14 @@ class SCGRPOTrainer(TrainerCore):
             if cached is None:
                 enc = self._encode_prompt(example)
                 completion_ids = self._rollout([enc])[0]
+                cached = (enc, completion_ids)
                 if keep:
-                    self._rollout_cache[id(example)] = (enc, completion_ids)
-            else:
-                enc, completion_ids = cached
+                    self._rollout_cache[id(example)] = cached
+            enc, completion_ids = cached[0], cached[1]
             items.append((example, enc, completion_ids))
+        # host copies of the completions BEFORE the scoring passes are enqueued: the reward callbacks (CPU Python) then run while
+        # the GPU executes the policy / reference forwards instead of waiting for them
+        host_ids = {id(ex): self._host_completions(ex, c) for ex, _, c in items}
         temp = a.temperature if a.loss_mode == "clip" else 1.0   # Q1: SC mode does not temperature-scale the logits
         if a.shared_prefix:
             batch = self.model.prepare_groups([dict(prompt_ids=enc["input_ids"], completion_ids=c, pixel_values=enc["pixel_values"],
@@ -433,7 +437,7 @@ class SCGRPOTrainer(TrainerCore):
                 batch = self.model.prepare_batch(ids, enc["pixel_values"], enc["grid_thw"], prompt_len=P)
                 rows = (torch.arange(G, device=dev)[:, None] * T + (P - 1) + torch.arange(C, device=dev)[None, :]).reshape(-1).to(torch.int32)
                 per_group.append(self._score(batch, rows, c.reshape(-1).to(torch.int32).contiguous(), temp))
-        losses = [self._group_loss(ex, c, lp.view(G, -1), None if rf is None else rf.view(G, -1))
+        losses = [self._group_loss(ex, c, lp.view(G, -1), None if rf is None else rf.view(G, -1), host_ids[id(ex)])
                   for (ex, _, c), (lp, rf) in zip(items, per_group)]
         return torch.stack(losses).mean()
 
@@ -449,7 +453,17 @@ class SCGRPOTrainer(TrainerCore):
                 ref_logps, _ = self.ref_model.logprobs_forward(batch, rows, labels, temp, save=False, image_embeds=ref_img)
         return logps, ref_logps
 
-    def _group_loss(self, example: dict, completion_ids: torch.Tensor, logps: torch.Tensor, ref_logps) -> torch.Tensor:
+    def _host_completions(self, example, completion_ids: torch.Tensor) -> torch.Tensor:
+        """CPU copy of a group's completion ids, made once per rollout (cached with it)."""
+        cache = self.__dict__.setdefault("_host_ids", {})
+        key = (id(example), completion_ids.data_ptr())
+        if key not in cache:
+            if len(cache) > 256:
+                cache.clear()
+            cache[key] = completion_ids.cpu()
+        return cache[key]
+
+    def _group_loss(self, example: dict, completion_ids: torch.Tensor, logps: torch.Tensor, ref_logps, host_ids=None) -> torch.Tensor:
         """Mask, rewards, advantages and loss of ONE group from its [G, C] log-probs (ref: :722-726, :746-798)."""
         G, dev, a = self.num_generations, self.device, self.args
         mask = grpo_loss.completion_mask(completion_ids.long(), self.processing_class.eos_token_id)          # :722-726
@@ -466,7 +480,7 @@ class SCGRPOTrainer(TrainerCore):
                 self._old_logps.pop(id(example), None)
         # ---- rewards on decoded text (CPU Python callbacks, verbatim convention :749-781) ----
         with self._phase("rewards"):
-            texts = self.processing_class.batch_decode(completion_ids.cpu(), skip_special_tokens=True)
+            texts = self.processing_class.batch_decode(completion_ids.cpu() if host_ids is None else host_ids, skip_special_tokens=True)
             rewards_per_func = call_reward_funcs(self.reward_funcs, example, texts, self.state.global_step,
                                                   getattr(self, "reward_processing_classes", None)).to(dev)
         rw = torch.tensor(a.reward_weights, device=dev) if (a.reward_weights and a.loss_mode == "clip") else None
