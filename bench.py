@@ -27,6 +27,9 @@ import sys
 import threading
 import time
 
+# stdout carries exactly ONE JSON line: NCCL's own version / debug banner goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
