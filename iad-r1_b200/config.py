@@ -16,8 +16,9 @@ class TextConfig:
     head_dim: int
     rms_norm_eps: float = 1e-6
     rope_theta: float = 1e6
-    mrope_section: tuple = (16, 24, 24)   # () -> plain 1-D rotary (Qwen2 under LLaVA-OneVision)
+    mrope_section: tuple = (16, 24, 24)   # () -> plain 1-D rotary (Qwen2 under LLaVA-OneVision, LLaMA under LLaVA-1.5)
     tie_word_embeddings: bool = True
+    qkv_bias: bool = True                 # Qwen2 projections carry a bias, LLaMA / Vicuna ones do not
 
     @property
     def qkv_dim(self) -> int:
@@ -28,6 +29,8 @@ class TextConfig:
 class VisionConfig:
     kind: str                 # "qwen2_5_vl" (RMSNorm, SwiGLU+bias, windowed attention) | "qwen2_vl" (LayerNorm, quick-GELU MLP)
                               # | "siglip" (LLaVA-OneVision tower: LayerNorm, tanh-GELU MLP, learned position table, no rotary)
+                              # | "clip" (LLaVA-1.5 tower: class token + learned positions, pre-LayerNorm, quick-GELU MLP;
+                              #   features = hidden state `feature_layer` with the class token dropped)
     depth: int
     hidden_size: int
     num_heads: int
@@ -39,11 +42,18 @@ class VisionConfig:
     in_channels: int = 3
     window_size: int = 112
     fullatt_block_indexes: tuple = (7, 15, 23, 31)
-    image_size: int = 0       # siglip: side of one crop in pixels (384 -> 27 x 27 = 729 tokens per crop)
+    image_size: int = 0       # siglip / clip: side of one crop in pixels (384 -> 27 x 27 = 729 tokens per crop)
+    feature_layer: int = -1   # clip: index into HF's hidden_states tuple (-2 for LLaVA-1.5: the last block is not run)
 
     @property
     def tokens_per_crop(self) -> int:
-        return (self.image_size // self.patch_size) ** 2
+        """Tower tokens per crop (CLIP: the class token counts, it is dropped only after the tower)."""
+        return (self.image_size // self.patch_size) ** 2 + (1 if self.kind == "clip" else 0)
+
+    @property
+    def run_depth(self) -> int:
+        """Blocks actually executed: hidden_states[feature_layer] of a `depth`-block encoder (tuple of depth + 1 entries)."""
+        return self.depth + 1 + self.feature_layer if self.feature_layer < 0 else self.feature_layer
 
     @property
     def head_dim(self) -> int:
@@ -55,8 +65,10 @@ class VisionConfig:
 
     @property
     def patch_dim_padded(self) -> int:
-        """K of the patch-embedding GEMM rounded up to 8 elements (SigLIP: 3*14*14 = 588 -> 592; Qwen: 1176)."""
-        return (self.patch_dim + 7) // 8 * 8
+        """K of the patch-embedding GEMM rounded up to 8 elements (SigLIP: 3*14*14 = 588 -> 592; Qwen: 1176). CLIP keeps one
+        extra column: the class embedding is column `patch_dim` of the fused patch weight and the class-token row of the
+        pixel matrix is the unit vector of that column, so the class token comes out of the same GEMM."""
+        return (self.patch_dim + (1 if self.kind == "clip" else 0) + 7) // 8 * 8
 
     @property
     def intermediate_padded(self) -> int:
@@ -66,7 +78,7 @@ class VisionConfig:
 
 @dataclass
 class VLMConfig:
-    family: str               # "qwen2_5_vl" | "qwen2_vl" | "llava_onevision"
+    family: str               # "qwen2_5_vl" | "qwen2_vl" | "llava_onevision" | "llava" (LLaVA-1.5)
     text: TextConfig
     vision: VisionConfig
     image_token_id: int = 151655
@@ -86,8 +98,10 @@ class VLMConfig:
         mt = d.get("model_type", "")
         if mt == "llava_onevision":
             return VLMConfig._from_llava_onevision(d)
+        if mt == "llava":
+            return VLMConfig._from_llava(d)
         if mt not in ("qwen2_5_vl", "qwen2_vl"):
-            raise ValueError(f"unsupported model_type {mt!r} (supported: qwen2_5_vl, qwen2_vl, llava_onevision)")
+            raise ValueError(f"unsupported model_type {mt!r} (supported: qwen2_5_vl, qwen2_vl, llava_onevision, llava)")
         t = d.get("text_config") or d
         rope = t.get("rope_parameters") or t.get("rope_scaling") or d.get("rope_scaling") or {}
         theta = rope.get("rope_theta", t.get("rope_theta", d.get("rope_theta", 1e6)))
@@ -153,9 +167,68 @@ class VLMConfig:
                          extra={"image_grid_pinpoints": [list(x) for x in d["image_grid_pinpoints"]],
                                 "vision_layer_norm_eps": v.get("layer_norm_eps", 1e-6)})
 
+    @staticmethod
+    def _from_llava(d: dict) -> "VLMConfig":
+        """LlavaConfig (LLaVA-1.5, ref: sc_grpo_trainer.py:134-136): CLIP ViT tower (class token, pre-LayerNorm, quick-GELU),
+        features = hidden_states[vision_feature_layer] without the class token, 2-layer GELU projector, LLaMA / Vicuna decoder
+        (no projection biases, 1-D rotary). HF modeling_llava.py, modeling_clip.py."""
+        t, v = d["text_config"], d["vision_config"]
+        if d.get("vision_feature_select_strategy", "default") != "default":
+            raise ValueError("llava: only vision_feature_select_strategy='default' (class token dropped) is supported")
+        if isinstance(d.get("vision_feature_layer", -2), (list, tuple)):
+            raise ValueError("llava: a single vision_feature_layer is supported")
+        if d.get("projector_hidden_act", "gelu") != "gelu" or d.get("multimodal_projector_bias", True) is not True:
+            raise ValueError("llava: the projector must be Linear - GELU - Linear with biases")
+        nh = t.get("num_attention_heads", 32)
+        hidden = t.get("hidden_size", 4096)
+        rope = t.get("rope_parameters") or {}
+        text = TextConfig(
+            vocab_size=t.get("vocab_size", 32064), hidden_size=hidden, intermediate_size=t.get("intermediate_size", 11008),
+            num_layers=t.get("num_hidden_layers", 32), num_heads=nh, num_kv_heads=t.get("num_key_value_heads", nh),
+            head_dim=t.get("head_dim") or hidden // nh, rms_norm_eps=t.get("rms_norm_eps", 1e-5),
+            rope_theta=float(rope.get("rope_theta", t.get("rope_theta", 10000.0))), mrope_section=(),
+            tie_word_embeddings=bool(d.get("tie_word_embeddings", t.get("tie_word_embeddings", False))),
+            qkv_bias=bool(t.get("attention_bias", False)))
+        if t.get("mlp_bias", False):
+            raise ValueError("llava: MLP biases in the language model are not supported")
+        vision = VisionConfig(
+            kind="clip", depth=v.get("num_hidden_layers", 24), hidden_size=v.get("hidden_size", 1024),
+            num_heads=v.get("num_attention_heads", 16), intermediate_size=v.get("intermediate_size", 4096),
+            out_hidden_size=text.hidden_size, patch_size=v.get("patch_size", 14), spatial_merge_size=1, temporal_patch_size=1,
+            in_channels=v.get("num_channels", 3), window_size=0, fullatt_block_indexes=(), image_size=v.get("image_size", 336),
+            feature_layer=int(d.get("vision_feature_layer", -2)))
+        if v.get("hidden_act", "quick_gelu") != "quick_gelu":
+            raise ValueError("llava: the CLIP tower must use quick_gelu")
+        eos = d.get("eos_token_id", t.get("eos_token_id", 2))
+        return VLMConfig(family="llava", text=text, vision=vision,
+                         image_token_id=d.get("image_token_index", d.get("image_token_id", 32000)), video_token_id=-1,
+                         vision_start_token_id=-1, vision_end_token_id=-1,
+                         eos_token_id=eos[0] if isinstance(eos, list) else eos,
+                         pad_token_id=d.get("pad_token_id") if d.get("pad_token_id") is not None else t.get("pad_token_id", 32001),
+                         extra={"vision_layer_norm_eps": v.get("layer_norm_eps", 1e-5)})
+
     def to_hf_dict(self) -> dict:
         """config.json in the 4.51-era flat schema the reference's `from_pretrained` expects."""
         t, v = self.text, self.vision
+        if self.family == "llava":
+            return {
+                "model_type": "llava", "architectures": ["LlavaForConditionalGeneration"],
+                "image_token_index": self.image_token_id, "vision_feature_layer": v.feature_layer,
+                "vision_feature_select_strategy": "default", "projector_hidden_act": "gelu", "multimodal_projector_bias": True,
+                "image_seq_length": v.tokens_per_crop - 1, "tie_word_embeddings": t.tie_word_embeddings,
+                "pad_token_id": self.pad_token_id, "eos_token_id": self.eos_token_id,
+                "vision_config": {"model_type": "clip_vision_model", "hidden_size": v.hidden_size,
+                                  "intermediate_size": v.intermediate_size, "num_hidden_layers": v.depth,
+                                  "num_attention_heads": v.num_heads, "image_size": v.image_size, "patch_size": v.patch_size,
+                                  "num_channels": v.in_channels, "hidden_act": "quick_gelu", "projection_dim": v.hidden_size,
+                                  "layer_norm_eps": self.extra.get("vision_layer_norm_eps", 1e-5)},
+                "text_config": {"model_type": "llama", "vocab_size": t.vocab_size, "hidden_size": t.hidden_size,
+                                "intermediate_size": t.intermediate_size, "num_hidden_layers": t.num_layers,
+                                "num_attention_heads": t.num_heads, "num_key_value_heads": t.num_kv_heads,
+                                "head_dim": t.head_dim, "rms_norm_eps": t.rms_norm_eps, "rope_theta": t.rope_theta,
+                                "max_position_embeddings": 4096, "hidden_act": "silu", "attention_bias": t.qkv_bias,
+                                "mlp_bias": False, "tie_word_embeddings": t.tie_word_embeddings,
+                                "eos_token_id": self.eos_token_id, "pad_token_id": self.pad_token_id}}
         if self.family == "llava_onevision":
             return {
                 "model_type": "llava_onevision", "architectures": ["LlavaOnevisionForConditionalGeneration"],
@@ -260,6 +333,17 @@ def tiny_config(family: str = "qwen2_5_vl") -> VLMConfig:
                          vision_end_token_id=-1, eos_token_id=1005, pad_token_id=1006,
                          extra={"image_grid_pinpoints": [[56, 56], [56, 112], [112, 56], [112, 112], [168, 56], [56, 168]],
                                 "vision_layer_norm_eps": 1e-6})
+    if family == "llava":
+        # LLaVA-1.5 twin: multi-head attention without projection biases (LLaMA), CLIP tower of 3 blocks whose last one is
+        # skipped (vision_feature_layer -2), class token + 4 x 4 patches of a 56-pixel image
+        text = TextConfig(vocab_size=1024, hidden_size=128, intermediate_size=256, num_layers=2, num_heads=2,
+                          num_kv_heads=2, head_dim=64, rms_norm_eps=1e-5, rope_theta=10000.0, mrope_section=(),
+                          tie_word_embeddings=False, qkv_bias=False)
+        vis = VisionConfig(kind="clip", depth=3, hidden_size=64, num_heads=4, intermediate_size=160, out_hidden_size=128,
+                           patch_size=14, spatial_merge_size=1, temporal_patch_size=1, window_size=0,
+                           fullatt_block_indexes=(), image_size=56, feature_layer=-2)
+        return VLMConfig(family, text, vis, image_token_id=1001, video_token_id=-1, vision_start_token_id=-1,
+                         vision_end_token_id=-1, eos_token_id=1005, pad_token_id=1006, extra={"vision_layer_norm_eps": 1e-5})
     if family == "qwen2_5_vl":
         vis = VisionConfig(kind="qwen2_5_vl", depth=2, hidden_size=64, num_heads=4, intermediate_size=108,
                            out_hidden_size=128, window_size=56, fullatt_block_indexes=(1,))

@@ -169,7 +169,7 @@ static int layer_weights(const Model& m, int i, LayerW& w) {
   w.ln1 = m.find(b + "ln1.weight"); w.qkv = m.find(b + "qkv.weight"); w.qkv_b = m.find(b + "qkv.bias");
   w.o = m.find(b + "o.weight"); w.ln2 = m.find(b + "ln2.weight"); w.gu = m.find(b + "gate_up.weight");
   w.down = m.find(b + "down.weight");
-  if (!w.ln1 || !w.qkv || !w.qkv_b || !w.o || !w.ln2 || !w.gu || !w.down)
+  if (!w.ln1 || !w.qkv || !w.o || !w.ln2 || !w.gu || !w.down)      // qkv.bias is optional (LLaMA / Vicuna have none)
     return set_error("decoder layer %d: weights not bound (iadr1_bind_weights)", i);
   return 0;
 }
@@ -182,7 +182,7 @@ static int layer_fwd(const Model& m, int i, const void* h_in, void* h_out, const
   LayerW w;
   TRY(layer_weights(m, i, w));
   TRY(iadr1_rmsnorm_fwd(h_in, w.ln1->p, b.xn, save ? b.r1 : nullptr, N, H, H, H, c.rms_eps, s));
-  TRY(linear_fwd(b.xn, w.qkv->p, b.qkv, N, D, H, w.qkv_b->p, nullptr, s));
+  TRY(linear_fwd(b.xn, w.qkv->p, b.qkv, N, D, H, w.qkv_b ? w.qkv_b->p : nullptr, nullptr, s));
   TRY(iadr1_rope(b.qkv, cos, sin, N, c.nq + c.nkv, c.hd, D, 1, 0, s));
   if (sink && sink->kp) {
     // rollout prefill: post-rotary K / V rows of every prompt go to the shared-prefix cache [layer][group][p_max][nkv][hd]
@@ -298,7 +298,7 @@ int iadr1_decoder_bwd(void* handle, void* dh, const int* src_index, const float*
     TRY(iadr1_rope(L.dqkv, cos_t, sin_t, N, c.nq + c.nkv, c.hd, D, 0, 1, s));
     TRY(linear_dgrad(L.dqkv, w.qkv->p, L.dx, N, D, H, s));
     TRY(linear_wgrad(L.dqkv, b.xn, w.qkv->g, N, D, H, s));
-    if (w.qkv_b->g) TRY(iadr1_colsum(L.dqkv, w.qkv_b->g, N, D, D, s));
+    if (w.qkv_b && w.qkv_b->g) TRY(iadr1_colsum(L.dqkv, w.qkv_b->g, N, D, D, s));
     TRY(iadr1_rmsnorm_bwd(L.dx, L.h[i], w.ln1->p, b.r1, dh, w.ln1->g, N, H, H, 1, s));
     if (on_layer_done) on_layer_done(i, cb_user);
   }
@@ -525,13 +525,13 @@ static int decode_step_chained(Model& m, const iadr1_decode_t* e, cudaStream_t s
   LayerW w, wn;
   TRY(layer_weights(m, 0, w));
   TRY(launch_decode_chain(R, H, I, QH, D, c.rms_eps, e->h, e->xn, e->act, e->qkv, nullptr, nullptr, nullptr, nullptr, nullptr,
-                          w.ln1->p, w.qkv->p, w.qkv_b->p, 0, 1, 1, e->chain_counters, s));
+                          w.ln1->p, w.qkv->p, w.qkv_b ? w.qkv_b->p : nullptr, 0, 1, 1, e->chain_counters, s));
   for (int i = 0; i < c.layers; ++i) {
     const bool last = i + 1 == c.layers;
     if (!last) TRY(layer_weights(m, i + 1, wn));
     TRY(decode_attention(c, e, i, s));
     TRY(launch_decode_chain(R, H, I, QH, D, c.rms_eps, e->h, e->xn, e->act, e->qkv, e->attn, w.o->p, w.ln2->p, w.gu->p, w.down->p,
-                            last ? nw->p : wn.ln1->p, last ? nullptr : wn.qkv->p, last ? nullptr : wn.qkv_b->p, 1, 1, last ? 0 : 1,
+                            last ? nw->p : wn.ln1->p, last ? nullptr : wn.qkv->p, (last || !wn.qkv_b) ? nullptr : wn.qkv_b->p, 1, 1, last ? 0 : 1,
                             e->chain_counters + (i + 1) * 8, s));
     if (!last) w = wn;
   }
@@ -555,7 +555,7 @@ int iadr1_decode_step(void* handle, const iadr1_decode_t* e, void* stream) {
     LayerW w;
     TRY(layer_weights(m, i, w));
     TRY(iadr1_rmsnorm_f32in(e->h, w.ln1->p, e->xn, R, H, c.rms_eps, e->qkv, D, s));
-    TRY(skinny(w.qkv->p, e->xn, e->qkv, D, H, R, sk_qkv, w.qkv_b->p, e->block_n, s));
+    TRY(skinny(w.qkv->p, e->xn, e->qkv, D, H, R, sk_qkv, w.qkv_b ? w.qkv_b->p : nullptr, e->block_n, s));
     TRY(decode_attention(c, e, i, s));
     TRY(skinny(w.o->p, e->attn, e->h, H, QH, R, sk_o, nullptr, e->block_n, s));
     TRY(iadr1_rmsnorm_f32in(e->h, w.ln2->p, e->xn, R, H, c.rms_eps, nullptr, 0, s));
@@ -593,7 +593,7 @@ struct VBlockBuf {
 struct VisionLayout {
   std::vector<void*> x;            // x[i] = input of block i, x[depth] = tower output
   std::vector<VBlockBuf> bb;       // per block (save) or one shared
-  void* pos; float* stq; void* xq; void* m1; void* a1; void* feat;       // embedding residual, merger / projector
+  void* pos; void* x_pre; float* st0; float* stq; void* xq; void* m1; void* a1; void* feat;       // embedding residual, merger / projector
   void* dx; void* dact; void* dxn; void* dattn; void* dqkv; float* delta; float* dkv32; void* dm1; void* dfeat; float* dfeat32;
   size_t bytes;
 };
@@ -625,10 +625,12 @@ static VisionLayout vision_layout(const iadr1_model_cfg_t& c, long long N, long 
     b.act = a.take(N * Ip * 2);
     L.bb.push_back(b);
   }
-  L.pos = c.v_kind == 2 ? a.take(N * E * 2) : nullptr;
+  L.pos = c.v_kind >= 2 ? a.take(N * E * 2) : nullptr;
+  L.x_pre = c.v_kind == 3 ? a.take(N * E * 2) : nullptr;            // CLIP: embeddings before pre_layrnorm
+  L.st0 = c.v_kind == 3 ? static_cast<float*>(a.take(2 * N * 4)) : nullptr;
   L.stq = static_cast<float*>(a.take(2 * N * 4));
   L.xq = a.take(N * E * 2);
-  const long long Mm = c.v_kind == 2 ? N : N / unit, Km = c.v_kind == 2 ? Ho : unit * E;      // merger rows / fc1 width
+  const long long Mm = c.v_kind >= 2 ? N : N / unit, Km = c.v_kind >= 2 ? Ho : unit * E;      // merger rows / fc1 width
   L.m1 = a.take(Mm * Km * 2);
   L.a1 = a.take(Mm * Km * 2);
   L.feat = a.take(Mm * Ho * 2);
@@ -644,7 +646,7 @@ static VisionLayout vision_layout(const iadr1_model_cfg_t& c, long long N, long 
     L.dkv32 = static_cast<float*>(a.take((size_t)N * 2 * E * 4));
     L.dm1 = a.take(Mm * Km * 2);
     L.dfeat = a.take(Mm * Ho * 2);
-    L.dfeat32 = c.v_kind == 2 ? static_cast<float*>(a.take((size_t)N * Ho * 4)) : nullptr;
+    L.dfeat32 = c.v_kind >= 2 ? static_cast<float*>(a.take((size_t)N * Ho * 4)) : nullptr;
   }
   (void)n_out;
   L.bytes = a.off;
@@ -722,6 +724,14 @@ int iadr1_vision_fwd(void* handle, const void* pixel_values, const iadr1_vision_
     if (!pb || !pt) return set_error("vision_fwd: SigLIP embedding weights not bound");
     TRY(iadr1_gather_rows(pt->p, nullptr, geo->pos_index, L.pos, N, E, E, 0, E, s));       // position table tiled over the crops
     TRY(linear_fwd(pixel_values, pe->p, L.x[0], N, E, Kp, pb->p, L.pos, s));
+  } else if (c.v_kind == 3) {
+    // CLIP (HF modeling_clip.py CLIPVisionEmbeddings + pre_layrnorm): no conv bias; the class token is the row whose pixel
+    // vector is the unit vector of the class-embedding column of the fused patch weight; LayerNorm before the first block
+    const Weight *pt = m.find("visual.pos_embed.weight"), *pl = m.find("visual.pre_ln.weight"), *plb = m.find("visual.pre_ln.bias");
+    if (!pt || !pl || !plb) return set_error("vision_fwd: CLIP embedding weights not bound");
+    TRY(iadr1_gather_rows(pt->p, nullptr, geo->pos_index, L.pos, N, E, E, 0, E, s));
+    TRY(linear_fwd(pixel_values, pe->p, L.x_pre, N, E, Kp, nullptr, L.pos, s));
+    TRY(iadr1_layernorm_fwd(L.x_pre, pl->p, plb->p, L.x[0], L.st0, L.st0 + N, N, E, E, c.v_eps, s));
   } else if (geo->window_index) {
     // block 0's normalised-input buffer is free until its first norm: scratch for the un-permuted patch embedding (x[depth]
     // would alias x[0] in the two-buffer layout of a forward-only call with an even depth)
@@ -748,21 +758,22 @@ int iadr1_vision_fwd(void* handle, const void* pixel_values, const iadr1_vision_
     TRY(vnorm_fwd(c, b.x_mid, w.n2, w.n2b, b.xn2, b.st2, N, s));
     TRY(linear_fwd(b.xn2, w.w1->p, b.gu, N, W1, E, w.w1b->p, nullptr, s));
     if (c.v_kind == 0) TRY(iadr1_act_mul_fwd(b.gu, b.act, N, Ip, 2 * Ip, Ip, Ip, 0, s));
-    else TRY(iadr1_act_mul_fwd(b.gu, b.act, N, Ip, Ip, -1, Ip, c.v_kind == 1 ? 2 : 3, s));
+    else TRY(iadr1_act_mul_fwd(b.gu, b.act, N, Ip, Ip, -1, Ip, c.v_kind == 2 ? 3 : 2, s));      // quick-GELU (Qwen2-VL, CLIP) / tanh-GELU
     TRY(linear_fwd(b.act, w.w2->p, L.x[i + 1], N, E, Ip, w.w2b->p, b.x_mid, s));
   }
   const void* xl = L.x[c.v_depth];
   const Weight *f1 = m.find("visual.merger.fc1.weight"), *f1b = m.find("visual.merger.fc1.bias");
   const Weight *f2 = m.find("visual.merger.fc2.weight"), *f2b = m.find("visual.merger.fc2.bias");
   if (!f1 || !f1b || !f2 || !f2b) return set_error("vision_fwd: merger / projector weights not bound");
-  if (c.v_kind == 2) {
-    // LlavaOnevisionMultiModalProjector on the last encoder layer's output, then anyres packing with image_newline
+  if (c.v_kind >= 2) {
+    // Llava(Onevision)MultiModalProjector on the selected encoder hidden state, then the packing gather: anyres re-tiling
+    // with image_newline (OneVision) or simply the patch tokens without the class token (LLaVA-1.5)
     const Weight* nl = m.find("image_newline");
-    if (!nl) return set_error("vision_fwd: image_newline not bound");
+    if (c.v_kind == 2 && !nl) return set_error("vision_fwd: image_newline not bound");
     TRY(linear_fwd(xl, f1->p, L.m1, N, Ho, E, f1b->p, nullptr, s));
     TRY(iadr1_act_mul_fwd(L.m1, L.a1, N, Ho, Ho, -1, Ho, 1, s));
     TRY(linear_fwd(L.a1, f2->p, L.feat, N, Ho, Ho, f2b->p, nullptr, s));
-    TRY(iadr1_gather_rows(L.feat, nl->p, geo->pack_index, out, geo->n_out, Ho, Ho, Ho, Ho, s));
+    TRY(iadr1_gather_rows(L.feat, nl ? nl->p : nullptr, geo->pack_index, out, geo->n_out, Ho, Ho, nl ? Ho : 0, Ho, s));
   } else {
     const Weight *lq = m.find("visual.merger.ln_q.weight"), *lqb = m.find("visual.merger.ln_q.bias");
     if (!lq || (c.v_kind == 1 && !lqb)) return set_error("vision_fwd: merger ln_q not bound");
@@ -797,11 +808,11 @@ int iadr1_vision_bwd(void* handle, const void* d_out, const void* pixel_values, 
   const Weight *f1 = m.find("visual.merger.fc1.weight"), *f1b = m.find("visual.merger.fc1.bias");
   const Weight *f2 = m.find("visual.merger.fc2.weight"), *f2b = m.find("visual.merger.fc2.bias");
   const void* xl = L.x[c.v_depth];
-  if (c.v_kind == 2) {
+  if (c.v_kind >= 2) {
     const Weight* nl = m.find("image_newline");
-    // un-pack: dropped features get zero gradient, image_newline collects one row per feature-map row
+    // un-pack: dropped features (and CLIP's class token) get zero gradient, image_newline collects one row per feature-map row
     if (cudaMemsetAsync(L.dfeat32, 0, (size_t)N * Ho * 4, s) != cudaSuccess) return set_error("vision_bwd: memset failed");
-    TRY(iadr1_scatter_add_rows(d_out, geo->pack_index, L.dfeat32, nl->g, geo->n_out, Ho, Ho, Ho, Ho, s));
+    TRY(iadr1_scatter_add_rows(d_out, geo->pack_index, L.dfeat32, nl ? nl->g : nullptr, geo->n_out, Ho, Ho, Ho, nl ? Ho : 0, s));
     TRY(iadr1_cast_f32_bf16(L.dfeat32, L.dfeat, N * Ho, s));
     TRY(vlinear_bwd(L.dfeat, L.a1, f2, f2b, L.dm1, N, Ho, Ho, s));
     TRY(iadr1_act_mul_bwd(L.dm1, L.m1, L.m1, N, Ho, Ho, -1, Ho, 1, s));
@@ -828,7 +839,7 @@ int iadr1_vision_bwd(void* handle, const void* d_out, const void* pixel_values, 
     const iadr1_attn_plan_t* plan = full ? pf : geo->plan_win;
     TRY(vlinear_bwd(L.dx, b.act, w.w2, w.w2b, L.dact, N, E, Ip, s));
     if (c.v_kind == 0) TRY(iadr1_act_mul_bwd(L.dact, b.gu, b.gu, N, Ip, 2 * Ip, Ip, Ip, 0, s));
-    else TRY(iadr1_act_mul_bwd(L.dact, b.gu, b.gu, N, Ip, Ip, -1, Ip, c.v_kind == 1 ? 2 : 3, s));
+    else TRY(iadr1_act_mul_bwd(L.dact, b.gu, b.gu, N, Ip, Ip, -1, Ip, c.v_kind == 2 ? 3 : 2, s));
     TRY(vlinear_bwd(b.gu, b.xn2, w.w1, w.w1b, L.dxn, N, W1, E, s));
     TRY(vnorm_bwd(c, L.dxn, b.x_mid, w.n2, w.n2b, b.st2, L.dx, N, 1, s));
     TRY(vlinear_bwd(L.dx, b.attn, w.proj, w.projb, L.dattn, N, E, E, s));
@@ -840,7 +851,13 @@ int iadr1_vision_bwd(void* handle, const void* d_out, const void* pixel_values, 
     TRY(vnorm_bwd(c, L.dxn, L.x[i], w.n1, w.n1b, b.st1, L.dx, N, 1, s));
   }
   const Weight* pe = m.find("visual.patch_embed.weight");
-  if (c.v_kind == 2) {
+  if (c.v_kind == 3) {
+    // through pre_layrnorm to the embeddings; the class embedding's gradient is a column of the patch-weight gradient
+    const Weight *pt = m.find("visual.pos_embed.weight"), *pl = m.find("visual.pre_ln.weight"), *plb = m.find("visual.pre_ln.bias");
+    TRY(iadr1_layernorm_bwd(L.dx, L.x_pre, pl->p, L.st0, L.st0 + N, L.dxn, pl->g, plb->g, N, E, E, 0, s));
+    if (pt->g) TRY(iadr1_colsum(L.dxn, pt->g, N / c.v_tokens_per_crop, c.v_tokens_per_crop * E, c.v_tokens_per_crop * E, s));
+    TRY(vlinear_bwd(L.dxn, pixel_values, pe, nullptr, nullptr, N, E, Kp, s));
+  } else if (c.v_kind == 2) {
     const Weight *pb = m.find("visual.patch_embed.bias"), *pt = m.find("visual.pos_embed.weight");
     // x0 = patch_embed(px) + bias + pos[tile]: the table's gradient is the sum over crops
     if (pt->g) TRY(iadr1_colsum(L.dx, pt->g, N / c.v_tokens_per_crop, c.v_tokens_per_crop * E, c.v_tokens_per_crop * E, s));

@@ -288,6 +288,8 @@ def image_token_count(cfg: VLMConfig, grid_entry) -> int:
     (n_crops, H, W) with the ORIGINAL image size in pixels for LLaVA-OneVision."""
     if cfg.family == "llava_onevision":
         return len(llava_pack_index(cfg, (int(grid_entry[1]), int(grid_entry[2])))[0])
+    if cfg.family == "llava":          # LLaVA-1.5: one 336-pixel crop, class token dropped (select strategy "default")
+        return cfg.vision.tokens_per_crop - 1
     t, h, w = grid_entry
     return int(t * h * w) // cfg.vision.spatial_merge_size ** 2
 
@@ -296,7 +298,7 @@ def position_ids(input_ids: np.ndarray, grid_thw: list, cfg: VLMConfig, attentio
                  prompt_len: int | None = None):
     """Family dispatch: M-RoPE ids for Qwen2(.5)-VL; plain 1-D positions (cumulative count of unmasked tokens, the
     Qwen2 text model under LLaVA-OneVision) replicated on the three axes otherwise. Returns ([3, B, T], deltas [B])."""
-    if cfg.family != "llava_onevision":
+    if cfg.family not in ("llava_onevision", "llava"):
         return mrope_position_ids(input_ids, grid_thw, cfg, attention_mask, prompt_len)
     B, T = input_ids.shape
     am = np.ones((B, T), dtype=np.int64) if attention_mask is None else attention_mask.astype(np.int64)
@@ -315,7 +317,10 @@ class SiglipGeometry:
         tpc = cfg.vision.tokens_per_crop
         packs, base, n_crops_total = [], 0, 0
         for n_crops, h, w in grid:
-            idx, n = llava_pack_index(cfg, (int(h), int(w)))
+            if cfg.family == "llava":      # LLaVA-1.5: every patch token of the single crop, class token (row 0) dropped
+                idx, n = np.arange(1, tpc, dtype=np.int64), 1
+            else:
+                idx, n = llava_pack_index(cfg, (int(h), int(w)))
             if n != int(n_crops):
                 raise ValueError(f"image of size {(h, w)} needs {n} crops, processor supplied {n_crops}")
             packs.append(np.where(idx >= 0, idx + base, -1))
@@ -352,6 +357,19 @@ def patchify_crops(pixel_values: torch.Tensor, patch: int) -> torch.Tensor:
     return x.reshape(n * g * g, c * patch * patch).contiguous()
 
 
+def clip_pixel_rows(pixel_values: torch.Tensor, v: VisionConfig) -> torch.Tensor:
+    """[n_images, C, S, S] (CLIPImageProcessor output) -> the rows of the CLIP patch-embedding GEMM, `tokens_per_crop` per image:
+    row 0 of every image is the class token = the unit vector of column `patch_dim` (that column of the fused patch weight holds
+    the class embedding, HF modeling_clip.py CLIPVisionEmbeddings), rows 1.. are the patches in (grid row, grid col) order with
+    (channel, py, px) columns; width `patch_dim_padded`."""
+    n = pixel_values.shape[0]
+    patches = patchify_crops(pixel_values, v.patch_size).view(n, v.tokens_per_crop - 1, v.patch_dim)
+    rows = torch.zeros(n, v.tokens_per_crop, v.patch_dim_padded, dtype=patches.dtype, device=patches.device)
+    rows[:, 1:, :v.patch_dim] = patches
+    rows[:, 0, v.patch_dim] = 1
+    return rows.view(n * v.tokens_per_crop, v.patch_dim_padded)
+
+
 def vision_inputs_from_processor(cfg: VLMConfig, enc) -> tuple:
     """(pixel_values, grid) in the layout the vision kernels take, from a processor's output mapping.
     Qwen processors already emit patch rows + `image_grid_thw`. LLaVA-OneVision processors emit crops
@@ -363,6 +381,11 @@ def vision_inputs_from_processor(cfg: VLMConfig, enc) -> tuple:
     if "image_grid_thw" in enc:
         g = enc["image_grid_thw"]
         return pv, (g.tolist() if torch.is_tensor(g) else g)
+    if cfg.family == "llava":              # LlavaProcessor: pixel_values [n_images, C, S, S], one crop per image
+        if pv.dim() == 3:
+            pv = pv[None]
+        S = cfg.vision.image_size
+        return clip_pixel_rows(pv, cfg.vision), [(1, S, S)] * pv.shape[0]
     if cfg.family != "llava_onevision" or "image_sizes" not in enc:
         raise ValueError("processor output has pixel_values but neither image_grid_thw nor image_sizes")
     sizes = enc["image_sizes"].tolist() if torch.is_tensor(enc["image_sizes"]) else enc["image_sizes"]

@@ -70,7 +70,7 @@ class VLM:
     def vision_forward(self, pixel_values: torch.Tensor, grid_thw, save: bool = True):
         """pixel_values [Np, C*tp*ps*ps] (any float dtype) -> image embeddings [Np/merge^2, H_text] bf16."""
         v, p = self.cfg.vision, self.p
-        if v.kind == "siglip":
+        if v.kind in ("siglip", "clip"):
             return self._siglip_forward(pixel_values, grid_thw, save)
         geo = vision_geometry(v, grid_thw, self.device)
         E, nh, hd, Ip = v.hidden_size, v.num_heads, v.head_dim, v.intermediate_padded
@@ -179,7 +179,7 @@ class VLM:
             self.native.vision_bwd(d_out.contiguous(), ctx.px, ctx.cgeom, ctx.ws)
             ctx.ws = None
             return
-        if v.kind == "siglip":
+        if v.kind in ("siglip", "clip"):
             return self._siglip_backward(d_out, ctx)
         E, nh, hd, Ip = v.hidden_size, v.num_heads, v.head_dim, v.intermediate_padded
         unit = v.spatial_merge_size ** 2
@@ -251,12 +251,14 @@ class VLM:
         if pixel_values.shape[0] != Np:
             raise ValueError(f"pixel_values has {pixel_values.shape[0]} patches, the image sizes imply {Np}")
         px = pixel_values.to(device=self.device, dtype=bf16)
-        if v.patch_dim_padded != v.patch_dim:                      # K of the patch GEMM: 588 -> 592 (zero columns)
-            px = torch.nn.functional.pad(px, (0, v.patch_dim_padded - v.patch_dim))
+        if px.shape[1] != v.patch_dim_padded:                      # K of the patch GEMM: 588 -> 592 (zero columns)
+            px = torch.nn.functional.pad(px, (0, v.patch_dim_padded - px.shape[1]))
         px = px.contiguous()
         if self._native_vision(hd):
             fa = ops.range_attention(geo, "crops", geo.full_lo, geo.full_hi, nh, nh, hd)
             return self._vision_native(px, geo, fa, None, geo.n_tokens, save)
+        if v.kind == "clip":
+            raise NotImplementedError("the CLIP tower (LLaVA-1.5) runs through iadr1_vision_fwd only (head_dim must be a multiple of 8)")
         pos = p["visual.pos_embed.weight"].repeat(nc, 1)          # position table tiled over the crops (residual operand)
         x = ops.linear_fwd(px, p["visual.patch_embed.weight"], bias=p["visual.patch_embed.bias"], residual=pos)
         sh = ops.AttnShape(nc, tpc, nh, nh, hd, causal=False)     # attention within one crop
@@ -378,7 +380,7 @@ class VLM:
         I, nq, nkv, hd = t.intermediate_size, t.num_heads, t.num_kv_heads, t.head_dim
         b = f"layers.{i}."
         xn, r1 = ops.rmsnorm_fwd(h, p[b + "ln1.weight"], t.rms_norm_eps, save_rstd=save)
-        qkv = ops.linear_fwd(xn, p[b + "qkv.weight"], bias=p[b + "qkv.bias"])
+        qkv = ops.linear_fwd(xn, p[b + "qkv.weight"], bias=p.get(b + "qkv.bias"))      # no bias under LLaMA (LLaVA-1.5)
         ops.rope_(qkv, cos, sin, nq + nkv, hd, bf16_ops=1)
         if kv_sink is not None:
             kv_sink(i, qkv)
@@ -411,7 +413,7 @@ class VLM:
             dattn = ops.linear_bwd(dh, attn, p[b + "o.weight"], g[b + "o.weight"])
             dqkv = ctx.attn.backward(dattn, qkv, P)
             ops.rope_(dqkv, ctx.cos, ctx.sin, nq + nkv, hd, bf16_ops=0, backward=True)
-            dxn = ops.linear_bwd(dqkv, xn, p[b + "qkv.weight"], g[b + "qkv.weight"], g[b + "qkv.bias"])
+            dxn = ops.linear_bwd(dqkv, xn, p[b + "qkv.weight"], g[b + "qkv.weight"], g.get(b + "qkv.bias"))
             ops.rmsnorm_bwd(dxn, h, p[b + "ln1.weight"], r1, dh, g[b + "ln1.weight"], add_dx=True)
             ctx.layers[i] = None  # free this layer's activations as the sweep passes
             if self.on_layer_grad_ready is not None:

@@ -50,7 +50,7 @@ class VisionGeom(C.Structure):
                 ("plan_win", C.POINTER(AttnPlan)), ("pos_index", C.c_void_p), ("pack_index", C.c_void_p)]
 
 
-V_KINDS = {"qwen2_5_vl": 0, "qwen2_vl": 1, "siglip": 2}
+V_KINDS = {"qwen2_5_vl": 0, "qwen2_vl": 1, "siglip": 2, "clip": 3}
 
 LAYER_CB = C.CFUNCTYPE(None, C.c_int, C.c_void_p)
 
@@ -76,9 +76,9 @@ class NativeModel:
         for i in v.fullatt_block_indexes:
             mask |= 1 << i
         mc = ModelCfg(t.vocab_size, t.hidden_size, t.intermediate_size, t.num_layers, t.num_heads, t.num_kv_heads, t.head_dim,
-                      t.rms_norm_eps, V_KINDS[v.kind], v.depth, v.hidden_size, v.num_heads, v.intermediate_padded,
-                      v.out_hidden_size, v.patch_dim_padded, v.spatial_merge_size ** 2,
-                      v.tokens_per_crop if v.kind == "siglip" else 0, mask,
+                      t.rms_norm_eps, V_KINDS[v.kind], v.run_depth if v.kind == "clip" else v.depth, v.hidden_size, v.num_heads,
+                      v.intermediate_padded, v.out_hidden_size, v.patch_dim_padded, v.spatial_merge_size ** 2,
+                      v.tokens_per_crop if v.kind in ("siglip", "clip") else 0, mask,
                       float(cfg.extra.get("vision_layer_norm_eps", 1e-6)))
         L.check(L.lib().iadr1_model_create(C.byref(mc), C.byref(self.handle)), "model_create")
         for name, w in params.p.items():

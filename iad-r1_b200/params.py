@@ -85,6 +85,11 @@ class ParamStore:
         if v.kind == "siglip":
             self._add("visual.patch_embed.bias", (E,), False)
             self._add("visual.pos_embed.weight", (v.tokens_per_crop, E), False)   # learned table: no weight decay
+        if v.kind == "clip":
+            # column `patch_dim` of the patch weight IS the class embedding (see VisionConfig.patch_dim_padded)
+            self._add("visual.pos_embed.weight", (v.tokens_per_crop, E), False)
+            self._add("visual.pre_ln.weight", (E,), False)
+            self._add("visual.pre_ln.bias", (E,), False)
         for i in range(v.depth):
             b = f"visual.blocks.{i}."
             self._add(b + "qkv.weight", (3 * E, E), True)
@@ -106,7 +111,15 @@ class ParamStore:
                 self._add(b + "fc2.weight", (E, Ip), True)
                 self._add(b + "fc2.bias", (E,), False)
         m = v.spatial_merge_size ** 2 * E
-        if v.kind == "siglip":
+        if v.kind == "clip":
+            # post_layernorm is not on LLaVA's path (features come from an encoder hidden state); kept for round trips
+            self._add("visual.post_layernorm.weight", (E,), False)
+            self._add("visual.post_layernorm.bias", (E,), False)
+            self._add("visual.merger.fc1.weight", (v.out_hidden_size, E), True)
+            self._add("visual.merger.fc1.bias", (v.out_hidden_size,), False)
+            self._add("visual.merger.fc2.weight", (v.out_hidden_size, v.out_hidden_size), True)
+            self._add("visual.merger.fc2.bias", (v.out_hidden_size,), False)
+        elif v.kind == "siglip":
             # SigLIP's post_layernorm is NOT on the path (features = last encoder layer output); kept for round trips.
             self._add("visual.post_layernorm.weight", (E,), False)
             self._add("visual.post_layernorm.bias", (E,), False)
@@ -128,7 +141,8 @@ class ParamStore:
         for i in range(t.num_layers):
             b = f"layers.{i}."
             self._add(b + "qkv.weight", (t.qkv_dim, t.hidden_size), True)
-            self._add(b + "qkv.bias", (t.qkv_dim,), False)
+            if t.qkv_bias:
+                self._add(b + "qkv.bias", (t.qkv_dim,), False)
             self._add(b + "o.weight", (t.hidden_size, t.num_heads * t.head_dim), True)
             self._add(b + "gate_up.weight", (2 * t.intermediate_size, t.hidden_size), True)
             self._add(b + "down.weight", (t.hidden_size, t.intermediate_size), True)
@@ -172,7 +186,7 @@ class ParamStore:
         src = {"p": self.p, "g": self.g}[which]
         t, v = self.cfg.text, self.cfg.vision
         E, I, Ip = v.hidden_size, v.intermediate_size, v.intermediate_padded
-        if v.kind == "siglip":
+        if v.kind in ("siglip", "clip"):
             yield from self._hf_named_siglip(src)
             yield from self._hf_named_text(src, "language_model.model.", "language_model.lm_head.weight")
             return
@@ -214,7 +228,12 @@ class ParamStore:
         E = v.hidden_size
         vb = "vision_tower.vision_model."
         yield vb + "embeddings.patch_embedding.weight", src["visual.patch_embed.weight"][:, :v.patch_dim]
-        yield vb + "embeddings.patch_embedding.bias", src["visual.patch_embed.bias"]
+        if v.kind == "clip":
+            yield vb + "embeddings.class_embedding", src["visual.patch_embed.weight"][:, v.patch_dim]
+            yield vb + "pre_layrnorm.weight", src["visual.pre_ln.weight"]        # (sic: HF's CLIP spells it this way)
+            yield vb + "pre_layrnorm.bias", src["visual.pre_ln.bias"]
+        else:
+            yield vb + "embeddings.patch_embedding.bias", src["visual.patch_embed.bias"]
         yield vb + "embeddings.position_embedding.weight", src["visual.pos_embed.weight"]
         for i in range(v.depth):
             b, hb = f"visual.blocks.{i}.", f"{vb}encoder.layers.{i}."
@@ -238,7 +257,8 @@ class ParamStore:
         yield "multi_modal_projector.linear_1.bias", src["visual.merger.fc1.bias"]
         yield "multi_modal_projector.linear_2.weight", src["visual.merger.fc2.weight"]
         yield "multi_modal_projector.linear_2.bias", src["visual.merger.fc2.bias"]
-        yield "image_newline", src["image_newline"]
+        if v.kind == "siglip":
+            yield "image_newline", src["image_newline"]
 
     def _hf_named_text(self, src, prefix, head_name):
         t = self.cfg.text
@@ -247,13 +267,15 @@ class ParamStore:
         Ti = t.intermediate_size
         for i in range(t.num_layers):
             b, hb = f"layers.{i}.", f"{prefix}layers.{i}."
-            w, bi = src[b + "qkv.weight"], src[b + "qkv.bias"]
+            w = src[b + "qkv.weight"]
             yield hb + "self_attn.q_proj.weight", w[:nq]
             yield hb + "self_attn.k_proj.weight", w[nq:nq + nkv]
             yield hb + "self_attn.v_proj.weight", w[nq + nkv:]
-            yield hb + "self_attn.q_proj.bias", bi[:nq]
-            yield hb + "self_attn.k_proj.bias", bi[nq:nq + nkv]
-            yield hb + "self_attn.v_proj.bias", bi[nq + nkv:]
+            if t.qkv_bias:
+                bi = src[b + "qkv.bias"]
+                yield hb + "self_attn.q_proj.bias", bi[:nq]
+                yield hb + "self_attn.k_proj.bias", bi[nq:nq + nkv]
+                yield hb + "self_attn.v_proj.bias", bi[nq + nkv:]
             yield hb + "self_attn.o_proj.weight", src[b + "o.weight"]
             yield hb + "mlp.gate_proj.weight", src[b + "gate_up.weight"][:Ti]
             yield hb + "mlp.up_proj.weight", src[b + "gate_up.weight"][Ti:]
@@ -266,7 +288,7 @@ class ParamStore:
 
     def canonical_name(self, name: str) -> str:
         """Map transformers-5.x key names (`model.visual.*`, `model.language_model.*`) onto the 4.51 layout."""
-        if self.cfg.family == "llava_onevision":
+        if self.cfg.family in ("llava_onevision", "llava"):
             # 5.x: model.vision_tower.*, model.multi_modal_projector.*, model.image_newline, model.language_model.*, lm_head.*
             if name.startswith("model.language_model."):
                 return "language_model.model." + name[len("model.language_model."):]

@@ -185,7 +185,7 @@ class RolloutEngine:
             # RMSNorm also clears the fp32 qkv accumulator the split-K GEMM adds into
             L.check(lib.iadr1_rmsnorm_f32in(self.h.data_ptr(), p[b + "ln1.weight"].data_ptr(), self.xn.data_ptr(), R, H,
                                             t.rms_norm_eps, self.qkv.data_ptr(), t.qkv_dim, s), "rmsnorm_f32in")
-            self._skinny(p[b + "qkv.weight"], self.xn, self.qkv, split_k=sk_qkv, atomic=True, bias=p[b + "qkv.bias"])
+            self._skinny(p[b + "qkv.weight"], self.xn, self.qkv, split_k=sk_qkv, atomic=True, bias=p.get(b + "qkv.bias"))
             L.check(lib.iadr1_decode_attention_fused(
                 self.qkv.data_ptr(), self.cos_tab.data_ptr(), self.sin_tab.data_ptr(), self.rope_delta.data_ptr(),
                 self.kp[i].data_ptr(), self.vp[i].data_ptr(), self.kc[i].data_ptr(), self.vc[i].data_ptr(),

@@ -232,7 +232,9 @@ typedef struct iadr1_model_cfg_t {
   int vocab, hidden, inter, layers, nq, nkv, hd;   /* decoder geometry (HF config.json: vocab_size, hidden_size, ...)   */
   float rms_eps;
   /* vision tower: v_kind -1 none, 0 qwen2_5_vl (RMSNorm, SwiGLU + bias, windowed / full attention), 1 qwen2_vl (LayerNorm,
-   * quick-GELU MLP), 2 siglip (LLaVA-OneVision: learned positions, LayerNorm, tanh-GELU MLP, projector + anyres packing).
+   * quick-GELU MLP), 2 siglip (LLaVA-OneVision: learned positions, LayerNorm, tanh-GELU MLP, projector + anyres packing),
+ * 3 clip (LLaVA-1.5: class token as a unit-vector pixel row, learned positions, pre-LayerNorm, quick-GELU MLP; v_depth = the
+ * blocks actually run for vision_feature_layer; the packing gather drops the class token).
    * v_inter / v_patch_dim are the 8-element padded widths of the store; v_fullatt_mask bit i = block i attends the whole image */
   int v_kind, v_depth, v_hidden, v_heads, v_inter, v_out_hidden, v_patch_dim, v_merge_unit, v_tokens_per_crop;
   unsigned int v_fullatt_mask;

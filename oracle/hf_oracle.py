@@ -44,6 +44,23 @@ def hf_config(cfg, attn_implementation="eager"):
             multimodal_projector_bias=True, tie_word_embeddings=t.tie_word_embeddings)
         c._attn_implementation = attn_implementation
         return c
+    if cfg.family == "llava":
+        from transformers import LlavaConfig
+        c = LlavaConfig(
+            text_config=dict(model_type="llama", vocab_size=t.vocab_size, hidden_size=t.hidden_size,
+                             intermediate_size=t.intermediate_size, num_hidden_layers=t.num_layers,
+                             num_attention_heads=t.num_heads, num_key_value_heads=t.num_kv_heads, head_dim=t.head_dim,
+                             max_position_embeddings=4096, rms_norm_eps=t.rms_norm_eps, rope_theta=t.rope_theta,
+                             attention_bias=t.qkv_bias, mlp_bias=False, tie_word_embeddings=t.tie_word_embeddings),
+            vision_config=dict(model_type="clip_vision_model", hidden_size=v.hidden_size, intermediate_size=v.intermediate_size,
+                               num_hidden_layers=v.depth, num_attention_heads=v.num_heads, patch_size=v.patch_size,
+                               image_size=v.image_size, num_channels=v.in_channels, hidden_act="quick_gelu",
+                               projection_dim=v.hidden_size, layer_norm_eps=cfg.extra.get("vision_layer_norm_eps", 1e-5)),
+            image_token_index=cfg.image_token_id, vision_feature_layer=v.feature_layer,
+            vision_feature_select_strategy="default", projector_hidden_act="gelu", multimodal_projector_bias=True,
+            image_seq_length=v.tokens_per_crop - 1, tie_word_embeddings=t.tie_word_embeddings)
+        c._attn_implementation = attn_implementation
+        return c
     if cfg.family == "qwen2_5_vl":
         from transformers import Qwen2_5_VLConfig
         vis = dict(depth=v.depth, hidden_size=v.hidden_size, intermediate_size=v.intermediate_size, num_heads=v.num_heads,
@@ -67,6 +84,8 @@ def build_hf_model(cfg, seed=0, dtype=torch.float32, attn_implementation="eager"
     fp32 oracle and the bf16 product path hold bit-identical parameters."""
     if cfg.family == "llava_onevision":
         from transformers import LlavaOnevisionForConditionalGeneration as Cls
+    elif cfg.family == "llava":
+        from transformers import LlavaForConditionalGeneration as Cls
     elif cfg.family == "qwen2_5_vl":
         from transformers import Qwen2_5_VLForConditionalGeneration as Cls
     else:
@@ -102,6 +121,17 @@ def hf_logits_llava(model, input_ids, pixel_values, image_sizes, position_ids, a
     """LLaVA-OneVision: pixel_values [B, n_crops, 3, S, S] (crop 0 = base crop), image_sizes [B, 2] (H, W)."""
     kw = dict(input_ids=input_ids, position_ids=position_ids, use_cache=False,
               pixel_values=pixel_values.to(next(model.parameters()).dtype), image_sizes=image_sizes)
+    if logits_to_keep:
+        kw["logits_to_keep"] = int(logits_to_keep)
+    if attention_mask is not None:
+        kw["attention_mask"] = attention_mask
+    return model(**kw).logits
+
+
+def hf_logits_llava15(model, input_ids, pixel_values, position_ids, attention_mask=None, logits_to_keep=0):
+    """LLaVA-1.5: pixel_values [n_images, 3, S, S] (one crop per image, one image per row of input_ids)."""
+    kw = dict(input_ids=input_ids, position_ids=position_ids, use_cache=False,
+              pixel_values=pixel_values.to(next(model.parameters()).dtype))
     if logits_to_keep:
         kw["logits_to_keep"] = int(logits_to_keep)
     if attention_mask is not None:

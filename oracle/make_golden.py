@@ -12,9 +12,9 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from iad_r1_b200.config import tiny_config  # noqa: E402
-from iad_r1_b200.geometry import mrope_position_ids, position_ids as family_position_ids, image_token_count, patchify_crops  # noqa: E402
+from iad_r1_b200.geometry import mrope_position_ids, position_ids as family_position_ids, image_token_count, patchify_crops, clip_pixel_rows  # noqa: E402
 from oracle import grpo_ref  # noqa: E402
-from oracle.hf_oracle import build_hf_model, hf_logits, hf_logits_llava, per_token_logps  # noqa: E402
+from oracle.hf_oracle import build_hf_model, hf_logits, hf_logits_llava, hf_logits_llava15, per_token_logps  # noqa: E402
 
 
 def synthetic_batch(cfg, G=4, C=12, grid=(1, 8, 8), seed=0):
@@ -57,15 +57,39 @@ def synthetic_batch_llava(cfg, G=4, C=12, image_hw=(80, 100), seed=0):
     return ids, P, crops, (n_crops, image_hw[0], image_hw[1])
 
 
+def synthetic_batch_llava15(cfg, G=4, C=12, seed=0):
+    """LLaVA-1.5 twin: one S x S crop [1, 3, S, S] (bf16-valued), prompt with tokens_per_crop - 1 <image> placeholders."""
+    rng = np.random.RandomState(seed)
+    n_img = cfg.vision.tokens_per_crop - 1
+    prompt = list(rng.randint(10, 900, size=6)) + [cfg.image_token_id] * n_img + list(rng.randint(10, 900, size=5))
+    P = len(prompt)
+    comp = rng.randint(10, 900, size=(G, C))
+    for g, e in enumerate([None, 7, C - 1, 2][:G]):
+        if e is not None:
+            comp[g, e] = cfg.eos_token_id
+            comp[g, e + 1:] = cfg.pad_token_id
+    ids = np.concatenate([np.tile(np.array(prompt)[None], (G, 1)), comp], 1).astype(np.int64)
+    gen = torch.Generator().manual_seed(seed + 7)
+    S = cfg.vision.image_size
+    img = torch.randn(1, cfg.vision.in_channels, S, S, generator=gen).to(torch.bfloat16).float()
+    return ids, P, img, (1, S, S)
+
+
 def main():
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
-    for family in ("qwen2_5_vl", "qwen2_vl", "llava_onevision"):
+    only = sys.argv[1:]
+    for family in ("qwen2_5_vl", "qwen2_vl", "llava_onevision", "llava"):
+        if only and family not in only:
+            continue
         cfg = tiny_config(family)
         G, C, grid = 4, 12, (1, 8, 8)
         if family == "llava_onevision":
             ids, P, crops, grid = synthetic_batch_llava(cfg, G, C)
             px = patchify_crops(crops, cfg.vision.patch_size)
+        elif family == "llava":
+            ids, P, crops, grid = synthetic_batch_llava15(cfg, G, C)
+            px = clip_pixel_rows(crops, cfg.vision)
         else:
             ids, P, px = synthetic_batch(cfg, G, C, grid)
         pos, deltas = family_position_ids(ids, [grid] * G, cfg)
@@ -82,6 +106,9 @@ def main():
 
             def fwd(m):
                 return hf_logits_llava(m, ids_t, crops[None].repeat(G, 1, 1, 1, 1), sizes, pos_t[0], attn_mask)
+        elif family == "llava":
+            def fwd(m):
+                return hf_logits_llava15(m, ids_t, crops.repeat(G, 1, 1, 1), pos_t[0], attn_mask)
         else:
             def fwd(m):
                 return hf_logits(m, ids_t, px.repeat(G, 1), grid_t, pos_t, attn_mask)
