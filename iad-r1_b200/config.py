@@ -301,6 +301,16 @@ PRESETS = {
         image_token_id=151646, video_token_id=151647, vision_start_token_id=-1, vision_end_token_id=-1,
         extra={"image_grid_pinpoints": [[384 * a, 384 * b] for a in range(1, 7) for b in range(1, 7)],
                "vision_layer_norm_eps": 1e-6}),
+    # llava-1.5-7b-hf: Vicuna-7B (LLaMA: MHA 32 x 128, no projection biases, untied head) + CLIP ViT-L/14-336 (24 blocks,
+    # hidden_states[-2] = 23 blocks run, class token dropped: 576 image tokens)
+    "llava-1.5-7b": lambda: VLMConfig(
+        "llava", TextConfig(32064, 4096, 11008, 32, 32, 32, 128, rms_norm_eps=1e-5, rope_theta=10000.0, mrope_section=(),
+                            tie_word_embeddings=False, qkv_bias=False),
+        VisionConfig(kind="clip", depth=24, hidden_size=1024, num_heads=16, intermediate_size=4096, out_hidden_size=4096,
+                     patch_size=14, spatial_merge_size=1, temporal_patch_size=1, window_size=0, fullatt_block_indexes=(),
+                     image_size=336, feature_layer=-2),
+        image_token_id=32000, video_token_id=-1, vision_start_token_id=-1, vision_end_token_id=-1, eos_token_id=2,
+        pad_token_id=32001, extra={"vision_layer_norm_eps": 1e-5}),
 }
 
 

@@ -1,10 +1,10 @@
 """PA-SFT data path, natively: sharegpt rows -> chat template -> `<image>` expansion -> per-turn
 token pairs -> truncation -> labels -> pad-to-8 collation, without importing LLaMA-Factory.
 
-Restates, for the two templates the reference's PA-SFT scripts select (`--template qwen2_vl` for the Qwen families,
-`--template llava_next_qwen` for LLaVA-OneVision; ref: scripts/train/PA_SFT/*.sh:33):
-  * the template tables            ref: train/stage_sft/llamafactory/data/template.py:901-913, 1121-1133
-  * `<image>` expansion            ref: data/mm_plugin.py:327-367 (llava_next), :808-823, 850-897 (qwen2_vl)
+Restates, for the templates the reference's PA-SFT scripts select (`--template qwen2_vl` for the Qwen families,
+`--template llava_next_qwen` for LLaVA-OneVision, `--template llava` for LLaVA-1.5; ref: scripts/train/PA_SFT/*.sh:33):
+  * the template tables            ref: train/stage_sft/llamafactory/data/template.py:832-841, 901-913, 1121-1133
+  * `<image>` expansion            ref: data/mm_plugin.py:287-311 (llava), :327-367 (llava_next), :808-823, 850-897 (qwen2_vl)
   * multi-turn pair encoding       ref: data/template.py `Template._encode` / `encode_multiturn`
   * labels + per-turn truncation   ref: data/processors/supervised.py:34-88, processor_utils.py:51-65
   * collation                      ref: data/collator.py:79-161 (pad to a multiple of 8, IGNORE_INDEX labels)
@@ -30,7 +30,7 @@ class Template:
     user: str              # includes the assistant header, as in the reference's format_user
     assistant: str
     default_system: str
-    plugin: str            # "qwen2_vl" | "llava_next"
+    plugin: str            # "qwen2_vl" | "llava_next" | "llava"
     image_token: str
 
 
@@ -40,16 +40,22 @@ _CHATML = dict(system="<|im_start|>system\n{content}<|im_end|>\n",
 TEMPLATES = {
     "qwen2_vl": Template("qwen2_vl", plugin="qwen2_vl", image_token="<|image_pad|>", **_CHATML),
     "llava_next_qwen": Template("llava_next_qwen", plugin="llava_next", image_token="<image>", **_CHATML),
+    # the vicuna format (template.py:832-841): the system text runs straight into the first "USER:" (default system
+    # formatter, no separator), an answer ends with the tokenizer's eos token, every <image> becomes image_seqlen tokens
+    "llava": Template("llava", plugin="llava", image_token="<image>", system="{content}", user="USER: {content} ASSISTANT:",
+                      assistant="{content}{eos}",
+                      default_system="A chat between a curious user and an artificial intelligence assistant. "
+                                     "The assistant gives helpful, detailed, and polite answers to the user's questions."),
 }
-FAMILY_TEMPLATE = {"qwen2_vl": "qwen2_vl", "qwen2_5_vl": "qwen2_vl", "llava_onevision": "llava_next_qwen"}
+FAMILY_TEMPLATE = {"qwen2_vl": "qwen2_vl", "qwen2_5_vl": "qwen2_vl", "llava_onevision": "llava_next_qwen", "llava": "llava"}
 
 
 def get_template(name: Optional[str], family: Optional[str] = None) -> Template:
     if name is None:
         name = FAMILY_TEMPLATE.get(family)
     if name not in TEMPLATES:
-        raise ValueError(f"Template {name} does not exist on the B200 path (supported: {sorted(TEMPLATES)}; the LLaVA-1.5 / "
-                         f"LLaVA-Next templates belong to model families outside it)")
+        raise ValueError(f"Template {name} does not exist on the B200 path (supported: {sorted(TEMPLATES)}; the LLaVA-Next "
+                         f"templates belong to a model family outside it)")
     return TEMPLATES[name]
 
 
@@ -104,7 +110,7 @@ def expand_image_placeholders(messages: list, seqlens: list, tpl: Template) -> l
     return out
 
 
-def render_pairs(messages: list, tpl: Template) -> list:
+def render_pairs(messages: list, tpl: Template, eos: str = "</s>") -> list:
     """[(prompt text, response text)] per (user, assistant) turn: the first prompt carries the system block (the dataset's
     system message, else the template default), every prompt ends with the assistant header, every response with the
     end-of-turn token - Template._encode with the chatml slots."""
@@ -121,7 +127,7 @@ def render_pairs(messages: list, tpl: Template) -> list:
         if u["role"] != "user" or a["role"] != "assistant":
             raise ValueError(f"expected a (user, assistant) turn at message {i}, got ({u['role']}, {a['role']})")
         prompt = (tpl.system.format(content=system) if i == 0 and system else "") + tpl.user.format(content=u["content"])
-        pairs.append((prompt, tpl.assistant.format(content=a["content"])))
+        pairs.append((prompt, tpl.assistant.format(content=a["content"], eos=eos)))
     return pairs
 
 

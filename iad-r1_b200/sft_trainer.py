@@ -117,6 +117,8 @@ def encode_supervised_example(example: dict, processor, cutoff_len: int, image_d
     from . import sft_data as D
     from .geometry import image_token_count
     family = cfg.family if cfg is not None else ("llava_onevision" if getattr(processor, "llava", False) else "qwen2_5_vl")
+    if cfg is None and getattr(processor, "llava15", False):
+        family = "llava"
     tpl = D.get_template(template, family)
     images = D.load_images(example, image_dir, image_resolution, tpl.plugin)
     pv, grid, seqlens = None, None, []
@@ -143,7 +145,8 @@ def encode_supervised_example(example: dict, processor, cutoff_len: int, image_d
             pv, grid = vision_inputs_from_processor(cfg, im)
             seqlens = [image_token_count(cfg, g) for g in grid]
     msgs = D.expand_image_placeholders(example["messages"], seqlens, tpl)
-    pair_ids = [(D.tokenize(processor, p), D.tokenize(processor, r)) for p, r in D.render_pairs(msgs, tpl)]
+    eos = getattr(getattr(processor, "tokenizer", processor), "eos_token", None) or "</s>"
+    pair_ids = [(D.tokenize(processor, p), D.tokenize(processor, r)) for p, r in D.render_pairs(msgs, tpl, eos)]
     ids, labels = D.encode_pairs(pair_ids, cutoff_len)
     return dict(input_ids=np.asarray(ids, dtype=np.int64), labels=np.asarray(labels, dtype=np.int64), pixel_values=pv, grid_thw=grid)
 

@@ -31,8 +31,14 @@ class _Encoding(dict):
 class SyntheticProcessor:
     def __init__(self, cfg: VLMConfig, min_pixels: int = 3136, max_pixels: int = 12845056):
         self.cfg = cfg
-        self.llava = cfg.family == "llava_onevision"
-        if self.llava:
+        self.llava = cfg.family in ("llava_onevision", "llava")     # bare <image> placeholder in the chat template
+        self.llava15 = cfg.family == "llava"
+        if self.llava15:
+            # the REAL HF CLIP image processor (shortest edge -> S bicubic, centre crop S x S, CLIP mean / std)
+            from transformers import CLIPImageProcessor
+            S = cfg.vision.image_size
+            self.image_processor = CLIPImageProcessor(size={"shortest_edge": S}, crop_size={"height": S, "width": S})
+        elif self.llava:
             # the REAL HF anyres image processor (best-resolution select, resize + pad, 384-pixel crops + base crop)
             from transformers import LlavaOnevisionImageProcessor
             S = cfg.vision.image_size
@@ -95,7 +101,10 @@ class SyntheticProcessor:
         counts = []
         if images is not None and len(images) > 0:
             im = self.image_processor(images=list(images), return_tensors="pt")
-            if self.llava:
+            if self.llava15:
+                enc["pixel_values"] = im["pixel_values"]                      # [n_images, 3, S, S], one crop per image
+                counts = [self.cfg.vision.tokens_per_crop - 1] * im["pixel_values"].shape[0]
+            elif self.llava:
                 from .geometry import image_token_count, llava_image_layout
                 enc["pixel_values"], enc["image_sizes"] = im["pixel_values"], im["image_sizes"]
                 for h, w in im["image_sizes"].tolist():

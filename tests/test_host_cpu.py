@@ -548,6 +548,13 @@ def test_sft_native_data_path():
     lt = D.get_template(None, "llava_onevision")
     assert lt.name == "llava_next_qwen"
     assert D.expand_image_placeholders(msgs[:2], [4], lt)[0]["content"] == "<image><image><image><image>first?"
+    # `--template llava` (LLaVA-1.5, template.py:832-841 "copied from vicuna"): system text straight into "USER:", eos after answers
+    vt = D.get_template(None, "llava")
+    assert vt.name == "llava" and vt.plugin == "llava"
+    vexp = D.expand_image_placeholders(msgs[:2], [2], vt)
+    vp = D.render_pairs(vexp, vt, eos="</s>")
+    assert vp[0] == ("A chat between a curious user and an artificial intelligence assistant. The assistant gives helpful, "
+                     "detailed, and polite answers to the user's questions.USER: <image><image>first? ASSISTANT:", "yes</s>")
     for bad in ([3], [3, 2, 1]):
         with pytest.raises(ValueError, match="number of <image> tokens|less than the number"):
             D.expand_image_placeholders(msgs, bad, tpl)
@@ -558,7 +565,7 @@ def test_sft_native_data_path():
     col = D.collate([dict(input_ids=ids, labels=labels), dict(input_ids=[1, 2], labels=[-100, 2])], pad_token_id=0)
     assert col["input_ids"].shape == (2, 16) and (col["labels"][1, 2:] == -100).all() and col["attention_mask"].sum() == 11
     # end to end on the twins: two images in one conversation, two assistant turns
-    for fam in ("qwen2_5_vl", "llava_onevision"):
+    for fam in ("qwen2_5_vl", "llava_onevision", "llava"):
         cfg = tiny_config(fam)
         proc = SyntheticProcessor(cfg)
         ex = {"messages": msgs, "images": [synthetic_image(0, 112), synthetic_image(1, 84)]}

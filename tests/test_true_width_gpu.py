@@ -25,6 +25,7 @@ CASES = {
     "qwen2-vl-2b": (2, 40, (1, 16, 24)),
     "llava-ov-0.5b": (2, 24, (400, 600)),
     "qwen2.5-vl-7b": (2, 24, (1, 16, 16)),      # H 3584, GQA 7:1, I 18944, V 152064, untied lm_head
+    "llava-1.5-7b": (2, 24, None),              # LLaMA-7B widths (MHA 32 x 128, no biases), CLIP ViT-L/14-336 (hd 64, 577 tokens)
 }
 
 
@@ -34,11 +35,16 @@ def _build_case(model, seed=0):
     from oracle import grpo_ref
     from oracle.hf_oracle import build_hf_model
     from oracle.make_golden import synthetic_batch, synthetic_batch_llava
-    cfg = depth_reduced(PRESETS[model](), 2, 2)
+    cfg = depth_reduced(PRESETS[model](), 2, 3 if model == "llava-1.5-7b" else 2)   # CLIP: 3 blocks, the last one not run
     G, C, spec = CASES[model]
     if cfg.family == "llava_onevision":
         ids, P, crops, grid = synthetic_batch_llava(cfg, G, C, image_hw=spec, seed=seed)
         px = patchify_crops(crops, cfg.vision.patch_size)
+    elif cfg.family == "llava":
+        from iad_r1_b200.geometry import clip_pixel_rows
+        from oracle.make_golden import synthetic_batch_llava15
+        ids, P, crops, grid = synthetic_batch_llava15(cfg, G, C, seed=seed)
+        px = clip_pixel_rows(crops, cfg.vision)
     else:
         grid, crops = spec, None
         ids, P, px = synthetic_batch(cfg, G, C, grid, seed=seed)
@@ -52,8 +58,10 @@ def _build_case(model, seed=0):
 
 
 def _hf_tail_logits(case, ids_t, pos_t, attn_mask, keep):
-    from oracle.hf_oracle import hf_logits, hf_logits_llava
+    from oracle.hf_oracle import hf_logits, hf_logits_llava, hf_logits_llava15
     cfg, G, grid = case["cfg"], ids_t.shape[0], case["grid"]
+    if cfg.family == "llava":
+        return hf_logits_llava15(case["hf"], ids_t, case["crops"].repeat(G, 1, 1, 1), pos_t[0], attn_mask, logits_to_keep=keep)
     if cfg.family == "llava_onevision":
         sizes = torch.tensor([[grid[1], grid[2]]] * G)
         return hf_logits_llava(case["hf"], ids_t, case["crops"][None].repeat(G, 1, 1, 1, 1), sizes, pos_t[0], attn_mask,
@@ -160,7 +168,7 @@ def test_true_width_logprobs_and_grads_match_hf(cuda, model):
     assert not failures, failures
 
 
-@pytest.mark.parametrize("model", ["qwen2.5-vl-3b", "llava-ov-0.5b", "qwen2.5-vl-7b"])
+@pytest.mark.parametrize("model", ["qwen2.5-vl-3b", "llava-ov-0.5b", "qwen2.5-vl-7b", "llava-1.5-7b"])
 def test_true_width_rollout_logits_match_hf(cuda, model):
     """Decode logits of RolloutEngine (prefill KV, tensor-core decode attention at head_dim 128 / 64, swap-AB split-K
     products, fused SwiGLU, fp32 residual stream) against HF logits of [prompt + sampled tokens] - not against the
