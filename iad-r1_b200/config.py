@@ -78,7 +78,7 @@ class VisionConfig:
 
 @dataclass
 class VLMConfig:
-    family: str               # "qwen2_5_vl" | "qwen2_vl" | "llava_onevision" | "llava" (LLaVA-1.5)
+    family: str               # "qwen2_5_vl" | "qwen2_vl" | "llava_onevision" | "llava" (LLaVA-1.5) | "llava_next" (LLaVA-1.6)
     text: TextConfig
     vision: VisionConfig
     image_token_id: int = 151655
@@ -98,10 +98,10 @@ class VLMConfig:
         mt = d.get("model_type", "")
         if mt == "llava_onevision":
             return VLMConfig._from_llava_onevision(d)
-        if mt == "llava":
+        if mt in ("llava", "llava_next"):
             return VLMConfig._from_llava(d)
         if mt not in ("qwen2_5_vl", "qwen2_vl"):
-            raise ValueError(f"unsupported model_type {mt!r} (supported: qwen2_5_vl, qwen2_vl, llava_onevision, llava)")
+            raise ValueError(f"unsupported model_type {mt!r} (supported: qwen2_5_vl, qwen2_vl, llava_onevision, llava, llava_next)")
         t = d.get("text_config") or d
         rope = t.get("rope_parameters") or t.get("rope_scaling") or d.get("rope_scaling") or {}
         theta = rope.get("rope_theta", t.get("rope_theta", d.get("rope_theta", 1e6)))
@@ -169,10 +169,12 @@ class VLMConfig:
 
     @staticmethod
     def _from_llava(d: dict) -> "VLMConfig":
-        """LlavaConfig (LLaVA-1.5, ref: sc_grpo_trainer.py:134-136): CLIP ViT tower (class token, pre-LayerNorm, quick-GELU),
-        features = hidden_states[vision_feature_layer] without the class token, 2-layer GELU projector, LLaMA / Vicuna decoder
-        (no projection biases, 1-D rotary). HF modeling_llava.py, modeling_clip.py."""
+        """LlavaConfig (LLaVA-1.5, ref: sc_grpo_trainer.py:134-136) and LlavaNextConfig (LLaVA-1.6, :131-133): CLIP ViT tower
+        (class token, pre-LayerNorm, quick-GELU), features = hidden_states[vision_feature_layer] without the class token,
+        2-layer GELU projector, LLaMA / Vicuna / Mistral decoder (no projection biases, 1-D rotary); LLaVA-Next adds anyres crops
+        packed with `image_newline` (no feature shrink). HF modeling_llava.py, modeling_llava_next.py, modeling_clip.py."""
         t, v = d["text_config"], d["vision_config"]
+        family = d.get("model_type", "llava")
         if d.get("vision_feature_select_strategy", "default") != "default":
             raise ValueError("llava: only vision_feature_select_strategy='default' (class token dropped) is supported")
         if isinstance(d.get("vision_feature_layer", -2), (list, tuple)):
@@ -200,19 +202,28 @@ class VLMConfig:
         if v.get("hidden_act", "quick_gelu") != "quick_gelu":
             raise ValueError("llava: the CLIP tower must use quick_gelu")
         eos = d.get("eos_token_id", t.get("eos_token_id", 2))
-        return VLMConfig(family="llava", text=text, vision=vision,
+        extra = {"vision_layer_norm_eps": v.get("layer_norm_eps", 1e-5), "text_model_type": t.get("model_type", "llama")}
+        if family == "llava_next":
+            if not d.get("use_image_newline_parameter", True):
+                raise ValueError("llava_next: only use_image_newline_parameter=True is supported")
+            extra["image_grid_pinpoints"] = [list(x) for x in d.get("image_grid_pinpoints") or
+                                             [[336, 672], [672, 336], [672, 672], [1008, 336], [336, 1008]]]
+        return VLMConfig(family=family, text=text, vision=vision,
                          image_token_id=d.get("image_token_index", d.get("image_token_id", 32000)), video_token_id=-1,
                          vision_start_token_id=-1, vision_end_token_id=-1,
                          eos_token_id=eos[0] if isinstance(eos, list) else eos,
                          pad_token_id=d.get("pad_token_id") if d.get("pad_token_id") is not None else t.get("pad_token_id", 32001),
-                         extra={"vision_layer_norm_eps": v.get("layer_norm_eps", 1e-5)})
+                         extra=extra)
 
     def to_hf_dict(self) -> dict:
         """config.json in the 4.51-era flat schema the reference's `from_pretrained` expects."""
         t, v = self.text, self.vision
-        if self.family == "llava":
+        if self.family in ("llava", "llava_next"):
+            nxt = self.family == "llava_next"
             return {
-                "model_type": "llava", "architectures": ["LlavaForConditionalGeneration"],
+                "model_type": self.family,
+                "architectures": ["LlavaNextForConditionalGeneration" if nxt else "LlavaForConditionalGeneration"],
+                **({"image_grid_pinpoints": self.extra["image_grid_pinpoints"], "use_image_newline_parameter": True} if nxt else {}),
                 "image_token_index": self.image_token_id, "vision_feature_layer": v.feature_layer,
                 "vision_feature_select_strategy": "default", "projector_hidden_act": "gelu", "multimodal_projector_bias": True,
                 "image_seq_length": v.tokens_per_crop - 1, "tie_word_embeddings": t.tie_word_embeddings,
@@ -222,7 +233,8 @@ class VLMConfig:
                                   "num_attention_heads": v.num_heads, "image_size": v.image_size, "patch_size": v.patch_size,
                                   "num_channels": v.in_channels, "hidden_act": "quick_gelu", "projection_dim": v.hidden_size,
                                   "layer_norm_eps": self.extra.get("vision_layer_norm_eps", 1e-5)},
-                "text_config": {"model_type": "llama", "vocab_size": t.vocab_size, "hidden_size": t.hidden_size,
+                "text_config": {"model_type": self.extra.get("text_model_type", "llama"), "vocab_size": t.vocab_size,
+                                "hidden_size": t.hidden_size,
                                 "intermediate_size": t.intermediate_size, "num_hidden_layers": t.num_layers,
                                 "num_attention_heads": t.num_heads, "num_key_value_heads": t.num_kv_heads,
                                 "head_dim": t.head_dim, "rms_norm_eps": t.rms_norm_eps, "rope_theta": t.rope_theta,
@@ -311,6 +323,17 @@ PRESETS = {
                      image_size=336, feature_layer=-2),
         image_token_id=32000, video_token_id=-1, vision_start_token_id=-1, vision_end_token_id=-1, eos_token_id=2,
         pad_token_id=32001, extra={"vision_layer_norm_eps": 1e-5}),
+    # llava-v1.6-mistral-7b-hf: Mistral-7B (GQA 32 : 8, hd 128, I 14336, no biases) + the same CLIP tower, anyres crops of 336
+    "llava-1.6-mistral-7b": lambda: VLMConfig(
+        "llava_next", TextConfig(32064, 4096, 14336, 32, 32, 8, 128, rms_norm_eps=1e-5, rope_theta=1000000.0, mrope_section=(),
+                                 tie_word_embeddings=False, qkv_bias=False),
+        VisionConfig(kind="clip", depth=24, hidden_size=1024, num_heads=16, intermediate_size=4096, out_hidden_size=4096,
+                     patch_size=14, spatial_merge_size=1, temporal_patch_size=1, window_size=0, fullatt_block_indexes=(),
+                     image_size=336, feature_layer=-2),
+        image_token_id=32000, video_token_id=-1, vision_start_token_id=-1, vision_end_token_id=-1, eos_token_id=2,
+        pad_token_id=32001,
+        extra={"vision_layer_norm_eps": 1e-5, "text_model_type": "mistral",
+               "image_grid_pinpoints": [[336, 672], [672, 336], [672, 672], [1008, 336], [336, 1008]]}),
 }
 
 
@@ -343,6 +366,19 @@ def tiny_config(family: str = "qwen2_5_vl") -> VLMConfig:
                          vision_end_token_id=-1, eos_token_id=1005, pad_token_id=1006,
                          extra={"image_grid_pinpoints": [[56, 56], [56, 112], [112, 56], [112, 112], [168, 56], [56, 168]],
                                 "vision_layer_norm_eps": 1e-6})
+    if family == "llava_next":
+        # LLaVA-1.6 twin: CLIP tower as the 1.5 twin, anyres crops of 56 pixels (4 x 4 patch tokens + class token each) packed with
+        # image_newline, grouped-query decoder without biases (Mistral-like), head_dim 64
+        text = TextConfig(vocab_size=1024, hidden_size=128, intermediate_size=256, num_layers=2, num_heads=2,
+                          num_kv_heads=1, head_dim=64, rms_norm_eps=1e-5, rope_theta=10000.0, mrope_section=(),
+                          tie_word_embeddings=False, qkv_bias=False)
+        vis = VisionConfig(kind="clip", depth=3, hidden_size=64, num_heads=4, intermediate_size=160, out_hidden_size=128,
+                           patch_size=14, spatial_merge_size=1, temporal_patch_size=1, window_size=0,
+                           fullatt_block_indexes=(), image_size=56, feature_layer=-2)
+        return VLMConfig(family, text, vis, image_token_id=1001, video_token_id=-1, vision_start_token_id=-1,
+                         vision_end_token_id=-1, eos_token_id=1005, pad_token_id=1006,
+                         extra={"vision_layer_norm_eps": 1e-5, "text_model_type": "mistral",
+                                "image_grid_pinpoints": [[56, 112], [112, 56], [112, 112], [168, 56], [56, 168]]})
     if family == "llava":
         # LLaVA-1.5 twin: multi-head attention without projection biases (LLaMA), CLIP tower of 3 blocks whose last one is
         # skipped (vision_feature_layer -2), class token + 4 x 4 patches of a 56-pixel image

@@ -260,7 +260,7 @@ def llava_image_layout(cfg: VLMConfig, image_hw):
         pad = (cur_w - new_w) // 2
         rows, cols = (0, cur_h), (pad, cur_w - pad)
     kh, kw = rows[1] - rows[0], cols[1] - cols[0]
-    if (kh * kw / (9 * side * side)) ** 0.5 > 1.1:
+    if cfg.family == "llava_onevision" and (kh * kw / (9 * side * side)) ** 0.5 > 1.1:      # LLaVA-Next never shrinks
         raise NotImplementedError("anyres_max_9 bilinear feature shrink (image spanning > 9 crops) is not implemented")
     return gh * gw + 1, (gh, gw), rows, cols
 
@@ -272,12 +272,13 @@ def llava_pack_index(cfg: VLMConfig, image_hw):
     v = cfg.vision
     side = v.image_size // v.patch_size
     tpc = side * side
+    stride, off = v.tokens_per_crop, v.tokens_per_crop - tpc     # CLIP (LLaVA-Next): a crop's row 0 is its class token, never packed
     n_crops, (gh, gw), rows, cols = llava_image_layout(cfg, image_hw)
-    idx = [np.arange(tpc, dtype=np.int64)]
+    idx = [np.arange(tpc, dtype=np.int64) + off]
     ys = np.arange(rows[0], rows[1])
     xs = np.arange(cols[0], cols[1])
     crop = 1 + (ys[:, None] // side) * gw + (xs[None, :] // side)
-    body = crop * tpc + (ys[:, None] % side) * side + (xs[None, :] % side)
+    body = crop * stride + off + (ys[:, None] % side) * side + (xs[None, :] % side)
     body = np.concatenate([body, np.full((len(ys), 1), -1, dtype=np.int64)], 1)
     idx.append(body.reshape(-1))
     return np.concatenate(idx).astype(np.int32), n_crops
@@ -286,7 +287,7 @@ def llava_pack_index(cfg: VLMConfig, image_hw):
 def image_token_count(cfg: VLMConfig, grid_entry) -> int:
     """Number of placeholder tokens one image expands to. grid_entry: (t, h, w) patch grid for the Qwen families;
     (n_crops, H, W) with the ORIGINAL image size in pixels for LLaVA-OneVision."""
-    if cfg.family == "llava_onevision":
+    if cfg.family in ("llava_onevision", "llava_next"):
         return len(llava_pack_index(cfg, (int(grid_entry[1]), int(grid_entry[2])))[0])
     if cfg.family == "llava":          # LLaVA-1.5: one 336-pixel crop, class token dropped (select strategy "default")
         return cfg.vision.tokens_per_crop - 1
@@ -298,7 +299,7 @@ def position_ids(input_ids: np.ndarray, grid_thw: list, cfg: VLMConfig, attentio
                  prompt_len: int | None = None):
     """Family dispatch: M-RoPE ids for Qwen2(.5)-VL; plain 1-D positions (cumulative count of unmasked tokens, the
     Qwen2 text model under LLaVA-OneVision) replicated on the three axes otherwise. Returns ([3, B, T], deltas [B])."""
-    if cfg.family not in ("llava_onevision", "llava"):
+    if cfg.family not in ("llava_onevision", "llava", "llava_next"):
         return mrope_position_ids(input_ids, grid_thw, cfg, attention_mask, prompt_len)
     B, T = input_ids.shape
     am = np.ones((B, T), dtype=np.int64) if attention_mask is None else attention_mask.astype(np.int64)
@@ -338,7 +339,8 @@ class SiglipGeometry:
 
 
 def siglip_geometry(cfg: VLMConfig, grid, device) -> SiglipGeometry:
-    key = ("siglip", cfg.vision.image_size, cfg.vision.patch_size, tuple(map(tuple, grid)), str(device))
+    key = ("siglip", cfg.family, cfg.vision.kind, cfg.vision.image_size, cfg.vision.patch_size, tuple(map(tuple, grid)), str(device),
+           str(cfg.extra.get("image_grid_pinpoints")))
     g = _GEOM_CACHE.get(key)
     if g is None:
         if len(_GEOM_CACHE) > 64:
@@ -386,7 +388,7 @@ def vision_inputs_from_processor(cfg: VLMConfig, enc) -> tuple:
             pv = pv[None]
         S = cfg.vision.image_size
         return clip_pixel_rows(pv, cfg.vision), [(1, S, S)] * pv.shape[0]
-    if cfg.family != "llava_onevision" or "image_sizes" not in enc:
+    if cfg.family not in ("llava_onevision", "llava_next") or "image_sizes" not in enc:
         raise ValueError("processor output has pixel_values but neither image_grid_thw nor image_sizes")
     sizes = enc["image_sizes"].tolist() if torch.is_tensor(enc["image_sizes"]) else enc["image_sizes"]
     if pv.dim() == 4:
@@ -394,6 +396,7 @@ def vision_inputs_from_processor(cfg: VLMConfig, enc) -> tuple:
     rows, grid = [], []
     for i, (h, w) in enumerate(sizes):
         n, _, _, _ = llava_image_layout(cfg, (int(h), int(w)))
-        rows.append(patchify_crops(pv[i, :n], cfg.vision.patch_size))
+        rows.append(clip_pixel_rows(pv[i, :n], cfg.vision) if cfg.vision.kind == "clip"
+                    else patchify_crops(pv[i, :n], cfg.vision.patch_size))
         grid.append((n, int(h), int(w)))
     return torch.cat(rows, 0), grid

@@ -119,6 +119,8 @@ class ParamStore:
             self._add("visual.merger.fc1.bias", (v.out_hidden_size,), False)
             self._add("visual.merger.fc2.weight", (v.out_hidden_size, v.out_hidden_size), True)
             self._add("visual.merger.fc2.bias", (v.out_hidden_size,), False)
+            if self.cfg.family == "llava_next":
+                self._add("image_newline", (v.out_hidden_size,), False)      # the anyres row separator
         elif v.kind == "siglip":
             # SigLIP's post_layernorm is NOT on the path (features = last encoder layer output); kept for round trips.
             self._add("visual.post_layernorm.weight", (E,), False)
@@ -257,7 +259,7 @@ class ParamStore:
         yield "multi_modal_projector.linear_1.bias", src["visual.merger.fc1.bias"]
         yield "multi_modal_projector.linear_2.weight", src["visual.merger.fc2.weight"]
         yield "multi_modal_projector.linear_2.bias", src["visual.merger.fc2.bias"]
-        if v.kind == "siglip":
+        if "image_newline" in src:
             yield "image_newline", src["image_newline"]
 
     def _hf_named_text(self, src, prefix, head_name):
@@ -288,7 +290,7 @@ class ParamStore:
 
     def canonical_name(self, name: str) -> str:
         """Map transformers-5.x key names (`model.visual.*`, `model.language_model.*`) onto the 4.51 layout."""
-        if self.cfg.family in ("llava_onevision", "llava"):
+        if self.cfg.family in ("llava_onevision", "llava", "llava_next"):
             # 5.x: model.vision_tower.*, model.multi_modal_projector.*, model.image_newline, model.language_model.*, lm_head.*
             if name.startswith("model.language_model."):
                 return "language_model.model." + name[len("model.language_model."):]

@@ -32,6 +32,7 @@ class Template:
     default_system: str
     plugin: str            # "qwen2_vl" | "llava_next" | "llava"
     image_token: str
+    prefix: str = ""       # in front of the first prompt ("{bos}" for the Mistral format)
 
 
 _CHATML = dict(system="<|im_start|>system\n{content}<|im_end|>\n",
@@ -46,8 +47,16 @@ TEMPLATES = {
                       assistant="{content}{eos}",
                       default_system="A chat between a curious user and an artificial intelligence assistant. "
                                      "The assistant gives helpful, detailed, and polite answers to the user's questions."),
+    # LLaVA-1.6 (template.py:844-853, 868-880): the vicuna format again / Mistral's [INST] format, with the anyres plugin
+    "llava_next": Template("llava_next", plugin="llava_next", image_token="<image>", system="{content}",
+                           user="USER: {content} ASSISTANT:", assistant="{content}{eos}",
+                           default_system="A chat between a curious user and an artificial intelligence assistant. "
+                                          "The assistant gives helpful, detailed, and polite answers to the user's questions."),
+    "llava_next_mistral": Template("llava_next_mistral", plugin="llava_next", image_token="<image>", system="{content}\n\n",
+                                   user="[INST] {content}[/INST]", assistant=" {content}{eos}", default_system="", prefix="{bos}"),
 }
-FAMILY_TEMPLATE = {"qwen2_vl": "qwen2_vl", "qwen2_5_vl": "qwen2_vl", "llava_onevision": "llava_next_qwen", "llava": "llava"}
+FAMILY_TEMPLATE = {"qwen2_vl": "qwen2_vl", "qwen2_5_vl": "qwen2_vl", "llava_onevision": "llava_next_qwen", "llava": "llava",
+                   "llava_next": "llava_next_mistral"}      # what PA_SFT_LLaVA_1_6.sh passes; `--template llava_next` for the Vicuna variant
 
 
 def get_template(name: Optional[str], family: Optional[str] = None) -> Template:
@@ -110,7 +119,7 @@ def expand_image_placeholders(messages: list, seqlens: list, tpl: Template) -> l
     return out
 
 
-def render_pairs(messages: list, tpl: Template, eos: str = "</s>") -> list:
+def render_pairs(messages: list, tpl: Template, eos: str = "</s>", bos: str = "<s>") -> list:
     """[(prompt text, response text)] per (user, assistant) turn: the first prompt carries the system block (the dataset's
     system message, else the template default), every prompt ends with the assistant header, every response with the
     end-of-turn token - Template._encode with the chatml slots."""
@@ -126,7 +135,8 @@ def render_pairs(messages: list, tpl: Template, eos: str = "</s>") -> list:
         u, a = msgs[i], msgs[i + 1]
         if u["role"] != "user" or a["role"] != "assistant":
             raise ValueError(f"expected a (user, assistant) turn at message {i}, got ({u['role']}, {a['role']})")
-        prompt = (tpl.system.format(content=system) if i == 0 and system else "") + tpl.user.format(content=u["content"])
+        prompt = ((tpl.prefix.format(bos=bos) if i == 0 else "") + (tpl.system.format(content=system) if i == 0 and system else "")
+                  + tpl.user.format(content=u["content"]))
         pairs.append((prompt, tpl.assistant.format(content=a["content"], eos=eos)))
     return pairs
 

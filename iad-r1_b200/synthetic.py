@@ -31,9 +31,15 @@ class _Encoding(dict):
 class SyntheticProcessor:
     def __init__(self, cfg: VLMConfig, min_pixels: int = 3136, max_pixels: int = 12845056):
         self.cfg = cfg
-        self.llava = cfg.family in ("llava_onevision", "llava")     # bare <image> placeholder in the chat template
+        self.llava = cfg.family in ("llava_onevision", "llava", "llava_next")     # bare <image> placeholder in the chat template
         self.llava15 = cfg.family == "llava"
-        if self.llava15:
+        if cfg.family == "llava_next":
+            # the REAL HF anyres image processor of LLaVA-1.6 (best-resolution select, resize + pad, S-pixel crops + base crop)
+            from transformers import LlavaNextImageProcessor
+            S = cfg.vision.image_size
+            self.image_processor = LlavaNextImageProcessor(image_grid_pinpoints=cfg.extra["image_grid_pinpoints"],
+                                                           size={"shortest_edge": S}, crop_size={"height": S, "width": S})
+        elif self.llava15:
             # the REAL HF CLIP image processor (shortest edge -> S bicubic, centre crop S x S, CLIP mean / std)
             from transformers import CLIPImageProcessor
             S = cfg.vision.image_size

@@ -141,9 +141,9 @@ class SCGRPOTrainer(TrainerCore):
             # substring test survives here only as the error message for a path WITHOUT a readable config.json.
             if not os.path.isfile(os.path.join(model, "config.json")):
                 families = ("qwen2-vl", "qwen2_vl", "qwen2vl", "qwen2.5-vl", "qwen2.5_vl", "qwen2.5vl", "qwen2_5_vl",
-                            "llava-ov", "llava_ov", "llava_si", "llava-onevision", "llava_onevision", "llava-1_5", "llava_1_5")
+                            "llava-ov", "llava_ov", "llava_si", "llava-onevision", "llava_onevision", "llava-1_5", "llava_1_5", "llava-next", "llava_next", "llava_1_6")
                 hint = "" if any(k in model.lower() for k in families) else \
-                    " (and the id names none of the supported families: Qwen2-VL / Qwen2.5-VL / LLaVA-OneVision / LLaVA-1.5)"
+                    " (and the id names none of the supported families: Qwen2-VL / Qwen2.5-VL / LLaVA-OneVision / LLaVA-1.5 / LLaVA-Next)"
                 raise ValueError(f"Unsupported model: {model}: no config.json under that path{hint}; there is no hub access "
                                  f"on the training box, pass a local checkpoint directory")
             from .checkpoint import load_config

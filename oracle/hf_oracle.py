@@ -44,10 +44,13 @@ def hf_config(cfg, attn_implementation="eager"):
             multimodal_projector_bias=True, tie_word_embeddings=t.tie_word_embeddings)
         c._attn_implementation = attn_implementation
         return c
-    if cfg.family == "llava":
-        from transformers import LlavaConfig
-        c = LlavaConfig(
-            text_config=dict(model_type="llama", vocab_size=t.vocab_size, hidden_size=t.hidden_size,
+    if cfg.family in ("llava", "llava_next"):
+        from transformers import LlavaConfig, LlavaNextConfig
+        nxt = cfg.family == "llava_next"
+        extra_kw = dict(image_grid_pinpoints=cfg.extra["image_grid_pinpoints"], use_image_newline_parameter=True) if nxt else {}
+        c = (LlavaNextConfig if nxt else LlavaConfig)(
+            **extra_kw,
+            text_config=dict(model_type=cfg.extra.get("text_model_type", "llama"), vocab_size=t.vocab_size, hidden_size=t.hidden_size,
                              intermediate_size=t.intermediate_size, num_hidden_layers=t.num_layers,
                              num_attention_heads=t.num_heads, num_key_value_heads=t.num_kv_heads, head_dim=t.head_dim,
                              max_position_embeddings=4096, rms_norm_eps=t.rms_norm_eps, rope_theta=t.rope_theta,
@@ -86,6 +89,8 @@ def build_hf_model(cfg, seed=0, dtype=torch.float32, attn_implementation="eager"
         from transformers import LlavaOnevisionForConditionalGeneration as Cls
     elif cfg.family == "llava":
         from transformers import LlavaForConditionalGeneration as Cls
+    elif cfg.family == "llava_next":
+        from transformers import LlavaNextForConditionalGeneration as Cls
     elif cfg.family == "qwen2_5_vl":
         from transformers import Qwen2_5_VLForConditionalGeneration as Cls
     else:

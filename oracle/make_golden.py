@@ -79,14 +79,14 @@ def main():
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
     only = sys.argv[1:]
-    for family in ("qwen2_5_vl", "qwen2_vl", "llava_onevision", "llava"):
+    for family in ("qwen2_5_vl", "qwen2_vl", "llava_onevision", "llava", "llava_next"):
         if only and family not in only:
             continue
         cfg = tiny_config(family)
         G, C, grid = 4, 12, (1, 8, 8)
-        if family == "llava_onevision":
+        if family in ("llava_onevision", "llava_next"):
             ids, P, crops, grid = synthetic_batch_llava(cfg, G, C)
-            px = patchify_crops(crops, cfg.vision.patch_size)
+            px = patchify_crops(crops, cfg.vision.patch_size) if family == "llava_onevision" else clip_pixel_rows(crops, cfg.vision)
         elif family == "llava":
             ids, P, crops, grid = synthetic_batch_llava15(cfg, G, C)
             px = clip_pixel_rows(crops, cfg.vision)
@@ -101,7 +101,7 @@ def main():
 
         model = build_hf_model(cfg, seed=0, dtype=torch.float32)
         sd = {k: v.detach().to(torch.bfloat16).clone() for k, v in model.state_dict().items()}
-        if family == "llava_onevision":
+        if family in ("llava_onevision", "llava_next"):
             sizes = torch.tensor([[grid[1], grid[2]]] * G)
 
             def fwd(m):

@@ -558,14 +558,16 @@ def test_sft_native_data_path():
     for bad in ([3], [3, 2, 1]):
         with pytest.raises(ValueError, match="number of <image> tokens|less than the number"):
             D.expand_image_placeholders(msgs, bad, tpl)
+    mt = D.get_template(None, "llava_next")          # PA_SFT_LLaVA_1_6.sh: --template llava_next_mistral (template.py:885-896)
+    assert mt.name == "llava_next_mistral" and D.render_pairs(msgs[:2], mt) == [("<s>[INST] <image>first?[/INST]", " yes</s>")]
     with pytest.raises(ValueError):
-        D.get_template("llava_next_mistral")
+        D.get_template("paligemma")
     ids, labels = D.encode_pairs([([1, 2, 3], [4, 5]), ([6], [7, 8, 9])], 100)
     assert ids == [1, 2, 3, 4, 5, 6, 7, 8, 9] and labels == [-100, -100, -100, 4, 5, -100, 7, 8, 9]
     col = D.collate([dict(input_ids=ids, labels=labels), dict(input_ids=[1, 2], labels=[-100, 2])], pad_token_id=0)
     assert col["input_ids"].shape == (2, 16) and (col["labels"][1, 2:] == -100).all() and col["attention_mask"].sum() == 11
     # end to end on the twins: two images in one conversation, two assistant turns
-    for fam in ("qwen2_5_vl", "llava_onevision", "llava"):
+    for fam in ("qwen2_5_vl", "llava_onevision", "llava", "llava_next"):
         cfg = tiny_config(fam)
         proc = SyntheticProcessor(cfg)
         ex = {"messages": msgs, "images": [synthetic_image(0, 112), synthetic_image(1, 84)]}

@@ -38,7 +38,7 @@ def _sel(fix, dev):
     return rows, labels
 
 
-@pytest.mark.parametrize("family", ["qwen2_5_vl", "qwen2_vl", "llava_onevision", "llava"])
+@pytest.mark.parametrize("family", ["qwen2_5_vl", "qwen2_vl", "llava_onevision", "llava", "llava_next"])
 def test_logprobs_and_grads_match_hf(cuda, family):
     fix = _load(family)
     cfg, ps, vlm = _build(fix, cuda)
@@ -89,7 +89,7 @@ def test_logprobs_and_grads_match_hf(cuda, family):
     print(f"[{family}] worst gradient rel err {worst[0]:.4f} at {worst[1]} over {len(fix['grads'])} tensors")
 
 
-@pytest.mark.parametrize("family", ["qwen2_5_vl", "qwen2_vl", "llava_onevision", "llava"])
+@pytest.mark.parametrize("family", ["qwen2_5_vl", "qwen2_vl", "llava_onevision", "llava", "llava_next"])
 def test_shared_prefix_layout_matches_hf(cuda, family):
     """The production layout [prompt | G completions] (prompt computed once, ops.SharedPrefixAttention) against the same
     HF oracle fixture, which runs the reference's full [G, P + C] batch: same log-probs, same gradients."""
@@ -124,7 +124,7 @@ def test_shared_prefix_layout_matches_hf(cuda, family):
     print(f"[{family}] shared-prefix worst gradient rel err {worst[0]:.4f} at {worst[1]}")
 
 
-@pytest.mark.parametrize("family", ["qwen2_5_vl", "llava_onevision", "llava"])
+@pytest.mark.parametrize("family", ["qwen2_5_vl", "llava_onevision", "llava", "llava_next"])
 def test_hf_state_dict_roundtrip(cuda, family):
     fix = _load(family)
     cfg, ps, vlm = _build(fix, cuda)

@@ -20,7 +20,7 @@ def _tiny_trainer(cuda, family="qwen2_5_vl", **over):
     return cfg, SCGRPOTrainer(model=cfg, reward_funcs=[format_reward, make_noise_reward(0)], args=args, processing_class=proc)
 
 
-@pytest.mark.parametrize("family", ["qwen2_5_vl", "llava_onevision", "llava"])
+@pytest.mark.parametrize("family", ["qwen2_5_vl", "llava_onevision", "llava", "llava_next"])
 def test_decode_matches_training_forward(cuda, family):
     """Teacher-forcing check of the whole rollout path: the log-prob the DECODE kernels assign to each sampled token
     (KV cache, prefix sharing, rope deltas, split-K atomics, fp32 residual) equals the TRAINING forward's log-prob of the
@@ -92,7 +92,7 @@ def test_cuda_graph_rollout_follows_the_seed(cuda):
     assert (res[True] == res[False]).float().mean().item() > 0.9
 
 
-@pytest.mark.parametrize("family", ["qwen2_5_vl", "llava_onevision", "llava"])
+@pytest.mark.parametrize("family", ["qwen2_5_vl", "llava_onevision", "llava", "llava_next"])
 def test_trainer_two_steps(cuda, family):
     from iad_r1_b200.synthetic import synthetic_dataset
     cfg, tr = _tiny_trainer(cuda, family)
@@ -201,7 +201,7 @@ def test_sft_trainer_reduces_loss(cuda, tmp_path):
     from iad_r1_b200.config import tiny_config
     from iad_r1_b200.sft_trainer import PASFTTrainer, SFTArguments
     from iad_r1_b200.synthetic import SyntheticProcessor, synthetic_image
-    for family, frozen in (("qwen2_5_vl", False), ("qwen2_vl", True), ("llava_onevision", False), ("llava", False)):
+    for family, frozen in (("qwen2_5_vl", False), ("qwen2_vl", True), ("llava_onevision", False), ("llava", False), ("llava_next", False)):
         cfg = tiny_config(family)
         data = [{"messages": [{"role": "user", "content": "<image>Is there a defect in the image?"},
                               {"role": "assistant", "content": "<think> the surface is scratch </think> <answer> yes </answer>"}],

@@ -26,6 +26,7 @@ CASES = {
     "llava-ov-0.5b": (2, 24, (400, 600)),
     "qwen2.5-vl-7b": (2, 24, (1, 16, 16)),      # H 3584, GQA 7:1, I 18944, V 152064, untied lm_head
     "llava-1.5-7b": (2, 24, None),              # LLaMA-7B widths (MHA 32 x 128, no biases), CLIP ViT-L/14-336 (hd 64, 577 tokens)
+    "llava-1.6-mistral-7b": (2, 16, (300, 500)),  # Mistral-7B widths (GQA 4:1, I 14336), 3 crops of 336 packed with image_newline
 }
 
 
@@ -35,11 +36,15 @@ def _build_case(model, seed=0):
     from oracle import grpo_ref
     from oracle.hf_oracle import build_hf_model
     from oracle.make_golden import synthetic_batch, synthetic_batch_llava
-    cfg = depth_reduced(PRESETS[model](), 2, 3 if model == "llava-1.5-7b" else 2)   # CLIP: 3 blocks, the last one not run
+    cfg = depth_reduced(PRESETS[model](), 2, 3 if model.startswith("llava-1.") else 2)   # CLIP: 3 blocks, the last one not run
     G, C, spec = CASES[model]
-    if cfg.family == "llava_onevision":
+    if cfg.family in ("llava_onevision", "llava_next"):
+        from iad_r1_b200.geometry import clip_pixel_rows, llava_image_layout
         ids, P, crops, grid = synthetic_batch_llava(cfg, G, C, image_hw=spec, seed=seed)
-        px = patchify_crops(crops, cfg.vision.patch_size)
+        n_crops = llava_image_layout(cfg, spec)[0]
+        if n_crops != crops.shape[0]:        # the generator draws 5 crops; keep what this image size needs
+            crops, grid = crops[:n_crops], (n_crops, spec[0], spec[1])
+        px = patchify_crops(crops, cfg.vision.patch_size) if cfg.family == "llava_onevision" else clip_pixel_rows(crops, cfg.vision)
     elif cfg.family == "llava":
         from iad_r1_b200.geometry import clip_pixel_rows
         from oracle.make_golden import synthetic_batch_llava15
@@ -62,7 +67,7 @@ def _hf_tail_logits(case, ids_t, pos_t, attn_mask, keep):
     cfg, G, grid = case["cfg"], ids_t.shape[0], case["grid"]
     if cfg.family == "llava":
         return hf_logits_llava15(case["hf"], ids_t, case["crops"].repeat(G, 1, 1, 1), pos_t[0], attn_mask, logits_to_keep=keep)
-    if cfg.family == "llava_onevision":
+    if cfg.family in ("llava_onevision", "llava_next"):
         sizes = torch.tensor([[grid[1], grid[2]]] * G)
         return hf_logits_llava(case["hf"], ids_t, case["crops"][None].repeat(G, 1, 1, 1, 1), sizes, pos_t[0], attn_mask,
                                logits_to_keep=keep)
