@@ -84,10 +84,12 @@ class ParamStore:
         self._add("visual.patch_embed.weight", (E, v.patch_dim_padded), True)   # pad columns stay exactly zero
         if v.kind == "siglip":
             self._add("visual.patch_embed.bias", (E,), False)
-            self._add("visual.pos_embed.weight", (v.tokens_per_crop, E), False)   # learned table: no weight decay
+            # HF Trainer's decay rule excludes only biases and norm weights (get_decay_parameter_names): the nn.Embedding position
+            # table, class_embedding and image_newline all decay
+            self._add("visual.pos_embed.weight", (v.tokens_per_crop, E), True)
         if v.kind == "clip":
             # column `patch_dim` of the patch weight IS the class embedding (see VisionConfig.patch_dim_padded)
-            self._add("visual.pos_embed.weight", (v.tokens_per_crop, E), False)
+            self._add("visual.pos_embed.weight", (v.tokens_per_crop, E), True)
             self._add("visual.pre_ln.weight", (E,), False)
             self._add("visual.pre_ln.bias", (E,), False)
         for i in range(v.depth):
@@ -120,7 +122,7 @@ class ParamStore:
             self._add("visual.merger.fc2.weight", (v.out_hidden_size, v.out_hidden_size), True)
             self._add("visual.merger.fc2.bias", (v.out_hidden_size,), False)
             if self.cfg.family == "llava_next":
-                self._add("image_newline", (v.out_hidden_size,), False)      # the anyres row separator
+                self._add("image_newline", (v.out_hidden_size,), True)       # the anyres row separator (a bare nn.Parameter: decays)
         elif v.kind == "siglip":
             # SigLIP's post_layernorm is NOT on the path (features = last encoder layer output); kept for round trips.
             self._add("visual.post_layernorm.weight", (E,), False)
@@ -130,7 +132,7 @@ class ParamStore:
             self._add("visual.merger.fc1.bias", (v.out_hidden_size,), False)
             self._add("visual.merger.fc2.weight", (v.out_hidden_size, v.out_hidden_size), True)
             self._add("visual.merger.fc2.bias", (v.out_hidden_size,), False)
-            self._add("image_newline", (v.out_hidden_size,), False)
+            self._add("image_newline", (v.out_hidden_size,), True)
         else:
             self._add("visual.merger.ln_q.weight", (E,), False)
             if v.kind == "qwen2_vl":
