@@ -142,8 +142,9 @@ class VLMConfig:
         t, v = d["text_config"], d["vision_config"]
         if d.get("vision_feature_select_strategy", "full") != "full" or d.get("vision_feature_layer", -1) != -1:
             raise ValueError("llava_onevision: only vision_feature_layer=-1 / select_strategy='full' is supported")
-        if str(d.get("vision_aspect_ratio", "anyres_max_9")) != "anyres_max_9":
-            raise ValueError("llava_onevision: only vision_aspect_ratio='anyres_max_9' is supported")
+        ar = str(d.get("vision_aspect_ratio", "anyres_max_9"))
+        if not ar.startswith("anyres_max_") or not ar[len("anyres_max_"):].isdigit():
+            raise ValueError("llava_onevision: vision_aspect_ratio must be 'anyres_max_<N>'")
         nh = t["num_attention_heads"]
         rope = t.get("rope_parameters") or {}
         text = TextConfig(
@@ -165,7 +166,8 @@ class VLMConfig:
                          eos_token_id=eos[0] if isinstance(eos, list) else eos,
                          pad_token_id=d.get("pad_token_id") or t.get("pad_token_id") or 151643,
                          extra={"image_grid_pinpoints": [list(x) for x in d["image_grid_pinpoints"]],
-                                "vision_layer_norm_eps": v.get("layer_norm_eps", 1e-6)})
+                                "vision_layer_norm_eps": v.get("layer_norm_eps", 1e-6),
+                                "anyres_max": int(ar[len("anyres_max_"):])})
 
     @staticmethod
     def _from_llava(d: dict) -> "VLMConfig":
@@ -246,7 +248,7 @@ class VLMConfig:
                 "model_type": "llava_onevision", "architectures": ["LlavaOnevisionForConditionalGeneration"],
                 "image_token_index": self.image_token_id, "video_token_index": self.video_token_id,
                 "image_grid_pinpoints": self.extra["image_grid_pinpoints"], "vision_feature_layer": -1,
-                "vision_feature_select_strategy": "full", "vision_aspect_ratio": "anyres_max_9",
+                "vision_feature_select_strategy": "full", "vision_aspect_ratio": f"anyres_max_{self.extra.get('anyres_max', 9)}",
                 "projector_hidden_act": "gelu", "multimodal_projector_bias": True,
                 "tie_word_embeddings": t.tie_word_embeddings, "torch_dtype": "bfloat16",
                 "text_config": {"model_type": "qwen2", "vocab_size": t.vocab_size, "hidden_size": t.hidden_size,

@@ -9,6 +9,8 @@ from __future__ import annotations
 
 import functools
 
+import math
+
 import numpy as np
 import torch
 
@@ -244,7 +246,7 @@ def select_best_resolution(original_size, possible_resolutions):
 
 def llava_image_layout(cfg: VLMConfig, image_hw):
     """For one image of size (H, W): (n_crops incl. the base crop, crop grid (gh, gw), kept feature-grid rows / cols after
-    unpadding as slices). Raises for images large enough to need the bilinear shrink of anyres_max_9."""
+    unpadding as slices). Whether the kept feature map is then shrunk (anyres_max_N) is `llava_shrink`."""
     v = cfg.vision
     side = v.image_size // v.patch_size                       # 27 feature rows / cols per crop
     bh, bw = select_best_resolution(image_hw, cfg.extra["image_grid_pinpoints"])
@@ -259,10 +261,23 @@ def llava_image_layout(cfg: VLMConfig, image_hw):
         new_w = int(round(ow * (cur_h / oh), 7))
         pad = (cur_w - new_w) // 2
         rows, cols = (0, cur_h), (pad, cur_w - pad)
-    kh, kw = rows[1] - rows[0], cols[1] - cols[0]
-    if cfg.family == "llava_onevision" and (kh * kw / (9 * side * side)) ** 0.5 > 1.1:      # LLaVA-Next never shrinks
-        raise NotImplementedError("anyres_max_9 bilinear feature shrink (image spanning > 9 crops) is not implemented")
     return gh * gw + 1, (gh, gw), rows, cols
+
+
+def llava_shrink(cfg: VLMConfig, image_hw):
+    """LLaVA-OneVision `anyres_max_N` (HF modeling_llava_onevision.py:328-335): when the kept feature map of an image holds more
+    than 1.1^2 x N crops' worth of tokens it is bilinearly resized to (kh // ratio, kw // ratio), ratio = sqrt(kh kw / (N side^2)).
+    Returns (kh, kw, kh2, kw2) or None (LLaVA-Next never shrinks)."""
+    if cfg.family != "llava_onevision":
+        return None
+    v = cfg.vision
+    side = v.image_size // v.patch_size
+    _, _, rows, cols = llava_image_layout(cfg, image_hw)
+    kh, kw = rows[1] - rows[0], cols[1] - cols[0]
+    ratio = math.sqrt(kh * kw / (int(cfg.extra.get("anyres_max", 9)) * side * side))
+    if ratio <= 1.1:
+        return None
+    return kh, kw, int(kh // ratio), int(kw // ratio)
 
 
 def llava_pack_index(cfg: VLMConfig, image_hw):
@@ -288,7 +303,12 @@ def image_token_count(cfg: VLMConfig, grid_entry) -> int:
     """Number of placeholder tokens one image expands to. grid_entry: (t, h, w) patch grid for the Qwen families;
     (n_crops, H, W) with the ORIGINAL image size in pixels for LLaVA-OneVision."""
     if cfg.family in ("llava_onevision", "llava_next"):
-        return len(llava_pack_index(cfg, (int(grid_entry[1]), int(grid_entry[2])))[0])
+        hw = (int(grid_entry[1]), int(grid_entry[2]))
+        sh = llava_shrink(cfg, hw)
+        if sh is not None:      # base crop + the resized feature map with one image_newline per row
+            side = cfg.vision.image_size // cfg.vision.patch_size
+            return side * side + sh[2] * (sh[3] + 1)
+        return len(llava_pack_index(cfg, hw)[0])
     if cfg.family == "llava":          # LLaVA-1.5: one 336-pixel crop, class token dropped (select strategy "default")
         return cfg.vision.tokens_per_crop - 1
     t, h, w = grid_entry
@@ -317,6 +337,10 @@ class SiglipGeometry:
     def __init__(self, cfg: VLMConfig, grid: list, device):
         tpc = cfg.vision.tokens_per_crop
         packs, base, n_crops_total = [], 0, 0
+        # anyres_max shrink (LLaVA-OneVision, rare: images spanning more than N crops): the kernels pack the UNSHRUNK map; the
+        # images listed here are resized afterwards (model.VLM._apply_shrink): (offset in the packed stream, packed length,
+        # offset in the final stream, final length, base tokens, kh, kw, kh2, kw2)
+        self.shrinks, u_off, f_off = [], 0, 0
         for n_crops, h, w in grid:
             if cfg.family == "llava":      # LLaVA-1.5: every patch token of the single crop, class token (row 0) dropped
                 idx, n = np.arange(1, tpc, dtype=np.int64), 1
@@ -325,8 +349,15 @@ class SiglipGeometry:
             if n != int(n_crops):
                 raise ValueError(f"image of size {(h, w)} needs {n} crops, processor supplied {n_crops}")
             packs.append(np.where(idx >= 0, idx + base, -1))
+            sh = llava_shrink(cfg, (int(h), int(w))) if cfg.family != "llava" else None
+            n_f = image_token_count(cfg, (n, h, w))
+            self.shrinks.append((u_off, len(idx), f_off, n_f, (cfg.vision.image_size // cfg.vision.patch_size) ** 2, sh))
+            u_off += len(idx)
+            f_off += n_f
             base += n * tpc
             n_crops_total += n
+        self.n_final = f_off
+        self.has_shrink = any(s_[5] is not None for s_ in self.shrinks)
         self.n_crops = n_crops_total
         self.n_patches = n_crops_total * tpc
         pack = np.concatenate(packs) if packs else np.zeros(0, dtype=np.int64)

@@ -175,6 +175,8 @@ class VLM:
     def vision_backward(self, d_out: torch.Tensor, ctx: VisionCtx):
         """Accumulates vision-tower gradients into the fp32 grad buffer given d(image embeddings) bf16."""
         v, p, g, geo = self.cfg.vision, self.p, self.g, ctx.geo
+        if getattr(geo, "has_shrink", False):          # anyres_max: back through the feature-map resize first
+            d_out = self._unshrink_grad(d_out, geo)
         if getattr(ctx, "native", False):
             self.native.vision_bwd(d_out.contiguous(), ctx.px, ctx.cgeom, ctx.ws)
             ctx.ws = None
@@ -238,6 +240,55 @@ class VLM:
 
     # ---- LLaVA-OneVision: SigLIP tower -> 2-layer GELU projector -> anyres packing -----------------------------------
     def _siglip_forward(self, pixel_values: torch.Tensor, grid, save: bool):
+        """Tower + projector + packing, then the anyres_max feature-map shrink for the (rare) images that need it."""
+        out, ctx = self._siglip_forward_core(pixel_values, grid, save)
+        geo = siglip_geometry(self.cfg, grid, self.device)
+        if geo.has_shrink:
+            out = self._apply_shrink(out, geo)
+        return out, ctx
+
+    def _apply_shrink(self, out_u: torch.Tensor, geo) -> torch.Tensor:
+        """LLaVA-OneVision `anyres_max_N` (HF modeling_llava_onevision.py:328-347): the kernels packed every image as
+        [base crop | kept feature rows, each followed by image_newline]; an image whose kept map exceeds N crops' worth of tokens
+        has that map bilinearly resized (torch's `interpolate`, exactly the reference's call - a rare branch outside the kernels)
+        and re-packed with one newline per resized row."""
+        Hd = out_u.shape[1]
+        nl = self.p["image_newline"].view(1, 1, Hd)
+        parts = []
+        for u_off, n_u, _, _, tpc, sh in geo.shrinks:
+            if sh is None:
+                parts.append(out_u[u_off:u_off + n_u])
+                continue
+            kh, kw, kh2, kw2 = sh
+            parts.append(out_u[u_off:u_off + tpc])
+            body = out_u[u_off + tpc:u_off + n_u].view(kh, kw + 1, Hd)[:, :kw]                # drop the newline column
+            small = torch.nn.functional.interpolate(body.permute(2, 0, 1)[None], [kh2, kw2], mode="bilinear")[0]
+            parts.append(torch.cat([small.permute(1, 2, 0), nl.expand(kh2, 1, Hd).to(small.dtype)], 1).reshape(kh2 * (kw2 + 1), Hd))
+        return torch.cat(parts, 0).contiguous()
+
+    def _unshrink_grad(self, d_out: torch.Tensor, geo) -> torch.Tensor:
+        """Adjoint of `_apply_shrink`: gradient of the final packed tokens -> gradient of the kernels' (unshrunk) packed tokens;
+        the newline columns of resized images feed `image_newline`'s gradient directly."""
+        Hd = d_out.shape[1]
+        parts = []
+        for _, n_u, f_off, n_f, tpc, sh in geo.shrinks:
+            if sh is None:
+                parts.append(d_out[f_off:f_off + n_f])
+                continue
+            kh, kw, kh2, kw2 = sh
+            parts.append(d_out[f_off:f_off + tpc])
+            dbody = d_out[f_off + tpc:f_off + n_f].view(kh2, kw2 + 1, Hd)
+            if self.g is not None and "image_newline" in self.g:
+                self.g["image_newline"].add_(dbody[:, kw2].float().sum(0))
+            x = torch.zeros(1, Hd, kh, kw, dtype=torch.float32, device=d_out.device, requires_grad=True)
+            y = torch.nn.functional.interpolate(x, [kh2, kw2], mode="bilinear")
+            (gx,) = torch.autograd.grad(y, x, dbody[:, :kw2].permute(2, 0, 1)[None].float())          # the resize is linear
+            du = torch.zeros(kh, kw + 1, Hd, dtype=d_out.dtype, device=d_out.device)
+            du[:, :kw] = gx[0].permute(1, 2, 0).to(d_out.dtype)
+            parts.append(du.view(kh * (kw + 1), Hd))
+        return torch.cat(parts, 0).contiguous()
+
+    def _siglip_forward_core(self, pixel_values: torch.Tensor, grid, save: bool):
         """pixel_values [n_crops * 729, 3*14*14] (crop 0 of every image = the base crop) -> packed image embeddings
         [n_image_tokens, H_text] bf16. HF: SiglipVisionEmbeddings (modeling_siglip.py:116-186: Conv2d patch embed with bias +
         learned position table), SiglipEncoderLayer x depth (pre-LN attention + tanh-GELU MLP), hidden_states[-1] WITHOUT

@@ -40,7 +40,8 @@ def hf_config(cfg, attn_implementation="eager"):
                                layer_norm_eps=cfg.extra.get("vision_layer_norm_eps", 1e-6), vision_use_head=False),
             image_token_index=cfg.image_token_id, video_token_index=cfg.video_token_id,
             image_grid_pinpoints=cfg.extra["image_grid_pinpoints"], vision_feature_layer=-1,
-            vision_feature_select_strategy="full", vision_aspect_ratio="anyres_max_9", projector_hidden_act="gelu",
+            vision_feature_select_strategy="full", vision_aspect_ratio=f"anyres_max_{cfg.extra.get('anyres_max', 9)}",
+            projector_hidden_act="gelu",
             multimodal_projector_bias=True, tie_word_embeddings=t.tie_word_embeddings)
         c._attn_implementation = attn_implementation
         return c

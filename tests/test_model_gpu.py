@@ -262,3 +262,56 @@ def test_native_vision_entry_points_match_python_block_loop(cuda, monkeypatch, f
     rel = ((gn - gp).norm() / gp.norm()).item()
     print(f"\n{family}: native vision vs python block loop: out max diff {(on - op_).abs().max().item():.2e}, grad rel diff {rel:.2e}")
     assert rel < 2e-2
+
+
+def test_llava_onevision_anyres_max_shrink_matches_hf(cuda):
+    """LLaVA-OneVision `anyres_max_N` (HF modeling_llava_onevision.py:328-347): an image whose kept feature map exceeds N crops'
+    worth of tokens has it bilinearly resized before the newline packing. The twin runs with anyres_max_2 so that a 2 x 2-crop
+    image triggers the branch: token count, log-probs and every gradient (tower, projector, image_newline) against HF fp32."""
+    from iad_r1_b200.config import tiny_config
+    from iad_r1_b200.geometry import image_token_count, llava_shrink, patchify_crops, position_ids as family_position_ids
+    from iad_r1_b200.model import VLM
+    from iad_r1_b200.params import ParamStore
+    from oracle import grpo_ref
+    from oracle.hf_oracle import build_hf_model, completion_logps, hf_logits_llava
+    from oracle.make_golden import synthetic_batch_llava
+    cfg = tiny_config("llava_onevision")
+    cfg.extra["anyres_max"] = 2
+    hw = (112, 112)
+    assert llava_shrink(cfg, hw) == (8, 8, 5, 5) and image_token_count(cfg, (5,) + hw) == 16 + 5 * 6
+    G, C = 2, 12
+    ids, P, crops, grid = synthetic_batch_llava(cfg, G, C, image_hw=hw, seed=3)
+    px = patchify_crops(crops, cfg.vision.patch_size)
+    pos, _ = family_position_ids(ids, [grid] * G, cfg)
+    ids_t, pos_t = torch.from_numpy(ids), torch.from_numpy(pos)
+    mask = grpo_ref.completion_mask_ref(ids_t[:, P:], cfg.eos_token_id)
+    attn_mask = torch.cat([torch.ones(G, P, dtype=torch.int64), mask.long()], 1)
+    hf = build_hf_model(cfg, seed=5, dtype=torch.float32)
+    sizes = torch.tensor([[hw[0], hw[1]]] * G)
+    tail = hf_logits_llava(hf, ids_t, crops[None].repeat(G, 1, 1, 1, 1), sizes, pos_t[0], attn_mask, logits_to_keep=C + 1)
+    logp_ref = completion_logps(tail, ids_t, C)
+    gen = torch.Generator().manual_seed(1)
+    dlogp = torch.randn(G, C, generator=gen) * mask
+    (logp_ref * dlogp).sum().backward()
+    ref_grads = {k: p_.grad.detach().clone() for k, p_ in hf.named_parameters() if p_.grad is not None}
+    ps = ParamStore(cfg, cuda, with_grads=True)
+    ps.load_hf_state_dict({k: v.detach().to(torch.bfloat16) for k, v in hf.state_dict().items()})
+    vlm = VLM(cfg, ps)
+    batch = vlm.prepare_group(ids[0, :P], ids_t[:, P:], px.to(torch.bfloat16), [grid])
+    logp, ctx = vlm.logprobs_forward(batch, batch["sel_index"], batch["labels"])
+    logp = logp.view(G, C).cpu()
+    err = (logp - logp_ref.detach()).abs()[mask.bool()].max().item()
+    vlm.logprobs_backward(dlogp.reshape(-1).to(cuda), ctx)
+    torch.cuda.synchronize()
+    ours = {ps.canonical_name(k): v for k, v in ps.hf_named_tensors("g")}
+    worst = (0.0, None)
+    for name, gref in ref_grads.items():
+        name = ps.canonical_name(name)
+        if name.endswith("lm_head.weight") or (name.endswith("k_proj.bias") and "vision_tower" in name):
+            continue
+        g = ours[name].float().cpu().reshape(gref.shape)
+        rel = ((g - gref.float()).norm() / (gref.float().norm() + 1e-12)).item()
+        worst = max(worst, (rel, name))
+        assert rel <= 0.03, f"{name}: rel err {rel:.4f}"
+    print(f"\nanyres_max shrink: logp max err vs HF fp32 {err:.5f}, worst gradient rel err {worst[0]:.4f} at {worst[1]}")
+    assert err <= 0.01
