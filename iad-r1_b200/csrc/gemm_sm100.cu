@@ -405,7 +405,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       };
       auto load_b = [&](const TileInfo& ti, int kb, int stg, int zlo_b, int zhi) {
         uint8_t* sb = smem + (size_t)stg * stage_bytes + a_bytes;
-        if (!g.b_mn) {
+        if (g.epi == EPI_SWIGLU_T) {
+          // ONE box {64 k, 128 rows, 2 halves} of the rank-3 view [gate | up][I][K]: accumulator columns 0-127 = gate features
+          // [n0 / 2, + 128), columns 128-255 = the up features of the same range
+          tma_load_4d(sb, &tmB, &full_bar[stg], kb * BK, ti.n0 >> 1, 0, 0);
+        } else if (!g.b_mn) {
           tma_load_4d(sb, &tmB, &full_bar[stg], kb * BK, ti.n0, zlo_b, zhi);
         } else if (g.b_chunked) {
           tma_load_5d(sb, &tmB, &full_bar[stg], 0, kb * BK, ti.n0 >> 6, zlo_b, zhi);
@@ -555,6 +559,45 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           }
           named_bar_sync(1, 128);
         }
+        if (++as == 2) { as = 0; aph ^= 1; }
+        continue;
+      }
+      if (g.epi == EPI_SWIGLU_T) {
+        // thread = token row m: gate columns [c, c + 32) and up columns [128 + c, ...) of the accumulator -> act[m][f0 + c ..]
+        const int f0 = ti.n0 >> 1, half_i = g.N >> 1;
+        __nv_bfloat16* arow = reinterpret_cast<__nv_bfloat16*>(g.C) + (long long)m * g.ldc + f0;
+        __nv_bfloat16* grow = g.gu_out ? g.gu_out + (long long)m * g.gu_ld + f0 : nullptr;
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t gv[32], uv[32];
+          tmem_ld_32x32b_x32(taddr + c0, gv);
+          tmem_ld_32x32b_x32(taddr + 128 + c0, uv);
+          tmem_ld_wait();
+          if (m < g.M) {
+            uint4 og[4], ou[4], oa[4];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const __nv_bfloat162 gb = __floats2bfloat162_rn(have_acc ? __uint_as_float(gv[j]) : 0.f, have_acc ? __uint_as_float(gv[j + 1]) : 0.f);
+              const __nv_bfloat162 ub = __floats2bfloat162_rn(have_acc ? __uint_as_float(uv[j]) : 0.f, have_acc ? __uint_as_float(uv[j + 1]) : 0.f);
+              const float2 gf = __bfloat1622float2(gb), uf = __bfloat1622float2(ub);
+              const float s0 = __bfloat162float(__float2bfloat16(gf.x / (1.f + __expf(-gf.x))));
+              const float s1 = __bfloat162float(__float2bfloat16(gf.y / (1.f + __expf(-gf.y))));
+              const __nv_bfloat162 ab = __floats2bfloat162_rn(s0 * uf.x, s1 * uf.y);
+              reinterpret_cast<__nv_bfloat162*>(og)[j >> 1] = gb;
+              reinterpret_cast<__nv_bfloat162*>(ou)[j >> 1] = ub;
+              reinterpret_cast<__nv_bfloat162*>(oa)[j >> 1] = ab;
+            }
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              reinterpret_cast<uint4*>(arow + c0)[q4] = oa[q4];
+              if (grow) {
+                reinterpret_cast<uint4*>(grow + c0)[q4] = og[q4];
+                reinterpret_cast<uint4*>(grow + half_i + c0)[q4] = ou[q4];
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[as]);
         if (++as == 2) { as = 0; aph ^= 1; }
         continue;
       }
@@ -753,6 +796,8 @@ static int make_map_chunked(CUtensorMap* out, const void* ptr, long long mn, lon
   return 0;
 }
 
+int make_tensor_map_pair(CUtensorMap* out, const void* ptr, long long cols, long long rows, long long ld, int box_cols, int box_rows);
+
 static int g_num_sms = 0;
 static int num_sms() {
   if (g_num_sms == 0) {
@@ -909,6 +954,15 @@ int launch_gemm(const iadr1_gemm_t& d, cudaStream_t stream) {
         (d.M % 128) || d.up_row_off * 2 != d.M || (d.ldc % 2))
       return set_error("gemm: swiglu epilogue needs K-major operands, bf16 C, M = 2 * up_row_off, M %% 128 == 0");
   }
+  if (g.epi == EPI_SWIGLU_T) {
+    // d.N = I features; B = fused gate|up weight [2I][K]; C = act [M][I]; d.gu_out (optional) [M][2I]
+    if (g.a_mn || g.b_mn || g.batch != 1 || g.split_k != 1 || g.atomic || g.c_f32 || g.trans_c || d.stream_k || g.kmode || g.skip_mode ||
+        (d.N % 128) || (d.ldc % 8) || (d.gu_out && (d.gu_ld % 8)) || d.bias || d.residual)
+      return set_error("gemm: training swiglu epilogue needs K-major operands, bf16 row-major C, I %% 128 == 0, no bias / residual");
+    g.N = 2 * d.N;                // accumulator columns: 128 gate + 128 up per tile
+    g.gu_out = reinterpret_cast<__nv_bfloat16*>(d.gu_out);
+    g.gu_ld = d.gu_ld;
+  }
   g.stream_k = d.stream_k;
   if (g.stream_k && !(g.atomic && g.c_f32 && g.batch == 1 && g.kmode == 0 && g.skip_mode == 0 && g.split_k == 1 &&
                       g.epi == EPI_STORE))
@@ -917,6 +971,7 @@ int launch_gemm(const iadr1_gemm_t& d, cudaStream_t stream) {
   if (g.atomic && !g.c_f32) return set_error("gemm: atomic output must be f32");
   if (g.batch % g.batch_lo) return set_error("gemm: batch must be a multiple of batch_lo");
   g.block_n = d.block_n > 0 ? d.block_n : pick_block_n(d.N, d.b_mn);
+  if (g.epi == EPI_SWIGLU_T) g.block_n = 256;
   if (g.block_n % 16 || g.block_n > 256 || g.block_n < 16) return set_error("gemm: bad block_n %d", g.block_n);
   if (g.b_mn && (g.block_n % 64)) return set_error("gemm: MN-major B needs block_n %% 64 == 0");
   if (g.epi == EPI_LSE && d.lse_tiles_n != (d.N + g.block_n - 1) / g.block_n)
@@ -982,7 +1037,9 @@ int launch_gemm(const iadr1_gemm_t& d, cudaStream_t stream) {
     rc = make_map(&tmA, d.A, d.M, d.K, g.batch_lo, nb_hi, d.lda, d.a_bs_lo ? d.a_bs_lo : d.lda,
                   d.a_bs_hi ? d.a_bs_hi : d.lda, 64, BK);
   if (rc) return rc;
-  if (!g.b_mn)
+  if (g.epi == EPI_SWIGLU_T)
+    rc = make_tensor_map_pair(&tmB, d.B, d.K, d.N, d.ldb, BK, 128);
+  else if (!g.b_mn)
     rc = make_map(&tmB, d.B, d.K, d.N, nb_lo_b, nb_hi, d.ldb, d.b_bs_lo ? d.b_bs_lo : d.ldb,
                   d.b_bs_hi ? d.b_bs_hi : d.ldb, BK, g.block_n);
   else if (g.b_chunked)

@@ -10,6 +10,8 @@ enum GemmEpilogue : int {
   EPI_LSE = 1,       // per-row partial (max, sum exp) over this tile's columns + target-logit pick  (fused lm_head)
   EPI_SWIGLU = 3,    // A = [gate rows; up rows] (M = 2I): C^T[n][f] = bf16(silu(gate_f . b_n)) * (up_f . b_n), bf16 (decode MLP)
   EPI_DLOGITS = 2,   // C = (exp(alpha*acc - lse[m]) - [n == label[m]]) * gscale[m]  as bf16         (lm_head bwd)
+  EPI_SWIGLU_T = 4,  // training MLP: B = [gate rows; up rows] (N = 2I accumulator columns per 2 x 128-feature tile):
+                     // C[m][f] = bf16(silu(bf16(x_m . gate_f))) * bf16(x_m . up_f), optionally gate | up kept for the backward
 };
 
 struct GemmArgs {
@@ -48,6 +50,8 @@ struct GemmArgs {
   float* tgt_logit;      // [M]
   const float* lse;      // [M]
   const float* gscale;   // [M]
+  __nv_bfloat16* gu_out; // EPI_SWIGLU_T: bf16 [M][2I] gate | up pre-activations kept for the backward (or nullptr)
+  long long gu_ld;
 };
 
 }  // namespace iadr1

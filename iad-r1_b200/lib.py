@@ -37,6 +37,7 @@ class GemmDesc(C.Structure):
         ("lse", C.c_void_p), ("gscale", C.c_void_p),
         ("block_n", C.c_int), ("stages", C.c_int), ("max_ctas", C.c_int), ("a_static", C.c_int),
         ("stream_k", C.c_int), ("up_row_off", C.c_int), ("raster", C.c_int), ("no_chunked_maps", C.c_int), ("no_bulk_red", C.c_int), ("co_resident", C.c_int),
+        ("gu_out", C.c_void_p), ("gu_ld", C.c_longlong),
     ]
 
 
@@ -194,6 +195,26 @@ def gemm_swiglu(w_gate_up: torch.Tensor, x: torch.Tensor, out: torch.Tensor, *, 
     d.block_n, d.a_static, d.co_resident = block_n, int(a_static), int(co_resident)
     check(lib().iadr1_gemm_bf16(C.byref(d), stream_ptr()), "iadr1_gemm_bf16(swiglu)")
     return out
+
+
+def gemm_swiglu_train(x: torch.Tensor, w_gate_up: torch.Tensor, act: torch.Tensor, gu: torch.Tensor | None = None) -> torch.Tensor:
+    """Training MLP front half in one launch (epi 4): act[M, I] = bf16(silu(bf16(x @ Wg^T))) * bf16(x @ Wu^T) with the fused weight
+    w_gate_up = [Wg; Wu] ([2I, K]); `gu` [M, 2I] optionally receives the gate | up pre-activations the backward needs."""
+    M, K = x.shape
+    I2, K2 = w_gate_up.shape
+    if K != K2 or tuple(act.shape) != (M, I2 // 2) or act.dtype != torch.bfloat16:
+        raise ValueError("gemm_swiglu_train: shape/dtype mismatch")
+    d = GemmDesc()
+    d.M, d.N, d.K = M, I2 // 2, K
+    d.batch = d.batch_lo = d.b_lo_div = 1
+    d.A, d.lda, d.a_mn = _mat(x, "x")
+    d.B, d.ldb, d.b_mn = _mat(w_gate_up, "w_gate_up")
+    d.C, d.ldc = act.data_ptr(), act.stride(0)
+    d.split_k, d.alpha, d.epi = 1, 1.0, 4
+    if gu is not None:
+        d.gu_out, d.gu_ld = gu.data_ptr(), gu.stride(0)
+    check(lib().iadr1_gemm_bf16(C.byref(d), stream_ptr()), "iadr1_gemm_bf16(swiglu, training)")
+    return act
 
 
 def gemm_batched(a, b, out, *, M, N, K, batch, batch_lo=0, b_lo_div=1, lda, a_bs_lo=0, a_bs_hi=0, a_mn=0, ldb,

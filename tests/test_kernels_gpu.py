@@ -618,3 +618,22 @@ def test_image_preprocess_matches_hf_processor(ops, hw, max_pixels):
         assert err.max().item() <= 2 ** -7 * want.abs().max().item()
     else:
         assert err.max().item() <= 0.035 and err.mean().item() <= 0.004, (err.max().item(), err.mean().item())
+
+
+@pytest.mark.parametrize("M,I,K,keep", [(300, 256, 192, True), (1000, 1408, 256, False), (129, 128, 64, True)])
+def test_gemm_swiglu_training_epilogue(ops, M, I, K, keep):
+    """Training MLP front half in one launch (epi 4): the gate_up product with the SwiGLU epilogue against the two-kernel form
+    (GEMM -> act_mul): bit-identical act and gate | up pre-activations (same bf16 rounding points)."""
+    from iad_r1_b200 import lib as L
+    torch.manual_seed(M + I)
+    x = rnd(M, K)
+    w = rnd(2 * I, K, scale=K ** -0.5)
+    gu_ref = ops.linear_fwd(x, w)
+    act_ref = ops.act_mul_fwd(gu_ref, I, ops.ACT_SILU, gated=True)
+    act = torch.full((M, I), float("nan"), dtype=bf16, device="cuda")
+    gu = torch.full((M, 2 * I), float("nan"), dtype=bf16, device="cuda") if keep else None
+    L.gemm_swiglu_train(x, w, act, gu)
+    torch.cuda.synchronize()
+    assert torch.equal(act, act_ref)
+    if keep:
+        assert torch.equal(gu, gu_ref)
