@@ -371,7 +371,7 @@ class SiglipGeometry:
 
 def siglip_geometry(cfg: VLMConfig, grid, device) -> SiglipGeometry:
     key = ("siglip", cfg.family, cfg.vision.kind, cfg.vision.image_size, cfg.vision.patch_size, tuple(map(tuple, grid)), str(device),
-           str(cfg.extra.get("image_grid_pinpoints")))
+           str(cfg.extra.get("image_grid_pinpoints")), cfg.extra.get("anyres_max"), cfg.vision.feature_layer)
     g = _GEOM_CACHE.get(key)
     if g is None:
         if len(_GEOM_CACHE) > 64:
