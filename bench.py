@@ -50,6 +50,10 @@ def parse():
     ap.add_argument("--image-size", type=int, default=448)
     ap.add_argument("--num-generations", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference only. cpu (default, the contract's reference arm): bounded depth-reduced sample on "
+                         "the host cores. cuda: BASELINE.md §4.4's optional arm - the same HF modules + HF generate + restated "
+                         "loss, FULL size, bf16, on one B200 (context for the >= 10x target; not the contract's reference line)")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
@@ -147,6 +151,34 @@ def cpu_reference_sample(args, cfg_full, steps=1, warmup=0):
     return gps, info, t_s
 
 
+def hf_on_gpu(args, cfg):
+    """full-size HF model + HF generate + restated compute_loss + autograd + torch AdamW on cuda:0, bf16
+    weights, sdpa attention - the reference's arithmetic stack (minus vLLM / DeepSpeed, absent here) on the same GPU."""
+    import torch
+    from iad_r1_b200.synthetic import SyntheticProcessor, synthetic_dataset
+    from oracle.cpu_reference import CPUReference
+    G, C = args.num_generations, args.completion_len
+    proc = SyntheticProcessor(cfg, max_pixels=480000)
+    ex = synthetic_dataset(1, args.image_size)[0]
+    enc = proc(text=[proc.apply_chat_template(ex["prompt"])], images=ex["image"])
+    ids = enc["input_ids"][0]
+    px = enc["pixel_values"]
+    grid = (enc["image_sizes"] if cfg.family == "llava_onevision" else enc["image_grid_thw"]).tolist()
+    ref = CPUReference(cfg, seed=0, device="cuda:0", dtype=torch.bfloat16, attn_implementation="sdpa")
+    times = []
+    W, K = min(args.warmup, 1), max(1, min(args.steps, 3))
+    for i in range(W + K):
+        dt, _ = ref.group_step(ids, px, grid, G, C, lambda comp: torch.randn(comp.shape[0]).tolist(), seed=i)
+        if i >= W:
+            times.append(dt)
+    t_s = sum(times) / len(times)
+    info = {"value": 1.0 / t_s, "unit": "groups/s", "cores": 0, "kind": "port",
+            "sample": (f"HF-on-B200 (BASELINE.md §4.4): FULL-size {args.model}, bf16, sdpa, one group per step (G={G}, "
+                       f"P={ids.shape[0]}, C={C}): HF generate + policy / reference log-prob forwards + autograd backward + "
+                       f"torch AdamW, {t_s:.2f} s per group over {K} groups, peak {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB")}
+    return 1.0 / t_s, info, t_s
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -154,6 +186,16 @@ def run_reference(args):
     from iad_r1_b200.config import PRESETS
     cfg = PRESETS[args.model]()
     t0 = time.time()
+    if args.ref_device == "cuda":
+        gps, info, t_s = hf_on_gpu(args, cfg)
+        line = {"metric": f"GRPO groups/sec (G={args.num_generations})", "value": gps, "unit": "groups/s", "impl": "reference",
+                "ref_device": "cuda", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1000.0 * args.ga / gps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic", "config": workload_config(args, cfg, 1), "cpu_baseline": info,
+                "e2e": {"value": gps, "unit": "groups/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "wall_s": time.time() - t0}
+        print(json.dumps(line), flush=True)
+        return
     gps, info, t_s = cpu_reference_sample(args, cfg, steps=max(1, args.steps), warmup=min(args.warmup, 1))
     line = {"metric": f"GRPO groups/sec (G={args.num_generations})", "value": gps, "unit": "groups/s", "impl": "reference", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * args.ga / gps, "higher_is_better": True,

@@ -44,11 +44,15 @@ def reference_form_flops(cfg, G, P, C, n_patches):
 
 
 class CPUReference:
-    def __init__(self, cfg, seed=0, threads=None):
+    """`device="cuda"` + `dtype=torch.bfloat16` runs the SAME reference-form step with the HF modules on the GPU
+    (BASELINE.md §4.4 "optional GPU reference": context for the >= 10x target; bench.py --impl reference --ref-device cuda)."""
+
+    def __init__(self, cfg, seed=0, threads=None, device="cpu", dtype=torch.float32, attn_implementation="eager"):
         if threads:
             torch.set_num_threads(threads)
         self.cfg = cfg
-        self.policy = build_hf_model(cfg, seed=seed, dtype=torch.float32)
+        self.device = torch.device(device)
+        self.policy = build_hf_model(cfg, seed=seed, dtype=dtype, attn_implementation=attn_implementation).to(self.device)
         self.policy.train(False)
         self.ref = copy.deepcopy(self.policy).requires_grad_(False)
         self.opt = torch.optim.AdamW(self.policy.parameters(), lr=1e-6, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0)
@@ -56,14 +60,18 @@ class CPUReference:
     def group_step(self, prompt_ids, pixel_values, grid_thw, G, C, reward_fn, beta=0.04, seed=0):
         """prompt_ids [P] LongTensor; Qwen families: pixel_values [Np, patch_dim] float + grid_thw [[t,h,w]];
         LLaVA-OneVision: pixel_values [1, n_crops, 3, S, S] + grid_thw = image_sizes [[H, W]]. Returns (seconds, loss)."""
-        cfg = self.cfg
+        cfg, dev = self.cfg, self.device
+        if dev.type == "cuda":
+            torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
         torch.manual_seed(seed)
+        prompt_ids = prompt_ids.to(dev)
+        pixel_values = pixel_values.to(dev, next(self.policy.parameters()).dtype)
         ids = prompt_ids[None, :].repeat(G, 1)                                   # sc_grpo_trainer.py:624-628
         if cfg.family == "llava_onevision":
-            mm = dict(pixel_values=pixel_values.repeat(G, 1, 1, 1, 1), image_sizes=torch.tensor(grid_thw * G))
+            mm = dict(pixel_values=pixel_values.repeat(G, 1, 1, 1, 1), image_sizes=torch.tensor(grid_thw * G, device=dev))
         else:
-            mm = dict(pixel_values=pixel_values.repeat(G, 1), image_grid_thw=torch.tensor(grid_thw * G))
+            mm = dict(pixel_values=pixel_values.repeat(G, 1), image_grid_thw=torch.tensor(grid_thw * G, device=dev))
         P = ids.shape[1]
         with torch.no_grad():                                                      # stands in for vLLM, :343-358, :667
             out = self.policy.generate(input_ids=ids, attention_mask=torch.ones_like(ids), do_sample=True, temperature=0.9,
@@ -71,16 +79,17 @@ class CPUReference:
                                        pad_token_id=cfg.pad_token_id, eos_token_id=cfg.eos_token_id, **mm)
         comp = out[:, P:]
         mask = grpo_ref.completion_mask_ref(comp, cfg.eos_token_id)
-        attn = torch.cat([torch.ones(G, P, dtype=torch.long), mask.long()], 1)
+        attn = torch.cat([torch.ones(G, P, dtype=torch.long, device=dev), mask.long()], 1)
         kw = dict(input_ids=out, attention_mask=attn, use_cache=False, **mm)
         logps = per_token_logps(self.policy(**kw).logits, out)[:, P - 1:]          # :733-735
         with torch.no_grad():
             ref_logps = per_token_logps(self.ref(**kw).logits, out)[:, P - 1:]     # :737-743
-        rewards = torch.tensor(reward_fn(comp), dtype=torch.float32).view(G, -1)
+        rewards = torch.tensor(reward_fn(comp), dtype=torch.float32, device=dev).view(G, -1)
         adv, _, _ = grpo_ref.advantages_ref(rewards, G)
         loss, _ = grpo_ref.sc_grpo_loss_ref(logps, ref_logps, adv, mask, beta)
         loss.backward()
         torch.nn.utils.clip_grad_norm_(self.policy.parameters(), 1.0)
         self.opt.step()
         self.opt.zero_grad(set_to_none=True)
-        return time.perf_counter() - t0, float(loss.detach())
+        loss_v = float(loss.detach())                                            # device sync on the GPU arm
+        return time.perf_counter() - t0, loss_v

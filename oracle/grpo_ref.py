@@ -20,9 +20,9 @@ import torch.nn.functional as F
 
 def completion_mask_ref(completion_ids: torch.Tensor, eos_token_id: int) -> torch.Tensor:
     is_eos = completion_ids == eos_token_id
-    eos_idx = torch.full((is_eos.size(0),), is_eos.size(1), dtype=torch.long)
+    eos_idx = torch.full((is_eos.size(0),), is_eos.size(1), dtype=torch.long, device=completion_ids.device)
     eos_idx[is_eos.any(dim=1)] = is_eos.int().argmax(dim=1)[is_eos.any(dim=1)]
-    sequence_indices = torch.arange(is_eos.size(1)).expand(is_eos.size(0), -1)
+    sequence_indices = torch.arange(is_eos.size(1), device=completion_ids.device).expand(is_eos.size(0), -1)
     return (sequence_indices <= eos_idx.unsqueeze(1)).int()
 
 
