@@ -972,6 +972,21 @@ int launch_gemm(const iadr1_gemm_t& d, cudaStream_t stream) {
   if (g.batch % g.batch_lo) return set_error("gemm: batch must be a multiple of batch_lo");
   g.block_n = d.block_n > 0 ? d.block_n : pick_block_n(d.N, d.b_mn);
   if (g.epi == EPI_SWIGLU_T) g.block_n = 256;
+  if (d.block_n <= 0 && g.b_mn && g.epi == EPI_STORE && g.batch == 1 && g.split_k == 1 && !d.stream_k && g.kmode == 0 &&
+      !g.skip_mode && d.N > 256) {
+    // Wave quantisation of the gradient products: the persistent CTAs take tiles round-robin, so a product costs
+    // ceil(tiles / SMs) tile times and a tile time scales with block_n. 2560 x 2048 (qkv weight gradient) is 160 tiles
+    // of 256 columns = two waves for 1.08 waves of work; 220 tiles of 192 columns are two SHORTER waves (-25 %); the
+    // vision tower's 1280 x 1280 is 50 tiles of 256 on 148 SMs, 100 tiles of 128 use twice the machine.
+    const long long tm = (d.M + BM - 1) / BM, sms = num_sms();
+    auto cost = [&](int bn) { return ((tm * ((d.N + bn - 1) / bn) + sms - 1) / sms) * bn; };
+    long long best_cost = cost(g.block_n);
+    for (int bn : {192, 128})
+      if (cost(bn) * 10 < best_cost * 9) {
+        g.block_n = bn;
+        best_cost = cost(bn);
+      }
+  }
   if (g.block_n % 16 || g.block_n > 256 || g.block_n < 16) return set_error("gemm: bad block_n %d", g.block_n);
   if (g.b_mn && (g.block_n % 64)) return set_error("gemm: MN-major B needs block_n %% 64 == 0");
   if (g.epi == EPI_LSE && d.lse_tiles_n != (d.N + g.block_n - 1) / g.block_n)

@@ -161,7 +161,9 @@ class TrainerCore:
         with self._phase("optimizer"):
             scale = 1.0 / self.world
             self._sumsq.zero_()
-            L.check(lib.iadr1_sumsq_f32(ps.grad_flat.data_ptr(), ps.numel, self._sumsq.data_ptr(), s), "sumsq")
+            for lo, hi, _ in self._trainable_ranges():          # frozen ranges carry no gradient and are never zeroed
+                if hi > lo:
+                    L.check(lib.iadr1_sumsq_f32(ps.grad_flat.data_ptr() + 4 * lo, hi - lo, self._sumsq.data_ptr(), s), "sumsq")
             self._opt_step += 1
             lr = self._lr_at(self.state.global_step)
             self._last_lr = lr

@@ -67,6 +67,23 @@ def test_gemm_epilogues(ops):
           x.float() @ w.float().t() + bm.float(), 1e-5, "decode swap-AB")
 
 
+@pytest.mark.parametrize("N_out,K_in,T", [(2560, 2048, 1111), (1280, 1280, 1024), (3840, 1280, 520), (2048, 11008, 300)])
+def test_gemm_weight_gradient_wave_quantised_tiles(ops, N_out, K_in, T):
+    """dW[N, K] += dy[T, N]^T x[T, K], fp32 accumulate: the shapes whose 256-column tiling leaves a ragged last wave take 192- or
+    128-column tiles (gemm_sm100.cu: wave quantisation); values must not depend on the tile width."""
+    from iad_r1_b200 import lib as L
+    torch.manual_seed(N_out + T)
+    dy, x = rnd(T, N_out), rnd(T, K_in)
+    base = torch.randn(N_out, K_in, device="cuda")
+    want = base + dy.float().t() @ x.float()
+    got = base.clone()
+    L.gemm(dy.t(), x.t(), out=got, accumulate=True, out_dtype=f32)
+    close(got, want, 2 ** -9, "wgrad")
+    ref = base.clone()
+    L.gemm(dy.t(), x.t(), out=ref, accumulate=True, out_dtype=f32, block_n=256)
+    assert torch.equal(got, ref), "tile width changed the accumulated values"
+
+
 @pytest.mark.parametrize("F,K,R", [(22016, 2048, 64), (2560, 2048, 64), (2048, 11008, 16), (1000, 200, 8), (128, 64, 24)])
 def test_gemm_stream_k(ops, F, K, R):
     """Stream-K schedule of the decode products (k-block units spread evenly over the SMs, fp32 atomics, bias added once
