@@ -975,16 +975,19 @@ int launch_gemm(const iadr1_gemm_t& d, cudaStream_t stream) {
   if (d.block_n <= 0 && g.b_mn && g.epi == EPI_STORE && g.batch == 1 && g.split_k == 1 && !d.stream_k && g.kmode == 0 &&
       !g.skip_mode && d.N > 256) {
     // Wave quantisation of the gradient products: the persistent CTAs take tiles round-robin, so a product costs
-    // ceil(tiles / SMs) tile times and a tile time scales with block_n. 2560 x 2048 (qkv weight gradient) is 160 tiles
-    // of 256 columns = two waves for 1.08 waves of work; 220 tiles of 192 columns are two SHORTER waves (-25 %); the
-    // vision tower's 1280 x 1280 is 50 tiles of 256 on 148 SMs, 100 tiles of 128 use twice the machine.
+    // ceil(tiles / SMs) tile times. Narrower tiles are NOT proportionally cheaper (A is re-staged per tile and the L2 -> SM
+    // path is already near its limit at 256 columns): measured tile times relative to 256 columns are 0.92 (192) and 0.85
+    // (128) (tools/gemm_tile_probe.py). 2560 x 2048 (qkv weight gradient): 160 tiles of 256 = two waves, 220 tiles of 192 =
+    // two cheaper waves (1.09x measured); the vision tower's 1280 x 1280: 50 tiles on 148 SMs -> 100 tiles of 128 (1.15x);
+    // 4608 x 3584 (7B qkv) stays at 256 (7 waves of 128 would lose 30 %).
     const long long tm = (d.M + BM - 1) / BM, sms = num_sms();
-    auto cost = [&](int bn) { return ((tm * ((d.N + bn - 1) / bn) + sms - 1) / sms) * bn; };
-    long long best_cost = cost(g.block_n);
-    for (int bn : {192, 128})
-      if (cost(bn) * 10 < best_cost * 9) {
-        g.block_n = bn;
-        best_cost = cost(bn);
+    auto cost = [&](int bn, int rel) { return ((tm * ((d.N + bn - 1) / bn) + sms - 1) / sms) * rel; };
+    long long best_cost = cost(g.block_n, 100);
+    const int cand[2][2] = {{192, 92}, {128, 85}};
+    for (auto& c : cand)
+      if (cost(c[0], c[1]) * 100 < best_cost * 95) {
+        g.block_n = c[0];
+        best_cost = cost(c[0], c[1]);
       }
   }
   if (g.block_n % 16 || g.block_n > 256 || g.block_n < 16) return set_error("gemm: bad block_n %d", g.block_n);

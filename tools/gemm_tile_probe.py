@@ -1,0 +1,52 @@
+"""Weight-gradient products dW[N, K] += dy[T, N]^T x[T, K] (fp32 accumulate, MN-major operands) at the headline shapes: the
+library's wave-quantisation-aware tile width (block_n = 0) against fixed 256-column tiles, same process, same clocks.
+
+    python tools/gemm_tile_probe.py      -> one line per shape
+"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    from iad_r1_b200 import lib as L
+    dev = torch.device("cuda:0")
+    T = 8786
+    shapes = [("qkv (3B)", 2560, 2048, T), ("o (3B)", 2048, 2048, T), ("down (3B)", 2048, 11008, T), ("gate_up (3B)", 22016, 2048, T),
+              ("vision qkv", 3840, 1280, 16384), ("vision proj", 1280, 1280, 16384), ("vision up", 6848, 1280, 16384),
+              ("qkv (7B)", 4608, 3584, T), ("o (7B)", 3584, 3584, T)]
+    for name, N, K, rows in shapes:
+        dy = [torch.randn(rows, N, device=dev).bfloat16() for _ in range(3)]
+        x = [torch.randn(rows, K, device=dev).bfloat16() for _ in range(3)]
+        out = torch.zeros(N, K, device=dev)
+        res = {}
+        for bn in (256, 0):
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for i in range(3):
+                    L.gemm(dy[i].t(), x[i].t(), out=out, accumulate=True, out_dtype=torch.float32, block_n=bn)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    for i in range(3):
+                        L.gemm(dy[i].t(), x[i].t(), out=out, accumulate=True, out_dtype=torch.float32, block_n=bn)
+                g.replay()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(10):
+                    g.replay()
+                e1.record()
+                torch.cuda.synchronize()
+            res[bn] = 1000 * e0.elapsed_time(e1) / 30
+        fl = 2.0 * N * K * rows
+        print(f"{name:14s} [{N} x {K}] K={rows}: block_n 256 {res[256]:7.1f} us ({fl / res[256] / 1e6:6.0f} TFLOP/s)   auto {res[0]:7.1f} us "
+              f"({fl / res[0] / 1e6:6.0f} TFLOP/s)   {res[256] / res[0]:.2f}x", flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--rows", type=int, default=8786)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--only", default="")
+    ap.add_argument("--eager", action="store_true", help="plain launches, no timing (for an ncu capture)")
     a = ap.parse_args()
     from iad_r1_b200 import ops
     dev = torch.device("cuda:0")
@@ -39,21 +40,37 @@ def main():
     results = []
 
     def timed(name, nbytes, fn):
+        """One CUDA graph of RING launches (one per ring buffer) replayed `iters` times: the Python / ctypes issue time of a
+        launch (~20 us) would otherwise hide every kernel shorter than that."""
         if a.only and a.only not in name:
             return
-        for i in range(3):
-            fn(i % RING)
-        torch.cuda.synchronize()
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.iters + 1)]
-        ev[0].record()
-        for i in range(a.iters):
-            fn(i % RING)
-            ev[i + 1].record()
-        torch.cuda.synchronize()
-        us = sorted(1000 * ev[i].elapsed_time(ev[i + 1]) for i in range(a.iters))[a.iters // 2]
+        if a.eager:                                          # ncu capture: plain launches
+            for i in range(a.iters):
+                fn(i % RING)
+            torch.cuda.synchronize()
+            return
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for i in range(RING):
+                fn(i)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                for i in range(RING):
+                    fn(i)
+            g.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(a.iters):
+                g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+        us = 1000 * e0.elapsed_time(e1) / (a.iters * RING)
         gbs = nbytes / us / 1e3
         results.append({"kernel": name, "us": round(us, 1), "MB": round(nbytes / 1e6, 1), "GB/s": round(gbs), "frac": round(gbs / peak, 3)})
-        print(f"{name:34s} {us:8.1f} us  {nbytes / 1e6:8.1f} MB  {gbs:7.0f} GB/s  {gbs / peak:5.2f} of HBM", flush=True)
+        print(f"{name:38s} {us:8.1f} us  {nbytes / 1e6:8.1f} MB  {gbs:7.0f} GB/s  {gbs / peak:5.2f} of HBM", flush=True)
 
     x, dy, dx = ring(T, H), ring(T, H), ring(T, H)
     w = torch.ones(H, device=dev, dtype=bf16)
