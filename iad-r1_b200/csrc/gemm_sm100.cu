@@ -972,8 +972,9 @@ int launch_gemm(const iadr1_gemm_t& d, cudaStream_t stream) {
   if (g.batch % g.batch_lo) return set_error("gemm: batch must be a multiple of batch_lo");
   g.block_n = d.block_n > 0 ? d.block_n : pick_block_n(d.N, d.b_mn);
   if (g.epi == EPI_SWIGLU_T) g.block_n = 256;
-  if (d.block_n <= 0 && g.b_mn && g.epi == EPI_STORE && g.batch == 1 && g.split_k == 1 && !d.stream_k && g.kmode == 0 &&
-      !g.skip_mode && d.N > 256) {
+  static const bool wave_tiles = [] { const char* e = getenv("IADR1_GEMM_WAVE_TILES"); return !(e && e[0] == '0'); }();
+  if (wave_tiles && d.block_n <= 0 && g.b_mn && g.epi == EPI_STORE && g.batch == 1 && g.split_k == 1 && !d.stream_k &&
+      g.kmode == 0 && !g.skip_mode && d.N > 256) {
     // Wave quantisation of the gradient products: the persistent CTAs take tiles round-robin, so a product costs
     // ceil(tiles / SMs) tile times. Narrower tiles are NOT proportionally cheaper (A is re-staged per tile and the L2 -> SM
     // path is already near its limit at 256 columns): measured tile times relative to 256 columns are 0.92 (192) and 0.85
