@@ -601,6 +601,64 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         if (++as == 2) { as = 0; aph ^= 1; }
         continue;
       }
+      if (kMinCtas == 1 && g.epi == EPI_SWIGLU_BWD) {   // training-only epilogue: not compiled into the 128-register decode variant
+        // thread = token row m; accumulator column c = feature n0 + c of dact (block_n = 256: eight 32-column chunks). gate / up
+        // of the same features are read from gu two chunks ahead of the one being processed and overwritten with dgate / dup:
+        // the act_mul_bwd row kernel's arithmetic on the same bf16-rounded inputs, without dact reaching HBM. Four warps doing
+        // this math take ~23 us per tile (issue-bound, not latency-bound: lookahead 1 -> 2 changed nothing), so the host uses
+        // this epilogue only where a tile's MMA is longer than that (K >= 3072, model.cu).
+        const int I = g.N;
+        __nv_bfloat16* grow = g.gu_out + (long long)m * g.gu_ld + ti.n0;
+        const bool row_ok = m < g.M;
+        uint4 bg[3][4], bu[3][4];
+        auto fetch = [&](int c0, uint4 (&dg)[4], uint4 (&du)[4]) {
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const bool ok = row_ok && ti.n0 + c0 + q4 * 8 < I;      // I % 8 == 0 (host check): whole 16-byte groups
+            dg[q4] = ok ? reinterpret_cast<const uint4*>(grow + c0)[q4] : make_uint4(0, 0, 0, 0);
+            du[q4] = ok ? reinterpret_cast<const uint4*>(grow + I + c0)[q4] : make_uint4(0, 0, 0, 0);
+          }
+        };
+        fetch(0, bg[0], bu[0]);
+        fetch(32, bg[1], bu[1]);
+#pragma unroll
+        for (int ci = 0; ci < 8; ++ci) {
+          const int c0 = ci * 32;
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr + c0, v);
+          if (ci + 2 < 8) fetch(c0 + 64, bg[(ci + 2) % 3], bu[(ci + 2) % 3]);
+          tmem_ld_wait();
+          const uint4 (&cg)[4] = bg[ci % 3];
+          const uint4 (&cu)[4] = bu[ci % 3];
+          uint4 og[4], ou[4];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float2 dd = __bfloat1622float2(__floats2bfloat162_rn(have_acc ? g.alpha * __uint_as_float(v[j]) : 0.f,
+                                                                       have_acc ? g.alpha * __uint_as_float(v[j + 1]) : 0.f));
+            const float2 gf = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(cg)[j >> 1]);
+            const float2 uf = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(cu)[j >> 1]);
+            const float t0 = 1.f + __expf(-gf.x), t1 = 1.f + __expf(-gf.y);
+            const float s0 = 1.f / t0, s1 = 1.f / t1;
+            const float dg0 = dd.x * uf.x * (s0 * (1.f + gf.x * (1.f - s0)));
+            const float dg1 = dd.y * uf.y * (s1 * (1.f + gf.y * (1.f - s1)));
+            const float du0 = dd.x * (gf.x / t0);
+            const float du1 = dd.y * (gf.y / t1);
+            reinterpret_cast<__nv_bfloat162*>(og)[j >> 1] = __floats2bfloat162_rn(dg0, dg1);
+            reinterpret_cast<__nv_bfloat162*>(ou)[j >> 1] = __floats2bfloat162_rn(du0, du1);
+          }
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            if (row_ok && ti.n0 + c0 + q4 * 8 < I) {
+              reinterpret_cast<uint4*>(grow + c0)[q4] = og[q4];
+              reinterpret_cast<uint4*>(grow + I + c0)[q4] = ou[q4];
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[as]);
+        if (++as == 2) { as = 0; aph ^= 1; }
+        continue;
+      }
       if (g.bulk_red) {
         // Transposed fp32 accumulate-into-C via the TMA unit: the tile is staged as sC[n][128 m] (lanes = consecutive m:
         // conflict-free stores) and every decode row n is added to C^T[n][m0 .. m0 + 128) by ONE bulk reduction.
@@ -963,6 +1021,14 @@ int launch_gemm(const iadr1_gemm_t& d, cudaStream_t stream) {
     g.gu_out = reinterpret_cast<__nv_bfloat16*>(d.gu_out);
     g.gu_ld = d.gu_ld;
   }
+  if (g.epi == EPI_SWIGLU_BWD) {
+    // d.N = I features of dact = dy @ W_down; d.gu_out = gate | up [M][2I] (ld gu_ld), rewritten in place with dgate | dup
+    if (g.batch != 1 || g.split_k != 1 || g.atomic || g.c_f32 || g.trans_c || d.stream_k || g.kmode || g.skip_mode || (d.N % 8) ||
+        !d.gu_out || (d.gu_ld % 8) || (reinterpret_cast<uintptr_t>(d.gu_out) & 15) || d.bias || d.residual || d.co_resident)
+      return set_error("gemm: swiglu backward epilogue needs one plain problem, I %% 8 == 0, a 16-byte aligned gate | up buffer");
+    g.gu_out = reinterpret_cast<__nv_bfloat16*>(d.gu_out);
+    g.gu_ld = d.gu_ld;
+  }
   g.stream_k = d.stream_k;
   if (g.stream_k && !(g.atomic && g.c_f32 && g.batch == 1 && g.kmode == 0 && g.skip_mode == 0 && g.split_k == 1 &&
                       g.epi == EPI_STORE))
@@ -972,6 +1038,7 @@ int launch_gemm(const iadr1_gemm_t& d, cudaStream_t stream) {
   if (g.batch % g.batch_lo) return set_error("gemm: batch must be a multiple of batch_lo");
   g.block_n = d.block_n > 0 ? d.block_n : pick_block_n(d.N, d.b_mn);
   if (g.epi == EPI_SWIGLU_T) g.block_n = 256;
+  if (g.epi == EPI_SWIGLU_BWD) g.block_n = 256;   // the epilogue is unrolled over eight 32-column chunks
   static const bool wave_tiles = [] { const char* e = getenv("IADR1_GEMM_WAVE_TILES"); return !(e && e[0] == '0'); }();
   if (wave_tiles && d.block_n <= 0 && g.b_mn && g.epi == EPI_STORE && g.batch == 1 && g.split_k == 1 && !d.stream_k &&
       g.kmode == 0 && !g.skip_mode && d.N > 256) {

@@ -12,6 +12,8 @@ enum GemmEpilogue : int {
   EPI_DLOGITS = 2,   // C = (exp(alpha*acc - lse[m]) - [n == label[m]]) * gscale[m]  as bf16         (lm_head bwd)
   EPI_SWIGLU_T = 4,  // training MLP: B = [gate rows; up rows] (N = 2I accumulator columns per 2 x 128-feature tile):
                      // C[m][f] = bf16(silu(bf16(x_m . gate_f))) * bf16(x_m . up_f), optionally gate | up kept for the backward
+  EPI_SWIGLU_BWD = 5,  // down-projection input gradient with the SwiGLU backward in the epilogue: d = bf16(acc) (= dact[m][f]),
+                       // gu[m][f] <- bf16(d * up * silu'(gate)), gu[m][I + f] <- bf16(d * silu(gate)) in place (gu = gu_out, N = I)
 };
 
 struct GemmArgs {
@@ -50,7 +52,8 @@ struct GemmArgs {
   float* tgt_logit;      // [M]
   const float* lse;      // [M]
   const float* gscale;   // [M]
-  __nv_bfloat16* gu_out; // EPI_SWIGLU_T: bf16 [M][2I] gate | up pre-activations kept for the backward (or nullptr)
+  __nv_bfloat16* gu_out; // EPI_SWIGLU_T: bf16 [M][2I] gate | up pre-activations kept for the backward (or nullptr);
+                         // EPI_SWIGLU_BWD: the same buffer, read and overwritten with dgate | dup
   long long gu_ld;
 };
 

@@ -82,6 +82,28 @@ static int linear_wgrad(const void* dy, const void* x, float* dW, long long M, i
   return launch_gemm(d, s);
 }
 
+// gu[M, 2I] (gate | up) <- (dgate | dup) for dact = dy[M, H] @ Wdown[H, I]: the down-projection input gradient with the SwiGLU
+// backward in its epilogue (epi 5) - replaces linear_dgrad + iadr1_act_mul_bwd, dact is never written.
+// Measured (tools/gemm_tile_probe.py swiglu_bwd): the four epilogue warps need ~23 us per 128 x 256 tile for the SwiGLU backward
+// arithmetic, the MMA of a tile takes 15 us at K = H = 2048 (3B: fused 498 us vs 458 us for GEMM + row kernel) and 27 us at
+// H = 3584 (7B: 1133 vs 1279 us) - so the fused form is used where the reduction is long enough to hide it.
+// IADR1_SWIGLU_BWD_EPILOGUE: 0 never, 1 (default) H >= 3072, 2 always.
+static bool swiglu_bwd_epilogue_enabled(int H) {
+  static const int mode = [] { const char* e = getenv("IADR1_SWIGLU_BWD_EPILOGUE"); return e && e[0] >= '0' && e[0] <= '2' ? e[0] - '0' : 1; }();
+  return mode == 2 || (mode == 1 && H >= 3072);
+}
+static int linear_dgrad_swiglu_bwd(const void* dy, const void* Wdown, void* gu, long long M, int H, int I, cudaStream_t s) {
+  iadr1_gemm_t d;
+  memset(&d, 0, sizeof(d));
+  d.M = (int)M; d.N = I; d.K = H;
+  d.batch = d.batch_lo = d.b_lo_div = 1;
+  d.A = dy; d.lda = H;
+  d.B = Wdown; d.ldb = I; d.b_mn = 1;
+  d.split_k = 1; d.alpha = 1.f; d.epi = 5;
+  d.gu_out = gu; d.gu_ld = 2LL * I;
+  return launch_gemm(d, s);
+}
+
 __global__ void scale_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n, float scale) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     dst[i] = src[i] * scale;
@@ -302,9 +324,13 @@ int iadr1_decoder_bwd(void* handle, void* dh, const int* src_index, const float*
     if (mode == 2)      // recompute this layer's activations from its saved input (h[i + 1] is rewritten with the same values)
       TRY(layer_fwd(m, i, L.h[i], L.h[i + 1], b, true, N, cos_t, sin_t, plan, nullptr, s));
     // MLP
-    TRY(linear_dgrad(dh, w.down->p, L.dact, N, H, I, s));
     TRY(linear_wgrad(dh, b.act, w.down->g, N, H, I, s));
-    TRY(iadr1_act_mul_bwd(L.dact, b.gu, b.gu, N, I, 2 * I, I, I, 0, s));
+    if (swiglu_bwd_epilogue_enabled(H) && I % 8 == 0) {
+      TRY(linear_dgrad_swiglu_bwd(dh, w.down->p, b.gu, N, H, I, s));
+    } else {
+      TRY(linear_dgrad(dh, w.down->p, L.dact, N, H, I, s));
+      TRY(iadr1_act_mul_bwd(L.dact, b.gu, b.gu, N, I, 2 * I, I, I, 0, s));
+    }
     TRY(linear_dgrad(b.gu, w.gu->p, L.dx, N, 2 * I, H, s));
     TRY(linear_wgrad(b.gu, b.xn2, w.gu->g, N, 2 * I, H, s));
     TRY(iadr1_rmsnorm_bwd(L.dx, b.h_mid, w.ln2->p, b.r2, dh, w.ln2->g, N, H, H, 1, s));

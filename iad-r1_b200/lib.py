@@ -217,6 +217,24 @@ def gemm_swiglu_train(x: torch.Tensor, w_gate_up: torch.Tensor, act: torch.Tenso
     return act
 
 
+def gemm_swiglu_bwd(dy: torch.Tensor, w_down: torch.Tensor, gu: torch.Tensor) -> torch.Tensor:
+    """Down-projection input gradient with the SwiGLU backward in its epilogue (epi 5): for dact = dy[M, H] @ w_down[H, I] (never
+    written), gu[M, 2I] = gate | up is overwritten in place with dgate | dup - bit-identical to gemm + act_mul_bwd."""
+    M, H = dy.shape
+    H2, I = w_down.shape
+    if H != H2 or gu.shape[0] != M or gu.shape[1] != 2 * I or gu.dtype != torch.bfloat16:
+        raise ValueError("gemm_swiglu_bwd: shape/dtype mismatch")
+    d = GemmDesc()
+    d.M, d.N, d.K = M, I, H
+    d.batch = d.batch_lo = d.b_lo_div = 1
+    d.A, d.lda, d.a_mn = _mat(dy, "dy")
+    d.B, d.ldb, d.b_mn = _mat(w_down.t(), "w_down")
+    d.split_k, d.alpha, d.epi = 1, 1.0, 5
+    d.gu_out, d.gu_ld = gu.data_ptr(), gu.stride(0)
+    check(lib().iadr1_gemm_bf16(C.byref(d), stream_ptr()), "iadr1_gemm_bf16(swiglu backward)")
+    return gu
+
+
 def gemm_batched(a, b, out, *, M, N, K, batch, batch_lo=0, b_lo_div=1, lda, a_bs_lo=0, a_bs_hi=0, a_mn=0, ldb,
                  b_bs_lo=0, b_bs_hi=0, b_mn=0, ldc, c_bs_lo=0, c_bs_hi=0, alpha=1.0, kmode=0, skip_mode=0,
                  causal_off=0, block_n=0, a_off=0, b_off=0, c_off=0, residual=None):

@@ -48,7 +48,9 @@ typedef struct iadr1_gemm_t {
   const void* residual;              /* bf16, indexed like C */
   int kmode, skip_mode, causal_off;  /* causal trimming for attention products, see gemm_sm100.cuh */
   int epi;                           /* 0 store, 1 row log-sum-exp partials, 2 softmax-gradient (lm_head backward), 3 SwiGLU (decode),
-                                        4 SwiGLU (training: N = I features, B = fused gate|up weight [2I][K], C = act bf16 [M][I]) */
+                                        4 SwiGLU (training: N = I features, B = fused gate|up weight [2I][K], C = act bf16 [M][I]),
+                                        5 SwiGLU backward (A = dy [M][K = H], B = down weight (MN-major [H][I]), N = I: the product
+                                          dact never leaves the SM - gu_out [M][2I] (gate | up) is rewritten with dgate | dup; C unused) */
   const int* labels; float* part_max; float* part_sum; float* tgt_logit; int lse_tiles_n;
   const float* lse; const float* gscale;
   int block_n, stages, max_ctas;     /* 0 = library heuristics */
@@ -60,7 +62,8 @@ typedef struct iadr1_gemm_t {
   int no_chunked_maps;               /* probes: MN-major operands as 64-column 2-D boxes (several TMA instructions per k-block) */
   int no_bulk_red;                   /* probes: force per-lane atomics instead of bulk reductions for transposed fp32 atomic C */
   int co_resident;                   /* decode chain: <= 113 KB smem, <= 128 regs, minimal TMEM so two CTAs fit per SM */
-  void* gu_out; long long gu_ld;     /* epi 4: optional bf16 [M][2I] gate | up pre-activations kept for the backward */
+  void* gu_out; long long gu_ld;     /* epi 4: optional bf16 [M][2I] gate | up pre-activations kept for the backward;
+                                        epi 5: the same buffer, read and overwritten in place with dgate | dup */
 } iadr1_gemm_t;
 int iadr1_gemm_bf16(const iadr1_gemm_t* desc, void* stream);
 /* block_n the library would choose for an N-wide product (sizes the EPI_LSE partial buffers). */

@@ -654,3 +654,23 @@ def test_gemm_swiglu_training_epilogue(ops, M, I, K, keep):
     assert torch.equal(act, act_ref)
     if keep:
         assert torch.equal(gu, gu_ref)
+
+
+@pytest.mark.parametrize("M,I,H", [(300, 384, 256), (1111, 3424, 1280), (1000, 11008, 2048), (64, 520, 128)])
+def test_gemm_swiglu_backward_epilogue(ops, M, I, H):
+    """epi 5: the down-projection input gradient with the SwiGLU backward in the epilogue rewrites gate | up with dgate | dup
+    bit-identically to GEMM (bf16 dact) -> act_mul_bwd (what it replaces in iadr1_decoder_bwd), and matches fp32 autograd."""
+    from iad_r1_b200 import lib as L
+    torch.manual_seed(M + I)
+    dy, w_down, gu = rnd(M, H, scale=0.5), rnd(H, I, scale=0.05), rnd(M, 2 * I)
+    want = gu.clone()
+    dact = L.gemm(dy, w_down.t())                                   # dy @ w_down, bf16
+    ops.act_mul_bwd(dact, want, I, 0, True, dgu=want)
+    got = gu.clone()
+    L.gemm_swiglu_bwd(dy, w_down, got)
+    assert torch.equal(got, want), f"max diff {(got.float() - want.float()).abs().max().item():.4g}"
+    g32 = gu[:, :I].float().requires_grad_()
+    u32 = gu[:, I:].float().requires_grad_()
+    (torch.nn.functional.silu(g32) * u32).backward(dy.float() @ w_down.float())
+    close(got[:, :I], g32.grad, 2 ** -6, "dgate")
+    close(got[:, I:], u32.grad, 2 ** -6, "dup")

@@ -48,5 +48,50 @@ def main():
               f"({fl / res[0] / 1e6:6.0f} TFLOP/s)   {res[256] / res[0]:.2f}x", flush=True)
 
 
+def graph_time(fn, n=3, iters=10):
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for i in range(n):
+            fn(i)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            for i in range(n):
+                fn(i)
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+    return 1000 * e0.elapsed_time(e1) / (iters * n)
+
+
+def swiglu_bwd():
+    """Down-projection input gradient + SwiGLU backward: GEMM -> act_mul_bwd against the fused epilogue (epi 5)."""
+    from iad_r1_b200 import lib as L, ops
+    dev = torch.device("cuda:0")
+    for name, M, I, H in [("3B", 8786, 11008, 2048), ("7B", 8786, 18944, 3584)]:
+        dy = [torch.randn(M, H, device=dev).bfloat16() for _ in range(3)]
+        w = (torch.randn(H, I, device=dev) * 0.02).bfloat16()
+        gu = [torch.randn(M, 2 * I, device=dev).bfloat16() for _ in range(3)]
+        dact = torch.empty(M, I, device=dev, dtype=torch.bfloat16)
+
+        def unfused(i):
+            L.gemm(dy[i], w.t(), out=dact)
+            ops.act_mul_bwd(dact, gu[i], I, 0, True, dgu=gu[i])
+        t_gemm = graph_time(lambda i: L.gemm(dy[i], w.t(), out=dact))
+        t_un = graph_time(unfused)
+        t_f = graph_time(lambda i: L.gemm_swiglu_bwd(dy[i], w, gu[i]))
+        print(f"swiglu backward {name} [M={M}, I={I}, H={H}]: GEMM alone {t_gemm:7.1f} us, GEMM + act_mul_bwd {t_un:7.1f} us, fused epilogue "
+              f"{t_f:7.1f} us ({t_un / t_f:.2f}x)", flush=True)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "swiglu_bwd":
+        swiglu_bwd()
+    else:
+        main()
