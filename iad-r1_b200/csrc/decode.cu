@@ -1692,7 +1692,7 @@ __global__ void decode_silu_mul_f32_kernel(float* __restrict__ gu, bf16* __restr
     *up = make_float4(0.f, 0.f, 0.f, 0.f);
     auto f = [](float gg, float uu) {
       gg = bf16r(gg);
-      return bf16r(gg / (1.f + __expf(-gg))) * bf16r(uu);
+      return bf16r(silu_f(gg)) * bf16r(uu);
     };
     __nv_bfloat162 o0 = __floats2bfloat162_rn(f(g.x, u.x), f(g.y, u.y));
     __nv_bfloat162 o1 = __floats2bfloat162_rn(f(g.z, u.z), f(g.w, u.w));

@@ -381,7 +381,7 @@ decode_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                   const float g = bf16r(__uint_as_float(gv[2 * j + e]));
-                  const float sv = bf16r(g / (1.f + __expf(-g)));
+                  const float sv = bf16r(silu_f(g));
                   r2[e] = sv * bf16r(__uint_as_float(uv[2 * j + e]));
                 }
                 const __nv_bfloat162 pk = __floats2bfloat162_rn(r2[0], r2[1]);

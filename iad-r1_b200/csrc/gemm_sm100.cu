@@ -328,7 +328,7 @@ __device__ __forceinline__ void epilogue_lean32(const GemmArgs& g, const uint32_
 template <int kMinCtas>
 __global__ void __launch_bounds__(kThreads, kMinCtas)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const GemmArgs g) {
+                         const __grid_constant__ CUtensorMap tmC, const GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by pointer arithmetic on the __shared__ array (keeps the shared address space). Launches that need
   // every byte (g.smem_tight: two co-resident CTAs with a 3-stage ring) request no slack and rely on the window base being
@@ -358,6 +358,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (g.tma_store) tma_prefetch_desc(&tmC);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < g.stages; ++i) {
@@ -501,12 +502,28 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                         ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) &&
                         (g.residual == nullptr || (reinterpret_cast<uintptr_t>(g.residual) & 15) == 0);
     int as = 0;
+    int tbuf = 0;
     uint32_t aph = 0;
     TileInfo ti;
     WorkIter it(g, total_tiles, tiles_m * tiles_n);
     while (it.next(g, tiles_m, tiles_n, ti)) {
       if (ti.skip) continue;
       const bool have_acc = ti.kb_end > ti.kb_begin;
+      if (kMinCtas == 1 && g.epi == EPI_SWIGLU_BWD) {
+        // Ask L2 for this thread's WHOLE row segment of gate and of up (<= 512 contiguous bytes each) before waiting for the
+        // accumulator: the epilogue's own reads are 64-byte pieces of 128 different rows per chunk, and issued one chunk at
+        // a time every piece opens a DRAM page of its own (774 MB in 64-byte reads: the fused kernel took 500 us against 320 us
+        // for the bare product, whatever the lookahead or the arithmetic cost). One bulk prefetch per row segment turns that
+        // into eight times fewer, eight times longer DRAM bursts, and the loads below hit L2.
+        const int mp = ti.m0 + q * 32 + lane;
+        const int ncol = min(g.block_n, g.N - ti.n0);
+        if (mp < g.M && ncol > 0) {
+          const __nv_bfloat16* prow = g.gu_out + (long long)mp * g.gu_ld + ti.n0;
+          const uint32_t nbytes = (uint32_t)ncol * 2u;              // multiple of 16: I % 8 == 0
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(prow), "r"(nbytes) : "memory");
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(prow + g.N), "r"(nbytes) : "memory");
+        }
+      }
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
       const int m = ti.m0 + q * 32 + lane;
@@ -550,7 +567,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             const float2 uu = *reinterpret_cast<const float2*>(sC + n * BM + 64 + f);
             auto act = [](float gv, float uv) {
               gv = __bfloat162float(__float2bfloat16(gv));
-              const float sv = __bfloat162float(__float2bfloat16(gv / (1.f + __expf(-gv))));
+              const float sv = __bfloat162float(__float2bfloat16(silu_f(gv)));
               return sv * __bfloat162float(__float2bfloat16(uv));
             };
             if (f0 + f < (g.M >> 1))
@@ -579,8 +596,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
               const __nv_bfloat162 gb = __floats2bfloat162_rn(have_acc ? __uint_as_float(gv[j]) : 0.f, have_acc ? __uint_as_float(gv[j + 1]) : 0.f);
               const __nv_bfloat162 ub = __floats2bfloat162_rn(have_acc ? __uint_as_float(uv[j]) : 0.f, have_acc ? __uint_as_float(uv[j + 1]) : 0.f);
               const float2 gf = __bfloat1622float2(gb), uf = __bfloat1622float2(ub);
-              const float s0 = __bfloat162float(__float2bfloat16(gf.x / (1.f + __expf(-gf.x))));
-              const float s1 = __bfloat162float(__float2bfloat16(gf.y / (1.f + __expf(-gf.y))));
+              const float s0 = __bfloat162float(__float2bfloat16(silu_f(gf.x)));
+              const float s1 = __bfloat162float(__float2bfloat16(silu_f(gf.y)));
               const __nv_bfloat162 ab = __floats2bfloat162_rn(s0 * uf.x, s1 * uf.y);
               reinterpret_cast<__nv_bfloat162*>(og)[j >> 1] = gb;
               reinterpret_cast<__nv_bfloat162*>(ou)[j >> 1] = ub;
@@ -631,20 +648,35 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           const uint4 (&cg)[4] = bg[ci % 3];
           const uint4 (&cu)[4] = bu[ci % 3];
           uint4 og[4], ou[4];
+          // Staged over 16 elements at a time so that the SFU ops (ex2, rcp) of different elements are independent and
+          // adjacent in program order: the four epilogue warps run one per scheduler, in order - written element by element
+          // the dependent chain cvt -> ex2 -> add -> rcp -> mul ran at 0.13 instructions per cycle (ncu) and the epilogue took
+          // 23 us per tile against 15 us of MMA.
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            const float2 dd = __bfloat1622float2(__floats2bfloat162_rn(have_acc ? g.alpha * __uint_as_float(v[j]) : 0.f,
-                                                                       have_acc ? g.alpha * __uint_as_float(v[j + 1]) : 0.f));
-            const float2 gf = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(cg)[j >> 1]);
-            const float2 uf = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(cu)[j >> 1]);
-            const float t0 = 1.f + __expf(-gf.x), t1 = 1.f + __expf(-gf.y);
-            const float s0 = 1.f / t0, s1 = 1.f / t1;
-            const float dg0 = dd.x * uf.x * (s0 * (1.f + gf.x * (1.f - s0)));
-            const float dg1 = dd.y * uf.y * (s1 * (1.f + gf.y * (1.f - s1)));
-            const float du0 = dd.x * (gf.x / t0);
-            const float du1 = dd.y * (gf.y / t1);
-            reinterpret_cast<__nv_bfloat162*>(og)[j >> 1] = __floats2bfloat162_rn(dg0, dg1);
-            reinterpret_cast<__nv_bfloat162*>(ou)[j >> 1] = __floats2bfloat162_rn(du0, du1);
+          for (int h16 = 0; h16 < 2; ++h16) {
+            float gf[16], uf[16], dd[16], sg[16];
+#pragma unroll
+            for (int k = 0; k < 16; k += 2) {
+              const int j = h16 * 16 + k;
+              const float2 g2 = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(cg)[j >> 1]);
+              const float2 u2 = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(cu)[j >> 1]);
+              const float2 d2 = __bfloat1622float2(__floats2bfloat162_rn(have_acc ? g.alpha * __uint_as_float(v[j]) : 0.f,
+                                                                         have_acc ? g.alpha * __uint_as_float(v[j + 1]) : 0.f));
+              gf[k] = g2.x; gf[k + 1] = g2.y; uf[k] = u2.x; uf[k + 1] = u2.y; dd[k] = d2.x; dd[k + 1] = d2.y;
+            }
+#pragma unroll
+            for (int k = 0; k < 16; ++k) sg[k] = __expf(-gf[k]);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) sg[k] = rcp_approx_f(__fadd_rn(1.f, sg[k]));      // sigmoid, as sigmoid_f()
+#pragma unroll
+            for (int k = 0; k < 16; k += 2) {
+              const int j = h16 * 16 + k;
+              float dg0, dg1, du0, du1;
+              swiglu_bwd_s(dd[k], gf[k], uf[k], sg[k], dg0, du0);
+              swiglu_bwd_s(dd[k + 1], gf[k + 1], uf[k + 1], sg[k + 1], dg1, du1);
+              reinterpret_cast<__nv_bfloat162*>(og)[j >> 1] = __floats2bfloat162_rn(dg0, dg1);
+              reinterpret_cast<__nv_bfloat162*>(ou)[j >> 1] = __floats2bfloat162_rn(du0, du1);
+            }
           }
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
@@ -654,6 +686,78 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             }
           }
         }
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[as]);
+        if (++as == 2) { as = 0; aph ^= 1; }
+        continue;
+      }
+      if (kMinCtas == 1 && g.tma_store) {
+        // Plain store / fp32 accumulate through the TMA unit. Each thread owns accumulator row r; written straight to global
+        // memory that is 32 different cache lines per store instruction, and those wavefronts share the L1 / shared-memory
+        // pipe with the TMA loads feeding the MMA (measured: the K = 2048 products ran 16-19 % faster with the stores
+        // removed). So the row's 128 bytes of a chunk (64 bf16 / 32 fp32 columns) go into a 128B-swizzled staging box
+        // (conflict-free 16-byte shared stores) and ONE thread hands the [128 rows x 128 B] box to the TMA unit, which
+        // clips the M / N tails and - for the weight gradients - adds into C at L2 (no read-modify-write by the SM).
+        uint8_t* sT = smem + (size_t)g.stages * stage_bytes + 1024;
+        const int r = q * 32 + lane;
+        const int cw = g.c_f32 ? 32 : 64;
+        const bool issuer = threadIdx.x == 128;
+        const __nv_bfloat16* bias_n = (g.bias != nullptr && ti.split == 0) ? g.bias + ti.n0 : nullptr;
+        int buf = tbuf;      // the two staging boxes alternate ACROSS tiles too (a tile may have an odd number of chunks)
+        for (int c0 = 0; c0 < g.block_n && ti.n0 + c0 < g.N; c0 += cw) {
+          uint32_t v[32], v2[32];
+          tmem_ld_32x32b_x32(taddr + c0, v);
+          if (!g.c_f32) tmem_ld_32x32b_x32(taddr + c0 + 32, v2);
+          if (issuer) bulk_wait_read1();                 // the store that last read this buffer (two chunks ago) is done with it
+          named_bar_sync(1, 128);
+          tmem_ld_wait();
+          uint8_t* row = sT + buf * 16384 + r * 128;
+          if (g.c_f32) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              float4 o;
+              o.x = have_acc ? g.alpha * __uint_as_float(v[4 * k]) : 0.f;
+              o.y = have_acc ? g.alpha * __uint_as_float(v[4 * k + 1]) : 0.f;
+              o.z = have_acc ? g.alpha * __uint_as_float(v[4 * k + 2]) : 0.f;
+              o.w = have_acc ? g.alpha * __uint_as_float(v[4 * k + 3]) : 0.f;
+              *reinterpret_cast<float4*>(row + ((k ^ (r & 7)) << 4)) = o;
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              float a8[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const uint32_t raw = k < 4 ? v[8 * k + e] : v2[8 * (k - 4) + e];
+                a8[e] = have_acc ? g.alpha * __uint_as_float(raw) : 0.f;
+              }
+              if (bias_n != nullptr && ti.n0 + c0 + 8 * k < g.N) {
+                const uint4 b = *reinterpret_cast<const uint4*>(bias_n + c0 + 8 * k);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __bfloat1622float2(h[e]);
+                  a8[2 * e] += f.x;
+                  a8[2 * e + 1] += f.y;
+                }
+              }
+              uint4 o;
+              __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) oh[e] = __floats2bfloat162_rn(a8[2 * e], a8[2 * e + 1]);
+              *reinterpret_cast<uint4*>(row + ((k ^ (r & 7)) << 4)) = o;
+            }
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (issuer) {
+            if (g.tma_store == 2) tma_reduce_add_2d(&tmC, sT + buf * 16384, ti.n0 + c0, ti.m0);
+            else tma_store_2d(&tmC, sT + buf * 16384, ti.n0 + c0, ti.m0);
+            bulk_commit();
+          }
+          buf ^= 1;
+        }
+        tbuf = buf;
         tc_fence_before();
         mbar_arrive(&tempty_bar[as]);
         if (++as == 2) { as = 0; aph ^= 1; }
@@ -734,7 +838,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
   }
 
-  if (g.bulk_red && warp >= 4) bulk_wait0();   // this thread's bulk reductions have been performed
+  if ((g.bulk_red || g.tma_store) && warp >= 4) bulk_wait0();   // this thread's bulk reductions / tile stores have been performed
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -809,6 +913,37 @@ static int make_map(CUtensorMap* out, const void* ptr, long long d0, long long d
 }
 
 // K-major 2-D operand [rows][cols] (row stride ld elements) with a {box_cols, box_rows} box, 128-byte swizzle (decode chain).
+// Output map for the TMA-store epilogue: C[rows][cols] (bf16 or f32, row stride ld elements), box = 128 rows x 128 bytes,
+// 128B swizzle (the staging box the epilogue warps fill).
+static int make_map_c(CUtensorMap* out, const void* ptr, long long cols, long long rows, long long ld, int f32) {
+  static std::map<MapKey, CUtensorMap> cache;
+  static std::mutex mu;
+  MapKey key{ptr, cols, rows, ld, f32, 0, 0, 0, 0, -7};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return 0;
+    }
+  }
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error("cuTensorMapEncodeTiled entry point not found (no CUDA driver?)");
+  const int esz = f32 ? 4 : 2;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims,
+                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled(C) failed (%d) cols=%lld rows=%lld ld=%lld", (int)r, cols, rows, ld);
+  std::lock_guard<std::mutex> lk(mu);
+  if (cache.size() > 8192) cache.clear();
+  cache[key] = *out;
+  return 0;
+}
+
 int make_tensor_map_2d(CUtensorMap* out, const void* ptr, long long cols, long long rows, long long ld, int box_cols, int box_rows) {
   return make_map(out, ptr, cols, rows, 1, 1, ld, ld, ld, box_cols, box_rows);
 }
@@ -1095,7 +1230,17 @@ int launch_gemm(const iadr1_gemm_t& d, cudaStream_t stream) {
   // transposed fp32 atomic accumulation goes through bulk reductions (needs a [block_n][128] fp32 staging tile)
   g.bulk_red = g.trans_c && g.atomic && g.c_f32 && g.epi == EPI_STORE && g.residual == nullptr && g.batch == 1 &&
                (g.M % 4 == 0) && (g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) && !d.no_bulk_red;
-  const int epi_bytes = g.epi == EPI_SWIGLU ? g.swiglu_rows * BM * 4 : (g.bulk_red ? g.block_n * BM * 4 : 0);
+  // Plain stores and fp32 accumulation of the training products go through a tensor map of C (see the epilogue): needs a plain
+  // row-major single problem, 16-byte aligned rows, tiles that split into whole 128-byte chunks, and no residual operand
+  // (that one is still read row by row). IADR1_GEMM_TMA_STORE=0 restores the per-thread stores.
+  static const bool tma_store_on = [] { const char* e = getenv("IADR1_GEMM_TMA_STORE"); return !(e && e[0] == '0'); }();
+  g.tma_store = 0;
+  if (tma_store_on && !co_resident && g.epi == EPI_STORE && !g.trans_c && !g.atomic && g.batch == 1 && g.split_k == 1 &&
+      !g.stream_k && g.residual == nullptr && !g.bias_per_m && (g.bias == nullptr || (!g.c_f32 && (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0)) &&
+      (reinterpret_cast<uintptr_t>(g.C) & 15) == 0 && ((g.ldc * (g.c_f32 ? 4 : 2)) % 16) == 0 && (g.block_n % (g.c_f32 ? 32 : 64)) == 0 &&
+      (g.c_f32 || (d.N % 8) == 0) && d.M >= BM && d.N >= (g.c_f32 ? 32 : 64) && (g.c_f32 || !g.accumulate))
+    g.tma_store = (g.c_f32 && g.accumulate) ? 2 : 1;
+  const int epi_bytes = g.epi == EPI_SWIGLU ? g.swiglu_rows * BM * 4 : (g.bulk_red ? g.block_n * BM * 4 : (g.tma_store ? 512 + 2 * 16384 : 0));
   const int smem_slack = g.smem_tight ? 0 : 1024;
   const int smem_budget = (co_resident ? 113 : 227) * 1024 - smem_slack - 512 - epi_bytes;
   int stages = smem_budget / stage_bytes;
@@ -1135,6 +1280,11 @@ int launch_gemm(const iadr1_gemm_t& d, cudaStream_t stream) {
     rc = make_map(&tmB, d.B, d.N, d.K, nb_lo_b, nb_hi, d.ldb, d.b_bs_lo ? d.b_bs_lo : d.ldb,
                   d.b_bs_hi ? d.b_bs_hi : d.ldb, 64, BK);
   if (rc) return rc;
+  CUtensorMap tmC = tmA;          // placeholder unless the epilogue stores through it
+  if (g.tma_store) {
+    rc = make_map_c(&tmC, d.C, d.N, d.M, d.ldc, g.c_f32);
+    if (rc) return rc;
+  }
 
   static bool attr_set = false;
   if (!attr_set) {
@@ -1155,9 +1305,9 @@ int launch_gemm(const iadr1_gemm_t& d, cudaStream_t stream) {
   cudaEvent_t pe0, pe1;
   const bool timed = prof_begin(stream, &pe0, &pe1);
   if (co_resident)
-    launch_kernel(gemm_bf16_tcgen05_kernel<2>, dim3(grid), dim3(kThreads), smem_bytes, stream, tmA, tmB, g);
+    launch_kernel(gemm_bf16_tcgen05_kernel<2>, dim3(grid), dim3(kThreads), smem_bytes, stream, tmA, tmB, tmC, g);
   else
-    launch_kernel(gemm_bf16_tcgen05_kernel<1>, dim3(grid), dim3(kThreads), smem_bytes, stream, tmA, tmB, g);
+    launch_kernel(gemm_bf16_tcgen05_kernel<1>, dim3(grid), dim3(kThreads), smem_bytes, stream, tmA, tmB, tmC, g);
   if (timed) {
     cudaEventRecord(pe1, stream);
     // algorithmic FLOPs: causal products count only the unmasked half

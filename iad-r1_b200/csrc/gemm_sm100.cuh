@@ -55,6 +55,7 @@ struct GemmArgs {
   __nv_bfloat16* gu_out; // EPI_SWIGLU_T: bf16 [M][2I] gate | up pre-activations kept for the backward (or nullptr);
                          // EPI_SWIGLU_BWD: the same buffer, read and overwritten with dgate | dup
   long long gu_ld;
+  int tma_store;         // EPI_STORE through a tensor map of C: 1 = tile store (bf16 / f32), 2 = f32 reduce-add (accumulate)
 };
 
 }  // namespace iadr1

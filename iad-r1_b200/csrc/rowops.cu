@@ -407,7 +407,7 @@ __global__ void rope_vec8_kernel(bf16* __restrict__ x, const float* __restrict__
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float act_fwd(int act, float g) {
   switch (act) {
-    case 0: return g / (1.f + __expf(-g));
+    case 0: return silu_f(g);
     case 1: return 0.5f * g * (1.f + erff(g * 0.70710678118654752f));
     case 2: return g / (1.f + __expf(-1.702f * g));
     default: {
@@ -418,10 +418,7 @@ __device__ __forceinline__ float act_fwd(int act, float g) {
 }
 __device__ __forceinline__ float act_grad(int act, float g) {
   switch (act) {
-    case 0: {
-      const float s = 1.f / (1.f + __expf(-g));
-      return s * (1.f + g * (1.f - s));
-    }
+    case 0: return silu_grad_f(g);
     case 1: return 0.5f * (1.f + erff(g * 0.70710678118654752f)) + g * 0.3989422804014327f * __expf(-0.5f * g * g);
     case 2: {
       const float s = 1.f / (1.f + __expf(-1.702f * g));
@@ -472,7 +469,9 @@ __global__ void act_mul_bwd_kernel(const bf16* __restrict__ dout, const bf16* gu
     unpack8(*reinterpret_cast<const bf16x8*>(dout + r * dout_ld + v * 8), d);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      if (up_off >= 0) {
+      if (up_off >= 0 && act == 0) {
+        swiglu_bwd_f(d[j], g[j], u[j], dg[j], du[j]);
+      } else if (up_off >= 0) {
         dg[j] = d[j] * u[j] * act_grad(act, g[j]);
         du[j] = d[j] * act_fwd(act, g[j]);
       } else {

@@ -97,6 +97,30 @@ __device__ __forceinline__ void trace_value(unsigned long long tag, unsigned lon
   }
 }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// Sigmoid / SiLU and its derivative with the SFU reciprocal (rcp.approx: <= 1 ulp, ~4 fp32 ulp for the whole expression -
+// far below the bf16 rounding that follows every use). ONE definition, explicit roundings (no FMA contraction choices left to the
+// compiler), used by the row kernels, the GEMM epilogues (epi 3 / 4 / 5), the decode chain and the decode fallback, so the
+// fused and unfused forms of the same op stay bit-identical. An IEEE division here costs ~15 issue slots per element, which is
+// what made the four epilogue warps of the fused SwiGLU GEMMs slower than the tile's MMA.
+__device__ __forceinline__ float rcp_approx_f(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float sigmoid_f(float g) { return rcp_approx_f(__fadd_rn(1.f, __expf(-g))); }
+__device__ __forceinline__ float silu_f(float g) { return __fmul_rn(g, sigmoid_f(g)); }
+// d silu(g) / dg = s (1 + g (1 - s)), s = sigmoid(g)
+__device__ __forceinline__ float silu_grad_s(float g, float s) { return __fmul_rn(s, __fmaf_rn(g, __fsub_rn(1.f, s), 1.f)); }
+__device__ __forceinline__ float silu_grad_f(float g) { return silu_grad_s(g, sigmoid_f(g)); }
+// SwiGLU backward for one element: dgate = d u silu'(g), dup = d silu(g); _s takes s = sigmoid_f(g) computed by the caller
+__device__ __forceinline__ void swiglu_bwd_s(float d, float g, float u, float s, float& dg, float& du) {
+  dg = __fmul_rn(__fmul_rn(d, u), silu_grad_s(g, s));
+  du = __fmul_rn(d, __fmul_rn(g, s));
+}
+__device__ __forceinline__ void swiglu_bwd_f(float d, float g, float u, float& dg, float& du) {
+  swiglu_bwd_s(d, g, u, sigmoid_f(g), dg, du);
+}
 }  // namespace iadr1
 #endif
 
