@@ -1164,8 +1164,21 @@ int launch_gemm(const iadr1_gemm_t& d, cudaStream_t stream) {
     g.gu_out = reinterpret_cast<__nv_bfloat16*>(d.gu_out);
     g.gu_ld = d.gu_ld;
   }
-  g.stream_k = d.stream_k;
-  if (g.stream_k && !(g.atomic && g.c_f32 && g.batch == 1 && g.kmode == 0 && g.skip_mode == 0 && g.split_k == 1 &&
+  // Weight-gradient form (fp32 accumulate into C, one problem): when whole 256-column tiles leave the last wave mostly idle
+  // (2560 x 2048: 160 tiles on 148 SMs; the vision tower's 1280 x 1280: 50 tiles), cut the k-block units evenly over the SMs
+  // instead (stream-K). The partial tiles are ADDED into C by the TMA unit (reduce-add epilogue below), so the SM issues no
+  // atomics; the order of the two or three partial sums of a tile depends on which CTA gets there first.
+  static const bool auto_sk_on = [] { const char* e = getenv("IADR1_GEMM_WGRAD_STREAMK"); return !(e && e[0] == '0'); }();
+  bool auto_sk = false;
+  if (auto_sk_on && !d.stream_k && g.epi == EPI_STORE && g.c_f32 && g.accumulate && !g.atomic && !g.trans_c && g.batch == 1 &&
+      g.split_k == 1 && g.kmode == 0 && !g.skip_mode && d.block_n <= 0 && !d.co_resident && !d.bias && !d.residual) {
+    const int bn = pick_block_n(d.N, d.b_mn);
+    const long long tiles = (long long)((d.M + BM - 1) / BM) * ((d.N + bn - 1) / bn), sms = num_sms();
+    const long long waves = (tiles + sms - 1) / sms, nkb = (d.K + BK - 1) / BK;
+    auto_sk = tiles * 10 < waves * sms * 8 && tiles * nkb >= sms * 8;
+  }
+  g.stream_k = d.stream_k || auto_sk;
+  if (g.stream_k && !((g.atomic || auto_sk) && g.c_f32 && g.batch == 1 && g.kmode == 0 && g.skip_mode == 0 && g.split_k == 1 &&
                       g.epi == EPI_STORE))
     return set_error("gemm: stream_k needs a single full-K problem with atomic f32 output and split_k == 1");
   if (g.split_k > 1 && !(g.atomic && g.c_f32)) return set_error("gemm: split_k > 1 needs atomic f32 output");
@@ -1175,7 +1188,7 @@ int launch_gemm(const iadr1_gemm_t& d, cudaStream_t stream) {
   if (g.epi == EPI_SWIGLU_T) g.block_n = 256;
   if (g.epi == EPI_SWIGLU_BWD) g.block_n = 256;   // the epilogue is unrolled over eight 32-column chunks
   static const bool wave_tiles = [] { const char* e = getenv("IADR1_GEMM_WAVE_TILES"); return !(e && e[0] == '0'); }();
-  if (wave_tiles && d.block_n <= 0 && g.b_mn && g.epi == EPI_STORE && g.batch == 1 && g.split_k == 1 && !d.stream_k &&
+  if (wave_tiles && d.block_n <= 0 && g.b_mn && g.epi == EPI_STORE && g.batch == 1 && g.split_k == 1 && !g.stream_k &&
       g.kmode == 0 && !g.skip_mode && d.N > 256) {
     // Wave quantisation of the gradient products: the persistent CTAs take tiles round-robin, so a product costs
     // ceil(tiles / SMs) tile times. Narrower tiles are NOT proportionally cheaper (A is re-staged per tile and the L2 -> SM
@@ -1236,10 +1249,11 @@ int launch_gemm(const iadr1_gemm_t& d, cudaStream_t stream) {
   static const bool tma_store_on = [] { const char* e = getenv("IADR1_GEMM_TMA_STORE"); return !(e && e[0] == '0'); }();
   g.tma_store = 0;
   if (tma_store_on && !co_resident && g.epi == EPI_STORE && !g.trans_c && !g.atomic && g.batch == 1 && g.split_k == 1 &&
-      !g.stream_k && g.residual == nullptr && !g.bias_per_m && (g.bias == nullptr || (!g.c_f32 && (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0)) &&
+      (!g.stream_k || auto_sk) && g.residual == nullptr && !g.bias_per_m && (g.bias == nullptr || (!g.c_f32 && (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0)) &&
       (reinterpret_cast<uintptr_t>(g.C) & 15) == 0 && ((g.ldc * (g.c_f32 ? 4 : 2)) % 16) == 0 && (g.block_n % (g.c_f32 ? 32 : 64)) == 0 &&
       (g.c_f32 || (d.N % 8) == 0) && d.M >= BM && d.N >= (g.c_f32 ? 32 : 64) && (g.c_f32 || !g.accumulate))
     g.tma_store = (g.c_f32 && g.accumulate) ? 2 : 1;
+  if (auto_sk && g.tma_store != 2) g.stream_k = 0;   // no reduce-add epilogue available: whole tiles, read-modify-write
   const int epi_bytes = g.epi == EPI_SWIGLU ? g.swiglu_rows * BM * 4 : (g.bulk_red ? g.block_n * BM * 4 : (g.tma_store ? 512 + 2 * 16384 : 0));
   const int smem_slack = g.smem_tight ? 0 : 1024;
   const int smem_budget = (co_resident ? 113 : 227) * 1024 - smem_slack - 512 - epi_bytes;

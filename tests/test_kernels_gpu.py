@@ -81,7 +81,9 @@ def test_gemm_weight_gradient_wave_quantised_tiles(ops, N_out, K_in, T):
     close(got, want, 2 ** -9, "wgrad")
     ref = base.clone()
     L.gemm(dy.t(), x.t(), out=ref, accumulate=True, out_dtype=f32, block_n=256)
-    assert torch.equal(got, ref), "tile width changed the accumulated values"
+    # stream-K shapes accumulate a tile's K range in two or three fp32 partial sums added in arrival order: equal up to the
+    # fp32 rounding of ~K products (measured 2e-4 on values up to 180), far inside the bf16-product tolerance above
+    close(got, ref, 2 ** -17, "tile width / stream-K changed the accumulated values")
 
 
 @pytest.mark.parametrize("F,K,R", [(22016, 2048, 64), (2560, 2048, 64), (2048, 11008, 16), (1000, 200, 8), (128, 64, 24)])
