@@ -1168,14 +1168,15 @@ int launch_gemm(const iadr1_gemm_t& d, cudaStream_t stream) {
   // (2560 x 2048: 160 tiles on 148 SMs; the vision tower's 1280 x 1280: 50 tiles), cut the k-block units evenly over the SMs
   // instead (stream-K). The partial tiles are ADDED into C by the TMA unit (reduce-add epilogue below), so the SM issues no
   // atomics; the order of the two or three partial sums of a tile depends on which CTA gets there first.
-  static const bool auto_sk_on = [] { const char* e = getenv("IADR1_GEMM_WGRAD_STREAMK"); return !(e && e[0] == '0'); }();
+  static const int auto_sk_on = [] { const char* e = getenv("IADR1_GEMM_WGRAD_STREAMK"); return e && e[0] >= '0' && e[0] <= '9' ? e[0] - '0' : 1; }();
   bool auto_sk = false;
   if (auto_sk_on && !d.stream_k && g.epi == EPI_STORE && g.c_f32 && g.accumulate && !g.atomic && !g.trans_c && g.batch == 1 &&
       g.split_k == 1 && g.kmode == 0 && !g.skip_mode && d.block_n <= 0 && !d.co_resident && !d.bias && !d.residual) {
     const int bn = pick_block_n(d.N, d.b_mn);
     const long long tiles = (long long)((d.M + BM - 1) / BM) * ((d.N + bn - 1) / bn), sms = num_sms();
     const long long waves = (tiles + sms - 1) / sms, nkb = (d.K + BK - 1) / BK;
-    auto_sk = tiles * 10 < waves * sms * 8 && tiles * nkb >= sms * 8;
+    const long long pct = auto_sk_on == 1 ? 80 : (auto_sk_on == 2 ? 101 : 10 * auto_sk_on + 60);   // probes: 3..9 -> 90..150 %
+    auto_sk = tiles * 100 < waves * sms * pct && tiles * nkb >= sms * 8;
   }
   g.stream_k = d.stream_k || auto_sk;
   if (g.stream_k && !((g.atomic || auto_sk) && g.c_f32 && g.batch == 1 && g.kmode == 0 && g.skip_mode == 0 && g.split_k == 1 &&
